@@ -1,0 +1,191 @@
+/* mgconv.h -- C ABI of the B200-native multigrid-convolution hot path.
+ *
+ * Drop-in boundary for buttomnutstoast/Multigrid-Neural-Architectures: every entry point
+ * below replaces a chain of upstream Torch7 nn/cunn/cudnn module calls that the
+ * reference's model builders assemble (the reference has no FFI of its own for this
+ * path -- it is 100 % Lua on top of un-vendored luarocks packages -- so the "reference
+ * interface" cited per function is the Lua builder code whose GPU work the call subsumes).
+ *
+ * Plain C, handle based, no C++ types or exceptions cross the boundary.  The header is
+ * consumed verbatim by LuaJIT `ffi.cdef` (lua/mgconv_ffi.lua) and by Python ctypes/cffi
+ * (mgconv/ffi.py).  Every function returns mg_status (0 = ok); the message of the last
+ * failure on a context is available from mg_last_error().  Nothing here allocates device
+ * memory: the host (Torch) owns all tensors and passes raw device pointers on every call
+ * (getParameters() re-homes weights after construction -- pipelines/standard/train.lua:115).
+ * All work is enqueued on the stream given to the context; no call synchronises.
+ *
+ * Tensor convention ("grid"): NHWC, element type = the context dtype (fp32 or bf16),
+ * channel pitch Cp = C rounded up to a multiple of 8, pad channels are zero.  A grid may
+ * carry a *pending* per-channel affine (+ReLU) -- the BatchNorm(+ReLU) of its producer,
+ * which is applied on the fly by whatever consumes the grid and never materialised:
+ *      a[n,y,x,c] = relu?( scale[c] * data[n,y,x,c] + shift[c] )
+ */
+#ifndef MGCONV_H
+#define MGCONV_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MG_MAX_SEG 6   /* input segments of one conv (3 for mg-conv; up to 6 after nn.ConcatUnet) */
+#define MG_MAX_SRC 8   /* gradient contributions combined into one tensor */
+
+typedef struct mg_ctx mg_ctx;
+
+typedef enum {
+  MG_OK = 0,
+  MG_ERR_INVALID_ARG = 1,
+  MG_ERR_SHAPE = 2,
+  MG_ERR_CUDA = 3,
+  MG_ERR_NCCL = 4,
+  MG_ERR_UNSUPPORTED = 5
+} mg_status;
+
+typedef enum { MG_F32 = 0, MG_BF16 = 1 } mg_dtype;
+
+/* how a source grid enters a conv's channel-concatenated input
+ * (ResampleConcat, models/ilsvrc/rnmg.lua:41-89) */
+typedef enum {
+  MG_SEG_SAME = 0, /* nn.SelectTable(i)                                  rnmg.lua:64  */
+  MG_SEG_POOL = 1, /* finer grid through SpatialMaxPooling(2,2,2,2):ceil rnmg.lua:54-60 */
+  MG_SEG_UP = 2    /* coarser grid through SpatialUpSamplingNearest(2)   rnmg.lua:70-76 */
+} mg_seg_mode;
+
+typedef enum { MG_IMPL_AUTO = 0, MG_IMPL_SIMT = 1, MG_IMPL_TCGEN05 = 2 } mg_impl;
+
+typedef struct {
+  void* data;         /* device, NHWC [N][H][W][Cp] */
+  const float* scale; /* device [Cp] or NULL (identity) */
+  const float* shift; /* device [Cp] or NULL */
+  int32_t relu;       /* ReLU after the affine */
+  int32_t N, H, W, C, Cp;
+} mg_grid;
+
+/* One convolution of an mg stage: y = conv_k( cat_C[ seg_0 | seg_1 | ... ] ) + bias,
+ * stride `stride` (1 everywhere except the ImageNet stem), zero padding `pad`.
+ * Replaces Concat{Max,Select,UpSample} -> JoinTable(2) -> cudnn.SpatialConvolution
+ * (models/ilsvrc/rnmg.lua:53-82 + 26/36; models/cifar/nmg.lua:46-79 + 22). */
+typedef struct {
+  int32_t n_seg;
+  mg_grid seg[MG_MAX_SEG];
+  int32_t seg_mode[MG_MAX_SEG];
+  int32_t ksize, stride, pad;
+  int32_t Cout;
+  int32_t H, W; /* spatial size of the concatenated input (= output size when stride 1) */
+} mg_conv_desc;
+
+typedef struct {
+  mg_grid g;        /* gradient tensor of a consumer */
+  int32_t c_offset; /* first channel of g that belongs to this tensor */
+  int32_t mode;     /* MG_SEG_SAME: same resolution; MG_SEG_POOL: the consumer max-pooled this
+                       tensor (g is at the coarser size, route through the 2x2 argmax);
+                       MG_SEG_UP: the consumer upsampled this tensor (g is finer, sum 2x2);
+                       3 = the consumer applied SpatialMaxPooling(3,3,2,2,1,1) (stem) */
+} mg_grad_src;
+
+/* ---- context ------------------------------------------------------------------------ */
+int mg_ctx_create(int device, void* cuda_stream, int dtype, mg_ctx** out);
+int mg_ctx_destroy(mg_ctx* ctx);
+int mg_ctx_set_stream(mg_ctx* ctx, void* cuda_stream);
+int mg_ctx_set_impl(mg_ctx* ctx, int impl);          /* mg_impl; AUTO = tcgen05 for bf16 */
+int mg_ctx_sync(mg_ctx* ctx);                         /* cutorch.synchronize() equivalent */
+const char* mg_last_error(mg_ctx* ctx);
+int mg_version(void);
+int mg_ctx_launch_count(mg_ctx* ctx, int64_t* out);   /* kernels launched through this ctx */
+
+/* ---- layout conversion at the Torch boundary (NCHW fp32 <-> grid) --------------------- */
+int mg_import_nchw(mg_ctx* ctx, const float* src, mg_grid* dst);            /* put2GPU output -> grid */
+int mg_export_nchw(mg_ctx* ctx, const mg_grid* src, float* dst);            /* applies pending affine */
+
+/* ---- forward -------------------------------------------------------------------------- */
+/* packed weight bytes for the tcgen05 path (0 when the SIMT path is used) */
+size_t mg_conv_packed_bytes(const mg_conv_desc* d, int transposed);
+/* repack fp32 [Cout][Ccat][k][k] master weights (cudnn.SpatialConvolution.weight) into the
+ * UMMA operand images for forward (transposed=0) and dgrad (transposed=1) */
+int mg_conv_pack_weights(mg_ctx* ctx, const mg_conv_desc* d, const float* w, void* wpack, int transposed);
+
+/* fused gather + conv + bias; writes raw y and accumulates per-channel (sum, sumsq) of y in
+ * bn_sums[2*Cout] (fp64, caller zeroes) for the following SpatialBatchNormalization */
+int mg_conv_forward(mg_ctx* ctx, const mg_conv_desc* d, const float* w, const void* wpack,
+                    const float* bias, mg_grid* y, double* bn_sums);
+
+/* nn.SpatialBatchNormalization statistics -> pending affine of the conv output.
+ * training: batch stats from bn_sums over `count` elements per channel, running stats updated
+ * (momentum, unbiased var); else running stats.  models/ilsvrc/rnmg.lua:27,37 */
+int mg_bn_finalize(mg_ctx* ctx, const double* bn_sums, int64_t count, int32_t C, int32_t Cp,
+                   const float* gamma, const float* beta, float* running_mean, float* running_var,
+                   float eps, float momentum, int training,
+                   float* scale, float* shift, float* save_mean, float* save_invstd);
+
+/* out = relu?( T(z) + T(s)[c < s.C] ): CAddTable(true) + ReLU(true) with nn.Padding /
+ * Identity shortcut (models/ilsvrc/rnmg.lua:13-20,140-154).  s may be NULL. */
+int mg_residual_forward(mg_ctx* ctx, const mg_grid* z, const mg_grid* s, int relu, mg_grid* out);
+
+/* out[..., c_offset + c] = maxpool2x2_ceil(T(in))[..., c]  (mgPool, rnmg.lua:191-224);
+ * argmax (nullable, int32 [N][Ho][Wo][C]) receives the flat y*W+x index, 0-based */
+int mg_pool_forward(mg_ctx* ctx, const mg_grid* in, mg_grid* out, int32_t c_offset, int32_t* argmax);
+/* out[..., c_offset + c] = T(in)[..., c]   (JoinTable(2) of mgPool isConcat) */
+int mg_copy_channels(mg_ctx* ctx, const mg_grid* in, mg_grid* out, int32_t c_offset);
+/* cudnn.SpatialAveragePooling(r,r,r,r) on NHWC (image pyramid, rnmg.lua:175-177) */
+int mg_avgpool_forward(mg_ctx* ctx, const mg_grid* in, int32_t r, mg_grid* out);
+/* SpatialMaxPooling(3,3,2,2,1,1) of the ImageNet stem (rnmg.lua:183) */
+int mg_pool3s2_forward(mg_ctx* ctx, const mg_grid* in, mg_grid* out);
+/* SelectTable(1) -> AvgPool(HxW) -> View: out[n][c] fp32 (rnmg.lua:281-283) */
+int mg_global_avgpool_forward(mg_ctx* ctx, const mg_grid* in, mg_grid* out);
+int mg_global_avgpool_backward(mg_ctx* ctx, const mg_grid* dout, mg_grid* din);
+
+/* ---- backward ------------------------------------------------------------------------- */
+/* Sum of all consumers' gradient contributions into tensor x (ConcatTable backward sums
+ * its branches), routed through pool argmax / upsample block-sum, times the ReLU mask of x
+ * when relu_mask.  Writes d (same shape as x).  If bn_sums != NULL also accumulates
+ * (sum d, sum d*xraw) per channel with xraw = bn_x ? bn_x : x (raw data). */
+int mg_grad_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid* bn_x,
+                    int32_t n_src, const mg_grad_src* src, mg_grid* d, double* bn_sums);
+/* BatchNorm backward given the sums: out = gamma*invstd*(d - mean(d) - xhat*mean(d*xhat))
+ * (out may alias d); dgamma += gscale*sum(d*xhat); dbeta += gscale*sum(d). */
+int mg_bn_backward(mg_ctx* ctx, const mg_grid* xraw, const mg_grid* d, mg_grid* out, const double* bn_sums,
+                   int64_t count, const float* gamma, const float* save_mean, const float* save_invstd,
+                   float* dgamma, float* dbeta, float gscale, float* coef_ws /* [3*Cp] scratch */);
+/* dcat = conv_transpose(g, w): gradient w.r.t. the concatenated input, segment s at channel
+ * offset sum_{t<s} Cp_t */
+int mg_conv_backward_data(mg_ctx* ctx, const mg_conv_desc* d, const float* w, const void* wpack_t,
+                          const mg_grid* g, mg_grid* dcat);
+/* dw += gscale * g^T * gather(x) ; dbias += gscale * sum(g)   (accGradParameters) */
+int mg_conv_backward_weight(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g,
+                            float* dw, float* dbias, float gscale);
+
+/* ---- head / criterion / optimiser ("next" rows of the scope table) ------------------- */
+/* LogSoftMax + ClassNLLCriterion (mean): logits grid N x 1 x 1 x C; target int32 0-based;
+ * loss (1 float, device, caller zeroes) += NLL; logprob fp32 [N][C] (nullable);
+ * dlogits = gscale * dloss/dlogits (nullable) */
+int mg_nll_forward_backward(mg_ctx* ctx, const mg_grid* logits, const int32_t* target, float* logprob,
+                            float* loss, mg_grid* dlogits, float gscale);
+/* LogSoftMax alone (the model's last module, rnmg.lua:285) and its backward */
+int mg_logsoftmax_forward(mg_ctx* ctx, const mg_grid* logits, float* logprob);
+int mg_logsoftmax_backward(mg_ctx* ctx, const float* logprob, const float* grad_out, mg_grid* dlogits);
+/* Sigmoid + BCECriterion (mean over elements) on a grid; target fp32 NCHW; loss += (caller zeroes) */
+int mg_bce_forward_backward(mg_ctx* ctx, const mg_grid* x, const float* target_nchw, float* prob_nchw,
+                            float* loss, mg_grid* dx, float gscale);
+/* nn.Sigmoid alone: prob_nchw = sigmoid(T(x)); backward dx = grad_out * p * (1-p) */
+int mg_sigmoid_forward(mg_ctx* ctx, const mg_grid* x, float* prob_nchw);
+int mg_sigmoid_backward(mg_ctx* ctx, const float* prob_nchw, const float* grad_out_nchw, mg_grid* dx);
+/* optim.sgd on a flat fp32 vector: g += wd*w; v = first ? g : mu*v+g; w -= lr*v */
+int mg_sgd_step(mg_ctx* ctx, float* w, const float* g, float* v, int64_t n,
+                float lr, float momentum, float wd, int first);
+
+/* ---- data parallel (replaces nn.DataParallelTable, multigpu.lua:81-103) ---------------- */
+int mg_comm_unique_id(void* out128);                                  /* ncclGetUniqueId */
+int mg_comm_init(mg_ctx* ctx, int rank, int nranks, const void* id128);
+int mg_comm_destroy(mg_ctx* ctx);
+/* in-place sum all-reduce on the context's communication stream, ordered after everything
+ * enqueued so far on the compute stream; mg_allreduce_wait makes the compute stream wait */
+int mg_allreduce_launch(mg_ctx* ctx, void* buf, int64_t count, int is_double);
+int mg_allreduce_wait(mg_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGCONV_H */

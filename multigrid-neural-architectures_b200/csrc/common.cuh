@@ -1,0 +1,123 @@
+// Shared device/host helpers of libmgconv (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/mgconv.h"
+
+struct mg_ctx {
+  int device;
+  cudaStream_t stream;
+  int dtype;        // mg_dtype
+  int impl;         // mg_impl
+  int num_sms;
+  int64_t launches; // kernels launched through this context
+  char err[512];
+  // data parallel
+  void* nccl_comm;
+  cudaStream_t comm_stream;
+  cudaEvent_t ev_compute, ev_comm;
+  int rank, nranks;
+};
+
+#define MG_FAIL(ctx, code, ...)                                  \
+  do {                                                           \
+    if (ctx) snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__); \
+    return (code);                                               \
+  } while (0)
+
+#define MG_CUDA(ctx, expr)                                                        \
+  do {                                                                            \
+    cudaError_t _e = (expr);                                                      \
+    if (_e != cudaSuccess)                                                        \
+      MG_FAIL(ctx, MG_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define MG_CHECK_LAUNCH(ctx)              \
+  do {                                    \
+    (ctx)->launches++;                    \
+    MG_CUDA(ctx, cudaGetLastError());     \
+  } while (0)
+
+#define MG_REQUIRE(ctx, cond, code, ...) \
+  do {                                   \
+    if (!(cond)) MG_FAIL(ctx, code, __VA_ARGS__); \
+  } while (0)
+
+static inline int mg_round_up(int a, int b) { return (a + b - 1) / b * b; }
+static inline int64_t mg_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- element access --------------------------------------------------------------
+__device__ __forceinline__ float mg_ld(const float* p) { return *p; }
+__device__ __forceinline__ float mg_ld(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void mg_st(float* p, float v) { *p = v; }
+__device__ __forceinline__ void mg_st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// pending affine (+ReLU) of a grid; identical expression everywhere so that forward
+// values, ReLU masks and pool arg-maxima agree bit for bit between kernels
+__device__ __forceinline__ float mg_xform(float v, float sc, float sh, int relu) {
+  float a = fmaf(v, sc, sh);
+  return relu ? fmaxf(a, 0.f) : a;
+}
+
+// device view of a grid
+template <typename T>
+struct GridV {
+  const T* data;
+  const float* scale;
+  const float* shift;
+  int relu;
+  int N, H, W, C, Cp;
+  __device__ __forceinline__ float raw(int n, int y, int x, int c) const {
+    return mg_ld(data + (((size_t)n * H + y) * W + x) * Cp + c);
+  }
+  __device__ __forceinline__ float at(int n, int y, int x, int c) const {
+    float v = raw(n, y, x, c);
+    if (scale) v = mg_xform(v, scale[c], shift[c], relu);
+    return v;
+  }
+  // SpatialMaxPooling(2,2,2,2,0,0):ceil() window at pooled position (py,px): rows then cols,
+  // strict '>' so the first maximum wins; *arg = flat y*W+x of the winner
+  __device__ __forceinline__ float pooled(int n, int py, int px, int c, int* arg) const {
+    int y0 = 2 * py, x0 = 2 * px;
+    int y1 = min(y0 + 2, H), x1 = min(x0 + 2, W);
+    float best = -INFINITY;
+    int bi = y0 * W + x0;
+    for (int yy = y0; yy < y1; ++yy)
+      for (int xx = x0; xx < x1; ++xx) {
+        float v = at(n, yy, xx, c);
+        if (v > best || v != v) { best = v; bi = yy * W + xx; }
+      }
+    if (arg) *arg = bi;
+    return best;
+  }
+};
+
+template <typename T>
+static inline GridV<T> make_view(const mg_grid& g) {
+  GridV<T> v;
+  v.data = (const T*)g.data; v.scale = g.scale; v.shift = g.shift; v.relu = g.relu;
+  v.N = g.N; v.H = g.H; v.W = g.W; v.C = g.C; v.Cp = g.Cp;
+  return v;
+}
+
+static inline size_t mg_elt_size(int dtype) { return dtype == MG_BF16 ? 2 : 4; }
+
+// dispatch on the context dtype
+#define MG_DISPATCH(ctx, ...)                          \
+  do {                                                 \
+    if ((ctx)->dtype == MG_BF16) { using T = __nv_bfloat16; __VA_ARGS__ } \
+    else { using T = float; __VA_ARGS__ }              \
+  } while (0)
+
+// block-wide helpers
+__device__ __forceinline__ double warp_sum(double v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}

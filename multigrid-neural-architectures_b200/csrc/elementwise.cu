@@ -1,0 +1,519 @@
+// HBM-bound passes of the multigrid hot path: layout import/export, BatchNorm finalise and
+// backward, residual add, pooling, the gradient "combine" (gather-form scatter through pool
+// arg-max / upsample / shortcut), criteria and SGD.  One thread per (pixel, channel) with the
+// channel index fastest, so a warp touches 32 consecutive channels of one NHWC pixel row.
+#include "common.cuh"
+
+namespace {
+
+constexpr int EB = 256;
+
+// ---------------------------------------------------------------- import / export ---
+template <typename T>
+__global__ void import_nchw_kernel(const float* __restrict__ src, T* __restrict__ dst, int N, int C, int Cp, int H, int W) {
+  int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x;
+  int64_t total = (int64_t)N * H * W * Cp;
+  if (i >= total) return;
+  int c = i % Cp; int64_t p = i / Cp;
+  int x = p % W; p /= W; int y = p % H; int n = p / H;
+  float v = c < C ? src[(((size_t)n * C + c) * H + y) * W + x] : 0.f;
+  mg_st(dst + i, v);
+}
+
+template <typename T>
+__global__ void export_nchw_kernel(GridV<T> g, float* __restrict__ dst) {
+  int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x;
+  int64_t total = (int64_t)g.N * g.C * g.H * g.W;
+  if (i >= total) return;
+  int x = i % g.W; int64_t p = i / g.W;
+  int y = p % g.H; p /= g.H; int c = p % g.C; int n = p / g.C;
+  dst[i] = g.at(n, y, x, c);
+}
+
+// ---------------------------------------------------------------- BN finalise -------
+__global__ void bn_finalize_kernel(const double* sums, int64_t count, int C, int Cp, const float* gamma,
+                                   const float* beta, float* rmean, float* rvar, float eps, float momentum,
+                                   int training, float* scale, float* shift, float* smean, float* sinvstd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cp) return;
+  if (c >= C) { scale[c] = 0.f; shift[c] = 0.f; if (smean) { smean[c] = 0.f; sinvstd[c] = 0.f; } return; }
+  double mean, var;
+  if (training) {
+    mean = sums[c] / (double)count;
+    var = sums[C + c] / (double)count - mean * mean;   // biased
+    if (var < 0) var = 0;
+    if (rmean) {
+      double unb = count > 1 ? var * (double)count / (double)(count - 1) : var;
+      rmean[c] = (float)((1.0 - momentum) * rmean[c] + momentum * mean);
+      rvar[c] = (float)((1.0 - momentum) * rvar[c] + momentum * unb);
+    }
+  } else {
+    mean = rmean[c]; var = rvar[c];
+  }
+  double invstd = 1.0 / sqrt(var + (double)eps);
+  float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  scale[c] = (float)(g * invstd);
+  shift[c] = (float)(b - g * invstd * mean);
+  if (smean) { smean[c] = (float)mean; sinvstd[c] = (float)invstd; }
+}
+
+// ---------------------------------------------------------------- residual ----------
+template <typename T>
+__global__ void residual_kernel(GridV<T> z, GridV<T> s, int has_s, int relu, T* __restrict__ out, int out_cp) {
+  int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x;
+  int64_t total = (int64_t)z.N * z.H * z.W * out_cp;
+  if (i >= total) return;
+  int c = i % out_cp; int64_t p = i / out_cp;
+  float v = 0.f;
+  if (c < z.C) {
+    v = mg_ld(z.data + p * z.Cp + c);
+    if (z.scale) v = mg_xform(v, z.scale[c], z.shift[c], z.relu);
+    if (has_s && c < s.C) {
+      float sv = mg_ld(s.data + p * s.Cp + c);
+      if (s.scale) sv = mg_xform(sv, s.scale[c], s.shift[c], s.relu);
+      v += sv;
+    }
+    if (relu) v = fmaxf(v, 0.f);
+  }
+  mg_st(out + i, v);
+}
+
+// ---------------------------------------------------------------- pooling -----------
+template <typename T>
+__global__ void pool2_kernel(GridV<T> in, T* __restrict__ out, int Ho, int Wo, int out_cp, int c_off, int32_t* argmax) {
+  int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x;
+  int64_t total = (int64_t)in.N * Ho * Wo * in.C;
+  if (i >= total) return;
+  int c = i % in.C; int64_t p = i / in.C;
+  int px = p % Wo; int64_t q = p / Wo; int py = q % Ho; int n = q / Ho;
+  int arg;
+  float v = in.pooled(n, py, px, c, &arg);
+  mg_st(out + p * out_cp + c_off + c, v);
+  if (argmax) argmax[i] = arg;
+}
+
+template <typename T>
+__global__ void copy_channels_kernel(GridV<T> in, T* __restrict__ out, int out_cp, int c_off) {
+  int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x;
+  int64_t total = (int64_t)in.N * in.H * in.W * in.C;
+  if (i >= total) return;
+  int c = i % in.C; int64_t p = i / in.C;
+  float v = mg_ld(in.data + p * in.Cp + c);
+  if (in.scale) v = mg_xform(v, in.scale[c], in.shift[c], in.relu);
+  mg_st(out + p * out_cp + c_off + c, v);
+}
+
+template <typename T>
+__global__ void avgpool_kernel(GridV<T> in, int r, T* __restrict__ out, int Ho, int Wo, int out_cp) {
+  int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x;
+  int64_t total = (int64_t)in.N * Ho * Wo * out_cp;
+  if (i >= total) return;
+  int c = i % out_cp; int64_t p = i / out_cp;
+  int px = p % Wo; int64_t q = p / Wo; int py = q % Ho; int n = q / Ho;
+  float s = 0.f;
+  if (c < in.C) {
+    for (int dy = 0; dy < r; ++dy)
+      for (int dx = 0; dx < r; ++dx) s += in.at(n, py * r + dy, px * r + dx, c);
+    s /= (float)(r * r);
+  }
+  mg_st(out + i, s);
+}
+
+// SpatialMaxPooling(3,3,2,2,1,1): floor mode, windows clipped to the image
+template <typename T>
+__device__ __forceinline__ float pool3_window(const GridV<T>& in, int n, int oy, int ox, int c, int* arg) {
+  int y0 = max(oy * 2 - 1, 0), x0 = max(ox * 2 - 1, 0);
+  int y1 = min(oy * 2 + 2, in.H), x1 = min(ox * 2 + 2, in.W);
+  float best = -INFINITY; int bi = y0 * in.W + x0;
+  for (int yy = y0; yy < y1; ++yy)
+    for (int xx = x0; xx < x1; ++xx) {
+      float v = in.at(n, yy, xx, c);
+      if (v > best || v != v) { best = v; bi = yy * in.W + xx; }
+    }
+  *arg = bi;
+  return best;
+}
+
+template <typename T>
+__global__ void pool3_kernel(GridV<T> in, T* __restrict__ out, int Ho, int Wo, int out_cp) {
+  int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x;
+  int64_t total = (int64_t)in.N * Ho * Wo * out_cp;
+  if (i >= total) return;
+  int c = i % out_cp; int64_t p = i / out_cp;
+  int px = p % Wo; int64_t q = p / Wo; int py = q % Ho; int n = q / Ho;
+  int arg; float v = 0.f;
+  if (c < in.C) v = pool3_window(in, n, py, px, c, &arg);
+  mg_st(out + i, v);
+}
+
+template <typename T>
+__global__ void global_avgpool_kernel(GridV<T> in, T* __restrict__ out, int out_cp) {
+  int i = blockIdx.x * EB + threadIdx.x;
+  if (i >= in.N * out_cp) return;
+  int c = i % out_cp, n = i / out_cp;
+  float s = 0.f;
+  if (c < in.C) {
+    for (int y = 0; y < in.H; ++y)
+      for (int x = 0; x < in.W; ++x) s += in.at(n, y, x, c);
+    s /= (float)(in.H * in.W);
+  }
+  mg_st(out + i, s);
+}
+
+template <typename T>
+__global__ void global_avgpool_bwd_kernel(const T* __restrict__ dout, int dout_cp, T* __restrict__ din, int N, int H, int W, int C, int Cp) {
+  int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x;
+  int64_t total = (int64_t)N * H * W * Cp;
+  if (i >= total) return;
+  int c = i % Cp; int64_t p = i / Cp; int n = p / (H * W);
+  float v = c < C ? mg_ld(dout + (size_t)n * dout_cp + c) / (float)(H * W) : 0.f;
+  mg_st(din + i, v);
+}
+
+// ---------------------------------------------------------------- gradient combine --
+template <typename T>
+struct SrcV { GridV<T> g; int c_off; int mode; };
+
+template <typename T>
+struct CombineP {
+  GridV<T> x;
+  int relu_mask;
+  const T* bn_x; int bn_cp;
+  int n_src; SrcV<T> src[MG_MAX_SRC];
+  T* d; int d_cp;
+  double* bn_sums;
+  int pix_per_block;
+};
+
+// block = 32 channels x 8 pixel lanes
+template <typename T>
+__global__ void __launch_bounds__(256) combine_kernel(CombineP<T> p) {
+  const int cl = threadIdx.x % 32, lane = threadIdx.x / 32;
+  const int c = blockIdx.y * 32 + cl;
+  const int64_t P = (int64_t)p.x.N * p.x.H * p.x.W;
+  const int64_t p0 = (int64_t)blockIdx.x * p.pix_per_block;
+  const int64_t p1 = min(P, p0 + p.pix_per_block);
+  const GridV<T>& X = p.x;
+  float sd = 0.f, sdx = 0.f;
+  if (c < p.d_cp) {
+    for (int64_t pix = p0 + lane; pix < p1; pix += 8) {
+      float sum = 0.f;
+      if (c < X.C) {
+        int x = pix % X.W; int64_t q = pix / X.W; int y = q % X.H; int n = q / X.H;
+        for (int s = 0; s < p.n_src; ++s) {
+          const GridV<T>& G = p.src[s].g;
+          const int gc = p.src[s].c_off + c;
+          const int mode = p.src[s].mode;
+          if (mode == MG_SEG_SAME) {
+            sum += G.raw(n, y, x, gc);
+          } else if (mode == MG_SEG_UP) {
+            sum += G.raw(n, 2 * y, 2 * x, gc) + G.raw(n, 2 * y, 2 * x + 1, gc) +
+                   G.raw(n, 2 * y + 1, 2 * x, gc) + G.raw(n, 2 * y + 1, 2 * x + 1, gc);
+          } else if (mode == MG_SEG_POOL) {
+            int arg; X.pooled(n, y >> 1, x >> 1, c, &arg);
+            if (arg == y * X.W + x) sum += G.raw(n, y >> 1, x >> 1, gc);
+          } else {  // 3x3 stride-2 pad-1 windows containing (y, x)
+            int oy0 = max((y - 1 + 1) / 2, 0), oy1 = min((y + 1) / 2, G.H - 1);
+            int ox0 = max((x - 1 + 1) / 2, 0), ox1 = min((x + 1) / 2, G.W - 1);
+            for (int oy = oy0; oy <= oy1; ++oy)
+              for (int ox = ox0; ox <= ox1; ++ox) {
+                int arg; pool3_window(X, n, oy, ox, c, &arg);
+                if (arg == y * X.W + x) sum += G.raw(n, oy, ox, gc);
+              }
+          }
+        }
+        if (p.relu_mask) { float v = X.at(n, y, x, c); if (!(v > 0.f)) sum = 0.f; }
+        if (p.bn_sums) { sd += sum; sdx += sum * mg_ld(p.bn_x + pix * p.bn_cp + c); }
+      }
+      mg_st(p.d + pix * p.d_cp + c, sum);
+    }
+  }
+  if (p.bn_sums) {
+    __shared__ float red[2][8][33];
+    red[0][lane][cl] = sd; red[1][lane][cl] = sdx;
+    __syncthreads();
+    if (lane == 0 && c < X.C) {
+      float a = 0.f, b = 0.f;
+      for (int l = 0; l < 8; ++l) { a += red[0][l][cl]; b += red[1][l][cl]; }
+      atomicAdd(p.bn_sums + c, (double)a);
+      atomicAdd(p.bn_sums + X.C + c, (double)b);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- BN backward -------
+// coef[0*Cp+c]=A, [1*Cp+c]=B, [2*Cp+c]=Cc with d' = A*d + B*xraw + Cc
+__global__ void bn_bwd_coef_kernel(const double* sums, int64_t count, int C, int Cp, const float* gamma,
+                                   const float* mean, const float* invstd, float* dgamma, float* dbeta,
+                                   float gscale, float* coef) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Cp) return;
+  if (c >= C) { coef[c] = 0.f; coef[Cp + c] = 0.f; coef[2 * Cp + c] = 0.f; return; }
+  double sd = sums[c], sdx = sums[C + c];
+  double mu = mean[c], is = invstd[c], g = gamma ? gamma[c] : 1.0;
+  double dg = is * (sdx - mu * sd);
+  if (dgamma) dgamma[c] += gscale * (float)dg;
+  if (dbeta) dbeta[c] += gscale * (float)sd;
+  double n = (double)count;
+  coef[c] = (float)(g * is);
+  coef[Cp + c] = (float)(-g * is * is * dg / n);
+  coef[2 * Cp + c] = (float)(g * is * (mu * is * dg / n - sd / n));
+}
+
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ xraw, int x_cp, T* __restrict__ d, int d_cp, int C,
+                                    int64_t P, const float* __restrict__ coef) {
+  int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x;
+  if (i >= P * d_cp) return;
+  int c = i % d_cp; int64_t pix = i / d_cp;
+  if (c >= C) return;
+  float v = fmaf(coef[c], mg_ld(d + i), fmaf(coef[d_cp + c], mg_ld(xraw + pix * x_cp + c), coef[2 * d_cp + c]));
+  mg_st(d + i, v);
+}
+
+// ---------------------------------------------------------------- criteria ----------
+// one block per sample: LogSoftMax + ClassNLLCriterion(mean) forward and gradient
+template <typename T>
+__global__ void nll_kernel(const T* __restrict__ logits, int C, int ld, const int32_t* __restrict__ target,
+                           float* logprob, float* loss, T* dlogits, int dl_ld, float gscale, int N) {
+  int n = blockIdx.x;
+  const T* row = logits + (size_t)n * ld;
+  __shared__ float red[32];
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) m = fmaxf(m, mg_ld(row + c));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = m;
+  __syncthreads();
+  m = red[0];
+  for (int w = 1; w < blockDim.x / 32; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float s = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s += expf(mg_ld(row + c) - m);
+  s = warp_sum(s);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int w = 0; w < blockDim.x / 32; ++w) s += red[w];
+  float lse = m + logf(s);
+  int t = target[n];
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float lp = mg_ld(row + c) - lse;
+    if (logprob) logprob[(size_t)n * C + c] = lp;
+    if (dlogits) mg_st(dlogits + (size_t)n * dl_ld + c, gscale * (expf(lp) - (c == t ? 1.f : 0.f)) / (float)N);
+  }
+  if (threadIdx.x == 0 && loss) atomicAdd(loss, -(mg_ld(row + t) - lse) / (float)N);
+}
+
+// Sigmoid + BCECriterion (mean over all elements, eps 1e-12)
+template <typename T>
+__global__ void bce_kernel(GridV<T> x, const float* __restrict__ target, float* prob, float* loss, T* dx, int dx_cp, float gscale) {
+  int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x;
+  int64_t total = (int64_t)x.N * x.C * x.H * x.W;
+  float l = 0.f;
+  if (i < total) {
+    int xx = i % x.W; int64_t p = i / x.W;
+    int y = p % x.H; p /= x.H; int c = p % x.C; int n = p / x.C;
+    float v = x.at(n, y, xx, c);
+    float pr = 1.f / (1.f + expf(-v));
+    float t = target[i];
+    const float eps = 1e-12f;
+    l = -(logf(pr + eps) * t + logf(1.f - pr + eps) * (1.f - t)) / (float)total;
+    if (prob) prob[i] = pr;
+    if (dx) {
+      float dp = -(t - pr) / ((1.f - pr + eps) * (pr + eps)) / (float)total;
+      mg_st(dx + (((size_t)n * x.H + y) * x.W + xx) * dx_cp + c, gscale * dp * pr * (1.f - pr));
+    }
+  }
+  l = warp_sum(l);
+  if (loss && threadIdx.x % 32 == 0 && l != 0.f) atomicAdd(loss, l);
+}
+
+__global__ void sgd_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ v, int64_t n,
+                           float lr, float mu, float wd, int first) {
+  int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x;
+  if (i >= n) return;
+  float gi = fmaf(wd, w[i], g[i]);
+  float vi = first ? gi : fmaf(mu, v[i], gi);
+  v[i] = vi;
+  w[i] = fmaf(-lr, vi, w[i]);
+}
+
+}  // namespace
+
+#define GRID1(total) (unsigned)mg_cdiv((int64_t)(total), EB)
+
+extern "C" {
+
+int mg_import_nchw(mg_ctx* ctx, const float* src, mg_grid* dst) {
+  if (!ctx || !src || !dst) return MG_ERR_INVALID_ARG;
+  int64_t total = (int64_t)dst->N * dst->H * dst->W * dst->Cp;
+  MG_DISPATCH(ctx, import_nchw_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>(src, (T*)dst->data, dst->N, dst->C, dst->Cp, dst->H, dst->W););
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int mg_export_nchw(mg_ctx* ctx, const mg_grid* src, float* dst) {
+  if (!ctx || !src || !dst) return MG_ERR_INVALID_ARG;
+  int64_t total = (int64_t)src->N * src->H * src->W * src->C;
+  MG_DISPATCH(ctx, export_nchw_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>(make_view<T>(*src), dst););
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int mg_bn_finalize(mg_ctx* ctx, const double* bn_sums, int64_t count, int32_t C, int32_t Cp, const float* gamma,
+                   const float* beta, float* running_mean, float* running_var, float eps, float momentum,
+                   int training, float* scale, float* shift, float* save_mean, float* save_invstd) {
+  if (!ctx || !scale || !shift) return MG_ERR_INVALID_ARG;
+  MG_REQUIRE(ctx, training ? bn_sums != nullptr : (running_mean && running_var), MG_ERR_INVALID_ARG,
+             "bn_finalize: missing statistics");
+  bn_finalize_kernel<<<(unsigned)mg_cdiv(Cp, 128), 128, 0, ctx->stream>>>(bn_sums, count, C, Cp, gamma, beta, running_mean,
+                                                                 running_var, eps, momentum, training, scale, shift,
+                                                                 save_mean, save_invstd);
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int mg_residual_forward(mg_ctx* ctx, const mg_grid* z, const mg_grid* s, int relu, mg_grid* out) {
+  if (!ctx || !z || !out) return MG_ERR_INVALID_ARG;
+  MG_REQUIRE(ctx, out->N == z->N && out->H == z->H && out->W == z->W && out->C == z->C, MG_ERR_SHAPE, "residual: out shape");
+  if (s) MG_REQUIRE(ctx, s->N == z->N && s->H == z->H && s->W == z->W && s->C <= z->C, MG_ERR_SHAPE,
+                    "residual: shortcut %dx%dx%d vs %dx%dx%d", s->H, s->W, s->C, z->H, z->W, z->C);
+  int64_t total = (int64_t)z->N * z->H * z->W * out->Cp;
+  MG_DISPATCH(ctx, residual_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>(make_view<T>(*z), s ? make_view<T>(*s) : make_view<T>(*z),
+                                                                           s != nullptr, relu, (T*)out->data, out->Cp););
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int mg_pool_forward(mg_ctx* ctx, const mg_grid* in, mg_grid* out, int32_t c_offset, int32_t* argmax) {
+  if (!ctx || !in || !out) return MG_ERR_INVALID_ARG;
+  int Ho = (in->H + 1) / 2, Wo = (in->W + 1) / 2;
+  MG_REQUIRE(ctx, out->H == Ho && out->W == Wo && out->N == in->N && c_offset + in->C <= out->Cp, MG_ERR_SHAPE,
+             "pool: out %dx%d (C %d) for in %dx%d (C %d, off %d)", out->H, out->W, out->C, in->H, in->W, in->C, c_offset);
+  int64_t total = (int64_t)in->N * Ho * Wo * in->C;
+  MG_DISPATCH(ctx, pool2_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>(make_view<T>(*in), (T*)out->data, Ho, Wo, out->Cp, c_offset, argmax););
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int mg_copy_channels(mg_ctx* ctx, const mg_grid* in, mg_grid* out, int32_t c_offset) {
+  if (!ctx || !in || !out) return MG_ERR_INVALID_ARG;
+  MG_REQUIRE(ctx, out->H == in->H && out->W == in->W && out->N == in->N && c_offset + in->C <= out->Cp, MG_ERR_SHAPE, "copy_channels: shape");
+  int64_t total = (int64_t)in->N * in->H * in->W * in->C;
+  MG_DISPATCH(ctx, copy_channels_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>(make_view<T>(*in), (T*)out->data, out->Cp, c_offset););
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int mg_avgpool_forward(mg_ctx* ctx, const mg_grid* in, int32_t r, mg_grid* out) {
+  if (!ctx || !in || !out || r < 1) return MG_ERR_INVALID_ARG;
+  int Ho = in->H / r, Wo = in->W / r;
+  MG_REQUIRE(ctx, out->H == Ho && out->W == Wo && out->N == in->N && out->C == in->C, MG_ERR_SHAPE, "avgpool: shape");
+  int64_t total = (int64_t)in->N * Ho * Wo * out->Cp;
+  MG_DISPATCH(ctx, avgpool_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>(make_view<T>(*in), r, (T*)out->data, Ho, Wo, out->Cp););
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int mg_pool3s2_forward(mg_ctx* ctx, const mg_grid* in, mg_grid* out) {
+  if (!ctx || !in || !out) return MG_ERR_INVALID_ARG;
+  int Ho = (in->H + 2 - 3) / 2 + 1, Wo = (in->W + 2 - 3) / 2 + 1;
+  MG_REQUIRE(ctx, out->H == Ho && out->W == Wo && out->N == in->N && out->C == in->C, MG_ERR_SHAPE, "pool3s2: shape");
+  int64_t total = (int64_t)in->N * Ho * Wo * out->Cp;
+  MG_DISPATCH(ctx, pool3_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>(make_view<T>(*in), (T*)out->data, Ho, Wo, out->Cp););
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int mg_global_avgpool_forward(mg_ctx* ctx, const mg_grid* in, mg_grid* out) {
+  if (!ctx || !in || !out) return MG_ERR_INVALID_ARG;
+  MG_REQUIRE(ctx, out->N == in->N && out->H == 1 && out->W == 1 && out->C == in->C, MG_ERR_SHAPE, "global_avgpool: shape");
+  MG_DISPATCH(ctx, global_avgpool_kernel<T><<<GRID1(in->N * out->Cp), EB, 0, ctx->stream>>>(make_view<T>(*in), (T*)out->data, out->Cp););
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int mg_global_avgpool_backward(mg_ctx* ctx, const mg_grid* dout, mg_grid* din) {
+  if (!ctx || !dout || !din) return MG_ERR_INVALID_ARG;
+  int64_t total = (int64_t)din->N * din->H * din->W * din->Cp;
+  MG_DISPATCH(ctx, global_avgpool_bwd_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>((const T*)dout->data, dout->Cp, (T*)din->data,
+                                                                                     din->N, din->H, din->W, din->C, din->Cp););
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int mg_grad_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid* bn_x, int32_t n_src,
+                    const mg_grad_src* src, mg_grid* d, double* bn_sums) {
+  if (!ctx || !x || !d || n_src < 0 || n_src > MG_MAX_SRC || (n_src && !src)) return MG_ERR_INVALID_ARG;
+  MG_REQUIRE(ctx, d->N == x->N && d->H == x->H && d->W == x->W && d->C == x->C, MG_ERR_SHAPE, "combine: d shape");
+  for (int s = 0; s < n_src; ++s) {
+    const mg_grid& g = src[s].g;
+    int m = src[s].mode;
+    bool ok = g.N == x->N && src[s].c_offset + x->C <= g.Cp;
+    if (m == MG_SEG_SAME) ok = ok && g.H == x->H && g.W == x->W;
+    else if (m == MG_SEG_UP) ok = ok && g.H == 2 * x->H && g.W == 2 * x->W;
+    else if (m == MG_SEG_POOL) ok = ok && g.H == (x->H + 1) / 2 && g.W == (x->W + 1) / 2;
+    else if (m == 3) ok = ok && g.H == (x->H - 1) / 2 + 1 && g.W == (x->W - 1) / 2 + 1;
+    else ok = false;
+    MG_REQUIRE(ctx, ok, MG_ERR_SHAPE, "combine: src %d (mode %d, %dx%dx%d off %d) does not match x %dx%dx%d", s, m, g.H,
+               g.W, g.Cp, src[s].c_offset, x->H, x->W, x->C);
+  }
+  int64_t P = (int64_t)x->N * x->H * x->W;
+  MG_DISPATCH(ctx, {
+    CombineP<T> p;
+    p.x = make_view<T>(*x); p.relu_mask = relu_mask;
+    p.bn_x = (const T*)(bn_x ? bn_x->data : x->data); p.bn_cp = bn_x ? bn_x->Cp : x->Cp;
+    p.n_src = n_src;
+    for (int s = 0; s < n_src; ++s) { p.src[s].g = make_view<T>(src[s].g); p.src[s].c_off = src[s].c_offset; p.src[s].mode = src[s].mode; }
+    p.d = (T*)d->data; p.d_cp = d->Cp; p.bn_sums = bn_sums;
+    p.pix_per_block = 64;
+    dim3 grid((unsigned)mg_cdiv(P, p.pix_per_block), (unsigned)mg_cdiv(d->Cp, 32));
+    combine_kernel<T><<<grid, 256, 0, ctx->stream>>>(p);
+  });
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int mg_bn_backward(mg_ctx* ctx, const mg_grid* xraw, mg_grid* d, const double* bn_sums, int64_t count, const float* gamma,
+                   const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, float gscale,
+                   float* coef_ws) {
+  if (!ctx || !xraw || !d || !bn_sums || !save_mean || !save_invstd || !coef_ws) return MG_ERR_INVALID_ARG;
+  MG_REQUIRE(ctx, d->N == xraw->N && d->H == xraw->H && d->W == xraw->W && d->C == xraw->C, MG_ERR_SHAPE, "bn_backward: shape");
+  bn_bwd_coef_kernel<<<(unsigned)mg_cdiv(d->Cp, 128), 128, 0, ctx->stream>>>(bn_sums, count, d->C, d->Cp, gamma, save_mean, save_invstd,
+                                                                   dgamma, dbeta, gscale, coef_ws);
+  MG_CHECK_LAUNCH(ctx);
+  int64_t P = (int64_t)d->N * d->H * d->W;
+  MG_DISPATCH(ctx, bn_bwd_apply_kernel<T><<<GRID1(P * d->Cp), EB, 0, ctx->stream>>>((const T*)xraw->data, xraw->Cp, (T*)d->data, d->Cp, d->C, P, coef_ws););
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int mg_nll_forward_backward(mg_ctx* ctx, const mg_grid* logits, const int32_t* target, float* logprob, float* loss,
+                            mg_grid* dlogits, float gscale) {
+  if (!ctx || !logits || !target) return MG_ERR_INVALID_ARG;
+  MG_REQUIRE(ctx, logits->H == 1 && logits->W == 1, MG_ERR_SHAPE, "nll: logits must be N x 1 x 1 x C");
+  MG_DISPATCH(ctx, nll_kernel<T><<<logits->N, 256, 0, ctx->stream>>>((const T*)logits->data, logits->C, logits->Cp, target, logprob, loss,
+                                                                    dlogits ? (T*)dlogits->data : nullptr, dlogits ? dlogits->Cp : 0,
+                                                                    gscale, logits->N););
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int mg_bce_forward_backward(mg_ctx* ctx, const mg_grid* x, const float* target_nchw, float* prob_nchw, float* loss,
+                            mg_grid* dx, float gscale) {
+  if (!ctx || !x || !target_nchw) return MG_ERR_INVALID_ARG;
+  int64_t total = (int64_t)x->N * x->C * x->H * x->W;
+  MG_DISPATCH(ctx, bce_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>(make_view<T>(*x), target_nchw, prob_nchw, loss,
+                                                                      dx ? (T*)dx->data : nullptr, dx ? dx->Cp : 0, gscale););
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int mg_sgd_step(mg_ctx* ctx, float* w, const float* g, float* v, int64_t n, float lr, float momentum, float wd, int first) {
+  if (!ctx || !w || !g || !v) return MG_ERR_INVALID_ARG;
+  sgd_kernel<<<GRID1(n), EB, 0, ctx->stream>>>(w, g, v, n, lr, momentum, wd, first);
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+}  // extern "C"
