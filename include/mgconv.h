@@ -122,7 +122,15 @@ int mg_bn_finalize(mg_ctx* ctx, const double* bn_sums, int64_t count, int32_t C,
 
 /* out = relu?( T(z) + T(s)[c < s.C] ): CAddTable(true) + ReLU(true) with nn.Padding /
  * Identity shortcut (models/ilsvrc/rnmg.lua:13-20,140-154).  s may be NULL. */
-int mg_residual_forward(mg_ctx* ctx, const mg_grid* z, const mg_grid* s, int relu, mg_grid* out);
+int mg_residual_forward(mg_ctx* ctx, const mg_grid* z, const mg_grid* s, int relu, mg_grid* out, mg_grid* pooled);
+/* `pooled` (nullable): also writes maxpool2x2_ceil(out) -- the operand the next stage's coarser
+ * neighbour gathers (rnmg.lua:54-60), produced here so the conv's loader stays a pure copy */
+
+/* per-channel (sum, sumsq) of a stored grid accumulated into bn_sums[2*C] (fp64, caller zeroes):
+ * the statistics pass of nn.SpatialBatchNormalization when the conv epilogue did not fuse it */
+int mg_bn_stats(mg_ctx* ctx, const mg_grid* y, double* bn_sums);
+/* cudaMemsetAsync(ptr, 0, bytes) on the context stream (graph-capturable zeroing of sums/loss) */
+int mg_memset_zero(mg_ctx* ctx, void* ptr, size_t bytes);
 
 /* out[..., c_offset + c] = maxpool2x2_ceil(T(in))[..., c]  (mgPool, rnmg.lua:191-224);
  * argmax (nullable, int32 [N][Ho][Wo][C]) receives the flat y*W+x index, 0-based */
@@ -172,6 +180,13 @@ int mg_bce_forward_backward(mg_ctx* ctx, const mg_grid* x, const float* target_n
 /* nn.Sigmoid alone: prob_nchw = sigmoid(T(x)); backward dx = grad_out * p * (1-p) */
 int mg_sigmoid_forward(mg_ctx* ctx, const mg_grid* x, float* prob_nchw);
 int mg_sigmoid_backward(mg_ctx* ctx, const float* prob_nchw, const float* grad_out_nchw, mg_grid* dx);
+/* nn.ClassNLLCriterion (sizeAverage) on log-probabilities [N][C]: loss += -mean logprob[n][t[n]]
+ * (caller zeroes); grad_out[N][C] (nullable) = -gscale/N at the target, 0 elsewhere */
+int mg_nll_criterion(mg_ctx* ctx, const float* logprob, const int32_t* target, int32_t N, int32_t C,
+                     float* loss, float* grad_out, float gscale);
+/* nn.BCECriterion (sizeAverage, eps 1e-12) on probabilities, `count` elements */
+int mg_bce_criterion(mg_ctx* ctx, const float* prob, const float* target, int64_t count,
+                     float* loss, float* grad_prob, float gscale);
 /* optim.sgd on a flat fp32 vector: g += wd*w; v = first ? g : mu*v+g; w -= lr*v */
 int mg_sgd_step(mg_ctx* ctx, float* w, const float* g, float* v, int64_t n,
                 float lr, float momentum, float wd, int first);

@@ -3,6 +3,7 @@
 // arg-max / upsample / shortcut), criteria and SGD.  One thread per (pixel, channel) with the
 // channel index fastest, so a warp touches 32 consecutive channels of one NHWC pixel row.
 #include "common.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -76,6 +77,61 @@ __global__ void residual_kernel(GridV<T> z, GridV<T> s, int has_s, int relu, T* 
     if (relu) v = fmaxf(v, 0.f);
   }
   mg_st(out + i, v);
+}
+
+// same, one thread per (2x2 output block, channel): also writes maxpool2x2_ceil(out)
+template <typename T>
+__global__ void residual_pool_kernel(GridV<T> z, GridV<T> s, int has_s, int relu, T* __restrict__ out, int out_cp,
+                                     T* __restrict__ pooled, int p_cp, int Hp, int Wp) {
+  int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x;
+  int64_t total = (int64_t)z.N * Hp * Wp * out_cp;
+  if (i >= total) return;
+  int c = i % out_cp; int64_t q = i / out_cp;
+  int px = q % Wp; q /= Wp; int py = q % Hp; int n = q / Hp;
+  float best = -INFINITY;
+  for (int dy = 0; dy < 2; ++dy)
+    for (int dx = 0; dx < 2; ++dx) {
+      int y = 2 * py + dy, x = 2 * px + dx;
+      if (y >= z.H || x >= z.W) continue;
+      int64_t p = ((int64_t)n * z.H + y) * z.W + x;
+      float v = 0.f;
+      if (c < z.C) {
+        v = mg_ld(z.data + p * z.Cp + c);
+        if (z.scale) v = mg_xform(v, z.scale[c], z.shift[c], z.relu);
+        if (has_s && c < s.C) {
+          float sv = mg_ld(s.data + p * s.Cp + c);
+          if (s.scale) sv = mg_xform(sv, s.scale[c], s.shift[c], s.relu);
+          v += sv;
+        }
+        if (relu) v = fmaxf(v, 0.f);
+      }
+      T r; mg_st(&r, v);
+      out[p * out_cp + c] = r;
+      float vr = mg_ld(&r);   // pool the stored (rounded) value: what a later gather would read
+      if (vr > best || vr != vr) best = vr;
+    }
+  if (c < p_cp) mg_st(pooled + (((int64_t)n * Hp + py) * Wp + px) * p_cp + c, c < z.C ? best : 0.f);
+}
+
+// per-channel sum / sum of squares of a stored grid
+template <typename T>
+__global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ y, int cp, int C, int64_t P, int pix_per_block,
+                                                       double* sums) {
+  const int cl = threadIdx.x % 32, lane = threadIdx.x / 32;
+  const int c = blockIdx.y * 32 + cl;
+  const int64_t p0 = (int64_t)blockIdx.x * pix_per_block, p1 = min(P, p0 + pix_per_block);
+  float s = 0.f, s2 = 0.f;
+  if (c < C)
+    for (int64_t p = p0 + lane; p < p1; p += 8) { float v = mg_ld(y + p * cp + c); s += v; s2 = fmaf(v, v, s2); }
+  __shared__ float red[2][8][33];
+  red[0][lane][cl] = s; red[1][lane][cl] = s2;
+  __syncthreads();
+  if (lane == 0 && c < C) {
+    float a = 0.f, b = 0.f;
+    for (int l = 0; l < 8; ++l) { a += red[0][l][cl]; b += red[1][l][cl]; }
+    atomicAdd(sums + c, (double)a);
+    atomicAdd(sums + C + c, (double)b);
+  }
 }
 
 // ---------------------------------------------------------------- pooling -----------
@@ -261,14 +317,15 @@ __global__ void bn_bwd_coef_kernel(const double* sums, int64_t count, int C, int
 }
 
 template <typename T>
-__global__ void bn_bwd_apply_kernel(const T* __restrict__ xraw, int x_cp, T* __restrict__ d, int d_cp, int C,
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ xraw, int x_cp, const T* d, int d_cp, T* out, int o_cp, int C,
                                     int64_t P, const float* __restrict__ coef) {
   int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x;
-  if (i >= P * d_cp) return;
-  int c = i % d_cp; int64_t pix = i / d_cp;
-  if (c >= C) return;
-  float v = fmaf(coef[c], mg_ld(d + i), fmaf(coef[d_cp + c], mg_ld(xraw + pix * x_cp + c), coef[2 * d_cp + c]));
-  mg_st(d + i, v);
+  if (i >= P * o_cp) return;
+  int c = i % o_cp; int64_t pix = i / o_cp;
+  float v = 0.f;
+  if (c < C)
+    v = fmaf(coef[c], mg_ld(d + pix * d_cp + c), fmaf(coef[d_cp + c], mg_ld(xraw + pix * x_cp + c), coef[2 * d_cp + c]));
+  mg_st(out + i, v);
 }
 
 // ---------------------------------------------------------------- criteria ----------
@@ -373,15 +430,42 @@ int mg_bn_finalize(mg_ctx* ctx, const double* bn_sums, int64_t count, int32_t C,
   return MG_OK;
 }
 
-int mg_residual_forward(mg_ctx* ctx, const mg_grid* z, const mg_grid* s, int relu, mg_grid* out) {
+int mg_residual_forward(mg_ctx* ctx, const mg_grid* z, const mg_grid* s, int relu, mg_grid* out, mg_grid* pooled) {
   if (!ctx || !z || !out) return MG_ERR_INVALID_ARG;
   MG_REQUIRE(ctx, out->N == z->N && out->H == z->H && out->W == z->W && out->C == z->C, MG_ERR_SHAPE, "residual: out shape");
   if (s) MG_REQUIRE(ctx, s->N == z->N && s->H == z->H && s->W == z->W && s->C <= z->C, MG_ERR_SHAPE,
                     "residual: shortcut %dx%dx%d vs %dx%dx%d", s->H, s->W, s->C, z->H, z->W, z->C);
+  if (pooled) {
+    int Hp = (z->H + 1) / 2, Wp = (z->W + 1) / 2;
+    MG_REQUIRE(ctx, pooled->N == z->N && pooled->H == Hp && pooled->W == Wp && pooled->C == z->C && pooled->Cp <= out->Cp,
+               MG_ERR_SHAPE, "residual: pooled shape");
+    int64_t total = (int64_t)z->N * Hp * Wp * out->Cp;
+    MG_DISPATCH(ctx, residual_pool_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>(make_view<T>(*z), s ? make_view<T>(*s) : make_view<T>(*z),
+                                                                                  s != nullptr, relu, (T*)out->data, out->Cp,
+                                                                                  (T*)pooled->data, pooled->Cp, Hp, Wp););
+    MG_CHECK_LAUNCH(ctx);
+    return MG_OK;
+  }
   int64_t total = (int64_t)z->N * z->H * z->W * out->Cp;
   MG_DISPATCH(ctx, residual_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>(make_view<T>(*z), s ? make_view<T>(*s) : make_view<T>(*z),
                                                                            s != nullptr, relu, (T*)out->data, out->Cp););
   MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int mg_bn_stats(mg_ctx* ctx, const mg_grid* y, double* bn_sums) {
+  if (!ctx || !y || !bn_sums) return MG_ERR_INVALID_ARG;
+  int64_t P = (int64_t)y->N * y->H * y->W;
+  int ppb = (int)std::max<int64_t>(64, mg_cdiv(P, (int64_t)ctx->num_sms * 8));
+  dim3 grid((unsigned)mg_cdiv(P, ppb), (unsigned)mg_cdiv(y->C, 32));
+  MG_DISPATCH(ctx, bn_stats_kernel<T><<<grid, 256, 0, ctx->stream>>>((const T*)y->data, y->Cp, y->C, P, ppb, bn_sums););
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int mg_memset_zero(mg_ctx* ctx, void* ptr, size_t bytes) {
+  if (!ctx || !ptr) return MG_ERR_INVALID_ARG;
+  MG_CUDA(ctx, cudaMemsetAsync(ptr, 0, bytes, ctx->stream));
   return MG_OK;
 }
 
@@ -474,16 +558,18 @@ int mg_grad_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid*
   return MG_OK;
 }
 
-int mg_bn_backward(mg_ctx* ctx, const mg_grid* xraw, mg_grid* d, const double* bn_sums, int64_t count, const float* gamma,
-                   const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta, float gscale,
-                   float* coef_ws) {
-  if (!ctx || !xraw || !d || !bn_sums || !save_mean || !save_invstd || !coef_ws) return MG_ERR_INVALID_ARG;
+int mg_bn_backward(mg_ctx* ctx, const mg_grid* xraw, const mg_grid* d, mg_grid* out, const double* bn_sums, int64_t count,
+                   const float* gamma, const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta,
+                   float gscale, float* coef_ws) {
+  if (!ctx || !xraw || !d || !out || !bn_sums || !save_mean || !save_invstd || !coef_ws) return MG_ERR_INVALID_ARG;
   MG_REQUIRE(ctx, d->N == xraw->N && d->H == xraw->H && d->W == xraw->W && d->C == xraw->C, MG_ERR_SHAPE, "bn_backward: shape");
+  MG_REQUIRE(ctx, out->N == d->N && out->H == d->H && out->W == d->W && out->C == d->C, MG_ERR_SHAPE, "bn_backward: out shape");
   bn_bwd_coef_kernel<<<(unsigned)mg_cdiv(d->Cp, 128), 128, 0, ctx->stream>>>(bn_sums, count, d->C, d->Cp, gamma, save_mean, save_invstd,
                                                                    dgamma, dbeta, gscale, coef_ws);
   MG_CHECK_LAUNCH(ctx);
   int64_t P = (int64_t)d->N * d->H * d->W;
-  MG_DISPATCH(ctx, bn_bwd_apply_kernel<T><<<GRID1(P * d->Cp), EB, 0, ctx->stream>>>((const T*)xraw->data, xraw->Cp, (T*)d->data, d->Cp, d->C, P, coef_ws););
+  MG_DISPATCH(ctx, bn_bwd_apply_kernel<T><<<GRID1(P * out->Cp), EB, 0, ctx->stream>>>((const T*)xraw->data, xraw->Cp, (const T*)d->data, d->Cp,
+                                                                                      (T*)out->data, out->Cp, d->C, P, coef_ws););
   MG_CHECK_LAUNCH(ctx);
   return MG_OK;
 }
@@ -512,6 +598,158 @@ int mg_bce_forward_backward(mg_ctx* ctx, const mg_grid* x, const float* target_n
 int mg_sgd_step(mg_ctx* ctx, float* w, const float* g, float* v, int64_t n, float lr, float momentum, float wd, int first) {
   if (!ctx || !w || !g || !v) return MG_ERR_INVALID_ARG;
   sgd_kernel<<<GRID1(n), EB, 0, ctx->stream>>>(w, g, v, n, lr, momentum, wd, first);
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- module-level head ops
+namespace {
+
+// nn.LogSoftMax over the channel dim of an N x 1 x 1 x C grid, one block per sample
+template <typename T>
+__global__ void logsoftmax_fwd_kernel(const T* __restrict__ logits, int C, int ld, float* __restrict__ logprob) {
+  int n = blockIdx.x;
+  const T* row = logits + (size_t)n * ld;
+  __shared__ float red[32];
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) m = fmaxf(m, mg_ld(row + c));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = m;
+  __syncthreads();
+  m = red[0];
+  for (int w = 1; w < blockDim.x / 32; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float s = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s += expf(mg_ld(row + c) - m);
+  s = warp_sum(s);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int w = 0; w < blockDim.x / 32; ++w) s += red[w];
+  float lse = m + logf(s);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) logprob[(size_t)n * C + c] = mg_ld(row + c) - lse;
+}
+
+// dlogits = grad_out - exp(logprob) * sum_c grad_out
+template <typename T>
+__global__ void logsoftmax_bwd_kernel(const float* __restrict__ logprob, const float* __restrict__ go, int C,
+                                      T* __restrict__ dlogits, int ld) {
+  int n = blockIdx.x;
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s += go[(size_t)n * C + c];
+  s = warp_sum(s);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int w = 0; w < blockDim.x / 32; ++w) s += red[w];
+  for (int c = threadIdx.x; c < ld; c += blockDim.x) {
+    float v = 0.f;
+    if (c < C) v = go[(size_t)n * C + c] - expf(logprob[(size_t)n * C + c]) * s;
+    mg_st(dlogits + (size_t)n * ld + c, v);
+  }
+}
+
+__global__ void nll_criterion_kernel(const float* __restrict__ logprob, const int32_t* __restrict__ target, int N, int C,
+                                     float* loss, float* grad_out, float gscale) {
+  int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x;
+  if (i >= (int64_t)N * C) return;
+  int c = i % C, n = i / C;
+  bool hit = target[n] == c;
+  if (grad_out) grad_out[i] = hit ? -gscale / (float)N : 0.f;
+  if (hit && loss) atomicAdd(loss, -logprob[i] / (float)N);
+}
+
+__global__ void bce_criterion_kernel(const float* __restrict__ prob, const float* __restrict__ target, int64_t count,
+                                     float* loss, float* grad, float gscale) {
+  int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x;
+  float l = 0.f;
+  if (i < count) {
+    const float eps = 1e-12f;
+    float p = prob[i], t = target[i];
+    l = -(logf(p + eps) * t + logf(1.f - p + eps) * (1.f - t)) / (float)count;
+    if (grad) grad[i] = -gscale * (t - p) / ((1.f - p + eps) * (p + eps)) / (float)count;
+  }
+  l = warp_sum(l);
+  if (loss && threadIdx.x % 32 == 0 && l != 0.f) atomicAdd(loss, l);
+}
+
+template <typename T>
+__global__ void sigmoid_fwd_kernel(GridV<T> x, float* __restrict__ prob) {
+  int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x;
+  int64_t total = (int64_t)x.N * x.C * x.H * x.W;
+  if (i >= total) return;
+  int xx = i % x.W; int64_t p = i / x.W;
+  int y = p % x.H; p /= x.H; int c = p % x.C; int n = p / x.C;
+  prob[i] = 1.f / (1.f + expf(-x.at(n, y, xx, c)));
+}
+
+template <typename T>
+__global__ void sigmoid_bwd_kernel(const float* __restrict__ prob, const float* __restrict__ go, T* __restrict__ dx,
+                                   int N, int C, int Cp, int H, int W) {
+  int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x;
+  int64_t total = (int64_t)N * H * W * Cp;
+  if (i >= total) return;
+  int c = i % Cp; int64_t p = i / Cp;
+  int x = p % W; p /= W; int y = p % H; int n = p / H;
+  float v = 0.f;
+  if (c < C) {
+    size_t j = (((size_t)n * C + c) * H + y) * W + x;
+    float pr = prob[j];
+    v = go[j] * pr * (1.f - pr);
+  }
+  mg_st(dx + i, v);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mg_logsoftmax_forward(mg_ctx* ctx, const mg_grid* logits, float* logprob) {
+  if (!ctx || !logits || !logprob) return MG_ERR_INVALID_ARG;
+  MG_REQUIRE(ctx, logits->H == 1 && logits->W == 1, MG_ERR_SHAPE, "logsoftmax: logits must be N x 1 x 1 x C");
+  MG_DISPATCH(ctx, logsoftmax_fwd_kernel<T><<<logits->N, 256, 0, ctx->stream>>>((const T*)logits->data, logits->C, logits->Cp, logprob););
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int mg_logsoftmax_backward(mg_ctx* ctx, const float* logprob, const float* grad_out, mg_grid* dlogits) {
+  if (!ctx || !logprob || !grad_out || !dlogits) return MG_ERR_INVALID_ARG;
+  MG_DISPATCH(ctx, logsoftmax_bwd_kernel<T><<<dlogits->N, 256, 0, ctx->stream>>>(logprob, grad_out, dlogits->C, (T*)dlogits->data, dlogits->Cp););
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int mg_nll_criterion(mg_ctx* ctx, const float* logprob, const int32_t* target, int32_t N, int32_t C, float* loss,
+                     float* grad_out, float gscale) {
+  if (!ctx || !logprob || !target || N < 1 || C < 1) return MG_ERR_INVALID_ARG;
+  nll_criterion_kernel<<<GRID1((int64_t)N * C), EB, 0, ctx->stream>>>(logprob, target, N, C, loss, grad_out, gscale);
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int mg_bce_criterion(mg_ctx* ctx, const float* prob, const float* target, int64_t count, float* loss, float* grad_prob,
+                     float gscale) {
+  if (!ctx || !prob || !target || count < 1) return MG_ERR_INVALID_ARG;
+  bce_criterion_kernel<<<GRID1(count), EB, 0, ctx->stream>>>(prob, target, count, loss, grad_prob, gscale);
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int mg_sigmoid_forward(mg_ctx* ctx, const mg_grid* x, float* prob_nchw) {
+  if (!ctx || !x || !prob_nchw) return MG_ERR_INVALID_ARG;
+  int64_t total = (int64_t)x->N * x->C * x->H * x->W;
+  MG_DISPATCH(ctx, sigmoid_fwd_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>(make_view<T>(*x), prob_nchw););
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int mg_sigmoid_backward(mg_ctx* ctx, const float* prob_nchw, const float* grad_out_nchw, mg_grid* dx) {
+  if (!ctx || !prob_nchw || !grad_out_nchw || !dx) return MG_ERR_INVALID_ARG;
+  int64_t total = (int64_t)dx->N * dx->H * dx->W * dx->Cp;
+  MG_DISPATCH(ctx, sigmoid_bwd_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>(prob_nchw, grad_out_nchw, (T*)dx->data, dx->N, dx->C, dx->Cp, dx->H, dx->W););
   MG_CHECK_LAUNCH(ctx);
   return MG_OK;
 }

@@ -1,0 +1,135 @@
+"""Plan executor: lowers a module graph for one input shape, owns every device buffer, and
+replays the plan's C-ABI calls for forward and backward on the caller's CUDA stream.
+
+PyTorch is used for device memory (torch.zeros as the allocator), streams and, in
+dataparallel.py, torch.distributed rendezvous -- all arithmetic is libmgconv's.
+"""
+import os
+import torch
+
+from . import ffi, lower, ops
+
+_PRECISION = {"bf16": (ffi.MG_BF16, torch.bfloat16), "fp32": (ffi.MG_F32, torch.float32)}
+_IMPL = {"auto": ffi.MG_IMPL_AUTO, "simt": ffi.MG_IMPL_SIMT, "tcgen05": ffi.MG_IMPL_TCGEN05}
+_crit_ctx = {}
+
+
+def criterion_ctx(t):
+    """context used by the criteria (dtype independent kernels), one per device"""
+    if not t.is_cuda:
+        raise ffi.MGError("criterion inputs must be CUDA tensors: the multigrid hot path has no CPU fallback")
+    dev = t.device.index
+    if dev not in _crit_ctx:
+        _crit_ctx[dev] = ffi.Context(dev, 0, ffi.MG_F32)
+    _crit_ctx[dev].set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    return _crit_ctx[dev]
+
+
+def _flatten(x):
+    if isinstance(x, (list, tuple)):
+        out = []
+        for e in x:
+            out.extend(_flatten(e))
+        return out
+    return [x]
+
+
+class Engine:
+    def __init__(self, model, input):
+        inputs = _flatten(input)
+        for t in inputs:
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dim() == 4):
+                raise ffi.MGError("forward() needs 4-D CUDA tensors (NCHW); there is no CPU fallback -- "
+                                  "call model:cuda() and move the inputs with put2GPU first")
+        self.model = model
+        self.device = inputs[0].device
+        self.key = (tuple(input.shape) if isinstance(input, torch.Tensor) else tuple(tuple(t.shape) for t in inputs),
+                    self.device.index)
+        precision = getattr(model, "precision", os.environ.get("MGCONV_PRECISION", "bf16"))
+        self.dtype, self.elt = _PRECISION[precision]
+        self.ctx = ffi.Context(self.device.index, torch.cuda.current_stream(self.device).cuda_stream, self.dtype)
+        impl = getattr(model, "impl", os.environ.get("MGCONV_IMPL", "auto"))
+        self.ctx.set_impl(_IMPL[impl])
+        self.use_packed = self.dtype == ffi.MG_BF16 and impl != "simt"
+        self.training = True
+        self.gscale = 1.0
+        self.bytes = 0
+        self.on_param_done = None
+        for m in model.listModules():
+            for _, w, _ in m.own_parameters():
+                if w.device != self.device:
+                    raise ffi.MGError(f"{m.typename} parameters live on {w.device}, inputs on {self.device}: call model:cuda()")
+
+        shapes = [tuple(t.shape) for t in inputs]
+        b, out = lower.trace_model(model, shapes if isinstance(input, (list, tuple)) else shapes[0],
+                                   bool(getattr(model, "needInputGrad", False)))
+        self.out_struct = self._wrap_outputs(out, b)
+        self.plan = b
+        self.input_ops = [o for o in b.ops if isinstance(o, ops.InputOp)]
+        self.conv_ops = [o for o in b.ops if isinstance(o, ops.ConvOp)]
+        for o in b.ops:
+            o.setup_fwd(self)
+        self._bwd_ready = False
+
+    def _wrap_outputs(self, out, b):
+        if isinstance(out, (list, tuple)):
+            return [self._wrap_outputs(e, b) for e in out]
+        if isinstance(out, lower.OutVal):
+            return out.op
+        if isinstance(out, lower.CatVal):
+            out = b.as_tensor(out)
+        if isinstance(out, lower.TVal):
+            return b.emit(ops.ExportOp(out.spec))
+        raise NotImplementedError(f"model output of kind {type(out).__name__}")
+
+    def alloc(self, shape, dtype=None):
+        t = torch.zeros(shape, dtype=dtype or self.elt, device=self.device)
+        self.bytes += t.numel() * t.element_size()
+        return t
+
+    def param_done(self, mod):
+        if self.on_param_done is not None:
+            self.on_param_done(mod)
+
+    def _bind_stream(self):
+        self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- execution ------------------------------------------------------------------------
+    def pack_weights(self):
+        for o in self.conv_ops:
+            o.pack(self)
+
+    def forward(self, input, training=True):
+        self._bind_stream()
+        self.training = training
+        for op, t in zip(self.input_ops, _flatten(input)):
+            op.src = t.contiguous().float()
+        self.pack_weights()
+        for o in self.plan.ops:
+            o.fwd(self)
+        return self._results(self.out_struct)
+
+    def _results(self, s):
+        if isinstance(s, list):
+            return [self._results(e) for e in s]
+        return s.result
+
+    def _setup_bwd(self):
+        for o in reversed(self.plan.ops):
+            o.setup_bwd(self)
+        self._bwd_ready = True
+
+    def backward(self, gradOutput, scale=1.0):
+        self._bind_stream()
+        if not self._bwd_ready:
+            self._setup_bwd()
+            self.pack_weights()  # transposed images for dgrad were allocated just now
+        self.gscale = float(scale)
+        for op, g in zip(_flatten(self.out_struct), _flatten(gradOutput)):
+            op.grad_out = g.contiguous().float()
+        for o in reversed(self.plan.ops):
+            o.bwd(self)
+        gi = [op.grad_nchw for op in self.input_ops]
+        if all(g is None for g in gi):
+            return None
+        return gi if len(gi) > 1 else gi[0]

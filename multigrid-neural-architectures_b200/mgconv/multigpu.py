@@ -1,0 +1,214 @@
+"""Data parallelism: the four global helpers of multigpu.lua (makeDataParallel:81,
+saveDataParallel:105, loadDataParallel:137, loadAndRemoveDPT:150) on a process-per-GPU design.
+
+The reference wraps the model in nn.DataParallelTable(1, true, true): one process, one Lua
+thread per GPU, batch split ceil(B/nGPU) along dim 1, nccl.reduce of the flat gradient to GPU 1
+after backward, SGD on GPU 1, nccl.bcast of the parameters (pipelines/standard/train.lua:163-169).
+Here every rank owns a full replica and its shard of the batch; the flat gradient is cut into
+buckets in reverse layer order and each bucket is all-reduced (ncclAllReduce through libmgconv,
+over NVLink) on a side stream as soon as the last wgrad that writes into it has been enqueued,
+overlapping the rest of backward; every rank then applies the same SGD step, so no broadcast is
+needed after initialisation.  BN statistics stay per replica, as in the reference (multigpu.lua:38-41).
+"""
+import ctypes as C
+import os
+import torch
+import torch.distributed as dist
+
+from . import ffi
+from .ffi import ptr
+
+BUCKET_BYTES = int(os.environ.get("MGCONV_BUCKET_MB", "16")) << 20
+
+
+def shard_range(B, nGPU, rank):
+    """rows of a global batch owned by `rank`: DataParallelTable splits dim 1 into ceil(B/nGPU) chunks"""
+    per = -(-B // nGPU)
+    lo = min(B, rank * per)
+    return lo, min(B, lo + per)
+
+
+def plan_buckets(sizes, bucket_bytes=BUCKET_BYTES, elt=4):
+    """cut the flat vector (parameter sizes in module order) into contiguous buckets, built from the
+    END of the vector because backward produces gradients in reverse module order.
+    Returns [(offset, count, first_param_index)] in launch order; a bucket is complete when the
+    gradient of parameter `first_param_index` (its lowest-indexed member) has been written."""
+    buckets, end, count = [], sum(sizes), 0
+    off = end
+    for i in range(len(sizes) - 1, -1, -1):
+        off -= sizes[i]
+        count += sizes[i]
+        if count * elt >= bucket_bytes or i == 0:
+            buckets.append((off, count, i))
+            count = 0
+    return buckets
+
+
+class DataParallel:
+    """stands where nn.DataParallelTable stood: same module protocol, local shard in, local
+    outputs out; gradients are global sums divided by nothing -- the criterion already averages
+    over the *global* batch through gscale = 1/nranks (equal shards)."""
+    typename = "nn.DataParallelTable"
+
+    def __init__(self, model, nGPU, group=None):
+        self.model = model
+        self.nGPU = nGPU
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if self.world != nGPU:
+            raise ffi.MGError(f"makeDataParallel: -nGPU {nGPU} but {self.world} ranks were launched "
+                              "(one process per GPU: torchrun --nproc-per-node nGPU)")
+        self.flat = self.gflat = None
+        self.buckets = []
+        self._comm_ready = False
+        self._owner = {}
+        self.needsSync = False
+        self.train = True
+
+    # ---- module protocol passthrough ----------------------------------------------------
+    def __getattr__(self, name):
+        return getattr(self.__dict__["model"], name)
+
+    def listModules(self):
+        return self.model.listModules()
+
+    def training(self):
+        self.train = True
+        self.model.training()
+        return self
+
+    def evaluate(self):
+        self.train = False
+        self.model.evaluate()
+        return self
+
+    def getParameters(self):
+        self.flat, self.gflat = self.model.getParameters()
+        sizes, self._owner, idx = [], {}, 0
+        for m in self.model.listModules():
+            for name, w, _ in m.own_parameters():
+                sizes.append(w.numel())
+                self._owner.setdefault(id(m), []).append(idx)
+                idx += 1
+        self.sizes = sizes
+        self.buckets = plan_buckets(sizes)
+        self._trigger = {first: (off, cnt) for off, cnt, first in self.buckets}
+        self.syncParameters()
+        return self.flat, self.gflat
+
+    def syncParameters(self):
+        """nccl.bcast(root = GPU 1) of the flat parameter vector (train.lua:166-168): needed once,
+        after initialisation / checkpoint load; afterwards every rank takes identical steps"""
+        if self.world > 1 and self.flat is not None:
+            if self.flat.is_cuda and dist.get_backend(self.group) == "gloo":
+                tmp = self.flat.cpu()
+                dist.broadcast(tmp, 0, group=self.group)
+                self.flat.copy_(tmp)
+            else:
+                dist.broadcast(self.flat, 0, group=self.group)
+        self.needsSync = False
+
+    def _init_comm(self, eng):
+        if self._comm_ready or self.world == 1:
+            return
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            ffi_rc = ffi.lib.mg_comm_unique_id(C.c_void_p(uid.data_ptr()))
+            if ffi_rc != 0:
+                raise ffi.MGError("mg_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        if dist.get_backend(self.group) == "nccl":
+            u = uid.cuda()
+            dist.broadcast(u, 0, group=self.group)
+            uid = u.cpu()
+        else:
+            dist.broadcast(uid, 0, group=self.group)
+        eng.ctx.call("mg_comm_init", self.rank, self.world, C.c_void_p(uid.data_ptr()))
+        self._comm_ready = True
+
+    def forward(self, input):
+        out = self.model.forward(input)
+        eng = self.model._engine
+        if self.world > 1 and eng.on_param_done is None and self.gflat is not None:
+            self._init_comm(eng)
+            eng.on_param_done = self._param_done
+        return out
+
+    def backward(self, input, gradOutput, scale=1.0):
+        self._done = set()
+        gi = self.model.backward(input, gradOutput, scale / self.world)
+        if self.world > 1 and self.gflat is not None:
+            self.model._engine.ctx.call("mg_allreduce_wait")
+        return gi
+
+    def _param_done(self, mod):
+        """called by the engine right after the wgrad / BN-backward of `mod` was enqueued"""
+        for idx in self._owner.get(id(mod), ()):
+            self._done.add(idx)
+        eng = self.model._engine
+        for off, cnt, first in self.buckets:
+            if first in self._done and ("b", first) not in self._done:
+                # every parameter of the bucket has index >= first and was produced earlier in backward
+                if all(i in self._done for i in range(first, self._bucket_end(first))):
+                    self._done.add(("b", first))
+                    eng.ctx.call("mg_allreduce_launch", ptr(self.gflat[off:off + cnt]), cnt, 0)
+
+    def _bucket_end(self, first):
+        firsts = sorted(f for _, _, f in self.buckets)
+        i = firsts.index(first)
+        return firsts[i + 1] if i + 1 < len(firsts) else len(self.sizes)
+
+
+def makeDataParallel(model, nGPU, net=None):
+    """multigpu.lua:81-103"""
+    if nGPU > 1:
+        if not dist.is_initialized():
+            raise ffi.MGError("makeDataParallel(nGPU > 1) needs torch.distributed to be initialised: launch one "
+                              "process per GPU (python -m torch.distributed.run --nproc-per-node nGPU ...)")
+        return DataParallel(model, nGPU)
+    return model
+
+
+def _state(model):
+    m = model.model if isinstance(model, DataParallel) else model
+    st = []
+    for mod in m.listModules():
+        d = {k: v.detach().cpu().clone() for k, v in vars(mod).items()
+             if isinstance(v, torch.Tensor) and not k.startswith("grad") and not k.startswith("_")}
+        st.append((mod.typename, d))
+    return st
+
+
+def saveDataParallel(filename, model):
+    """multigpu.lua:105-135: persist replica 1 with its buffers cleared.  The module graph is
+    rebuilt by the builder; what is stored are the per-module tensors in listModules() order."""
+    if not dist.is_initialized() or dist.get_rank() == 0:
+        torch.save({"format": "mgconv-b200/1", "modules": _state(model)}, filename)
+
+
+def _load_into(model, filename):
+    blob = torch.load(filename, map_location="cpu")
+    mods = (model.model if isinstance(model, DataParallel) else model).listModules()
+    if len(mods) != len(blob["modules"]):
+        raise ffi.MGError(f"{filename}: {len(blob['modules'])} modules stored, model has {len(mods)}")
+    for mod, (tn, d) in zip(mods, blob["modules"]):
+        if tn != mod.typename:
+            raise ffi.MGError(f"{filename}: module type {tn} does not match {mod.typename}")
+        for k, v in d.items():
+            getattr(mod, k).copy_(v)
+    return model
+
+
+def loadDataParallel(filename, nGPU, net, opt):
+    """multigpu.lua:137-148: rebuild through the net's createModel, load, wrap for nGPU"""
+    o = type(opt)(opt)
+    o["nGPU"] = 1
+    model = _load_into(net.createModel(o), filename)
+    return makeDataParallel(model, nGPU, net)
+
+
+def loadAndRemoveDPT(filename, net, opt):
+    """multigpu.lua:150-160: load a checkpoint as a plain single-GPU module"""
+    o = type(opt)(opt)
+    o["nGPU"] = 1
+    return _load_into(net.createModel(o), filename)

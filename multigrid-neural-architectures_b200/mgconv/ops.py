@@ -1,0 +1,479 @@
+"""Plan ops: each owns its device buffers and the pre-built C structs of its libmgconv calls.
+
+setup_fwd runs in forward order (allocate activations), setup_bwd in reverse order (so that by
+the time a tensor's producer plans its gradient, every consumer has registered the grid it will
+write its contribution to).  Gradients are combined in *gather form* (mg_grad_combine): each
+tensor reads its consumers' gradient grids through the routing that consumer applied (same /
+2x2 arg-max / 2x2 block sum / 3x3-s2 arg-max), so there are no atomics and the summation order
+is fixed -- ConcatTable's backward-sum (models/ilsvrc/rnmg.lua:53-82,106,140) without scatter.
+"""
+import ctypes as C
+import torch
+
+from . import ffi
+from .ffi import mg_grid, mg_conv_desc, mg_grad_src, ptr, MG_SEG_SAME, MG_SEG_POOL, MG_SEG_UP, MG_SRC_POOL3, MG_MAX_SRC
+
+
+def cpad(c):
+    return (c + 7) // 8 * 8
+
+
+class TSpec:
+    """a materialised NHWC activation tensor of the plan"""
+
+    def __init__(self, idx, N, C, H, W, name, needs_grad=True):
+        self.idx, self.N, self.C, self.H, self.W = idx, N, C, H, W
+        self.Cp = cpad(C)
+        self.name = name
+        self.needs_grad = needs_grad
+        self.producer = None
+        self.pooled = None   # companion TSpec = maxpool2x2_ceil(self)
+        self.srcs = []       # Src records registered by consumers (backward)
+        self.buf = None
+        self.G = None        # mg_grid of the gradient w.r.t. this tensor, set by the producer's backward plan
+
+    def grid(self, buf=None, scale=None, shift=None, relu=0):
+        b = self.buf if buf is None else buf
+        return mg_grid(b.data_ptr(), None if scale is None else scale.data_ptr(),
+                       None if shift is None else shift.data_ptr(), relu, self.N, self.H, self.W, self.C, self.Cp)
+
+    def shape(self):
+        return (self.N, self.H, self.W, self.Cp)
+
+
+class Src:
+    """one gradient contribution: grid `buf` [N,H,W,Cp] read at channel offset c_off through `mode`"""
+
+    def __init__(self, buf, H, W, C, Cp, c_off, mode):
+        self.buf, self.H, self.W, self.C, self.Cp, self.c_off, self.mode = buf, H, W, C, Cp, c_off, mode
+
+
+class Combine:
+    """gradient of tensor t = sum of its registered sources (optionally x ReLU mask, + BN sums)"""
+
+    def __init__(self, E, t, relu_mask=False, bn_x=None, sums=None, private=False):
+        self.E, self.t = E, t
+        srcs = t.srcs
+        if len(srcs) > MG_MAX_SRC:
+            raise NotImplementedError(f"{t.name}: {len(srcs)} gradient sources > MG_MAX_SRC")
+        s0 = srcs[0] if len(srcs) == 1 else None
+        self.noop = False
+        self.alias = (s0 is not None and s0.mode == MG_SEG_SAME and s0.c_off == 0 and s0.Cp == t.Cp
+                      and not relu_mask and sums is None and not private)
+        if self.alias:
+            self.buf = s0.buf
+            return
+        self.buf = E.alloc(t.shape())
+        self.noop = len(srcs) == 0  # unused output (e.g. grids dropped by SelectTable(1)): gradient stays zero
+        self.x = t.grid()
+        self.bn_x = bn_x.grid() if bn_x is not None else None
+        self.arr = (mg_grad_src * max(1, len(srcs)))()
+        for i, s in enumerate(srcs):
+            self.arr[i].g = mg_grid(s.buf.data_ptr(), None, None, 0, t.N, s.H, s.W, s.C, s.Cp)
+            self.arr[i].c_offset = s.c_off
+            self.arr[i].mode = s.mode
+        self.n = len(srcs)
+        self.relu_mask = int(relu_mask)
+        self.sums = sums
+        self.d = t.grid(self.buf)
+
+    def grid(self):
+        return self.t.grid(self.buf)
+
+    def run(self):
+        if self.alias or self.noop:
+            return
+        self.E.ctx.call("mg_grad_combine", C.byref(self.x), self.relu_mask,
+                        C.byref(self.bn_x) if self.bn_x is not None else None, self.n, self.arr,
+                        C.byref(self.d), ptr(self.sums))
+
+
+def plan_companion_grad(E, x, p):
+    """route the gradient of p = maxpool2x2_ceil(x) into x (arg-max recomputed from x in the combine).
+    Sources of p that read it at its own resolution compose with the pooling directly; anything else
+    (p up-sampled or pooled again by its consumer) needs p's gradient materialised first."""
+    if p is None or not p.needs_grad or not x.needs_grad:
+        return None
+    if all(s.mode == MG_SEG_SAME for s in p.srcs):
+        for s in p.srcs:
+            x.srcs.append(Src(s.buf, s.H, s.W, s.C, s.Cp, s.c_off, MG_SEG_POOL))
+        return None
+    comb = Combine(E, p)
+    x.srcs.append(Src(comb.buf, p.H, p.W, p.C, p.Cp, 0, MG_SEG_POOL))
+    return comb
+
+
+class Op:
+    def setup_fwd(self, E): pass
+    def setup_bwd(self, E): pass
+    def fwd(self, E): pass
+    def bwd(self, E): pass
+
+
+class InputOp(Op):
+    def __init__(self, out):
+        self.out = out
+        out.producer = self
+        self.src = None   # NCHW fp32 torch tensor, set by the engine per call
+        self.comb = None
+        self.grad_nchw = None
+
+    def setup_fwd(self, E):
+        self.out.buf = E.alloc(self.out.shape())
+        self.g = self.out.grid()
+
+    def fwd(self, E):
+        E.ctx.call("mg_import_nchw", ptr(self.src), C.byref(self.g))
+
+    def setup_bwd(self, E):
+        if self.out.needs_grad:
+            self.comb = Combine(E, self.out)
+            self.grad_nchw = torch.empty((self.out.N, self.out.C, self.out.H, self.out.W), dtype=torch.float32, device=E.device)
+            self.dg = self.comb.grid()
+
+    def bwd(self, E):
+        if self.comb is not None:
+            self.comb.run()
+            E.ctx.call("mg_export_nchw", C.byref(self.dg), ptr(self.grad_nchw))
+
+
+class AvgPoolOp(Op):
+    """cudnn.SpatialAveragePooling(r,r,r,r) of the input image (ilsvrc/rnmg.lua:175-177)"""
+
+    def __init__(self, inp, r, out):
+        self.inp, self.r, self.out = inp, r, out
+        out.producer = self
+
+    def setup_fwd(self, E):
+        self.out.buf = E.alloc(self.out.shape())
+        self.gi, self.go = self.inp.grid(), self.out.grid()
+
+    def fwd(self, E):
+        E.ctx.call("mg_avgpool_forward", C.byref(self.gi), self.r, C.byref(self.go))
+
+
+class ConvOp(Op):
+    """gather(segments) -> k x k convolution (+bias); raw output y and, when a BatchNorm follows,
+    the per-channel (sum, sumsq) of y.  ResampleConcat + cudnn.SpatialConvolution
+    (ilsvrc/rnmg.lua:41-89 + 26/36)."""
+
+    def __init__(self, b, mod, segs, H, W, name):
+        self.mod, self.segs, self.H, self.W, self.name = mod, segs, H, W, name
+        self.k, self.stride, self.pad, self.Cout = mod.kW, mod.dW, mod.padW, mod.nOutputPlane
+        self.Ho = (H + 2 * self.pad - self.k) // self.stride + 1
+        self.Wo = (W + 2 * self.pad - self.k) // self.stride + 1
+        self.y = b.new_tensor(self.Cout, self.Ho, self.Wo, name + ".y")
+        self.y.producer = self
+        self.apply = None
+        self.want_stats = False
+        self.sums = None
+        self.ycomb = None
+
+    def setup_fwd(self, E):
+        d = mg_conv_desc()
+        d.n_seg = len(self.segs)
+        for i, (t, m) in enumerate(self.segs):
+            d.seg[i] = t.grid()
+            d.seg_mode[i] = m
+        d.ksize, d.stride, d.pad, d.Cout, d.H, d.W = self.k, self.stride, self.pad, self.Cout, self.H, self.W
+        self.desc = d
+        self.y.buf = E.alloc(self.y.shape())
+        self.yg = self.y.grid()
+        if self.want_stats:
+            self.sums = E.alloc((2 * self.Cout,), torch.float64)
+        self.wpack = self.wpack_t = None
+        nb = ffi.lib.mg_conv_packed_bytes(C.byref(d), 0) if E.use_packed else 0
+        if nb:
+            self.wpack = E.alloc((nb,), torch.uint8)
+        self.Ccat = sum(t.C for t, _ in self.segs)
+        self.CcatP = sum(t.Cp for t, _ in self.segs)
+
+    def pack(self, E):
+        if self.wpack is not None:
+            E.ctx.call("mg_conv_pack_weights", C.byref(self.desc), ptr(self.mod.weight), ptr(self.wpack), 0)
+        if self.wpack_t is not None:
+            E.ctx.call("mg_conv_pack_weights", C.byref(self.desc), ptr(self.mod.weight), ptr(self.wpack_t), 1)
+
+    def fwd(self, E):
+        if self.sums is not None:
+            E.ctx.call("mg_memset_zero", ptr(self.sums), self.sums.numel() * 8)
+        E.ctx.call("mg_conv_forward", C.byref(self.desc), ptr(self.mod.weight), ptr(self.wpack), ptr(self.mod.bias),
+                   C.byref(self.yg), ptr(self.sums))
+
+    def setup_bwd(self, E):
+        if self.apply is None:  # plain convolution (Linear head): gradient of y comes straight from its consumers
+            self.ycomb = Combine(E, self.y)
+            self.y.G = self.ycomb.grid()
+        self.needs_dgrad = any(t.needs_grad for t, _ in self.segs)
+        self.dcat = None
+        if self.needs_dgrad:
+            self.dcat = E.alloc((self.y.N, self.H, self.W, self.CcatP))
+            self.dcat_g = mg_grid(self.dcat.data_ptr(), None, None, 0, self.y.N, self.H, self.W, self.CcatP, self.CcatP)
+            off = 0
+            for t, m in self.segs:
+                if t.needs_grad:
+                    t.srcs.append(Src(self.dcat, self.H, self.W, self.CcatP, self.CcatP, off, m))
+                off += t.Cp
+            nb = ffi.lib.mg_conv_packed_bytes(C.byref(self.desc), 1) if E.use_packed else 0
+            if nb:
+                self.wpack_t = E.alloc((nb,), torch.uint8)
+
+    def bwd(self, E):
+        if self.ycomb is not None:
+            self.ycomb.run()
+        g = self.y.G
+        E.ctx.call("mg_conv_backward_weight", C.byref(self.desc), C.byref(g), ptr(self.mod.gradWeight),
+                   ptr(self.mod.gradBias), E.gscale)
+        if self.needs_dgrad:
+            E.ctx.call("mg_conv_backward_data", C.byref(self.desc), ptr(self.mod.weight), ptr(self.wpack_t),
+                       C.byref(g), C.byref(self.dcat_g))
+        E.param_done(self.mod)
+
+
+class ApplyOp(Op):
+    """epilogue pass of a convolution: out = relu?( BN(y) + shortcut[c < C_s] ), plus the pooled
+    companion of out when a coarser neighbour gathers it.  SpatialBatchNormalization -> [ReLU] or
+    -> CAddTable(true) with Identity / nn.Padding shortcut -> [ReLU] (ilsvrc/rnmg.lua:13-39,140-154)."""
+
+    def __init__(self, conv, bn, relu, res, out):
+        self.conv, self.bn, self.relu, self.res, self.out = conv, bn, relu, res, out
+        conv.apply = self
+        conv.want_stats = bn is not None
+        out.producer = self
+        self.pooled = None
+
+    def setup_fwd(self, E):
+        t, y = self.out, self.conv.y
+        t.buf = E.alloc(t.shape())
+        self.og = t.grid()
+        self.pg = None
+        if self.pooled is not None:
+            self.pooled.buf = E.alloc(self.pooled.shape())
+            self.pg = self.pooled.grid()
+        self.rg = self.res.grid() if self.res is not None else None
+        if self.bn is not None:
+            self.scale, self.shift = E.alloc((y.Cp,), torch.float32), E.alloc((y.Cp,), torch.float32)
+            self.mean, self.invstd = E.alloc((y.Cp,), torch.float32), E.alloc((y.Cp,), torch.float32)
+            self.zg = y.grid(scale=self.scale, shift=self.shift)
+        else:
+            self.zg = y.grid()
+        self.count = y.N * y.H * y.W
+
+    def fwd(self, E):
+        bn = self.bn
+        if bn is not None:
+            E.ctx.call("mg_bn_finalize", ptr(self.conv.sums), self.count, self.out.C, self.out.Cp, ptr(bn.weight), ptr(bn.bias),
+                       ptr(bn.running_mean), ptr(bn.running_var), bn.eps, bn.momentum, int(E.training),
+                       ptr(self.scale), ptr(self.shift), ptr(self.mean), ptr(self.invstd))
+        E.ctx.call("mg_residual_forward", C.byref(self.zg), C.byref(self.rg) if self.rg is not None else None,
+                   int(self.relu), C.byref(self.og), C.byref(self.pg) if self.pg is not None else None)
+
+    def setup_bwd(self, E):
+        t, y = self.out, self.conv.y
+        self.pc = plan_companion_grad(E, t, self.pooled)
+        self.dsums = E.alloc((2 * t.C,), torch.float64) if self.bn is not None else None
+        self.comb = Combine(E, t, relu_mask=self.relu, bn_x=y if self.bn is not None else None, sums=self.dsums,
+                            private=self.bn is not None)
+        D = self.comb.buf
+        if self.res is not None and self.res.needs_grad:
+            self.res.srcs.append(Src(D, t.H, t.W, t.C, t.Cp, 0, MG_SEG_SAME))
+        if self.bn is not None:
+            G = E.alloc(t.shape()) if self.res is not None else D   # the shortcut still reads D
+            self.coef = E.alloc((3 * t.Cp,), torch.float32)
+            self.dg, self.gg = t.grid(D), t.grid(G)
+            self.yraw = y.grid()
+            y.G = self.gg
+        else:
+            y.G = t.grid(D)
+
+    def bwd(self, E):
+        if self.pc is not None:
+            self.pc.run()
+        if self.dsums is not None:
+            E.ctx.call("mg_memset_zero", ptr(self.dsums), self.dsums.numel() * 8)
+        self.comb.run()
+        bn = self.bn
+        if bn is not None:
+            E.ctx.call("mg_bn_backward", C.byref(self.yraw), C.byref(self.dg), C.byref(self.gg), ptr(self.dsums), self.count,
+                       ptr(bn.weight), ptr(self.mean), ptr(self.invstd), ptr(bn.gradWeight), ptr(bn.gradBias),
+                       E.gscale, ptr(self.coef))
+            E.param_done(bn)
+
+
+class PoolOp(Op):
+    """stand-alone SpatialMaxPooling(2,2,2,2):ceil() (mgPool, ilsvrc/rnmg.lua:191-224) when the
+    producer of `inp` is not an apply pass that could write the companion itself"""
+
+    def __init__(self, inp, out):
+        self.inp, self.out = inp, out
+        out.producer = self
+
+    def setup_fwd(self, E):
+        self.out.buf = E.alloc(self.out.shape())
+        self.gi, self.go = self.inp.grid(), self.out.grid()
+
+    def fwd(self, E):
+        E.ctx.call("mg_pool_forward", C.byref(self.gi), C.byref(self.go), 0, None)
+
+    def setup_bwd(self, E):
+        self.pc = plan_companion_grad(E, self.inp, self.out)
+
+    def bwd(self, E):
+        if self.pc is not None:
+            self.pc.run()
+
+
+class Pool3Op(Op):
+    """SpatialMaxPooling(3,3,2,2,1,1) of the ImageNet stem (ilsvrc/rnmg.lua:183)"""
+
+    def __init__(self, inp, out):
+        self.inp, self.out = inp, out
+        out.producer = self
+
+    def setup_fwd(self, E):
+        self.out.buf = E.alloc(self.out.shape())
+        self.gi, self.go = self.inp.grid(), self.out.grid()
+
+    def fwd(self, E):
+        E.ctx.call("mg_pool3s2_forward", C.byref(self.gi), C.byref(self.go))
+
+    def setup_bwd(self, E):
+        t = self.out
+        self.comb = None
+        if self.inp.needs_grad:
+            self.comb = Combine(E, t)
+            self.inp.srcs.append(Src(self.comb.buf, t.H, t.W, t.C, t.Cp, 0, MG_SRC_POOL3))
+
+    def bwd(self, E):
+        if self.comb is not None:
+            self.comb.run()
+
+
+class CatOp(Op):
+    """JoinTable(2) materialised because a shortcut needs the concatenation as one tensor
+    (first residual unit after an isConcat mgPool, ilsvrc/rnmg.lua:133-137,207)"""
+
+    def __init__(self, parts, out):
+        self.parts, self.out = parts, out
+        out.producer = self
+
+    def setup_fwd(self, E):
+        self.out.buf = E.alloc(self.out.shape())
+        self.go = self.out.grid()
+        self.gp = [p.grid() for p in self.parts]
+
+    def fwd(self, E):
+        off = 0
+        for p, g in zip(self.parts, self.gp):
+            E.ctx.call("mg_copy_channels", C.byref(g), C.byref(self.go), off)
+            off += p.C
+
+    def setup_bwd(self, E):
+        t = self.out
+        self.comb = None
+        if t.needs_grad:
+            self.comb = Combine(E, t)
+            off = 0
+            for p in self.parts:
+                if p.needs_grad:
+                    p.srcs.append(Src(self.comb.buf, t.H, t.W, t.C, t.Cp, off, MG_SEG_SAME))
+                off += p.C
+
+    def bwd(self, E):
+        if self.comb is not None:
+            self.comb.run()
+
+
+class GlobalAvgOp(Op):
+    """SelectTable(1) -> cudnn.SpatialAveragePooling(7,7,1,1) on the 7x7 grid (ilsvrc/rnmg.lua:281-282)"""
+
+    def __init__(self, inp, out):
+        self.inp, self.out = inp, out
+        out.producer = self
+
+    def setup_fwd(self, E):
+        self.out.buf = E.alloc(self.out.shape())
+        self.gi, self.go = self.inp.grid(), self.out.grid()
+
+    def fwd(self, E):
+        E.ctx.call("mg_global_avgpool_forward", C.byref(self.gi), C.byref(self.go))
+
+    def setup_bwd(self, E):
+        self.comb = Combine(E, self.out)
+        self.din = E.alloc(self.inp.shape())
+        self.dg_out, self.dg_in = self.comb.grid(), self.inp.grid(self.din)
+        self.inp.srcs.append(Src(self.din, self.inp.H, self.inp.W, self.inp.C, self.inp.Cp, 0, MG_SEG_SAME))
+
+    def bwd(self, E):
+        self.comb.run()
+        E.ctx.call("mg_global_avgpool_backward", C.byref(self.dg_out), C.byref(self.dg_in))
+
+
+class LogSoftMaxOp(Op):
+    def __init__(self, inp):
+        self.inp = inp
+
+    def setup_fwd(self, E):
+        self.result = torch.empty((self.inp.N, self.inp.C), dtype=torch.float32, device=E.device)
+        self.gi = self.inp.grid()
+
+    def fwd(self, E):
+        E.ctx.call("mg_logsoftmax_forward", C.byref(self.gi), ptr(self.result))
+
+    def setup_bwd(self, E):
+        self.dl = E.alloc(self.inp.shape())
+        self.dlg = self.inp.grid(self.dl)
+        self.inp.srcs.append(Src(self.dl, 1, 1, self.inp.C, self.inp.Cp, 0, MG_SEG_SAME))
+        self.grad_out = None
+
+    def bwd(self, E):
+        E.ctx.call("mg_logsoftmax_backward", ptr(self.result), ptr(self.grad_out), C.byref(self.dlg))
+
+
+class SigmoidOp(Op):
+    def __init__(self, inp):
+        self.inp = inp
+
+    def setup_fwd(self, E):
+        t = self.inp
+        self.result = torch.empty((t.N, t.C, t.H, t.W), dtype=torch.float32, device=E.device)
+        self.gi = t.grid()
+
+    def fwd(self, E):
+        E.ctx.call("mg_sigmoid_forward", C.byref(self.gi), ptr(self.result))
+
+    def setup_bwd(self, E):
+        t = self.inp
+        self.dx = E.alloc(t.shape())
+        self.dxg = t.grid(self.dx)
+        t.srcs.append(Src(self.dx, t.H, t.W, t.C, t.Cp, 0, MG_SEG_SAME))
+        self.grad_out = None
+
+    def bwd(self, E):
+        E.ctx.call("mg_sigmoid_backward", ptr(self.result), ptr(self.grad_out), C.byref(self.dxg))
+
+
+class ExportOp(Op):
+    """a raw activation grid returned at the Torch boundary as NCHW fp32 (unit tests of single
+    mg stages; whole networks end in LogSoftMax / Sigmoid)"""
+
+    def __init__(self, inp):
+        self.inp = inp
+
+    def setup_fwd(self, E):
+        t = self.inp
+        self.result = torch.empty((t.N, t.C, t.H, t.W), dtype=torch.float32, device=E.device)
+        self.gi = t.grid()
+
+    def fwd(self, E):
+        E.ctx.call("mg_export_nchw", C.byref(self.gi), ptr(self.result))
+
+    def setup_bwd(self, E):
+        t = self.inp
+        self.dx = E.alloc(t.shape())
+        self.dxg = t.grid(self.dx)
+        t.srcs.append(Src(self.dx, t.H, t.W, t.C, t.Cp, 0, MG_SEG_SAME))
+        self.grad_out = None
+
+    def bwd(self, E):
+        E.ctx.call("mg_import_nchw", ptr(self.grad_out), C.byref(self.dxg))

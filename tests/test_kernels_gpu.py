@@ -1,0 +1,386 @@
+"""GPU parity tests of every libmgconv entry point against the CPU oracle (oracle/nn_ops.py),
+called through the C ABI exactly as the LuaJIT/ctypes host does.
+
+Bars (BASELINE.json north_star): pool arg-max indices and up-sample gathers bit-exact;
+floating point within rel 1e-4 in fp32 mode and rel 2e-2 in bf16 (fp32 accumulate) mode.
+Inputs are rounded to bf16-representable values first, so both sides read identical numbers.
+"""
+import ctypes as C
+import numpy as np
+import pytest
+import torch
+
+from oracle import nn_ops as O
+from mgconv import ffi
+from mgconv.ffi import ptr, mg_grad_src, MG_SEG_SAME, MG_SEG_POOL, MG_SEG_UP, MG_SRC_POOL3
+from util import Grid, conv_desc, dev, rel_err, max_rel, bf16_round, TOL, TDT
+
+pytestmark = pytest.mark.gpu
+DTYPES = [ffi.MG_F32, ffi.MG_BF16]
+rng = np.random.default_rng(7)
+
+
+@pytest.fixture(scope="module", params=DTYPES, ids=["fp32", "bf16"])
+def ctx(request):
+    c = ffi.Context(0, torch.cuda.current_stream().cuda_stream, request.param)
+    yield c
+    c.sync()
+    c.close()
+
+
+def rnd(*shape):
+    return bf16_round(rng.standard_normal(shape))
+
+
+# ---------------------------------------------------------------- layout
+def test_import_export_roundtrip(ctx):
+    x = rnd(2, 5, 7, 6)
+    g = Grid(ctx.dtype, 2, 5, 7, 6)
+    ctx.call("mg_import_nchw", ptr(dev(x)), C.byref(g.g()))
+    assert np.array_equal(g.nchw(), x)
+    assert not g.pad_channels().any()
+    out = torch.empty(2, 5, 7, 6, device="cuda")
+    g.affine(np.full(5, 2.0), np.full(5, -1.0), True)
+    ctx.call("mg_export_nchw", C.byref(g.g()), ptr(out))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), np.maximum(2 * x - 1, 0).astype(np.float32))
+
+
+# ---------------------------------------------------------------- pooling / up-sampling (bit-exact)
+@pytest.mark.parametrize("H,W", [(8, 8), (7, 7), (5, 9), (1, 1), (2, 3), (56, 56)])
+def test_pool2x2_ceil_values_and_argmax_bit_exact(ctx, H, W):
+    x = rnd(2, 11, H, W)
+    x[0, 0, :min(2, H), :min(2, W)] = 1.5  # ties: the first maximum of the row-major scan must win
+    x[1, 3] = 0.25                          # a whole plane of ties
+    y, idx = O.maxpool_forward(x)
+    gi = Grid(ctx.dtype, 2, 11, H, W, x)
+    go = Grid(ctx.dtype, 2, 11, y.shape[2], y.shape[3])
+    am = torch.full((2, y.shape[2], y.shape[3], 11), -1, dtype=torch.int32, device="cuda")
+    ctx.call("mg_pool_forward", C.byref(gi.g()), C.byref(go.g()), 0, ptr(am))
+    assert np.array_equal(go.nchw(), y)
+    assert np.array_equal(am.permute(0, 3, 1, 2).cpu().numpy(), idx)
+
+
+def test_pool_with_channel_offset_and_copy_channels(ctx):
+    """mgPool isConcat: JoinTable(2){pool(x_{n-1}), x_n} (models/ilsvrc/rnmg.lua:201-207)"""
+    a, b = rnd(2, 6, 6, 6), rnd(2, 5, 3, 3)
+    ga, gb = Grid(ctx.dtype, 2, 6, 6, 6, a), Grid(ctx.dtype, 2, 5, 3, 3, b)
+    out = Grid(ctx.dtype, 2, 11, 3, 3)
+    ctx.call("mg_pool_forward", C.byref(ga.g()), C.byref(out.g()), 0, None)
+    ctx.call("mg_copy_channels", C.byref(gb.g()), C.byref(out.g()), 6)
+    ref = np.concatenate([O.maxpool_forward(a)[0], b], axis=1)
+    assert np.array_equal(out.nchw(), ref)
+
+
+def test_stem_pool3x3s2p1(ctx):
+    x = rnd(2, 9, 12, 12)
+    y, _ = O.maxpool_forward(x, 3, 2, 1, ceil_mode=False)
+    gi, go = Grid(ctx.dtype, 2, 9, 12, 12, x), Grid(ctx.dtype, 2, 9, 6, 6)
+    ctx.call("mg_pool3s2_forward", C.byref(gi.g()), C.byref(go.g()))
+    assert np.array_equal(go.nchw(), y)
+
+
+def test_avgpool_and_global_avgpool(ctx):
+    x = rnd(2, 3, 8, 8)
+    gi, go = Grid(ctx.dtype, 2, 3, 8, 8, x), Grid(ctx.dtype, 2, 3, 2, 2)
+    ctx.call("mg_avgpool_forward", C.byref(gi.g()), 4, C.byref(go.g()))
+    assert max_rel(go.nchw(), O.avgpool_forward(x, 4)) <= TOL[ctx.dtype]
+    x = rnd(3, 10, 7, 7)
+    gi, go = Grid(ctx.dtype, 3, 10, 7, 7, x), Grid(ctx.dtype, 3, 10, 1, 1)
+    ctx.call("mg_global_avgpool_forward", C.byref(gi.g()), C.byref(go.g()))
+    assert max_rel(go.nchw(), O.avgpool_forward(x, 7, 1)) <= TOL[ctx.dtype]
+    d = rnd(3, 10, 1, 1)
+    gd, gin = Grid(ctx.dtype, 3, 10, 1, 1, d), Grid(ctx.dtype, 3, 10, 7, 7)
+    ctx.call("mg_global_avgpool_backward", C.byref(gd.g()), C.byref(gin.g()))
+    assert max_rel(gin.nchw(), O.avgpool_backward(d, x.shape, 7, 1)) <= TOL[ctx.dtype]
+
+
+# ---------------------------------------------------------------- the multigrid convolution
+def _mg_inputs(N, cs, H):
+    """finer (2H), same (H), coarser (H/2) grids"""
+    return rnd(N, cs[0], 2 * H, 2 * H), rnd(N, cs[1], H, H), rnd(N, cs[2], H // 2, H // 2)
+
+
+def _oracle_cat(f, s, c):
+    pooled, idx = O.maxpool_forward(f)
+    return np.concatenate([pooled, s, O.upsample_forward(c)], axis=1), idx
+
+
+CONV_CASES = [  # N, (C_finer, C_same, C_coarser), H, Cout, k
+    (2, (5, 7, 3), 8, 6, 3),
+    (2, (16, 8, 8), 14, 24, 3),     # odd finer size is impossible here; 14 -> finer 28, coarser 7
+    (1, (64, 32, 16), 28, 32, 3),   # R-MG-34 block-1 grid 2 (models/ilsvrc/rnmg.lua:250)
+    (2, (8, 12, 4), 4, 10, 1),      # 1x1 kernel of the coarsest CIFAR grids (models/cifar/nmg.lua:152-153)
+    (3, (40, 20, 10), 2, 20, 3),    # 2x2 grid: every tap hits the border
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+def test_mgconv_forward_dgrad_wgrad(ctx, case, impl):
+    if impl == "auto" and ctx.dtype != ffi.MG_BF16:
+        pytest.skip("tcgen05 path is bf16 only")
+    N, cs, H, Cout, k = case
+    pad = 0 if k == 1 else 1
+    f, s, c = _mg_inputs(N, cs, H)
+    cat, idx = _oracle_cat(f, s, c)
+    w = bf16_round(rng.standard_normal((Cout, sum(cs), k, k)) * 0.2)
+    b = bf16_round(rng.standard_normal(Cout) * 0.1)
+    y_ref = O.conv_forward(cat, w, b, 1, pad)
+    ctx.set_impl(ffi.MG_IMPL_SIMT if impl == "simt" else ffi.MG_IMPL_AUTO)
+    gf, gs, gc = Grid(ctx.dtype, N, cs[0], 2 * H, 2 * H, f), Grid(ctx.dtype, N, cs[1], H, H, s), Grid(ctx.dtype, N, cs[2], H // 2, H // 2, c)
+    # the tcgen05 path gathers by pure copies: its POOL operand is the pooled companion tensor
+    if impl == "auto":
+        gp = Grid(ctx.dtype, N, cs[0], H, H)
+        ctx.call("mg_pool_forward", C.byref(gf.g()), C.byref(gp.g()), 0, None)
+        d = conv_desc([gp, gs, gc], [MG_SEG_SAME, MG_SEG_SAME, MG_SEG_UP], k, 1, pad, Cout, H, H)
+    else:
+        d = conv_desc([gf, gs, gc], [MG_SEG_POOL, MG_SEG_SAME, MG_SEG_UP], k, 1, pad, Cout, H, H)
+    wd, bd = dev(w), dev(b)
+    wpack = wpack_t = None
+    nb = ffi.lib.mg_conv_packed_bytes(C.byref(d), 0) if impl == "auto" else 0
+    if nb:
+        wpack = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+        wpack_t = torch.zeros(ffi.lib.mg_conv_packed_bytes(C.byref(d), 1), dtype=torch.uint8, device="cuda")
+        ctx.call("mg_conv_pack_weights", C.byref(d), ptr(wd), ptr(wpack), 0)
+        ctx.call("mg_conv_pack_weights", C.byref(d), ptr(wd), ptr(wpack_t), 1)
+    gy = Grid(ctx.dtype, N, Cout, H, H)
+    sums = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
+    ctx.call("mg_conv_forward", C.byref(d), ptr(wd), ptr(wpack), ptr(bd), C.byref(gy.g()), ptr(sums))
+    tol = TOL[ctx.dtype]
+    y = gy.nchw()
+    assert max_rel(y, y_ref) <= tol, max_rel(y, y_ref)
+    assert not gy.pad_channels().any()
+    # BatchNorm statistics accumulated by the conv
+    cnt = N * H * H
+    sm = sums.cpu().numpy()
+    assert np.allclose(sm[:Cout] / cnt, y_ref.mean(axis=(0, 2, 3)), atol=tol * np.abs(y_ref).max())
+    assert np.allclose(sm[Cout:] / cnt, (y_ref ** 2).mean(axis=(0, 2, 3)), rtol=4 * tol, atol=tol)
+
+    # backward: dcat (gradient w.r.t. the concatenated input), dW, dbias
+    g = rnd(N, Cout, H, H)
+    gcat_ref, gw_ref, gb_ref = O.conv_backward(cat, w, g, 1, pad)
+    gg = Grid(ctx.dtype, N, Cout, H, H, g)
+    cps = [gf.Cp, gs.Cp, gc.Cp]
+    dcat = Grid(ctx.dtype, N, sum(cps), H, H, Cp=sum(cps))
+    ctx.call("mg_conv_backward_data", C.byref(d), ptr(wd), ptr(wpack_t), C.byref(gg.g()), C.byref(dcat.g()))
+    dc = dcat.nchw()
+    got = np.concatenate([dc[:, 0:cs[0]], dc[:, cps[0]:cps[0] + cs[1]], dc[:, cps[0] + cps[1]:cps[0] + cps[1] + cs[2]]], axis=1)
+    assert max_rel(got, gcat_ref) <= tol, max_rel(got, gcat_ref)
+    dw = torch.zeros_like(wd)
+    db = torch.zeros_like(bd)
+    ctx.call("mg_conv_backward_weight", C.byref(d), C.byref(gg.g()), ptr(dw), ptr(db), 1.0)
+    ctx.call("mg_conv_backward_weight", C.byref(d), C.byref(gg.g()), ptr(dw), ptr(db), 0.5)  # accGradParameters accumulates
+    torch.cuda.synchronize()
+    assert max_rel(dw.cpu().numpy(), 1.5 * gw_ref) <= tol, max_rel(dw.cpu().numpy(), 1.5 * gw_ref)
+    assert max_rel(db.cpu().numpy(), 1.5 * gb_ref) <= tol
+    ctx.set_impl(ffi.MG_IMPL_AUTO)
+
+
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+def test_stem_conv7x7_stride2(ctx, impl):
+    """cudnn.SpatialConvolution(3, nOP, 7,7, 2,2, 3,3) of the ImageNet stem (ilsvrc/rnmg.lua:180)"""
+    if impl == "auto" and ctx.dtype != ffi.MG_BF16:
+        pytest.skip("tcgen05 path is bf16 only")
+    x = rnd(2, 3, 20, 20)
+    w = bf16_round(rng.standard_normal((16, 3, 7, 7)) * 0.1)
+    b = bf16_round(rng.standard_normal(16) * 0.1)
+    y_ref = O.conv_forward(x, w, b, 2, 3)
+    ctx.set_impl(ffi.MG_IMPL_SIMT if impl == "simt" else ffi.MG_IMPL_AUTO)
+    gx = Grid(ctx.dtype, 2, 3, 20, 20, x)
+    d = conv_desc([gx], [MG_SEG_SAME], 7, 2, 3, 16, 20, 20)
+    wd, bd = dev(w), dev(b)
+    wpack = None
+    nb = ffi.lib.mg_conv_packed_bytes(C.byref(d), 0) if impl == "auto" else 0
+    if nb:
+        wpack = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+        ctx.call("mg_conv_pack_weights", C.byref(d), ptr(wd), ptr(wpack), 0)
+    gy = Grid(ctx.dtype, 2, 16, 10, 10)
+    ctx.call("mg_conv_forward", C.byref(d), ptr(wd), ptr(wpack), ptr(bd), C.byref(gy.g()), None)
+    assert max_rel(gy.nchw(), y_ref) <= TOL[ctx.dtype]
+    g = rnd(2, 16, 10, 10)
+    _, gw_ref, gb_ref = O.conv_backward(x, w, g, 2, 3)
+    gg = Grid(ctx.dtype, 2, 16, 10, 10, g)
+    dw, db = torch.zeros_like(wd), torch.zeros_like(bd)
+    ctx.call("mg_conv_backward_weight", C.byref(d), C.byref(gg.g()), ptr(dw), ptr(db), 1.0)
+    torch.cuda.synchronize()
+    assert max_rel(dw.cpu().numpy(), gw_ref) <= TOL[ctx.dtype]
+    assert max_rel(db.cpu().numpy(), gb_ref) <= TOL[ctx.dtype]
+    ctx.set_impl(ffi.MG_IMPL_AUTO)
+
+
+def test_conv_shape_errors_are_reported_not_fatal(ctx):
+    """JoinTable would raise on inconsistent sizes in the reference; here: status + message"""
+    a, b = Grid(ctx.dtype, 1, 4, 8, 8), Grid(ctx.dtype, 1, 4, 5, 5)
+    d = conv_desc([a, b], [MG_SEG_SAME, MG_SEG_UP], 3, 1, 1, 4, 8, 8)
+    y = Grid(ctx.dtype, 1, 4, 8, 8)
+    w = torch.zeros(4, 8, 3, 3, device="cuda")
+    with pytest.raises(ffi.MGError, match="UP seg"):
+        ctx.call("mg_conv_forward", C.byref(d), ptr(w), None, None, C.byref(y.g()), None)
+
+
+# ---------------------------------------------------------------- BatchNorm + epilogue
+@pytest.mark.parametrize("eps", [1e-5, 1e-3])
+def test_bn_finalize_apply_residual_and_backward(ctx, eps):
+    N, Cc, H = 3, 12, 6
+    x = bf16_round(rnd(N, Cc, H, H) * 2 + 1)
+    gamma, beta = rng.random(Cc) + 0.5, rng.standard_normal(Cc) * 0.1
+    rm, rv = np.zeros(Cc), np.ones(Cc)
+    y_ref, mean, invstd = O.bn_forward_train(x, gamma, beta, eps, rm, rv)
+    sc = rnd(N, 8, H, H)  # zero-padded shortcut with fewer channels (nn.Padding, ilsvrc/rnmg.lua:16)
+    out_ref = O.relu_forward(y_ref + O.pad_channels(sc, Cc))
+    gx = Grid(ctx.dtype, N, Cc, H, H, x)
+    sums = torch.zeros(2 * Cc, dtype=torch.float64, device="cuda")
+    ctx.call("mg_bn_stats", C.byref(gx.g()), ptr(sums))
+    drm, drv = dev(rm), dev(rv)
+    scale, shift = torch.zeros(gx.Cp, device="cuda"), torch.zeros(gx.Cp, device="cuda")
+    smean, sinv = torch.zeros(gx.Cp, device="cuda"), torch.zeros(gx.Cp, device="cuda")
+    dgam, dbet = dev(gamma), dev(beta)
+    ctx.call("mg_bn_finalize", ptr(sums), N * H * H, Cc, gx.Cp, ptr(dgam), ptr(dbet), ptr(drm), ptr(drv), eps, 0.1, 1,
+             ptr(scale), ptr(shift), ptr(smean), ptr(sinv))
+    torch.cuda.synchronize()
+    assert np.allclose(drm.cpu().numpy(), rm, atol=1e-5) and np.allclose(drv.cpu().numpy(), rv, rtol=1e-4)  # unbiased running var
+    gx.scale, gx.shift = scale, shift
+    gsc, gout = Grid(ctx.dtype, N, 8, H, H, sc), Grid(ctx.dtype, N, Cc, H, H)
+    gpool = Grid(ctx.dtype, N, Cc, H // 2, H // 2)
+    ctx.call("mg_residual_forward", C.byref(gx.g()), C.byref(gsc.g()), 1, C.byref(gout.g()), C.byref(gpool.g()))
+    tol = TOL[ctx.dtype]
+    out = gout.nchw()
+    assert max_rel(out, out_ref) <= tol
+    # the pooled companion is exactly the 2x2 max of what was stored
+    assert np.array_equal(gpool.nchw(), O.maxpool_forward(out)[0])
+
+    # backward: mask by the stored output, reduce (sum d, sum d*x), BN backward
+    go = rnd(N, Cc, H, H)
+    d_ref = O.relu_backward(out, go)
+    gxr, dg_ref, db_ref = O.bn_backward_train(x, d_ref, gamma, mean, invstd)
+    ggo, gd, gres = Grid(ctx.dtype, N, Cc, H, H, go), Grid(ctx.dtype, N, Cc, H, H), Grid(ctx.dtype, N, Cc, H, H)
+    src = (mg_grad_src * 1)()
+    src[0].g, src[0].c_offset, src[0].mode = ggo.g(), 0, MG_SEG_SAME
+    dsums = torch.zeros(2 * Cc, dtype=torch.float64, device="cuda")
+    xraw = Grid(ctx.dtype, N, Cc, H, H, x)
+    ctx.call("mg_grad_combine", C.byref(gout.g()), 1, C.byref(xraw.g()), 1, src, C.byref(gd.g()), ptr(dsums))
+    assert np.array_equal(gd.nchw(), bf16_round(d_ref) if ctx.dtype == ffi.MG_BF16 else d_ref)
+    dgamma, dbeta = torch.zeros(Cc, device="cuda"), torch.zeros(Cc, device="cuda")
+    coef = torch.zeros(3 * gx.Cp, device="cuda")
+    ctx.call("mg_bn_backward", C.byref(xraw.g()), C.byref(gd.g()), C.byref(gres.g()), ptr(dsums), N * H * H, ptr(dgam),
+             ptr(smean), ptr(sinv), ptr(dgamma), ptr(dbeta), 1.0, ptr(coef))
+    torch.cuda.synchronize()
+    assert max_rel(gres.nchw(), gxr) <= tol
+    assert max_rel(dgamma.cpu().numpy(), dg_ref) <= tol and max_rel(dbeta.cpu().numpy(), db_ref) <= tol
+    # evaluation mode uses the running statistics
+    ctx.call("mg_bn_finalize", None, N * H * H, Cc, gx.Cp, ptr(dgam), ptr(dbet), ptr(drm), ptr(drv), eps, 0.1, 0,
+             ptr(scale), ptr(shift), None, None)
+    ctx.call("mg_residual_forward", C.byref(gx.g()), None, 0, C.byref(gout.g()), None)
+    assert max_rel(gout.nchw(), O.bn_forward_eval(x, gamma, beta, rm, rv, eps)) <= tol
+
+
+# ---------------------------------------------------------------- gradient routing (bit-exact paths)
+@pytest.mark.parametrize("H", [8, 7])
+def test_grad_combine_routes_through_argmax_and_upsample(ctx, H):
+    """ConcatTable backward-sum of ResampleConcat (ilsvrc/rnmg.lua:53-82): tensor x receives its
+    gradient as the same-scale source of grid i, through the 2x2 arg-max as the pooled source of
+    grid i+1 and as a 2x2 block sum as the up-sampled source of grid i-1."""
+    N, Cc = 2, 6
+    Hc = (H + 1) // 2
+    x = rnd(N, Cc, H, H)
+    x[0, 0, :2, :2] = 0.75  # tie inside a pooling window: only the first max receives gradient
+    g_same = rnd(N, Cc + 4, H, H)          # dcat of conv i: channels [4, 4+Cc)
+    g_pool = rnd(N, Cc, Hc, Hc)            # dcat slice of conv i+1 (coarser)
+    g_up = rnd(N, Cc + 2, 2 * H, 2 * H)    # dcat of conv i-1 (finer): channels [2, 2+Cc)
+    _, idx = O.maxpool_forward(x)
+    ref = g_same[:, 4:4 + Cc] + O.maxpool_backward(g_pool, idx, x.shape) + O.upsample_backward(g_up[:, 2:2 + Cc])
+    gx = Grid(ctx.dtype, N, Cc, H, H, x)
+    a, b, c = Grid(ctx.dtype, N, Cc + 4, H, H, g_same), Grid(ctx.dtype, N, Cc, Hc, Hc, g_pool), Grid(ctx.dtype, N, Cc + 2, 2 * H, 2 * H, g_up)
+    src = (mg_grad_src * 3)()
+    for i, (gr, off, mode) in enumerate([(a, 4, MG_SEG_SAME), (b, 0, MG_SEG_POOL), (c, 2, MG_SEG_UP)]):
+        src[i].g, src[i].c_offset, src[i].mode = gr.g(), off, mode
+    gd = Grid(ctx.dtype, N, Cc, H, H)
+    ctx.call("mg_grad_combine", C.byref(gx.g()), 0, None, 3, src, C.byref(gd.g()), None)
+    got = gd.nchw()
+    assert max_rel(got, ref) <= TOL[ctx.dtype]
+    # routing itself is exact: zero / non-zero pattern of the pooled contribution alone
+    src1 = (mg_grad_src * 1)()
+    src1[0].g, src1[0].c_offset, src1[0].mode = b.g(), 0, MG_SEG_POOL
+    ctx.call("mg_grad_combine", C.byref(gx.g()), 0, None, 1, src1, C.byref(gd.g()), None)
+    assert np.array_equal(gd.nchw(), O.maxpool_backward(g_pool, idx, x.shape))
+
+
+def test_grad_combine_stem_pool3(ctx):
+    x = rnd(2, 5, 12, 12)
+    y, idx = O.maxpool_forward(x, 3, 2, 1, ceil_mode=False)
+    g = rnd(*y.shape)
+    gx, gg, gd = Grid(ctx.dtype, 2, 5, 12, 12, x), Grid(ctx.dtype, 2, 5, 6, 6, g), Grid(ctx.dtype, 2, 5, 12, 12)
+    src = (mg_grad_src * 1)()
+    src[0].g, src[0].c_offset, src[0].mode = gg.g(), 0, MG_SRC_POOL3
+    ctx.call("mg_grad_combine", C.byref(gx.g()), 0, None, 1, src, C.byref(gd.g()), None)
+    assert max_rel(gd.nchw(), O.maxpool_backward(g, idx, x.shape)) <= TOL[ctx.dtype]
+
+
+# ---------------------------------------------------------------- head, criteria, optimiser
+def test_logsoftmax_nll_and_fused(ctx):
+    N, Cc = 6, 37
+    x = rnd(N, Cc, 1, 1)
+    t = rng.integers(0, Cc, N)
+    lp_ref = O.logsoftmax_forward(x.reshape(N, Cc))
+    gl = Grid(ctx.dtype, N, Cc, 1, 1, x)
+    lp = torch.zeros(N, Cc, device="cuda")
+    ctx.call("mg_logsoftmax_forward", C.byref(gl.g()), ptr(lp))
+    torch.cuda.synchronize()
+    assert np.allclose(lp.cpu().numpy(), lp_ref, atol=1e-5)
+    loss = torch.zeros(1, device="cuda")
+    go = torch.zeros(N, Cc, device="cuda")
+    td = dev(t, torch.int32)
+    ctx.call("mg_nll_criterion", ptr(lp), ptr(td), N, Cc, ptr(loss), ptr(go), 1.0)
+    torch.cuda.synchronize()
+    assert np.allclose(loss.item(), O.nll_forward(lp_ref, t), rtol=1e-5)
+    assert np.allclose(go.cpu().numpy(), O.nll_backward(lp_ref, t))
+    dl = Grid(ctx.dtype, N, Cc, 1, 1)
+    ctx.call("mg_logsoftmax_backward", ptr(lp), ptr(go), C.byref(dl.g()))
+    ref = O.logsoftmax_backward(lp_ref, O.nll_backward(lp_ref, t)).reshape(N, Cc, 1, 1)
+    assert max_rel(dl.nchw(), ref) <= TOL[ctx.dtype]
+    # fused LogSoftMax + ClassNLLCriterion
+    loss.zero_()
+    dl2 = Grid(ctx.dtype, N, Cc, 1, 1)
+    ctx.call("mg_nll_forward_backward", C.byref(gl.g()), ptr(td), None, ptr(loss), C.byref(dl2.g()), 1.0)
+    torch.cuda.synchronize()
+    assert np.allclose(loss.item(), O.nll_forward(lp_ref, t), rtol=1e-5)
+    assert max_rel(dl2.nchw(), ref) <= TOL[ctx.dtype]
+
+
+def test_sigmoid_bce(ctx):
+    x = rnd(2, 3, 5, 5)
+    t = (rng.random((2, 3, 5, 5)) > 0.5).astype(np.float64)
+    p_ref = O.sigmoid_forward(x)
+    gx = Grid(ctx.dtype, 2, 3, 5, 5, x)
+    p = torch.zeros(2, 3, 5, 5, device="cuda")
+    ctx.call("mg_sigmoid_forward", C.byref(gx.g()), ptr(p))
+    loss, gp = torch.zeros(1, device="cuda"), torch.zeros_like(p)
+    ctx.call("mg_bce_criterion", ptr(p), ptr(dev(t)), p.numel(), ptr(loss), ptr(gp), 1.0)
+    torch.cuda.synchronize()
+    assert np.allclose(p.cpu().numpy(), p_ref, atol=1e-6)
+    assert np.allclose(loss.item(), O.bce_forward(p_ref, t), rtol=1e-4)
+    assert np.allclose(gp.cpu().numpy(), O.bce_backward(p_ref, t), rtol=1e-3, atol=1e-7)
+    dx = Grid(ctx.dtype, 2, 3, 5, 5)
+    ctx.call("mg_sigmoid_backward", ptr(p), ptr(gp), C.byref(dx.g()))
+    ref = O.bce_backward(p_ref, t) * p_ref * (1 - p_ref)
+    assert max_rel(dx.nchw(), ref) <= max(TOL[ctx.dtype], 1e-3)
+
+
+def test_sgd_step_matches_optim_sgd(ctx):
+    w, st = rng.standard_normal(1000), {}
+    dw, dv = dev(w), torch.zeros(1000, device="cuda")
+    for it in range(3):
+        g = rng.standard_normal(1000)
+        w = O.sgd_step(w, g, st, 0.1, 0.9, 1e-4)
+        ctx.call("mg_sgd_step", ptr(dw), ptr(dev(g)), ptr(dv), 1000, 0.1, 0.9, 1e-4, int(it == 0))
+    torch.cuda.synchronize()
+    assert np.allclose(dw.cpu().numpy(), w, atol=1e-5)
+
+
+def test_launch_counter_counts_our_kernels(ctx):
+    n0 = ctx.launches()
+    g = Grid(ctx.dtype, 1, 3, 4, 4, rnd(1, 3, 4, 4))
+    o = Grid(ctx.dtype, 1, 3, 2, 2)
+    ctx.call("mg_pool_forward", C.byref(g.g()), C.byref(o.g()), 0, None)
+    assert ctx.launches() == n0 + 1
