@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench.py -- R-MG-34 ImageNet-shape training throughput (BASELINE.json metric), one JSON line.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (CUDA hot path)
+    python bench.py --impl reference --gpus N ...            # the reference's CPU path (oracle port)
+
+A "step" is what pipelines/standard/train.lua:trainBatch does between its synchronisations:
+zeroGradParameters -> NETOBJ.ftrain (forward, ClassNLL, backward; models/basic_model.lua:56-62)
+-> NETOBJ.btrain (optim.sgd momentum .9, wd 1e-4, lr .1; 64-66) on `-netType ilsvrc/rnmg -depth 34`,
+synthetic N(0,1) images [B,3,224,224] and uniform labels 1..1000, B = 256 per GPU (weak scaling).
+
+value  : images/s with the batch already resident in HBM (CUDA events, max over ranks).
+e2e    : the same step driven from HOST buffers: pinned-memory H2D copy of images+labels (the
+         reference's put2GPU, utils/utilfuncs.lua:3-30) and a D2H read of the loss, inside the timed region.
+roofline: the implicit-GEMM multigrid convolution kernels (forward, dgrad, wgrad) -- algorithmic
+         FLOPs = 2*MACs*3 of every conv of the plan / their summed CUDA-event time in the timed steps.
+cpu_baseline: the oracle's PyTorch-CPU restatement of the same network (the reference's Torch7 nn
+         path cannot run: no Lua/Torch7 here) on a bounded sample, all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "multigrid-neural-architectures_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "R-MG-34 train images/sec"
+WORKLOAD = "R-MG-34 (ilsvrc/rnmg -depth 34) ImageNet 224x224 synthetic, batch 256/GPU, fwd+NLL+bwd+SGD"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d.get("bf16_tflops_sustained", 1405.9), d.get("hbm_gbs", 6542.1), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        try:
+            p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        self.proc = p
+        for line in p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+            if self.stop_flag:
+                break
+        p.kill()
+
+    def summary(self):
+        self.stop_flag = True
+        time.sleep(0.25)
+        try:
+            self.proc.kill()
+        except Exception:
+            pass
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(batch, steps, warmup):
+    """oracle port of the same network on the host cores (bounded sample)"""
+    import torch
+    from oracle import builders as OB
+    torch.manual_seed(2)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    om = OB.ilsvrc_rnmg(34)
+    opt = torch.optim.SGD(om.parameters(), lr=0.1, momentum=0.9, weight_decay=1e-4)
+    x = torch.randn(batch, 3, 224, 224)
+    t = torch.randint(0, 1000, (batch,))
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=False)
+        loss = torch.nn.functional.nll_loss(om(x), t)
+        loss.backward()
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return {"value": batch / dt, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"R-MG-34 224x224 fp32 PyTorch-CPU oracle, batch {batch}, {steps} timed steps after {warmup} warm-up"}, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, dt = cpu_baseline(args.cpu_batch, max(1, min(args.steps, 3)), 1)
+    line = {"metric": METRIC, "value": cb["value"], "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD, "note": "reference = Torch7 nn CPU path; Torch7 cannot run here, timed as the oracle's "
+                       "PyTorch-CPU restatement on a bounded sample", "sample_batch": args.cpu_batch},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="mgconv")
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU")
+    ap.add_argument("--depth", type=int, default=34)
+    ap.add_argument("--precision", default="bf16")
+    ap.add_argument("--cpu-batch", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from mgconv import builders as B, ffi
+    from mgconv.engine import criterion_ctx
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+
+    torch.manual_seed(2)  # -manualSeed default (opts.lua:23); identical initial weights on every rank
+    net = B.load_net("ilsvrc/rnmg")
+    model = net.createModel(B.Opt(depth=args.depth, nGPU=world))
+    model.precision = args.precision
+    model.cuda()
+    criterion = net.createCriterion()
+    params, grads = model.getParameters()
+    rule = net.trainRule(1, B.Opt())
+    optimState = dict(learningRate=rule["LR"], momentum=0.9, weightDecay=rule["WD"], dampening=0.0, learningRateDecay=0.0)
+
+    Bsz = args.batch
+    g = torch.Generator(device="cpu").manual_seed(100 + rank)
+    host_x = torch.randn(Bsz, 3, 224, 224, generator=g).pin_memory()
+    host_t = torch.randint(1, 1001, (Bsz,), generator=g).pin_memory()
+    dev_x, dev_t = host_x.to(dev), host_t.to(dev)
+    state = {}
+
+    def step(x, t):
+        model.zeroGradParameters()
+
+        def feval(_p):
+            outputs, err = net.ftrain(x, t, model, criterion)
+            state["loss"] = err
+            return err, grads
+        net.btrain(params, feval, optimState)
+
+    def engine():
+        return (model.model if hasattr(model, "model") else model)._engine
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step(dev_x, dev_t)
+    sync_all()
+    eng = engine()
+    cctx = criterion_ctx(params)
+    eng.ctx.call("mg_ctx_profile", 1)
+    l0 = eng.ctx.launches() + cctx.launches()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(dev_x, dev_t)
+    e1.record()
+    sync_all()
+    clocks = sampler.summary()
+    ms = e0.elapsed_time(e1)
+    launches = eng.ctx.launches() + cctx.launches() - l0
+    prof = eng.ctx.profile_read()
+    eng.ctx.call("mg_ctx_profile", 0)
+    if world > 1:
+        tms = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = tms.item()
+    ms_per_step = ms / args.steps
+    value = Bsz * world / (ms_per_step * 1e-3)
+
+    # end to end through the public API from host buffers
+    e2e = None
+    if not args.no_e2e:
+        sync_all()
+        e0.record()
+        for _ in range(args.steps):
+            x = host_x.to(dev, non_blocking=True)   # put2GPU
+            t = host_t.to(dev, non_blocking=True)
+            step(x, t)
+            _ = float(state["loss"])                # D2H read of the step's loss
+        e1.record()
+        sync_all()
+        ems = e0.elapsed_time(e1)
+        if world > 1:
+            tms = torch.tensor([ems], device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ems = tms.item()
+        e2e = {"value": Bsz * world / (ems / args.steps * 1e-3), "unit": "images/s",
+               "h2d_bytes_per_step": host_x.numel() * 4 + host_t.numel() * 8, "d2h_bytes_per_step": 4}
+
+    if rank != 0:
+        return
+    from mgconv import lower as L
+    summ = L.plan_summary(eng.plan)
+    # per image: 2 FLOP/MAC x (fwd + dgrad + wgrad); the three stem convs read the image and have no dgrad
+    no_dgrad = sum(sum(t.C for t, _ in o.segs) * o.Cout * o.k * o.k * o.Ho * o.Wo for o in eng.conv_ops if not o.needs_dgrad)
+    conv_flops_step = Bsz * (2.0 * summ["macs"] * 3 - 2.0 * no_dgrad)
+    tf_peak, hbm_peak, which = peaks()
+    conv_ms_step = prof["conv_ms"] / args.steps if prof["conv_ms"] > 0 else None
+    achieved = conv_flops_step / (conv_ms_step * 1e-3) / 1e12 if conv_ms_step else None
+    roofline = {"bound": "tensor", "kernel": "implicit-GEMM multigrid conv (fwd+dgrad+wgrad launches)",
+                "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": (achieved / tf_peak) if achieved else None,
+                "traffic": None, "peak_source": which, "conv_ms_per_step": conv_ms_step, "conv_launches_per_step": prof["conv_launches"] / args.steps,
+                "share_of_step": (conv_ms_step / ms_per_step) if conv_ms_step else None,
+                "algorithmic_flops_per_step": conv_flops_step}
+    cb = None
+    if not args.no_cpu_baseline and world == 1:
+        cb, _ = cpu_baseline(args.cpu_batch, 2, 1)
+    line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": WORKLOAD if (args.depth == 34 and Bsz == 256) else f"R-MG-{args.depth} batch {Bsz}/GPU (NOT the headline config)",
+                       "global_batch": Bsz * world, "parallelism": f"dp{world}", "l2_flush": "inputs larger than L2 (154 MB of images, >10 GB of activations per step)",
+                       "impl": os.environ.get("MGCONV_IMPL", "auto"), "device_bytes": eng.bytes},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cb,
+            "loss": float(state["loss"])}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

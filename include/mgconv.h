@@ -95,6 +95,11 @@ int mg_ctx_sync(mg_ctx* ctx);                         /* cutorch.synchronize() e
 const char* mg_last_error(mg_ctx* ctx);
 int mg_version(void);
 int mg_ctx_launch_count(mg_ctx* ctx, int64_t* out);   /* kernels launched through this ctx */
+/* CUDA-event timing of the convolution entry points (forward / backward_data / backward_weight):
+ * while on, every such call is bracketed by two events on the context stream; read returns the
+ * summed device time and the number of calls since the last read (synchronises the stream) */
+int mg_ctx_profile(mg_ctx* ctx, int on);
+int mg_ctx_profile_read(mg_ctx* ctx, double* conv_ms, int64_t* conv_calls);
 
 /* ---- layout conversion at the Torch boundary (NCHW fp32 <-> grid) --------------------- */
 int mg_import_nchw(mg_ctx* ctx, const float* src, mg_grid* dst);            /* put2GPU output -> grid */

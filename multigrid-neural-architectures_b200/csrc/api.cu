@@ -17,6 +17,47 @@ int umma_conv_forward(mg_ctx*, const mg_conv_desc*, const void*, const float*, m
 int umma_conv_backward_data(mg_ctx*, const mg_conv_desc*, const void*, const mg_grid*, mg_grid*);
 int umma_conv_backward_weight(mg_ctx*, const mg_conv_desc*, const mg_grid*, float*, float*, float);
 
+#include <vector>
+struct ProfState {
+  std::vector<cudaEvent_t> pool;             // events, reused
+  std::vector<std::pair<int, int>> spans;    // (begin, end) indices into pool
+  size_t used = 0;
+  double acc_ms = 0;                         // spans already folded
+  int64_t launches = 0;
+};
+
+// fold the pending spans into acc_ms (synchronises the stream) so the pool can be reused
+static void prof_flush(mg_ctx* ctx) {
+  ProfState* ps = (ProfState*)ctx->prof;
+  if (!ps || ps->spans.empty()) return;
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& sp : ps->spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ps->pool[sp.first], ps->pool[sp.second]) == cudaSuccess) ps->acc_ms += ms;
+  }
+  ps->spans.clear();
+  ps->used = 0;
+}
+
+struct ProfSpan {
+  mg_ctx* ctx; int b = -1;
+  explicit ProfSpan(mg_ctx* c) : ctx(c) {
+    if (!c->profile) return;
+    ProfState* ps = (ProfState*)c->prof;
+    if (ps->used + 2 > 8192) prof_flush(c);
+    while (ps->pool.size() < ps->used + 2) { cudaEvent_t e; cudaEventCreate(&e); ps->pool.push_back(e); }
+    b = (int)ps->used; ps->used += 2;
+    cudaEventRecord(ps->pool[b], c->stream);
+  }
+  ~ProfSpan() {
+    if (b < 0) return;
+    ProfState* ps = (ProfState*)ctx->prof;
+    cudaEventRecord(ps->pool[b + 1], ctx->stream);
+    ps->spans.push_back({b, b + 1});
+    ps->launches++;
+  }
+};
+
 static bool use_umma(const mg_ctx* ctx, const mg_conv_desc* d, const void* wpack, int kind) {
   if (ctx->dtype != MG_BF16 || ctx->impl == MG_IMPL_SIMT) return false;
   if (kind != 2 && !wpack) return false;
@@ -46,8 +87,31 @@ int mg_ctx_create(int device, void* cuda_stream, int dtype, mg_ctx** out) {
   return MG_OK;
 }
 
+int mg_ctx_profile(mg_ctx* ctx, int on) {
+  if (!ctx) return MG_ERR_INVALID_ARG;
+  if (on && !ctx->prof) ctx->prof = new (std::nothrow) ProfState();
+  if (on && !ctx->prof) return MG_ERR_INVALID_ARG;
+  ctx->profile = on ? 1 : 0;
+  return MG_OK;
+}
+
+int mg_ctx_profile_read(mg_ctx* ctx, double* conv_ms, int64_t* conv_launches) {
+  if (!ctx || !conv_ms || !conv_launches) return MG_ERR_INVALID_ARG;
+  ProfState* ps = (ProfState*)ctx->prof;
+  if (!ps) { *conv_ms = 0; *conv_launches = 0; return MG_OK; }
+  prof_flush(ctx);
+  *conv_ms = ps->acc_ms; *conv_launches = ps->launches;
+  ps->acc_ms = 0; ps->launches = 0;
+  return MG_OK;
+}
+
 int mg_ctx_destroy(mg_ctx* ctx) {
   if (!ctx) return MG_ERR_INVALID_ARG;
+  if (ctx->prof) {
+    ProfState* ps = (ProfState*)ctx->prof;
+    for (auto e : ps->pool) cudaEventDestroy(e);
+    delete ps;
+  }
   mg_comm_destroy(ctx);
   delete ctx;
   return MG_OK;
@@ -82,6 +146,7 @@ int mg_conv_forward(mg_ctx* ctx, const mg_conv_desc* d, const float* w, const vo
   MG_REQUIRE(ctx, y->C == d->Cout && y->Cp >= y->C && y->Cp % 8 == 0, MG_ERR_SHAPE, "conv_forward: y.C %d Cp %d vs Cout %d", y->C, y->Cp, d->Cout);
   int Ho = (d->H + 2 * d->pad - d->ksize) / d->stride + 1, Wo = (d->W + 2 * d->pad - d->ksize) / d->stride + 1;
   MG_REQUIRE(ctx, y->H == Ho && y->W == Wo && y->N == d->seg[0].N, MG_ERR_SHAPE, "conv_forward: y is %dx%d, expected %dx%d", y->H, y->W, Ho, Wo);
+  ProfSpan span(ctx);
   if (use_umma(ctx, d, wpack, 0)) return umma_conv_forward(ctx, d, wpack, bias, y, bn_sums);
   MG_REQUIRE(ctx, ctx->impl != MG_IMPL_TCGEN05, MG_ERR_UNSUPPORTED, "conv_forward: shape not supported by the tcgen05 path");
   MG_REQUIRE(ctx, w != nullptr, MG_ERR_INVALID_ARG, "conv_forward: null weights");
@@ -92,6 +157,7 @@ int mg_conv_backward_data(mg_ctx* ctx, const mg_conv_desc* d, const float* w, co
   if (!ctx || !d || !g || !dcat) return MG_ERR_INVALID_ARG;
   MG_REQUIRE(ctx, g->C == d->Cout, MG_ERR_SHAPE, "conv_backward_data: g.C %d != Cout %d", g->C, d->Cout);
   MG_REQUIRE(ctx, dcat->H == d->H && dcat->W == d->W && dcat->N == g->N, MG_ERR_SHAPE, "conv_backward_data: dcat shape");
+  ProfSpan span(ctx);
   if (use_umma(ctx, d, wpack_t, 1)) return umma_conv_backward_data(ctx, d, wpack_t, g, dcat);
   MG_REQUIRE(ctx, ctx->impl != MG_IMPL_TCGEN05, MG_ERR_UNSUPPORTED, "conv_backward_data: shape not supported by the tcgen05 path");
   MG_REQUIRE(ctx, w != nullptr, MG_ERR_INVALID_ARG, "conv_backward_data: null weights");
@@ -101,6 +167,7 @@ int mg_conv_backward_data(mg_ctx* ctx, const mg_conv_desc* d, const float* w, co
 int mg_conv_backward_weight(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g, float* dw, float* dbias, float gscale) {
   if (!ctx || !d || !g || !dw) return MG_ERR_INVALID_ARG;
   MG_REQUIRE(ctx, g->C == d->Cout, MG_ERR_SHAPE, "conv_backward_weight: g.C %d != Cout %d", g->C, d->Cout);
+  ProfSpan span(ctx);
   if (use_umma(ctx, d, nullptr, 2)) return umma_conv_backward_weight(ctx, d, g, dw, dbias, gscale);
   MG_REQUIRE(ctx, ctx->impl != MG_IMPL_TCGEN05, MG_ERR_UNSUPPORTED, "conv_backward_weight: shape not supported by the tcgen05 path");
   return simt_conv_backward_weight(ctx, d, g, dw, dbias, gscale);

@@ -20,6 +20,9 @@ struct mg_ctx {
   cudaStream_t comm_stream;
   cudaEvent_t ev_compute, ev_comm;
   int rank, nranks;
+  // optional CUDA-event timing of the convolution kernels (bench.py roofline)
+  int profile;
+  void* prof;  // ProfState*
 };
 
 #define MG_FAIL(ctx, code, ...)                                  \

@@ -34,6 +34,12 @@ def _flatten(x):
     return [x]
 
 
+def engine_key(input):
+    ts = _flatten(input)
+    return (tuple(input.shape) if isinstance(input, torch.Tensor) else tuple(tuple(t.shape) for t in ts),
+            ts[0].device.index)
+
+
 class Engine:
     def __init__(self, model, input):
         inputs = _flatten(input)
@@ -43,8 +49,7 @@ class Engine:
                                   "call model:cuda() and move the inputs with put2GPU first")
         self.model = model
         self.device = inputs[0].device
-        self.key = (tuple(input.shape) if isinstance(input, torch.Tensor) else tuple(tuple(t.shape) for t in inputs),
-                    self.device.index)
+        self.key = engine_key(input)
         precision = getattr(model, "precision", os.environ.get("MGCONV_PRECISION", "bf16"))
         self.dtype, self.elt = _PRECISION[precision]
         self.ctx = ffi.Context(self.device.index, torch.cuda.current_stream(self.device).cuda_stream, self.dtype)

@@ -61,6 +61,8 @@ SIGNATURES = {
     "mg_last_error": (C.c_char_p, [_P]),
     "mg_version": (_I, []),
     "mg_ctx_launch_count": (_I, [_P, C.POINTER(_I64)]),
+    "mg_ctx_profile": (_I, [_P, _I]),
+    "mg_ctx_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(_I64)]),
     "mg_import_nchw": (_I, [_P, _P, _G]),
     "mg_export_nchw": (_I, [_P, _G, _P]),
     "mg_conv_packed_bytes": (_SZ, [_D, _I]),
@@ -134,6 +136,11 @@ class Context:
         n = _I64(0)
         self.call("mg_ctx_launch_count", C.byref(n))
         return n.value
+
+    def profile_read(self):
+        ms, n = C.c_double(0), _I64(0)
+        self.call("mg_ctx_profile_read", C.byref(ms), C.byref(n))
+        return {"conv_ms": ms.value, "conv_launches": n.value}
 
     def close(self):
         if self.h:

@@ -184,7 +184,7 @@ class Builder:
         if t.pooled is None:
             p = self.new_tensor(t.C, (t.H + 1) // 2, (t.W + 1) // 2, t.name + ".pool", needs_grad=t.needs_grad)
             t.pooled = p
-            if isinstance(t.producer, O.ApplyOp):
+            if isinstance(t.producer, O.ApplyOp) and t.producer.out is t:
                 t.producer.pooled = p   # fused into the apply pass
                 p.producer = t.producer
             else:

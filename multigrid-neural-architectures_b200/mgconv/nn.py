@@ -123,7 +123,8 @@ class Module:
     # ---- execution (top-level module only) ----------------------------------------------
     def _get_engine(self, input):
         from .engine import Engine
-        key = (tuple(input.shape), input.device.index)
+        from .engine import engine_key
+        key = engine_key(input)
         if self._engine is None or self._engine.key != key:
             self._engine = Engine(self, input)
         return self._engine
@@ -136,7 +137,7 @@ class Module:
     updateOutput = forward
 
     def backward(self, input, gradOutput, scale=1.0):
-        eng = self._get_engine(input)
+        eng = self._engine if input is None else self._get_engine(input)
         self.gradInput = eng.backward(gradOutput, scale)
         return self.gradInput
 

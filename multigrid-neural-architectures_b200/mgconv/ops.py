@@ -279,6 +279,7 @@ class ApplyOp(Op):
             self.res.srcs.append(Src(D, t.H, t.W, t.C, t.Cp, 0, MG_SEG_SAME))
         if self.bn is not None:
             G = E.alloc(t.shape()) if self.res is not None else D   # the shortcut still reads D
+            self.G = G   # keep the storage alive: the mg_grid structs below only hold raw pointers
             self.coef = E.alloc((3 * t.Cp,), torch.float32)
             self.dg, self.gg = t.grid(D), t.grid(G)
             self.yraw = y.grid()

@@ -226,13 +226,13 @@ def test_bn_finalize_apply_residual_and_backward(ctx, eps):
     x = bf16_round(rnd(N, Cc, H, H) * 2 + 1)
     gamma, beta = rng.random(Cc) + 0.5, rng.standard_normal(Cc) * 0.1
     rm, rv = np.zeros(Cc), np.ones(Cc)
+    drm, drv = dev(rm), dev(rv)   # device copies of the initial running stats (the oracle updates rm/rv in place)
     y_ref, mean, invstd = O.bn_forward_train(x, gamma, beta, eps, rm, rv)
     sc = rnd(N, 8, H, H)  # zero-padded shortcut with fewer channels (nn.Padding, ilsvrc/rnmg.lua:16)
     out_ref = O.relu_forward(y_ref + O.pad_channels(sc, Cc))
     gx = Grid(ctx.dtype, N, Cc, H, H, x)
     sums = torch.zeros(2 * Cc, dtype=torch.float64, device="cuda")
     ctx.call("mg_bn_stats", C.byref(gx.g()), ptr(sums))
-    drm, drv = dev(rm), dev(rv)
     scale, shift = torch.zeros(gx.Cp, device="cuda"), torch.zeros(gx.Cp, device="cuda")
     smean, sinv = torch.zeros(gx.Cp, device="cuda"), torch.zeros(gx.Cp, device="cuda")
     dgam, dbet = dev(gamma), dev(beta)

@@ -93,3 +93,20 @@ def copy_params_from_oracle(omodel, model):
             p.running_mean.copy_(o.running_mean)
             p.running_var.copy_(o.running_var)
     return olist, plist
+
+
+def emulate_bf16_storage(omodel):
+    """bf16 mode of the product = bf16 *storage* of every activation / gradient tensor, fp32
+    accumulation and fp32 BatchNorm arithmetic.  The fp64 oracle is given the same storage points
+    (forward hooks that round to bf16; autograd rounds the gradient at the same places), so that
+    ReLU masks and pool arg-maxima are decided on identical values and the remaining difference is
+    accumulation order only."""
+    import torch.nn as tnn
+    from oracle import t7nn
+
+    def rnd(_m, _i, o):
+        return o.to(torch.bfloat16).to(o.dtype)
+    for m in omodel.modules():
+        if isinstance(m, (tnn.Conv2d, tnn.Linear, tnn.ReLU, tnn.AvgPool2d, t7nn.CAddTable)):
+            m.register_forward_hook(rnd)
+    return omodel
