@@ -95,6 +95,7 @@ int mg_ctx_sync(mg_ctx* ctx);                         /* cutorch.synchronize() e
 const char* mg_last_error(mg_ctx* ctx);
 int mg_version(void);
 int mg_ctx_launch_count(mg_ctx* ctx, int64_t* out);   /* kernels launched through this ctx */
+int mg_ctx_tc_launch_count(mg_ctx* ctx, int64_t* out); /* ... of which tcgen05 tensor-core kernels */
 /* CUDA-event timing of the convolution entry points (forward / backward_data / backward_weight):
  * while on, every such call is bracketed by two events on the context stream; read returns the
  * summed device time and the number of calls since the last read (synchronises the stream) */

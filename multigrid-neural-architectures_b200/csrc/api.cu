@@ -130,6 +130,7 @@ int mg_ctx_sync(mg_ctx* ctx) {
   return MG_OK;
 }
 const char* mg_last_error(mg_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+int mg_ctx_tc_launch_count(mg_ctx* ctx, int64_t* out) { if (!ctx || !out) return MG_ERR_INVALID_ARG; *out = ctx->tc_launches; return MG_OK; }
 int mg_ctx_launch_count(mg_ctx* ctx, int64_t* out) { if (!ctx || !out) return MG_ERR_INVALID_ARG; *out = ctx->launches; return MG_OK; }
 
 // ---- conv dispatch ------------------------------------------------------------------

@@ -14,6 +14,7 @@ struct mg_ctx {
   int impl;         // mg_impl
   int num_sms;
   int64_t launches; // kernels launched through this context
+  int64_t tc_launches; // of which tcgen05 (UMMA) kernels
   char err[512];
   // data parallel
   void* nccl_comm;

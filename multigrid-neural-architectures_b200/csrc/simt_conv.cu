@@ -7,6 +7,7 @@
 // concatenated tensor of ResampleConcat (models/ilsvrc/rnmg.lua:41-89) never exists in HBM.
 #include "common.cuh"
 #include "conv_view.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -307,6 +308,20 @@ static int simt_wgrad_t(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g, fl
     MG_CHECK_LAUNCH(ctx);
   }
   return MG_OK;
+}
+
+template <typename T>
+static int simt_dbias_t(mg_ctx* ctx, const mg_grid* g, int Cout, float* dbias, float gscale) {
+  const int64_t M = (int64_t)g->N * g->H * g->W;
+  dim3 g2((unsigned)mg_cdiv(Cout, 32), (unsigned)std::min<int64_t>(mg_cdiv(M, 64), 256));
+  dbias_kernel<T><<<g2, 256, 0, ctx->stream>>>((const T*)g->data, g->Cp, Cout, M, dbias, gscale);
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+// dbias += gscale * sum over pixels of g (accGradParameters' gradBias)
+int simt_dbias(mg_ctx* ctx, const mg_grid* g, int Cout, float* dbias, float gscale) {
+  MG_DISPATCH(ctx, return simt_dbias_t<T>(ctx, g, Cout, dbias, gscale););
 }
 
 int simt_conv_backward_weight(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g, float* dw, float* dbias, float gscale) {

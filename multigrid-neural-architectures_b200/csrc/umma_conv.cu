@@ -1,8 +1,415 @@
-// placeholder until the tcgen05 path lands
+// tcgen05 / TMEM implicit-GEMM multigrid convolution for sm_100a (bf16 operands, fp32 accumulate).
+//
+//   D[m][n] = sum_k A[m][k] * B[n][k]        m = output pixel (n, oy, ox), n = output channel
+//
+// K runs over "k-vectors" of 8 channels (16 bytes): for tap in k*k, for segment in the conv's
+// gather list, for c8 in Cp_seg/8.  A is never materialised: four producer warps copy each
+// k-vector of each of the CTA's 128 pixels straight from the source grids into the 128B-swizzled
+// K-major operand image in shared memory with cp.async (zero-fill for the conv's zero padding);
+// the same-scale grid, the pooled companion of the finer grid and the coarser grid (read at
+// (y>>1, x>>1) -- SpatialUpSamplingNearest) are just different base pointers / shifts, so the
+// channel concatenation of ResampleConcat (models/ilsvrc/rnmg.lua:41-89) exists only as the order
+// of the K loop.  B (the weights) is pre-packed by pack_weights_kernel into exactly the shared
+// memory image of each pipeline stage, so one thread moves a stage with a single cp.async.bulk.
+// One elected thread issues tcgen05.mma (M=128, N<=256, K=16) into a TMEM accumulator; the
+// producer warps drain it with tcgen05.ld, add the bias and store bf16 NHWC rows.
+//
+// forward:  A = gather(x),  B = W[co][(tap,ci)]                      -> y[m][co]
+// dgrad  :  A = g (one SAME segment), B = W^T[cpad][(tap',co)], taps mirrored -> dcat[m][cpad]
+// wgrad  :  see umma_wgrad.cu (MN-major operands).
 #include "common.cuh"
-bool umma_conv_supported(const mg_ctx*, const mg_conv_desc*, int) { return false; }
-size_t umma_packed_bytes(const mg_conv_desc*, int) { return 0; }
-int umma_pack_weights(mg_ctx* ctx, const mg_conv_desc*, const float*, void*, int) { MG_FAIL(ctx, MG_ERR_UNSUPPORTED, "tcgen05 path not built"); }
-int umma_conv_forward(mg_ctx* ctx, const mg_conv_desc*, const void*, const float*, mg_grid*, double*) { MG_FAIL(ctx, MG_ERR_UNSUPPORTED, "tcgen05 path not built"); }
-int umma_conv_backward_data(mg_ctx* ctx, const mg_conv_desc*, const void*, const mg_grid*, mg_grid*) { MG_FAIL(ctx, MG_ERR_UNSUPPORTED, "tcgen05 path not built"); }
-int umma_conv_backward_weight(mg_ctx* ctx, const mg_conv_desc*, const mg_grid*, float*, float*, float) { MG_FAIL(ctx, MG_ERR_UNSUPPORTED, "tcgen05 path not built"); }
+#include "conv_view.cuh"
+#include "umma_common.cuh"
+#include <algorithm>
+
+namespace {
+
+constexpr int BM = 128;           // pixels per CTA = UMMA M
+constexpr int KV_PER_STAGE = 8;   // 8 k-vectors of 8 bf16 = one 128-byte swizzle row
+constexpr int A_STAGE_BYTES = BM * 128;
+constexpr int N_PRODUCERS = 128;
+constexpr int MMA_WARP = 4, B_WARP = 5;
+constexpr int N_THREADS = 192;
+constexpr int MAX_STAGES = 8;
+
+struct UParams {
+  USeg seg[MG_MAX_SEG];
+  int n_seg;
+  int k, stride, pad;
+  int H, W;      // logical (concatenated) input size
+  int Ho, Wo;
+  int64_t M;     // N * Ho * Wo
+  int Nimg;
+  int kv_per_tap, nkv, n_stages;
+  int n_tile;    // UMMA N of this launch (multiple of 16, <= 256)
+  const uint8_t* wpack;  // [n_tiles][n_stages][n_tile][128B]
+  const float* bias;     // [c_bias] or null
+  int c_bias;
+  __nv_bfloat16* y;
+  int y_pitch;   // elements per output pixel
+  int c_valid;   // channels to write (multiple of 8)
+  int stages, lag;
+  int tmem_cols;
+};
+
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M=128
+__host__ __device__ constexpr uint32_t idesc_bf16_m128(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- the kernel ---------------
+__global__ void __launch_bounds__(N_THREADS, 1) umma_conv_kernel(const __grid_constant__ UParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 bytes the swizzle atoms need
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], tmem_full_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t s_row[BM];
+  __shared__ USeg s_seg[MG_MAX_SEG];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = p.stages;
+  const int b_stage_bytes = p.n_tile * 128;
+  uint8_t* a_smem = smem;
+  uint8_t* b_smem = smem + (size_t)S * A_STAGE_BYTES;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int ntile = blockIdx.y;
+
+  if (tid < p.n_seg) s_seg[tid] = p.seg[tid];
+  if (tid < BM) {  // packed (n, oy, ox) of this CTA's rows; 0xFFFFFFFF = row beyond M
+    int64_t m = m0 + tid;
+    uint32_t v = 0xFFFFFFFFu;
+    if (m < p.M) {
+      int ox = (int)(m % p.Wo); int64_t q = m / p.Wo;
+      int oy = (int)(q % p.Ho); int n = (int)(q / p.Ho);
+      v = ((uint32_t)n << 20) | ((uint32_t)oy << 10) | (uint32_t)ox;
+    }
+    s_row[tid] = v;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], N_PRODUCERS + 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < 4) {
+    // ================= A producers: gather k-vectors with cp.async ==========================
+    const int v = tid & 7;       // k-vector slot of the stage (16-byte column of the 128-byte row)
+    const int rg = tid >> 3;     // row group 0..15; rows rg, rg+16, ...
+    const int L = p.lag;
+    for (int ks = 0; ks < p.n_stages + L; ++ks) {
+      if (ks < p.n_stages) {
+        const int s = ks % S;
+        if (ks >= S) mbar_wait(&empty_bar[s], ((ks / S) - 1) & 1);
+        // decode this lane's k-vector: (tap, segment, channel offset)
+        const int j = ks * KV_PER_STAGE + v;
+        const bool kv_ok = j < p.nkv;
+        int tap = 0, r = 0, sg = 0;
+        if (kv_ok) {
+          tap = j / p.kv_per_tap; r = j - tap * p.kv_per_tap;
+          while (sg + 1 < p.n_seg && r >= s_seg[sg + 1].kv_begin) ++sg;
+        }
+        const USeg sgm = s_seg[sg];
+        const int c8 = r - sgm.kv_begin;
+        const int dy = tap / p.k - p.pad, dx = tap % p.k - p.pad;
+        const uint32_t dst0 = smem_u32(a_smem + (size_t)s * A_STAGE_BYTES);
+#pragma unroll
+        for (int it = 0; it < BM / 16; ++it) {
+          const int row = it * 16 + rg;
+          const uint32_t ri = s_row[row];
+          const int ox = ri & 1023, oy = (ri >> 10) & 1023, n = ri >> 20;
+          const int iy = oy * p.stride + dy, ix = ox * p.stride + dx;
+          const bool ok = kv_ok && ri != 0xFFFFFFFFu && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+          const __nv_bfloat16* src = sgm.ptr;
+          if (ok) src += ((size_t)((size_t)n * sgm.Hs + (iy >> sgm.shift)) * sgm.Ws + (ix >> sgm.shift)) * sgm.Cp + c8 * 8;
+          cp_async16(dst0 + row * 128 + ((v ^ (row & 7)) << 4), src, ok ? 16u : 0u);
+        }
+      }
+      cp_async_commit();
+      if (ks >= L) {  // stage ks-L has landed for this thread: publish it to the tensor core (async proxy)
+        cp_async_wait_dyn(L);
+        fence_proxy_async();
+        mbar_arrive(&full_bar[(ks - L) % S]);
+      }
+    }
+    // ================= epilogue: TMEM -> registers -> bf16 NHWC rows ======================
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    const int64_t m = m0 + row;
+    const int n_base = ntile * p.n_tile;
+    __nv_bfloat16* yrow = p.y + (size_t)(m < p.M ? m : 0) * p.y_pitch;
+    for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+      uint32_t acc[16];
+      tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
+      tc_wait_ld();
+      if (m < p.M) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int n0 = n_base + c0 + h * 8;
+          if (n0 + 8 <= p.c_valid) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float a = __uint_as_float(acc[h * 8 + 2 * e]), b = __uint_as_float(acc[h * 8 + 2 * e + 1]);
+              if (p.bias) {
+                if (n0 + 2 * e < p.c_bias) a += __ldg(p.bias + n0 + 2 * e);
+                if (n0 + 2 * e + 1 < p.c_bias) b += __ldg(p.bias + n0 + 2 * e + 1);
+              }
+              __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+              pk[e] = *reinterpret_cast<uint32_t*>(&t);
+            }
+            *reinterpret_cast<uint4*>(yrow + n0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == B_WARP) {
+    // ================= B loader: one bulk copy per stage =====================================
+    if (lane == 0) {
+      const uint8_t* wsrc = p.wpack + (size_t)ntile * p.n_stages * b_stage_bytes;
+      for (int ks = 0; ks < p.n_stages; ++ks) {
+        const int s = ks % S;
+        if (ks >= S) mbar_wait(&empty_bar[s], ((ks / S) - 1) & 1);
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)b_stage_bytes);
+        bulk_g2s(smem_u32(b_smem + (size_t)s * b_stage_bytes), wsrc + (size_t)ks * b_stage_bytes, (uint32_t)b_stage_bytes, &full_bar[s]);
+      }
+    }
+  } else {
+    // ================= MMA issuer ================================================================
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16_m128(p.n_tile);
+      for (int ks = 0; ks < p.n_stages; ++ks) {
+        const int s = ks % S;
+        mbar_wait(&full_bar[s], (ks / S) & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(a_smem + (size_t)s * A_STAGE_BYTES);
+        const uint32_t b_addr = smem_u32(b_smem + (size_t)s * b_stage_bytes);
+        const int kv_here = min(KV_PER_STAGE, p.nkv - ks * KV_PER_STAGE);
+        const int ksteps = (kv_here + 1) >> 1;   // 16 bf16 = 2 k-vectors per UMMA K step
+        for (int q = 0; q < ksteps; ++q)
+          tc_mma_bf16(tmem_base, smem_desc_k_sw128(a_addr + q * 32), smem_desc_k_sw128(b_addr + q * 32), idesc, (ks | q) != 0);
+        tc_commit(&empty_bar[s]);   // frees the stage once these MMAs have read it
+      }
+      tc_commit(&tmem_full_bar);    // accumulator complete
+    }
+  }
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- weight packing -----------
+struct PackParams {
+  const float* w;   // [Cout][Ccat][k][k]
+  uint8_t* out;
+  int transposed;
+  int k, Ccat, Cout;
+  int n_seg;
+  int seg_C[MG_MAX_SEG], seg_cbegin[MG_MAX_SEG], seg_kvbegin[MG_MAX_SEG], seg_cpbegin[MG_MAX_SEG];
+  int kv_per_tap, nkv, n_stages, n_tile, n_tiles;
+  int n_rows_valid;  // forward: Cout; transposed: CcatP (rows that may be non-zero)
+};
+
+// one thread per (n row, k-vector): writes 16 bytes of the swizzled stage image
+__global__ void pack_weights_kernel(PackParams p) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int kv_total = p.n_stages * KV_PER_STAGE;
+  const int64_t total = (int64_t)p.n_tiles * p.n_tile * kv_total;
+  if (i >= total) return;
+  const int j = (int)(i % kv_total);
+  const int nrow = (int)(i / kv_total);          // global row = tile * n_tile + local
+  const int tile = nrow / p.n_tile, nl = nrow % p.n_tile;
+  const int stage = j / KV_PER_STAGE, v = j % KV_PER_STAGE;
+  __nv_bfloat16 vals[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) vals[e] = __float2bfloat16_rn(0.f);
+  if (j < p.nkv && nrow < p.n_rows_valid) {
+    const int tap = j / p.kv_per_tap, r = j % p.kv_per_tap;
+    const int KK = p.k * p.k;
+    if (!p.transposed) {
+      int sg = 0;
+      while (sg + 1 < p.n_seg && r >= p.seg_kvbegin[sg + 1]) ++sg;
+      const int c0 = (r - p.seg_kvbegin[sg]) * 8;
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (c0 + e < p.seg_C[sg]) vals[e] = __float2bfloat16_rn(p.w[((size_t)nrow * p.Ccat + p.seg_cbegin[sg] + c0 + e) * KK + tap]);
+    } else {
+      // row = padded concat channel, K = (mirrored tap, output channel co)
+      int sg = 0;
+      while (sg + 1 < p.n_seg && nrow >= p.seg_cpbegin[sg + 1]) ++sg;
+      const int cl = nrow - p.seg_cpbegin[sg];
+      if (cl < p.seg_C[sg]) {
+        const int ci = p.seg_cbegin[sg] + cl;
+        const int ky = p.k - 1 - tap / p.k, kx = p.k - 1 - tap % p.k;
+        const int co0 = r * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (co0 + e < p.Cout) vals[e] = __float2bfloat16_rn(p.w[((size_t)(co0 + e) * p.Ccat + ci) * KK + ky * p.k + kx]);
+      }
+    }
+  }
+  uint8_t* dst = p.out + ((size_t)(tile * p.n_stages + stage) * p.n_tile + nl) * 128 + ((v ^ (nl & 7)) << 4);
+  *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(vals);
+}
+
+// ---------------------------------------------------------------- host side -----------------
+struct Geometry {
+  int kv_per_tap, nkv, n_stages, n_tile, n_tiles, n_rows;
+};
+
+static void n_tiling(int n_rows_pad16, int* n_tile, int* n_tiles) {
+  *n_tiles = (n_rows_pad16 + 255) / 256;
+  *n_tile = mg_round_up((n_rows_pad16 + *n_tiles - 1) / *n_tiles, 16);
+}
+
+// geometry of the forward (transposed = 0) or dgrad (transposed = 1) GEMM of a conv descriptor
+static Geometry geometry(const mg_conv_desc* d, int transposed) {
+  Geometry g;
+  int CcatP = 0;
+  for (int s = 0; s < d->n_seg; ++s) CcatP += d->seg[s].Cp;
+  const int CoutP = mg_round_up(d->Cout, 8);
+  const int taps = d->ksize * d->ksize;
+  if (!transposed) { g.kv_per_tap = CcatP / 8; g.n_rows = d->Cout; n_tiling(mg_round_up(d->Cout, 16), &g.n_tile, &g.n_tiles); }
+  else { g.kv_per_tap = CoutP / 8; g.n_rows = CcatP; n_tiling(mg_round_up(CcatP, 16), &g.n_tile, &g.n_tiles); }
+  g.nkv = taps * g.kv_per_tap;
+  g.n_stages = (g.nkv + KV_PER_STAGE - 1) / KV_PER_STAGE;
+  return g;
+}
+
+static int pick_stages(int n_tile, int* smem_bytes) {
+  const int stage = A_STAGE_BYTES + n_tile * 128;
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("MGCONV_STAGES"); forced = e ? atoi(e) : 0; }
+  int S = forced > 0 ? forced : std::min(MAX_STAGES, (200 * 1024) / stage);
+  S = std::max(2, std::min(S, MAX_STAGES));
+  *smem_bytes = S * stage + 1024;  // + alignment slack
+  return S;
+}
+
+static int launch(mg_ctx* ctx, UParams& p, int n_tiles) {
+  int smem = 0;
+  p.stages = pick_stages(p.n_tile, &smem);
+  p.stages = std::min(p.stages, std::max(2, p.n_stages));
+  p.lag = std::min(p.stages - 1, 3);
+  int cols = 32;
+  while (cols < p.n_tile) cols <<= 1;
+  p.tmem_cols = cols;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)mg_cdiv(p.M, BM), (unsigned)n_tiles);
+  umma_conv_kernel<<<grid, N_THREADS, smem, ctx->stream>>>(p);
+  MG_CHECK_LAUNCH(ctx);
+  ctx->tc_launches++;
+  return MG_OK;
+}
+
+}  // namespace
+
+bool umma_wgrad_supported(const mg_ctx* ctx, const mg_conv_desc* d);
+
+bool umma_conv_supported(const mg_ctx* ctx, const mg_conv_desc* d, int kind) {
+  if (ctx->dtype != MG_BF16) return false;
+  if (kind == 2) return umma_wgrad_supported(ctx, d);
+  if (kind == 1 && d->stride != 1) return false;     // dgrad of the strided stem is never needed
+  if (d->n_seg < 1 || d->n_seg > MG_MAX_SEG) return false;
+  for (int s = 0; s < d->n_seg; ++s) {
+    const mg_grid& g = d->seg[s];
+    if (d->seg_mode[s] == MG_SEG_POOL) return false;  // gathers are pure copies: POOL operands come as pooled companions
+    if (g.scale || g.shift) return false;             // pending affines are materialised by the apply pass
+    if (g.Cp % 8) return false;
+    if (g.H > 1023 || g.W > 1023 || g.N > 4095) return false;
+  }
+  return d->H <= 1023 && d->W <= 1023;
+}
+
+size_t umma_packed_bytes(const mg_conv_desc* d, int transposed) {
+  if (!d || d->n_seg < 1 || d->n_seg > MG_MAX_SEG) return 0;
+  if (transposed && d->stride != 1) return 0;
+  for (int s = 0; s < d->n_seg; ++s)
+    if (d->seg_mode[s] == MG_SEG_POOL || d->seg[s].scale || d->seg[s].Cp % 8) return 0;
+  Geometry g = geometry(d, transposed);
+  return (size_t)g.n_tiles * g.n_stages * g.n_tile * 128;
+}
+
+int umma_pack_weights(mg_ctx* ctx, const mg_conv_desc* d, const float* w, void* wpack, int transposed) {
+  Geometry g = geometry(d, transposed);
+  PackParams p;
+  memset(&p, 0, sizeof(p));
+  p.w = w; p.out = (uint8_t*)wpack; p.transposed = transposed;
+  p.k = d->ksize; p.Cout = d->Cout; p.n_seg = d->n_seg;
+  int c = 0, cp = 0;
+  for (int s = 0; s < d->n_seg; ++s) {
+    p.seg_C[s] = d->seg[s].C; p.seg_cbegin[s] = c; p.seg_cpbegin[s] = cp; p.seg_kvbegin[s] = cp / 8;
+    c += d->seg[s].C; cp += d->seg[s].Cp;
+  }
+  p.Ccat = c;
+  p.kv_per_tap = g.kv_per_tap; p.nkv = g.nkv; p.n_stages = g.n_stages; p.n_tile = g.n_tile; p.n_tiles = g.n_tiles;
+  p.n_rows_valid = g.n_rows;
+  const int64_t total = (int64_t)g.n_tiles * g.n_tile * g.n_stages * KV_PER_STAGE;
+  pack_weights_kernel<<<(unsigned)mg_cdiv(total, 256), 256, 0, ctx->stream>>>(p);
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int umma_conv_forward(mg_ctx* ctx, const mg_conv_desc* d, const void* wpack, const float* bias, mg_grid* y, double* bn_sums) {
+  Geometry g = geometry(d, 0);
+  UParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_seg = d->n_seg;
+  int cp = 0;
+  for (int s = 0; s < d->n_seg; ++s) {
+    const mg_grid& sg = d->seg[s];
+    const int m = d->seg_mode[s];
+    if (m == MG_SEG_SAME) MG_REQUIRE(ctx, sg.H == d->H && sg.W == d->W, MG_ERR_SHAPE, "conv: SAME seg %d is %dx%d, expected %dx%d", s, sg.H, sg.W, d->H, d->W);
+    else MG_REQUIRE(ctx, sg.H * 2 == d->H && sg.W * 2 == d->W, MG_ERR_SHAPE, "conv: UP seg %d is %dx%d, x2 != %dx%d", s, sg.H, sg.W, d->H, d->W);
+    MG_REQUIRE(ctx, sg.N == d->seg[0].N, MG_ERR_SHAPE, "conv: seg %d batch", s);
+    p.seg[s].ptr = (const __nv_bfloat16*)sg.data; p.seg[s].Hs = sg.H; p.seg[s].Ws = sg.W; p.seg[s].Cp = sg.Cp;
+    p.seg[s].shift = m == MG_SEG_UP ? 1 : 0; p.seg[s].kv_begin = cp / 8;
+    cp += sg.Cp;
+  }
+  p.k = d->ksize; p.stride = d->stride; p.pad = d->pad; p.H = d->H; p.W = d->W;
+  p.Ho = y->H; p.Wo = y->W; p.Nimg = y->N;
+  p.M = (int64_t)y->N * y->H * y->W;
+  p.kv_per_tap = g.kv_per_tap; p.nkv = g.nkv; p.n_stages = g.n_stages; p.n_tile = g.n_tile;
+  p.wpack = (const uint8_t*)wpack; p.bias = bias; p.c_bias = d->Cout;
+  p.y = (__nv_bfloat16*)y->data; p.y_pitch = y->Cp; p.c_valid = y->Cp;
+  int rc = launch(ctx, p, g.n_tiles);
+  if (rc) return rc;
+  if (bn_sums) return mg_bn_stats(ctx, y, bn_sums);
+  return MG_OK;
+}
+
+int umma_conv_backward_data(mg_ctx* ctx, const mg_conv_desc* d, const void* wpack_t, const mg_grid* gr, mg_grid* dcat) {
+  Geometry g = geometry(d, 1);
+  UParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_seg = 1;
+  p.seg[0].ptr = (const __nv_bfloat16*)gr->data; p.seg[0].Hs = gr->H; p.seg[0].Ws = gr->W; p.seg[0].Cp = gr->Cp;
+  p.seg[0].shift = 0; p.seg[0].kv_begin = 0;
+  MG_REQUIRE(ctx, gr->Cp == mg_round_up(d->Cout, 8), MG_ERR_SHAPE, "dgrad: g.Cp %d", gr->Cp);
+  p.k = d->ksize; p.stride = 1; p.pad = d->ksize - 1 - d->pad; p.H = gr->H; p.W = gr->W;
+  p.Ho = dcat->H; p.Wo = dcat->W; p.Nimg = dcat->N;
+  p.M = (int64_t)dcat->N * dcat->H * dcat->W;
+  p.kv_per_tap = g.kv_per_tap; p.nkv = g.nkv; p.n_stages = g.n_stages; p.n_tile = g.n_tile;
+  p.wpack = (const uint8_t*)wpack_t; p.bias = nullptr;
+  p.y = (__nv_bfloat16*)dcat->data; p.y_pitch = dcat->Cp; p.c_valid = dcat->Cp;
+  MG_REQUIRE(ctx, dcat->Cp == g.n_rows, MG_ERR_SHAPE, "dgrad: dcat.Cp %d != %d", dcat->Cp, g.n_rows);
+  return launch(ctx, p, g.n_tiles);
+}
+

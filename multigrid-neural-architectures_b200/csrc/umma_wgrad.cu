@@ -1,0 +1,265 @@
+// tcgen05 weight gradient of the multigrid convolution (accGradParameters of
+// cudnn.SpatialConvolution, models/ilsvrc/rnmg.lua:26,36) for sm_100a.
+//
+//   dW[(tap, ci)][co] += gscale * sum_pixels  gather(x)[pixel][(tap, ci)] * g[pixel][co]
+//
+// GEMM view: M = 128 consecutive gathered channels of the K order of the forward kernel (16
+// k-vectors: (tap, segment, c8)), N = Cout (<= 256 per launch column), reduction over pixels.
+// Both operands are "MN-major" for the tensor core: the shared-memory images are exactly the ones
+// the forward kernel builds (rows = pixels, 128 bytes = 64 channels, 128B swizzle), only the
+// descriptors differ.  The cross-scale gather (pooled companion | same | up-sampled coarser grid)
+// is recomputed here with the same cp.async loader -- the concatenated tensor is not stored for
+// backward either.  The pixel range is split across CTAs; partial sums are added to dW with
+// fp32 reductions (red.global.add), so dW accumulates like Torch's accGradParameters.
+#include "common.cuh"
+#include "umma_common.cuh"
+#include <algorithm>
+
+namespace {
+
+constexpr int WM = 128;           // gathered channels per CTA = UMMA M = 16 k-vectors
+constexpr int PIX = 64;           // pixels per pipeline stage = 4 UMMA K steps
+constexpr int A_IMG = PIX * 128;  // one 64-channel operand image of a stage
+constexpr int N_PROD = 128;
+constexpr int W_THREADS = 160;    // 4 producer/epilogue warps + 1 MMA warp
+constexpr int W_MAX_STAGES = 8;
+
+struct WParams {
+  USeg seg[MG_MAX_SEG];
+  int seg_C[MG_MAX_SEG], seg_cbegin[MG_MAX_SEG];
+  int n_seg;
+  int k, stride, pad;
+  int H, W, Ho, Wo;
+  int64_t M;             // N * Ho * Wo (pixels of g)
+  int kv_per_tap, nkv;
+  const __nv_bfloat16* g;
+  int g_cp;              // channel pitch of g
+  int Cout, Ccat;
+  int n_tile;            // UMMA N (multiple of 16)
+  int n_blk;             // 64-channel images of g per stage = ceil(n_tile / 64)
+  float* dw;             // [Cout][Ccat][k][k]
+  float gscale;
+  int64_t pix_per_cta;   // multiple of PIX
+  int stages, lag, tmem_cols;
+};
+
+__host__ __device__ constexpr uint32_t idesc_bf16_m128_mn(int n) {
+  // D fp32, A/B bf16, both MN-major (bits 15, 16), M = 128
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(WM >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(W_THREADS, 1) umma_wgrad_kernel(const __grid_constant__ WParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[W_MAX_STAGES], empty_bar[W_MAX_STAGES], tmem_full_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ USeg s_seg[MG_MAX_SEG];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = p.stages;
+  const int stage_bytes = 2 * A_IMG + p.n_blk * A_IMG;
+  const int mt = blockIdx.x;                 // which 16 k-vectors
+  const int nt = blockIdx.y;                 // which column tile of Cout
+  const int64_t pix0 = (int64_t)blockIdx.z * p.pix_per_cta;
+  const int64_t pix1 = min(p.M, pix0 + p.pix_per_cta);
+  const int n_iters = (int)((pix1 - pix0 + PIX - 1) / PIX);
+
+  if (tid < p.n_seg) s_seg[tid] = p.seg[tid];
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], N_PROD); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < 4) {
+    // ---- this thread's fixed k-vector of the gathered operand --------------------------------
+    const int kvl = tid & 15;                 // 0..15 within the M tile
+    const int pg = tid >> 4;                  // pixel lane 0..7: pixels pg, pg+8, ... of each stage
+    const int j = mt * 16 + kvl;
+    const bool kv_ok = j < p.nkv;
+    int tap = 0, r = 0, sg = 0;
+    if (kv_ok) {
+      tap = j / p.kv_per_tap; r = j - tap * p.kv_per_tap;
+      while (sg + 1 < p.n_seg && r >= s_seg[sg + 1].kv_begin) ++sg;
+    }
+    const USeg sgm = s_seg[sg];
+    const int c8 = r - sgm.kv_begin;
+    const int dy = tap / p.k - p.pad, dx = tap % p.k - p.pad;
+    const int blk = kvl >> 3, v = kvl & 7;
+    // running (n, oy, ox) of the next pixel this thread gathers; advances by 8 per copy
+    int64_t m = pix0 + pg;
+    int ox = (int)(m % p.Wo); int64_t q = m / p.Wo;
+    int oy = (int)(q % p.Ho); int n = (int)(q / p.Ho);
+    // ---- g operand: chunk (16 B) gc of pixel gp, 8 pixels apart -------------------------------
+    const int chunks = p.n_blk * 8;           // 16-byte chunks per pixel row across the g images
+    const int g_per_thread = (PIX * chunks) / N_PROD;
+    const int L = p.lag;
+
+    for (int it = 0; it < n_iters + L; ++it) {
+      if (it < n_iters) {
+        const int s = it % S;
+        if (it >= S) mbar_wait(&empty_bar[s], ((it / S) - 1) & 1);
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        const uint32_t a_dst = smem_u32(st) + blk * A_IMG;
+        const int64_t mbase = pix0 + (int64_t)it * PIX;
+#pragma unroll
+        for (int i = 0; i < PIX / 8; ++i) {
+          const int prow = i * 8 + pg;
+          const int iy = oy * p.stride + dy, ix = ox * p.stride + dx;
+          const bool ok = kv_ok && (mbase + prow) < pix1 && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+          const __nv_bfloat16* src = sgm.ptr;
+          if (ok) src += ((size_t)((size_t)n * sgm.Hs + (iy >> sgm.shift)) * sgm.Ws + (ix >> sgm.shift)) * sgm.Cp + c8 * 8;
+          cp_async16(a_dst + prow * 128 + ((v ^ (prow & 7)) << 4), src, ok ? 16u : 0u);
+          ox += 8;
+          while (ox >= p.Wo) { ox -= p.Wo; if (++oy == p.Ho) { oy = 0; ++n; } }
+        }
+        const uint32_t g_dst = smem_u32(st) + 2 * A_IMG;
+        for (int i = 0; i < g_per_thread; ++i) {
+          const int idx = i * N_PROD + tid;       // consecutive threads -> consecutive chunks of one pixel row
+          const int prow = idx / chunks, ch = idx - prow * chunks;
+          const int gb = ch >> 3, gv = ch & 7;
+          const int c0 = nt * p.n_tile + ch * 8;  // first output channel of the chunk
+          const bool ok = (mbase + prow) < pix1 && ch * 8 < p.n_tile && c0 < p.g_cp;
+          const __nv_bfloat16* src = ok ? p.g + (size_t)(mbase + prow) * p.g_cp + c0 : p.g;
+          cp_async16(g_dst + gb * A_IMG + prow * 128 + ((gv ^ (prow & 7)) << 4), src, ok ? 16u : 0u);
+        }
+      }
+      cp_async_commit();
+      if (it >= L) {
+        cp_async_wait_dyn(L);
+        fence_proxy_async();
+        mbar_arrive(&full_bar[(it - L) % S]);
+      }
+    }
+    // ---- epilogue: TMEM -> fp32 reductions into dW --------------------------------------------
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;           // row of D = gathered channel (k-vector row/8, element row%8)
+    const int jr = mt * 16 + (row >> 3), e = row & 7;
+    int rtap = 0, rr = 0, rsg = 0;
+    bool row_ok = jr < p.nkv;
+    if (row_ok) {
+      rtap = jr / p.kv_per_tap; rr = jr - rtap * p.kv_per_tap;
+      while (rsg + 1 < p.n_seg && rr >= s_seg[rsg + 1].kv_begin) ++rsg;
+      const int cl = (rr - s_seg[rsg].kv_begin) * 8 + e;
+      row_ok = cl < p.seg_C[rsg];
+      rr = p.seg_cbegin[rsg] + cl;              // logical concat channel ci
+    }
+    const int KK = p.k * p.k;
+    float* dwrow = p.dw + (size_t)rr * KK + rtap;
+    for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+      uint32_t acc[16];
+      tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
+      tc_wait_ld();
+      if (row_ok) {
+#pragma unroll
+        for (int x = 0; x < 16; ++x) {
+          const int co = nt * p.n_tile + c0 + x;
+          if (co < p.Cout) atomicAdd(dwrow + (size_t)co * p.Ccat * KK, p.gscale * __uint_as_float(acc[x]));
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ---- MMA issuer -----------------------------------------------------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16_m128_mn(p.n_tile);
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % S;
+        mbar_wait(&full_bar[s], (it / S) & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t b_addr = a_addr + 2 * A_IMG;
+#pragma unroll
+        for (int q = 0; q < PIX / 16; ++q)   // 16 pixels (K) per UMMA: 16 rows of 128 bytes
+          tc_mma_bf16(tmem_base, smem_desc_mn_sw128(a_addr + q * 2048, A_IMG), smem_desc_mn_sw128(b_addr + q * 2048, A_IMG), idesc,
+                      (it | q) != 0);
+        tc_commit(&empty_bar[s]);
+      }
+      tc_commit(&tmem_full_bar);
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+}  // namespace
+
+int simt_dbias(mg_ctx* ctx, const mg_grid* g, int Cout, float* dbias, float gscale);
+
+bool umma_wgrad_supported(const mg_ctx* ctx, const mg_conv_desc* d) {
+  if (ctx->dtype != MG_BF16) return false;
+  if (d->n_seg < 1 || d->n_seg > MG_MAX_SEG) return false;
+  for (int s = 0; s < d->n_seg; ++s) {
+    const mg_grid& g = d->seg[s];
+    if (d->seg_mode[s] == MG_SEG_POOL || g.scale || g.shift || g.Cp % 8) return false;
+  }
+  return true;
+}
+
+int umma_conv_backward_weight(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g, float* dw, float* dbias, float gscale) {
+  WParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_seg = d->n_seg;
+  int c = 0, cp = 0;
+  for (int s = 0; s < d->n_seg; ++s) {
+    const mg_grid& sg = d->seg[s];
+    const int m = d->seg_mode[s];
+    if (m == MG_SEG_SAME) MG_REQUIRE(ctx, sg.H == d->H && sg.W == d->W, MG_ERR_SHAPE, "wgrad: SAME seg %d is %dx%d, expected %dx%d", s, sg.H, sg.W, d->H, d->W);
+    else MG_REQUIRE(ctx, sg.H * 2 == d->H && sg.W * 2 == d->W, MG_ERR_SHAPE, "wgrad: UP seg %d is %dx%d, x2 != %dx%d", s, sg.H, sg.W, d->H, d->W);
+    p.seg[s].ptr = (const __nv_bfloat16*)sg.data; p.seg[s].Hs = sg.H; p.seg[s].Ws = sg.W; p.seg[s].Cp = sg.Cp;
+    p.seg[s].shift = m == MG_SEG_UP ? 1 : 0; p.seg[s].kv_begin = cp / 8;
+    p.seg_C[s] = sg.C; p.seg_cbegin[s] = c;
+    c += sg.C; cp += sg.Cp;
+  }
+  p.k = d->ksize; p.stride = d->stride; p.pad = d->pad; p.H = d->H; p.W = d->W;
+  p.Ho = g->H; p.Wo = g->W;
+  p.M = (int64_t)g->N * g->H * g->W;
+  p.kv_per_tap = cp / 8; p.nkv = p.k * p.k * p.kv_per_tap;
+  p.g = (const __nv_bfloat16*)g->data; p.g_cp = g->Cp;
+  p.Cout = d->Cout; p.Ccat = c;
+  const int np = mg_round_up(d->Cout, 16);
+  const int n_tiles = (np + 255) / 256;
+  p.n_tile = mg_round_up((np + n_tiles - 1) / n_tiles, 16);
+  p.n_blk = (p.n_tile + 63) / 64;
+  p.dw = dw; p.gscale = gscale;
+  const int m_tiles = (p.nkv + 15) / 16;
+  // split the pixel range so that the grid covers the machine about twice
+  const int64_t want = 2 * (int64_t)ctx->num_sms;
+  int64_t splits = std::max<int64_t>(1, want / ((int64_t)m_tiles * n_tiles));
+  splits = std::min<int64_t>(splits, mg_cdiv(p.M, 4 * PIX));
+  splits = std::max<int64_t>(1, std::min<int64_t>(splits, 65535));
+  p.pix_per_cta = mg_round_up((int)mg_cdiv(p.M, splits), PIX);
+  const int z = (int)mg_cdiv(p.M, p.pix_per_cta);
+  const int stage_bytes = 2 * A_IMG + p.n_blk * A_IMG;
+  int S = std::min(W_MAX_STAGES, (200 * 1024) / stage_bytes);
+  const int iters = (int)(p.pix_per_cta / PIX);
+  S = std::max(2, std::min(S, std::max(2, iters)));
+  p.stages = S; p.lag = std::min(S - 1, 3);
+  int cols = 32;
+  while (cols < p.n_tile) cols <<= 1;
+  p.tmem_cols = cols;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MG_CUDA(ctx, cudaFuncSetAttribute(umma_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8 * 1024));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)z);
+  umma_wgrad_kernel<<<grid, W_THREADS, S * stage_bytes + 1024, ctx->stream>>>(p);
+  MG_CHECK_LAUNCH(ctx);
+  ctx->tc_launches++;
+  if (dbias) return simt_dbias(ctx, g, d->Cout, dbias, gscale);
+  return MG_OK;
+}

@@ -61,6 +61,7 @@ SIGNATURES = {
     "mg_last_error": (C.c_char_p, [_P]),
     "mg_version": (_I, []),
     "mg_ctx_launch_count": (_I, [_P, C.POINTER(_I64)]),
+    "mg_ctx_tc_launch_count": (_I, [_P, C.POINTER(_I64)]),
     "mg_ctx_profile": (_I, [_P, _I]),
     "mg_ctx_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(_I64)]),
     "mg_import_nchw": (_I, [_P, _P, _G]),
@@ -135,6 +136,11 @@ class Context:
     def launches(self):
         n = _I64(0)
         self.call("mg_ctx_launch_count", C.byref(n))
+        return n.value
+
+    def tc_launches(self):
+        n = _I64(0)
+        self.call("mg_ctx_tc_launch_count", C.byref(n))
         return n.value
 
     def profile_read(self):

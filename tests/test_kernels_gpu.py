@@ -146,7 +146,9 @@ def test_mgconv_forward_dgrad_wgrad(ctx, case, impl):
         ctx.call("mg_conv_pack_weights", C.byref(d), ptr(wd), ptr(wpack_t), 1)
     gy = Grid(ctx.dtype, N, Cout, H, H)
     sums = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
+    tc0 = ctx.tc_launches()
     ctx.call("mg_conv_forward", C.byref(d), ptr(wd), ptr(wpack), ptr(bd), C.byref(gy.g()), ptr(sums))
+    assert ctx.tc_launches() - tc0 == (1 if impl == "auto" else 0), "forward must run on the tcgen05 kernel in auto/bf16 mode"
     tol = TOL[ctx.dtype]
     y = gy.nchw()
     assert max_rel(y, y_ref) <= tol, max_rel(y, y_ref)
@@ -163,14 +165,18 @@ def test_mgconv_forward_dgrad_wgrad(ctx, case, impl):
     gg = Grid(ctx.dtype, N, Cout, H, H, g)
     cps = [gf.Cp, gs.Cp, gc.Cp]
     dcat = Grid(ctx.dtype, N, sum(cps), H, H, Cp=sum(cps))
+    tc0 = ctx.tc_launches()
     ctx.call("mg_conv_backward_data", C.byref(d), ptr(wd), ptr(wpack_t), C.byref(gg.g()), C.byref(dcat.g()))
+    assert ctx.tc_launches() - tc0 == (1 if impl == "auto" else 0), "dgrad must run on the tcgen05 kernel in auto/bf16 mode"
     dc = dcat.nchw()
     got = np.concatenate([dc[:, 0:cs[0]], dc[:, cps[0]:cps[0] + cs[1]], dc[:, cps[0] + cps[1]:cps[0] + cps[1] + cs[2]]], axis=1)
     assert max_rel(got, gcat_ref) <= tol, max_rel(got, gcat_ref)
     dw = torch.zeros_like(wd)
     db = torch.zeros_like(bd)
+    tc0 = ctx.tc_launches()
     ctx.call("mg_conv_backward_weight", C.byref(d), C.byref(gg.g()), ptr(dw), ptr(db), 1.0)
     ctx.call("mg_conv_backward_weight", C.byref(d), C.byref(gg.g()), ptr(dw), ptr(db), 0.5)  # accGradParameters accumulates
+    assert ctx.tc_launches() - tc0 == (2 if impl == "auto" else 0), "wgrad must run on the tcgen05 kernel in auto/bf16 mode"
     torch.cuda.synchronize()
     assert max_rel(dw.cpu().numpy(), 1.5 * gw_ref) <= tol, max_rel(dw.cpu().numpy(), 1.5 * gw_ref)
     assert max_rel(db.cpu().numpy(), 1.5 * gb_ref) <= tol

@@ -79,10 +79,17 @@ def max_rel(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
-def copy_params_from_oracle(omodel, model):
-    """oracle (torch.nn) parameters/buffers -> product modules, matched in construction order"""
+def copy_params_from_oracle(omodel, model, bf16_weights=False):
+    """oracle (torch.nn) parameters/buffers -> product modules, matched in construction order.
+    bf16_weights: first round the oracle's conv / linear weights to bf16-representable values, so
+    that the bf16 tensor-core path (which packs its operands to bf16) sees identical weights."""
     import torch.nn as tnn
     olist = [m for m in omodel.modules() if isinstance(m, (tnn.Conv2d, tnn.BatchNorm2d, tnn.Linear))]
+    if bf16_weights:
+        with torch.no_grad():
+            for o in olist:
+                if not isinstance(o, tnn.BatchNorm2d):
+                    o.weight.copy_(o.weight.to(torch.bfloat16).to(o.weight.dtype))
     plist = [m for m in model.listModules() if m.own_parameters()]
     assert len(olist) == len(plist), (len(olist), len(plist))
     for o, p in zip(olist, plist):
