@@ -84,6 +84,8 @@ typedef struct {
                        tensor (g is at the coarser size, route through the 2x2 argmax);
                        MG_SEG_UP: the consumer upsampled this tensor (g is finer, sum 2x2);
                        3 = the consumer applied SpatialMaxPooling(3,3,2,2,1,1) (stem) */
+  const void* aux;  /* mode 3: arg-max codes (uint8 [N][Ho][Wo][Cp], ky*3+kx) written by
+                       mg_pool3s2_forward, or NULL to recompute the arg-max from x */
 } mg_grad_src;
 
 /* ---- context ------------------------------------------------------------------------ */
@@ -146,7 +148,7 @@ int mg_copy_channels(mg_ctx* ctx, const mg_grid* in, mg_grid* out, int32_t c_off
 /* cudnn.SpatialAveragePooling(r,r,r,r) on NHWC (image pyramid, rnmg.lua:175-177) */
 int mg_avgpool_forward(mg_ctx* ctx, const mg_grid* in, int32_t r, mg_grid* out);
 /* SpatialMaxPooling(3,3,2,2,1,1) of the ImageNet stem (rnmg.lua:183) */
-int mg_pool3s2_forward(mg_ctx* ctx, const mg_grid* in, mg_grid* out);
+int mg_pool3s2_forward(mg_ctx* ctx, const mg_grid* in, mg_grid* out, uint8_t* argmax_code /* nullable, bf16 mode */);
 /* SelectTable(1) -> AvgPool(HxW) -> View: out[n][c] fp32 (rnmg.lua:281-283) */
 int mg_global_avgpool_forward(mg_ctx* ctx, const mg_grid* in, mg_grid* out);
 int mg_global_avgpool_backward(mg_ctx* ctx, const mg_grid* dout, mg_grid* din);

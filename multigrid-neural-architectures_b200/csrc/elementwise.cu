@@ -5,6 +5,13 @@
 #include "common.cuh"
 #include <algorithm>
 
+// bf16 fast paths (elementwise_bf16.cu); each returns false when it does not apply
+bool bf16_apply(mg_ctx*, const mg_grid* z, const mg_grid* s, int relu, mg_grid* out, mg_grid* pooled);
+bool bf16_bn_stats(mg_ctx*, const mg_grid* y, double* sums);
+bool bf16_combine(mg_ctx*, const mg_grid* x, int relu_mask, const mg_grid* bn_x, int n_src, const mg_grad_src* src, mg_grid* d, double* sums);
+bool bf16_bn_bwd_apply(mg_ctx*, const mg_grid* xraw, const mg_grid* d, mg_grid* out, const float* coef);
+bool bf16_pool3(mg_ctx*, const mg_grid* in, mg_grid* out, uint8_t* code);
+
 namespace {
 
 constexpr int EB = 256;
@@ -439,6 +446,10 @@ int mg_residual_forward(mg_ctx* ctx, const mg_grid* z, const mg_grid* s, int rel
     int Hp = (z->H + 1) / 2, Wp = (z->W + 1) / 2;
     MG_REQUIRE(ctx, pooled->N == z->N && pooled->H == Hp && pooled->W == Wp && pooled->C == z->C && pooled->Cp <= out->Cp,
                MG_ERR_SHAPE, "residual: pooled shape");
+  }
+  if (ctx->dtype == MG_BF16 && bf16_apply(ctx, z, s, relu, out, pooled)) { MG_CHECK_LAUNCH(ctx); return MG_OK; }
+  if (pooled) {
+    int Hp = (z->H + 1) / 2, Wp = (z->W + 1) / 2;
     int64_t total = (int64_t)z->N * Hp * Wp * out->Cp;
     MG_DISPATCH(ctx, residual_pool_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>(make_view<T>(*z), s ? make_view<T>(*s) : make_view<T>(*z),
                                                                                   s != nullptr, relu, (T*)out->data, out->Cp,
@@ -455,6 +466,7 @@ int mg_residual_forward(mg_ctx* ctx, const mg_grid* z, const mg_grid* s, int rel
 
 int mg_bn_stats(mg_ctx* ctx, const mg_grid* y, double* bn_sums) {
   if (!ctx || !y || !bn_sums) return MG_ERR_INVALID_ARG;
+  if (ctx->dtype == MG_BF16 && bf16_bn_stats(ctx, y, bn_sums)) { MG_CHECK_LAUNCH(ctx); return MG_OK; }
   int64_t P = (int64_t)y->N * y->H * y->W;
   int ppb = (int)std::max<int64_t>(64, mg_cdiv(P, (int64_t)ctx->num_sms * 8));
   dim3 grid((unsigned)mg_cdiv(P, ppb), (unsigned)mg_cdiv(y->C, 32));
@@ -499,10 +511,12 @@ int mg_avgpool_forward(mg_ctx* ctx, const mg_grid* in, int32_t r, mg_grid* out) 
   return MG_OK;
 }
 
-int mg_pool3s2_forward(mg_ctx* ctx, const mg_grid* in, mg_grid* out) {
+int mg_pool3s2_forward(mg_ctx* ctx, const mg_grid* in, mg_grid* out, uint8_t* argmax_code) {
   if (!ctx || !in || !out) return MG_ERR_INVALID_ARG;
   int Ho = (in->H + 2 - 3) / 2 + 1, Wo = (in->W + 2 - 3) / 2 + 1;
   MG_REQUIRE(ctx, out->H == Ho && out->W == Wo && out->N == in->N && out->C == in->C, MG_ERR_SHAPE, "pool3s2: shape");
+  if (ctx->dtype == MG_BF16 && bf16_pool3(ctx, in, out, argmax_code)) { MG_CHECK_LAUNCH(ctx); return MG_OK; }
+  MG_REQUIRE(ctx, argmax_code == nullptr, MG_ERR_UNSUPPORTED, "pool3s2: arg-max codes are only produced by the bf16 path");
   int64_t total = (int64_t)in->N * Ho * Wo * out->Cp;
   MG_DISPATCH(ctx, pool3_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>(make_view<T>(*in), (T*)out->data, Ho, Wo, out->Cp););
   MG_CHECK_LAUNCH(ctx);
@@ -542,6 +556,7 @@ int mg_grad_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid*
     MG_REQUIRE(ctx, ok, MG_ERR_SHAPE, "combine: src %d (mode %d, %dx%dx%d off %d) does not match x %dx%dx%d", s, m, g.H,
                g.W, g.Cp, src[s].c_offset, x->H, x->W, x->C);
   }
+  if (ctx->dtype == MG_BF16 && bf16_combine(ctx, x, relu_mask, bn_x, n_src, src, d, bn_sums)) { MG_CHECK_LAUNCH(ctx); return MG_OK; }
   int64_t P = (int64_t)x->N * x->H * x->W;
   MG_DISPATCH(ctx, {
     CombineP<T> p;
@@ -567,6 +582,7 @@ int mg_bn_backward(mg_ctx* ctx, const mg_grid* xraw, const mg_grid* d, mg_grid* 
   bn_bwd_coef_kernel<<<(unsigned)mg_cdiv(d->Cp, 128), 128, 0, ctx->stream>>>(bn_sums, count, d->C, d->Cp, gamma, save_mean, save_invstd,
                                                                    dgamma, dbeta, gscale, coef_ws);
   MG_CHECK_LAUNCH(ctx);
+  if (ctx->dtype == MG_BF16 && bf16_bn_bwd_apply(ctx, xraw, d, out, coef_ws)) { MG_CHECK_LAUNCH(ctx); return MG_OK; }
   int64_t P = (int64_t)d->N * d->H * d->W;
   MG_DISPATCH(ctx, bn_bwd_apply_kernel<T><<<GRID1(P * out->Cp), EB, 0, ctx->stream>>>((const T*)xraw->data, xraw->Cp, (const T*)d->data, d->Cp,
                                                                                       (T*)out->data, out->Cp, d->C, P, coef_ws););

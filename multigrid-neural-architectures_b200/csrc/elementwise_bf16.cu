@@ -1,0 +1,404 @@
+// bf16 fast paths of the HBM-bound passes: every thread moves 8 channels (16 bytes) of a pixel
+// -- or of a 2x2 pixel block when the pass pools, routes through an arg-max or sums an up-sampled
+// gradient -- so each byte of every tensor is read once per pass with 128-bit coalesced accesses.
+// Same arithmetic, expression for expression, as the generic kernels in elementwise.cu (which
+// remain the fp32 path and the fallback for unaligned channel offsets).
+#include "common.cuh"
+#include <algorithm>
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+struct V8 { float v[8]; };
+
+__device__ __forceinline__ V8 ld8(const bf16* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  V8 r;
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    r.v[2 * i] = __uint_as_float(w[i] << 16);
+    r.v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+  return r;
+}
+__device__ __forceinline__ uint4 pack8(const V8& a) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a.v[2 * i], a.v[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&t);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ V8 unpack8(const uint4& u) {
+  V8 r;
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    r.v[2 * i] = __uint_as_float(w[i] << 16);
+    r.v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+  return r;
+}
+__device__ __forceinline__ void ldf8(const float* p, float (&o)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+
+// per-block reduction of per-thread channel sums into fp64 global sums.
+// Threads of a block own vector column (gtid % V); V*8 <= 4096 channels.
+__device__ __forceinline__ void block_channel_sums(const float (&a)[8], const float (&b)[8], int vc, int V, int C, bool active,
+                                                   double* sums, float* sh /* [2 * V * 8] zeroed */) {
+  if (active) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { atomicAdd(&sh[vc * 8 + e], a[e]); atomicAdd(&sh[V * 8 + vc * 8 + e], b[e]); }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < V * 8; c += blockDim.x)
+    if (c < C) { atomicAdd(sums + c, (double)sh[c]); atomicAdd(sums + C + c, (double)sh[V * 8 + c]); }
+}
+
+// ---------------------------------------------------------------- apply (BN + shortcut + ReLU [+ pool]) ----
+struct ApplyP {
+  const bf16* z; int z_cp; const float* scale; const float* shift; int z_relu;
+  const bf16* s; int s_cp;      // shortcut or null; channels >= s_cp contribute nothing
+  int relu;
+  bf16* out; int o_cp;
+  bf16* pooled; int p_cp;       // or null
+  int N, H, W, C, Hp, Wp;
+};
+
+__global__ void __launch_bounds__(256) apply_bf16_kernel(ApplyP p) {
+  const int V = p.o_cp >> 3;
+  const int64_t total = (int64_t)p.N * p.Hp * p.Wp * V;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int vc = (int)(i % V); int64_t q = i / V;
+  const int px = (int)(q % p.Wp); q /= p.Wp;
+  const int py = (int)(q % p.Hp); const int n = (int)(q / p.Hp);
+  const int c0 = vc * 8;
+  float sc[8], sh[8];
+  const bool has_aff = p.scale != nullptr;
+  if (has_aff) { ldf8(p.scale + c0, sc); ldf8(p.shift + c0, sh); }
+  const bool has_s = p.s != nullptr && c0 < p.s_cp;
+  float best[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) best[e] = -INFINITY;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const int y = 2 * py + dy, x = 2 * px + dx;
+      if (y >= p.H || x >= p.W) continue;
+      const int64_t pix = ((int64_t)n * p.H + y) * p.W + x;
+      V8 v = ld8(p.z + pix * p.z_cp + c0);
+      if (has_aff) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v.v[e] = mg_xform(v.v[e], sc[e], sh[e], p.z_relu);
+      }
+      if (has_s) {
+        const V8 sv = ld8(p.s + pix * p.s_cp + c0);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v.v[e] += sv.v[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (p.relu) v.v[e] = fmaxf(v.v[e], 0.f);
+        if (c0 + e >= p.C) v.v[e] = 0.f;
+      }
+      const uint4 u = pack8(v);
+      *reinterpret_cast<uint4*>(p.out + pix * p.o_cp + c0) = u;
+      const V8 r = unpack8(u);   // pool what was stored
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (r.v[e] > best[e] || r.v[e] != r.v[e]) best[e] = r.v[e];
+    }
+  if (p.pooled && c0 < p.p_cp) {
+    V8 b;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) b.v[e] = (c0 + e < p.C) ? best[e] : 0.f;
+    *reinterpret_cast<uint4*>(p.pooled + (((int64_t)n * p.Hp + py) * p.Wp + px) * p.p_cp + c0) = pack8(b);
+  }
+}
+
+// ---------------------------------------------------------------- BN statistics ----------
+__global__ void __launch_bounds__(256) bn_stats_bf16_kernel(const bf16* __restrict__ y, int cp, int C, int64_t P, double* sums) {
+  extern __shared__ float sh[];
+  const int V = cp >> 3;
+  for (int c = threadIdx.x; c < 2 * V * 8; c += blockDim.x) sh[c] = 0.f;
+  __syncthreads();
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const int64_t lanes = nthreads / V;          // pixel lanes; threads beyond lanes*V idle
+  const int vc = (int)(gtid % V);
+  const int64_t lane = gtid / V;
+  float a[8], b[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { a[e] = 0.f; b[e] = 0.f; }
+  const bool active = lane < lanes;
+  if (active)
+    for (int64_t pix = lane; pix < P; pix += lanes) {
+      const V8 v = ld8(y + pix * cp + vc * 8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { a[e] += v.v[e]; b[e] = fmaf(v.v[e], v.v[e], b[e]); }
+    }
+  block_channel_sums(a, b, vc, V, C, active, sums, sh);
+}
+
+// ---------------------------------------------------------------- gradient combine ----------
+struct CSrc { const bf16* g; const uint8_t* aux; int H, W, cp, c_off, mode; };
+struct CombP {
+  const bf16* x; int x_cp;       // activation tensor (ReLU mask, pool arg-max)
+  const bf16* bnx; int bn_cp;    // raw conv output for the BatchNorm sums, or null
+  int relu_mask;
+  int n_src; CSrc src[MG_MAX_SRC];
+  bf16* d; int d_cp;
+  double* sums;
+  int N, H, W, C, Hb, Wb;        // Hb = ceil(H/2): 2x2 blocks
+};
+
+__global__ void __launch_bounds__(256) combine_bf16_kernel(CombP p) {
+  extern __shared__ float sh[];
+  const int V = p.d_cp >> 3;
+  if (p.sums) {
+    for (int c = threadIdx.x; c < 2 * V * 8; c += blockDim.x) sh[c] = 0.f;
+    __syncthreads();
+  }
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const int64_t lanes = nthreads / V;
+  const int vc = (int)(gtid % V);
+  const int c0 = vc * 8;
+  const int64_t lane = gtid / V;
+  const int64_t nblocks = (int64_t)p.N * p.Hb * p.Wb;
+  const bool active = lane < lanes;
+  float sd[8], sdx[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sd[e] = 0.f; sdx[e] = 0.f; }
+  bool need_x = p.relu_mask != 0;
+  for (int s = 0; s < p.n_src; ++s) need_x = need_x || p.src[s].mode == MG_SEG_POOL;
+
+  if (active)
+    for (int64_t blk = lane; blk < nblocks; blk += lanes) {
+      const int bx = (int)(blk % p.Wb); int64_t q = blk / p.Wb;
+      const int by = (int)(q % p.Hb); const int n = (int)(q / p.Hb);
+      const int y0 = 2 * by, x0 = 2 * bx;
+      const bool vy1 = y0 + 1 < p.H, vx1 = x0 + 1 < p.W;
+      const bool valid[4] = {true, vx1, vy1, vy1 && vx1};
+      int64_t pix[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pix[k] = ((int64_t)n * p.H + y0 + (k >> 1)) * p.W + x0 + (k & 1);
+      V8 X[4];
+      if (need_x) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (valid[k]) X[k] = ld8(p.x + pix[k] * p.x_cp + c0);
+      }
+      V8 acc[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[k].v[e] = 0.f;
+
+      for (int s = 0; s < p.n_src; ++s) {
+        const CSrc S = p.src[s];
+        if (S.mode == MG_SEG_SAME) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (valid[k]) {
+              const V8 g = ld8(S.g + pix[k] * S.cp + S.c_off + c0);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[k].v[e] += g.v[e];
+            }
+        } else if (S.mode == MG_SEG_UP) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (valid[k]) {
+              const int y = y0 + (k >> 1), x = x0 + (k & 1);
+              const bf16* gp = S.g + (((int64_t)n * S.H + 2 * y) * S.W + 2 * x) * S.cp + S.c_off + c0;
+              const V8 g0 = ld8(gp), g1 = ld8(gp + S.cp), g2 = ld8(gp + (int64_t)S.W * S.cp), g3 = ld8(gp + (int64_t)S.W * S.cp + S.cp);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[k].v[e] += g0.v[e] + g1.v[e] + g2.v[e] + g3.v[e];
+            }
+        } else if (S.mode == MG_SEG_POOL) {
+          // this 2x2 block is exactly one pooling window: route to the first maximum (row-major scan)
+          const V8 g = ld8(S.g + (((int64_t)n * S.H + by) * S.W + bx) * S.cp + S.c_off + c0);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float best = -INFINITY; int bi = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (valid[k]) { const float v = X[k].v[e]; if (v > best || v != v) { best = v; bi = k; } }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (bi == k) acc[k].v[e] += g.v[e];
+          }
+        } else {
+          // SpatialMaxPooling(3,3,2,2,1,1) of the stem: arg-max code (ky*3+kx) stored by the forward pass
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (valid[k]) {
+              const int y = y0 + (k >> 1), x = x0 + (k & 1);
+              const int oy0 = max(y / 2, 0), oy1 = min((y + 1) / 2, S.H - 1);
+              const int ox0 = max(x / 2, 0), ox1 = min((x + 1) / 2, S.W - 1);
+              for (int oy = oy0; oy <= oy1; ++oy)
+                for (int ox = ox0; ox <= ox1; ++ox) {
+                  const int64_t o = ((int64_t)n * S.H + oy) * S.W + ox;
+                  const uint2 code = *reinterpret_cast<const uint2*>(S.aux + o * S.cp + S.c_off + c0);
+                  const int want = (y - (2 * oy - 1)) * 3 + (x - (2 * ox - 1));
+                  const V8 g = ld8(S.g + o * S.cp + S.c_off + c0);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    const int cd = ((e < 4 ? code.x : code.y) >> (8 * (e & 3))) & 0xFF;
+                    if (cd == want) acc[k].v[e] += g.v[e];
+                  }
+                }
+            }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (valid[k]) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if (p.relu_mask && !(X[k].v[e] > 0.f)) acc[k].v[e] = 0.f;
+            if (c0 + e >= p.C) acc[k].v[e] = 0.f;
+          }
+          if (p.sums) {
+            const V8 yr = ld8(p.bnx + pix[k] * p.bn_cp + c0);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { sd[e] += acc[k].v[e]; sdx[e] = fmaf(acc[k].v[e], yr.v[e], sdx[e]); }
+          }
+          *reinterpret_cast<uint4*>(p.d + pix[k] * p.d_cp + c0) = pack8(acc[k]);
+        }
+    }
+  if (p.sums) block_channel_sums(sd, sdx, vc, V, p.C, active, p.sums, sh);
+}
+
+// ---------------------------------------------------------------- BN backward apply ----------
+__global__ void __launch_bounds__(256) bn_bwd_apply_bf16_kernel(const bf16* __restrict__ xraw, int x_cp, const bf16* d, int d_cp, bf16* out,
+                                                                int o_cp, int C, int64_t P, const float* __restrict__ coef) {
+  const int V = o_cp >> 3;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * V) return;
+  const int vc = (int)(i % V); const int64_t pix = i / V;
+  const int c0 = vc * 8;
+  float A[8], B[8], Cc[8];
+  ldf8(coef + c0, A); ldf8(coef + d_cp + c0, B); ldf8(coef + 2 * d_cp + c0, Cc);
+  const V8 dv = ld8(d + pix * d_cp + c0), xv = ld8(xraw + pix * x_cp + c0);
+  V8 o;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o.v[e] = (c0 + e < C) ? fmaf(A[e], dv.v[e], fmaf(B[e], xv.v[e], Cc[e])) : 0.f;
+  *reinterpret_cast<uint4*>(out + pix * o_cp + c0) = pack8(o);
+}
+
+// ---------------------------------------------------------------- stem max-pool with arg-max codes ----------
+__global__ void __launch_bounds__(256) pool3_bf16_kernel(const bf16* __restrict__ in, int H, int W, int cp, int C, bf16* __restrict__ out,
+                                                         uint8_t* __restrict__ code, int Ho, int Wo, int N) {
+  const int V = cp >> 3;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)N * Ho * Wo * V) return;
+  const int vc = (int)(i % V); int64_t q = i / V;
+  const int ox = (int)(q % Wo); q /= Wo;
+  const int oy = (int)(q % Ho); const int n = (int)(q / Ho);
+  const int c0 = vc * 8;
+  float best[8]; int bc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; bc[e] = -1; }
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      const int y = 2 * oy - 1 + ky, x = 2 * ox - 1 + kx;
+      if (y < 0 || y >= H || x < 0 || x >= W) continue;
+      const V8 v = ld8(in + (((int64_t)n * H + y) * W + x) * cp + c0);
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (v.v[e] > best[e] || v.v[e] != v.v[e] || bc[e] < 0) { best[e] = v.v[e]; bc[e] = ky * 3 + kx; }
+    }
+  V8 b;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) b.v[e] = (c0 + e < C) ? best[e] : 0.f;
+  const int64_t o = ((int64_t)n * Ho + oy) * Wo + ox;
+  *reinterpret_cast<uint4*>(out + o * cp + c0) = pack8(b);
+  if (code) {
+    uint2 cd;
+    cd.x = (uint32_t)bc[0] | ((uint32_t)bc[1] << 8) | ((uint32_t)bc[2] << 16) | ((uint32_t)bc[3] << 24);
+    cd.y = (uint32_t)bc[4] | ((uint32_t)bc[5] << 8) | ((uint32_t)bc[6] << 16) | ((uint32_t)bc[7] << 24);
+    *reinterpret_cast<uint2*>(code + o * cp + c0) = cd;
+  }
+}
+
+static inline unsigned grid_for(int64_t threads) { return (unsigned)mg_cdiv(threads, 256); }
+// persistent-style grid for the reducing kernels: a few CTAs per SM, each thread loops
+static inline unsigned reduce_grid(const mg_ctx* ctx, int64_t items) {
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(mg_cdiv(items, 256), (int64_t)ctx->num_sms * 8));
+}
+
+}  // namespace
+
+// ---- entry points used by elementwise.cu; return false when the fast path does not apply -------------
+bool bf16_apply(mg_ctx* ctx, const mg_grid* z, const mg_grid* s, int relu, mg_grid* out, mg_grid* pooled) {
+  if (s && (s->scale || s->Cp % 8)) return false;
+  if (z->Cp % 8 || out->Cp % 8 || z->Cp < out->Cp) return false;
+  if (pooled && pooled->Cp % 8) return false;
+  ApplyP p;
+  p.z = (const bf16*)z->data; p.z_cp = z->Cp; p.scale = z->scale; p.shift = z->shift; p.z_relu = z->relu;
+  p.s = s ? (const bf16*)s->data : nullptr; p.s_cp = s ? s->Cp : 0;
+  p.relu = relu; p.out = (bf16*)out->data; p.o_cp = out->Cp;
+  p.pooled = pooled ? (bf16*)pooled->data : nullptr; p.p_cp = pooled ? pooled->Cp : 0;
+  p.N = z->N; p.H = z->H; p.W = z->W; p.C = z->C; p.Hp = (z->H + 1) / 2; p.Wp = (z->W + 1) / 2;
+  const int64_t total = (int64_t)p.N * p.Hp * p.Wp * (p.o_cp / 8);
+  apply_bf16_kernel<<<grid_for(total), 256, 0, ctx->stream>>>(p);
+  return true;
+}
+
+bool bf16_bn_stats(mg_ctx* ctx, const mg_grid* y, double* sums) {
+  if (y->Cp % 8 || y->Cp > 4096) return false;
+  const int64_t P = (int64_t)y->N * y->H * y->W;
+  const int V = y->Cp / 8;
+  bn_stats_bf16_kernel<<<reduce_grid(ctx, P * V / 4), 256, 2 * V * 8 * sizeof(float), ctx->stream>>>((const bf16*)y->data, y->Cp, y->C, P, sums);
+  return true;
+}
+
+bool bf16_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid* bn_x, int n_src, const mg_grad_src* src, mg_grid* d,
+                  double* sums) {
+  if (x->Cp % 8 || d->Cp % 8 || d->Cp > 4096 || x->scale || x->Cp < d->Cp) return false;
+  if (sums && bn_x && bn_x->Cp < d->Cp) return false;
+  CombP p;
+  memset(&p, 0, sizeof(p));
+  for (int s = 0; s < n_src; ++s) {
+    const mg_grad_src& g = src[s];
+    if (g.c_offset % 8 || g.g.Cp % 8 || g.c_offset + d->Cp > g.g.Cp) return false;
+    if (g.mode == 3 && !g.aux) return false;
+    p.src[s].g = (const bf16*)g.g.data; p.src[s].aux = (const uint8_t*)g.aux;
+    p.src[s].H = g.g.H; p.src[s].W = g.g.W; p.src[s].cp = g.g.Cp; p.src[s].c_off = g.c_offset; p.src[s].mode = g.mode;
+  }
+  p.n_src = n_src;
+  p.x = (const bf16*)x->data; p.x_cp = x->Cp;
+  const mg_grid* bx = bn_x ? bn_x : x;
+  p.bnx = (const bf16*)bx->data; p.bn_cp = bx->Cp;
+  p.relu_mask = relu_mask; p.d = (bf16*)d->data; p.d_cp = d->Cp; p.sums = sums;
+  p.N = x->N; p.H = x->H; p.W = x->W; p.C = x->C; p.Hb = (x->H + 1) / 2; p.Wb = (x->W + 1) / 2;
+  const int V = d->Cp / 8;
+  const int64_t items = (int64_t)p.N * p.Hb * p.Wb * V;
+  const unsigned grid = sums ? reduce_grid(ctx, items) : (unsigned)std::max<int64_t>(1, std::min<int64_t>(mg_cdiv(items, 256), (int64_t)ctx->num_sms * 16));
+  combine_bf16_kernel<<<grid, 256, 2 * V * 8 * sizeof(float), ctx->stream>>>(p);
+  return true;
+}
+
+bool bf16_bn_bwd_apply(mg_ctx* ctx, const mg_grid* xraw, const mg_grid* d, mg_grid* out, const float* coef) {
+  if (xraw->Cp % 8 || d->Cp % 8 || out->Cp % 8 || d->Cp != out->Cp || xraw->Cp < out->Cp) return false;
+  const int64_t P = (int64_t)d->N * d->H * d->W;
+  bn_bwd_apply_bf16_kernel<<<grid_for(P * (out->Cp / 8)), 256, 0, ctx->stream>>>((const bf16*)xraw->data, xraw->Cp, (const bf16*)d->data, d->Cp,
+                                                                           (bf16*)out->data, out->Cp, d->C, P, coef);
+  return true;
+}
+
+bool bf16_pool3(mg_ctx* ctx, const mg_grid* in, mg_grid* out, uint8_t* code) {
+  if (in->Cp % 8 || in->Cp != out->Cp || in->scale) return false;
+  const int64_t total = (int64_t)in->N * out->H * out->W * (in->Cp / 8);
+  pool3_bf16_kernel<<<grid_for(total), 256, 0, ctx->stream>>>((const bf16*)in->data, in->H, in->W, in->Cp, in->C, (bf16*)out->data, code,
+                                                             out->H, out->W, in->N);
+  return true;
+}

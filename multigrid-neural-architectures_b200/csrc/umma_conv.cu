@@ -58,7 +58,7 @@ __host__ __device__ constexpr uint32_t idesc_bf16_m128(int n) {
 }
 
 // ---------------------------------------------------------------- the kernel ---------------
-__global__ void __launch_bounds__(N_THREADS, 1) umma_conv_kernel(const __grid_constant__ UParams p) {
+__global__ void __launch_bounds__(N_THREADS, 2) umma_conv_kernel(const __grid_constant__ UParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 bytes the swizzle atoms need
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -293,7 +293,9 @@ static int pick_stages(int n_tile, int* smem_bytes) {
   const int stage = A_STAGE_BYTES + n_tile * 128;
   static int forced = -1;
   if (forced < 0) { const char* e = getenv("MGCONV_STAGES"); forced = e ? atoi(e) : 0; }
-  int S = forced > 0 ? forced : std::min(MAX_STAGES, (200 * 1024) / stage);
+  static int budget_kb = -1;   // per-CTA shared memory target: ~108 KB keeps two CTAs resident per SM
+  if (budget_kb < 0) { const char* e = getenv("MGCONV_SMEM_KB"); budget_kb = e ? atoi(e) : 108; }
+  int S = forced > 0 ? forced : std::min(MAX_STAGES, (budget_kb * 1024) / stage);
   S = std::max(2, std::min(S, MAX_STAGES));
   *smem_bytes = S * stage + 1024;  // + alignment slack
   return S;

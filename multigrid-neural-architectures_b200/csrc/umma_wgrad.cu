@@ -48,7 +48,7 @@ __host__ __device__ constexpr uint32_t idesc_bf16_m128_mn(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(WM >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(W_THREADS, 1) umma_wgrad_kernel(const __grid_constant__ WParams p) {
+__global__ void __launch_bounds__(W_THREADS, 2) umma_wgrad_kernel(const __grid_constant__ WParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t full_bar[W_MAX_STAGES], empty_bar[W_MAX_STAGES], tmem_full_bar;
@@ -244,7 +244,9 @@ int umma_conv_backward_weight(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid*
   p.pix_per_cta = mg_round_up((int)mg_cdiv(p.M, splits), PIX);
   const int z = (int)mg_cdiv(p.M, p.pix_per_cta);
   const int stage_bytes = 2 * A_IMG + p.n_blk * A_IMG;
-  int S = std::min(W_MAX_STAGES, (200 * 1024) / stage_bytes);
+  static int budget_kb = -1;
+  if (budget_kb < 0) { const char* e = getenv("MGCONV_SMEM_KB"); budget_kb = e ? atoi(e) : 108; }
+  int S = std::min(W_MAX_STAGES, (budget_kb * 1024) / stage_bytes);
   const int iters = (int)(p.pix_per_cta / PIX);
   S = std::max(2, std::min(S, std::max(2, iters)));
   p.stages = S; p.lag = std::min(S - 1, 3);

@@ -34,7 +34,7 @@ class mg_conv_desc(C.Structure):
 
 
 class mg_grad_src(C.Structure):
-    _fields_ = [("g", mg_grid), ("c_offset", C.c_int32), ("mode", C.c_int32)]
+    _fields_ = [("g", mg_grid), ("c_offset", C.c_int32), ("mode", C.c_int32), ("aux", C.c_void_p)]
 
 
 def _load():
@@ -76,7 +76,7 @@ SIGNATURES = {
     "mg_pool_forward": (_I, [_P, _G, _G, C.c_int32, _P]),
     "mg_copy_channels": (_I, [_P, _G, _G, C.c_int32]),
     "mg_avgpool_forward": (_I, [_P, _G, C.c_int32, _G]),
-    "mg_pool3s2_forward": (_I, [_P, _G, _G]),
+    "mg_pool3s2_forward": (_I, [_P, _G, _G, _P]),
     "mg_global_avgpool_forward": (_I, [_P, _G, _G]),
     "mg_global_avgpool_backward": (_I, [_P, _G, _G]),
     "mg_grad_combine": (_I, [_P, _G, _I, _G, C.c_int32, C.POINTER(mg_grad_src), _G, _P]),

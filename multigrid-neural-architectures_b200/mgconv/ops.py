@@ -44,8 +44,8 @@ class TSpec:
 class Src:
     """one gradient contribution: grid `buf` [N,H,W,Cp] read at channel offset c_off through `mode`"""
 
-    def __init__(self, buf, H, W, C, Cp, c_off, mode):
-        self.buf, self.H, self.W, self.C, self.Cp, self.c_off, self.mode = buf, H, W, C, Cp, c_off, mode
+    def __init__(self, buf, H, W, C, Cp, c_off, mode, aux=None):
+        self.buf, self.H, self.W, self.C, self.Cp, self.c_off, self.mode, self.aux = buf, H, W, C, Cp, c_off, mode, aux
 
 
 class Combine:
@@ -72,6 +72,7 @@ class Combine:
             self.arr[i].g = mg_grid(s.buf.data_ptr(), None, None, 0, t.N, s.H, s.W, s.C, s.Cp)
             self.arr[i].c_offset = s.c_off
             self.arr[i].mode = s.mode
+            self.arr[i].aux = None if s.aux is None else s.aux.data_ptr()
         self.n = len(srcs)
         self.relu_mask = int(relu_mask)
         self.sums = sums
@@ -334,16 +335,18 @@ class Pool3Op(Op):
     def setup_fwd(self, E):
         self.out.buf = E.alloc(self.out.shape())
         self.gi, self.go = self.inp.grid(), self.out.grid()
+        # arg-max codes for the backward routing (1 byte / element), bf16 mode only
+        self.code = E.alloc(self.out.shape(), torch.uint8) if (E.dtype == ffi.MG_BF16 and self.inp.needs_grad) else None
 
     def fwd(self, E):
-        E.ctx.call("mg_pool3s2_forward", C.byref(self.gi), C.byref(self.go))
+        E.ctx.call("mg_pool3s2_forward", C.byref(self.gi), C.byref(self.go), ptr(self.code))
 
     def setup_bwd(self, E):
         t = self.out
         self.comb = None
         if self.inp.needs_grad:
             self.comb = Combine(E, t)
-            self.inp.srcs.append(Src(self.comb.buf, t.H, t.W, t.C, t.Cp, 0, MG_SRC_POOL3))
+            self.inp.srcs.append(Src(self.comb.buf, t.H, t.W, t.C, t.Cp, 0, MG_SRC_POOL3, aux=self.code))
 
     def bwd(self, E):
         if self.comb is not None:

@@ -45,7 +45,7 @@ def test_struct_layout_matches_header():
     from mgconv import ffi
     assert ctypes.sizeof(ffi.mg_grid) == 48
     assert ctypes.sizeof(ffi.mg_conv_desc) == 8 + 6 * 48 + 6 * 4 + 6 * 4
-    assert ctypes.sizeof(ffi.mg_grad_src) == 56
+    assert ctypes.sizeof(ffi.mg_grad_src) == 64
 
 
 KNOWN = [  # netType, opt, input, params, conv+linear MACs  (README.md:85-92,109)

@@ -76,8 +76,14 @@ def test_stem_pool3x3s2p1(ctx):
     x = rnd(2, 9, 12, 12)
     y, _ = O.maxpool_forward(x, 3, 2, 1, ceil_mode=False)
     gi, go = Grid(ctx.dtype, 2, 9, 12, 12, x), Grid(ctx.dtype, 2, 9, 6, 6)
-    ctx.call("mg_pool3s2_forward", C.byref(gi.g()), C.byref(go.g()))
+    code = torch.zeros((2, 6, 6, go.Cp), dtype=torch.uint8, device="cuda") if ctx.dtype == ffi.MG_BF16 else None
+    ctx.call("mg_pool3s2_forward", C.byref(gi.g()), C.byref(go.g()), ptr(code))
     assert np.array_equal(go.nchw(), y)
+    if code is not None:  # arg-max codes ky*3+kx of the 3x3 window <-> the oracle's flat input index
+        _, idx = O.maxpool_forward(x, 3, 2, 1, ceil_mode=False)
+        cd = code[..., :9].permute(0, 3, 1, 2).cpu().numpy().astype(np.int64)
+        oy, ox = np.meshgrid(np.arange(6), np.arange(6), indexing="ij")
+        assert np.array_equal((2 * oy - 1 + cd // 3) * 12 + (2 * ox - 1 + cd % 3), idx)
 
 
 def test_avgpool_and_global_avgpool(ctx):
@@ -319,8 +325,16 @@ def test_grad_combine_stem_pool3(ctx):
     gx, gg, gd = Grid(ctx.dtype, 2, 5, 12, 12, x), Grid(ctx.dtype, 2, 5, 6, 6, g), Grid(ctx.dtype, 2, 5, 12, 12)
     src = (mg_grad_src * 1)()
     src[0].g, src[0].c_offset, src[0].mode = gg.g(), 0, MG_SRC_POOL3
-    ctx.call("mg_grad_combine", C.byref(gx.g()), 0, None, 1, src, C.byref(gd.g()), None)
+    ctx.call("mg_grad_combine", C.byref(gx.g()), 0, None, 1, src, C.byref(gd.g()), None)   # arg-max recomputed from x
     assert max_rel(gd.nchw(), O.maxpool_backward(g, idx, x.shape)) <= TOL[ctx.dtype]
+    if ctx.dtype == ffi.MG_BF16:  # routed through the arg-max codes written by the forward pass
+        gp = Grid(ctx.dtype, 2, 5, 6, 6)
+        code = torch.zeros((2, 6, 6, gp.Cp), dtype=torch.uint8, device="cuda")
+        ctx.call("mg_pool3s2_forward", C.byref(gx.g()), C.byref(gp.g()), ptr(code))
+        src[0].aux = code.data_ptr()
+        gd2 = Grid(ctx.dtype, 2, 5, 12, 12)
+        ctx.call("mg_grad_combine", C.byref(gx.g()), 0, None, 1, src, C.byref(gd2.g()), None)
+        assert max_rel(gd2.nchw(), O.maxpool_backward(g, idx, x.shape)) <= TOL[ctx.dtype]  # overlapping windows: sums round
 
 
 # ---------------------------------------------------------------- head, criteria, optimiser
