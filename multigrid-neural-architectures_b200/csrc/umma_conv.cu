@@ -58,7 +58,8 @@ __host__ __device__ constexpr uint32_t idesc_bf16_m128(int n) {
 }
 
 // ---------------------------------------------------------------- the kernel ---------------
-__global__ void __launch_bounds__(N_THREADS, 2) umma_conv_kernel(const __grid_constant__ UParams p) {
+template <bool FAST>
+__global__ void __launch_bounds__(N_THREADS, 4) umma_conv_kernel(const __grid_constant__ UParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // dynamic smem is only guaranteed 16-byte aligned: round up to the 1024 bytes the swizzle atoms need
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -106,39 +107,114 @@ __global__ void __launch_bounds__(N_THREADS, 2) umma_conv_kernel(const __grid_co
     const int v = tid & 7;       // k-vector slot of the stage (16-byte column of the 128-byte row)
     const int rg = tid >> 3;     // row group 0..15; rows rg, rg+16, ...
     const int L = p.lag;
-    for (int ks = 0; ks < p.n_stages + L; ++ks) {
-      if (ks < p.n_stages) {
-        const int s = ks % S;
-        if (ks >= S) mbar_wait(&empty_bar[s], ((ks / S) - 1) & 1);
-        // decode this lane's k-vector: (tap, segment, channel offset)
-        const int j = ks * KV_PER_STAGE + v;
-        const bool kv_ok = j < p.nkv;
-        int tap = 0, r = 0, sg = 0;
-        if (kv_ok) {
-          tap = j / p.kv_per_tap; r = j - tap * p.kv_per_tap;
-          while (sg + 1 < p.n_seg && r >= s_seg[sg + 1].kv_begin) ++sg;
-        }
-        const USeg sgm = s_seg[sg];
-        const int c8 = r - sgm.kv_begin;
-        const int dy = tap / p.k - p.pad, dx = tap % p.k - p.pad;
-        const uint32_t dst0 = smem_u32(a_smem + (size_t)s * A_STAGE_BYTES);
+    if (FAST) {
+      // stride 1, "same" padding, k in {1,3}: everything that depends on the pixel is computed once per
+      // CTA -- linear pixel index (SAME segments), half-resolution pixel index (UP segments) and a
+      // validity bit per tap -- so that one k-vector copy costs a handful of instructions.
+      uint32_t pix_up[BM / 16], flags[BM / 16];
+      const uint32_t pix_same0 = (uint32_t)m0 + rg;   // pixel index of row it*16+rg = pix_same0 + it*16
+      const int Hs2 = p.H >> 1, Ws2 = p.W >> 1;
 #pragma unroll
-        for (int it = 0; it < BM / 16; ++it) {
-          const int row = it * 16 + rg;
-          const uint32_t ri = s_row[row];
-          const int ox = ri & 1023, oy = (ri >> 10) & 1023, n = ri >> 20;
-          const int iy = oy * p.stride + dy, ix = ox * p.stride + dx;
-          const bool ok = kv_ok && ri != 0xFFFFFFFFu && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
-          const __nv_bfloat16* src = sgm.ptr;
-          if (ok) src += ((size_t)((size_t)n * sgm.Hs + (iy >> sgm.shift)) * sgm.Ws + (ix >> sgm.shift)) * sgm.Cp + c8 * 8;
-          cp_async16(dst0 + row * 128 + ((v ^ (row & 7)) << 4), src, ok ? 16u : 0u);
+      for (int it = 0; it < BM / 16; ++it) {
+        const uint32_t ri = s_row[it * 16 + rg];
+        const int ox = ri & 1023, oy = (ri >> 10) & 1023, n = ri >> 20;
+        uint32_t f = 0;
+        if (ri != 0xFFFFFFFFu) {
+          for (int t = 0; t < p.k * p.k; ++t) {
+            const int iy = oy + t / p.k - p.pad, ix = ox + t % p.k - p.pad;
+            if ((unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W) f |= 1u << t;
+          }
+          f |= (uint32_t)(oy & 1) << 9 | (uint32_t)(ox & 1) << 10;
+          pix_up[it] = (uint32_t)(((size_t)n * Hs2 + (oy >> 1)) * Ws2 + (ox >> 1));
+        } else {
+          pix_up[it] = 0;
+        }
+        flags[it] = f;
+      }
+      const uint32_t dst_thread = (uint32_t)(rg * 128 + ((v ^ (rg & 7)) << 4));  // (it*16+rg)&7 == rg&7
+      for (int ks = 0; ks < p.n_stages + L; ++ks) {
+        if (ks < p.n_stages) {
+          const int s = ks % S;
+          if (ks >= S) mbar_wait(&empty_bar[s], ((ks / S) - 1) & 1);
+          const int j = ks * KV_PER_STAGE + v;
+          const bool kv_ok = j < p.nkv;
+          int tap = 0, r = 0, sg = 0;
+          if (kv_ok) {
+            tap = j / p.kv_per_tap; r = j - tap * p.kv_per_tap;
+            while (sg + 1 < p.n_seg && r >= s_seg[sg + 1].kv_begin) ++sg;
+          }
+          const USeg sgm = s_seg[sg];
+          const int c8 = r - sgm.kv_begin;
+          const int dy = tap / p.k - p.pad, dx = tap % p.k - p.pad;
+          const uint32_t dst0 = smem_u32(a_smem + (size_t)s * A_STAGE_BYTES) + dst_thread;
+          const uint32_t tapbit = kv_ok ? (1u << tap) : 0u;
+          const uint32_t pitch = (uint32_t)sgm.Cp * 2u;
+          const char* base = reinterpret_cast<const char*>(sgm.ptr) + c8 * 16;
+          if (sgm.shift == 0) {
+            base += (int64_t)(dy * p.W + dx) * (int64_t)pitch;
+#pragma unroll
+            for (int it = 0; it < BM / 16; ++it) {
+              const bool ok = (flags[it] & tapbit) != 0;
+              const char* src = ok ? base + (uint64_t)(pix_same0 + it * 16) * pitch : reinterpret_cast<const char*>(sgm.ptr);
+              cp_async16(dst0 + it * 2048, src, ok ? 16u : 0u);
+            }
+          } else {
+            // (o+d)>>1 - (o>>1):  d=-1 -> -1 if o even;  d=+1 -> +1 if o odd
+#pragma unroll
+            for (int it = 0; it < BM / 16; ++it) {
+              const uint32_t f = flags[it];
+              const bool ok = (f & tapbit) != 0;
+              const int py = (f >> 9) & 1, px = (f >> 10) & 1;
+              const int dyo = dy < 0 ? py - 1 : (dy > 0 ? py : 0);
+              const int dxo = dx < 0 ? px - 1 : (dx > 0 ? px : 0);
+              const char* src = ok ? base + (int64_t)((int64_t)pix_up[it] + dyo * Ws2 + dxo) * (int64_t)pitch
+                                   : reinterpret_cast<const char*>(sgm.ptr);
+              cp_async16(dst0 + it * 2048, src, ok ? 16u : 0u);
+            }
+          }
+        }
+        cp_async_commit();
+        if (ks >= L) {
+          cp_async_wait_dyn(L);
+          fence_proxy_async();
+          mbar_arrive(&full_bar[(ks - L) % S]);
         }
       }
-      cp_async_commit();
-      if (ks >= L) {  // stage ks-L has landed for this thread: publish it to the tensor core (async proxy)
-        cp_async_wait_dyn(L);
-        fence_proxy_async();
-        mbar_arrive(&full_bar[(ks - L) % S]);
+    } else {
+      for (int ks = 0; ks < p.n_stages + L; ++ks) {
+        if (ks < p.n_stages) {
+          const int s = ks % S;
+          if (ks >= S) mbar_wait(&empty_bar[s], ((ks / S) - 1) & 1);
+          // decode this lane's k-vector: (tap, segment, channel offset)
+          const int j = ks * KV_PER_STAGE + v;
+          const bool kv_ok = j < p.nkv;
+          int tap = 0, r = 0, sg = 0;
+          if (kv_ok) {
+            tap = j / p.kv_per_tap; r = j - tap * p.kv_per_tap;
+            while (sg + 1 < p.n_seg && r >= s_seg[sg + 1].kv_begin) ++sg;
+          }
+          const USeg sgm = s_seg[sg];
+          const int c8 = r - sgm.kv_begin;
+          const int dy = tap / p.k - p.pad, dx = tap % p.k - p.pad;
+          const uint32_t dst0 = smem_u32(a_smem + (size_t)s * A_STAGE_BYTES);
+#pragma unroll
+          for (int it = 0; it < BM / 16; ++it) {
+            const int row = it * 16 + rg;
+            const uint32_t ri = s_row[row];
+            const int ox = ri & 1023, oy = (ri >> 10) & 1023, n = ri >> 20;
+            const int iy = oy * p.stride + dy, ix = ox * p.stride + dx;
+            const bool ok = kv_ok && ri != 0xFFFFFFFFu && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+            const __nv_bfloat16* src = sgm.ptr;
+            if (ok) src += ((size_t)((size_t)n * sgm.Hs + (iy >> sgm.shift)) * sgm.Ws + (ix >> sgm.shift)) * sgm.Cp + c8 * 8;
+            cp_async16(dst0 + row * 128 + ((v ^ (row & 7)) << 4), src, ok ? 16u : 0u);
+          }
+        }
+        cp_async_commit();
+        if (ks >= L) {  // stage ks-L has landed for this thread: publish it to the tensor core (async proxy)
+          cp_async_wait_dyn(L);
+          fence_proxy_async();
+          mbar_arrive(&full_bar[(ks - L) % S]);
+        }
       }
     }
     // ================= epilogue: TMEM -> registers -> bf16 NHWC rows ======================
@@ -293,8 +369,8 @@ static int pick_stages(int n_tile, int* smem_bytes) {
   const int stage = A_STAGE_BYTES + n_tile * 128;
   static int forced = -1;
   if (forced < 0) { const char* e = getenv("MGCONV_STAGES"); forced = e ? atoi(e) : 0; }
-  static int budget_kb = -1;   // per-CTA shared memory target: ~108 KB keeps two CTAs resident per SM
-  if (budget_kb < 0) { const char* e = getenv("MGCONV_SMEM_KB"); budget_kb = e ? atoi(e) : 108; }
+  static int budget_kb = -1;   // per-CTA shared memory target: ~54 KB keeps four CTAs resident per SM (measured best on R-MG-34)
+  if (budget_kb < 0) { const char* e = getenv("MGCONV_SMEM_KB"); budget_kb = e ? atoi(e) : 54; }
   int S = forced > 0 ? forced : std::min(MAX_STAGES, (budget_kb * 1024) / stage);
   S = std::max(2, std::min(S, MAX_STAGES));
   *smem_bytes = S * stage + 1024;  // + alignment slack
@@ -311,11 +387,19 @@ static int launch(mg_ctx* ctx, UParams& p, int n_tiles) {
   p.tmem_cols = cols;
   static bool attr_set = false;
   if (!attr_set) {
-    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8 * 1024));
+    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8 * 1024));
+    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8 * 1024));
     attr_set = true;
   }
   dim3 grid((unsigned)mg_cdiv(p.M, BM), (unsigned)n_tiles);
-  umma_conv_kernel<<<grid, N_THREADS, smem, ctx->stream>>>(p);
+  // fast gather: stride 1, "same" padding (output size = input size), 1x1 or 3x3, every UP segment at exactly half size
+  bool fast = p.stride == 1 && (p.k == 1 || p.k == 3) && p.pad == p.k / 2 && p.Ho == p.H && p.Wo == p.W && p.M < (int64_t)1 << 31;
+  for (int s = 0; s < p.n_seg; ++s) {
+    if (p.seg[s].shift) fast = fast && p.seg[s].Hs == p.H / 2 && p.seg[s].Ws == p.W / 2 && p.H % 2 == 0 && p.W % 2 == 0;
+    else fast = fast && p.seg[s].Hs == p.H && p.seg[s].Ws == p.W;
+  }
+  if (fast) umma_conv_kernel<true><<<grid, N_THREADS, smem, ctx->stream>>>(p);
+  else umma_conv_kernel<false><<<grid, N_THREADS, smem, ctx->stream>>>(p);
   MG_CHECK_LAUNCH(ctx);
   ctx->tc_launches++;
   return MG_OK;

@@ -245,7 +245,7 @@ int umma_conv_backward_weight(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid*
   const int z = (int)mg_cdiv(p.M, p.pix_per_cta);
   const int stage_bytes = 2 * A_IMG + p.n_blk * A_IMG;
   static int budget_kb = -1;
-  if (budget_kb < 0) { const char* e = getenv("MGCONV_SMEM_KB"); budget_kb = e ? atoi(e) : 108; }
+  if (budget_kb < 0) { const char* e = getenv("MGCONV_SMEM_KB"); budget_kb = e ? atoi(e) : 54; }
   int S = std::min(W_MAX_STAGES, (budget_kb * 1024) / stage_bytes);
   const int iters = (int)(p.pix_per_cta / PIX);
   S = std::max(2, std::min(S, std::max(2, iters)));
