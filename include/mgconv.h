@@ -30,8 +30,10 @@
 extern "C" {
 #endif
 
-#define MG_MAX_SEG 6   /* input segments of one conv (3 for mg-conv; up to 6 after nn.ConcatUnet) */
-#define MG_MAX_SRC 8   /* gradient contributions combined into one tensor */
+enum {
+  MG_MAX_SEG = 6, /* input segments of one conv (3 for mg-conv; up to 6 after nn.ConcatUnet) */
+  MG_MAX_SRC = 8  /* gradient contributions combined into one tensor */
+};
 
 typedef struct mg_ctx mg_ctx;
 

@@ -33,6 +33,19 @@ def test_library_exports_every_declared_symbol():
     assert lib.mg_version() >= 100
 
 
+def test_header_parses_in_ffi_cdef_syntax():
+    """lua/mgconv_ffi.lua feeds include/mgconv.h (minus preprocessor lines) to LuaJIT's ffi.cdef;
+    Python cffi's ABI mode accepts the same C-declaration syntax: parse it and dlopen the library"""
+    import cffi
+    ffi = cffi.FFI()
+    lines = [l for l in open(HEADER).read().split("\n")
+             if not l.strip().startswith("#") and not l.startswith('extern "C"') and l.strip() != "}"]
+    ffi.cdef("\n".join(lines).replace("size_t", "unsigned long"))
+    lib = ffi.dlopen(os.path.join(ROOT, "multigrid-neural-architectures_b200", "mgconv", "libmgconv.so"))
+    assert lib.mg_version() >= 100
+    assert ffi.sizeof("mg_grid") == 48 and ffi.sizeof("mg_grad_src") == 64 and lib.MG_MAX_SEG == 6
+
+
 def test_ctx_create_fails_loudly_without_gpu():
     from mgconv import ffi
     if torch.cuda.is_available():
