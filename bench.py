@@ -157,7 +157,7 @@ def main():
     torch.manual_seed(2)  # -manualSeed default (opts.lua:23); identical initial weights on every rank
     net = B.load_net("ilsvrc/rnmg")
     model = net.createModel(B.Opt(depth=args.depth, nGPU=world))
-    model.precision = args.precision
+    (model.model if hasattr(model, "model") else model).precision = args.precision
     model.cuda()
     criterion = net.createCriterion()
     params, grads = model.getParameters()
@@ -238,7 +238,14 @@ def main():
         e2e = {"value": Bsz * world / (ems / args.steps * 1e-3), "unit": "images/s",
                "h2d_bytes_per_step": host_x.numel() * 4 + host_t.numel() * 8, "d2h_bytes_per_step": 4}
 
+    in_sync = None
+    if world > 1:   # every rank applied the same all-reduced gradient: parameters must be bit-identical
+        lo, hi = params.clone(), params.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        in_sync = bool(torch.equal(lo, hi))
     if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
         return
     from mgconv import lower as L
     summ = L.plan_summary(eng.plan)
@@ -261,7 +268,8 @@ def main():
             "dtype": args.precision, "data": "synthetic",
             "config": {"workload": WORKLOAD if (args.depth == 34 and Bsz == 256) else f"R-MG-{args.depth} batch {Bsz}/GPU (NOT the headline config)",
                        "global_batch": Bsz * world, "parallelism": f"dp{world}", "l2_flush": "inputs larger than L2 (154 MB of images, >10 GB of activations per step)",
-                       "impl": os.environ.get("MGCONV_IMPL", "auto"), "device_bytes": eng.bytes},
+                       "impl": os.environ.get("MGCONV_IMPL", "auto"), "device_bytes": eng.bytes,
+                       "dp_params_in_sync": in_sync, "tc_launches": eng.ctx.tc_launches()},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cb,
             "loss": float(state["loss"])}
     print(json.dumps(line), flush=True)

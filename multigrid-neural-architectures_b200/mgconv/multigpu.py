@@ -135,28 +135,43 @@ class DataParallel:
         return out
 
     def backward(self, input, gradOutput, scale=1.0):
-        self._done = set()
+        if self.gflat is not None:
+            self._reset_buckets()
         gi = self.model.backward(input, gradOutput, scale / self.world)
         if self.world > 1 and self.gflat is not None:
-            self.model._engine.ctx.call("mg_allreduce_wait")
+            eng = self.model._engine
+            for b, (off, cnt, _) in enumerate(self.buckets):   # parameters the plan never touched
+                if b not in self.launched:
+                    eng.ctx.call("mg_allreduce_launch", ptr(self.gflat[off:off + cnt]), cnt, 0)
+            eng.ctx.call("mg_allreduce_wait")
         return gi
 
     def _param_done(self, mod):
-        """called by the engine right after the wgrad / BN-backward of `mod` was enqueued"""
-        for idx in self._owner.get(id(mod), ()):
-            self._done.add(idx)
+        """called by the engine right after the wgrad / BN-backward of `mod` was enqueued: a bucket whose
+        last missing gradient this was is all-reduced now, overlapping the rest of backward"""
         eng = self.model._engine
-        for off, cnt, first in self.buckets:
-            if first in self._done and ("b", first) not in self._done:
-                # every parameter of the bucket has index >= first and was produced earlier in backward
-                if all(i in self._done for i in range(first, self._bucket_end(first))):
-                    self._done.add(("b", first))
-                    eng.ctx.call("mg_allreduce_launch", ptr(self.gflat[off:off + cnt]), cnt, 0)
+        for idx in self._owner.get(id(mod), ()):
+            if idx in self._done:
+                continue
+            self._done.add(idx)
+            b = self._bucket_of[idx]
+            self._missing[b] -= 1
+            if self._missing[b] == 0:
+                off, cnt, _ = self.buckets[b]
+                eng.ctx.call("mg_allreduce_launch", ptr(self.gflat[off:off + cnt]), cnt, 0)
+                self.launched.append(b)
 
-    def _bucket_end(self, first):
-        firsts = sorted(f for _, _, f in self.buckets)
-        i = firsts.index(first)
-        return firsts[i + 1] if i + 1 < len(firsts) else len(self.sizes)
+    def _reset_buckets(self):
+        self._done = set()
+        self.launched = []
+        firsts = sorted((f, i) for i, (_, _, f) in enumerate(self.buckets))
+        self._bucket_of = {}
+        self._missing = [0] * len(self.buckets)
+        for k, (f, b) in enumerate(firsts):
+            end = firsts[k + 1][0] if k + 1 < len(firsts) else len(self.sizes)
+            for idx in range(f, end):
+                self._bucket_of[idx] = b
+                self._missing[b] += 1
 
 
 def makeDataParallel(model, nGPU, net=None):

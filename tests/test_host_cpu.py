@@ -162,13 +162,16 @@ class Ctx:
     def call(self, name, p, cnt, dbl): launched.append((name, cnt))
 class Eng: ctx = Ctx()
 m.model._engine = Eng()
-m._done = set()
 mods = [mod for mod in m.model.listModules() if mod.own_parameters()]
-total = 0
-for mod in reversed(mods):
-    m._param_done(mod)
-assert sum(c for _, c in launched) == flat.numel(), (sum(c for _, c in launched), flat.numel())
-assert len(launched) == len(m.buckets)
+import random
+for order in (list(reversed(mods)), random.Random(rank).sample(mods, len(mods))):   # backward order, then any order
+    del launched[:]
+    m._reset_buckets()
+    for mod in order:
+        m._param_done(mod)
+        m._param_done(mod)                  # idempotent
+    assert sum(c for _, c in launched) == flat.numel(), (sum(c for _, c in launched), flat.numel())
+    assert len(launched) == len(m.buckets)
 lo, hi = multigpu.shard_range(7, 2, rank)
 assert (lo, hi) == ((0, 4) if rank == 0 else (4, 7))
 dist.barrier()
