@@ -159,7 +159,7 @@ struct CombP {
   int N, H, W, C, Hb, Wb;        // Hb = ceil(H/2): 2x2 blocks
 };
 
-__global__ void __launch_bounds__(256) combine_bf16_kernel(CombP p) {
+__global__ void __launch_bounds__(256, 3) combine_bf16_kernel(CombP p) {
   extern __shared__ float sh[];
   const int V = p.d_cp >> 3;
   if (p.sums) {
@@ -190,11 +190,13 @@ __global__ void __launch_bounds__(256) combine_bf16_kernel(CombP p) {
       int64_t pix[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) pix[k] = ((int64_t)n * p.H + y0 + (k >> 1)) * p.W + x0 + (k & 1);
-      V8 X[4];
+      uint4 Xr[4];   // raw bf16 (4 registers each); unpacked where needed
+#pragma unroll
+      for (int k = 0; k < 4; ++k) Xr[k] = make_uint4(0, 0, 0, 0);
       if (need_x) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (valid[k]) X[k] = ld8(p.x + pix[k] * p.x_cp + c0);
+          if (valid[k]) Xr[k] = *reinterpret_cast<const uint4*>(p.x + pix[k] * p.x_cp + c0);
       }
       V8 acc[4];
 #pragma unroll
@@ -225,6 +227,9 @@ __global__ void __launch_bounds__(256) combine_bf16_kernel(CombP p) {
         } else if (S.mode == MG_SEG_POOL) {
           // this 2x2 block is exactly one pooling window: route to the first maximum (row-major scan)
           const V8 g = ld8(S.g + (((int64_t)n * S.H + by) * S.W + bx) * S.cp + S.c_off + c0);
+          V8 X[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) X[k] = unpack8(Xr[k]);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             float best = -INFINITY; int bi = 0;
@@ -261,9 +266,10 @@ __global__ void __launch_bounds__(256) combine_bf16_kernel(CombP p) {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         if (valid[k]) {
+          const V8 xk = unpack8(Xr[k]);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            if (p.relu_mask && !(X[k].v[e] > 0.f)) acc[k].v[e] = 0.f;
+            if (p.relu_mask && !(xk.v[e] > 0.f)) acc[k].v[e] = 0.f;
             if (c0 + e >= p.C) acc[k].v[e] = 0.f;
           }
           if (p.sums) {

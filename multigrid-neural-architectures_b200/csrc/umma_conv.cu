@@ -50,6 +50,12 @@ struct UParams {
   int c_valid;   // channels to write (multiple of 8)
   int stages, lag;
   int tmem_cols;
+  // halo kernel (3x3, stride 1): M rows are SLOTS of the zero-padded linear image space
+  int Wp, Hp;        // slot pitch of an image row (W + 1) and rows per image (H + 1): the extra column / row is the conv's zero padding
+  int64_t T;         // N * Hp * Wp slots
+  int HL;            // halo slots staged per 64-channel chunk = 128 + 2 * Wp + 2
+  int n_chunks;      // ceil(kv_per_tap / 8)
+  int halo_bytes;    // HL * 128 rounded up to 1024
 };
 
 // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M=128
@@ -287,6 +293,181 @@ __global__ void __launch_bounds__(N_THREADS, 4) umma_conv_kernel(const __grid_co
   }
 }
 
+
+// ---------------------------------------------------------------- halo kernel ----------------
+// 3x3 / stride 1 convolutions.  The CTA's 128 GEMM rows are 128 consecutive SLOTS of the zero-padded
+// linear image space t = (n*(H+1) + y)*(W+1) + x (slot x == W and row y == H are the conv's zero
+// padding, shared between neighbouring rows / images), so that tap (ky,kx) of every row is the slot
+// (ky-1)*(W+1) + (kx-1) further on.  Per 64-channel chunk the producers stage ONE halo of
+// 128 + 2*(W+1) + 2 slots; the nine taps are nine UMMA descriptors into that same buffer, offset by
+// whole 128-byte rows (the 128B swizzle is a function of the absolute shared-memory address, so a
+// descriptor may start at any row -- verified on hardware, scratch/desc_test.cu).  A is fetched from
+// L2 once per chunk instead of once per tap (x4.4 - x7 less gather traffic than umma_conv_kernel).
+constexpr int HALO_MAX_SLOTS = 128 + 2 * 64 + 2;   // W <= 63
+
+__global__ void __launch_bounds__(N_THREADS, 2) umma_conv_halo_kernel(const __grid_constant__ UParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], a_full[2], a_empty[2], tmem_full_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t s_pix[HALO_MAX_SLOTS];   // full-resolution pixel index of a halo slot, 0xFFFFFFFF = padding / outside
+  __shared__ uint32_t s_pup[HALO_MAX_SLOTS];   // half-resolution pixel index (UP segments)
+  __shared__ USeg s_seg[MG_MAX_SEG];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = p.stages;
+  const int b_stage_bytes = p.n_tile * 128;
+  uint8_t* a_smem = smem;                               // two halo buffers
+  uint8_t* b_smem = smem + 2 * (size_t)p.halo_bytes;    // B ring
+  const int64_t t0 = (int64_t)blockIdx.x * BM;
+  const int ntile = blockIdx.y;
+  const int KK = 9;
+
+  if (tid < p.n_seg) s_seg[tid] = p.seg[tid];
+  {
+    const int slots_per_img = p.Hp * p.Wp;
+    const int Hs2 = p.H >> 1, Ws2 = p.W >> 1;
+    for (int h = tid; h < p.HL; h += N_THREADS) {
+      const int64_t t = t0 - p.Wp - 1 + h;
+      uint32_t pix = 0xFFFFFFFFu, pup = 0;
+      if (t >= 0 && t < p.T) {
+        const int n = (int)(t / slots_per_img); const int rem = (int)(t - (int64_t)n * slots_per_img);
+        const int yy = rem / p.Wp, xs = rem - yy * p.Wp;
+        if (yy < p.H && xs < p.W) {
+          pix = (uint32_t)(((size_t)n * p.H + yy) * p.W + xs);
+          pup = (uint32_t)(((size_t)n * Hs2 + (yy >> 1)) * Ws2 + (xs >> 1));
+        }
+      }
+      s_pix[h] = pix; s_pup[h] = pup;
+    }
+  }
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], N_PRODUCERS); mbar_init(&a_empty[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < 4) {
+    // ================= A producers: one halo per 64-channel chunk ===============================
+    const int v = tid & 7;       // k-vector column of the chunk
+    const int rg = tid >> 3;     // halo slots rg, rg+16, ...
+    for (int c = 0; c < p.n_chunks + 1; ++c) {
+      if (c < p.n_chunks) {
+        const int buf = c & 1;
+        if (c >= 2) mbar_wait(&a_empty[buf], ((c >> 1) - 1) & 1);
+        const int r = c * KV_PER_STAGE + v;            // k-vector within a tap
+        const bool kv_ok = r < p.kv_per_tap;
+        int sg = 0;
+        if (kv_ok) while (sg + 1 < p.n_seg && r >= s_seg[sg + 1].kv_begin) ++sg;
+        const USeg sgm = s_seg[sg];
+        const uint32_t pitch = (uint32_t)sgm.Cp * 2u;
+        const char* base = reinterpret_cast<const char*>(sgm.ptr) + (r - sgm.kv_begin) * 16;
+        const uint32_t* tab = sgm.shift ? s_pup : s_pix;
+        const uint32_t dst0 = smem_u32(a_smem + (size_t)buf * p.halo_bytes) + (uint32_t)(v << 4);
+        for (int h = rg; h < p.HL; h += 16) {
+          const bool ok = kv_ok && s_pix[h] != 0xFFFFFFFFu;
+          const char* src = ok ? base + (uint64_t)tab[h] * pitch : reinterpret_cast<const char*>(sgm.ptr);
+          // 16-byte chunk v of slot h, swizzled by the slot's absolute 128-byte row (buffers are 1024-aligned)
+          cp_async16((dst0 ^ ((uint32_t)(h & 7) << 4)) + (uint32_t)h * 128, src, ok ? 16u : 0u);
+        }
+      }
+      cp_async_commit();
+      if (c >= 1) {   // chunk c-1 has landed for this thread
+        cp_async_wait_dyn(1);
+        fence_proxy_async();
+        mbar_arrive(&a_full[(c - 1) & 1]);
+      }
+    }
+    // ================= epilogue: TMEM -> registers -> bf16 NHWC rows ======================
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    const uint32_t pix = s_pix[row + p.Wp + 1];          // slot t0 + row
+    const bool row_ok = pix != 0xFFFFFFFFu;
+    const int n_base = ntile * p.n_tile;
+    __nv_bfloat16* yrow = p.y + (size_t)(row_ok ? pix : 0) * p.y_pitch;
+    for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+      uint32_t acc[16];
+      tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
+      tc_wait_ld();
+      if (row_ok) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int n0 = n_base + c0 + h * 8;
+          if (n0 + 8 <= p.c_valid) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float a = __uint_as_float(acc[h * 8 + 2 * e]), b = __uint_as_float(acc[h * 8 + 2 * e + 1]);
+              if (p.bias) {
+                if (n0 + 2 * e < p.c_bias) a += __ldg(p.bias + n0 + 2 * e);
+                if (n0 + 2 * e + 1 < p.c_bias) b += __ldg(p.bias + n0 + 2 * e + 1);
+              }
+              __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+              pk[e] = *reinterpret_cast<uint32_t*>(&t);
+            }
+            *reinterpret_cast<uint4*>(yrow + n0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == B_WARP) {
+    // ================= B loader: one bulk copy per (chunk, tap) stage ============================
+    if (lane == 0) {
+      const int n_st = p.n_chunks * KK;
+      const uint8_t* wsrc = p.wpack + (size_t)ntile * n_st * b_stage_bytes;
+      for (int ks = 0; ks < n_st; ++ks) {
+        const int s = ks % S;
+        if (ks >= S) mbar_wait(&empty_bar[s], ((ks / S) - 1) & 1);
+        mbar_arrive_expect_tx(&full_bar[s], (uint32_t)b_stage_bytes);
+        bulk_g2s(smem_u32(b_smem + (size_t)s * b_stage_bytes), wsrc + (size_t)ks * b_stage_bytes, (uint32_t)b_stage_bytes, &full_bar[s]);
+      }
+    }
+  } else {
+    // ================= MMA issuer: 9 shifted descriptors per chunk ===============================
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16_m128(p.n_tile);
+      int ks = 0;
+      for (int c = 0; c < p.n_chunks; ++c) {
+        const int buf = c & 1;
+        mbar_wait(&a_full[buf], (c >> 1) & 1);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(a_smem + (size_t)buf * p.halo_bytes);
+        const int kv_here = min(KV_PER_STAGE, p.kv_per_tap - c * KV_PER_STAGE);
+        const int ksteps = (kv_here + 1) >> 1;
+        for (int tap = 0; tap < KK; ++tap, ++ks) {
+          const int s = ks % S;
+          mbar_wait(&full_bar[s], (ks / S) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = a_base + (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 128u;
+          const uint32_t b_addr = smem_u32(b_smem + (size_t)s * b_stage_bytes);
+          for (int q = 0; q < ksteps; ++q)
+            tc_mma_bf16(tmem_base, smem_desc_k_sw128(a_addr + q * 32), smem_desc_k_sw128(b_addr + q * 32), idesc, (ks | q) != 0);
+          tc_commit(&empty_bar[s]);
+        }
+        tc_commit(&a_empty[buf]);   // halo buffer free once this chunk's MMAs have read it
+      }
+      tc_commit(&tmem_full_bar);
+    }
+  }
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------- weight packing -----------
 struct PackParams {
   const float* w;   // [Cout][Ccat][k][k]
@@ -297,6 +478,7 @@ struct PackParams {
   int seg_C[MG_MAX_SEG], seg_cbegin[MG_MAX_SEG], seg_kvbegin[MG_MAX_SEG], seg_cpbegin[MG_MAX_SEG];
   int kv_per_tap, nkv, n_stages, n_tile, n_tiles;
   int n_rows_valid;  // forward: Cout; transposed: CcatP (rows that may be non-zero)
+  int halo;          // stage order of umma_conv_halo_kernel: stage = chunk * 9 + tap, k-vector = chunk * 8 + v
 };
 
 // one thread per (n row, k-vector): writes 16 bytes of the swizzled stage image
@@ -312,9 +494,12 @@ __global__ void pack_weights_kernel(PackParams p) {
   __nv_bfloat16 vals[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) vals[e] = __float2bfloat16_rn(0.f);
-  if (j < p.nkv && nrow < p.n_rows_valid) {
-    const int tap = j / p.kv_per_tap, r = j % p.kv_per_tap;
-    const int KK = p.k * p.k;
+  const int KK = p.k * p.k;
+  int tap, r;
+  bool kv_ok;
+  if (p.halo) { tap = stage % KK; r = (stage / KK) * KV_PER_STAGE + v; kv_ok = r < p.kv_per_tap; }
+  else { tap = j / p.kv_per_tap; r = j % p.kv_per_tap; kv_ok = j < p.nkv; }
+  if (kv_ok && nrow < p.n_rows_valid) {
     if (!p.transposed) {
       int sg = 0;
       while (sg + 1 < p.n_seg && r >= p.seg_kvbegin[sg + 1]) ++sg;
@@ -344,7 +529,23 @@ __global__ void pack_weights_kernel(PackParams p) {
 // ---------------------------------------------------------------- host side -----------------
 struct Geometry {
   int kv_per_tap, nkv, n_stages, n_tile, n_tiles, n_rows;
+  int halo, n_chunks;
 };
+
+// the halo kernel serves 3x3 / stride 1 / pad 1 convolutions on grids of at least `MGCONV_HALO_MIN_W`
+// (default 7) and at most 63 columns whose UP segments are exactly half size
+static bool halo_applies(const mg_conv_desc* d) {
+  static int min_w = -1;
+  if (min_w < 0) { const char* e = getenv("MGCONV_HALO_MIN_W"); min_w = e ? atoi(e) : 7; }
+  if (d->ksize != 3 || d->stride != 1 || d->pad != 1) return false;
+  if (d->W < min_w || d->W > 63 || d->H > 1023) return false;
+  for (int s = 0; s < d->n_seg; ++s) {
+    const mg_grid& g = d->seg[s];
+    if (d->seg_mode[s] == MG_SEG_UP) { if (g.H * 2 != d->H || g.W * 2 != d->W) return false; }
+    else if (g.H != d->H || g.W != d->W) return false;
+  }
+  return (int64_t)d->seg[0].N * (d->H + 1) * (d->W + 1) < ((int64_t)1 << 31);
+}
 
 static void n_tiling(int n_rows_pad16, int* n_tile, int* n_tiles) {
   *n_tiles = (n_rows_pad16 + 255) / 256;
@@ -362,6 +563,9 @@ static Geometry geometry(const mg_conv_desc* d, int transposed) {
   else { g.kv_per_tap = CoutP / 8; g.n_rows = CcatP; n_tiling(mg_round_up(CcatP, 16), &g.n_tile, &g.n_tiles); }
   g.nkv = taps * g.kv_per_tap;
   g.n_stages = (g.nkv + KV_PER_STAGE - 1) / KV_PER_STAGE;
+  g.halo = halo_applies(d) ? 1 : 0;
+  g.n_chunks = (g.kv_per_tap + KV_PER_STAGE - 1) / KV_PER_STAGE;
+  if (g.halo) g.n_stages = g.n_chunks * taps;   // one weight stage per (chunk, tap)
   return g;
 }
 
@@ -400,6 +604,34 @@ static int launch(mg_ctx* ctx, UParams& p, int n_tiles) {
   }
   if (fast) umma_conv_kernel<true><<<grid, N_THREADS, smem, ctx->stream>>>(p);
   else umma_conv_kernel<false><<<grid, N_THREADS, smem, ctx->stream>>>(p);
+  MG_CHECK_LAUNCH(ctx);
+  ctx->tc_launches++;
+  return MG_OK;
+}
+
+static int launch_halo(mg_ctx* ctx, UParams& p, const Geometry& g) {
+  p.Wp = p.W + 1; p.Hp = p.H + 1;
+  p.T = (int64_t)p.Nimg * p.Hp * p.Wp;
+  p.HL = BM + 2 * p.Wp + 2;
+  p.n_chunks = g.n_chunks;
+  p.halo_bytes = mg_round_up(p.HL * 128, 1024);
+  const int b_stage = p.n_tile * 128;
+  static int budget_kb = -1;
+  if (budget_kb < 0) { const char* e = getenv("MGCONV_HALO_SMEM_KB"); budget_kb = e ? atoi(e) : 108; }
+  int S = (budget_kb * 1024 - 2 * p.halo_bytes) / b_stage;
+  S = std::max(2, std::min(S, MAX_STAGES));
+  p.stages = S; p.lag = 1;
+  int cols = 32;
+  while (cols < p.n_tile) cols <<= 1;
+  p.tmem_cols = cols;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8 * 1024));
+    attr_set = true;
+  }
+  const int smem = 2 * p.halo_bytes + S * b_stage + 1024;
+  dim3 grid((unsigned)mg_cdiv(p.T, BM), (unsigned)g.n_tiles);
+  umma_conv_halo_kernel<<<grid, N_THREADS, smem, ctx->stream>>>(p);
   MG_CHECK_LAUNCH(ctx);
   ctx->tc_launches++;
   return MG_OK;
@@ -446,7 +678,7 @@ int umma_pack_weights(mg_ctx* ctx, const mg_conv_desc* d, const float* w, void* 
   }
   p.Ccat = c;
   p.kv_per_tap = g.kv_per_tap; p.nkv = g.nkv; p.n_stages = g.n_stages; p.n_tile = g.n_tile; p.n_tiles = g.n_tiles;
-  p.n_rows_valid = g.n_rows;
+  p.n_rows_valid = g.n_rows; p.halo = g.halo;
   const int64_t total = (int64_t)g.n_tiles * g.n_tile * g.n_stages * KV_PER_STAGE;
   pack_weights_kernel<<<(unsigned)mg_cdiv(total, 256), 256, 0, ctx->stream>>>(p);
   MG_CHECK_LAUNCH(ctx);
@@ -475,7 +707,7 @@ int umma_conv_forward(mg_ctx* ctx, const mg_conv_desc* d, const void* wpack, con
   p.kv_per_tap = g.kv_per_tap; p.nkv = g.nkv; p.n_stages = g.n_stages; p.n_tile = g.n_tile;
   p.wpack = (const uint8_t*)wpack; p.bias = bias; p.c_bias = d->Cout;
   p.y = (__nv_bfloat16*)y->data; p.y_pitch = y->Cp; p.c_valid = y->Cp;
-  int rc = launch(ctx, p, g.n_tiles);
+  int rc = g.halo ? launch_halo(ctx, p, g) : launch(ctx, p, g.n_tiles);
   if (rc) return rc;
   if (bn_sums) return mg_bn_stats(ctx, y, bn_sums);
   return MG_OK;
@@ -496,6 +728,6 @@ int umma_conv_backward_data(mg_ctx* ctx, const mg_conv_desc* d, const void* wpac
   p.wpack = (const uint8_t*)wpack_t; p.bias = nullptr;
   p.y = (__nv_bfloat16*)dcat->data; p.y_pitch = dcat->Cp; p.c_valid = dcat->Cp;
   MG_REQUIRE(ctx, dcat->Cp == g.n_rows, MG_ERR_SHAPE, "dgrad: dcat.Cp %d != %d", dcat->Cp, g.n_rows);
-  return launch(ctx, p, g.n_tiles);
+  return g.halo ? launch_halo(ctx, p, g) : launch(ctx, p, g.n_tiles);
 }
 

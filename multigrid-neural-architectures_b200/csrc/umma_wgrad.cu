@@ -236,8 +236,10 @@ int umma_conv_backward_weight(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid*
   p.n_blk = (p.n_tile + 63) / 64;
   p.dw = dw; p.gscale = gscale;
   const int m_tiles = (p.nkv + 15) / 16;
-  // split the pixel range so that the grid covers the machine about twice
-  const int64_t want = 2 * (int64_t)ctx->num_sms;
+  // split the pixel range so that four CTAs are resident per SM (the loaders are latency bound)
+  static int per_sm = -1;
+  if (per_sm < 0) { const char* e = getenv("MGCONV_WGRAD_CTAS"); per_sm = e ? atoi(e) : 4; }
+  const int64_t want = (int64_t)per_sm * ctx->num_sms;
   int64_t splits = std::max<int64_t>(1, want / ((int64_t)m_tiles * n_tiles));
   splits = std::min<int64_t>(splits, mg_cdiv(p.M, 4 * PIX));
   splits = std::max<int64_t>(1, std::min<int64_t>(splits, 65535));
