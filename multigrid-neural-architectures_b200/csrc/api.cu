@@ -113,6 +113,7 @@ int mg_ctx_destroy(mg_ctx* ctx) {
     delete ps;
   }
   mg_comm_destroy(ctx);
+  if (ctx->ws) cudaFree(ctx->ws);
   delete ctx;
   return MG_OK;
 }

@@ -24,7 +24,21 @@ struct mg_ctx {
   // optional CUDA-event timing of the convolution kernels (bench.py roofline)
   int profile;
   void* prof;  // ProfState*
+  // scratch owned by the context (split-K partial sums of the weight gradient), grown on demand
+  void* ws;
+  size_t ws_bytes;
 };
+
+// make the context workspace at least `bytes` large (one blocking cudaMalloc when it grows)
+static inline int mg_ctx_workspace(mg_ctx* ctx, size_t bytes, void** out) {
+  if (ctx->ws_bytes < bytes) {
+    if (ctx->ws) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->ws); ctx->ws = nullptr; ctx->ws_bytes = 0; }
+    if (cudaMalloc(&ctx->ws, bytes) != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "workspace: cudaMalloc(%zu) failed", bytes); return MG_ERR_CUDA; }
+    ctx->ws_bytes = bytes;
+  }
+  *out = ctx->ws;
+  return MG_OK;
+}
 
 #define MG_FAIL(ctx, code, ...)                                  \
   do {                                                           \

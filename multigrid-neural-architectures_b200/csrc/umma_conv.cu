@@ -56,6 +56,7 @@ struct UParams {
   int HL;            // halo slots staged per 64-channel chunk = 128 + 2 * Wp + 2
   int n_chunks;      // ceil(kv_per_tap / 8)
   int halo_bytes;    // HL * 128 rounded up to 1024
+  int n_abuf;        // halo buffers (1 or 2)
 };
 
 // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M=128
@@ -304,8 +305,11 @@ __global__ void __launch_bounds__(N_THREADS, 4) umma_conv_kernel(const __grid_co
 // descriptor may start at any row -- verified on hardware, scratch/desc_test.cu).  A is fetched from
 // L2 once per chunk instead of once per tap (x4.4 - x7 less gather traffic than umma_conv_kernel).
 constexpr int HALO_MAX_SLOTS = 128 + 2 * 64 + 2;   // W <= 63
+constexpr int H_PROD = 256;                        // 8 loader warps (the first 4 also drain TMEM): the gather is issue bound
+constexpr int H_MMA_WARP = H_PROD / 32, H_B_WARP = H_MMA_WARP + 1;
+constexpr int H_THREADS = H_PROD + 64;
 
-__global__ void __launch_bounds__(N_THREADS, 2) umma_conv_halo_kernel(const __grid_constant__ UParams p) {
+__global__ void __launch_bounds__(H_THREADS, 2) umma_conv_halo_kernel(const __grid_constant__ UParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], a_full[2], a_empty[2], tmem_full_bar;
@@ -318,7 +322,7 @@ __global__ void __launch_bounds__(N_THREADS, 2) umma_conv_halo_kernel(const __gr
   const int S = p.stages;
   const int b_stage_bytes = p.n_tile * 128;
   uint8_t* a_smem = smem;                               // two halo buffers
-  uint8_t* b_smem = smem + 2 * (size_t)p.halo_bytes;    // B ring
+  uint8_t* b_smem = smem + (size_t)p.n_abuf * p.halo_bytes;    // B ring
   const int64_t t0 = (int64_t)blockIdx.x * BM;
   const int ntile = blockIdx.y;
   const int KK = 9;
@@ -327,7 +331,7 @@ __global__ void __launch_bounds__(N_THREADS, 2) umma_conv_halo_kernel(const __gr
   {
     const int slots_per_img = p.Hp * p.Wp;
     const int Hs2 = p.H >> 1, Ws2 = p.W >> 1;
-    for (int h = tid; h < p.HL; h += N_THREADS) {
+    for (int h = tid; h < p.HL; h += H_THREADS) {
       const int64_t t = t0 - p.Wp - 1 + h;
       uint32_t pix = 0xFFFFFFFFu, pup = 0;
       if (t >= 0 && t < p.T) {
@@ -343,11 +347,11 @@ __global__ void __launch_bounds__(N_THREADS, 2) umma_conv_halo_kernel(const __gr
   }
   if (tid == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], N_PRODUCERS); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], H_PROD); mbar_init(&a_empty[s], 1); }
     mbar_init(&tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == MMA_WARP) {
+  if (warp == H_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(p.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -357,14 +361,15 @@ __global__ void __launch_bounds__(N_THREADS, 2) umma_conv_halo_kernel(const __gr
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp < 4) {
+  if (warp < H_MMA_WARP) {
     // ================= A producers: one halo per 64-channel chunk ===============================
     const int v = tid & 7;       // k-vector column of the chunk
     const int rg = tid >> 3;     // halo slots rg, rg+16, ...
-    for (int c = 0; c < p.n_chunks + 1; ++c) {
+    const int NB = p.n_abuf, lagA = NB - 1;   // one buffer: publish at once; two: publish the previous chunk
+    for (int c = 0; c < p.n_chunks + lagA; ++c) {
       if (c < p.n_chunks) {
-        const int buf = c & 1;
-        if (c >= 2) mbar_wait(&a_empty[buf], ((c >> 1) - 1) & 1);
+        const int buf = c % NB;
+        if (c >= NB) mbar_wait(&a_empty[buf], ((c / NB) - 1) & 1);
         const int r = c * KV_PER_STAGE + v;            // k-vector within a tap
         const bool kv_ok = r < p.kv_per_tap;
         int sg = 0;
@@ -374,7 +379,7 @@ __global__ void __launch_bounds__(N_THREADS, 2) umma_conv_halo_kernel(const __gr
         const char* base = reinterpret_cast<const char*>(sgm.ptr) + (r - sgm.kv_begin) * 16;
         const uint32_t* tab = sgm.shift ? s_pup : s_pix;
         const uint32_t dst0 = smem_u32(a_smem + (size_t)buf * p.halo_bytes) + (uint32_t)(v << 4);
-        for (int h = rg; h < p.HL; h += 16) {
+        for (int h = rg; h < p.HL; h += H_PROD / 8) {
           const bool ok = kv_ok && s_pix[h] != 0xFFFFFFFFu;
           const char* src = ok ? base + (uint64_t)tab[h] * pitch : reinterpret_cast<const char*>(sgm.ptr);
           // 16-byte chunk v of slot h, swizzled by the slot's absolute 128-byte row (buffers are 1024-aligned)
@@ -382,13 +387,14 @@ __global__ void __launch_bounds__(N_THREADS, 2) umma_conv_halo_kernel(const __gr
         }
       }
       cp_async_commit();
-      if (c >= 1) {   // chunk c-1 has landed for this thread
-        cp_async_wait_dyn(1);
+      if (c >= lagA) {   // chunk c-lagA has landed for this thread
+        cp_async_wait_dyn(lagA);
         fence_proxy_async();
-        mbar_arrive(&a_full[(c - 1) & 1]);
+        mbar_arrive(&a_full[(c - lagA) % NB]);
       }
     }
-    // ================= epilogue: TMEM -> registers -> bf16 NHWC rows ======================
+    // ================= epilogue (warps 0-3): TMEM -> registers -> bf16 NHWC rows ===========
+    if (warp < 4) {
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
     const int row = warp * 32 + lane;
@@ -422,7 +428,8 @@ __global__ void __launch_bounds__(N_THREADS, 2) umma_conv_halo_kernel(const __gr
       }
     }
     tc_fence_before();
-  } else if (warp == B_WARP) {
+    }
+  } else if (warp == H_B_WARP) {
     // ================= B loader: one bulk copy per (chunk, tap) stage ============================
     if (lane == 0) {
       const int n_st = p.n_chunks * KK;
@@ -440,8 +447,8 @@ __global__ void __launch_bounds__(N_THREADS, 2) umma_conv_halo_kernel(const __gr
       const uint32_t idesc = idesc_bf16_m128(p.n_tile);
       int ks = 0;
       for (int c = 0; c < p.n_chunks; ++c) {
-        const int buf = c & 1;
-        mbar_wait(&a_full[buf], (c >> 1) & 1);
+        const int buf = c % p.n_abuf;
+        mbar_wait(&a_full[buf], (c / p.n_abuf) & 1);
         tc_fence_after();
         const uint32_t a_base = smem_u32(a_smem + (size_t)buf * p.halo_bytes);
         const int kv_here = min(KV_PER_STAGE, p.kv_per_tap - c * KV_PER_STAGE);
@@ -462,7 +469,7 @@ __global__ void __launch_bounds__(N_THREADS, 2) umma_conv_halo_kernel(const __gr
     }
   }
   __syncthreads();
-  if (warp == MMA_WARP) {
+  if (warp == H_MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
@@ -585,7 +592,7 @@ static int launch(mg_ctx* ctx, UParams& p, int n_tiles) {
   int smem = 0;
   p.stages = pick_stages(p.n_tile, &smem);
   p.stages = std::min(p.stages, std::max(2, p.n_stages));
-  p.lag = std::min(p.stages - 1, 3);
+  p.lag = std::max(0, std::min(p.stages - 2, 3));   // lag <= S-2: loaders issue ahead while the MMAs of the current stage run
   int cols = 32;
   while (cols < p.n_tile) cols <<= 1;
   p.tmem_cols = cols;
@@ -616,9 +623,15 @@ static int launch_halo(mg_ctx* ctx, UParams& p, const Geometry& g) {
   p.n_chunks = g.n_chunks;
   p.halo_bytes = mg_round_up(p.HL * 128, 1024);
   const int b_stage = p.n_tile * 128;
-  static int budget_kb = -1;
-  if (budget_kb < 0) { const char* e = getenv("MGCONV_HALO_SMEM_KB"); budget_kb = e ? atoi(e) : 108; }
-  int S = (budget_kb * 1024 - 2 * p.halo_bytes) / b_stage;
+  static int budget_env = -1;
+  if (budget_env < 0) { const char* e = getenv("MGCONV_HALO_SMEM_KB"); budget_env = e ? atoi(e) : 0; }
+  // measured on R-MG-34 (scratch/conv_bench.py): narrow tiles are bound by per-CTA latency chains and want
+  // four resident CTAs (54 KB each, one halo buffer); N >= 192 tiles are bound by the weight stream and
+  // prefer two CTAs with a deeper ring
+  const int budget_kb = budget_env > 0 ? budget_env : (p.n_tile >= 192 ? 108 : 54);
+  // two halo buffers when several chunks follow each other and the budget allows, else one
+  p.n_abuf = (g.n_chunks > 1 && 2 * p.halo_bytes + 2 * b_stage <= budget_kb * 1024) ? 2 : 1;
+  int S = (budget_kb * 1024 - p.n_abuf * p.halo_bytes) / b_stage;
   S = std::max(2, std::min(S, MAX_STAGES));
   p.stages = S; p.lag = 1;
   int cols = 32;
@@ -629,9 +642,9 @@ static int launch_halo(mg_ctx* ctx, UParams& p, const Geometry& g) {
     MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8 * 1024));
     attr_set = true;
   }
-  const int smem = 2 * p.halo_bytes + S * b_stage + 1024;
+  const int smem = p.n_abuf * p.halo_bytes + S * b_stage + 1024;
   dim3 grid((unsigned)mg_cdiv(p.T, BM), (unsigned)g.n_tiles);
-  umma_conv_halo_kernel<<<grid, N_THREADS, smem, ctx->stream>>>(p);
+  umma_conv_halo_kernel<<<grid, H_THREADS, smem, ctx->stream>>>(p);
   MG_CHECK_LAUNCH(ctx);
   ctx->tc_launches++;
   return MG_OK;

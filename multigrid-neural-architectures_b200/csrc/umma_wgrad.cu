@@ -195,6 +195,206 @@ __global__ void __launch_bounds__(W_THREADS, 2) umma_wgrad_kernel(const __grid_c
   }
 }
 
+
+// ---------------------------------------------------------------- halo weight gradient -------------
+// 3x3 / stride 1: the same zero-padded slot space as umma_conv_halo_kernel.  A CTA owns one
+// 64-channel chunk of the gathered input (8 k-vectors), one column tile of Cout (<= 96) and a range of
+// 128-slot tiles.  Per tile it stages ONE halo of the chunk (128 + 2*(W+1) + 2 slots) and the g rows of
+// the 128 slots; the nine taps are nine row-shifted views of that halo.  Two taps form one UMMA
+// M = 128 operand (MN-major: its two 64-channel blocks are the same buffer LBO = shift_b - shift_a
+// rows apart), so five accumulators hold dW[tap][64 channels][n_tile] for the whole pixel range.
+constexpr int WH_MAX_SLOTS = 128 + 2 * 64 + 2;
+constexpr int WH_PROD = 512;              // 8 loader warps (the first 4 also drain TMEM)
+constexpr int WH_MMA_WARP = WH_PROD / 32;
+constexpr int WH_THREADS = WH_PROD + 32;
+constexpr int G_IMG = 128 * 128;   // g rows of one tile, one 64-channel block
+
+struct WHParams {
+  USeg seg[MG_MAX_SEG];
+  int seg_C[MG_MAX_SEG], seg_cbegin[MG_MAX_SEG];
+  int n_seg;
+  int H, W, Wp, Hp, HL, halo_bytes;
+  int64_t T;
+  int kv_per_tap;
+  const __nv_bfloat16* g;
+  int g_cp, Cout, Ccat;
+  int n_tile, n_blk;
+  float* partial;      // [splits][9][Cout][Ccat] fp32 partial sums (context workspace)
+  int n_slot_tiles, tiles_per_cta;
+  int stages, lag, tmem_cols;
+  int chunk_shift;     // log2(n_blk * 8)
+};
+
+__global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __grid_constant__ WHParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[W_MAX_STAGES], empty_bar[W_MAX_STAGES], tmem_full_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t s_pix[2][WH_MAX_SLOTS], s_pup[2][WH_MAX_SLOTS];
+  __shared__ USeg s_seg[MG_MAX_SEG];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = p.stages;
+  const int stage_bytes = p.halo_bytes + p.n_blk * G_IMG;
+  const int chunk = blockIdx.x, nt = blockIdx.y;
+  const int tile0 = blockIdx.z * p.tiles_per_cta;
+  const int n_iters = min(p.tiles_per_cta, p.n_slot_tiles - tile0);
+
+  if (tid < p.n_seg) s_seg[tid] = p.seg[tid];
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], WH_PROD); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WH_MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < WH_MMA_WARP) {
+    const int v = tid & 7, rg = tid >> 3;
+    const int r = chunk * 8 + v;                 // this thread's k-vector within a tap
+    const bool kv_ok = r < p.kv_per_tap;
+    int sg = 0;
+    if (kv_ok) while (sg + 1 < p.n_seg && r >= s_seg[sg + 1].kv_begin) ++sg;
+    const USeg sgm = s_seg[sg];
+    const uint32_t pitch = (uint32_t)sgm.Cp * 2u;
+    const char* abase = reinterpret_cast<const char*>(sgm.ptr) + (r - sgm.kv_begin) * 16;
+    const int slots_per_img = p.Hp * p.Wp, Hs2 = p.H >> 1, Ws2 = p.W >> 1;
+    const int chunks = p.n_blk * 8;               // 16-byte chunks per g row across the blocks
+    const int L = p.lag;
+    for (int it = 0; it < n_iters + L; ++it) {
+      if (it < n_iters) {
+        const int s = it % S, tb = it & 1;
+        if (it >= S) mbar_wait(&empty_bar[s], ((it / S) - 1) & 1);
+        // slot -> pixel table of this tile (double buffered: the previous tile's copies may still be issuing)
+        const int64_t t0 = (int64_t)(tile0 + it) * 128;
+        for (int h = tid; h < p.HL; h += WH_PROD) {
+          const int64_t t = t0 - p.Wp - 1 + h;
+          uint32_t pix = 0xFFFFFFFFu, pup = 0;
+          if (t >= 0 && t < p.T) {
+            const uint32_t tu = (uint32_t)t;
+            const uint32_t n = tu / (uint32_t)slots_per_img, rem = tu - n * (uint32_t)slots_per_img;
+            const uint32_t yy = rem / (uint32_t)p.Wp, xs = rem - yy * (uint32_t)p.Wp;
+            if ((int)yy < p.H && (int)xs < p.W) {
+              pix = (n * p.H + yy) * p.W + xs;
+              pup = (n * Hs2 + (yy >> 1)) * Ws2 + (xs >> 1);
+            }
+          }
+          s_pix[tb][h] = pix; s_pup[tb][h] = pup;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(WH_PROD) : "memory");   // loader warps only
+        uint8_t* st = smem + (size_t)s * stage_bytes;
+        const uint32_t* tab = sgm.shift ? s_pup[tb] : s_pix[tb];
+        const uint32_t dst0 = smem_u32(st) + (uint32_t)(v << 4);
+        for (int h = rg; h < p.HL; h += WH_PROD / 8) {
+          const bool ok = kv_ok && s_pix[tb][h] != 0xFFFFFFFFu;
+          const char* src = ok ? abase + (uint64_t)tab[h] * pitch : reinterpret_cast<const char*>(sgm.ptr);
+          cp_async16((dst0 ^ ((uint32_t)(h & 7) << 4)) + (uint32_t)h * 128, src, ok ? 16u : 0u);
+        }
+        const uint32_t g_dst = smem_u32(st) + p.halo_bytes;
+        for (int i = tid; i < 128 * chunks; i += WH_PROD) {
+          const int row = i >> p.chunk_shift, ch = i & (chunks - 1);
+          const uint32_t pix = s_pix[tb][row + p.Wp + 1];
+          const int c0 = nt * p.n_tile + ch * 8;
+          const bool ok = pix != 0xFFFFFFFFu && ch * 8 < p.n_tile && c0 < p.g_cp;
+          const __nv_bfloat16* src = ok ? p.g + (size_t)pix * p.g_cp + c0 : p.g;
+          cp_async16(g_dst + (ch >> 3) * G_IMG + row * 128 + (((ch & 7) ^ (row & 7)) << 4), src, ok ? 16u : 0u);
+        }
+      }
+      cp_async_commit();
+      if (it >= L) {
+        cp_async_wait_dyn(L);
+        fence_proxy_async();
+        mbar_arrive(&full_bar[(it - L) % S]);
+      }
+    }
+    // ---- epilogue (warps 0-3: one TMEM lane quarter each): five accumulators -> partial sums --------
+    if (warp < 4) {
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;            // rows 0..63: first tap of the pair, 64..127: second
+    const int rr0 = chunk * 8 + ((row & 63) >> 3), e = row & 7;
+    int rsg = 0;
+    bool row_ok = rr0 < p.kv_per_tap;
+    int ci = 0;
+    if (row_ok) {
+      while (rsg + 1 < p.n_seg && rr0 >= s_seg[rsg + 1].kv_begin) ++rsg;
+      const int cl = (rr0 - s_seg[rsg].kv_begin) * 8 + e;
+      row_ok = cl < p.seg_C[rsg];
+      ci = p.seg_cbegin[rsg] + cl;
+    }
+    // plain coalesced stores of this CTA's partial sums (consecutive rows = consecutive ci); the
+    // reduction over the pixel splits is a separate pass (wgrad_reduce_kernel): no atomics
+    float* part = p.partial + (size_t)blockIdx.z * 9 * p.Cout * p.Ccat;
+    for (int pair = 0; pair < 5; ++pair) {
+      const int tap = pair * 2 + (row >> 6);
+      const bool ok = row_ok && tap < 9;
+      float* prow = part + (size_t)tap * p.Cout * p.Ccat + ci;
+      for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+        uint32_t acc[16];
+        tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(pair * p.n_tile + c0), acc);
+        tc_wait_ld();
+        if (ok) {
+#pragma unroll
+          for (int x = 0; x < 16; ++x) {
+            const int co = nt * p.n_tile + c0 + x;
+            if (co < p.Cout) prow[(size_t)co * p.Ccat] = __uint_as_float(acc[x]);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    }
+  } else {
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16_m128_mn(p.n_tile);
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % S;
+        mbar_wait(&full_bar[s], (it / S) & 1);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t b_base = a_base + p.halo_bytes;
+#pragma unroll 1
+        for (int pair = 0; pair < 5; ++pair) {
+          const int ta = pair * 2, tb2 = min(pair * 2 + 1, 8);
+          const int sa = (ta / 3) * p.Wp + ta % 3, sb = (tb2 / 3) * p.Wp + tb2 % 3;   // halo slot of tile row 0
+          const uint32_t lbo = (uint32_t)(sb - sa) * 128u;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)   // 16 slots (K) per UMMA
+            tc_mma_bf16(tmem_base + pair * p.n_tile, smem_desc_mn_sw128(a_base + (uint32_t)sa * 128u + q * 2048, lbo),
+                        smem_desc_mn_sw128(b_base + q * 2048, G_IMG), idesc, (it | q) != 0);
+        }
+        tc_commit(&empty_bar[s]);
+      }
+      tc_commit(&tmem_full_bar);
+    }
+  }
+  __syncthreads();
+  if (warp == WH_MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// dw[co][ci][tap] += gscale * sum_z partial[z][tap][co][ci]
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Cout, int Ccat, float* __restrict__ dw,
+                                                           float gscale) {
+  const int64_t plane = (int64_t)9 * Cout * Ccat;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // index in [tap][co][ci] order (coalesced reads)
+  if (i >= plane) return;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += partial[(size_t)z * plane + i];
+  const int ci = (int)(i % Ccat); const int64_t q = i / Ccat;
+  const int co = (int)(q % Cout); const int tap = (int)(q / Cout);
+  dw[((size_t)co * Ccat + ci) * 9 + tap] += gscale * s;
+}
+
 }  // namespace
 
 int simt_dbias(mg_ctx* ctx, const mg_grid* g, int Cout, float* dbias, float gscale);
@@ -209,7 +409,85 @@ bool umma_wgrad_supported(const mg_ctx* ctx, const mg_conv_desc* d) {
   return true;
 }
 
+static bool wgrad_halo_applies(const mg_conv_desc* d) {
+  static int on = -1, min_w = -1;
+  if (on < 0) { const char* e = getenv("MGCONV_WGRAD_HALO"); on = e ? atoi(e) : 1; }
+  if (min_w < 0) { const char* e = getenv("MGCONV_HALO_MIN_W"); min_w = e ? atoi(e) : 7; }
+  if (!on || d->ksize != 3 || d->stride != 1 || d->pad != 1) return false;
+  if (d->W < min_w || d->W > 63 || d->H > 1023) return false;
+  for (int s = 0; s < d->n_seg; ++s) {
+    const mg_grid& g = d->seg[s];
+    if (d->seg_mode[s] == MG_SEG_UP) { if (g.H * 2 != d->H || g.W * 2 != d->W) return false; }
+    else if (g.H != d->H || g.W != d->W) return false;
+  }
+  return (int64_t)d->seg[0].N * (d->H + 1) * (d->W + 1) < ((int64_t)1 << 31);
+}
+
+static int wgrad_halo(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g, float* dw, float gscale) {
+  WHParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_seg = d->n_seg;
+  int c = 0, cp = 0;
+  for (int s = 0; s < d->n_seg; ++s) {
+    const mg_grid& sg = d->seg[s];
+    p.seg[s].ptr = (const __nv_bfloat16*)sg.data; p.seg[s].Hs = sg.H; p.seg[s].Ws = sg.W; p.seg[s].Cp = sg.Cp;
+    p.seg[s].shift = d->seg_mode[s] == MG_SEG_UP ? 1 : 0; p.seg[s].kv_begin = cp / 8;
+    p.seg_C[s] = sg.C; p.seg_cbegin[s] = c;
+    c += sg.C; cp += sg.Cp;
+  }
+  p.H = d->H; p.W = d->W; p.Wp = d->W + 1; p.Hp = d->H + 1;
+  p.T = (int64_t)g->N * p.Hp * p.Wp;
+  p.HL = 128 + 2 * p.Wp + 2;
+  p.halo_bytes = mg_round_up(p.HL * 128, 1024);
+  p.kv_per_tap = cp / 8;
+  p.g = (const __nv_bfloat16*)g->data; p.g_cp = g->Cp; p.Cout = d->Cout; p.Ccat = c;
+  // five accumulators of n_tile columns must fit the 512 TMEM columns: n_tile <= 96
+  const int np = mg_round_up(d->Cout, 16);
+  const int n_tiles = (np + 95) / 96;
+  p.n_tile = mg_round_up((np + n_tiles - 1) / n_tiles, 16);
+  p.n_blk = (p.n_tile + 63) / 64;
+  p.chunk_shift = p.n_blk > 1 ? 4 : 3;
+  p.n_slot_tiles = (int)mg_cdiv(p.T, 128);
+  const int n_chunks = (p.kv_per_tap + 7) / 8;
+  int64_t splits = std::max<int64_t>(1, (int64_t)ctx->num_sms / ((int64_t)n_chunks * n_tiles));
+  splits = std::min<int64_t>(splits, std::max(1, p.n_slot_tiles / 2));
+  p.tiles_per_cta = (int)mg_cdiv(p.n_slot_tiles, splits);
+  const int z = (int)mg_cdiv(p.n_slot_tiles, p.tiles_per_cta);
+  const int stage_bytes = p.halo_bytes + p.n_blk * G_IMG;
+  int S = std::min(W_MAX_STAGES, (200 * 1024) / stage_bytes);
+  S = std::max(2, std::min(S, std::max(2, p.tiles_per_cta)));
+  // a stage is published `lag` iterations after it was issued; lag <= S-2 keeps one slot free so that the
+  // loaders issue the next tile while the tensor core works on the current one (lag = S-1 serialises them)
+  p.stages = S; p.lag = std::max(0, std::min(S - 2, 3));
+  int cols = 32;
+  while (cols < 5 * p.n_tile) cols <<= 1;
+  p.tmem_cols = cols;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MG_CUDA(ctx, cudaFuncSetAttribute(umma_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 12 * 1024));
+    attr_set = true;
+  }
+  void* ws = nullptr;
+  const size_t plane = (size_t)9 * p.Cout * p.Ccat;
+  int rc = mg_ctx_workspace(ctx, (size_t)z * plane * sizeof(float), &ws);
+  if (rc) return rc;
+  p.partial = (float*)ws;
+  dim3 grid((unsigned)n_chunks, (unsigned)n_tiles, (unsigned)z);
+  umma_wgrad_halo_kernel<<<grid, WH_THREADS, S * stage_bytes + 1024, ctx->stream>>>(p);
+  MG_CHECK_LAUNCH(ctx);
+  ctx->tc_launches++;
+  wgrad_reduce_kernel<<<(unsigned)mg_cdiv((int64_t)plane, 256), 256, 0, ctx->stream>>>(p.partial, z, p.Cout, p.Ccat, dw, gscale);
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
 int umma_conv_backward_weight(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g, float* dw, float* dbias, float gscale) {
+  if (wgrad_halo_applies(d)) {
+    int rc = wgrad_halo(ctx, d, g, dw, gscale);
+    if (rc) return rc;
+    if (dbias) return simt_dbias(ctx, g, d->Cout, dbias, gscale);
+    return MG_OK;
+  }
   WParams p;
   memset(&p, 0, sizeof(p));
   p.n_seg = d->n_seg;
@@ -251,7 +529,7 @@ int umma_conv_backward_weight(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid*
   int S = std::min(W_MAX_STAGES, (budget_kb * 1024) / stage_bytes);
   const int iters = (int)(p.pix_per_cta / PIX);
   S = std::max(2, std::min(S, std::max(2, iters)));
-  p.stages = S; p.lag = std::min(S - 1, 3);
+  p.stages = S; p.lag = std::max(0, std::min(S - 2, 3));
   int cols = 32;
   while (cols < p.n_tile) cols <<= 1;
   p.tmem_cols = cols;
