@@ -163,10 +163,13 @@ int mg_global_avgpool_backward(mg_ctx* ctx, const mg_grid* dout, mg_grid* din);
 int mg_grad_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid* bn_x,
                     int32_t n_src, const mg_grad_src* src, mg_grid* d, double* bn_sums);
 /* BatchNorm backward given the sums: out = gamma*invstd*(d - mean(d) - xhat*mean(d*xhat))
- * (out may alias d); dgamma += gscale*sum(d*xhat); dbeta += gscale*sum(d). */
+ * (out may alias d); dgamma += gscale*sum(d*xhat); dbeta += gscale*sum(d).
+ * conv_dbias (nullable): gradBias of the convolution that produced xraw, += gscale * sum_pixels(out),
+ * fused here so that the weight-gradient call can be given dbias = NULL. */
 int mg_bn_backward(mg_ctx* ctx, const mg_grid* xraw, const mg_grid* d, mg_grid* out, const double* bn_sums,
                    int64_t count, const float* gamma, const float* save_mean, const float* save_invstd,
-                   float* dgamma, float* dbeta, float gscale, float* coef_ws /* [3*Cp] scratch */);
+                   float* dgamma, float* dbeta, float gscale, float* coef_ws /* [3*Cp] scratch */,
+                   float* conv_dbias);
 /* dcat = conv_transpose(g, w): gradient w.r.t. the concatenated input, segment s at channel
  * offset sum_{t<s} Cp_t */
 int mg_conv_backward_data(mg_ctx* ctx, const mg_conv_desc* d, const float* w, const void* wpack_t,

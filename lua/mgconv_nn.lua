@@ -85,8 +85,9 @@ function MGConvBN:backward(input, gradSources, scale)
    mg.check(ctx, C.mg_memset_zero(ctx, s.dsums, 16 * self.nOutputPlane))
    mg.check(ctx, C.mg_grad_combine(ctx, s.out, self.relu, s.y, #gradSources, s.srcs(gradSources), s.D, s.dsums))
    mg.check(ctx, C.mg_bn_backward(ctx, s.y, s.D, s.G, s.dsums, s.count, self.bn_weight:data(), s.mean, s.invstd,
-                                  self.bn_gradWeight:data(), self.bn_gradBias:data(), scale or 1, s.coef))
-   mg.check(ctx, C.mg_conv_backward_weight(ctx, d, s.G, self.gradWeight:data(), self.gradBias:data(), scale or 1))
+                                  self.bn_gradWeight:data(), self.bn_gradBias:data(), scale or 1, s.coef,
+                                  self.gradBias:data()))   -- conv gradBias fused into the BN-backward pass
+   mg.check(ctx, C.mg_conv_backward_weight(ctx, d, s.G, self.gradWeight:data(), nil, scale or 1))
    mg.check(ctx, C.mg_conv_pack_weights(ctx, d, self.weight:data(), s.wpack_t, 1))
    mg.check(ctx, C.mg_conv_backward_data(ctx, d, self.weight:data(), s.wpack_t, s.G, s.dcat))
    self.gradInput = s.dcat

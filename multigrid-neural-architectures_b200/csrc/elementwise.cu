@@ -9,7 +9,8 @@
 bool bf16_apply(mg_ctx*, const mg_grid* z, const mg_grid* s, int relu, mg_grid* out, mg_grid* pooled);
 bool bf16_bn_stats(mg_ctx*, const mg_grid* y, double* sums);
 bool bf16_combine(mg_ctx*, const mg_grid* x, int relu_mask, const mg_grid* bn_x, int n_src, const mg_grad_src* src, mg_grid* d, double* sums);
-bool bf16_bn_bwd_apply(mg_ctx*, const mg_grid* xraw, const mg_grid* d, mg_grid* out, const float* coef);
+bool bf16_bn_bwd_apply(mg_ctx*, const mg_grid* xraw, const mg_grid* d, mg_grid* out, const float* coef, float* conv_dbias, float gscale);
+int simt_dbias(mg_ctx* ctx, const mg_grid* g, int Cout, float* dbias, float gscale);
 bool bf16_pool3(mg_ctx*, const mg_grid* in, mg_grid* out, uint8_t* code);
 
 namespace {
@@ -575,18 +576,19 @@ int mg_grad_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid*
 
 int mg_bn_backward(mg_ctx* ctx, const mg_grid* xraw, const mg_grid* d, mg_grid* out, const double* bn_sums, int64_t count,
                    const float* gamma, const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta,
-                   float gscale, float* coef_ws) {
+                   float gscale, float* coef_ws, float* conv_dbias) {
   if (!ctx || !xraw || !d || !out || !bn_sums || !save_mean || !save_invstd || !coef_ws) return MG_ERR_INVALID_ARG;
   MG_REQUIRE(ctx, d->N == xraw->N && d->H == xraw->H && d->W == xraw->W && d->C == xraw->C, MG_ERR_SHAPE, "bn_backward: shape");
   MG_REQUIRE(ctx, out->N == d->N && out->H == d->H && out->W == d->W && out->C == d->C, MG_ERR_SHAPE, "bn_backward: out shape");
   bn_bwd_coef_kernel<<<(unsigned)mg_cdiv(d->Cp, 128), 128, 0, ctx->stream>>>(bn_sums, count, d->C, d->Cp, gamma, save_mean, save_invstd,
                                                                    dgamma, dbeta, gscale, coef_ws);
   MG_CHECK_LAUNCH(ctx);
-  if (ctx->dtype == MG_BF16 && bf16_bn_bwd_apply(ctx, xraw, d, out, coef_ws)) { MG_CHECK_LAUNCH(ctx); return MG_OK; }
+  if (ctx->dtype == MG_BF16 && bf16_bn_bwd_apply(ctx, xraw, d, out, coef_ws, conv_dbias, gscale)) { MG_CHECK_LAUNCH(ctx); return MG_OK; }
   int64_t P = (int64_t)d->N * d->H * d->W;
   MG_DISPATCH(ctx, bn_bwd_apply_kernel<T><<<GRID1(P * out->Cp), EB, 0, ctx->stream>>>((const T*)xraw->data, xraw->Cp, (const T*)d->data, d->Cp,
                                                                                       (T*)out->data, out->Cp, d->C, P, coef_ws););
   MG_CHECK_LAUNCH(ctx);
+  if (conv_dbias) return simt_dbias(ctx, out, out->C, conv_dbias, gscale);
   return MG_OK;
 }
 

@@ -284,20 +284,51 @@ __global__ void __launch_bounds__(256, 3) combine_bf16_kernel(CombP p) {
 }
 
 // ---------------------------------------------------------------- BN backward apply ----------
+// G = A*D + B*y + C per channel; optionally also the conv's gradBias += gscale * sum_pixels G
+// (accGradParameters of the convolution that produced y), saving a separate pass over G
 __global__ void __launch_bounds__(256) bn_bwd_apply_bf16_kernel(const bf16* __restrict__ xraw, int x_cp, const bf16* d, int d_cp, bf16* out,
-                                                                int o_cp, int C, int64_t P, const float* __restrict__ coef) {
+                                                                int o_cp, int C, int64_t P, const float* __restrict__ coef,
+                                                                float* dbias, float gscale) {
+  extern __shared__ float sh[];
   const int V = o_cp >> 3;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P * V) return;
-  const int vc = (int)(i % V); const int64_t pix = i / V;
+  if (dbias) {
+    for (int c = threadIdx.x; c < V * 8; c += blockDim.x) sh[c] = 0.f;
+    __syncthreads();
+  }
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t lanes = ((int64_t)gridDim.x * blockDim.x) / V;
+  const int vc = (int)(gtid % V);
+  const int64_t lane = gtid / V;
   const int c0 = vc * 8;
-  float A[8], B[8], Cc[8];
-  ldf8(coef + c0, A); ldf8(coef + d_cp + c0, B); ldf8(coef + 2 * d_cp + c0, Cc);
-  const V8 dv = ld8(d + pix * d_cp + c0), xv = ld8(xraw + pix * x_cp + c0);
-  V8 o;
+  const bool active = lane < lanes;
+  float sb[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) o.v[e] = (c0 + e < C) ? fmaf(A[e], dv.v[e], fmaf(B[e], xv.v[e], Cc[e])) : 0.f;
-  *reinterpret_cast<uint4*>(out + pix * o_cp + c0) = pack8(o);
+  for (int e = 0; e < 8; ++e) sb[e] = 0.f;
+  if (active) {
+    float A[8], B[8], Cc[8];
+    ldf8(coef + c0, A); ldf8(coef + d_cp + c0, B); ldf8(coef + 2 * d_cp + c0, Cc);
+    for (int64_t pix = lane; pix < P; pix += lanes) {
+      const V8 dv = ld8(d + pix * d_cp + c0), xv = ld8(xraw + pix * x_cp + c0);
+      V8 o;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o.v[e] = (c0 + e < C) ? fmaf(A[e], dv.v[e], fmaf(B[e], xv.v[e], Cc[e])) : 0.f;
+      const uint4 u = pack8(o);
+      *reinterpret_cast<uint4*>(out + pix * o_cp + c0) = u;
+      if (dbias) {
+        const V8 r = unpack8(u);   // sum what the weight-gradient kernel will read
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sb[e] += r.v[e];
+      }
+    }
+  }
+  if (dbias) {
+    if (active) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) atomicAdd(&sh[c0 + e], sb[e]);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dbias + c, gscale * sh[c]);
+  }
 }
 
 // ---------------------------------------------------------------- stem max-pool with arg-max codes ----------
@@ -393,11 +424,13 @@ bool bf16_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid* b
   return true;
 }
 
-bool bf16_bn_bwd_apply(mg_ctx* ctx, const mg_grid* xraw, const mg_grid* d, mg_grid* out, const float* coef) {
-  if (xraw->Cp % 8 || d->Cp % 8 || out->Cp % 8 || d->Cp != out->Cp || xraw->Cp < out->Cp) return false;
+bool bf16_bn_bwd_apply(mg_ctx* ctx, const mg_grid* xraw, const mg_grid* d, mg_grid* out, const float* coef, float* conv_dbias, float gscale) {
+  if (xraw->Cp % 8 || d->Cp % 8 || out->Cp % 8 || d->Cp != out->Cp || xraw->Cp < out->Cp || out->Cp > 4096) return false;
   const int64_t P = (int64_t)d->N * d->H * d->W;
-  bn_bwd_apply_bf16_kernel<<<grid_for(P * (out->Cp / 8)), 256, 0, ctx->stream>>>((const bf16*)xraw->data, xraw->Cp, (const bf16*)d->data, d->Cp,
-                                                                           (bf16*)out->data, out->Cp, d->C, P, coef);
+  const int V = out->Cp / 8;
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(mg_cdiv(P * V, 256), (int64_t)ctx->num_sms * 16));
+  bn_bwd_apply_bf16_kernel<<<grid, 256, V * 8 * sizeof(float), ctx->stream>>>((const bf16*)xraw->data, xraw->Cp, (const bf16*)d->data, d->Cp,
+                                                                              (bf16*)out->data, out->Cp, d->C, P, coef, conv_dbias, gscale);
   return true;
 }
 

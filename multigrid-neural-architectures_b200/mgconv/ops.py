@@ -223,8 +223,9 @@ class ConvOp(Op):
         if self.ycomb is not None:
             self.ycomb.run()
         g = self.y.G
+        fused_bias = self.apply is not None and self.apply.bn is not None   # done by mg_bn_backward
         E.ctx.call("mg_conv_backward_weight", C.byref(self.desc), C.byref(g), ptr(self.mod.gradWeight),
-                   ptr(self.mod.gradBias), E.gscale)
+                   None if fused_bias else ptr(self.mod.gradBias), E.gscale)
         if self.needs_dgrad:
             E.ctx.call("mg_conv_backward_data", C.byref(self.desc), ptr(self.mod.weight), ptr(self.wpack_t),
                        C.byref(g), C.byref(self.dcat_g))
@@ -298,7 +299,7 @@ class ApplyOp(Op):
         if bn is not None:
             E.ctx.call("mg_bn_backward", C.byref(self.yraw), C.byref(self.dg), C.byref(self.gg), ptr(self.dsums), self.count,
                        ptr(bn.weight), ptr(self.mean), ptr(self.invstd), ptr(bn.gradWeight), ptr(bn.gradBias),
-                       E.gscale, ptr(self.coef))
+                       E.gscale, ptr(self.coef), ptr(self.conv.mod.gradBias))   # conv gradBias fused into this pass
             E.param_done(bn)
 
 

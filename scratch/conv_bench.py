@@ -47,9 +47,11 @@ def run(name, N=256, iters=20, which=("fwd", "dgrad", "wgrad")):
     cp = sum(x.Cp for x in gs)
     dcat = Grid(ffi.MG_BF16, N, cp, H, H, Cp=cp)
     dw = torch.zeros_like(w); db = torch.zeros_like(b)
+    sums = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
     flops = 2.0 * N * H * H * Cout * cin * k * k
     calls = {
         "fwd": lambda: ctx.call("mg_conv_forward", C.byref(d), ptr(w), ptr(wp), ptr(b), C.byref(y.g()), None),
+        "fwd_stats": lambda: ctx.call("mg_conv_forward", C.byref(d), ptr(w), ptr(wp), ptr(b), C.byref(y.g()), ptr(sums)),
         "dgrad": lambda: ctx.call("mg_conv_backward_data", C.byref(d), ptr(w), ptr(wpt), C.byref(g.g()), C.byref(dcat.g())),
         "wgrad": lambda: ctx.call("mg_conv_backward_weight", C.byref(d), C.byref(g.g()), ptr(dw), None, 1.0),
     }

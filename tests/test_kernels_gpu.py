@@ -275,10 +275,13 @@ def test_bn_finalize_apply_residual_and_backward(ctx, eps):
     assert np.array_equal(gd.nchw(), bf16_round(d_ref) if ctx.dtype == ffi.MG_BF16 else d_ref)
     dgamma, dbeta = torch.zeros(Cc, device="cuda"), torch.zeros(Cc, device="cuda")
     coef = torch.zeros(3 * gx.Cp, device="cuda")
+    conv_db = torch.zeros(Cc, device="cuda")
     ctx.call("mg_bn_backward", C.byref(xraw.g()), C.byref(gd.g()), C.byref(gres.g()), ptr(dsums), N * H * H, ptr(dgam),
-             ptr(smean), ptr(sinv), ptr(dgamma), ptr(dbeta), 1.0, ptr(coef))
+             ptr(smean), ptr(sinv), ptr(dgamma), ptr(dbeta), 1.0, ptr(coef), ptr(conv_db))
     torch.cuda.synchronize()
     assert max_rel(gres.nchw(), gxr) <= tol
+    # fused gradBias of the producing convolution = sum over pixels of the BN-backward output (what was stored)
+    assert np.allclose(conv_db.cpu().numpy(), gres.nchw().sum(axis=(0, 2, 3)), atol=1e-3)
     assert max_rel(dgamma.cpu().numpy(), dg_ref) <= tol and max_rel(dbeta.cpu().numpy(), db_ref) <= tol
     # evaluation mode uses the running statistics
     ctx.call("mg_bn_finalize", None, N * H * H, Cc, gx.Cp, ptr(dgam), ptr(dbet), ptr(drm), ptr(drv), eps, 0.1, 0,
