@@ -138,12 +138,23 @@ __global__ void __launch_bounds__(256) bn_stats_bf16_kernel(const bf16* __restri
 #pragma unroll
   for (int e = 0; e < 8; ++e) { a[e] = 0.f; b[e] = 0.f; }
   const bool active = lane < lanes;
-  if (active)
-    for (int64_t pix = lane; pix < P; pix += lanes) {
+  if (active) {
+    int64_t pix = lane;
+    for (; pix + 3 * lanes < P; pix += 4 * lanes) {   // four independent 16-byte loads in flight per thread
+      V8 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ld8(y + (pix + u * lanes) * cp + vc * 8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { a[e] += v[u].v[e]; b[e] = fmaf(v[u].v[e], v[u].v[e], b[e]); }
+    }
+    for (; pix < P; pix += lanes) {
       const V8 v = ld8(y + pix * cp + vc * 8);
 #pragma unroll
       for (int e = 0; e < 8; ++e) { a[e] += v.v[e]; b[e] = fmaf(v.v[e], v.v[e], b[e]); }
     }
+  }
   block_channel_sums(a, b, vc, V, C, active, sums, sh);
 }
 
@@ -307,17 +318,28 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_bf16_kernel(const bf16* __re
   if (active) {
     float A[8], B[8], Cc[8];
     ldf8(coef + c0, A); ldf8(coef + d_cp + c0, B); ldf8(coef + 2 * d_cp + c0, Cc);
-    for (int64_t pix = lane; pix < P; pix += lanes) {
-      const V8 dv = ld8(d + pix * d_cp + c0), xv = ld8(xraw + pix * x_cp + c0);
-      V8 o;
+    for (int64_t pix0 = lane; pix0 < P; pix0 += 4 * lanes) {
+      V8 dv[4], xv[4];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o.v[e] = (c0 + e < C) ? fmaf(A[e], dv.v[e], fmaf(B[e], xv.v[e], Cc[e])) : 0.f;
-      const uint4 u = pack8(o);
-      *reinterpret_cast<uint4*>(out + pix * o_cp + c0) = u;
-      if (dbias) {
-        const V8 r = unpack8(u);   // sum what the weight-gradient kernel will read
+      for (int u = 0; u < 4; ++u) {   // eight independent 16-byte loads in flight per thread
+        const int64_t pix = pix0 + u * lanes;
+        if (pix < P) { dv[u] = ld8(d + pix * d_cp + c0); xv[u] = ld8(xraw + pix * x_cp + c0); }
+      }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) sb[e] += r.v[e];
+      for (int u = 0; u < 4; ++u) {
+        const int64_t pix = pix0 + u * lanes;
+        if (pix < P) {
+          V8 o;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o.v[e] = (c0 + e < C) ? fmaf(A[e], dv[u].v[e], fmaf(B[e], xv[u].v[e], Cc[e])) : 0.f;
+          const uint4 pk = pack8(o);
+          *reinterpret_cast<uint4*>(out + pix * o_cp + c0) = pk;
+          if (dbias) {
+            const V8 r = unpack8(pk);   // sum what the weight-gradient kernel will read
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sb[e] += r.v[e];
+          }
+        }
       }
     }
   }
@@ -368,8 +390,9 @@ __global__ void __launch_bounds__(256) pool3_bf16_kernel(const bf16* __restrict_
 
 static inline unsigned grid_for(int64_t threads) { return (unsigned)mg_cdiv(threads, 256); }
 // persistent-style grid for the reducing kernels: a few CTAs per SM, each thread loops
-static inline unsigned reduce_grid(const mg_ctx* ctx, int64_t items) {
-  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(mg_cdiv(items, 256), (int64_t)ctx->num_sms * 8));
+static inline unsigned reduce_grid(const mg_ctx* ctx, int64_t items, int per_sm = 4) {
+  // every CTA ends with 2*C global atomics: keep the grid at a few resident CTAs per SM and let threads loop
+  return (unsigned)std::max<int64_t>(1, std::min<int64_t>(mg_cdiv(items, 256), (int64_t)ctx->num_sms * per_sm));
 }
 
 }  // namespace
@@ -419,7 +442,7 @@ bool bf16_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid* b
   p.N = x->N; p.H = x->H; p.W = x->W; p.C = x->C; p.Hb = (x->H + 1) / 2; p.Wb = (x->W + 1) / 2;
   const int V = d->Cp / 8;
   const int64_t items = (int64_t)p.N * p.Hb * p.Wb * V;
-  const unsigned grid = sums ? reduce_grid(ctx, items) : (unsigned)std::max<int64_t>(1, std::min<int64_t>(mg_cdiv(items, 256), (int64_t)ctx->num_sms * 16));
+  const unsigned grid = reduce_grid(ctx, items, 3);   // 80 registers: three CTAs per SM are resident
   combine_bf16_kernel<<<grid, 256, 2 * V * 8 * sizeof(float), ctx->stream>>>(p);
   return true;
 }
@@ -428,7 +451,7 @@ bool bf16_bn_bwd_apply(mg_ctx* ctx, const mg_grid* xraw, const mg_grid* d, mg_gr
   if (xraw->Cp % 8 || d->Cp % 8 || out->Cp % 8 || d->Cp != out->Cp || xraw->Cp < out->Cp || out->Cp > 4096) return false;
   const int64_t P = (int64_t)d->N * d->H * d->W;
   const int V = out->Cp / 8;
-  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(mg_cdiv(P * V, 256), (int64_t)ctx->num_sms * 16));
+  const unsigned grid = reduce_grid(ctx, P * V, 4);
   bn_bwd_apply_bf16_kernel<<<grid, 256, V * 8 * sizeof(float), ctx->stream>>>((const bf16*)xraw->data, xraw->Cp, (const bf16*)d->data, d->Cp,
                                                                               (bf16*)out->data, out->Cp, d->C, P, coef, conv_dbias, gscale);
   return true;
