@@ -135,6 +135,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--bn-sync", action="store_true", help="cross-replica BatchNorm statistics (default: per replica, as the reference)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
@@ -156,7 +157,7 @@ def main():
 
     torch.manual_seed(2)  # -manualSeed default (opts.lua:23); identical initial weights on every rank
     net = B.load_net("ilsvrc/rnmg")
-    model = net.createModel(B.Opt(depth=args.depth, nGPU=world))
+    model = net.createModel(B.Opt(depth=args.depth, nGPU=world, bnSync=args.bn_sync))
     (model.model if hasattr(model, "model") else model).precision = args.precision
     model.cuda()
     criterion = net.createCriterion()
@@ -290,7 +291,7 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
             "config": {"workload": WORKLOAD if (args.depth == 34 and Bsz == 256) else f"R-MG-{args.depth} batch {Bsz}/GPU (NOT the headline config)",
-                       "global_batch": Bsz * world, "parallelism": f"dp{world}", "l2_flush": "inputs larger than L2 (154 MB of images, >10 GB of activations per step)",
+                       "global_batch": Bsz * world, "parallelism": f"dp{world}", "bn": "sync" if (args.bn_sync and world > 1) else "per-replica (reference DataParallelTable behaviour)", "l2_flush": "inputs larger than L2 (154 MB of images, >10 GB of activations per step)",
                        "impl": os.environ.get("MGCONV_IMPL", "auto"), "device_bytes": eng.bytes,
                        "dp_params_in_sync": in_sync, "tc_launches": eng.ctx.tc_launches()},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cb,

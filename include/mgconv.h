@@ -212,6 +212,9 @@ int mg_comm_destroy(mg_ctx* ctx);
  * enqueued so far on the compute stream; mg_allreduce_wait makes the compute stream wait */
 int mg_allreduce_launch(mg_ctx* ctx, void* buf, int64_t count, int is_double);
 int mg_allreduce_wait(mg_ctx* ctx);
+/* in-place sum all-reduce enqueued on the COMPUTE stream itself: the cross-replica BatchNorm statistics
+ * (sum, sumsq) forward and (sum d, sum d*y) backward of the -bnSync mode -- a few KB, latency bound */
+int mg_allreduce_inline(mg_ctx* ctx, void* buf, int64_t count, int is_double);
 
 #ifdef __cplusplus
 }

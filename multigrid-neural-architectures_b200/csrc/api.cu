@@ -252,6 +252,14 @@ int mg_allreduce_launch(mg_ctx* ctx, void* buf, int64_t count, int is_double) {
   return MG_OK;
 }
 
+int mg_allreduce_inline(mg_ctx* ctx, void* buf, int64_t count, int is_double) {
+  if (!ctx || !buf || count < 0) return MG_ERR_INVALID_ARG;
+  MG_REQUIRE(ctx, ctx->nccl_comm != nullptr, MG_ERR_NCCL, "allreduce: communicator not initialised");
+  const int ncclFloat32 = 7, ncclFloat64 = 8, ncclSum = 0;
+  MG_NCCL(ctx, g_nccl.AllReduce(buf, buf, (size_t)count, is_double ? ncclFloat64 : ncclFloat32, ncclSum, ctx->nccl_comm, ctx->stream));
+  return MG_OK;
+}
+
 int mg_allreduce_wait(mg_ctx* ctx) {
   if (!ctx) return MG_ERR_INVALID_ARG;
   if (!ctx->nccl_comm) return MG_OK;

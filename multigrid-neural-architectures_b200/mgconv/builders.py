@@ -313,7 +313,7 @@ def _nclass(opt, default=100):
 
 def _finish(model, opt, net):
     if (opt.nGPU or 1) > 1:
-        return makeDataParallel(model, opt.nGPU, net)
+        return makeDataParallel(model, opt.nGPU, net, bnSync=bool(opt.bnSync))
     return model
 
 

@@ -57,6 +57,7 @@ class Engine:
         self.ctx.set_impl(_IMPL[impl])
         self.use_packed = self.dtype == ffi.MG_BF16 and impl != "simt"
         self.training = True
+        self.bn_sync = 0   # 0 = per-replica BatchNorm statistics (the reference's DataParallelTable); N = sync over N ranks
         self.gscale = 1.0
         self.bytes = 0
         self.on_param_done = None

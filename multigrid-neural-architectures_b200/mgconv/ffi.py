@@ -97,6 +97,7 @@ SIGNATURES = {
     "mg_comm_destroy": (_I, [_P]),
     "mg_allreduce_launch": (_I, [_P, _P, _I64, _I]),
     "mg_allreduce_wait": (_I, [_P]),
+    "mg_allreduce_inline": (_I, [_P, _P, _I64, _I]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -50,8 +50,9 @@ class DataParallel:
     over the *global* batch through gscale = 1/nranks (equal shards)."""
     typename = "nn.DataParallelTable"
 
-    def __init__(self, model, nGPU, group=None):
+    def __init__(self, model, nGPU, group=None, bnSync=False):
         self.model = model
+        self.bnSync = bool(bnSync)
         self.nGPU = nGPU
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -132,6 +133,12 @@ class DataParallel:
         if self.world > 1 and eng.on_param_done is None and self.gflat is not None:
             self._init_comm(eng)
             eng.on_param_done = self._param_done
+            if self.bnSync:
+                # -bnSync: BatchNorm statistics over the GLOBAL batch (one tiny all-reduce of the per-channel
+                # sums per BN layer, forward and backward) -- equals the single-device result on the whole
+                # batch.  The first forward above still used local statistics: redo it.
+                eng.bn_sync = self.world
+                out = self.model.forward(input)
         return out
 
     def backward(self, input, gradOutput, scale=1.0):
@@ -174,13 +181,13 @@ class DataParallel:
                 self._missing[b] += 1
 
 
-def makeDataParallel(model, nGPU, net=None):
+def makeDataParallel(model, nGPU, net=None, bnSync=False):
     """multigpu.lua:81-103"""
     if nGPU > 1:
         if not dist.is_initialized():
             raise ffi.MGError("makeDataParallel(nGPU > 1) needs torch.distributed to be initialised: launch one "
                               "process per GPU (python -m torch.distributed.run --nproc-per-node nGPU ...)")
-        return DataParallel(model, nGPU)
+        return DataParallel(model, nGPU, bnSync=bnSync)
     return model
 
 

@@ -223,7 +223,7 @@ class ConvOp(Op):
         if self.ycomb is not None:
             self.ycomb.run()
         g = self.y.G
-        fused_bias = self.apply is not None and self.apply.bn is not None   # done by mg_bn_backward
+        fused_bias = self.apply is not None and self.apply.bn is not None and not E.bn_sync   # done by mg_bn_backward
         E.ctx.call("mg_conv_backward_weight", C.byref(self.desc), C.byref(g), ptr(self.mod.gradWeight),
                    None if fused_bias else ptr(self.mod.gradBias), E.gscale)
         if self.needs_dgrad:
@@ -264,7 +264,9 @@ class ApplyOp(Op):
     def fwd(self, E):
         bn = self.bn
         if bn is not None:
-            E.ctx.call("mg_bn_finalize", ptr(self.conv.sums), self.count, self.out.C, self.out.Cp, ptr(bn.weight), ptr(bn.bias),
+            if E.bn_sync and E.training:   # cross-replica statistics: sum (sum y, sum y^2) over the ranks
+                E.ctx.call("mg_allreduce_inline", ptr(self.conv.sums), self.conv.sums.numel(), 1)
+            E.ctx.call("mg_bn_finalize", ptr(self.conv.sums), self.count * (max(1, E.bn_sync) if E.training else 1), self.out.C, self.out.Cp, ptr(bn.weight), ptr(bn.bias),
                        ptr(bn.running_mean), ptr(bn.running_var), bn.eps, bn.momentum, int(E.training),
                        ptr(self.scale), ptr(self.shift), ptr(self.mean), ptr(self.invstd))
         E.ctx.call("mg_residual_forward", C.byref(self.zg), C.byref(self.rg) if self.rg is not None else None,
@@ -297,9 +299,14 @@ class ApplyOp(Op):
         self.comb.run()
         bn = self.bn
         if bn is not None:
-            E.ctx.call("mg_bn_backward", C.byref(self.yraw), C.byref(self.dg), C.byref(self.gg), ptr(self.dsums), self.count,
+            if E.bn_sync:
+                E.ctx.call("mg_allreduce_inline", ptr(self.dsums), self.dsums.numel(), 1)
+            E.ctx.call("mg_bn_backward", C.byref(self.yraw), C.byref(self.dg), C.byref(self.gg), ptr(self.dsums), self.count * max(1, E.bn_sync),
                        ptr(bn.weight), ptr(self.mean), ptr(self.invstd), ptr(bn.gradWeight), ptr(bn.gradBias),
-                       E.gscale, ptr(self.coef), ptr(self.conv.mod.gradBias))   # conv gradBias fused into this pass
+                       # sync-BN: the sums are already global, every rank adds 1/N of dgamma / dbeta before the
+                       # gradient all-reduce; the conv gradBias (a LOCAL pixel sum) is then left to the wgrad call
+                       E.gscale / max(1, E.bn_sync), ptr(self.coef),
+                       None if E.bn_sync else ptr(self.conv.mod.gradBias))
             E.param_done(bn)
 
 
