@@ -12,6 +12,9 @@ bool bf16_combine(mg_ctx*, const mg_grid* x, int relu_mask, const mg_grid* bn_x,
 bool bf16_bn_bwd_apply(mg_ctx*, const mg_grid* xraw, const mg_grid* d, mg_grid* out, const float* coef, float* conv_dbias, float gscale);
 int simt_dbias(mg_ctx* ctx, const mg_grid* g, int Cout, float* dbias, float gscale);
 bool bf16_pool3(mg_ctx*, const mg_grid* in, mg_grid* out, uint8_t* code);
+bool bf16_import_nchw(mg_ctx*, const float* src, mg_grid* dst);
+bool bf16_avgpool(mg_ctx*, const mg_grid* in, int r, mg_grid* out);
+bool bf16_pool2(mg_ctx*, const mg_grid* in, mg_grid* out, int c_off);
 
 namespace {
 
@@ -411,6 +414,7 @@ extern "C" {
 
 int mg_import_nchw(mg_ctx* ctx, const float* src, mg_grid* dst) {
   if (!ctx || !src || !dst) return MG_ERR_INVALID_ARG;
+  if (ctx->dtype == MG_BF16 && bf16_import_nchw(ctx, src, dst)) { MG_CHECK_LAUNCH(ctx); return MG_OK; }
   int64_t total = (int64_t)dst->N * dst->H * dst->W * dst->Cp;
   MG_DISPATCH(ctx, import_nchw_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>(src, (T*)dst->data, dst->N, dst->C, dst->Cp, dst->H, dst->W););
   MG_CHECK_LAUNCH(ctx);
@@ -487,6 +491,7 @@ int mg_pool_forward(mg_ctx* ctx, const mg_grid* in, mg_grid* out, int32_t c_offs
   int Ho = (in->H + 1) / 2, Wo = (in->W + 1) / 2;
   MG_REQUIRE(ctx, out->H == Ho && out->W == Wo && out->N == in->N && c_offset + in->C <= out->Cp, MG_ERR_SHAPE,
              "pool: out %dx%d (C %d) for in %dx%d (C %d, off %d)", out->H, out->W, out->C, in->H, in->W, in->C, c_offset);
+  if (ctx->dtype == MG_BF16 && !argmax && bf16_pool2(ctx, in, out, c_offset)) { MG_CHECK_LAUNCH(ctx); return MG_OK; }
   int64_t total = (int64_t)in->N * Ho * Wo * in->C;
   MG_DISPATCH(ctx, pool2_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>(make_view<T>(*in), (T*)out->data, Ho, Wo, out->Cp, c_offset, argmax););
   MG_CHECK_LAUNCH(ctx);
@@ -506,6 +511,7 @@ int mg_avgpool_forward(mg_ctx* ctx, const mg_grid* in, int32_t r, mg_grid* out) 
   if (!ctx || !in || !out || r < 1) return MG_ERR_INVALID_ARG;
   int Ho = in->H / r, Wo = in->W / r;
   MG_REQUIRE(ctx, out->H == Ho && out->W == Wo && out->N == in->N && out->C == in->C, MG_ERR_SHAPE, "avgpool: shape");
+  if (ctx->dtype == MG_BF16 && bf16_avgpool(ctx, in, r, out)) { MG_CHECK_LAUNCH(ctx); return MG_OK; }
   int64_t total = (int64_t)in->N * Ho * Wo * out->Cp;
   MG_DISPATCH(ctx, avgpool_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>(make_view<T>(*in), r, (T*)out->data, Ho, Wo, out->Cp););
   MG_CHECK_LAUNCH(ctx);

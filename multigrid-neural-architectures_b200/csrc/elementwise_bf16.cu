@@ -388,6 +388,49 @@ __global__ void __launch_bounds__(256) pool3_bf16_kernel(const bf16* __restrict_
   }
 }
 
+// ---------------------------------------------------------------- image import / pyramid / plain pool ----------
+// NCHW fp32 (Torch boundary) -> NHWC bf16 with C <= 8: one thread per pixel, coalesced plane reads, one 16-byte store
+__global__ void __launch_bounds__(256) import_nchw_c8_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int C, int64_t HW, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int64_t n = i / HW, r = i - n * HW;
+  V8 v;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) v.v[c] = c < C ? src[(n * C + c) * HW + r] : 0.f;
+  *reinterpret_cast<uint4*>(dst + i * 8) = pack8(v);
+}
+
+// SpatialAveragePooling(r,r,r,r) / plain SpatialMaxPooling(2,2,2,2):ceil(): one thread per (output pixel, 8 channels)
+template <bool MAX>
+__global__ void __launch_bounds__(256) pool_vec_kernel(const bf16* __restrict__ in, int H, int W, int cp, int C, int r, bf16* __restrict__ out,
+                                                       int Ho, int Wo, int o_cp, int c_off, int N) {
+  const int V = cp >> 3;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)N * Ho * Wo * V) return;
+  const int vc = (int)(i % V); int64_t q = i / V;
+  const int ox = (int)(q % Wo); q /= Wo;
+  const int oy = (int)(q % Ho); const int n = (int)(q / Ho);
+  const int c0 = vc * 8;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = MAX ? -INFINITY : 0.f;
+  for (int dy = 0; dy < r; ++dy)
+    for (int dx = 0; dx < r; ++dx) {
+      const int y = oy * r + dy, x = ox * r + dx;
+      if (y >= H || x >= W) continue;
+      const V8 v = ld8(in + (((int64_t)n * H + y) * W + x) * cp + c0);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (MAX) { if (v.v[e] > acc[e] || v.v[e] != v.v[e]) acc[e] = v.v[e]; }
+        else acc[e] += v.v[e];
+      }
+    }
+  V8 o;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) o.v[e] = (c0 + e < C) ? (MAX ? acc[e] : acc[e] / (float)(r * r)) : 0.f;
+  *reinterpret_cast<uint4*>(out + (((int64_t)n * Ho + oy) * Wo + ox) * o_cp + c_off + c0) = pack8(o);
+}
+
 static inline unsigned grid_for(int64_t threads) { return (unsigned)mg_cdiv(threads, 256); }
 // persistent-style grid for the reducing kernels: a few CTAs per SM, each thread loops
 static inline unsigned reduce_grid(const mg_ctx* ctx, int64_t items, int per_sm = 4) {
@@ -462,5 +505,28 @@ bool bf16_pool3(mg_ctx* ctx, const mg_grid* in, mg_grid* out, uint8_t* code) {
   const int64_t total = (int64_t)in->N * out->H * out->W * (in->Cp / 8);
   pool3_bf16_kernel<<<grid_for(total), 256, 0, ctx->stream>>>((const bf16*)in->data, in->H, in->W, in->Cp, in->C, (bf16*)out->data, code,
                                                              out->H, out->W, in->N);
+  return true;
+}
+
+bool bf16_import_nchw(mg_ctx* ctx, const float* src, mg_grid* dst) {
+  if (dst->Cp != 8) return false;
+  const int64_t HW = (int64_t)dst->H * dst->W, total = HW * dst->N;
+  import_nchw_c8_kernel<<<grid_for(total), 256, 0, ctx->stream>>>(src, (bf16*)dst->data, dst->C, HW, total);
+  return true;
+}
+
+bool bf16_avgpool(mg_ctx* ctx, const mg_grid* in, int r, mg_grid* out) {
+  if (in->scale || in->Cp % 8 || out->Cp != in->Cp) return false;
+  const int64_t total = (int64_t)in->N * out->H * out->W * (in->Cp / 8);
+  pool_vec_kernel<false><<<grid_for(total), 256, 0, ctx->stream>>>((const bf16*)in->data, in->H, in->W, in->Cp, in->C, r, (bf16*)out->data,
+                                                                   out->H, out->W, out->Cp, 0, in->N);
+  return true;
+}
+
+bool bf16_pool2(mg_ctx* ctx, const mg_grid* in, mg_grid* out, int c_off) {
+  if (in->scale || in->Cp % 8 || out->Cp % 8 || c_off % 8 || c_off + in->Cp > out->Cp) return false;
+  const int64_t total = (int64_t)in->N * out->H * out->W * (in->Cp / 8);
+  pool_vec_kernel<true><<<grid_for(total), 256, 0, ctx->stream>>>((const bf16*)in->data, in->H, in->W, in->Cp, in->C, 2, (bf16*)out->data,
+                                                                  out->H, out->W, out->Cp, c_off, in->N);
   return true;
 }

@@ -462,6 +462,77 @@ class cifar_prnmg(BASICNET):
     trainRule = cifar_rnmg.trainRule
 
 
+def mgConv_pnmg(nInputPlanes, nOutputPlanes, kernels, dropout=None):
+    """models/cifar/pnmg.lua:84-112: Sequential{ ResampleConcat, ParallelTable{ [Dropout] Conv BN(1e-3) ReLU } }"""
+    assert len(nInputPlanes) == len(nOutputPlanes), "number of input grid should be equal to output grid"
+    assert len(nInputPlanes) == len(kernels), "should provide kernel size for every scale of grid"
+    mg_conv = nn.Sequential()
+    resample_concat, _nIPs = ResampleConcat(nInputPlanes)
+    mg_conv.add(resample_concat)
+    convs = nn.ParallelTable()
+    for i in range(len(_nIPs)):
+        _conv = nn.Sequential()
+        if dropout:
+            _conv.add(nn.Dropout(dropout))   # pnmg.lua:25-27: dropout BEFORE the convolution
+        ConvBNReLU(_conv, _nIPs[i], nOutputPlanes[i], kernels[i], 1e-3)
+        convs.add(_conv)
+    mg_conv.add(convs)
+    return mg_conv
+
+
+class cifar_pnmg(BASICNET):
+    """models/cifar/pnmg.lua: plain progressive multigrid (P-NMG)"""
+    name = "cifar/pnmg"
+    blocks = CIFAR_WIDE_BLOCKS          # pnmg.lua:244-250
+    dropouts = [None, 0.1, 0.2, 0.3, 0.4]
+
+    @classmethod
+    def createModel(cls, opt):
+        model = nn.Sequential()
+        nIPs = [3, 3, 3]
+        nLayer = opt.nLayer or 1
+        for indBlock, (nOPs, kernels) in enumerate(opt.blocks or cls.blocks, 1):
+            dropout = cls.dropouts[indBlock - 1] if opt.isDropout else None
+            if indBlock == 1:   # MultiGridsInput, pnmg.lua:177-228
+                model.add(mgConvInput_pyramid(nOPs, 3, 1e-3))
+                n = len(nOPs)
+                for nGrid in range(1, n + 1):
+                    for _ in range(nLayer):
+                        if nGrid > 1:
+                            mg_convs = nn.ConcatTable()
+                            for j in range(1, n - nGrid + 1):
+                                mg_convs.add(nn.SelectTable(j))
+                            _select = nn.ConcatTable()
+                            _nOPs = []
+                            for j in range(n - nGrid + 1, n + 1):
+                                _select.add(nn.SelectTable(j))
+                                _nOPs.append(nOPs[j - 1])
+                            mg_convs.add(nn.Sequential().add(_select).add(mgConv_pnmg(_nOPs, _nOPs, [3] * len(_nOPs), dropout)))
+                            model.add(mg_convs)
+                            model.add(nn.FlattenTable())
+                        else:
+                            convs = nn.ParallelTable()
+                            for _j in range(n - 1):
+                                convs.add(nn.Identity())
+                            _conv = nn.Sequential()
+                            if dropout:
+                                _conv.add(nn.Dropout(dropout))
+                            convs.add(ConvBNReLU(_conv, nOPs[-1], nOPs[-1], 3, 1e-3))
+                            model.add(convs)
+                nIPs = list(nOPs)
+            else:               # MultiGrids, pnmg.lua:230-236
+                for _ in range(nLayer):
+                    model.add(mgConv_pnmg(nIPs, nOPs, kernels, dropout))
+                    nIPs = list(nOPs)
+            model.add(mgPool(nIPs, kernels[-1] == 1))
+        model.add(_classifier(nIPs[0], _nclass(opt)))
+        MSRinit(model)
+        return _finish(model, opt, cls)
+
+    createCriterion = BASICNET.createCriterion_nll
+    trainRule = cifar_rnmg.trainRule
+
+
 class ilsvrc_rnmg(BASICNET):
     """models/ilsvrc/rnmg.lua: R-MG-18/34 -- the north-star network"""
     name = "ilsvrc/rnmg"
@@ -528,7 +599,7 @@ class mnist_prnmg(BASICNET):
         return {"LR": 0.1 * 0.1 ** math.floor((currentEpoch - 1) / 30), "WD": 1e-4}
 
 
-NETS = {c.name: c for c in (cifar_nmg, cifar_rnmg, cifar_prnmg, ilsvrc_rnmg, mnist_prnmg)}
+NETS = {c.name: c for c in (cifar_nmg, cifar_rnmg, cifar_pnmg, cifar_prnmg, ilsvrc_rnmg, mnist_prnmg)}
 
 
 def load_net(netType):

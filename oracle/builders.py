@@ -323,6 +323,46 @@ def cifar_prnmg(nLayer=2, nClass=100, blocks=None):
     return model
 
 
+def cifar_pnmg(nLayer=1, nClass=100, blocks=None):
+    """models/cifar/pnmg.lua:238-310 (plain progressive multigrid; BN eps 1e-3, gamma keeps U(0,1))"""
+    blocks = blocks or CIFAR_WIDE
+    model = nn.Sequential()
+    nIPs = [3, 3, 3]
+    for indBlock, (nOPs, kernels) in enumerate(blocks, 1):
+        if indBlock == 1:  # MultiGridsInput, pnmg.lua:177-228
+            model.add(image_pyramid_convs(nOPs, 3, 1e-3))
+            n = len(nOPs)
+            for nGrid in range(1, n + 1):
+                for _ in range(nLayer):
+                    if nGrid > 1:
+                        mg_convs = nn.ConcatTable()
+                        for j in range(1, n - nGrid + 1):
+                            mg_convs.add(nn.SelectTable(j))
+                        _select = nn.ConcatTable()
+                        _nOPs = []
+                        for j in range(n - nGrid + 1, n + 1):
+                            _select.add(nn.SelectTable(j))
+                            _nOPs.append(nOPs[j - 1])
+                        mg_convs.add(nn.Sequential().add(_select).add(plain_mgConv(_nOPs, _nOPs, [3] * len(_nOPs), 1e-3)))
+                        model.add(mg_convs)
+                        model.add(nn.FlattenTable())
+                    else:
+                        convs = nn.ParallelTable()
+                        for _j in range(n - 1):
+                            convs.add(nn.Identity())
+                        convs.add(ConvBNReLU(nn.Sequential(), nOPs[-1], nOPs[-1], 3, 1e-3))
+                        model.add(convs)
+            nIPs = list(nOPs)
+        else:
+            for _ in range(nLayer):
+                model.add(plain_mgConv(nIPs, nOPs, kernels, 1e-3))
+                nIPs = list(nOPs)
+        model.add(mgPool(nIPs, kernels[-1] == 1))
+    model.add(classifier(nIPs[0], nClass))
+    nn.conv_init_msr_fanout(model)
+    return model
+
+
 def ilsvrc_stem(nOutputPlanes):
     """mgConvInput, models/ilsvrc/rnmg.lua:161-189"""
     resample_image = nn.ConcatTable()

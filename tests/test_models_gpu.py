@@ -91,6 +91,8 @@ NETS = [
     ("R-NMG-12 cifar/rnmg nLayer=1", lambda: OB.cifar_rnmg(1), B.cifar_rnmg, dict(nLayer=1), (16, 3, 32, 32), 100, 12),
     ("PR-NMG-16 cifar/prnmg nLayer=1 narrow", lambda: OB.cifar_prnmg(1, blocks=OB.CIFAR_RNMG_NARROW), B.cifar_prnmg,
      dict(nLayer=1, blocks=B.CIFAR_RNMG_BLOCKS), (16, 3, 32, 32), 100, 16),
+    ("P-NMG-11 cifar/pnmg nLayer=1 narrow", lambda: OB.cifar_pnmg(1, blocks=OB.CIFAR_RNMG_NARROW), B.cifar_pnmg,
+     dict(nLayer=1, blocks=B.CIFAR_RNMG_BLOCKS), (16, 3, 32, 32), 100, 11),
     ("R-MG-10 ilsvrc/rnmg reduced 64x64",
      lambda: OB.ilsvrc_rnmg(18, 10, [16, 8, 8], R10_BLOCKS, [1, 1, 1, 1], 2),
      B.ilsvrc_rnmg, dict(nClass=10, inputBlock=[16, 8, 8], cfg=[1, 1, 1, 1], avg=2, blocks=R10_BLOCKS),
