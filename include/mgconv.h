@@ -155,6 +155,14 @@ int mg_pool3s2_forward(mg_ctx* ctx, const mg_grid* in, mg_grid* out, uint8_t* ar
 int mg_global_avgpool_forward(mg_ctx* ctx, const mg_grid* in, mg_grid* out);
 int mg_global_avgpool_backward(mg_ctx* ctx, const mg_grid* dout, mg_grid* din);
 
+/* cudnn.SpatialFullConvolution(nIP, nOP, 2,2, 2,2, 0,0) -- the learned 2x up-sampling of U-MG
+ * (models/mnist-cluttered/unmg.lua:35-52): y[n,2y+dy,2x+dx,co] = b[co] + sum_ci x[n,y,x,ci] * w[ci][co][dy][dx];
+ * weight layout [nIP][nOP][2][2] as Torch stores it.  bn_sums as in mg_conv_forward.  backward: dx (nullable),
+ * dw += gscale * ..., dbias += gscale * sum(g) (both nullable). */
+int mg_upconv2x2_forward(mg_ctx* ctx, const mg_grid* x, const float* w, const float* bias, mg_grid* y, double* bn_sums);
+int mg_upconv2x2_backward(mg_ctx* ctx, const mg_grid* x, const float* w, const mg_grid* g, mg_grid* dx,
+                          float* dw, float* dbias, float gscale);
+
 /* ---- backward ------------------------------------------------------------------------- */
 /* Sum of all consumers' gradient contributions into tensor x (ConcatTable backward sums
  * its branches), routed through pool argmax / upsample block-sum, times the ReLU mask of x

@@ -779,3 +779,107 @@ int mg_sigmoid_backward(mg_ctx* ctx, const float* prob_nchw, const float* grad_o
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------- 2x2 stride-2 up-convolution (U-MG) ----
+// cudnn.SpatialFullConvolution(nIP, nOP, 2,2, 2,2, 0,0) of models/mnist-cluttered/unmg.lua:35-52:
+// every input pixel owns its 2x2 output block, y[n,2y+dy,2x+dx,co] = b[co] + sum_ci x[n,y,x,ci] * w[ci][co][dy][dx].
+// CUDA-core kernels (fp32 accumulate): the layer belongs to the config-5 comparator, not to the hot path.
+namespace {
+
+template <typename T>
+__global__ void upconv_fwd_kernel(const T* __restrict__ x, int x_cp, int Cin, const float* __restrict__ w, const float* __restrict__ bias,
+                                  T* __restrict__ y, int y_cp, int Cout, int N, int H, int W) {
+  int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x;
+  const int64_t total = (int64_t)N * 2 * H * 2 * W * y_cp;
+  if (i >= total) return;
+  const int co = i % y_cp; int64_t q = i / y_cp;
+  const int ox = q % (2 * W); q /= 2 * W; const int oy = q % (2 * H); const int n = q / (2 * H);
+  float acc = 0.f;
+  if (co < Cout) {
+    acc = bias ? bias[co] : 0.f;
+    const T* xp = x + (((size_t)n * H + (oy >> 1)) * W + (ox >> 1)) * x_cp;
+    const float* wp = w + (size_t)co * 4 + (oy & 1) * 2 + (ox & 1);
+    for (int ci = 0; ci < Cin; ++ci) acc = fmaf(mg_ld(xp + ci), wp[(size_t)ci * Cout * 4], acc);
+  }
+  mg_st(y + i, acc);
+}
+
+template <typename T>
+__global__ void upconv_dgrad_kernel(const T* __restrict__ g, int g_cp, int Cout, const float* __restrict__ w, T* __restrict__ dx, int x_cp,
+                                    int Cin, int N, int H, int W) {
+  int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x;
+  const int64_t total = (int64_t)N * H * W * x_cp;
+  if (i >= total) return;
+  const int ci = i % x_cp; int64_t q = i / x_cp;
+  const int x = q % W; q /= W; const int y = q % H; const int n = q / H;
+  float acc = 0.f;
+  if (ci < Cin)
+    for (int d = 0; d < 4; ++d) {
+      const T* gp = g + (((size_t)n * 2 * H + 2 * y + (d >> 1)) * 2 * W + 2 * x + (d & 1)) * g_cp;
+      const float* wp = w + (size_t)ci * Cout * 4 + d;
+      for (int co = 0; co < Cout; ++co) acc = fmaf(mg_ld(gp + co), wp[co * 4], acc);
+    }
+  mg_st(dx + i, acc);
+}
+
+// one block per (ci, co-tile of 64 x 4 positions = 256 threads), pixel range split over blockIdx.z
+template <typename T>
+__global__ void __launch_bounds__(256) upconv_wgrad_kernel(const T* __restrict__ x, int x_cp, const T* __restrict__ g, int g_cp, float* dw,
+                                                           int Cin, int Cout, int N, int H, int W, float gscale, int64_t pix_per_z) {
+  const int ci = blockIdx.x;
+  const int co = blockIdx.y * 64 + (threadIdx.x >> 2), d = threadIdx.x & 3;
+  const int64_t P = (int64_t)N * H * W;
+  const int64_t p0 = (int64_t)blockIdx.z * pix_per_z, p1 = min(P, p0 + pix_per_z);
+  if (co >= Cout) return;
+  float acc = 0.f;
+  for (int64_t p = p0; p < p1; ++p) {
+    const int xx = p % W; const int64_t q = p / W; const int yy = q % H; const int n = q / H;
+    const float xv = mg_ld(x + p * x_cp + ci);
+    acc = fmaf(xv, mg_ld(g + (((size_t)n * 2 * H + 2 * yy + (d >> 1)) * 2 * W + 2 * xx + (d & 1)) * g_cp + co), acc);
+  }
+  atomicAdd(dw + ((size_t)ci * Cout + co) * 4 + d, gscale * acc);
+}
+
+}  // namespace
+
+int simt_dbias(mg_ctx* ctx, const mg_grid* g, int Cout, float* dbias, float gscale);
+
+extern "C" {
+
+int mg_upconv2x2_forward(mg_ctx* ctx, const mg_grid* x, const float* w, const float* bias, mg_grid* y, double* bn_sums) {
+  if (!ctx || !x || !w || !y) return MG_ERR_INVALID_ARG;
+  MG_REQUIRE(ctx, y->H == 2 * x->H && y->W == 2 * x->W && y->N == x->N && !x->scale, MG_ERR_SHAPE, "upconv: y must be 2x the size of x");
+  const int64_t total = (int64_t)y->N * y->H * y->W * y->Cp;
+  MG_DISPATCH(ctx, upconv_fwd_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>((const T*)x->data, x->Cp, x->C, w, bias, (T*)y->data, y->Cp, y->C,
+                                                                             x->N, x->H, x->W););
+  MG_CHECK_LAUNCH(ctx);
+  if (bn_sums) return mg_bn_stats(ctx, y, bn_sums);
+  return MG_OK;
+}
+
+int mg_upconv2x2_backward(mg_ctx* ctx, const mg_grid* x, const float* w, const mg_grid* g, mg_grid* dx, float* dw, float* dbias,
+                          float gscale) {
+  if (!ctx || !x || !w || !g) return MG_ERR_INVALID_ARG;
+  MG_REQUIRE(ctx, g->H == 2 * x->H && g->W == 2 * x->W && g->N == x->N, MG_ERR_SHAPE, "upconv backward: g must be 2x the size of x");
+  if (dx) {
+    const int64_t total = (int64_t)x->N * x->H * x->W * dx->Cp;
+    MG_DISPATCH(ctx, upconv_dgrad_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>((const T*)g->data, g->Cp, g->C, w, (T*)dx->data, dx->Cp, x->C,
+                                                                                 x->N, x->H, x->W););
+    MG_CHECK_LAUNCH(ctx);
+  }
+  if (dw) {
+    const int64_t P = (int64_t)x->N * x->H * x->W;
+    const int gy = (int)mg_cdiv(g->C, 64);
+    int64_t z = std::max<int64_t>(1, std::min<int64_t>(mg_cdiv(P, 256), mg_cdiv((int64_t)ctx->num_sms * 8, (int64_t)x->C * gy)));
+    const int64_t ppz = mg_cdiv(P, z);
+    z = mg_cdiv(P, ppz);
+    dim3 grid((unsigned)x->C, (unsigned)gy, (unsigned)z);
+    MG_DISPATCH(ctx, upconv_wgrad_kernel<T><<<grid, 256, 0, ctx->stream>>>((const T*)x->data, x->Cp, (const T*)g->data, g->Cp, dw, x->C, g->C, x->N,
+                                                                          x->H, x->W, gscale, ppz););
+    MG_CHECK_LAUNCH(ctx);
+  }
+  if (dbias) return simt_dbias(ctx, g, g->C, dbias, gscale);
+  return MG_OK;
+}
+
+}  // extern "C"

@@ -599,7 +599,90 @@ class mnist_prnmg(BASICNET):
         return {"LR": 0.1 * 0.1 ** math.floor((currentEpoch - 1) / 30), "WD": 1e-4}
 
 
-NETS = {c.name: c for c in (cifar_nmg, cifar_rnmg, cifar_pnmg, cifar_prnmg, ilsvrc_rnmg, mnist_prnmg)}
+class mnist_unmg(BASICNET):
+    """models/mnist-cluttered/unmg.lua: U-Net whose every stage is a multigrid convolution; skip connections
+    are zipped by nn.ConcatUnet (layers/ConcatUnet.lua) and joined per grid by MapTable(JoinTable(2))"""
+    name = "mnist-cluttered/unmg"
+    blocks = [([64, 32, 16], False), ([128, 64, 32], True), ([256, 128], True), ([512], None)]   # unmg.lua:181-186
+
+    @staticmethod
+    def mgUpConv(nInputPlanes, nOutputPlanes):   # unmg.lua:35-52
+        assert len(nInputPlanes) == len(nOutputPlanes), "number of input grid should be equal to output grid"
+        upconvs = nn.ParallelTable()
+        for i in range(len(nInputPlanes)):
+            upconvs.add(nn.Sequential()
+                        .add(nn.SpatialFullConvolution(nInputPlanes[i], nOutputPlanes[i], 2, 2, 2, 2, 0, 0))
+                        .add(SBatchNorm(nOutputPlanes[i], 1e-3)).add(ReLU(True)))
+        return upconvs
+
+    @staticmethod
+    def mgConv(nIn, nOut, isReLU):               # unmg.lua:54-109: 3x3 ConvBNReLU, or 1x1 ConvBN for the output maps
+        k = 3 if isReLU else 1
+        return mgConv_plain(nIn, nOut, [k] * len(nIn), 1e-3, isReLU)
+
+    @staticmethod
+    def mgPool(nIn, isDrop):                     # unmg.lua:131-148: drops the coarsest grid when isDrop (mutates nIn)
+        mg_pool = nn.ConcatTable()
+        n = len(nIn)
+        for i in range(1, n + 1):
+            if i == n and isDrop:
+                del nIn[i - 1]
+            else:
+                mg_pool.add(nn.Sequential().add(nn.SelectTable(i)).add(Max(2, 2, 2, 2, 0, 0).ceil()))
+        return mg_pool
+
+    @classmethod
+    def createModel(cls, opt):
+        blocks = opt.blocks or cls.blocks
+        nClass = opt.nClass or (10 if (opt.dataset or "mnist-seg") == "mnist-seg" else 1)
+        state = {"nIP": [1]}
+
+        def Unet(depth):                         # unmg.lua:189-234
+            unetIP = state["nIP"]
+            unetOP, isDrop = blocks[depth - 1]
+            model = nn.Sequential()
+            if depth == len(blocks):
+                model.add(cls.mgConv(unetIP, unetOP, True))
+                model.add(cls.mgUpConv(unetOP, unetIP))
+            else:
+                if depth > 1:
+                    model.add(cls.mgConv(unetIP, unetOP, True))
+                else:
+                    model.add(mgConvInput_pyramid(unetOP, 1, 1e-3))
+                state["nIP"] = list(unetOP)
+                shortcut_subnet = nn.ConcatTable()
+                mg_pool = cls.mgPool(state["nIP"], isDrop)
+                subnet, subnetOP = Unet(depth + 1)
+                shortcut_subnet.add(nn.Identity())
+                shortcut_subnet.add(nn.Sequential().add(mg_pool).add(subnet))
+                model.add(shortcut_subnet)
+                model.add(nn.ConcatUnet())
+                model.add(nn.MapTable(nn.JoinTable(2)))
+                sumOP = [(unetOP[i] if i < len(unetOP) else 0) + (subnetOP[i] if i < len(subnetOP) else 0)
+                         for i in range(max(len(unetOP), len(subnetOP)))]
+                model.add(cls.mgConv(sumOP, unetOP, True))
+                if depth > 1:
+                    model.add(cls.mgUpConv(unetOP, unetIP))
+                else:
+                    model.add(cls.mgConv(unetOP, [nClass] * len(unetOP), False))
+                    model.add(nn.SelectTable(1))
+            return model, unetIP
+
+        model, _ = Unet(1)
+        model.add(nn.Sigmoid())
+        MSRinit(model)   # SpatialConvolution only (unmg.lua:239-252): up-convolutions and BN keep their defaults
+        return model
+
+    @classmethod
+    def createCriterion(cls):
+        return nn.MultiCriterion().add(nn.BCECriterion())
+
+    @classmethod
+    def trainRule(cls, currentEpoch, opt):
+        return {"LR": 0.1 * 0.1 ** math.floor((currentEpoch - 1) / 30), "WD": 1e-4}
+
+
+NETS = {c.name: c for c in (cifar_nmg, cifar_rnmg, cifar_pnmg, cifar_prnmg, ilsvrc_rnmg, mnist_prnmg, mnist_unmg)}
 
 
 def load_net(netType):

@@ -79,6 +79,8 @@ SIGNATURES = {
     "mg_pool3s2_forward": (_I, [_P, _G, _G, _P]),
     "mg_global_avgpool_forward": (_I, [_P, _G, _G]),
     "mg_global_avgpool_backward": (_I, [_P, _G, _G]),
+    "mg_upconv2x2_forward": (_I, [_P, _G, _P, _P, _G, _P]),
+    "mg_upconv2x2_backward": (_I, [_P, _G, _P, _G, _G, _P, _P, _F]),
     "mg_grad_combine": (_I, [_P, _G, _I, _G, C.c_int32, C.POINTER(mg_grad_src), _G, _P]),
     "mg_bn_backward": (_I, [_P, _G, _G, _G, _P, _I64, _P, _P, _P, _P, _P, _F, _P, _P]),
     "mg_conv_backward_data": (_I, [_P, _D, _P, _P, _G, _G]),

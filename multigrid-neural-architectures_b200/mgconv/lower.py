@@ -231,6 +231,14 @@ class Builder:
         self.emit(op)
         return NodeVal(op)
 
+    def upconv(self, mod, v):
+        t = self.as_tensor(v).spec
+        if t.C != mod.nInputPlane:
+            raise ValueError(f"SpatialFullConvolution: {t.C} input planes, expected {mod.nInputPlane}")
+        op = O.UpConvOp(self, mod, t, f"upconv{len([o for o in self.ops if isinstance(o, O.UpConvOp)])}")
+        self.emit(op)
+        return NodeVal(op)
+
     def batchnorm(self, mod, v):
         if not (isinstance(v, NodeVal) and v.out is None and v.bn is None and not v.relu1 and v.res is None):
             raise NotImplementedError("SpatialBatchNormalization must directly follow a convolution")

@@ -332,6 +332,30 @@ class SpatialConvolution(Module):
         return b.conv(self, x)
 
 
+class SpatialFullConvolution(Module):
+    """cudnn.SpatialFullConvolution(nIP, nOP, 2,2, 2,2, 0,0): learned 2x up-sampling (unmg.lua:35-41)"""
+    typename = "cudnn.SpatialFullConvolution"
+
+    def __init__(self, nInputPlane, nOutputPlane, kW, kH, dW, dH, padW=0, padH=0):
+        super().__init__()
+        assert (kW, kH, dW, dH, padW, padH) == (2, 2, 2, 2, 0, 0), "only the 2x2 stride-2 up-convolution of U-MG is lowered"
+        self.nInputPlane, self.nOutputPlane = nInputPlane, nOutputPlane
+        self.kW = self.kH = 2
+        self.weight = torch.empty(nInputPlane, nOutputPlane, 2, 2)
+        self.bias = torch.empty(nOutputPlane)
+        self.gradWeight = torch.zeros_like(self.weight)
+        self.gradBias = torch.zeros_like(self.bias)
+        stdv = 1.0 / math.sqrt(kW * kH * nInputPlane)   # torch7 SpatialFullConvolution:reset()
+        self.weight.uniform_(-stdv, stdv)
+        self.bias.uniform_(-stdv, stdv)
+
+    def own_parameters(self):
+        return [("weight", self.weight, self.gradWeight), ("bias", self.bias, self.gradBias)]
+
+    def trace(self, x, b):
+        return b.upconv(self, x)
+
+
 class Linear(Module):
     typename = "nn.Linear"
 

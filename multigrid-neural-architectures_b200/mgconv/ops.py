@@ -232,6 +232,57 @@ class ConvOp(Op):
         E.param_done(self.mod)
 
 
+class UpConvOp(Op):
+    """cudnn.SpatialFullConvolution(nIP, nOP, 2,2,2,2) of U-MG (unmg.lua:35-52); epilogue (BN, ReLU) through
+    the same ApplyOp as a convolution"""
+
+    def __init__(self, b, mod, inp, name):
+        self.mod, self.inp, self.name = mod, inp, name
+        self.Cout, self.Ho, self.Wo = mod.nOutputPlane, 2 * inp.H, 2 * inp.W
+        self.segs = [(inp, MG_SEG_SAME)]
+        self.k = 2
+        self.y = b.new_tensor(self.Cout, self.Ho, self.Wo, name + ".y")
+        self.y.producer = self
+        self.apply = None
+        self.want_stats = False
+        self.sums = None
+        self.ycomb = None
+        self.needs_dgrad = inp.needs_grad
+
+    def setup_fwd(self, E):
+        self.y.buf = E.alloc(self.y.shape())
+        self.gi, self.yg = self.inp.grid(), self.y.grid()
+        if self.want_stats:
+            self.sums = E.alloc((2 * self.Cout,), torch.float64)
+
+    def pack(self, E):
+        pass
+
+    def fwd(self, E):
+        if self.sums is not None:
+            E.ctx.call("mg_memset_zero", ptr(self.sums), self.sums.numel() * 8)
+        E.ctx.call("mg_upconv2x2_forward", C.byref(self.gi), ptr(self.mod.weight), ptr(self.mod.bias), C.byref(self.yg), ptr(self.sums))
+
+    def setup_bwd(self, E):
+        if self.apply is None:
+            self.ycomb = Combine(E, self.y)
+            self.y.G = self.ycomb.grid()
+        self.dx = None
+        if self.inp.needs_grad:
+            self.dx = E.alloc(self.inp.shape())
+            self.dxg = self.inp.grid(self.dx)
+            self.inp.srcs.append(Src(self.dx, self.inp.H, self.inp.W, self.inp.C, self.inp.Cp, 0, MG_SEG_SAME))
+
+    def bwd(self, E):
+        if self.ycomb is not None:
+            self.ycomb.run()
+        fused_bias = self.apply is not None and self.apply.bn is not None and not E.bn_sync
+        E.ctx.call("mg_upconv2x2_backward", C.byref(self.gi), ptr(self.mod.weight), C.byref(self.y.G),
+                   C.byref(self.dxg) if self.dx is not None else None, ptr(self.mod.gradWeight),
+                   None if fused_bias else ptr(self.mod.gradBias), E.gscale)
+        E.param_done(self.mod)
+
+
 class ApplyOp(Op):
     """epilogue pass of a convolution: out = relu?( BN(y) + shortcut[c < C_s] ), plus the pooled
     companion of out when a coarser neighbour gathers it.  SpatialBatchNormalization -> [ReLU] or

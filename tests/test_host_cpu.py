@@ -101,6 +101,19 @@ def test_ilsvrc_stage_shapes_and_fusion():
     assert sum(isinstance(o, O.CatOp) for o in b.ops) == 2
 
 
+def test_unmg_concat_unet_folds_into_segments():
+    """ConcatUnet + MapTable(JoinTable(2)) (unmg.lua:219-220) never materialise a concatenation: the joined
+    {shortcut_i, subnet_i} pairs, their pooled and up-sampled views all become segments (<= 6) of one conv"""
+    from mgconv import builders as B, lower as L, ops as O
+    m = B.load_net("mnist-cluttered/unmg").createModel(B.Opt(dataset="mnist-seg"))
+    assert sum(w.numel() for w in m.parameters()[0]) == 5_903_290     # = the oracle's restatement of unmg.lua
+    b, _ = L.trace_model(m, (2, 1, 64, 64))
+    s = L.plan_summary(b)
+    assert s["max_segs"] == 6 and s["convs"] == 20
+    assert sum(isinstance(o, O.UpConvOp) for o in b.ops) == 6
+    assert not any(isinstance(o, O.CatOp) for o in b.ops)
+
+
 def test_shared_conv_output_is_detected():
     from mgconv import nn, lower as L
     conv = nn.SpatialConvolution(3, 4, 3, 3, 1, 1, 1, 1)

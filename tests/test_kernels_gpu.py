@@ -221,6 +221,30 @@ def test_stem_conv7x7_stride2(ctx, impl):
     ctx.set_impl(ffi.MG_IMPL_AUTO)
 
 
+def test_upconv2x2_forward_backward(ctx):
+    """cudnn.SpatialFullConvolution(nIP, nOP, 2,2,2,2) of U-MG (models/mnist-cluttered/unmg.lua:35-41)"""
+    N, Cin, Cout, H = 2, 12, 10, 5
+    x = rnd(N, Cin, H, H)
+    w = bf16_round(rng.standard_normal((Cin, Cout, 2, 2)) * 0.3)
+    b = bf16_round(rng.standard_normal(Cout) * 0.1)
+    y_ref = O.upconv2x2_forward(x, w, b)
+    gx, gy = Grid(ctx.dtype, N, Cin, H, H, x), Grid(ctx.dtype, N, Cout, 2 * H, 2 * H)
+    wd, bd = dev(w), dev(b)
+    sums = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
+    ctx.call("mg_upconv2x2_forward", C.byref(gx.g()), ptr(wd), ptr(bd), C.byref(gy.g()), ptr(sums))
+    tol = TOL[ctx.dtype]
+    assert max_rel(gy.nchw(), y_ref) <= tol
+    assert np.allclose(sums.cpu().numpy()[:Cout] / (N * 4 * H * H), y_ref.mean(axis=(0, 2, 3)), atol=tol * np.abs(y_ref).max())
+    g = rnd(N, Cout, 2 * H, 2 * H)
+    gx_ref, gw_ref, gb_ref = O.upconv2x2_backward(x, w, g)
+    gg, dx = Grid(ctx.dtype, N, Cout, 2 * H, 2 * H, g), Grid(ctx.dtype, N, Cin, H, H)
+    dw, db = torch.zeros_like(wd), torch.zeros_like(bd)
+    ctx.call("mg_upconv2x2_backward", C.byref(gx.g()), ptr(wd), C.byref(gg.g()), C.byref(dx.g()), ptr(dw), ptr(db), 1.0)
+    torch.cuda.synchronize()
+    assert max_rel(dx.nchw(), gx_ref) <= tol
+    assert max_rel(dw.cpu().numpy(), gw_ref) <= tol and max_rel(db.cpu().numpy(), gb_ref) <= tol
+
+
 def test_conv_shape_errors_are_reported_not_fatal(ctx):
     """JoinTable would raise on inconsistent sizes in the reference; here: status + message"""
     a, b = Grid(ctx.dtype, 1, 4, 8, 8), Grid(ctx.dtype, 1, 4, 5, 5)

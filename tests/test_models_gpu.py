@@ -200,6 +200,51 @@ def test_mnist_prnmg_dense_prediction():
     assert rel_err(pg, og) <= 2e-3, rel_err(pg, og)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_mnist_unmg_concat_unet(precision):
+    """models/mnist-cluttered/unmg.lua + layers/ConcatUnet.lua: every ConcatUnet / MapTable(JoinTable) pair is
+    folded into the segment list (up to 6 segments) of the consuming multigrid convolutions; 2x2 stride-2
+    up-convolutions; 10 sigmoid output maps + BCE"""
+    torch.manual_seed(6)
+    rng = np.random.default_rng(9)
+    om = OB.mnist_unmg(10).double()
+    pm = B.mnist_unmg.createModel(B.Opt(nGPU=1, dataset="mnist-seg"))
+    pm.precision = precision
+    olist = [m for m in om.modules() if isinstance(m, (torch.nn.Conv2d, torch.nn.ConvTranspose2d, torch.nn.BatchNorm2d))]
+    plist = [m for m in pm.listModules() if m.own_parameters()]
+    assert len(olist) == len(plist)
+    with torch.no_grad():
+        for o, p in zip(olist, plist):
+            assert tuple(o.weight.shape) == tuple(p.weight.shape), (type(o).__name__, p.typename)
+            if precision == "bf16" and not isinstance(o, torch.nn.BatchNorm2d):
+                o.weight.copy_(o.weight.to(torch.bfloat16).to(o.weight.dtype))
+            p.weight.copy_(o.weight); p.bias.copy_(o.bias)
+    if precision == "bf16":
+        emulate_bf16_storage(om)
+        for m in om.modules():
+            if isinstance(m, torch.nn.ConvTranspose2d):
+                m.register_forward_hook(lambda _m, _i, o: o.to(torch.bfloat16).to(o.dtype))
+    pm.cuda()
+    plist = [m for m in pm.listModules() if m.own_parameters()]
+    x = bf16_round(rng.standard_normal((4, 1, 64, 64)))
+    t = (rng.random((4, 10, 64, 64)) < 0.1).astype(np.float64)
+    op = om(_t(x))
+    oloss = torch.nn.functional.binary_cross_entropy(op, _t(t))
+    oloss.backward()
+    crit = B.mnist_unmg.createCriterion()
+    out, err = B.mnist_unmg.ftrain(_t(x).float().cuda(), _t(t).float().cuda(), pm, crit)
+    torch.cuda.synchronize()
+    tol = TOL[precision]
+    e = rel_err(out.cpu().numpy(), op.detach().numpy())
+    assert e <= tol, ("probabilities", e)
+    assert abs(float(err) - oloss.item()) <= tol * max(1.0, abs(oloss.item()))
+    og = np.concatenate([(o.weight.grad if o.weight.grad is not None else torch.zeros_like(o.weight)).numpy().ravel() for o in olist])
+    pg = np.concatenate([p.gradWeight.cpu().numpy().ravel() for p in plist])
+    e = rel_err(pg, og)
+    assert e <= (2e-2 if precision == "fp32" else 0.3), ("parameter gradients", e)   # wiring check, see module docstring
+    assert pm._engine.ctx.launches() > 0
+
+
 def test_train_steps_follow_the_oracle():
     """three ftrain + btrain steps (optim.sgd momentum .9, wd 5e-4; models/basic_model.lua:56-66)"""
     torch.manual_seed(3)
