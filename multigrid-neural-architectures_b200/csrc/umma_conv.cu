@@ -21,6 +21,7 @@
 #include "conv_view.cuh"
 #include "umma_common.cuh"
 #include <algorithm>
+#include <vector>
 
 namespace {
 
@@ -57,6 +58,7 @@ struct UParams {
   int n_chunks;      // ceil(kv_per_tap / 8)
   int halo_bytes;    // HL * 128 rounded up to 1024
   int n_abuf;        // halo buffers (1 or 2)
+  long long* timeline;   // debug (MGCONV_TIMELINE=1): per-CTA clock stamps [grid][8], else null
 };
 
 // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M=128
@@ -317,8 +319,11 @@ __global__ void __launch_bounds__(H_THREADS, 2) umma_conv_halo_kernel(const __gr
   __shared__ uint32_t s_pix[HALO_MAX_SLOTS];   // full-resolution pixel index of a halo slot, 0xFFFFFFFF = padding / outside
   __shared__ uint32_t s_pup[HALO_MAX_SLOTS];   // half-resolution pixel index (UP segments)
   __shared__ USeg s_seg[MG_MAX_SEG];
+  __shared__ float s_bias[256];                // bias of this column tile (zero beyond Cout): no global loads in the epilogue
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long* tl = p.timeline ? p.timeline + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
+  if (tl && tid == 0) { tl[0] = clock64(); unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); tl[7] = sm; }
   const int S = p.stages;
   const int b_stage_bytes = p.n_tile * 128;
   uint8_t* a_smem = smem;                               // two halo buffers
@@ -328,6 +333,10 @@ __global__ void __launch_bounds__(H_THREADS, 2) umma_conv_halo_kernel(const __gr
   const int KK = 9;
 
   if (tid < p.n_seg) s_seg[tid] = p.seg[tid];
+  if (tid < p.n_tile) {
+    const int ch = blockIdx.y * p.n_tile + tid;
+    s_bias[tid] = (p.bias && ch < p.c_bias) ? p.bias[ch] : 0.f;
+  }
   {
     const int slots_per_img = p.Hp * p.Wp;
     const int Hs2 = p.H >> 1, Ws2 = p.W >> 1;
@@ -360,6 +369,7 @@ __global__ void __launch_bounds__(H_THREADS, 2) umma_conv_halo_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  if (tl && tid == 0) tl[1] = clock64();
 
   if (warp < H_MMA_WARP) {
     // ================= A producers: one halo per 64-channel chunk ===============================
@@ -397,6 +407,7 @@ __global__ void __launch_bounds__(H_THREADS, 2) umma_conv_halo_kernel(const __gr
     if (warp < 4) {
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
+    if (tl && tid == 0) tl[3] = clock64();
     const int row = warp * 32 + lane;
     const uint32_t pix = s_pix[row + p.Wp + 1];          // slot t0 + row
     const bool row_ok = pix != 0xFFFFFFFFu;
@@ -414,11 +425,8 @@ __global__ void __launch_bounds__(H_THREADS, 2) umma_conv_halo_kernel(const __gr
             uint32_t pk[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float a = __uint_as_float(acc[h * 8 + 2 * e]), b = __uint_as_float(acc[h * 8 + 2 * e + 1]);
-              if (p.bias) {
-                if (n0 + 2 * e < p.c_bias) a += __ldg(p.bias + n0 + 2 * e);
-                if (n0 + 2 * e + 1 < p.c_bias) b += __ldg(p.bias + n0 + 2 * e + 1);
-              }
+              const float a = __uint_as_float(acc[h * 8 + 2 * e]) + s_bias[c0 + h * 8 + 2 * e];
+              const float b = __uint_as_float(acc[h * 8 + 2 * e + 1]) + s_bias[c0 + h * 8 + 2 * e + 1];
               __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
               pk[e] = *reinterpret_cast<uint32_t*>(&t);
             }
@@ -428,6 +436,7 @@ __global__ void __launch_bounds__(H_THREADS, 2) umma_conv_halo_kernel(const __gr
       }
     }
     tc_fence_before();
+    if (tl && tid == 0) tl[4] = clock64();
     }
   } else if (warp == H_B_WARP) {
     // ================= B loader: one bulk copy per (chunk, tap) stage ============================
@@ -450,6 +459,7 @@ __global__ void __launch_bounds__(H_THREADS, 2) umma_conv_halo_kernel(const __gr
         const int buf = c % p.n_abuf;
         mbar_wait(&a_full[buf], (c / p.n_abuf) & 1);
         tc_fence_after();
+        if (tl && c == 0) tl[2] = clock64();
         const uint32_t a_base = smem_u32(a_smem + (size_t)buf * p.halo_bytes);
         const int kv_here = min(KV_PER_STAGE, p.kv_per_tap - c * KV_PER_STAGE);
         const int ksteps = (kv_here + 1) >> 1;
@@ -644,6 +654,26 @@ static int launch_halo(mg_ctx* ctx, UParams& p, const Geometry& g) {
   }
   const int smem = p.n_abuf * p.halo_bytes + S * b_stage + 1024;
   dim3 grid((unsigned)mg_cdiv(p.T, BM), (unsigned)g.n_tiles);
+  static int want_tl = -1;
+  if (want_tl < 0) { const char* e = getenv("MGCONV_TIMELINE"); want_tl = e ? atoi(e) : 0; }
+  p.timeline = nullptr;
+  if (want_tl) {   // debug: dump per-CTA phase stamps of this launch to $MGCONV_TIMELINE_FILE after it ran
+    static long long* d_tl = nullptr; static size_t cap = 0;
+    const size_t need = (size_t)grid.x * grid.y * 8;
+    if (cap < need) { if (d_tl) cudaFree(d_tl); cudaMalloc(&d_tl, need * sizeof(long long)); cap = need; }
+    cudaMemsetAsync(d_tl, 0, need * sizeof(long long), ctx->stream);
+    p.timeline = d_tl;
+    umma_conv_halo_kernel<<<grid, H_THREADS, smem, ctx->stream>>>(p);
+    cudaStreamSynchronize(ctx->stream);
+    std::vector<long long> h(need);
+    cudaMemcpy(h.data(), d_tl, need * sizeof(long long), cudaMemcpyDeviceToHost);
+    const char* fn = getenv("MGCONV_TIMELINE_FILE");
+    FILE* f = fopen(fn ? fn : "timeline.csv", "w");
+    if (f) { for (size_t i = 0; i < need / 8; ++i) fprintf(f, "%lld,%lld,%lld,%lld,%lld,%lld\n", h[i*8], h[i*8+1], h[i*8+2], h[i*8+3], h[i*8+4], h[i*8+7]); fclose(f); }
+    MG_CHECK_LAUNCH(ctx);
+    ctx->tc_launches++;
+    return MG_OK;
+  }
   umma_conv_halo_kernel<<<grid, H_THREADS, smem, ctx->stream>>>(p);
   MG_CHECK_LAUNCH(ctx);
   ctx->tc_launches++;
