@@ -139,3 +139,27 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// A kernel launched with mg_launch_pdl may become resident while its predecessor in the stream is still
+// draining; it must execute pdl_wait() before touching anything the predecessor wrote.  pdl_launch() (first
+// statement of every such kernel) lets the NEXT kernel start its launch once all CTAs of this grid started.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+static inline bool mg_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("MGCONV_PDL"); on = e ? atoi(e) : 1; }
+  return on != 0;
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t mg_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = mg_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}

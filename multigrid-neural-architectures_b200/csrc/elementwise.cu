@@ -46,6 +46,8 @@ __global__ void export_nchw_kernel(GridV<T> g, float* __restrict__ dst) {
 __global__ void bn_finalize_kernel(const double* sums, int64_t count, int C, int Cp, const float* gamma,
                                    const float* beta, float* rmean, float* rvar, float eps, float momentum,
                                    int training, float* scale, float* shift, float* smean, float* sinvstd) {
+  pdl_launch();
+  pdl_wait();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= Cp) return;
   if (c >= C) { scale[c] = 0.f; shift[c] = 0.f; if (smean) { smean[c] = 0.f; sinvstd[c] = 0.f; } return; }
@@ -313,6 +315,8 @@ __global__ void __launch_bounds__(256) combine_kernel(CombineP<T> p) {
 __global__ void bn_bwd_coef_kernel(const double* sums, int64_t count, int C, int Cp, const float* gamma,
                                    const float* mean, const float* invstd, float* dgamma, float* dbeta,
                                    float gscale, float* coef) {
+  pdl_launch();
+  pdl_wait();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= Cp) return;
   if (c >= C) { coef[c] = 0.f; coef[Cp + c] = 0.f; coef[2 * Cp + c] = 0.f; return; }
@@ -435,9 +439,8 @@ int mg_bn_finalize(mg_ctx* ctx, const double* bn_sums, int64_t count, int32_t C,
   if (!ctx || !scale || !shift) return MG_ERR_INVALID_ARG;
   MG_REQUIRE(ctx, training ? bn_sums != nullptr : (running_mean && running_var), MG_ERR_INVALID_ARG,
              "bn_finalize: missing statistics");
-  bn_finalize_kernel<<<(unsigned)mg_cdiv(Cp, 128), 128, 0, ctx->stream>>>(bn_sums, count, C, Cp, gamma, beta, running_mean,
-                                                                 running_var, eps, momentum, training, scale, shift,
-                                                                 save_mean, save_invstd);
+  mg_launch_pdl(bn_finalize_kernel, dim3((unsigned)mg_cdiv(Cp, 128)), dim3(128), 0, ctx->stream, bn_sums, count, (int)C, (int)Cp, gamma, beta,
+                running_mean, running_var, eps, momentum, training, scale, shift, save_mean, save_invstd);
   MG_CHECK_LAUNCH(ctx);
   return MG_OK;
 }
@@ -586,8 +589,8 @@ int mg_bn_backward(mg_ctx* ctx, const mg_grid* xraw, const mg_grid* d, mg_grid* 
   if (!ctx || !xraw || !d || !out || !bn_sums || !save_mean || !save_invstd || !coef_ws) return MG_ERR_INVALID_ARG;
   MG_REQUIRE(ctx, d->N == xraw->N && d->H == xraw->H && d->W == xraw->W && d->C == xraw->C, MG_ERR_SHAPE, "bn_backward: shape");
   MG_REQUIRE(ctx, out->N == d->N && out->H == d->H && out->W == d->W && out->C == d->C, MG_ERR_SHAPE, "bn_backward: out shape");
-  bn_bwd_coef_kernel<<<(unsigned)mg_cdiv(d->Cp, 128), 128, 0, ctx->stream>>>(bn_sums, count, d->C, d->Cp, gamma, save_mean, save_invstd,
-                                                                   dgamma, dbeta, gscale, coef_ws);
+  mg_launch_pdl(bn_bwd_coef_kernel, dim3((unsigned)mg_cdiv(d->Cp, 128)), dim3(128), 0, ctx->stream, bn_sums, count, (int)d->C, (int)d->Cp, gamma,
+                save_mean, save_invstd, dgamma, dbeta, gscale, coef_ws);
   MG_CHECK_LAUNCH(ctx);
   if (ctx->dtype == MG_BF16 && bf16_bn_bwd_apply(ctx, xraw, d, out, coef_ws, conv_dbias, gscale)) { MG_CHECK_LAUNCH(ctx); return MG_OK; }
   int64_t P = (int64_t)d->N * d->H * d->W;

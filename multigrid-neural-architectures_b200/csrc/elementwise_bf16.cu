@@ -71,6 +71,8 @@ struct ApplyP {
 };
 
 __global__ void __launch_bounds__(256) apply_bf16_kernel(ApplyP p) {
+  pdl_launch();
+  pdl_wait();
   const int V = p.o_cp >> 3;
   const int64_t total = (int64_t)p.N * p.Hp * p.Wp * V;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -125,6 +127,8 @@ __global__ void __launch_bounds__(256) apply_bf16_kernel(ApplyP p) {
 
 // ---------------------------------------------------------------- BN statistics ----------
 __global__ void __launch_bounds__(256) bn_stats_bf16_kernel(const bf16* __restrict__ y, int cp, int C, int64_t P, double* sums) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ float sh[];
   const int V = cp >> 3;
   for (int c = threadIdx.x; c < 2 * V * 8; c += blockDim.x) sh[c] = 0.f;
@@ -171,6 +175,8 @@ struct CombP {
 };
 
 __global__ void __launch_bounds__(256, 3) combine_bf16_kernel(CombP p) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ float sh[];
   const int V = p.d_cp >> 3;
   if (p.sums) {
@@ -300,6 +306,8 @@ __global__ void __launch_bounds__(256, 3) combine_bf16_kernel(CombP p) {
 __global__ void __launch_bounds__(256) bn_bwd_apply_bf16_kernel(const bf16* __restrict__ xraw, int x_cp, const bf16* d, int d_cp, bf16* out,
                                                                 int o_cp, int C, int64_t P, const float* __restrict__ coef,
                                                                 float* dbias, float gscale) {
+  pdl_launch();
+  pdl_wait();
   extern __shared__ float sh[];
   const int V = o_cp >> 3;
   if (dbias) {
@@ -452,7 +460,7 @@ bool bf16_apply(mg_ctx* ctx, const mg_grid* z, const mg_grid* s, int relu, mg_gr
   p.pooled = pooled ? (bf16*)pooled->data : nullptr; p.p_cp = pooled ? pooled->Cp : 0;
   p.N = z->N; p.H = z->H; p.W = z->W; p.C = z->C; p.Hp = (z->H + 1) / 2; p.Wp = (z->W + 1) / 2;
   const int64_t total = (int64_t)p.N * p.Hp * p.Wp * (p.o_cp / 8);
-  apply_bf16_kernel<<<grid_for(total), 256, 0, ctx->stream>>>(p);
+  mg_launch_pdl(apply_bf16_kernel, dim3(grid_for(total)), dim3(256), 0, ctx->stream, p);
   return true;
 }
 
@@ -460,7 +468,7 @@ bool bf16_bn_stats(mg_ctx* ctx, const mg_grid* y, double* sums) {
   if (y->Cp % 8 || y->Cp > 4096) return false;
   const int64_t P = (int64_t)y->N * y->H * y->W;
   const int V = y->Cp / 8;
-  bn_stats_bf16_kernel<<<reduce_grid(ctx, P * V / 4), 256, 2 * V * 8 * sizeof(float), ctx->stream>>>((const bf16*)y->data, y->Cp, y->C, P, sums);
+  mg_launch_pdl(bn_stats_bf16_kernel, dim3(reduce_grid(ctx, P * V / 4)), dim3(256), 2 * V * 8 * sizeof(float), ctx->stream, (const bf16*)y->data, y->Cp, y->C, P, sums);
   return true;
 }
 
@@ -486,7 +494,7 @@ bool bf16_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid* b
   const int V = d->Cp / 8;
   const int64_t items = (int64_t)p.N * p.Hb * p.Wb * V;
   const unsigned grid = reduce_grid(ctx, items, 3);   // 80 registers: three CTAs per SM are resident
-  combine_bf16_kernel<<<grid, 256, 2 * V * 8 * sizeof(float), ctx->stream>>>(p);
+  mg_launch_pdl(combine_bf16_kernel, dim3(grid), dim3(256), 2 * V * 8 * sizeof(float), ctx->stream, p);
   return true;
 }
 
@@ -495,8 +503,8 @@ bool bf16_bn_bwd_apply(mg_ctx* ctx, const mg_grid* xraw, const mg_grid* d, mg_gr
   const int64_t P = (int64_t)d->N * d->H * d->W;
   const int V = out->Cp / 8;
   const unsigned grid = reduce_grid(ctx, P * V, 4);
-  bn_bwd_apply_bf16_kernel<<<grid, 256, V * 8 * sizeof(float), ctx->stream>>>((const bf16*)xraw->data, xraw->Cp, (const bf16*)d->data, d->Cp,
-                                                                              (bf16*)out->data, out->Cp, d->C, P, coef, conv_dbias, gscale);
+  mg_launch_pdl(bn_bwd_apply_bf16_kernel, dim3(grid), dim3(256), V * 8 * sizeof(float), ctx->stream, (const bf16*)xraw->data, xraw->Cp,
+                (const bf16*)d->data, d->Cp, (bf16*)out->data, out->Cp, d->C, P, coef, conv_dbias, gscale);
   return true;
 }
 

@@ -311,6 +311,9 @@ constexpr int H_PROD = 256;                        // 8 loader warps (the first 
 constexpr int H_MMA_WARP = H_PROD / 32, H_B_WARP = H_MMA_WARP + 1;
 constexpr int H_THREADS = H_PROD + 64;
 
+// CL = thread-block cluster size along the tile index: the CL CTAs of a cluster need the same weight stages, so each
+// loads 1/CL of a stage and multicasts it to all of them (L2 -> SM weight traffic / CL)
+template <int CL>
 __global__ void __launch_bounds__(H_THREADS, 2) umma_conv_halo_kernel(const __grid_constant__ UParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -321,6 +324,7 @@ __global__ void __launch_bounds__(H_THREADS, 2) umma_conv_halo_kernel(const __gr
   __shared__ USeg s_seg[MG_MAX_SEG];
   __shared__ float s_bias[256];                // bias of this column tile (zero beyond Cout): no global loads in the epilogue
 
+  pdl_launch();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   long long* tl = p.timeline ? p.timeline + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
   if (tl && tid == 0) { tl[0] = clock64(); unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); tl[7] = sm; }
@@ -333,10 +337,7 @@ __global__ void __launch_bounds__(H_THREADS, 2) umma_conv_halo_kernel(const __gr
   const int KK = 9;
 
   if (tid < p.n_seg) s_seg[tid] = p.seg[tid];
-  if (tid < p.n_tile) {
-    const int ch = blockIdx.y * p.n_tile + tid;
-    s_bias[tid] = (p.bias && ch < p.c_bias) ? p.bias[ch] : 0.f;
-  }
+
   {
     const int slots_per_img = p.Hp * p.Wp;
     const int Hs2 = p.H >> 1, Ws2 = p.W >> 1;
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(H_THREADS, 2) umma_conv_halo_kernel(const __gr
     }
   }
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
     for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], H_PROD); mbar_init(&a_empty[s], 1); }
     mbar_init(&tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -365,8 +366,16 @@ __global__ void __launch_bounds__(H_THREADS, 2) umma_conv_halo_kernel(const __gr
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  // everything above touched only kernel parameters, shared memory and TMEM: it overlapped the tail of the
+  // previous kernel; from here on the predecessor's output (activations, packed weights, bias) is read
+  pdl_wait();
+  if (tid < p.n_tile) {
+    const int ch = blockIdx.y * p.n_tile + tid;
+    s_bias[tid] = (p.bias && ch < p.c_bias) ? p.bias[ch] : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // every CTA's barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   if (tl && tid == 0) tl[1] = clock64();
@@ -443,11 +452,17 @@ __global__ void __launch_bounds__(H_THREADS, 2) umma_conv_halo_kernel(const __gr
     if (lane == 0) {
       const int n_st = p.n_chunks * KK;
       const uint8_t* wsrc = p.wpack + (size_t)ntile * n_st * b_stage_bytes;
+      const uint32_t rank = CL > 1 ? cluster_ctarank() : 0;
+      const uint32_t slice = (uint32_t)b_stage_bytes / CL;   // n_tile * 128 / CL: a multiple of 16 bytes
       for (int ks = 0; ks < n_st; ++ks) {
         const int s = ks % S;
-        if (ks >= S) mbar_wait(&empty_bar[s], ((ks / S) - 1) & 1);
+        if (ks >= S) mbar_wait(&empty_bar[s], ((ks / S) - 1) & 1);   // CL arrivals: every CTA of the cluster freed slot s
         mbar_arrive_expect_tx(&full_bar[s], (uint32_t)b_stage_bytes);
-        bulk_g2s(smem_u32(b_smem + (size_t)s * b_stage_bytes), wsrc + (size_t)ks * b_stage_bytes, (uint32_t)b_stage_bytes, &full_bar[s]);
+        if (CL == 1)
+          bulk_g2s(smem_u32(b_smem + (size_t)s * b_stage_bytes), wsrc + (size_t)ks * b_stage_bytes, (uint32_t)b_stage_bytes, &full_bar[s]);
+        else
+          bulk_g2s_mcast(smem_u32(b_smem + (size_t)s * b_stage_bytes) + rank * slice, wsrc + (size_t)ks * b_stage_bytes + rank * slice, slice,
+                         &full_bar[s], (uint16_t)((1u << CL) - 1));
       }
     }
   } else {
@@ -455,30 +470,37 @@ __global__ void __launch_bounds__(H_THREADS, 2) umma_conv_halo_kernel(const __gr
     if (lane == 0) {
       const uint32_t idesc = idesc_bf16_m128(p.n_tile);
       int ks = 0;
+      long long wait_a = 0, wait_b = 0, tq = 0;
       for (int c = 0; c < p.n_chunks; ++c) {
         const int buf = c % p.n_abuf;
+        if (tl) tq = clock64();
         mbar_wait(&a_full[buf], (c / p.n_abuf) & 1);
         tc_fence_after();
         if (tl && c == 0) tl[2] = clock64();
+        if (tl && c > 0) wait_a += clock64() - tq;
         const uint32_t a_base = smem_u32(a_smem + (size_t)buf * p.halo_bytes);
         const int kv_here = min(KV_PER_STAGE, p.kv_per_tap - c * KV_PER_STAGE);
         const int ksteps = (kv_here + 1) >> 1;
         for (int tap = 0; tap < KK; ++tap, ++ks) {
           const int s = ks % S;
+          if (tl) tq = clock64();
           mbar_wait(&full_bar[s], (ks / S) & 1);
           tc_fence_after();
+          if (tl) wait_b += clock64() - tq;
           const uint32_t a_addr = a_base + (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 128u;
           const uint32_t b_addr = smem_u32(b_smem + (size_t)s * b_stage_bytes);
           for (int q = 0; q < ksteps; ++q)
             tc_mma_bf16(tmem_base, smem_desc_k_sw128(a_addr + q * 32), smem_desc_k_sw128(b_addr + q * 32), idesc, (ks | q) != 0);
-          tc_commit(&empty_bar[s]);
+          if (CL == 1) tc_commit(&empty_bar[s]); else tc_commit_mcast(&empty_bar[s], (uint16_t)((1u << CL) - 1));
         }
         tc_commit(&a_empty[buf]);   // halo buffer free once this chunk's MMAs have read it
       }
       tc_commit(&tmem_full_bar);
+      if (tl) { tl[5] = wait_a; tl[6] = wait_b; }
     }
   }
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == H_MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
@@ -500,6 +522,8 @@ struct PackParams {
 
 // one thread per (n row, k-vector): writes 16 bytes of the swizzled stage image
 __global__ void pack_weights_kernel(PackParams p) {
+  pdl_launch();
+  pdl_wait();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int kv_total = p.n_stages * KV_PER_STAGE;
   const int64_t total = (int64_t)p.n_tiles * p.n_tile * kv_total;
@@ -649,11 +673,18 @@ static int launch_halo(mg_ctx* ctx, UParams& p, const Geometry& g) {
   p.tmem_cols = cols;
   static bool attr_set = false;
   if (!attr_set) {
-    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8 * 1024));
+    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8 * 1024));
+    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8 * 1024));
+    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8 * 1024));
     attr_set = true;
   }
+  static int cl_env = -1;
+  if (cl_env < 0) { const char* e = getenv("MGCONV_CLUSTER"); cl_env = e ? atoi(e) : 1;   // measured: multicast clusters couple the CTAs and lose 5-10 % (weights are not the bottleneck) }
+  int CL = cl_env;
+  if ((p.n_tile * 128 / 16) % CL != 0 || CL < 1) CL = 1;          // each slice must be whole 16-byte units
+  if (CL != 1 && CL != 2 && CL != 4) CL = 1;
   const int smem = p.n_abuf * p.halo_bytes + S * b_stage + 1024;
-  dim3 grid((unsigned)mg_cdiv(p.T, BM), (unsigned)g.n_tiles);
+  dim3 grid((unsigned)mg_round_up((int)mg_cdiv(p.T, BM), CL), (unsigned)g.n_tiles);   // padding CTAs see only invalid slots
   static int want_tl = -1;
   if (want_tl < 0) { const char* e = getenv("MGCONV_TIMELINE"); want_tl = e ? atoi(e) : 0; }
   p.timeline = nullptr;
@@ -663,18 +694,30 @@ static int launch_halo(mg_ctx* ctx, UParams& p, const Geometry& g) {
     if (cap < need) { if (d_tl) cudaFree(d_tl); cudaMalloc(&d_tl, need * sizeof(long long)); cap = need; }
     cudaMemsetAsync(d_tl, 0, need * sizeof(long long), ctx->stream);
     p.timeline = d_tl;
-    umma_conv_halo_kernel<<<grid, H_THREADS, smem, ctx->stream>>>(p);
+    umma_conv_halo_kernel<1><<<grid, H_THREADS, smem, ctx->stream>>>(p);
     cudaStreamSynchronize(ctx->stream);
     std::vector<long long> h(need);
     cudaMemcpy(h.data(), d_tl, need * sizeof(long long), cudaMemcpyDeviceToHost);
     const char* fn = getenv("MGCONV_TIMELINE_FILE");
     FILE* f = fopen(fn ? fn : "timeline.csv", "w");
-    if (f) { for (size_t i = 0; i < need / 8; ++i) fprintf(f, "%lld,%lld,%lld,%lld,%lld,%lld\n", h[i*8], h[i*8+1], h[i*8+2], h[i*8+3], h[i*8+4], h[i*8+7]); fclose(f); }
+    if (f) { for (size_t i = 0; i < need / 8; ++i) fprintf(f, "%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld\n", h[i*8], h[i*8+1], h[i*8+2], h[i*8+3], h[i*8+4], h[i*8+7], h[i*8+5], h[i*8+6]); fclose(f); }
     MG_CHECK_LAUNCH(ctx);
     ctx->tc_launches++;
     return MG_OK;
   }
-  umma_conv_halo_kernel<<<grid, H_THREADS, smem, ctx->stream>>>(p);
+  if (CL == 1) {
+    MG_CUDA(ctx, mg_launch_pdl(umma_conv_halo_kernel<1>, grid, dim3(H_THREADS), (size_t)smem, ctx->stream, p));
+  } else {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = dim3(H_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    if (CL == 2) MG_CUDA(ctx, cudaLaunchKernelEx(&cfg, umma_conv_halo_kernel<2>, p));
+    else MG_CUDA(ctx, cudaLaunchKernelEx(&cfg, umma_conv_halo_kernel<4>, p));
+  }
   MG_CHECK_LAUNCH(ctx);
   ctx->tc_launches++;
   return MG_OK;
@@ -723,7 +766,7 @@ int umma_pack_weights(mg_ctx* ctx, const mg_conv_desc* d, const float* w, void* 
   p.kv_per_tap = g.kv_per_tap; p.nkv = g.nkv; p.n_stages = g.n_stages; p.n_tile = g.n_tile; p.n_tiles = g.n_tiles;
   p.n_rows_valid = g.n_rows; p.halo = g.halo;
   const int64_t total = (int64_t)g.n_tiles * g.n_tile * g.n_stages * KV_PER_STAGE;
-  pack_weights_kernel<<<(unsigned)mg_cdiv(total, 256), 256, 0, ctx->stream>>>(p);
+  mg_launch_pdl(pack_weights_kernel, dim3((unsigned)mg_cdiv(total, 256)), dim3(256), 0, ctx->stream, p);
   MG_CHECK_LAUNCH(ctx);
   return MG_OK;
 }

@@ -226,6 +226,7 @@ struct WHParams {
 };
 
 __global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __grid_constant__ WHParams p) {
+  pdl_launch();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t full_bar[W_MAX_STAGES], empty_bar[W_MAX_STAGES], tmem_full_bar;
@@ -251,6 +252,7 @@ __global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  pdl_wait();   // the prologue above overlapped the previous kernel's tail; g and the activations are read below
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -385,6 +387,8 @@ __global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __
 // dw[co][ci][tap] += gscale * sum_z partial[z][tap][co][ci]
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Cout, int Ccat, float* __restrict__ dw,
                                                            float gscale) {
+  pdl_launch();
+  pdl_wait();
   const int64_t plane = (int64_t)9 * Cout * Ccat;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // index in [tap][co][ci] order (coalesced reads)
   if (i >= plane) return;
@@ -473,10 +477,10 @@ static int wgrad_halo(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g, floa
   if (rc) return rc;
   p.partial = (float*)ws;
   dim3 grid((unsigned)n_chunks, (unsigned)n_tiles, (unsigned)z);
-  umma_wgrad_halo_kernel<<<grid, WH_THREADS, S * stage_bytes + 1024, ctx->stream>>>(p);
+  MG_CUDA(ctx, mg_launch_pdl(umma_wgrad_halo_kernel, grid, dim3(WH_THREADS), (size_t)(S * stage_bytes + 1024), ctx->stream, p));
   MG_CHECK_LAUNCH(ctx);
   ctx->tc_launches++;
-  wgrad_reduce_kernel<<<(unsigned)mg_cdiv((int64_t)plane, 256), 256, 0, ctx->stream>>>(p.partial, z, p.Cout, p.Ccat, dw, gscale);
+  MG_CUDA(ctx, mg_launch_pdl(wgrad_reduce_kernel, dim3((unsigned)mg_cdiv((int64_t)plane, 256)), dim3(256), 0, ctx->stream, (const float*)p.partial, z, p.Cout, p.Ccat, dw, gscale));
   MG_CHECK_LAUNCH(ctx);
   return MG_OK;
 }
