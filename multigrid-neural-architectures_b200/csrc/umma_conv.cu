@@ -679,7 +679,8 @@ static int launch_halo(mg_ctx* ctx, UParams& p, const Geometry& g) {
     attr_set = true;
   }
   static int cl_env = -1;
-  if (cl_env < 0) { const char* e = getenv("MGCONV_CLUSTER"); cl_env = e ? atoi(e) : 1;   // measured: multicast clusters couple the CTAs and lose 5-10 % (weights are not the bottleneck) }
+  // measured: multicast clusters couple the CTAs and lose 5-10 % (weights are not the bottleneck): off by default
+  if (cl_env < 0) { const char* e = getenv("MGCONV_CLUSTER"); cl_env = e ? atoi(e) : 1; }
   int CL = cl_env;
   if ((p.n_tile * 128 / 16) % CL != 0 || CL < 1) CL = 1;          // each slice must be whole 16-byte units
   if (CL != 1 && CL != 2 && CL != 4) CL = 1;
