@@ -133,18 +133,19 @@ __global__ void __launch_bounds__(256) bn_stats_bf16_kernel(const bf16* __restri
   const int V = cp >> 3;
   for (int c = threadIdx.x; c < 2 * V * 8; c += blockDim.x) sh[c] = 0.f;
   __syncthreads();
-  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  const int64_t lanes = nthreads / V;          // pixel lanes; threads beyond lanes*V idle
-  const int vc = (int)(gtid % V);
-  const int64_t lane = gtid / V;
+  // each CTA streams ONE contiguous pixel range (DRAM page locality); inside it the threads of a CTA form
+  // `lanes` pixel lanes x V channel vectors and walk the range lane-strided
+  const int lanes = blockDim.x / V;            // threads beyond lanes*V idle
+  const int vc = threadIdx.x % V, lane = threadIdx.x / V;
+  const int64_t per_cta = (P + gridDim.x - 1) / gridDim.x;
+  const int64_t p_begin = (int64_t)blockIdx.x * per_cta, p_end = min(P, p_begin + per_cta);
   float a[8], b[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { a[e] = 0.f; b[e] = 0.f; }
   const bool active = lane < lanes;
   if (active) {
-    int64_t pix = lane;
-    for (; pix + 3 * lanes < P; pix += 4 * lanes) {   // four independent 16-byte loads in flight per thread
+    int64_t pix = p_begin + lane;
+    for (; pix + 3 * lanes < p_end; pix += 4 * lanes) {   // four independent 16-byte loads in flight per thread
       V8 v[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) v[u] = ld8(y + (pix + u * lanes) * cp + vc * 8);
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(256) bn_stats_bf16_kernel(const bf16* __restri
 #pragma unroll
         for (int e = 0; e < 8; ++e) { a[e] += v[u].v[e]; b[e] = fmaf(v[u].v[e], v[u].v[e], b[e]); }
     }
-    for (; pix < P; pix += lanes) {
+    for (; pix < p_end; pix += lanes) {
       const V8 v = ld8(y + pix * cp + vc * 8);
 #pragma unroll
       for (int e = 0; e < 8; ++e) { a[e] += v.v[e]; b[e] = fmaf(v.v[e], v.v[e], b[e]); }
@@ -183,13 +184,12 @@ __global__ void __launch_bounds__(256, 3) combine_bf16_kernel(CombP p) {
     for (int c = threadIdx.x; c < 2 * V * 8; c += blockDim.x) sh[c] = 0.f;
     __syncthreads();
   }
-  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  const int64_t lanes = nthreads / V;
-  const int vc = (int)(gtid % V);
+  const int lanes = blockDim.x / V;
+  const int vc = threadIdx.x % V, lane = threadIdx.x / V;
   const int c0 = vc * 8;
-  const int64_t lane = gtid / V;
   const int64_t nblocks = (int64_t)p.N * p.Hb * p.Wb;
+  const int64_t per_cta = (nblocks + gridDim.x - 1) / gridDim.x;   // contiguous range of 2x2 blocks per CTA
+  const int64_t b_begin = (int64_t)blockIdx.x * per_cta, b_end = min(nblocks, b_begin + per_cta);
   const bool active = lane < lanes;
   float sd[8], sdx[8];
 #pragma unroll
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256, 3) combine_bf16_kernel(CombP p) {
   for (int s = 0; s < p.n_src; ++s) need_x = need_x || p.src[s].mode == MG_SEG_POOL;
 
   if (active)
-    for (int64_t blk = lane; blk < nblocks; blk += lanes) {
+    for (int64_t blk = b_begin + lane; blk < b_end; blk += lanes) {
       const int bx = (int)(blk % p.Wb); int64_t q = blk / p.Wb;
       const int by = (int)(q % p.Hb); const int n = (int)(q / p.Hb);
       const int y0 = 2 * by, x0 = 2 * bx;
@@ -314,29 +314,29 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_bf16_kernel(const bf16* __re
     for (int c = threadIdx.x; c < V * 8; c += blockDim.x) sh[c] = 0.f;
     __syncthreads();
   }
-  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t lanes = ((int64_t)gridDim.x * blockDim.x) / V;
-  const int vc = (int)(gtid % V);
-  const int64_t lane = gtid / V;
+  const int lanes = blockDim.x / V;
+  const int vc = threadIdx.x % V, lane = threadIdx.x / V;
   const int c0 = vc * 8;
   const bool active = lane < lanes;
+  const int64_t per_cta = (P + gridDim.x - 1) / gridDim.x;      // contiguous pixel range per CTA
+  const int64_t p_begin = (int64_t)blockIdx.x * per_cta, p_end = min(P, p_begin + per_cta);
   float sb[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) sb[e] = 0.f;
   if (active) {
     float A[8], B[8], Cc[8];
     ldf8(coef + c0, A); ldf8(coef + d_cp + c0, B); ldf8(coef + 2 * d_cp + c0, Cc);
-    for (int64_t pix0 = lane; pix0 < P; pix0 += 4 * lanes) {
+    for (int64_t pix0 = p_begin + lane; pix0 < p_end; pix0 += 4 * lanes) {
       V8 dv[4], xv[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {   // eight independent 16-byte loads in flight per thread
         const int64_t pix = pix0 + u * lanes;
-        if (pix < P) { dv[u] = ld8(d + pix * d_cp + c0); xv[u] = ld8(xraw + pix * x_cp + c0); }
+        if (pix < p_end) { dv[u] = ld8(d + pix * d_cp + c0); xv[u] = ld8(xraw + pix * x_cp + c0); }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int64_t pix = pix0 + u * lanes;
-        if (pix < P) {
+        if (pix < p_end) {
           V8 o;
 #pragma unroll
           for (int e = 0; e < 8; ++e) o.v[e] = (c0 + e < C) ? fmaf(A[e], dv[u].v[e], fmaf(B[e], xv[u].v[e], Cc[e])) : 0.f;

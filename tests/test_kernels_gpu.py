@@ -189,6 +189,77 @@ def test_mgconv_forward_dgrad_wgrad(ctx, case, impl):
     ctx.set_impl(ffi.MG_IMPL_AUTO)
 
 
+EDGE_CASES = [  # N, [(C, mode 's'|'u')], H, W, Cout, k -- shapes that take the less-travelled paths
+    (1, [(8, "s")], 1, 1, 16, 3),                 # 1x1 grid: only the centre tap is ever in bounds (CIFAR coarsest grid)
+    (2, [(24, "s"), (8, "u")], 6, 10, 520, 3),    # non-square, Cout > 256 -> several N tiles, rows spanning images
+    (1, [(16, "s")], 5, 70, 8, 3),                # W > 63: per-tap tcgen05 kernels instead of the halo kernels
+    (3, [(3, "s")], 9, 7, 40, 3),                 # Cin = 3 (Cp = 8, five zero channels), odd sizes
+    (2, [(72, "s"), (40, "s"), (16, "u")], 4, 4, 24, 1),   # 1x1 kernel over three segments (CIFAR last blocks)
+    (5, [(200, "s")], 3, 3, 96, 3),               # K spanning several 64-channel chunks with a ragged last chunk
+]
+
+
+@pytest.mark.parametrize("case", EDGE_CASES, ids=[f"case{i}" for i in range(len(EDGE_CASES))])
+def test_conv_edge_shapes_tcgen05(case):
+    """forward / dgrad / wgrad of the bf16 tensor-core path on ragged, tiny, wide and multi-tile shapes"""
+    ctx = ffi.Context(0, torch.cuda.current_stream().cuda_stream, ffi.MG_BF16)
+    N, segs, H, W, Cout, k = case
+    pad = 0 if k == 1 else 1
+    xs, grids, modes = [], [], []
+    for c, m in segs:
+        h, w = (H // 2, W // 2) if m == "u" else (H, W)
+        x = rnd(N, c, h, w)
+        xs.append(O.upsample_forward(x) if m == "u" else x)
+        grids.append(Grid(ffi.MG_BF16, N, c, h, w, x)); modes.append(MG_SEG_UP if m == "u" else MG_SEG_SAME)
+    cat = np.concatenate(xs, axis=1)
+    wgt = bf16_round(rng.standard_normal((Cout, cat.shape[1], k, k)) * 0.1)
+    b = bf16_round(rng.standard_normal(Cout) * 0.1)
+    d = conv_desc(grids, modes, k, 1, pad, Cout, H, W)
+    wd, bd = dev(wgt), dev(b)
+    wp = torch.zeros(ffi.lib.mg_conv_packed_bytes(C.byref(d), 0), dtype=torch.uint8, device="cuda")
+    wpt = torch.zeros(ffi.lib.mg_conv_packed_bytes(C.byref(d), 1), dtype=torch.uint8, device="cuda")
+    ctx.call("mg_conv_pack_weights", C.byref(d), ptr(wd), ptr(wp), 0)
+    ctx.call("mg_conv_pack_weights", C.byref(d), ptr(wd), ptr(wpt), 1)
+    gy = Grid(ffi.MG_BF16, N, Cout, H, W)
+    sums = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
+    tc0 = ctx.tc_launches()
+    ctx.call("mg_conv_forward", C.byref(d), ptr(wd), ptr(wp), ptr(bd), C.byref(gy.g()), ptr(sums))
+    y_ref = O.conv_forward(cat, wgt, b, 1, pad)
+    tol = TOL[ffi.MG_BF16]
+    assert max_rel(gy.nchw(), y_ref) <= tol
+    assert not gy.pad_channels().any()
+    assert np.allclose(sums.cpu().numpy()[:Cout] / (N * H * W), y_ref.mean(axis=(0, 2, 3)), atol=tol * np.abs(y_ref).max())
+    g = rnd(N, Cout, H, W)
+    gcat_ref, gw_ref, gb_ref = O.conv_backward(cat, wgt, g, 1, pad)
+    gg = Grid(ffi.MG_BF16, N, Cout, H, W, g)
+    cps = [x.Cp for x in grids]
+    dcat = Grid(ffi.MG_BF16, N, sum(cps), H, W, Cp=sum(cps))
+    ctx.call("mg_conv_backward_data", C.byref(d), ptr(wd), ptr(wpt), C.byref(gg.g()), C.byref(dcat.g()))
+    dc, off, lo = dcat.nchw(), 0, 0
+    for (c, m), cp in zip(segs, cps):   # dcat is laid out at padded channel offsets, at the conv's own resolution
+        assert max_rel(dc[:, off:off + c], gcat_ref[:, lo:lo + c]) <= tol, ("dgrad segment", c, m)
+        assert not np.abs(dc[:, off + c:off + cp]).any()
+        off += cp; lo += c
+    dw, db = torch.zeros_like(wd), torch.zeros_like(bd)
+    ctx.call("mg_conv_backward_weight", C.byref(d), C.byref(gg.g()), ptr(dw), ptr(db), 1.0)
+    assert ctx.tc_launches() - tc0 == 3, "all three passes must run on tcgen05 kernels"
+    torch.cuda.synchronize()
+    assert max_rel(dw.cpu().numpy(), gw_ref) <= tol and max_rel(db.cpu().numpy(), gb_ref) <= tol
+    ctx.close()
+
+
+def test_null_and_mismatched_arguments_return_status(ctx):
+    """error convention: status + message, never a crash"""
+    g = Grid(ctx.dtype, 1, 4, 4, 4)
+    o = Grid(ctx.dtype, 1, 4, 3, 3)   # wrong pooled size
+    with pytest.raises(ffi.MGError, match="pool"):
+        ctx.call("mg_pool_forward", C.byref(g.g()), C.byref(o.g()), 0, None)
+    assert ffi.lib.mg_pool_forward(ctx.h, None, None, 0, None) == 1      # MG_ERR_INVALID_ARG
+    assert ffi.lib.mg_conv_forward(None, None, None, None, None, None, None) == 1
+    with pytest.raises(ffi.MGError, match="communicator not initialised"):
+        ctx.call("mg_allreduce_launch", ptr(g.t), 16, 0)
+
+
 @pytest.mark.parametrize("impl", ["simt", "auto"])
 def test_stem_conv7x7_stride2(ctx, impl):
     """cudnn.SpatialConvolution(3, nOP, 7,7, 2,2, 3,3) of the ImageNet stem (ilsvrc/rnmg.lua:180)"""
