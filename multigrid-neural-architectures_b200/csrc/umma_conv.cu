@@ -59,6 +59,8 @@ struct UParams {
   int halo_bytes;    // HL * 128 rounded up to 1024
   int n_abuf;        // halo buffers (1 or 2)
   long long* timeline;   // debug (MGCONV_TIMELINE=1): per-CTA clock stamps [grid][8], else null
+  // persistent halo kernel
+  int m_tiles, n_ntiles, n_items;   // slot tiles, column tiles, work items = m_tiles * n_ntiles
 };
 
 // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M=128
@@ -398,11 +400,25 @@ __global__ void __launch_bounds__(H_THREADS, 2) umma_conv_halo_kernel(const __gr
         const char* base = reinterpret_cast<const char*>(sgm.ptr) + (r - sgm.kv_begin) * 16;
         const uint32_t* tab = sgm.shift ? s_pup : s_pix;
         const uint32_t dst0 = smem_u32(a_smem + (size_t)buf * p.halo_bytes) + (uint32_t)(v << 4);
-        for (int h = rg; h < p.HL; h += H_PROD / 8) {
-          const bool ok = kv_ok && s_pix[h] != 0xFFFFFFFFu;
-          const char* src = ok ? base + (uint64_t)tab[h] * pitch : reinterpret_cast<const char*>(sgm.ptr);
-          // 16-byte chunk v of slot h, swizzled by the slot's absolute 128-byte row (buffers are 1024-aligned)
-          cp_async16((dst0 ^ ((uint32_t)(h & 7) << 4)) + (uint32_t)h * 128, src, ok ? 16u : 0u);
+        // table reads are batched ahead of the copies (the asm copies are ordered, the compiler cannot hoist them)
+        for (int h0 = rg; h0 < p.HL; h0 += 4 * (H_PROD / 8)) {
+          uint32_t pv[4], tv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int h = h0 + u * (H_PROD / 8);
+            pv[u] = h < p.HL ? s_pix[h] : 0xFFFFFFFFu;
+            tv[u] = h < p.HL ? tab[h] : 0u;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int h = h0 + u * (H_PROD / 8);
+            if (h < p.HL) {
+              const bool ok = kv_ok && pv[u] != 0xFFFFFFFFu;
+              const char* src = ok ? base + (uint64_t)tv[u] * pitch : reinterpret_cast<const char*>(sgm.ptr);
+              // 16-byte chunk v of slot h, swizzled by the slot's absolute 128-byte row (buffers are 1024-aligned)
+              cp_async16((dst0 ^ ((uint32_t)(h & 7) << 4)) + (uint32_t)h * 128, src, ok ? 16u : 0u);
+            }
+          }
         }
       }
       cp_async_commit();
@@ -502,6 +518,233 @@ __global__ void __launch_bounds__(H_THREADS, 2) umma_conv_halo_kernel(const __gr
   __syncthreads();
   if (CL > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == H_MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+
+// ---------------------------------------------------------------- persistent halo kernel ----------
+// Same operand scheme as umma_conv_halo_kernel, but one CTA walks a strided list of (slot tile, column tile)
+// work items and its roles run decoupled, so that nothing of a tile's latency chain is exposed:
+//   8 loader warps   stage halos into a ring that runs ACROSS chunks and tiles (the next tile's halo is in
+//                    flight while the tensor core works on the current one),
+//   1 B-loader thread streams the (chunk, tap) weight stages through its own ring,
+//   1 MMA thread     accumulates tile i into TMEM accumulator i & 1,
+//   4 epilogue warps drain accumulator (i-1) & 1 meanwhile (TMEM double buffering).
+constexpr int P_LOAD = 256, P_EPI_WARP0 = 8, P_MMA_WARP = 12, P_B_WARP = 13, P_THREADS = 448;
+constexpr int P_MAX_ABUF = 4;
+
+__global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel(const __grid_constant__ UParams p) {
+  pdl_launch();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], a_full[P_MAX_ABUF], a_empty[P_MAX_ABUF], tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t s_pix[2][HALO_MAX_SLOTS], s_pup[2][HALO_MAX_SLOTS];
+  __shared__ float s_bias[2][256];
+  __shared__ USeg s_seg[MG_MAX_SEG];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int S = p.stages, NA = p.n_abuf;
+  const int b_stage_bytes = p.n_tile * 128;
+  uint8_t* a_smem = smem;
+  uint8_t* b_smem = smem + (size_t)NA * p.halo_bytes;
+  const int KK = 9;
+  const int n_my = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items blockIdx.x, +gridDim.x, ...
+
+  if (tid < p.n_seg) s_seg[tid] = p.seg[tid];
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], P_LOAD); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == P_MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  pdl_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int slots_per_img = p.Hp * p.Wp;
+
+  if (warp < P_EPI_WARP0) {
+    // ================= loaders ====================================================================
+    const int v = tid & 7, rg = tid >> 3;          // k-vector column, slot lane 0..31
+    const int Hs2 = p.H >> 1, Ws2 = p.W >> 1;
+    const int lagA = NA - 1;
+    int ac = 0;                                      // chunks issued so far (ring position)
+    const int total_chunks = n_my * p.n_chunks;
+    for (int it = 0; it < n_my; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int mt = item % p.m_tiles;
+      const int tb = it & 1;
+      const int64_t t0 = (int64_t)mt * BM;
+      for (int h = tid; h < p.HL; h += P_LOAD) {
+        const int64_t t = t0 - p.Wp - 1 + h;
+        uint32_t pix = 0xFFFFFFFFu, pup = 0;
+        if (t >= 0 && t < p.T) {
+          const uint32_t tu = (uint32_t)t;
+          const uint32_t n = tu / (uint32_t)slots_per_img, rem = tu - n * (uint32_t)slots_per_img;
+          const uint32_t yy = rem / (uint32_t)p.Wp, xs = rem - yy * (uint32_t)p.Wp;
+          if ((int)yy < p.H && (int)xs < p.W) {
+            pix = (n * p.H + yy) * p.W + xs;
+            pup = (n * Hs2 + (yy >> 1)) * Ws2 + (xs >> 1);
+          }
+        }
+        s_pix[tb][h] = pix; s_pup[tb][h] = pup;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(P_LOAD) : "memory");
+      for (int c = 0; c < p.n_chunks; ++c, ++ac) {
+        const int buf = ac % NA;
+        if (ac >= NA) mbar_wait(&a_empty[buf], ((ac / NA) - 1) & 1);
+        const int r = c * KV_PER_STAGE + v;
+        const bool kv_ok = r < p.kv_per_tap;
+        int sg = 0;
+        if (kv_ok) while (sg + 1 < p.n_seg && r >= s_seg[sg + 1].kv_begin) ++sg;
+        const USeg sgm = s_seg[sg];
+        const uint32_t pitch = (uint32_t)sgm.Cp * 2u;
+        const char* base = reinterpret_cast<const char*>(sgm.ptr) + (r - sgm.kv_begin) * 16;
+        const uint32_t* tab = sgm.shift ? s_pup[tb] : s_pix[tb];
+        const uint32_t dst0 = smem_u32(a_smem + (size_t)buf * p.halo_bytes) + (uint32_t)(v << 4);
+        for (int h0 = rg; h0 < p.HL; h0 += 4 * (P_LOAD / 8)) {
+          uint32_t pv[4], tv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int h = h0 + u * (P_LOAD / 8);
+            pv[u] = h < p.HL ? s_pix[tb][h] : 0xFFFFFFFFu;
+            tv[u] = h < p.HL ? tab[h] : 0u;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int h = h0 + u * (P_LOAD / 8);
+            if (h < p.HL) {
+              const bool ok = kv_ok && pv[u] != 0xFFFFFFFFu;
+              const char* src = ok ? base + (uint64_t)tv[u] * pitch : reinterpret_cast<const char*>(sgm.ptr);
+              cp_async16((dst0 ^ ((uint32_t)(h & 7) << 4)) + (uint32_t)h * 128, src, ok ? 16u : 0u);
+            }
+          }
+        }
+        cp_async_commit();
+        if (ac >= lagA) {
+          cp_async_wait_dyn(lagA);
+          fence_proxy_async();
+          mbar_arrive(&a_full[(ac - lagA) % NA]);
+        }
+      }
+    }
+    for (int q = max(0, total_chunks - lagA); q < total_chunks; ++q) {   // publish the chunks still in flight
+      cp_async_wait_dyn(total_chunks - 1 - q);
+      fence_proxy_async();
+      mbar_arrive(&a_full[q % NA]);
+    }
+  } else if (warp < P_MMA_WARP) {
+    // ================= epilogue warps: drain accumulator it & 1 ====================================
+    const int ew = warp - P_EPI_WARP0, et = tid - P_EPI_WARP0 * 32;   // TMEM lane quarter, thread 0..127
+    for (int it = 0; it < n_my; ++it) {
+      const int item = blockIdx.x + it * gridDim.x;
+      const int mt = item % p.m_tiles, ntile = item / p.m_tiles;
+      const int acc = it & 1;
+      for (int c = et; c < p.n_tile; c += 128) {
+        const int ch = ntile * p.n_tile + c;
+        s_bias[acc][c] = (p.bias && ch < p.c_bias) ? p.bias[ch] : 0.f;
+      }
+      // this thread's output pixel: slot t0 + row
+      const int row = ew * 32 + lane;
+      const int64_t t = (int64_t)mt * BM + row;
+      bool row_ok = false; uint32_t pix = 0;
+      if (t < p.T) {
+        const uint32_t tu = (uint32_t)t;
+        const uint32_t n = tu / (uint32_t)slots_per_img, rem = tu - n * (uint32_t)slots_per_img;
+        const uint32_t yy = rem / (uint32_t)p.Wp, xs = rem - yy * (uint32_t)p.Wp;
+        if ((int)yy < p.H && (int)xs < p.W) { row_ok = true; pix = (n * p.H + yy) * p.W + xs; }
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");   // bias tile visible to the four epilogue warps
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      const int n_base = ntile * p.n_tile;
+      __nv_bfloat16* yrow = p.y + (size_t)pix * p.y_pitch;
+      const uint32_t tcol = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * p.n_tile);
+      for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+        uint32_t a16[16];
+        tc_ld16(tcol + (uint32_t)c0, a16);
+        tc_wait_ld();
+        if (row_ok) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int n0 = n_base + c0 + h * 8;
+            if (n0 + 8 <= p.c_valid) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float a = __uint_as_float(a16[h * 8 + 2 * e]) + s_bias[acc][c0 + h * 8 + 2 * e];
+                const float b = __uint_as_float(a16[h * 8 + 2 * e + 1]) + s_bias[acc][c0 + h * 8 + 2 * e + 1];
+                __nv_bfloat162 t2 = __floats2bfloat162_rn(a, b);
+                pk[e] = *reinterpret_cast<uint32_t*>(&t2);
+              }
+              *reinterpret_cast<uint4*>(yrow + n0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);   // 128 arrivals: the accumulator may be overwritten
+    }
+  } else if (warp == P_B_WARP) {
+    // ================= B loader ==================================================================
+    if (lane == 0) {
+      const int n_st = p.n_chunks * KK;
+      int ks = 0;
+      for (int it = 0; it < n_my; ++it) {
+        const int item = blockIdx.x + it * gridDim.x;
+        const int ntile = item / p.m_tiles;
+        const uint8_t* wsrc = p.wpack + (size_t)ntile * n_st * b_stage_bytes;
+        for (int q = 0; q < n_st; ++q, ++ks) {
+          const int s = ks % S;
+          if (ks >= S) mbar_wait(&empty_bar[s], ((ks / S) - 1) & 1);
+          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)b_stage_bytes);
+          bulk_g2s(smem_u32(b_smem + (size_t)s * b_stage_bytes), wsrc + (size_t)q * b_stage_bytes, (uint32_t)b_stage_bytes, &full_bar[s]);
+        }
+      }
+    }
+  } else {
+    // ================= MMA issuer ================================================================
+    if (lane == 0) {
+      const uint32_t idesc = idesc_bf16_m128(p.n_tile);
+      int ks = 0, ac = 0;
+      for (int it = 0; it < n_my; ++it) {
+        const int acc = it & 1;
+        if (it >= 2) { mbar_wait(&tmem_empty[acc], ((it >> 1) - 1) & 1); tc_fence_after(); }
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
+        for (int c = 0; c < p.n_chunks; ++c, ++ac) {
+          const int buf = ac % NA;
+          mbar_wait(&a_full[buf], (ac / NA) & 1);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(a_smem + (size_t)buf * p.halo_bytes);
+          const int kv_here = min(KV_PER_STAGE, p.kv_per_tap - c * KV_PER_STAGE);
+          const int ksteps = (kv_here + 1) >> 1;
+          for (int tap = 0; tap < KK; ++tap, ++ks) {
+            const int s = ks % S;
+            mbar_wait(&full_bar[s], (ks / S) & 1);
+            tc_fence_after();
+            const uint32_t a_addr = a_base + (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 128u;
+            const uint32_t b_addr = smem_u32(b_smem + (size_t)s * b_stage_bytes);
+            for (int q = 0; q < ksteps; ++q)
+              tc_mma_bf16(d_tmem, smem_desc_k_sw128(a_addr + q * 32), smem_desc_k_sw128(b_addr + q * 32), idesc, (c | tap | q) != 0);
+            tc_commit(&empty_bar[s]);
+          }
+          tc_commit(&a_empty[buf]);
+        }
+        tc_commit(&tmem_full[acc]);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == P_MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
@@ -724,6 +967,47 @@ static int launch_halo(mg_ctx* ctx, UParams& p, const Geometry& g) {
   return MG_OK;
 }
 
+static int launch_halo_persistent(mg_ctx* ctx, UParams& p, const Geometry& g) {
+  p.Wp = p.W + 1; p.Hp = p.H + 1;
+  p.T = (int64_t)p.Nimg * p.Hp * p.Wp;
+  p.HL = BM + 2 * p.Wp + 2;
+  p.n_chunks = g.n_chunks;
+  p.halo_bytes = mg_round_up(p.HL * 128, 1024);
+  p.m_tiles = (int)mg_cdiv(p.T, BM); p.n_ntiles = g.n_tiles; p.n_items = p.m_tiles * p.n_ntiles;
+  const int b_stage = p.n_tile * 128;
+  int cols = 32;
+  while (cols < 2 * p.n_tile) cols <<= 1;            // two accumulators
+  p.tmem_cols = cols;
+  // one persistent CTA per SM (two when both accumulators and the rings of two CTAs fit)
+  static int cps_env = -1;
+  if (cps_env < 0) { const char* e = getenv("MGCONV_PERSIST_CTAS"); cps_env = e ? atoi(e) : 0; }
+  int cps = cps_env > 0 ? cps_env : (cols <= 256 ? 2 : 1);
+  const int budget = (cps == 1 ? 200 : 104) * 1024;
+  p.n_abuf = std::max(2, std::min(P_MAX_ABUF, (budget / 2) / p.halo_bytes));
+  int S = (budget - p.n_abuf * p.halo_bytes) / b_stage;
+  while (S < 3 && p.n_abuf > 2) { --p.n_abuf; S = (budget - p.n_abuf * p.halo_bytes) / b_stage; }
+  S = std::max(2, std::min(S, MAX_STAGES));
+  p.stages = S; p.lag = 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 12 * 1024));
+    attr_set = true;
+  }
+  const int smem = p.n_abuf * p.halo_bytes + S * b_stage + 1024;
+  const int grid = std::min(p.n_items, ctx->num_sms * cps);
+  p.timeline = nullptr;
+  MG_CUDA(ctx, mg_launch_pdl(umma_conv_halo_persistent_kernel, dim3(grid), dim3(P_THREADS), (size_t)smem, ctx->stream, p));
+  MG_CHECK_LAUNCH(ctx);
+  ctx->tc_launches++;
+  return MG_OK;
+}
+
+static bool persist_on() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("MGCONV_PERSIST"); on = e ? atoi(e) : 0; }
+  return on != 0;
+}
+
 }  // namespace
 
 bool umma_wgrad_supported(const mg_ctx* ctx, const mg_conv_desc* d);
@@ -794,7 +1078,7 @@ int umma_conv_forward(mg_ctx* ctx, const mg_conv_desc* d, const void* wpack, con
   p.kv_per_tap = g.kv_per_tap; p.nkv = g.nkv; p.n_stages = g.n_stages; p.n_tile = g.n_tile;
   p.wpack = (const uint8_t*)wpack; p.bias = bias; p.c_bias = d->Cout;
   p.y = (__nv_bfloat16*)y->data; p.y_pitch = y->Cp; p.c_valid = y->Cp;
-  int rc = g.halo ? launch_halo(ctx, p, g) : launch(ctx, p, g.n_tiles);
+  int rc = g.halo ? (persist_on() ? launch_halo_persistent(ctx, p, g) : launch_halo(ctx, p, g)) : launch(ctx, p, g.n_tiles);
   if (rc) return rc;
   if (bn_sums) return mg_bn_stats(ctx, y, bn_sums);
   return MG_OK;
@@ -815,6 +1099,6 @@ int umma_conv_backward_data(mg_ctx* ctx, const mg_conv_desc* d, const void* wpac
   p.wpack = (const uint8_t*)wpack_t; p.bias = nullptr;
   p.y = (__nv_bfloat16*)dcat->data; p.y_pitch = dcat->Cp; p.c_valid = dcat->Cp;
   MG_REQUIRE(ctx, dcat->Cp == g.n_rows, MG_ERR_SHAPE, "dgrad: dcat.Cp %d != %d", dcat->Cp, g.n_rows);
-  return g.halo ? launch_halo(ctx, p, g) : launch(ctx, p, g.n_tiles);
+  return g.halo ? (persist_on() ? launch_halo_persistent(ctx, p, g) : launch_halo(ctx, p, g)) : launch(ctx, p, g.n_tiles);
 }
 

@@ -294,19 +294,43 @@ __global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __
         uint8_t* st = smem + (size_t)s * stage_bytes;
         const uint32_t* tab = sgm.shift ? s_pup[tb] : s_pix[tb];
         const uint32_t dst0 = smem_u32(st) + (uint32_t)(v << 4);
-        for (int h = rg; h < p.HL; h += WH_PROD / 8) {
-          const bool ok = kv_ok && s_pix[tb][h] != 0xFFFFFFFFu;
-          const char* src = ok ? abase + (uint64_t)tab[h] * pitch : reinterpret_cast<const char*>(sgm.ptr);
-          cp_async16((dst0 ^ ((uint32_t)(h & 7) << 4)) + (uint32_t)h * 128, src, ok ? 16u : 0u);
+        for (int h0 = rg; h0 < p.HL; h0 += 4 * (WH_PROD / 8)) {   // table reads batched ahead of the ordered asm copies
+          uint32_t pv[4], tv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int h = h0 + u * (WH_PROD / 8);
+            pv[u] = h < p.HL ? s_pix[tb][h] : 0xFFFFFFFFu;
+            tv[u] = h < p.HL ? tab[h] : 0u;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int h = h0 + u * (WH_PROD / 8);
+            if (h < p.HL) {
+              const bool ok = kv_ok && pv[u] != 0xFFFFFFFFu;
+              const char* src = ok ? abase + (uint64_t)tv[u] * pitch : reinterpret_cast<const char*>(sgm.ptr);
+              cp_async16((dst0 ^ ((uint32_t)(h & 7) << 4)) + (uint32_t)h * 128, src, ok ? 16u : 0u);
+            }
+          }
         }
         const uint32_t g_dst = smem_u32(st) + p.halo_bytes;
-        for (int i = tid; i < 128 * chunks; i += WH_PROD) {
-          const int row = i >> p.chunk_shift, ch = i & (chunks - 1);
-          const uint32_t pix = s_pix[tb][row + p.Wp + 1];
-          const int c0 = nt * p.n_tile + ch * 8;
-          const bool ok = pix != 0xFFFFFFFFu && ch * 8 < p.n_tile && c0 < p.g_cp;
-          const __nv_bfloat16* src = ok ? p.g + (size_t)pix * p.g_cp + c0 : p.g;
-          cp_async16(g_dst + (ch >> 3) * G_IMG + row * 128 + (((ch & 7) ^ (row & 7)) << 4), src, ok ? 16u : 0u);
+        for (int i0 = tid; i0 < 128 * chunks; i0 += 4 * WH_PROD) {
+          uint32_t pv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * WH_PROD;
+            pv[u] = i < 128 * chunks ? s_pix[tb][(i >> p.chunk_shift) + p.Wp + 1] : 0xFFFFFFFFu;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * WH_PROD;
+            if (i < 128 * chunks) {
+              const int row = i >> p.chunk_shift, ch = i & (chunks - 1);
+              const int c0 = nt * p.n_tile + ch * 8;
+              const bool ok = pv[u] != 0xFFFFFFFFu && ch * 8 < p.n_tile && c0 < p.g_cp;
+              const __nv_bfloat16* src = ok ? p.g + (size_t)pv[u] * p.g_cp + c0 : p.g;
+              cp_async16(g_dst + (ch >> 3) * G_IMG + row * 128 + (((ch & 7) ^ (row & 7)) << 4), src, ok ? 16u : 0u);
+            }
+          }
         }
       }
       cp_async_commit();
