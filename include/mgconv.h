@@ -77,7 +77,15 @@ typedef struct {
   int32_t ksize, stride, pad;
   int32_t Cout;
   int32_t H, W; /* spatial size of the concatenated input (= output size when stride 1) */
+  /* kernel variant of the 3x3 tensor-core path for mg_conv_forward / mg_conv_backward_data: 0 = heuristic,
+   * MG_ALGO_*.  Hosts pick it by timing the variants once per layer -- what cudnn.benchmark = true does for the
+   * reference's cudnn.SpatialConvolution (models/ilsvrc/rnmg.lua:230-231).  Every variant accumulates in the same
+   * order, so the choice never changes results. */
+  int32_t algo_fwd, algo_bwd_data;
 } mg_conv_desc;
+enum { MG_ALGO_AUTO = 0, MG_ALGO_TILE128 = 1, /* one 128-slot tile per CTA, several CTAs per SM */
+       MG_ALGO_TILE256 = 2,                   /* two sub-tiles per CTA share every weight stage */
+       MG_ALGO_RESIDENT = 3 };                /* persistent CTAs, whole weight image resident in shared memory */
 
 typedef struct {
   mg_grid g;        /* gradient tensor of a consumer */
@@ -96,6 +104,11 @@ int mg_ctx_destroy(mg_ctx* ctx);
 int mg_ctx_set_stream(mg_ctx* ctx, void* cuda_stream);
 int mg_ctx_set_impl(mg_ctx* ctx, int impl);          /* mg_impl; AUTO = tcgen05 for bf16 */
 int mg_ctx_sync(mg_ctx* ctx);                         /* cutorch.synchronize() equivalent */
+/* kernel-selection overrides for tests and tuning (the analogue of cudnn.benchmark / cudnn.fastest,
+ * models/ilsvrc/rnmg.lua:230-231); value 0 = automatic choice */
+enum { MG_TUNE_HALO_SUBTILES = 0, /* 1 / 2: 128-slot sub-tiles per CTA of the 3x3 tensor-core kernel */
+       MG_TUNE_PERSISTENT = 1     /* 1: weight-resident persistent kernel whenever the weights fit, 2: never */ };
+int mg_ctx_set_tuning(mg_ctx* ctx, int knob, int value);
 const char* mg_last_error(mg_ctx* ctx);
 int mg_version(void);
 int mg_ctx_launch_count(mg_ctx* ctx, int64_t* out);   /* kernels launched through this ctx */
@@ -116,6 +129,10 @@ size_t mg_conv_packed_bytes(const mg_conv_desc* d, int transposed);
 /* repack fp32 [Cout][Ccat][k][k] master weights (cudnn.SpatialConvolution.weight) into the
  * UMMA operand images for forward (transposed=0) and dgrad (transposed=1) */
 int mg_conv_pack_weights(mg_ctx* ctx, const mg_conv_desc* d, const float* w, void* wpack, int transposed);
+/* the same for n (convolution, direction) pairs in ONE kernel launch: what a training step does for every
+ * cudnn.SpatialConvolution of the model after optim.sgd changed the weights (models/basic_model.lua:64-66) */
+int mg_conv_pack_weights_batched(mg_ctx* ctx, int32_t n, const mg_conv_desc* const* descs, const float* const* w,
+                                 void* const* wpack, const int32_t* transposed);
 
 /* fused gather + conv + bias; writes raw y and accumulates per-channel (sum, sumsq) of y in
  * bn_sums[2*Cout] (fp64, caller zeroes) for the following SpatialBatchNormalization */
@@ -135,6 +152,25 @@ int mg_bn_finalize(mg_ctx* ctx, const double* bn_sums, int64_t count, int32_t C,
 int mg_residual_forward(mg_ctx* ctx, const mg_grid* z, const mg_grid* s, int relu, mg_grid* out, mg_grid* pooled);
 /* `pooled` (nullable): also writes maxpool2x2_ceil(out) -- the operand the next stage's coarser
  * neighbour gathers (rnmg.lua:54-60), produced here so the conv's loader stays a pure copy */
+
+/* mg_bn_finalize + mg_residual_forward as ONE pass: SpatialBatchNormalization (statistics -> affine, running
+ * statistics update) -> [CAddTable(true) with the shortcut] -> [ReLU(true)] -> [pooled companion]
+ * (models/ilsvrc/rnmg.lua:27,37 + 13-20,140-154).  z is the raw conv output; z->scale / z->shift must point at
+ * [Cp] workspaces that receive the affine (kept for evaluation-time reuse and the fp32 path). */
+typedef struct {
+  const double* sums;   /* [2*C] (sum y, sum y^2) from mg_conv_forward / mg_bn_stats; unused when !training */
+  int64_t count;        /* elements per channel behind the sums */
+  const float* gamma;   /* nullable: 1 */
+  const float* beta;    /* nullable: 0 */
+  float* running_mean;  /* updated when training (nullable then); read when !training */
+  float* running_var;
+  float eps, momentum;
+  int32_t training;
+  float* save_mean;     /* nullable; [Cp] batch mean / invstd for mg_bn_backward */
+  float* save_invstd;
+} mg_bn_fused;
+int mg_bn_residual_forward(mg_ctx* ctx, const mg_grid* z, const mg_bn_fused* bn, const mg_grid* s, int relu,
+                           mg_grid* out, mg_grid* pooled);
 
 /* per-channel (sum, sumsq) of a stored grid accumulated into bn_sums[2*C] (fp64, caller zeroes):
  * the statistics pass of nn.SpatialBatchNormalization when the conv epilogue did not fuse it */

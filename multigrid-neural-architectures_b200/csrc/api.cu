@@ -2,6 +2,7 @@
 // communicator.  See include/mgconv.h for the contract of every function.
 #include "common.cuh"
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <new>
 
@@ -13,6 +14,7 @@ int simt_conv_backward_weight(mg_ctx*, const mg_conv_desc*, const mg_grid*, floa
 bool umma_conv_supported(const mg_ctx*, const mg_conv_desc*, int kind);
 size_t umma_packed_bytes(const mg_conv_desc*, int transposed);
 int umma_pack_weights(mg_ctx*, const mg_conv_desc*, const float*, void*, int transposed);
+int umma_pack_weights_batched(mg_ctx*, int n, const mg_conv_desc* const*, const float* const*, void* const*, const int32_t*);
 int umma_conv_forward(mg_ctx*, const mg_conv_desc*, const void*, const float*, mg_grid*, double*);
 int umma_conv_backward_data(mg_ctx*, const mg_conv_desc*, const void*, const mg_grid*, mg_grid*);
 int umma_conv_backward_weight(mg_ctx*, const mg_conv_desc*, const mg_grid*, float*, float*, float);
@@ -114,6 +116,8 @@ int mg_ctx_destroy(mg_ctx* ctx) {
   }
   mg_comm_destroy(ctx);
   if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->pack_dev) cudaFree(ctx->pack_dev);
+  free(ctx->pack_host);
   delete ctx;
   return MG_OK;
 }
@@ -122,6 +126,12 @@ int mg_ctx_set_stream(mg_ctx* ctx, void* s) { if (!ctx) return MG_ERR_INVALID_AR
 int mg_ctx_set_impl(mg_ctx* ctx, int impl) {
   if (!ctx || impl < 0 || impl > 2) return MG_ERR_INVALID_ARG;
   ctx->impl = impl; return MG_OK;
+}
+int mg_ctx_set_tuning(mg_ctx* ctx, int knob, int value) {
+  if (!ctx) return MG_ERR_INVALID_ARG;
+  if (knob == MG_TUNE_HALO_SUBTILES) { MG_REQUIRE(ctx, value >= 0 && value <= 2, MG_ERR_INVALID_ARG, "set_tuning: sub-tiles %d", value); ctx->tune_mt = value; return MG_OK; }
+  if (knob == MG_TUNE_PERSISTENT) { MG_REQUIRE(ctx, value >= 0 && value <= 2, MG_ERR_INVALID_ARG, "set_tuning: persistent %d", value); ctx->tune_persist = value; return MG_OK; }
+  MG_FAIL(ctx, MG_ERR_INVALID_ARG, "set_tuning: unknown knob %d", knob);
 }
 int mg_ctx_sync(mg_ctx* ctx) {
   if (!ctx) return MG_ERR_INVALID_ARG;
@@ -140,6 +150,13 @@ size_t mg_conv_packed_bytes(const mg_conv_desc* d, int transposed) { return d ? 
 int mg_conv_pack_weights(mg_ctx* ctx, const mg_conv_desc* d, const float* w, void* wpack, int transposed) {
   if (!ctx || !d || !w || !wpack) return MG_ERR_INVALID_ARG;
   return umma_pack_weights(ctx, d, w, wpack, transposed);
+}
+
+int mg_conv_pack_weights_batched(mg_ctx* ctx, int32_t n, const mg_conv_desc* const* descs, const float* const* w, void* const* wpack,
+                                 const int32_t* transposed) {
+  if (!ctx || n < 0 || (n && (!descs || !w || !wpack || !transposed))) return MG_ERR_INVALID_ARG;
+  if (n == 0) return MG_OK;
+  return umma_pack_weights_batched(ctx, n, descs, w, wpack, transposed);
 }
 
 int mg_conv_forward(mg_ctx* ctx, const mg_conv_desc* d, const float* w, const void* wpack, const float* bias,

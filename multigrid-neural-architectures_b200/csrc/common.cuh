@@ -27,6 +27,13 @@ struct mg_ctx {
   // scratch owned by the context (split-K partial sums of the weight gradient), grown on demand
   void* ws;
   size_t ws_bytes;
+  // kernel-selection overrides (mg_ctx_set_tuning); 0 = automatic
+  int tune_mt;       // 128-slot sub-tiles per CTA of the halo convolution kernel (1 / 2)
+  int tune_persist;  // weight-resident persistent kernel: 1 = whenever the weights fit, 2 = never
+  // job table of mg_conv_pack_weights_batched (device copy + the host image it was uploaded from)
+  void* pack_dev;
+  void* pack_host;
+  size_t pack_cap, pack_bytes;
 };
 
 // make the context workspace at least `bytes` large (one blocking cudaMalloc when it grows)

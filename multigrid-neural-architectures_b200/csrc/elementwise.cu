@@ -6,10 +6,11 @@
 #include <algorithm>
 
 // bf16 fast paths (elementwise_bf16.cu); each returns false when it does not apply
-bool bf16_apply(mg_ctx*, const mg_grid* z, const mg_grid* s, int relu, mg_grid* out, mg_grid* pooled);
+bool bf16_apply(mg_ctx*, const mg_grid* z, const mg_grid* s, int relu, mg_grid* out, mg_grid* pooled, const mg_bn_fused* bn);
 bool bf16_bn_stats(mg_ctx*, const mg_grid* y, double* sums);
 bool bf16_combine(mg_ctx*, const mg_grid* x, int relu_mask, const mg_grid* bn_x, int n_src, const mg_grad_src* src, mg_grid* d, double* sums);
-bool bf16_bn_bwd_apply(mg_ctx*, const mg_grid* xraw, const mg_grid* d, mg_grid* out, const float* coef, float* conv_dbias, float gscale);
+bool bf16_bn_bwd_apply(mg_ctx*, const mg_grid* xraw, const mg_grid* d, mg_grid* out, const double* sums, int64_t count, const float* gamma,
+                       const float* mean, const float* invstd, float* dgamma, float* dbeta, float* conv_dbias, float gscale);
 int simt_dbias(mg_ctx* ctx, const mg_grid* g, int Cout, float* dbias, float gscale);
 bool bf16_pool3(mg_ctx*, const mg_grid* in, mg_grid* out, uint8_t* code);
 bool bf16_import_nchw(mg_ctx*, const float* src, mg_grid* dst);
@@ -455,7 +456,7 @@ int mg_residual_forward(mg_ctx* ctx, const mg_grid* z, const mg_grid* s, int rel
     MG_REQUIRE(ctx, pooled->N == z->N && pooled->H == Hp && pooled->W == Wp && pooled->C == z->C && pooled->Cp <= out->Cp,
                MG_ERR_SHAPE, "residual: pooled shape");
   }
-  if (ctx->dtype == MG_BF16 && bf16_apply(ctx, z, s, relu, out, pooled)) { MG_CHECK_LAUNCH(ctx); return MG_OK; }
+  if (ctx->dtype == MG_BF16 && bf16_apply(ctx, z, s, relu, out, pooled, nullptr)) { MG_CHECK_LAUNCH(ctx); return MG_OK; }
   if (pooled) {
     int Hp = (z->H + 1) / 2, Wp = (z->W + 1) / 2;
     int64_t total = (int64_t)z->N * Hp * Wp * out->Cp;
@@ -470,6 +471,24 @@ int mg_residual_forward(mg_ctx* ctx, const mg_grid* z, const mg_grid* s, int rel
                                                                            s != nullptr, relu, (T*)out->data, out->Cp););
   MG_CHECK_LAUNCH(ctx);
   return MG_OK;
+}
+
+int mg_bn_residual_forward(mg_ctx* ctx, const mg_grid* z, const mg_bn_fused* bn, const mg_grid* s, int relu, mg_grid* out, mg_grid* pooled) {
+  if (!ctx || !z || !bn || !out) return MG_ERR_INVALID_ARG;
+  MG_REQUIRE(ctx, z->scale && z->shift, MG_ERR_INVALID_ARG, "bn_residual: z needs scale / shift workspaces");
+  MG_REQUIRE(ctx, bn->training ? bn->sums != nullptr : (bn->running_mean && bn->running_var), MG_ERR_INVALID_ARG,
+             "bn_residual: missing statistics");
+  MG_REQUIRE(ctx, out->N == z->N && out->H == z->H && out->W == z->W && out->C == z->C, MG_ERR_SHAPE, "bn_residual: out shape");
+  if (s) MG_REQUIRE(ctx, s->N == z->N && s->H == z->H && s->W == z->W && s->C <= z->C, MG_ERR_SHAPE,
+                    "bn_residual: shortcut %dx%dx%d vs %dx%dx%d", s->H, s->W, s->C, z->H, z->W, z->C);
+  if (pooled)
+    MG_REQUIRE(ctx, pooled->N == z->N && pooled->H == (z->H + 1) / 2 && pooled->W == (z->W + 1) / 2 && pooled->C == z->C && pooled->Cp <= out->Cp,
+               MG_ERR_SHAPE, "bn_residual: pooled shape");
+  if (ctx->dtype == MG_BF16 && bf16_apply(ctx, z, s, relu, out, pooled, bn)) { MG_CHECK_LAUNCH(ctx); return MG_OK; }
+  int rc = mg_bn_finalize(ctx, bn->sums, bn->count, z->C, z->Cp, bn->gamma, bn->beta, bn->running_mean, bn->running_var, bn->eps,
+                          bn->momentum, bn->training, const_cast<float*>(z->scale), const_cast<float*>(z->shift), bn->save_mean, bn->save_invstd);
+  if (rc) return rc;
+  return mg_residual_forward(ctx, z, s, relu, out, pooled);
 }
 
 int mg_bn_stats(mg_ctx* ctx, const mg_grid* y, double* bn_sums) {
@@ -589,10 +608,14 @@ int mg_bn_backward(mg_ctx* ctx, const mg_grid* xraw, const mg_grid* d, mg_grid* 
   if (!ctx || !xraw || !d || !out || !bn_sums || !save_mean || !save_invstd || !coef_ws) return MG_ERR_INVALID_ARG;
   MG_REQUIRE(ctx, d->N == xraw->N && d->H == xraw->H && d->W == xraw->W && d->C == xraw->C, MG_ERR_SHAPE, "bn_backward: shape");
   MG_REQUIRE(ctx, out->N == d->N && out->H == d->H && out->W == d->W && out->C == d->C, MG_ERR_SHAPE, "bn_backward: out shape");
+  // bf16: one pass (coefficients derived in-kernel, block 0 accumulates dgamma / dbeta)
+  if (ctx->dtype == MG_BF16 && bf16_bn_bwd_apply(ctx, xraw, d, out, bn_sums, count, gamma, save_mean, save_invstd, dgamma, dbeta, conv_dbias, gscale)) {
+    MG_CHECK_LAUNCH(ctx);
+    return MG_OK;
+  }
   mg_launch_pdl(bn_bwd_coef_kernel, dim3((unsigned)mg_cdiv(d->Cp, 128)), dim3(128), 0, ctx->stream, bn_sums, count, (int)d->C, (int)d->Cp, gamma,
                 save_mean, save_invstd, dgamma, dbeta, gscale, coef_ws);
   MG_CHECK_LAUNCH(ctx);
-  if (ctx->dtype == MG_BF16 && bf16_bn_bwd_apply(ctx, xraw, d, out, coef_ws, conv_dbias, gscale)) { MG_CHECK_LAUNCH(ctx); return MG_OK; }
   int64_t P = (int64_t)d->N * d->H * d->W;
   MG_DISPATCH(ctx, bn_bwd_apply_kernel<T><<<GRID1(P * out->Cp), EB, 0, ctx->stream>>>((const T*)xraw->data, xraw->Cp, (const T*)d->data, d->Cp,
                                                                                       (T*)out->data, out->Cp, d->C, P, coef_ws););

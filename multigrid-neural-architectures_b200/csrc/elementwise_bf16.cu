@@ -68,40 +68,98 @@ struct ApplyP {
   bf16* out; int o_cp;
   bf16* pooled; int p_cp;       // or null
   int N, H, W, C, Hp, Wp;
+  // fused BatchNorm finalisation (bn != 0): scale / shift are derived in-kernel from the fp64 sums (training) or the
+  // running statistics (evaluation) -- expression for expression bn_finalize_kernel -- and block 0 writes the
+  // module state (running statistics, saved mean / invstd, scale / shift)
+  int bn, training;
+  const double* sums; int64_t count;
+  const float* gamma; const float* beta; float* rmean; float* rvar; float eps, momentum;
+  float* smean; float* sinvstd; float* scale_out; float* shift_out;
 };
 
-__global__ void __launch_bounds__(256) apply_bf16_kernel(ApplyP p) {
+__global__ void __launch_bounds__(256, 3) apply_bf16_kernel(ApplyP p) {
   pdl_launch();
   pdl_wait();
+  extern __shared__ float s_aff[];   // [2][z_cp] when bn
+  if (p.bn) {
+    for (int c = threadIdx.x; c < p.z_cp; c += blockDim.x) {
+      float scv = 0.f, shv = 0.f, mv = 0.f, iv = 0.f;
+      if (c < p.C) {
+        double mean, var;
+        if (p.training) {
+          mean = p.sums[c] / (double)p.count;
+          var = p.sums[p.C + c] / (double)p.count - mean * mean;   // biased
+          if (var < 0) var = 0;
+          if (p.rmean && blockIdx.x == 0) {
+            const double unb = p.count > 1 ? var * (double)p.count / (double)(p.count - 1) : var;
+            p.rmean[c] = (float)((1.0 - p.momentum) * p.rmean[c] + p.momentum * mean);
+            p.rvar[c] = (float)((1.0 - p.momentum) * p.rvar[c] + p.momentum * unb);
+          }
+        } else {
+          mean = p.rmean[c]; var = p.rvar[c];
+        }
+        const double invstd = 1.0 / sqrt(var + (double)p.eps);
+        const float g = p.gamma ? p.gamma[c] : 1.f, b = p.beta ? p.beta[c] : 0.f;
+        scv = (float)(g * invstd);
+        shv = (float)(b - g * invstd * mean);
+        mv = (float)mean; iv = (float)invstd;
+      }
+      s_aff[c] = scv; s_aff[p.z_cp + c] = shv;
+      if (blockIdx.x == 0) {
+        p.scale_out[c] = scv; p.shift_out[c] = shv;
+        if (p.smean) { p.smean[c] = mv; p.sinvstd[c] = iv; }
+      }
+    }
+    __syncthreads();
+  }
+  // each CTA streams ONE contiguous range of 2x2 pixel blocks; its threads form `lanes` block lanes x V channel vectors
   const int V = p.o_cp >> 3;
-  const int64_t total = (int64_t)p.N * p.Hp * p.Wp * V;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int vc = (int)(i % V); int64_t q = i / V;
-  const int px = (int)(q % p.Wp); q /= p.Wp;
-  const int py = (int)(q % p.Hp); const int n = (int)(q / p.Hp);
+  const int lanes = blockDim.x / V;
+  const int vc = threadIdx.x % V, lane = threadIdx.x / V;
+  if (lane >= lanes) return;
+  const int64_t nblocks = (int64_t)p.N * p.Hp * p.Wp;
+  const int64_t per_cta = (nblocks + gridDim.x - 1) / gridDim.x;
+  const int64_t b_begin = (int64_t)blockIdx.x * per_cta, b_end = min(nblocks, b_begin + per_cta);
   const int c0 = vc * 8;
   float sc[8], sh[8];
-  const bool has_aff = p.scale != nullptr;
-  if (has_aff) { ldf8(p.scale + c0, sc); ldf8(p.shift + c0, sh); }
+  const bool has_aff = p.bn || p.scale != nullptr;
+  if (p.bn) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sc[e] = s_aff[c0 + e]; sh[e] = s_aff[p.z_cp + c0 + e]; }
+  } else if (has_aff) { ldf8(p.scale + c0, sc); ldf8(p.shift + c0, sh); }
   const bool has_s = p.s != nullptr && c0 < p.s_cp;
-  float best[8];
+  for (int64_t blk = b_begin + lane; blk < b_end; blk += lanes) {
+    const int px = (int)(blk % p.Wp); int64_t q = blk / p.Wp;
+    const int py = (int)(q % p.Hp); const int n = (int)(q / p.Hp);
+    float best[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) best[e] = -INFINITY;
+    for (int e = 0; e < 8; ++e) best[e] = -INFINITY;
+    // the (up to) eight 16-byte loads of the block are issued before any arithmetic
+    uint4 zr[4], sr[4];
+    bool ok[4];
 #pragma unroll
-  for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-    for (int dx = 0; dx < 2; ++dx) {
-      const int y = 2 * py + dy, x = 2 * px + dx;
-      if (y >= p.H || x >= p.W) continue;
+    for (int k = 0; k < 4; ++k) {
+      const int y = 2 * py + (k >> 1), x = 2 * px + (k & 1);
+      ok[k] = y < p.H && x < p.W;
       const int64_t pix = ((int64_t)n * p.H + y) * p.W + x;
-      V8 v = ld8(p.z + pix * p.z_cp + c0);
+      zr[k] = make_uint4(0, 0, 0, 0); sr[k] = make_uint4(0, 0, 0, 0);
+      if (ok[k]) {
+        zr[k] = __ldg(reinterpret_cast<const uint4*>(p.z + pix * p.z_cp + c0));
+        if (has_s) sr[k] = __ldg(reinterpret_cast<const uint4*>(p.s + pix * p.s_cp + c0));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!ok[k]) continue;
+      const int y = 2 * py + (k >> 1), x = 2 * px + (k & 1);
+      const int64_t pix = ((int64_t)n * p.H + y) * p.W + x;
+      V8 v = unpack8(zr[k]);
       if (has_aff) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) v.v[e] = mg_xform(v.v[e], sc[e], sh[e], p.z_relu);
       }
       if (has_s) {
-        const V8 sv = ld8(p.s + pix * p.s_cp + c0);
+        const V8 sv = unpack8(sr[k]);
 #pragma unroll
         for (int e = 0; e < 8; ++e) v.v[e] += sv.v[e];
       }
@@ -117,11 +175,12 @@ __global__ void __launch_bounds__(256) apply_bf16_kernel(ApplyP p) {
       for (int e = 0; e < 8; ++e)
         if (r.v[e] > best[e] || r.v[e] != r.v[e]) best[e] = r.v[e];
     }
-  if (p.pooled && c0 < p.p_cp) {
-    V8 b;
+    if (p.pooled && c0 < p.p_cp) {
+      V8 b;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) b.v[e] = (c0 + e < p.C) ? best[e] : 0.f;
-    *reinterpret_cast<uint4*>(p.pooled + (((int64_t)n * p.Hp + py) * p.Wp + px) * p.p_cp + c0) = pack8(b);
+      for (int e = 0; e < 8; ++e) b.v[e] = (c0 + e < p.C) ? best[e] : 0.f;
+      *reinterpret_cast<uint4*>(p.pooled + (((int64_t)n * p.Hp + py) * p.Wp + px) * p.p_cp + c0) = pack8(b);
+    }
   }
 }
 
@@ -175,7 +234,13 @@ struct CombP {
   int N, H, W, C, Hb, Wb;        // Hb = ceil(H/2): 2x2 blocks
 };
 
-__global__ void __launch_bounds__(256, 3) combine_bf16_kernel(CombP p) {
+// NS >= 0: the number of sources and their modes (2 bits each in MODES) are compile-time constants, so the source loop
+// unrolls, the mode branches fold and the compiler can issue the loads of ALL sources of a 2x2 block back to back
+// (the pass is latency bound: bytes in flight per SM are what matters).  NS < 0: generic (run-time source list).
+__device__ __forceinline__ V8 ldg8(const bf16* p) { return unpack8(__ldg(reinterpret_cast<const uint4*>(p))); }
+
+template <int NS, int MODES>
+__global__ void __launch_bounds__(256, NS < 0 ? 3 : 2) combine_bf16_kernel(const __grid_constant__ CombP p) {
   pdl_launch();
   pdl_wait();
   extern __shared__ float sh[];
@@ -194,8 +259,11 @@ __global__ void __launch_bounds__(256, 3) combine_bf16_kernel(CombP p) {
   float sd[8], sdx[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { sd[e] = 0.f; sdx[e] = 0.f; }
+  const int n_src = NS < 0 ? p.n_src : NS;
   bool need_x = p.relu_mask != 0;
-  for (int s = 0; s < p.n_src; ++s) need_x = need_x || p.src[s].mode == MG_SEG_POOL;
+#pragma unroll
+  for (int s = 0; s < (NS < 0 ? MG_MAX_SRC : NS); ++s)
+    if (s < n_src) need_x = need_x || (NS < 0 ? p.src[s].mode : ((MODES >> (2 * s)) & 3)) == MG_SEG_POOL;
 
   if (active)
     for (int64_t blk = b_begin + lane; blk < b_end; blk += lanes) {
@@ -213,7 +281,7 @@ __global__ void __launch_bounds__(256, 3) combine_bf16_kernel(CombP p) {
       if (need_x) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (valid[k]) Xr[k] = *reinterpret_cast<const uint4*>(p.x + pix[k] * p.x_cp + c0);
+          if (valid[k]) Xr[k] = __ldg(reinterpret_cast<const uint4*>(p.x + pix[k] * p.x_cp + c0));
       }
       V8 acc[4];
 #pragma unroll
@@ -221,29 +289,32 @@ __global__ void __launch_bounds__(256, 3) combine_bf16_kernel(CombP p) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[k].v[e] = 0.f;
 
-      for (int s = 0; s < p.n_src; ++s) {
-        const CSrc S = p.src[s];
-        if (S.mode == MG_SEG_SAME) {
+#pragma unroll
+      for (int s = 0; s < (NS < 0 ? MG_MAX_SRC : NS); ++s) {
+        if (s >= n_src) break;
+        const CSrc& S = p.src[s];
+        const int mode = NS < 0 ? S.mode : ((MODES >> (2 * s)) & 3);
+        if (mode == MG_SEG_SAME) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             if (valid[k]) {
-              const V8 g = ld8(S.g + pix[k] * S.cp + S.c_off + c0);
+              const V8 g = ldg8(S.g + pix[k] * S.cp + S.c_off + c0);
 #pragma unroll
               for (int e = 0; e < 8; ++e) acc[k].v[e] += g.v[e];
             }
-        } else if (S.mode == MG_SEG_UP) {
+        } else if (mode == MG_SEG_UP) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             if (valid[k]) {
               const int y = y0 + (k >> 1), x = x0 + (k & 1);
               const bf16* gp = S.g + (((int64_t)n * S.H + 2 * y) * S.W + 2 * x) * S.cp + S.c_off + c0;
-              const V8 g0 = ld8(gp), g1 = ld8(gp + S.cp), g2 = ld8(gp + (int64_t)S.W * S.cp), g3 = ld8(gp + (int64_t)S.W * S.cp + S.cp);
+              const V8 g0 = ldg8(gp), g1 = ldg8(gp + S.cp), g2 = ldg8(gp + (int64_t)S.W * S.cp), g3 = ldg8(gp + (int64_t)S.W * S.cp + S.cp);
 #pragma unroll
               for (int e = 0; e < 8; ++e) acc[k].v[e] += g0.v[e] + g1.v[e] + g2.v[e] + g3.v[e];
             }
-        } else if (S.mode == MG_SEG_POOL) {
+        } else if (mode == MG_SEG_POOL) {
           // this 2x2 block is exactly one pooling window: route to the first maximum (row-major scan)
-          const V8 g = ld8(S.g + (((int64_t)n * S.H + by) * S.W + bx) * S.cp + S.c_off + c0);
+          const V8 g = ldg8(S.g + (((int64_t)n * S.H + by) * S.W + bx) * S.cp + S.c_off + c0);
           V8 X[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) X[k] = unpack8(Xr[k]);
@@ -268,9 +339,9 @@ __global__ void __launch_bounds__(256, 3) combine_bf16_kernel(CombP p) {
               for (int oy = oy0; oy <= oy1; ++oy)
                 for (int ox = ox0; ox <= ox1; ++ox) {
                   const int64_t o = ((int64_t)n * S.H + oy) * S.W + ox;
-                  const uint2 code = *reinterpret_cast<const uint2*>(S.aux + o * S.cp + S.c_off + c0);
+                  const uint2 code = __ldg(reinterpret_cast<const uint2*>(S.aux + o * S.cp + S.c_off + c0));
                   const int want = (y - (2 * oy - 1)) * 3 + (x - (2 * ox - 1));
-                  const V8 g = ld8(S.g + o * S.cp + S.c_off + c0);
+                  const V8 g = ldg8(S.g + o * S.cp + S.c_off + c0);
 #pragma unroll
                   for (int e = 0; e < 8; ++e) {
                     const int cd = ((e < 4 ? code.x : code.y) >> (8 * (e & 3))) & 0xFF;
@@ -290,7 +361,7 @@ __global__ void __launch_bounds__(256, 3) combine_bf16_kernel(CombP p) {
             if (c0 + e >= p.C) acc[k].v[e] = 0.f;
           }
           if (p.sums) {
-            const V8 yr = ld8(p.bnx + pix[k] * p.bn_cp + c0);
+            const V8 yr = ldg8(p.bnx + pix[k] * p.bn_cp + c0);
 #pragma unroll
             for (int e = 0; e < 8; ++e) { sd[e] += acc[k].v[e]; sdx[e] = fmaf(acc[k].v[e], yr.v[e], sdx[e]); }
           }
@@ -303,17 +374,39 @@ __global__ void __launch_bounds__(256, 3) combine_bf16_kernel(CombP p) {
 // ---------------------------------------------------------------- BN backward apply ----------
 // G = A*D + B*y + C per channel; optionally also the conv's gradBias += gscale * sum_pixels G
 // (accGradParameters of the convolution that produced y), saving a separate pass over G
-__global__ void __launch_bounds__(256) bn_bwd_apply_bf16_kernel(const bf16* __restrict__ xraw, int x_cp, const bf16* d, int d_cp, bf16* out,
-                                                                int o_cp, int C, int64_t P, const float* __restrict__ coef,
+struct BnBwdP {   // coefficients derived in-kernel (bn_bwd_coef_kernel, expression for expression); block 0 accumulates dgamma / dbeta
+  const double* sums; int64_t count;
+  const float* gamma; const float* mean; const float* invstd;
+  float* dgamma; float* dbeta;
+};
+
+__global__ void __launch_bounds__(256, 3) bn_bwd_apply_bf16_kernel(const bf16* __restrict__ xraw, int x_cp, const bf16* d, int d_cp, bf16* out,
+                                                                int o_cp, int C, int64_t P, BnBwdP bp,
                                                                 float* dbias, float gscale) {
   pdl_launch();
   pdl_wait();
-  extern __shared__ float sh[];
+  extern __shared__ float sh[];   // [V*8] gradBias partials, then [3][V*8] coefficients
   const int V = o_cp >> 3;
-  if (dbias) {
-    for (int c = threadIdx.x; c < V * 8; c += blockDim.x) sh[c] = 0.f;
-    __syncthreads();
+  float* s_coef = sh + V * 8;
+  for (int c = threadIdx.x; c < V * 8; c += blockDim.x) {
+    sh[c] = 0.f;
+    float A = 0.f, B = 0.f, Cc = 0.f;
+    if (c < C) {
+      const double sd = bp.sums[c], sdx = bp.sums[C + c];
+      const double mu = bp.mean[c], is = bp.invstd[c], g = bp.gamma ? bp.gamma[c] : 1.0;
+      const double dg = is * (sdx - mu * sd);
+      if (blockIdx.x == 0) {
+        if (bp.dgamma) bp.dgamma[c] += gscale * (float)dg;
+        if (bp.dbeta) bp.dbeta[c] += gscale * (float)sd;
+      }
+      const double n = (double)bp.count;
+      A = (float)(g * is);
+      B = (float)(-g * is * is * dg / n);
+      Cc = (float)(g * is * (mu * is * dg / n - sd / n));
+    }
+    s_coef[c] = A; s_coef[V * 8 + c] = B; s_coef[2 * V * 8 + c] = Cc;
   }
+  __syncthreads();
   const int lanes = blockDim.x / V;
   const int vc = threadIdx.x % V, lane = threadIdx.x / V;
   const int c0 = vc * 8;
@@ -325,21 +418,27 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_bf16_kernel(const bf16* __re
   for (int e = 0; e < 8; ++e) sb[e] = 0.f;
   if (active) {
     float A[8], B[8], Cc[8];
-    ldf8(coef + c0, A); ldf8(coef + d_cp + c0, B); ldf8(coef + 2 * d_cp + c0, Cc);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { A[e] = s_coef[c0 + e]; B[e] = s_coef[V * 8 + c0 + e]; Cc[e] = s_coef[2 * V * 8 + c0 + e]; }
     for (int64_t pix0 = p_begin + lane; pix0 < p_end; pix0 += 4 * lanes) {
-      V8 dv[4], xv[4];
+      uint4 dr[4], xr[4];   // raw bf16, unpacked at use
 #pragma unroll
       for (int u = 0; u < 4; ++u) {   // eight independent 16-byte loads in flight per thread
         const int64_t pix = pix0 + u * lanes;
-        if (pix < p_end) { dv[u] = ld8(d + pix * d_cp + c0); xv[u] = ld8(xraw + pix * x_cp + c0); }
+        dr[u] = make_uint4(0, 0, 0, 0); xr[u] = make_uint4(0, 0, 0, 0);
+        if (pix < p_end) {
+          dr[u] = *reinterpret_cast<const uint4*>(d + pix * d_cp + c0);   // d may alias out: no read-only path
+          xr[u] = __ldg(reinterpret_cast<const uint4*>(xraw + pix * x_cp + c0));
+        }
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int64_t pix = pix0 + u * lanes;
         if (pix < p_end) {
+          const V8 dv = unpack8(dr[u]), xv = unpack8(xr[u]);
           V8 o;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o.v[e] = (c0 + e < C) ? fmaf(A[e], dv[u].v[e], fmaf(B[e], xv[u].v[e], Cc[e])) : 0.f;
+          for (int e = 0; e < 8; ++e) o.v[e] = (c0 + e < C) ? fmaf(A[e], dv.v[e], fmaf(B[e], xv.v[e], Cc[e])) : 0.f;
           const uint4 pk = pack8(o);
           *reinterpret_cast<uint4*>(out + pix * o_cp + c0) = pk;
           if (dbias) {
@@ -449,18 +548,26 @@ static inline unsigned reduce_grid(const mg_ctx* ctx, int64_t items, int per_sm 
 }  // namespace
 
 // ---- entry points used by elementwise.cu; return false when the fast path does not apply -------------
-bool bf16_apply(mg_ctx* ctx, const mg_grid* z, const mg_grid* s, int relu, mg_grid* out, mg_grid* pooled) {
+bool bf16_apply(mg_ctx* ctx, const mg_grid* z, const mg_grid* s, int relu, mg_grid* out, mg_grid* pooled, const mg_bn_fused* bn) {
   if (s && (s->scale || s->Cp % 8)) return false;
   if (z->Cp % 8 || out->Cp % 8 || z->Cp < out->Cp) return false;
   if (pooled && pooled->Cp % 8) return false;
+  if (bn && (!z->scale || !z->shift || z->Cp > 4096)) return false;
   ApplyP p;
+  memset(&p, 0, sizeof(p));
+  if (bn) {
+    p.bn = 1; p.training = bn->training; p.sums = bn->sums; p.count = bn->count; p.gamma = bn->gamma; p.beta = bn->beta;
+    p.rmean = bn->running_mean; p.rvar = bn->running_var; p.eps = bn->eps; p.momentum = bn->momentum;
+    p.smean = bn->save_mean; p.sinvstd = bn->save_invstd; p.scale_out = const_cast<float*>(z->scale); p.shift_out = const_cast<float*>(z->shift);
+  }
   p.z = (const bf16*)z->data; p.z_cp = z->Cp; p.scale = z->scale; p.shift = z->shift; p.z_relu = z->relu;
   p.s = s ? (const bf16*)s->data : nullptr; p.s_cp = s ? s->Cp : 0;
   p.relu = relu; p.out = (bf16*)out->data; p.o_cp = out->Cp;
   p.pooled = pooled ? (bf16*)pooled->data : nullptr; p.p_cp = pooled ? pooled->Cp : 0;
   p.N = z->N; p.H = z->H; p.W = z->W; p.C = z->C; p.Hp = (z->H + 1) / 2; p.Wp = (z->W + 1) / 2;
+  if (out->Cp > 2048) return false;
   const int64_t total = (int64_t)p.N * p.Hp * p.Wp * (p.o_cp / 8);
-  mg_launch_pdl(apply_bf16_kernel, dim3(grid_for(total)), dim3(256), 0, ctx->stream, p);
+  mg_launch_pdl(apply_bf16_kernel, dim3(reduce_grid(ctx, total, 8)), dim3(256), bn ? 2 * z->Cp * sizeof(float) : 0, ctx->stream, p);
   return true;
 }
 
@@ -493,18 +600,46 @@ bool bf16_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid* b
   p.N = x->N; p.H = x->H; p.W = x->W; p.C = x->C; p.Hb = (x->H + 1) / 2; p.Wb = (x->W + 1) / 2;
   const int V = d->Cp / 8;
   const int64_t items = (int64_t)p.N * p.Hb * p.Wb * V;
+  static int spec = -1;
+  if (spec < 0) { const char* e = getenv("MGCONV_COMBINE_SPEC"); spec = e ? atoi(e) : 1; }
+  int code = 0;
+  for (int s = 0; s < n_src; ++s) code |= (src[s].mode & 3) << (2 * s);
+  const size_t smem = 2 * V * 8 * sizeof(float);
+  // the source-mode lists of the multigrid builders (same / pool / up gathers of ResampleConcat + shortcut); anything else
+  // takes the generic kernel
+#define MG_COMBINE_CASE(NSRC, M0, M1, M2, M3)                                                                      \
+  if (spec && n_src == NSRC && code == ((M0) | (M1) << 2 | (M2) << 4 | (M3) << 6)) {                                  \
+    mg_launch_pdl(combine_bf16_kernel<NSRC, ((M0) | (M1) << 2 | (M2) << 4 | (M3) << 6)>, dim3(reduce_grid(ctx, items, 2)), \
+                  dim3(256), smem, ctx->stream, p);                                                                  \
+    return true;                                                                                                     \
+  }
+  MG_COMBINE_CASE(1, 0, 0, 0, 0)
+  MG_COMBINE_CASE(1, 1, 0, 0, 0)
+  MG_COMBINE_CASE(1, 3, 0, 0, 0)
+  MG_COMBINE_CASE(2, 0, 0, 0, 0)
+  MG_COMBINE_CASE(2, 0, 1, 0, 0)
+  MG_COMBINE_CASE(2, 0, 2, 0, 0)
+  MG_COMBINE_CASE(2, 1, 1, 0, 0)
+  MG_COMBINE_CASE(3, 0, 0, 1, 0)
+  MG_COMBINE_CASE(3, 0, 0, 2, 0)
+  MG_COMBINE_CASE(3, 0, 2, 1, 0)
+  MG_COMBINE_CASE(4, 0, 0, 2, 1)
+#undef MG_COMBINE_CASE
   const unsigned grid = reduce_grid(ctx, items, 3);   // 80 registers: three CTAs per SM are resident
-  mg_launch_pdl(combine_bf16_kernel, dim3(grid), dim3(256), 2 * V * 8 * sizeof(float), ctx->stream, p);
+  mg_launch_pdl(combine_bf16_kernel<-1, 0>, dim3(grid), dim3(256), smem, ctx->stream, p);
   return true;
 }
 
-bool bf16_bn_bwd_apply(mg_ctx* ctx, const mg_grid* xraw, const mg_grid* d, mg_grid* out, const float* coef, float* conv_dbias, float gscale) {
+bool bf16_bn_bwd_apply(mg_ctx* ctx, const mg_grid* xraw, const mg_grid* d, mg_grid* out, const double* sums, int64_t count, const float* gamma,
+                       const float* mean, const float* invstd, float* dgamma, float* dbeta, float* conv_dbias, float gscale) {
   if (xraw->Cp % 8 || d->Cp % 8 || out->Cp % 8 || d->Cp != out->Cp || xraw->Cp < out->Cp || out->Cp > 4096) return false;
+  BnBwdP bp;
+  bp.sums = sums; bp.count = count; bp.gamma = gamma; bp.mean = mean; bp.invstd = invstd; bp.dgamma = dgamma; bp.dbeta = dbeta;
   const int64_t P = (int64_t)d->N * d->H * d->W;
   const int V = out->Cp / 8;
   const unsigned grid = reduce_grid(ctx, P * V, 4);
-  mg_launch_pdl(bn_bwd_apply_bf16_kernel, dim3(grid), dim3(256), V * 8 * sizeof(float), ctx->stream, (const bf16*)xraw->data, xraw->Cp,
-                (const bf16*)d->data, d->Cp, (bf16*)out->data, out->Cp, d->C, P, coef, conv_dbias, gscale);
+  mg_launch_pdl(bn_bwd_apply_bf16_kernel, dim3(grid), dim3(256), 4 * V * 8 * sizeof(float), ctx->stream, (const bf16*)xraw->data, xraw->Cp,
+                (const bf16*)d->data, d->Cp, (bf16*)out->data, out->Cp, d->C, P, bp, conv_dbias, gscale);
   return true;
 }
 

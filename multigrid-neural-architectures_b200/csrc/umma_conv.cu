@@ -59,6 +59,8 @@ struct UParams {
   int halo_bytes;    // HL * 128 rounded up to 1024
   int n_abuf;        // halo buffers (1 or 2)
   long long* timeline;   // debug (MGCONV_TIMELINE=1): per-CTA clock stamps [grid][8], else null
+  double* stats;         // halo forward: per-channel (sum y, sum y^2) of the STORED bf16 output accumulated here ([2][c_stats]), or null
+  int c_stats;
   // persistent halo kernel
   int m_tiles, n_ntiles, n_items;   // slot tiles, column tiles, work items = m_tiles * n_ntiles
 };
@@ -308,21 +310,41 @@ __global__ void __launch_bounds__(N_THREADS, 4) umma_conv_kernel(const __grid_co
 // whole 128-byte rows (the 128B swizzle is a function of the absolute shared-memory address, so a
 // descriptor may start at any row -- verified on hardware, scratch/desc_test.cu).  A is fetched from
 // L2 once per chunk instead of once per tap (x4.4 - x7 less gather traffic than umma_conv_kernel).
-constexpr int HALO_MAX_SLOTS = 128 + 2 * 64 + 2;   // W <= 63
+// butterfly reduce-scatter over the 32 lanes of a warp: every lane contributes v[0..15], afterwards lane l
+// holds the warp-wide sum of element l & 15 (16 shuffles instead of 16 x 5)
+__device__ __forceinline__ float warp_reduce_scatter16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int o = 8; o >= 1; o >>= 1) {
+    const bool hi = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = hi ? v[i] : v[i + o];
+      const float keep = hi ? v[i + o] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
+constexpr int HALO_MAX_SLOTS = 256 + 2 * 64 + 2;   // W <= 63, up to two 128-slot sub-tiles per CTA
 constexpr int H_PROD = 256;                        // 8 loader warps (the first 4 also drain TMEM): the gather is issue bound
 constexpr int H_MMA_WARP = H_PROD / 32, H_B_WARP = H_MMA_WARP + 1;
 constexpr int H_THREADS = H_PROD + 64;
 
 // CL = thread-block cluster size along the tile index: the CL CTAs of a cluster need the same weight stages, so each
 // loads 1/CL of a stage and multicasts it to all of them (L2 -> SM weight traffic / CL)
-template <int CL>
-__global__ void __launch_bounds__(H_THREADS, 2) umma_conv_halo_kernel(const __grid_constant__ UParams p) {
+// MT = 128-slot sub-tiles per CTA (1 or 2).  With MT = 2 the CTA owns 256 consecutive slots and two TMEM accumulators:
+// every weight stage feeds both sub-tiles, so the weight stream per output row halves and the halo overhead per row
+// drops -- the kernel is bound by L2 -> SM bandwidth (measured ~42 B/clk/SM chip-wide), of which the weights that every
+// tile re-streams are 70-90 %.  All eight loader warps drain TMEM (warps 0-3 accumulator 0, warps 4-7 accumulator 1).
+template <int CL, int MT>
+__global__ void __launch_bounds__(H_THREADS, MT == 1 ? 4 : 3) umma_conv_halo_kernel(const __grid_constant__ UParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], a_full[2], a_empty[2], tmem_full_bar;
   __shared__ uint32_t tmem_base_s;
-  __shared__ uint32_t s_pix[HALO_MAX_SLOTS];   // full-resolution pixel index of a halo slot, 0xFFFFFFFF = padding / outside
-  __shared__ uint32_t s_pup[HALO_MAX_SLOTS];   // half-resolution pixel index (UP segments)
+  __shared__ uint32_t s_pix[BM * MT + 130];    // full-resolution pixel index of a halo slot, 0xFFFFFFFF = padding / outside
+  __shared__ uint32_t s_pup[BM * MT + 130];    // half-resolution pixel index (UP segments)
   __shared__ USeg s_seg[MG_MAX_SEG];
   __shared__ float s_bias[256];                // bias of this column tile (zero beyond Cout): no global loads in the epilogue
 
@@ -334,7 +356,7 @@ __global__ void __launch_bounds__(H_THREADS, 2) umma_conv_halo_kernel(const __gr
   const int b_stage_bytes = p.n_tile * 128;
   uint8_t* a_smem = smem;                               // two halo buffers
   uint8_t* b_smem = smem + (size_t)p.n_abuf * p.halo_bytes;    // B ring
-  const int64_t t0 = (int64_t)blockIdx.x * BM;
+  const int64_t t0 = (int64_t)blockIdx.x * (BM * MT);
   const int ntile = blockIdx.y;
   const int KK = 9;
 
@@ -429,38 +451,68 @@ __global__ void __launch_bounds__(H_THREADS, 2) umma_conv_halo_kernel(const __gr
       }
     }
     // ================= epilogue (warps 0-3): TMEM -> registers -> bf16 NHWC rows ===========
-    if (warp < 4) {
+    // With p.stats the BatchNorm statistics of this tile (sum, sum of squares of the STORED bf16 values over the
+    // valid rows) are reduced here: warp butterfly -> per-warp slots in the (now idle) halo buffer -> one fp64
+    // atomic pair per channel and CTA.  The separate statistics pass over y (one HBM read of y) disappears.
+    if (warp < 4 * MT) {
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
     if (tl && tid == 0) tl[3] = clock64();
-    const int row = warp * 32 + lane;
+    const int row = warp * 32 + lane;                      // sub-tile warp >> 2, TMEM lane quarter warp & 3
     const uint32_t pix = s_pix[row + p.Wp + 1];          // slot t0 + row
     const bool row_ok = pix != 0xFFFFFFFFu;
     const int n_base = ntile * p.n_tile;
+    const bool want_stats = p.stats != nullptr;
+    float* s_part = reinterpret_cast<float*>(a_smem);     // [4*MT warps][2][256]: every MMA has completed, the halo buffer is free
     __nv_bfloat16* yrow = p.y + (size_t)(row_ok ? pix : 0) * p.y_pitch;
+    const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * p.n_tile);
     for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
       uint32_t acc[16];
-      tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
+      tc_ld16(tacc + (uint32_t)c0, acc);
       tc_wait_ld();
-      if (row_ok) {
+      uint32_t pk[2][4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int n0 = n_base + c0 + h * 8;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float a = __uint_as_float(acc[h * 8 + 2 * e]) + s_bias[c0 + h * 8 + 2 * e];
+          const float b = __uint_as_float(acc[h * 8 + 2 * e + 1]) + s_bias[c0 + h * 8 + 2 * e + 1];
+          __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+          pk[h][e] = *reinterpret_cast<uint32_t*>(&t);
+        }
+        if (row_ok && n0 + 8 <= p.c_valid) *reinterpret_cast<uint4*>(yrow + n0) = make_uint4(pk[h][0], pk[h][1], pk[h][2], pk[h][3]);
+      }
+      if (want_stats) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int n0 = n_base + c0 + h * 8;
-          if (n0 + 8 <= p.c_valid) {
-            uint32_t pk[4];
+          const bool use = row_ok && n_base + c0 + h * 8 + 8 <= p.c_valid;
+          float sv[16];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float a = __uint_as_float(acc[h * 8 + 2 * e]) + s_bias[c0 + h * 8 + 2 * e];
-              const float b = __uint_as_float(acc[h * 8 + 2 * e + 1]) + s_bias[c0 + h * 8 + 2 * e + 1];
-              __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-              pk[e] = *reinterpret_cast<uint32_t*>(&t);
-            }
-            *reinterpret_cast<uint4*>(yrow + n0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          for (int e = 0; e < 4; ++e) {
+            const float ra = use ? __uint_as_float(pk[h][e] << 16) : 0.f, rb = use ? __uint_as_float(pk[h][e] & 0xFFFF0000u) : 0.f;
+            sv[2 * e] = ra; sv[2 * e + 1] = rb;
+            sv[8 + 2 * e] = ra * ra; sv[8 + 2 * e + 1] = rb * rb;
           }
+          const float tot = warp_reduce_scatter16(sv, lane);   // lane l: (l & 15) < 8 -> sum of column, else sum of squares
+          if (lane < 16) s_part[(warp * 2 + (lane >> 3)) * 256 + c0 + h * 8 + (lane & 7)] = tot;
         }
       }
     }
     tc_fence_before();
+    if (want_stats) {
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * MT) : "memory");       // the epilogue warps
+      for (int c = tid; c < p.n_tile; c += 128 * MT) {
+        const int ch = n_base + c;
+        if (ch < p.c_stats) {
+          float a = 0.f, b = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4 * MT; ++w) { a += s_part[(2 * w) * 256 + c]; b += s_part[(2 * w + 1) * 256 + c]; }
+          atomicAdd(p.stats + ch, (double)a);
+          atomicAdd(p.stats + p.c_stats + ch, (double)b);
+        }
+      }
+    }
     if (tl && tid == 0) tl[4] = clock64();
     }
   } else if (warp == H_B_WARP) {
@@ -505,8 +557,11 @@ __global__ void __launch_bounds__(H_THREADS, 2) umma_conv_halo_kernel(const __gr
           if (tl) wait_b += clock64() - tq;
           const uint32_t a_addr = a_base + (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 128u;
           const uint32_t b_addr = smem_u32(b_smem + (size_t)s * b_stage_bytes);
-          for (int q = 0; q < ksteps; ++q)
-            tc_mma_bf16(tmem_base, smem_desc_k_sw128(a_addr + q * 32), smem_desc_k_sw128(b_addr + q * 32), idesc, (ks | q) != 0);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)   // both sub-tiles consume the same weight stage
+            for (int q = 0; q < ksteps; ++q)
+              tc_mma_bf16(tmem_base + (uint32_t)(mt * p.n_tile), smem_desc_k_sw128(a_addr + (uint32_t)(mt * BM * 128) + q * 32),
+                          smem_desc_k_sw128(b_addr + q * 32), idesc, (ks | q) != 0);
           if (CL == 1) tc_commit(&empty_bar[s]); else tc_commit_mcast(&empty_bar[s], (uint16_t)((1u << CL) - 1));
         }
         tc_commit(&a_empty[buf]);   // halo buffer free once this chunk's MMAs have read it
@@ -525,38 +580,44 @@ __global__ void __launch_bounds__(H_THREADS, 2) umma_conv_halo_kernel(const __gr
 
 
 // ---------------------------------------------------------------- persistent halo kernel ----------
-// Same operand scheme as umma_conv_halo_kernel, but one CTA walks a strided list of (slot tile, column tile)
-// work items and its roles run decoupled, so that nothing of a tile's latency chain is exposed:
+// Same operand scheme as umma_conv_halo_kernel for convolutions whose WHOLE packed weight image fits in shared
+// memory next to a ring of halo buffers (R-MG-34 block 1: 96 -> 64 at 56x56 is 147 KB, its dgrad 110 KB).  The
+// non-persistent kernel re-streams the weights for every 128-slot tile -- 2.4x the activation traffic at N = 64 --
+// through a two-deep ring, which makes its main loop a chain of L2 round trips.  Here one CTA per SM loads the
+// weights ONCE, then walks slot tiles blockIdx.x, +gridDim.x, ... with decoupled roles:
 //   8 loader warps   stage halos into a ring that runs ACROSS chunks and tiles (the next tile's halo is in
 //                    flight while the tensor core works on the current one),
-//   1 B-loader thread streams the (chunk, tap) weight stages through its own ring,
-//   1 MMA thread     accumulates tile i into TMEM accumulator i & 1,
-//   4 epilogue warps drain accumulator (i-1) & 1 meanwhile (TMEM double buffering).
+//   1 MMA thread     accumulates tile i into TMEM accumulator i & 1 (every operand already in shared memory),
+//   4 epilogue warps drain accumulator (i-1) & 1 meanwhile (TMEM double buffering) and keep the BatchNorm
+//                    statistics of all the CTA's tiles in shared memory: one fp64 atomic pair per channel and CTA.
 constexpr int P_LOAD = 256, P_EPI_WARP0 = 8, P_MMA_WARP = 12, P_B_WARP = 13, P_THREADS = 448;
-constexpr int P_MAX_ABUF = 4;
+constexpr int P_MAX_ABUF = 6;
 
 __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel(const __grid_constant__ UParams p) {
   pdl_launch();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], a_full[P_MAX_ABUF], a_empty[P_MAX_ABUF], tmem_full[2], tmem_empty[2];
+  __shared__ uint64_t b_full, a_full[P_MAX_ABUF], a_empty[P_MAX_ABUF], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ uint32_t s_pix[2][HALO_MAX_SLOTS], s_pup[2][HALO_MAX_SLOTS];
-  __shared__ float s_bias[2][256];
+  __shared__ uint32_t s_pix[2][BM + 130], s_pup[2][BM + 130];
   __shared__ USeg s_seg[MG_MAX_SEG];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int S = p.stages, NA = p.n_abuf;
+  const int NA = p.n_abuf;
   const int b_stage_bytes = p.n_tile * 128;
-  uint8_t* a_smem = smem;
-  uint8_t* b_smem = smem + (size_t)NA * p.halo_bytes;
   const int KK = 9;
-  const int n_my = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items blockIdx.x, +gridDim.x, ...
+  const int n_st = p.n_chunks * KK;
+  uint8_t* a_smem = smem;
+  uint8_t* b_smem = smem + (size_t)NA * p.halo_bytes;                        // all n_st weight stages, resident
+  float* s_bias = reinterpret_cast<float*>(b_smem + (size_t)n_st * b_stage_bytes);   // [n_tile]
+  float* s_part = s_bias + p.n_tile;                                         // [4 epilogue warps][2][n_tile]
+  const int n_my = (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles blockIdx.x, +gridDim.x, ...
 
   if (tid < p.n_seg) s_seg[tid] = p.seg[tid];
+  for (int c = tid; c < 8 * p.n_tile; c += P_THREADS) s_part[c] = 0.f;
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], P_LOAD); mbar_init(&a_empty[s], 1); }
+    mbar_init(&b_full, 1);
+    for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], P_LOAD / 2); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -566,6 +627,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   pdl_wait();
+  for (int c = tid; c < p.n_tile; c += P_THREADS) s_bias[c] = (p.bias && c < p.c_bias) ? p.bias[c] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -573,86 +635,78 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
   const int slots_per_img = p.Hp * p.Wp;
 
   if (warp < P_EPI_WARP0) {
-    // ================= loaders ====================================================================
-    const int v = tid & 7, rg = tid >> 3;          // k-vector column, slot lane 0..31
+    // ================= loaders: two independent groups of four warps ===============================
+    // Group g stages chunks g, g+2, ... of the CTA's chunk sequence (which runs across tiles): wait for the ring
+    // slot, issue, wait for the data, publish.  While one group sits out the L2 latency of its chunk the other
+    // one is issuing, and neither ever waits on a buffer the other group's chunk has to release first.
+    const int grp = warp >> 2, gt = tid & 127;
+    const int v = gt & 7, rg = gt >> 3;            // k-vector column, slot lane 0..15
     const int Hs2 = p.H >> 1, Ws2 = p.W >> 1;
-    const int lagA = NA - 1;
-    int ac = 0;                                      // chunks issued so far (ring position)
     const int total_chunks = n_my * p.n_chunks;
-    for (int it = 0; it < n_my; ++it) {
-      const int item = blockIdx.x + it * gridDim.x;
-      const int mt = item % p.m_tiles;
-      const int tb = it & 1;
-      const int64_t t0 = (int64_t)mt * BM;
-      for (int h = tid; h < p.HL; h += P_LOAD) {
-        const int64_t t = t0 - p.Wp - 1 + h;
-        uint32_t pix = 0xFFFFFFFFu, pup = 0;
-        if (t >= 0 && t < p.T) {
-          const uint32_t tu = (uint32_t)t;
-          const uint32_t n = tu / (uint32_t)slots_per_img, rem = tu - n * (uint32_t)slots_per_img;
-          const uint32_t yy = rem / (uint32_t)p.Wp, xs = rem - yy * (uint32_t)p.Wp;
-          if ((int)yy < p.H && (int)xs < p.W) {
-            pix = (n * p.H + yy) * p.W + xs;
-            pup = (n * Hs2 + (yy >> 1)) * Ws2 + (xs >> 1);
-          }
-        }
-        s_pix[tb][h] = pix; s_pup[tb][h] = pup;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(P_LOAD) : "memory");
-      for (int c = 0; c < p.n_chunks; ++c, ++ac) {
-        const int buf = ac % NA;
-        if (ac >= NA) mbar_wait(&a_empty[buf], ((ac / NA) - 1) & 1);
-        const int r = c * KV_PER_STAGE + v;
-        const bool kv_ok = r < p.kv_per_tap;
-        int sg = 0;
-        if (kv_ok) while (sg + 1 < p.n_seg && r >= s_seg[sg + 1].kv_begin) ++sg;
-        const USeg sgm = s_seg[sg];
-        const uint32_t pitch = (uint32_t)sgm.Cp * 2u;
-        const char* base = reinterpret_cast<const char*>(sgm.ptr) + (r - sgm.kv_begin) * 16;
-        const uint32_t* tab = sgm.shift ? s_pup[tb] : s_pix[tb];
-        const uint32_t dst0 = smem_u32(a_smem + (size_t)buf * p.halo_bytes) + (uint32_t)(v << 4);
-        for (int h0 = rg; h0 < p.HL; h0 += 4 * (P_LOAD / 8)) {
-          uint32_t pv[4], tv[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int h = h0 + u * (P_LOAD / 8);
-            pv[u] = h < p.HL ? s_pix[tb][h] : 0xFFFFFFFFu;
-            tv[u] = h < p.HL ? tab[h] : 0u;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int h = h0 + u * (P_LOAD / 8);
-            if (h < p.HL) {
-              const bool ok = kv_ok && pv[u] != 0xFFFFFFFFu;
-              const char* src = ok ? base + (uint64_t)tv[u] * pitch : reinterpret_cast<const char*>(sgm.ptr);
-              cp_async16((dst0 ^ ((uint32_t)(h & 7) << 4)) + (uint32_t)h * 128, src, ok ? 16u : 0u);
+    int cur_it = -1;
+    for (int ac = grp; ac < total_chunks; ac += 2) {
+      const int it = ac / p.n_chunks, c = ac - it * p.n_chunks;
+      if (it != cur_it) {   // this group's slot tables of tile `it`
+        cur_it = it;
+        const int64_t t0 = (int64_t)(blockIdx.x + it * gridDim.x) * BM;
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");   // old table no longer read
+        for (int h = gt; h < p.HL; h += 128) {
+          const int64_t t = t0 - p.Wp - 1 + h;
+          uint32_t pix = 0xFFFFFFFFu, pup = 0;
+          if (t >= 0 && t < p.T) {
+            const uint32_t tu = (uint32_t)t;
+            const uint32_t n = tu / (uint32_t)slots_per_img, rem = tu - n * (uint32_t)slots_per_img;
+            const uint32_t yy = rem / (uint32_t)p.Wp, xs = rem - yy * (uint32_t)p.Wp;
+            if ((int)yy < p.H && (int)xs < p.W) {
+              pix = (n * p.H + yy) * p.W + xs;
+              pup = (n * Hs2 + (yy >> 1)) * Ws2 + (xs >> 1);
             }
           }
+          s_pix[grp][h] = pix; s_pup[grp][h] = pup;
         }
-        cp_async_commit();
-        if (ac >= lagA) {
-          cp_async_wait_dyn(lagA);
-          fence_proxy_async();
-          mbar_arrive(&a_full[(ac - lagA) % NA]);
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
+      }
+      const int buf = ac % NA;
+      if (ac >= NA) mbar_wait(&a_empty[buf], ((ac / NA) - 1) & 1);
+      const int r = c * KV_PER_STAGE + v;
+      const bool kv_ok = r < p.kv_per_tap;
+      int sg = 0;
+      if (kv_ok) while (sg + 1 < p.n_seg && r >= s_seg[sg + 1].kv_begin) ++sg;
+      const USeg sgm = s_seg[sg];
+      const uint32_t pitch = (uint32_t)sgm.Cp * 2u;
+      const char* base = reinterpret_cast<const char*>(sgm.ptr) + (r - sgm.kv_begin) * 16;
+      const uint32_t* tab = sgm.shift ? s_pup[grp] : s_pix[grp];
+      const uint32_t dst0 = smem_u32(a_smem + (size_t)buf * p.halo_bytes) + (uint32_t)(v << 4);
+      for (int h0 = rg; h0 < p.HL; h0 += 4 * 16) {
+        uint32_t pv[4], tv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int h = h0 + u * 16;
+          pv[u] = h < p.HL ? s_pix[grp][h] : 0xFFFFFFFFu;
+          tv[u] = h < p.HL ? tab[h] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int h = h0 + u * 16;
+          if (h < p.HL) {
+            const bool ok = kv_ok && pv[u] != 0xFFFFFFFFu;
+            const char* src = ok ? base + (uint64_t)tv[u] * pitch : reinterpret_cast<const char*>(sgm.ptr);
+            cp_async16((dst0 ^ ((uint32_t)(h & 7) << 4)) + (uint32_t)h * 128, src, ok ? 16u : 0u);
+          }
         }
       }
-    }
-    for (int q = max(0, total_chunks - lagA); q < total_chunks; ++q) {   // publish the chunks still in flight
-      cp_async_wait_dyn(total_chunks - 1 - q);
+      cp_async_commit();
+      cp_async_wait_dyn(0);
       fence_proxy_async();
-      mbar_arrive(&a_full[q % NA]);
+      mbar_arrive(&a_full[buf]);
     }
   } else if (warp < P_MMA_WARP) {
     // ================= epilogue warps: drain accumulator it & 1 ====================================
     const int ew = warp - P_EPI_WARP0, et = tid - P_EPI_WARP0 * 32;   // TMEM lane quarter, thread 0..127
+    const bool want_stats = p.stats != nullptr;
     for (int it = 0; it < n_my; ++it) {
-      const int item = blockIdx.x + it * gridDim.x;
-      const int mt = item % p.m_tiles, ntile = item / p.m_tiles;
+      const int mt = blockIdx.x + it * gridDim.x;
       const int acc = it & 1;
-      for (int c = et; c < p.n_tile; c += 128) {
-        const int ch = ntile * p.n_tile + c;
-        s_bias[acc][c] = (p.bias && ch < p.c_bias) ? p.bias[ch] : 0.f;
-      }
       // this thread's output pixel: slot t0 + row
       const int row = ew * 32 + lane;
       const int64_t t = (int64_t)mt * BM + row;
@@ -663,59 +717,72 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
         const uint32_t yy = rem / (uint32_t)p.Wp, xs = rem - yy * (uint32_t)p.Wp;
         if ((int)yy < p.H && (int)xs < p.W) { row_ok = true; pix = (n * p.H + yy) * p.W + xs; }
       }
-      asm volatile("bar.sync 2, 128;" ::: "memory");   // bias tile visible to the four epilogue warps
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();
-      const int n_base = ntile * p.n_tile;
       __nv_bfloat16* yrow = p.y + (size_t)pix * p.y_pitch;
       const uint32_t tcol = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * p.n_tile);
       for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
         uint32_t a16[16];
         tc_ld16(tcol + (uint32_t)c0, a16);
         tc_wait_ld();
-        if (row_ok) {
+        uint32_t pk[2][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int n0 = c0 + h * 8;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = __uint_as_float(a16[h * 8 + 2 * e]) + s_bias[c0 + h * 8 + 2 * e];
+            const float b = __uint_as_float(a16[h * 8 + 2 * e + 1]) + s_bias[c0 + h * 8 + 2 * e + 1];
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(a, b);
+            pk[h][e] = *reinterpret_cast<uint32_t*>(&t2);
+          }
+          if (row_ok && n0 + 8 <= p.c_valid) *reinterpret_cast<uint4*>(yrow + n0) = make_uint4(pk[h][0], pk[h][1], pk[h][2], pk[h][3]);
+        }
+        if (want_stats) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const int n0 = n_base + c0 + h * 8;
-            if (n0 + 8 <= p.c_valid) {
-              uint32_t pk[4];
+            const bool use = row_ok && c0 + h * 8 + 8 <= p.c_valid;
+            float sv[16];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float a = __uint_as_float(a16[h * 8 + 2 * e]) + s_bias[acc][c0 + h * 8 + 2 * e];
-                const float b = __uint_as_float(a16[h * 8 + 2 * e + 1]) + s_bias[acc][c0 + h * 8 + 2 * e + 1];
-                __nv_bfloat162 t2 = __floats2bfloat162_rn(a, b);
-                pk[e] = *reinterpret_cast<uint32_t*>(&t2);
-              }
-              *reinterpret_cast<uint4*>(yrow + n0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            for (int e = 0; e < 4; ++e) {
+              const float ra = use ? __uint_as_float(pk[h][e] << 16) : 0.f, rb = use ? __uint_as_float(pk[h][e] & 0xFFFF0000u) : 0.f;
+              sv[2 * e] = ra; sv[2 * e + 1] = rb;
+              sv[8 + 2 * e] = ra * ra; sv[8 + 2 * e + 1] = rb * rb;
             }
+            const float tot = warp_reduce_scatter16(sv, lane);
+            // slot owned by this lane of this warp for the whole kernel: accumulate over the CTA's tiles without synchronisation
+            if (lane < 16) s_part[(ew * 2 + (lane >> 3)) * p.n_tile + c0 + h * 8 + (lane & 7)] += tot;
           }
         }
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);   // 128 arrivals: the accumulator may be overwritten
     }
-  } else if (warp == P_B_WARP) {
-    // ================= B loader ==================================================================
-    if (lane == 0) {
-      const int n_st = p.n_chunks * KK;
-      int ks = 0;
-      for (int it = 0; it < n_my; ++it) {
-        const int item = blockIdx.x + it * gridDim.x;
-        const int ntile = item / p.m_tiles;
-        const uint8_t* wsrc = p.wpack + (size_t)ntile * n_st * b_stage_bytes;
-        for (int q = 0; q < n_st; ++q, ++ks) {
-          const int s = ks % S;
-          if (ks >= S) mbar_wait(&empty_bar[s], ((ks / S) - 1) & 1);
-          mbar_arrive_expect_tx(&full_bar[s], (uint32_t)b_stage_bytes);
-          bulk_g2s(smem_u32(b_smem + (size_t)s * b_stage_bytes), wsrc + (size_t)q * b_stage_bytes, (uint32_t)b_stage_bytes, &full_bar[s]);
+    if (want_stats) {
+      asm volatile("bar.sync 3, 128;" ::: "memory");
+      for (int c = et; c < p.n_tile; c += 128)
+        if (c < p.c_stats) {
+          float a = 0.f, b = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) { a += s_part[(w * 2) * p.n_tile + c]; b += s_part[(w * 2 + 1) * p.n_tile + c]; }
+          atomicAdd(p.stats + c, (double)a);
+          atomicAdd(p.stats + p.c_stats + c, (double)b);
         }
-      }
+    }
+  } else if (warp == P_B_WARP) {
+    // ================= weight loader: every stage once =============================================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&b_full, (uint32_t)(n_st * b_stage_bytes));
+      for (int q = 0; q < n_st; ++q)
+        bulk_g2s(smem_u32(b_smem + (size_t)q * b_stage_bytes), p.wpack + (size_t)q * b_stage_bytes, (uint32_t)b_stage_bytes, &b_full);
     }
   } else {
     // ================= MMA issuer ================================================================
     if (lane == 0) {
       const uint32_t idesc = idesc_bf16_m128(p.n_tile);
-      int ks = 0, ac = 0;
+      const uint32_t b_base = smem_u32(b_smem);
+      int ac = 0;
+      mbar_wait(&b_full, 0);
       for (int it = 0; it < n_my; ++it) {
         const int acc = it & 1;
         if (it >= 2) { mbar_wait(&tmem_empty[acc], ((it >> 1) - 1) & 1); tc_fence_after(); }
@@ -727,15 +794,11 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
           const uint32_t a_base = smem_u32(a_smem + (size_t)buf * p.halo_bytes);
           const int kv_here = min(KV_PER_STAGE, p.kv_per_tap - c * KV_PER_STAGE);
           const int ksteps = (kv_here + 1) >> 1;
-          for (int tap = 0; tap < KK; ++tap, ++ks) {
-            const int s = ks % S;
-            mbar_wait(&full_bar[s], (ks / S) & 1);
-            tc_fence_after();
+          for (int tap = 0; tap < KK; ++tap) {
             const uint32_t a_addr = a_base + (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 128u;
-            const uint32_t b_addr = smem_u32(b_smem + (size_t)s * b_stage_bytes);
+            const uint32_t b_addr = b_base + (uint32_t)((c * KK + tap) * b_stage_bytes);
             for (int q = 0; q < ksteps; ++q)
               tc_mma_bf16(d_tmem, smem_desc_k_sw128(a_addr + q * 32), smem_desc_k_sw128(b_addr + q * 32), idesc, (c | tap | q) != 0);
-            tc_commit(&empty_bar[s]);
           }
           tc_commit(&a_empty[buf]);
         }
@@ -764,10 +827,7 @@ struct PackParams {
 };
 
 // one thread per (n row, k-vector): writes 16 bytes of the swizzled stage image
-__global__ void pack_weights_kernel(PackParams p) {
-  pdl_launch();
-  pdl_wait();
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void pack_one(const PackParams& p, int64_t i) {
   const int kv_total = p.n_stages * KV_PER_STAGE;
   const int64_t total = (int64_t)p.n_tiles * p.n_tile * kv_total;
   if (i >= total) return;
@@ -808,6 +868,30 @@ __global__ void pack_weights_kernel(PackParams p) {
   }
   uint8_t* dst = p.out + ((size_t)(tile * p.n_stages + stage) * p.n_tile + nl) * 128 + ((v ^ (nl & 7)) << 4);
   *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(vals);
+}
+
+__global__ void pack_weights_kernel(PackParams p) {
+  pdl_launch();
+  pdl_wait();
+  pack_one(p, (int64_t)blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// every convolution of a plan in ONE launch: block b serves job j with blk_begin[j] <= b < blk_begin[j+1]
+// (150 launches of ~4 us each, pure launch latency, become one HBM-bound pass)
+__global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackParams* __restrict__ jobs, const int* __restrict__ blk_begin, int n_jobs) {
+  pdl_launch();
+  pdl_wait();
+  int lo = 0, hi = n_jobs - 1;
+  const int b = (int)blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (blk_begin[mid] <= b) lo = mid; else hi = mid - 1;
+  }
+  __shared__ PackParams sp;
+  const int* src = reinterpret_cast<const int*>(jobs + lo);
+  for (int t = threadIdx.x; t < (int)(sizeof(PackParams) / sizeof(int)); t += blockDim.x) reinterpret_cast<int*>(&sp)[t] = src[t];
+  __syncthreads();
+  pack_one(sp, (int64_t)(b - blk_begin[lo]) * blockDim.x + threadIdx.x);
 }
 
 // ---------------------------------------------------------------- host side -----------------
@@ -893,44 +977,64 @@ static int launch(mg_ctx* ctx, UParams& p, int n_tiles) {
   return MG_OK;
 }
 
-static int launch_halo(mg_ctx* ctx, UParams& p, const Geometry& g) {
+static int launch_halo(mg_ctx* ctx, UParams& p, const Geometry& g, int algo) {
   p.Wp = p.W + 1; p.Hp = p.H + 1;
   p.T = (int64_t)p.Nimg * p.Hp * p.Wp;
-  p.HL = BM + 2 * p.Wp + 2;
   p.n_chunks = g.n_chunks;
-  p.halo_bytes = mg_round_up(p.HL * 128, 1024);
   const int b_stage = p.n_tile * 128;
-  static int budget_env = -1;
+  static int budget_env = -1, mt_env = -1, cl_env = -1, want_tl = -1;
   if (budget_env < 0) { const char* e = getenv("MGCONV_HALO_SMEM_KB"); budget_env = e ? atoi(e) : 0; }
-  // measured on R-MG-34 (scratch/conv_bench.py): narrow tiles are bound by per-CTA latency chains and want
-  // four resident CTAs (54 KB each, one halo buffer); N >= 192 tiles are bound by the weight stream and
-  // prefer two CTAs with a deeper ring
-  const int budget_kb = budget_env > 0 ? budget_env : (p.n_tile >= 192 ? 108 : 54);
-  // two halo buffers when several chunks follow each other and the budget allows, else one
-  p.n_abuf = (g.n_chunks > 1 && 2 * p.halo_bytes + 2 * b_stage <= budget_kb * 1024) ? 2 : 1;
-  int S = (budget_kb * 1024 - p.n_abuf * p.halo_bytes) / b_stage;
-  S = std::max(2, std::min(S, MAX_STAGES));
-  p.stages = S; p.lag = 1;
-  int cols = 32;
-  while (cols < p.n_tile) cols <<= 1;
-  p.tmem_cols = cols;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8 * 1024));
-    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8 * 1024));
-    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8 * 1024));
-    attr_set = true;
-  }
-  static int cl_env = -1;
+  if (mt_env < 0) { const char* e = getenv("MGCONV_MT"); mt_env = e ? atoi(e) : 0; }
   // measured: multicast clusters couple the CTAs and lose 5-10 % (weights are not the bottleneck): off by default
   if (cl_env < 0) { const char* e = getenv("MGCONV_CLUSTER"); cl_env = e ? atoi(e) : 1; }
+  if (want_tl < 0) { const char* e = getenv("MGCONV_TIMELINE"); want_tl = e ? atoi(e) : 0; }
   int CL = cl_env;
   if ((p.n_tile * 128 / 16) % CL != 0 || CL < 1) CL = 1;          // each slice must be whole 16-byte units
   if (CL != 1 && CL != 2 && CL != 4) CL = 1;
+  // two sub-tiles per CTA (half the weight stream per row) whenever that still leaves about a CTA per SM
+  int MT = 1;
+  if (CL == 1 && !want_tl) {
+    const int64_t ctas2 = mg_cdiv(p.T, 2 * BM) * g.n_tiles;
+    const int want = algo == MG_ALGO_TILE128 ? 1 : (algo == MG_ALGO_TILE256 ? 2 : (ctx->tune_mt ? ctx->tune_mt : mt_env));
+    // heuristic (scratch/conv_bench.py on R-MG-34): sharing the weight stages pays off for narrow column tiles with a long K
+    // loop (224 -> 64 at 14x14: 59 -> 44 us); wide tiles lose more to the shallower weight ring and the lower CTA count
+    const bool heur2 = p.n_tile <= 64 && g.n_chunks >= 3 && ctas2 * 10 >= (int64_t)ctx->num_sms * 8;
+    MT = (want == 1 || want == 2) ? want : (heur2 ? 2 : 1);
+  }
+  p.HL = BM * MT + 2 * p.Wp + 2;
+  p.halo_bytes = mg_round_up(p.HL * 128, 1024);
+  int cols = 32;
+  while (cols < MT * p.n_tile) cols <<= 1;
+  p.tmem_cols = cols;
+  int budget_kb;
+  if (MT == 1) {
+    // measured on R-MG-34 (scratch/conv_bench.py): narrow tiles are bound by per-CTA latency chains and want
+    // four resident CTAs (54 KB each, one halo buffer); N >= 192 tiles prefer two CTAs with a deeper ring
+    budget_kb = p.n_tile >= 192 ? 108 : 54;
+  } else {
+    // TMEM allows 512 / cols CTAs per SM; at most three, so that the weight ring is at least four stages deep
+    const int ctas = std::max(1, std::min(512 / cols, 3));
+    budget_kb = ctas == 1 ? 200 : (ctas == 2 ? 108 : 71);
+  }
+  if (budget_env > 0) budget_kb = budget_env;
+  // two halo buffers when several chunks follow each other and the budget allows, else one
+  const int min_ring = MT == 1 ? 2 : 3;
+  p.n_abuf = (g.n_chunks > 1 && 2 * p.halo_bytes + min_ring * b_stage <= budget_kb * 1024) ? 2 : 1;
+  int S = (budget_kb * 1024 - p.n_abuf * p.halo_bytes) / b_stage;
+  S = std::max(2, std::min(S, MAX_STAGES));
+  p.stages = S; p.lag = 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    const int mx = 227 * 1024 - 8 * 1024;
+    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    attr_set = true;
+  }
   const int smem = p.n_abuf * p.halo_bytes + S * b_stage + 1024;
-  dim3 grid((unsigned)mg_round_up((int)mg_cdiv(p.T, BM), CL), (unsigned)g.n_tiles);   // padding CTAs see only invalid slots
-  static int want_tl = -1;
-  if (want_tl < 0) { const char* e = getenv("MGCONV_TIMELINE"); want_tl = e ? atoi(e) : 0; }
+  MG_REQUIRE(ctx, smem <= 227 * 1024 - 8 * 1024, MG_ERR_UNSUPPORTED, "halo conv: %d bytes of shared memory", smem);
+  dim3 grid((unsigned)mg_round_up((int)mg_cdiv(p.T, BM * MT), CL), (unsigned)g.n_tiles);   // padding CTAs see only invalid slots
   p.timeline = nullptr;
   if (want_tl) {   // debug: dump per-CTA phase stamps of this launch to $MGCONV_TIMELINE_FILE after it ran
     static long long* d_tl = nullptr; static size_t cap = 0;
@@ -938,7 +1042,7 @@ static int launch_halo(mg_ctx* ctx, UParams& p, const Geometry& g) {
     if (cap < need) { if (d_tl) cudaFree(d_tl); cudaMalloc(&d_tl, need * sizeof(long long)); cap = need; }
     cudaMemsetAsync(d_tl, 0, need * sizeof(long long), ctx->stream);
     p.timeline = d_tl;
-    umma_conv_halo_kernel<1><<<grid, H_THREADS, smem, ctx->stream>>>(p);
+    umma_conv_halo_kernel<1, 1><<<grid, H_THREADS, smem, ctx->stream>>>(p);
     cudaStreamSynchronize(ctx->stream);
     std::vector<long long> h(need);
     cudaMemcpy(h.data(), d_tl, need * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -950,61 +1054,81 @@ static int launch_halo(mg_ctx* ctx, UParams& p, const Geometry& g) {
     return MG_OK;
   }
   if (CL == 1) {
-    MG_CUDA(ctx, mg_launch_pdl(umma_conv_halo_kernel<1>, grid, dim3(H_THREADS), (size_t)smem, ctx->stream, p));
+    if (MT == 2) MG_CUDA(ctx, mg_launch_pdl(umma_conv_halo_kernel<1, 2>, grid, dim3(H_THREADS), (size_t)smem, ctx->stream, p));
+    else MG_CUDA(ctx, mg_launch_pdl(umma_conv_halo_kernel<1, 1>, grid, dim3(H_THREADS), (size_t)smem, ctx->stream, p));
   } else {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = dim3(H_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    if (CL == 2) MG_CUDA(ctx, cudaLaunchKernelEx(&cfg, umma_conv_halo_kernel<2>, p));
-    else MG_CUDA(ctx, cudaLaunchKernelEx(&cfg, umma_conv_halo_kernel<4>, p));
+    if (CL == 2) MG_CUDA(ctx, cudaLaunchKernelEx(&cfg, umma_conv_halo_kernel<2, 1>, p));
+    else MG_CUDA(ctx, cudaLaunchKernelEx(&cfg, umma_conv_halo_kernel<4, 1>, p));
   }
   MG_CHECK_LAUNCH(ctx);
   ctx->tc_launches++;
   return MG_OK;
 }
 
-static int launch_halo_persistent(mg_ctx* ctx, UParams& p, const Geometry& g) {
+// shared-memory plan of the persistent kernel, or false when the weights do not fit / the launch is too small to pay off
+struct PersistPlan { int n_abuf, smem, tmem_cols, grid; };
+static bool persist_plan(const mg_ctx* ctx, const mg_conv_desc* d, const Geometry& g, int Nimg, int algo, PersistPlan* pl) {
+  static int on = -1, min_tiles_per_sm = -1;
+  if (on < 0) { const char* e = getenv("MGCONV_PERSIST"); on = e ? atoi(e) : 1; }
+  if (min_tiles_per_sm < 0) { const char* e = getenv("MGCONV_PERSIST_MIN_TILES"); min_tiles_per_sm = e ? atoi(e) : 4; }
+  if (algo == MG_ALGO_TILE128 || algo == MG_ALGO_TILE256) return false;
+  const bool forced = algo == MG_ALGO_RESIDENT || ctx->tune_persist == 1;
+  if (!forced && (ctx->tune_persist == 2 || !on)) return false;
+  if (!g.halo || g.n_tiles != 1) return false;
+  const int Wp = d->W + 1, Hp = d->H + 1;
+  const int HL = BM + 2 * Wp + 2;
+  const int halo_bytes = mg_round_up(HL * 128, 1024);
+  const int64_t m_tiles = mg_cdiv((int64_t)Nimg * Hp * Wp, BM);
+  if (!forced && m_tiles < (int64_t)min_tiles_per_sm * ctx->num_sms) return false;
+  // heuristic (scratch/conv_bench.py on R-MG-34): pays off when a tile is a single chunk (the loaders then run a whole
+  // tile ahead of the tensor core); two-chunk tiles are left to the autotuner
+  if (!forced && g.n_chunks > 1) return false;
+  const int b_bytes = g.n_chunks * 9 * g.n_tile * 128;
+  const int tail = 9 * g.n_tile * 4;                       // bias tile + statistics slots
+  const int budget = 232448 - 9 * 1024 - 1024;             // 227 KB per CTA minus static shared memory and alignment slack
+  const int room = budget - b_bytes - tail;
+  int n_abuf = room / halo_bytes;
+  if (n_abuf < 2) return false;
+  n_abuf = std::min(n_abuf, std::min(P_MAX_ABUF, 2 * g.n_chunks + 1));
+  int cols = 32;
+  while (cols < 2 * g.n_tile) cols <<= 1;                  // two accumulators
+  if (cols > 512) return false;
+  pl->n_abuf = n_abuf; pl->smem = n_abuf * halo_bytes + b_bytes + tail + 1024; pl->tmem_cols = cols;
+  pl->grid = (int)std::min<int64_t>(m_tiles, ctx->num_sms);
+  return true;
+}
+
+static int launch_halo_persistent(mg_ctx* ctx, UParams& p, const Geometry& g, const PersistPlan& pl) {
   p.Wp = p.W + 1; p.Hp = p.H + 1;
   p.T = (int64_t)p.Nimg * p.Hp * p.Wp;
   p.HL = BM + 2 * p.Wp + 2;
   p.n_chunks = g.n_chunks;
   p.halo_bytes = mg_round_up(p.HL * 128, 1024);
-  p.m_tiles = (int)mg_cdiv(p.T, BM); p.n_ntiles = g.n_tiles; p.n_items = p.m_tiles * p.n_ntiles;
-  const int b_stage = p.n_tile * 128;
-  int cols = 32;
-  while (cols < 2 * p.n_tile) cols <<= 1;            // two accumulators
-  p.tmem_cols = cols;
-  // one persistent CTA per SM (two when both accumulators and the rings of two CTAs fit)
-  static int cps_env = -1;
-  if (cps_env < 0) { const char* e = getenv("MGCONV_PERSIST_CTAS"); cps_env = e ? atoi(e) : 0; }
-  int cps = cps_env > 0 ? cps_env : (cols <= 256 ? 2 : 1);
-  const int budget = (cps == 1 ? 200 : 104) * 1024;
-  p.n_abuf = std::max(2, std::min(P_MAX_ABUF, (budget / 2) / p.halo_bytes));
-  int S = (budget - p.n_abuf * p.halo_bytes) / b_stage;
-  while (S < 3 && p.n_abuf > 2) { --p.n_abuf; S = (budget - p.n_abuf * p.halo_bytes) / b_stage; }
-  S = std::max(2, std::min(S, MAX_STAGES));
-  p.stages = S; p.lag = 1;
+  p.m_tiles = (int)mg_cdiv(p.T, BM); p.n_ntiles = 1; p.n_items = p.m_tiles;
+  p.tmem_cols = pl.tmem_cols;
+  p.n_abuf = pl.n_abuf;
+  p.stages = 0; p.lag = 1;
   static bool attr_set = false;
   if (!attr_set) {
-    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 12 * 1024));
+    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 9 * 1024));
     attr_set = true;
   }
-  const int smem = p.n_abuf * p.halo_bytes + S * b_stage + 1024;
-  const int grid = std::min(p.n_items, ctx->num_sms * cps);
   p.timeline = nullptr;
-  MG_CUDA(ctx, mg_launch_pdl(umma_conv_halo_persistent_kernel, dim3(grid), dim3(P_THREADS), (size_t)smem, ctx->stream, p));
+  MG_CUDA(ctx, mg_launch_pdl(umma_conv_halo_persistent_kernel, dim3(pl.grid), dim3(P_THREADS), (size_t)pl.smem, ctx->stream, p));
   MG_CHECK_LAUNCH(ctx);
   ctx->tc_launches++;
   return MG_OK;
 }
 
-static bool persist_on() {
+static bool fused_stats_on() {
   static int on = -1;
-  if (on < 0) { const char* e = getenv("MGCONV_PERSIST"); on = e ? atoi(e) : 0; }
+  if (on < 0) { const char* e = getenv("MGCONV_FUSED_STATS"); on = e ? atoi(e) : 1; }
   return on != 0;
 }
 
@@ -1036,7 +1160,7 @@ size_t umma_packed_bytes(const mg_conv_desc* d, int transposed) {
   return (size_t)g.n_tiles * g.n_stages * g.n_tile * 128;
 }
 
-int umma_pack_weights(mg_ctx* ctx, const mg_conv_desc* d, const float* w, void* wpack, int transposed) {
+static PackParams make_pack_params(const mg_conv_desc* d, const float* w, void* wpack, int transposed, int64_t* total) {
   Geometry g = geometry(d, transposed);
   PackParams p;
   memset(&p, 0, sizeof(p));
@@ -1050,9 +1174,62 @@ int umma_pack_weights(mg_ctx* ctx, const mg_conv_desc* d, const float* w, void* 
   p.Ccat = c;
   p.kv_per_tap = g.kv_per_tap; p.nkv = g.nkv; p.n_stages = g.n_stages; p.n_tile = g.n_tile; p.n_tiles = g.n_tiles;
   p.n_rows_valid = g.n_rows; p.halo = g.halo;
-  const int64_t total = (int64_t)g.n_tiles * g.n_tile * g.n_stages * KV_PER_STAGE;
+  *total = (int64_t)g.n_tiles * g.n_tile * g.n_stages * KV_PER_STAGE;
+  return p;
+}
+
+int umma_pack_weights(mg_ctx* ctx, const mg_conv_desc* d, const float* w, void* wpack, int transposed) {
+  int64_t total = 0;
+  PackParams p = make_pack_params(d, w, wpack, transposed, &total);
   mg_launch_pdl(pack_weights_kernel, dim3((unsigned)mg_cdiv(total, 256)), dim3(256), 0, ctx->stream, p);
   MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+// The job table lives in device memory owned by the context and is re-uploaded only when its contents change
+// (plans are static: one upload, then every step is a single launch -- and nothing but that launch is seen by a
+// CUDA-graph capture of the step).
+int umma_pack_weights_batched(mg_ctx* ctx, int n, const mg_conv_desc* const* descs, const float* const* w, void* const* wpack,
+                              const int32_t* transposed) {
+  static_assert(sizeof(PackParams) % sizeof(int) == 0, "PackParams is copied as ints");
+  std::vector<PackParams> jobs((size_t)n);
+  std::vector<int> blk((size_t)n + 1);
+  int64_t nb = 0;
+  for (int j = 0; j < n; ++j) {
+    MG_REQUIRE(ctx, descs[j] && w[j] && wpack[j], MG_ERR_INVALID_ARG, "pack_weights_batched: job %d has a null pointer", j);
+    int64_t total = 0;
+    jobs[j] = make_pack_params(descs[j], w[j], wpack[j], transposed[j], &total);
+    blk[j] = (int)nb;
+    nb += mg_cdiv(total, 256);
+    MG_REQUIRE(ctx, nb < ((int64_t)1 << 31), MG_ERR_UNSUPPORTED, "pack_weights_batched: too many blocks");
+  }
+  blk[n] = (int)nb;
+  const size_t jb = (size_t)n * sizeof(PackParams), bb = ((size_t)n + 1) * sizeof(int), bytes = jb + bb;
+  std::vector<uint8_t> image(bytes);
+  memcpy(image.data(), jobs.data(), jb);
+  memcpy(image.data() + jb, blk.data(), bb);
+  if (ctx->pack_bytes != bytes || !ctx->pack_host || memcmp(ctx->pack_host, image.data(), bytes) != 0) {
+    if (ctx->pack_cap < bytes) {
+      MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      if (ctx->pack_dev) cudaFree(ctx->pack_dev);
+      free(ctx->pack_host);
+      ctx->pack_dev = nullptr; ctx->pack_host = nullptr; ctx->pack_cap = 0; ctx->pack_bytes = 0;
+      MG_CUDA(ctx, cudaMalloc(&ctx->pack_dev, bytes));
+      ctx->pack_host = malloc(bytes);
+      MG_REQUIRE(ctx, ctx->pack_host != nullptr, MG_ERR_INVALID_ARG, "pack_weights_batched: out of host memory");
+      ctx->pack_cap = bytes;
+    }
+    memcpy(ctx->pack_host, image.data(), bytes);
+    ctx->pack_bytes = bytes;
+    // pageable source: staged by the driver before the call returns, ordered on the stream after earlier readers
+    MG_CUDA(ctx, cudaMemcpyAsync(ctx->pack_dev, ctx->pack_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  const PackParams* djobs = (const PackParams*)ctx->pack_dev;
+  const int* dblk = (const int*)((const uint8_t*)ctx->pack_dev + jb);
+  if (nb > 0) {
+    MG_CUDA(ctx, mg_launch_pdl(pack_weights_batched_kernel, dim3((unsigned)nb), dim3(256), 0, ctx->stream, djobs, dblk, n));
+    MG_CHECK_LAUNCH(ctx);
+  }
   return MG_OK;
 }
 
@@ -1078,9 +1255,14 @@ int umma_conv_forward(mg_ctx* ctx, const mg_conv_desc* d, const void* wpack, con
   p.kv_per_tap = g.kv_per_tap; p.nkv = g.nkv; p.n_stages = g.n_stages; p.n_tile = g.n_tile;
   p.wpack = (const uint8_t*)wpack; p.bias = bias; p.c_bias = d->Cout;
   p.y = (__nv_bfloat16*)y->data; p.y_pitch = y->Cp; p.c_valid = y->Cp;
-  int rc = g.halo ? (persist_on() ? launch_halo_persistent(ctx, p, g) : launch_halo(ctx, p, g)) : launch(ctx, p, g.n_tiles);
+  // the halo kernel reduces the BatchNorm statistics in its epilogue; the other kernels are followed by the statistics pass
+  const bool fused_stats = bn_sums && g.halo && fused_stats_on();
+  if (fused_stats) { p.stats = bn_sums; p.c_stats = d->Cout; }
+  PersistPlan pl;
+  int rc = g.halo ? (persist_plan(ctx, d, g, p.Nimg, d->algo_fwd, &pl) ? launch_halo_persistent(ctx, p, g, pl) : launch_halo(ctx, p, g, d->algo_fwd))
+                  : launch(ctx, p, g.n_tiles);
   if (rc) return rc;
-  if (bn_sums) return mg_bn_stats(ctx, y, bn_sums);
+  if (bn_sums && !fused_stats) return mg_bn_stats(ctx, y, bn_sums);
   return MG_OK;
 }
 
@@ -1099,6 +1281,8 @@ int umma_conv_backward_data(mg_ctx* ctx, const mg_conv_desc* d, const void* wpac
   p.wpack = (const uint8_t*)wpack_t; p.bias = nullptr;
   p.y = (__nv_bfloat16*)dcat->data; p.y_pitch = dcat->Cp; p.c_valid = dcat->Cp;
   MG_REQUIRE(ctx, dcat->Cp == g.n_rows, MG_ERR_SHAPE, "dgrad: dcat.Cp %d != %d", dcat->Cp, g.n_rows);
-  return g.halo ? (persist_on() ? launch_halo_persistent(ctx, p, g) : launch_halo(ctx, p, g)) : launch(ctx, p, g.n_tiles);
+  PersistPlan pl;
+  return g.halo ? (persist_plan(ctx, d, g, p.Nimg, d->algo_bwd_data, &pl) ? launch_halo_persistent(ctx, p, g, pl) : launch_halo(ctx, p, g, d->algo_bwd_data))
+                : launch(ctx, p, g.n_tiles);
 }
 

@@ -61,6 +61,14 @@ class Engine:
         self.gscale = 1.0
         self.bytes = 0
         self.on_param_done = None
+        # fp64 BatchNorm sums of the whole plan live in two arenas (forward: sum y, sum y^2; backward: sum d, sum d*y),
+        # each zeroed by ONE memset per pass instead of one per convolution
+        self._sums = {"fwd": [torch.zeros(1 << 17, dtype=torch.float64, device=self.device), 0],
+                      "bwd": [torch.zeros(1 << 17, dtype=torch.float64, device=self.device), 0]}
+        self._pack_cache = None
+        # per-layer choice of the 3x3 kernel variant by timing (cudnn.benchmark of the reference); MGCONV_AUTOTUNE=0 keeps the heuristics
+        self.autotune = os.environ.get("MGCONV_AUTOTUNE", "1") != "0"
+        self._tuned_fwd = self._tuned_bwd = False
         for m in model.listModules():
             for _, w, _ in m.own_parameters():
                 if w.device != self.device:
@@ -93,17 +101,51 @@ class Engine:
         self.bytes += t.numel() * t.element_size()
         return t
 
+    def alloc_sums(self, n, which):
+        arena = self._sums[which]
+        n8 = (n + 7) // 8 * 8
+        if arena[1] + n8 > arena[0].numel():
+            raise ffi.MGError("BatchNorm statistics arena exhausted")
+        v = arena[0][arena[1]:arena[1] + n]
+        arena[1] += n8
+        return v
+
+    def zero_sums(self, which):
+        arena = self._sums[which]
+        if arena[1]:
+            self.ctx.call("mg_memset_zero", ffi.ptr(arena[0]), arena[1] * 8)
+
     def param_done(self, mod):
         if self.on_param_done is not None:
             self.on_param_done(mod)
+
+    def _report_tuning(self, field):
+        if os.environ.get("MGCONV_VERBOSE"):
+            import collections
+            names = {0: "heuristic", 1: "tile128", 2: "tile256", 3: "resident"}
+            cnt = collections.Counter((o.H, o.CcatP, o.Cout, names[getattr(o.desc, field)]) for o in self.conv_ops if o._tunable())
+            print(f"[mgconv] autotune {field}: " + ", ".join(f"{h}x{h} {ci}->{co}: {a} x{n}" for (h, ci, co, a), n in sorted(cnt.items())), flush=True)
 
     def _bind_stream(self):
         self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
 
     # ---- execution ------------------------------------------------------------------------
     def pack_weights(self):
-        for o in self.conv_ops:
-            o.pack(self)
+        """fp32 master weights -> bf16 operand images of every convolution, one launch for the whole plan"""
+        import ctypes as C
+        jobs = [j for o in self.conv_ops for j in o.pack_jobs()]
+        if not jobs:
+            return
+        key = tuple((id(d), w.data_ptr(), wp.data_ptr(), t) for d, w, wp, t in jobs)
+        if self._pack_cache is None or self._pack_cache[0] != key:
+            n = len(jobs)
+            descs = (C.POINTER(ffi.mg_conv_desc) * n)(*[C.pointer(d) for d, _, _, _ in jobs])
+            ws = (C.c_void_p * n)(*[w.data_ptr() for _, w, _, _ in jobs])
+            wps = (C.c_void_p * n)(*[wp.data_ptr() for _, _, wp, _ in jobs])
+            tr = (C.c_int32 * n)(*[t for _, _, _, t in jobs])
+            self._pack_cache = (key, n, descs, ws, wps, tr)
+        _, n, descs, ws, wps, tr = self._pack_cache
+        self.ctx.call("mg_conv_pack_weights_batched", n, descs, ws, wps, tr)
 
     def forward(self, input, training=True):
         self._bind_stream()
@@ -111,6 +153,12 @@ class Engine:
         for op, t in zip(self.input_ops, _flatten(input)):
             op.src = t.contiguous().float()
         self.pack_weights()
+        if self.autotune and not self._tuned_fwd and self.use_packed and not torch.cuda.is_current_stream_capturing():
+            self._tuned_fwd = True
+            for o in self.conv_ops:
+                o.tune_fwd(self)
+            self._report_tuning("algo_fwd")
+        self.zero_sums("fwd")
         for o in self.plan.ops:
             o.fwd(self)
         return self._results(self.out_struct)
@@ -133,6 +181,12 @@ class Engine:
         self.gscale = float(scale)
         for op, g in zip(_flatten(self.out_struct), _flatten(gradOutput)):
             op.grad_out = g.contiguous().float()
+        if self.autotune and not self._tuned_bwd and self.use_packed and not torch.cuda.is_current_stream_capturing():
+            self._tuned_bwd = True
+            for o in self.conv_ops:
+                o.tune_bwd(self)
+            self._report_tuning("algo_bwd_data")
+        self.zero_sums("bwd")
         for o in reversed(self.plan.ops):
             o.bwd(self)
         gi = [op.grad_nchw for op in self.input_ops]

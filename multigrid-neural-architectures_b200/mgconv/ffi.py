@@ -13,6 +13,8 @@ MG_MAX_SRC = 8
 MG_F32, MG_BF16 = 0, 1
 MG_SEG_SAME, MG_SEG_POOL, MG_SEG_UP, MG_SRC_POOL3 = 0, 1, 2, 3
 MG_IMPL_AUTO, MG_IMPL_SIMT, MG_IMPL_TCGEN05 = 0, 1, 2
+MG_TUNE_HALO_SUBTILES, MG_TUNE_PERSISTENT = 0, 1
+MG_ALGO_AUTO, MG_ALGO_TILE128, MG_ALGO_TILE256, MG_ALGO_RESIDENT = 0, 1, 2, 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MGCONV_LIB", os.path.join(_HERE, "libmgconv.so"))
@@ -30,11 +32,17 @@ class mg_grid(C.Structure):
 class mg_conv_desc(C.Structure):
     _fields_ = [("n_seg", C.c_int32), ("seg", mg_grid * MG_MAX_SEG), ("seg_mode", C.c_int32 * MG_MAX_SEG),
                 ("ksize", C.c_int32), ("stride", C.c_int32), ("pad", C.c_int32), ("Cout", C.c_int32),
-                ("H", C.c_int32), ("W", C.c_int32)]
+                ("H", C.c_int32), ("W", C.c_int32), ("algo_fwd", C.c_int32), ("algo_bwd_data", C.c_int32)]
 
 
 class mg_grad_src(C.Structure):
     _fields_ = [("g", mg_grid), ("c_offset", C.c_int32), ("mode", C.c_int32), ("aux", C.c_void_p)]
+
+
+class mg_bn_fused(C.Structure):
+    _fields_ = [("sums", C.c_void_p), ("count", C.c_int64), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("eps", C.c_float), ("momentum", C.c_float),
+                ("training", C.c_int32), ("save_mean", C.c_void_p), ("save_invstd", C.c_void_p)]
 
 
 def _load():
@@ -58,6 +66,7 @@ SIGNATURES = {
     "mg_ctx_set_stream": (_I, [_P, _P]),
     "mg_ctx_set_impl": (_I, [_P, _I]),
     "mg_ctx_sync": (_I, [_P]),
+    "mg_ctx_set_tuning": (_I, [_P, _I, _I]),
     "mg_last_error": (C.c_char_p, [_P]),
     "mg_version": (_I, []),
     "mg_ctx_launch_count": (_I, [_P, C.POINTER(_I64)]),
@@ -71,6 +80,8 @@ SIGNATURES = {
     "mg_conv_forward": (_I, [_P, _D, _P, _P, _P, _G, _P]),
     "mg_bn_finalize": (_I, [_P, _P, _I64, C.c_int32, C.c_int32, _P, _P, _P, _P, _F, _F, _I, _P, _P, _P, _P]),
     "mg_residual_forward": (_I, [_P, _G, _G, _I, _G, _G]),
+    "mg_bn_residual_forward": (_I, [_P, _G, C.POINTER(mg_bn_fused), _G, _I, _G, _G]),
+    "mg_conv_pack_weights_batched": (_I, [_P, C.c_int32, C.POINTER(_D), C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int32)]),
     "mg_bn_stats": (_I, [_P, _G, _P]),
     "mg_memset_zero": (_I, [_P, _P, _SZ]),
     "mg_pool_forward": (_I, [_P, _G, _G, C.c_int32, _P]),
@@ -132,6 +143,9 @@ class Context:
 
     def set_impl(self, impl):
         self.call("mg_ctx_set_impl", int(impl))
+
+    def set_tuning(self, knob, value):
+        self.call("mg_ctx_set_tuning", int(knob), int(value))
 
     def sync(self):
         self.call("mg_ctx_sync")

@@ -11,7 +11,7 @@ import ctypes as C
 import torch
 
 from . import ffi
-from .ffi import mg_grid, mg_conv_desc, mg_grad_src, ptr, MG_SEG_SAME, MG_SEG_POOL, MG_SEG_UP, MG_SRC_POOL3, MG_MAX_SRC
+from .ffi import mg_grid, mg_conv_desc, mg_grad_src, mg_bn_fused, ptr, MG_SEG_SAME, MG_SEG_POOL, MG_SEG_UP, MG_SRC_POOL3, MG_MAX_SRC
 
 
 def cpad(c):
@@ -181,7 +181,7 @@ class ConvOp(Op):
         self.y.buf = E.alloc(self.y.shape())
         self.yg = self.y.grid()
         if self.want_stats:
-            self.sums = E.alloc((2 * self.Cout,), torch.float64)
+            self.sums = E.alloc_sums(2 * self.Cout, "fwd")
         self.wpack = self.wpack_t = None
         nb = ffi.lib.mg_conv_packed_bytes(C.byref(d), 0) if E.use_packed else 0
         if nb:
@@ -195,9 +195,48 @@ class ConvOp(Op):
         if self.wpack_t is not None:
             E.ctx.call("mg_conv_pack_weights", C.byref(self.desc), ptr(self.mod.weight), ptr(self.wpack_t), 1)
 
+    def pack_jobs(self):
+        """(desc, weight, packed image, transposed) of every operand image this convolution needs"""
+        jobs = []
+        if self.wpack is not None:
+            jobs.append((self.desc, self.mod.weight, self.wpack, 0))
+        if self.wpack_t is not None:
+            jobs.append((self.desc, self.mod.weight, self.wpack_t, 1))
+        return jobs
+
+    def _tunable(self):
+        return self.wpack is not None and self.k == 3 and self.stride == 1 and self.pad == 1 and 7 <= self.W <= 63
+
+    def _pick(self, E, field, run):
+        """time the kernel variants of one direction on this layer's own buffers and keep the fastest
+        (cudnn.benchmark = true of the reference, models/ilsvrc/rnmg.lua:230-231)"""
+        best, best_t = 0, None
+        for algo in (ffi.MG_ALGO_TILE128, ffi.MG_ALGO_TILE256, ffi.MG_ALGO_RESIDENT):
+            setattr(self.desc, field, algo)
+            run()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                run()
+            e1.record()
+            e1.synchronize()
+            t = e0.elapsed_time(e1)
+            if best_t is None or t < best_t * 0.97:   # a later variant must win by 3 % (timer noise)
+                best, best_t = algo, t
+        setattr(self.desc, field, best)
+        return best
+
+    def tune_fwd(self, E):
+        if self._tunable():
+            self._pick(E, "algo_fwd", lambda: self.fwd(E))
+
+    def tune_bwd(self, E):
+        if self._tunable() and self.needs_dgrad and self.wpack_t is not None:
+            g = self.y.G
+            self._pick(E, "algo_bwd_data", lambda: E.ctx.call("mg_conv_backward_data", C.byref(self.desc), ptr(self.mod.weight),
+                                                              ptr(self.wpack_t), C.byref(g), C.byref(self.dcat_g)))
+
     def fwd(self, E):
-        if self.sums is not None:
-            E.ctx.call("mg_memset_zero", ptr(self.sums), self.sums.numel() * 8)
         E.ctx.call("mg_conv_forward", C.byref(self.desc), ptr(self.mod.weight), ptr(self.wpack), ptr(self.mod.bias),
                    C.byref(self.yg), ptr(self.sums))
 
@@ -253,14 +292,15 @@ class UpConvOp(Op):
         self.y.buf = E.alloc(self.y.shape())
         self.gi, self.yg = self.inp.grid(), self.y.grid()
         if self.want_stats:
-            self.sums = E.alloc((2 * self.Cout,), torch.float64)
+            self.sums = E.alloc_sums(2 * self.Cout, "fwd")
 
     def pack(self, E):
         pass
 
+    def pack_jobs(self):
+        return []
+
     def fwd(self, E):
-        if self.sums is not None:
-            E.ctx.call("mg_memset_zero", ptr(self.sums), self.sums.numel() * 8)
         E.ctx.call("mg_upconv2x2_forward", C.byref(self.gi), ptr(self.mod.weight), ptr(self.mod.bias), C.byref(self.yg), ptr(self.sums))
 
     def setup_bwd(self, E):
@@ -311,22 +351,39 @@ class ApplyOp(Op):
         else:
             self.zg = y.grid()
         self.count = y.N * y.H * y.W
+        self.bnf = None   # mg_bn_fused, built on first use (parameter storage may be re-homed by getParameters())
+
+    def _bn_struct(self, E):
+        bn = self.bn
+        key = (bn.weight.data_ptr(), bn.bias.data_ptr(), bn.running_mean.data_ptr(), bn.running_var.data_ptr(),
+               bool(E.training), E.bn_sync, float(bn.eps), float(bn.momentum))
+        if self.bnf is None or self.bnf_key != key:
+            f = mg_bn_fused()
+            f.sums = self.conv.sums.data_ptr()
+            f.count = self.count * (max(1, E.bn_sync) if E.training else 1)
+            f.gamma, f.beta = bn.weight.data_ptr(), bn.bias.data_ptr()
+            f.running_mean, f.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+            f.eps, f.momentum, f.training = bn.eps, bn.momentum, int(E.training)
+            f.save_mean, f.save_invstd = self.mean.data_ptr(), self.invstd.data_ptr()
+            self.bnf, self.bnf_key = f, key
+        return self.bnf
 
     def fwd(self, E):
         bn = self.bn
+        rg = C.byref(self.rg) if self.rg is not None else None
+        pg = C.byref(self.pg) if self.pg is not None else None
         if bn is not None:
             if E.bn_sync and E.training:   # cross-replica statistics: sum (sum y, sum y^2) over the ranks
                 E.ctx.call("mg_allreduce_inline", ptr(self.conv.sums), self.conv.sums.numel(), 1)
-            E.ctx.call("mg_bn_finalize", ptr(self.conv.sums), self.count * (max(1, E.bn_sync) if E.training else 1), self.out.C, self.out.Cp, ptr(bn.weight), ptr(bn.bias),
-                       ptr(bn.running_mean), ptr(bn.running_var), bn.eps, bn.momentum, int(E.training),
-                       ptr(self.scale), ptr(self.shift), ptr(self.mean), ptr(self.invstd))
-        E.ctx.call("mg_residual_forward", C.byref(self.zg), C.byref(self.rg) if self.rg is not None else None,
-                   int(self.relu), C.byref(self.og), C.byref(self.pg) if self.pg is not None else None)
+            # SpatialBatchNormalization finalisation + CAddTable + ReLU + pooled companion in one pass
+            E.ctx.call("mg_bn_residual_forward", C.byref(self.zg), C.byref(self._bn_struct(E)), rg, int(self.relu), C.byref(self.og), pg)
+        else:
+            E.ctx.call("mg_residual_forward", C.byref(self.zg), rg, int(self.relu), C.byref(self.og), pg)
 
     def setup_bwd(self, E):
         t, y = self.out, self.conv.y
         self.pc = plan_companion_grad(E, t, self.pooled)
-        self.dsums = E.alloc((2 * t.C,), torch.float64) if self.bn is not None else None
+        self.dsums = E.alloc_sums(2 * t.C, "bwd") if self.bn is not None else None
         self.comb = Combine(E, t, relu_mask=self.relu, bn_x=y if self.bn is not None else None, sums=self.dsums,
                             private=self.bn is not None)
         D = self.comb.buf
@@ -345,8 +402,6 @@ class ApplyOp(Op):
     def bwd(self, E):
         if self.pc is not None:
             self.pc.run()
-        if self.dsums is not None:
-            E.ctx.call("mg_memset_zero", ptr(self.dsums), self.dsums.numel() * 8)
         self.comb.run()
         bn = self.bn
         if bn is not None:

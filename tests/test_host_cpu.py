@@ -57,7 +57,7 @@ def test_ctx_create_fails_loudly_without_gpu():
 def test_struct_layout_matches_header():
     from mgconv import ffi
     assert ctypes.sizeof(ffi.mg_grid) == 48
-    assert ctypes.sizeof(ffi.mg_conv_desc) == 8 + 6 * 48 + 6 * 4 + 6 * 4
+    assert ctypes.sizeof(ffi.mg_conv_desc) == 8 + 6 * 48 + 6 * 4 + 6 * 4 + 2 * 4
     assert ctypes.sizeof(ffi.mg_grad_src) == 64
 
 

@@ -199,10 +199,22 @@ EDGE_CASES = [  # N, [(C, mode 's'|'u')], H, W, Cout, k -- shapes that take the 
 ]
 
 
+EDGE_CASES += [
+    (9, [(40, "s"), (24, "u")], 8, 12, 48, 3),    # two chunks, ragged last 256-slot tile (9 * 9 * 13 = 1053 slots)
+    (4, [(136, "s")], 14, 14, 136, 3),            # three chunks with a ragged tail, N tile 144
+]
+# kernel-selection overrides: automatic, two sub-tiles per CTA, persistent weight-resident kernel
+TUNINGS = [(0, 0), (2, 2), (1, 1)]
+
+
+@pytest.mark.parametrize("tuning", TUNINGS, ids=["auto", "subtiles2", "persistent"])
 @pytest.mark.parametrize("case", EDGE_CASES, ids=[f"case{i}" for i in range(len(EDGE_CASES))])
-def test_conv_edge_shapes_tcgen05(case):
-    """forward / dgrad / wgrad of the bf16 tensor-core path on ragged, tiny, wide and multi-tile shapes"""
+def test_conv_edge_shapes_tcgen05(case, tuning):
+    """forward / dgrad / wgrad of the bf16 tensor-core path on ragged, tiny, wide and multi-tile shapes,
+    under each variant of the 3x3 kernel (mg_ctx_set_tuning)"""
     ctx = ffi.Context(0, torch.cuda.current_stream().cuda_stream, ffi.MG_BF16)
+    ctx.set_tuning(ffi.MG_TUNE_HALO_SUBTILES, tuning[0])
+    ctx.set_tuning(ffi.MG_TUNE_PERSISTENT, tuning[1])
     N, segs, H, W, Cout, k = case
     pad = 0 if k == 1 else 1
     xs, grids, modes = [], [], []
@@ -229,6 +241,7 @@ def test_conv_edge_shapes_tcgen05(case):
     assert max_rel(gy.nchw(), y_ref) <= tol
     assert not gy.pad_channels().any()
     assert np.allclose(sums.cpu().numpy()[:Cout] / (N * H * W), y_ref.mean(axis=(0, 2, 3)), atol=tol * np.abs(y_ref).max())
+    assert np.allclose(sums.cpu().numpy()[Cout:] / (N * H * W), (y_ref ** 2).mean(axis=(0, 2, 3)), rtol=4 * tol, atol=tol)
     g = rnd(N, Cout, H, W)
     gcat_ref, gw_ref, gb_ref = O.conv_backward(cat, wgt, g, 1, pad)
     gg = Grid(ffi.MG_BF16, N, Cout, H, W, g)
@@ -326,6 +339,47 @@ def test_conv_shape_errors_are_reported_not_fatal(ctx):
         ctx.call("mg_conv_forward", C.byref(d), ptr(w), None, None, C.byref(y.g()), None)
 
 
+def test_persistent_weight_resident_kernel_block1_shape():
+    """R-MG-34 block-1 shapes (96 -> 64 at 56x56, enough slot tiles to take the persistent weight-resident kernel):
+    forward, its fused BatchNorm sums and dgrad against the CUDA-core implementation of the same entry points"""
+    ctx = ffi.Context(0, torch.cuda.current_stream().cuda_stream, ffi.MG_BF16)
+    for (N, H, cs, Cout) in [(32, 56, (64, 32), 64), (112, 28, (64, 32, 16), 32)]:
+        grids = [Grid(ffi.MG_BF16, N, cs[0], H, H)] + [Grid(ffi.MG_BF16, N, c, H, H) for c in cs[1:-1]] + [Grid(ffi.MG_BF16, N, cs[-1], H // 2, H // 2)]
+        modes = [MG_SEG_SAME] * (len(cs) - 1) + [MG_SEG_UP]
+        for g_ in grids:
+            g_.t[..., :g_.C].normal_()
+        d = conv_desc(grids, modes, 3, 1, 1, Cout, H, H)
+        w = (torch.randn(Cout, sum(cs), 3, 3, device="cuda") * 0.05).to(torch.bfloat16).float()
+        b = (torch.randn(Cout, device="cuda") * 0.1).to(torch.bfloat16).float()
+        wp = torch.zeros(ffi.lib.mg_conv_packed_bytes(C.byref(d), 0), dtype=torch.uint8, device="cuda")
+        wpt = torch.zeros(ffi.lib.mg_conv_packed_bytes(C.byref(d), 1), dtype=torch.uint8, device="cuda")
+        ctx.call("mg_conv_pack_weights", C.byref(d), ptr(w), ptr(wp), 0)
+        ctx.call("mg_conv_pack_weights", C.byref(d), ptr(w), ptr(wpt), 1)
+        ys, dcs = [], []
+        gg = Grid(ffi.MG_BF16, N, Cout, H, H)
+        gg.t[..., :Cout].normal_()
+        cp = sum(x.Cp for x in grids)
+        for impl in (ffi.MG_IMPL_AUTO, ffi.MG_IMPL_SIMT):
+            ctx.set_impl(impl)
+            gy = Grid(ffi.MG_BF16, N, Cout, H, H)
+            sums = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
+            tc0 = ctx.tc_launches()
+            ctx.call("mg_conv_forward", C.byref(d), ptr(w), ptr(wp), ptr(b), C.byref(gy.g()), ptr(sums))
+            dcat = Grid(ffi.MG_BF16, N, cp, H, H, Cp=cp)
+            ctx.call("mg_conv_backward_data", C.byref(d), ptr(w), ptr(wpt), C.byref(gg.g()), C.byref(dcat.g()))
+            assert ctx.tc_launches() - tc0 == (2 if impl == ffi.MG_IMPL_AUTO else 0)
+            torch.cuda.synchronize()
+            ys.append(gy.t.float()); dcs.append(dcat.t.float())
+            if impl == ffi.MG_IMPL_AUTO:   # the sums are those of the stored bf16 values
+                yf = gy.t.double().reshape(-1, gy.Cp)[:, :Cout]
+                assert torch.allclose(sums[:Cout], yf.sum(0), rtol=1e-5, atol=1e-2)
+                assert torch.allclose(sums[Cout:], (yf * yf).sum(0), rtol=1e-5, atol=1e-2)
+        tol = TOL[ffi.MG_BF16]
+        assert float((ys[0] - ys[1]).abs().max() / ys[1].abs().max()) <= tol
+        assert float((dcs[0] - dcs[1]).abs().max() / dcs[1].abs().max()) <= tol
+    ctx.close()
+
+
 # ---------------------------------------------------------------- BatchNorm + epilogue
 @pytest.mark.parametrize("eps", [1e-5, 1e-3])
 def test_bn_finalize_apply_residual_and_backward(ctx, eps):
@@ -383,6 +437,77 @@ def test_bn_finalize_apply_residual_and_backward(ctx, eps):
              ptr(scale), ptr(shift), None, None)
     ctx.call("mg_residual_forward", C.byref(gx.g()), None, 0, C.byref(gout.g()), None)
     assert max_rel(gout.nchw(), O.bn_forward_eval(x, gamma, beta, rm, rv, eps)) <= tol
+
+
+@pytest.mark.parametrize("training", [1, 0])
+def test_bn_residual_forward_one_pass_equals_finalize_plus_residual(ctx, training):
+    """mg_bn_residual_forward (finalisation fused into the apply pass) == mg_bn_finalize + mg_residual_forward:
+    affine, saved statistics and running statistics to fp32 rounding (the two kernels contract their fp64
+    expressions differently), outputs to one bf16 ulp, pooled companion == 2x2 max of what was stored"""
+    N, Cc, H = 4, 20, 9     # Cp = 24 (pad channels), odd size (ceil-mode companion)
+    x = bf16_round(rnd(N, Cc, H, H) * 1.5 - 0.3)
+    gamma, beta = dev(rng.random(Cc) + 0.5), dev(rng.standard_normal(Cc) * 0.1)
+    sc = rnd(N, 8, H, H)
+    res = {}
+    for mode in ("split", "fused"):
+        rm, rv = dev(rng.standard_normal(Cc) * 0 + 0.25), dev(np.full(Cc, 1.5))
+        gx = Grid(ctx.dtype, N, Cc, H, H, x)
+        sums = torch.zeros(2 * Cc, dtype=torch.float64, device="cuda")
+        ctx.call("mg_bn_stats", C.byref(gx.g()), ptr(sums))
+        gx.scale, gx.shift = torch.zeros(gx.Cp, device="cuda"), torch.zeros(gx.Cp, device="cuda")
+        smean, sinv = torch.zeros(gx.Cp, device="cuda"), torch.zeros(gx.Cp, device="cuda")
+        gsc, gout, gpool = Grid(ctx.dtype, N, 8, H, H, sc), Grid(ctx.dtype, N, Cc, H, H), Grid(ctx.dtype, N, Cc, (H + 1) // 2, (H + 1) // 2)
+        if mode == "split":
+            ctx.call("mg_bn_finalize", ptr(sums), N * H * H, Cc, gx.Cp, ptr(gamma), ptr(beta), ptr(rm), ptr(rv), 1e-5, 0.1, training,
+                     ptr(gx.scale), ptr(gx.shift), ptr(smean), ptr(sinv))
+            ctx.call("mg_residual_forward", C.byref(gx.g()), C.byref(gsc.g()), 1, C.byref(gout.g()), C.byref(gpool.g()))
+        else:
+            f = ffi.mg_bn_fused()
+            f.sums, f.count, f.gamma, f.beta = sums.data_ptr(), N * H * H, gamma.data_ptr(), beta.data_ptr()
+            f.running_mean, f.running_var, f.eps, f.momentum, f.training = rm.data_ptr(), rv.data_ptr(), 1e-5, 0.1, training
+            f.save_mean, f.save_invstd = smean.data_ptr(), sinv.data_ptr()
+            ctx.call("mg_bn_residual_forward", C.byref(gx.g()), C.byref(f), C.byref(gsc.g()), 1, C.byref(gout.g()), C.byref(gpool.g()))
+        torch.cuda.synchronize()
+        res[mode] = [gout.nchw(), gpool.nchw(), gout.pad_channels()] + [t.cpu().numpy() for t in (gx.scale, gx.shift, smean, sinv, rm, rv)]
+    for a, b in zip(res["split"][3:], res["fused"][3:]):
+        assert np.allclose(a, b, rtol=1e-6, atol=1e-7)
+    for a, b in zip(res["split"][:2], res["fused"][:2]):
+        assert np.allclose(a, b, rtol=2.0 ** -7, atol=1e-6)
+    assert not res["fused"][2].any()
+    assert np.array_equal(res["fused"][1], O.maxpool_forward(res["fused"][0])[0])
+
+
+def test_pack_weights_batched_equals_per_conv_packing():
+    """one launch over a table of (conv, direction) jobs writes the same operand images as mg_conv_pack_weights"""
+    ctx = ffi.Context(0, torch.cuda.current_stream().cuda_stream, ffi.MG_BF16)
+    shapes = [(2, [(24, "s"), (8, "u")], 8, 8, 40, 3), (1, [(16, "s")], 5, 70, 8, 3), (2, [(72, "s"), (40, "s")], 4, 4, 24, 1),
+              (1, [(200, "s")], 7, 7, 300, 3)]
+    jobs, keep = [], []
+    for N, segs, H, W, Cout, k in shapes:
+        grids = [Grid(ffi.MG_BF16, N, c, H // 2 if m == "u" else H, W // 2 if m == "u" else W) for c, m in segs]
+        modes = [MG_SEG_UP if m == "u" else MG_SEG_SAME for _, m in segs]
+        d = conv_desc(grids, modes, k, 1, 0 if k == 1 else 1, Cout, H, W)
+        w = dev(rng.standard_normal((Cout, sum(c for c, _ in segs), k, k)))
+        keep.append((grids, d, w))
+        for tr in (0, 1):
+            nb = ffi.lib.mg_conv_packed_bytes(C.byref(d), tr)
+            one = torch.full((nb,), 0xAB, dtype=torch.uint8, device="cuda")
+            many = torch.full((nb,), 0xCD, dtype=torch.uint8, device="cuda")
+            ctx.call("mg_conv_pack_weights", C.byref(d), ptr(w), ptr(one), tr)
+            jobs.append((d, w, one, many, tr))
+    n = len(jobs)
+    descs = (C.POINTER(ffi.mg_conv_desc) * n)(*[C.pointer(j[0]) for j in jobs])
+    ws = (C.c_void_p * n)(*[j[1].data_ptr() for j in jobs])
+    outs = (C.c_void_p * n)(*[j[3].data_ptr() for j in jobs])
+    tr = (C.c_int32 * n)(*[j[4] for j in jobs])
+    l0 = ctx.launches()
+    for _ in range(2):   # the second call reuses the uploaded job table
+        ctx.call("mg_conv_pack_weights_batched", n, descs, ws, outs, tr)
+    assert ctx.launches() - l0 == 2
+    torch.cuda.synchronize()
+    for j in jobs:
+        assert torch.equal(j[2], j[3])
+    ctx.close()
 
 
 # ---------------------------------------------------------------- gradient routing (bit-exact paths)
