@@ -85,7 +85,9 @@ typedef struct {
 } mg_conv_desc;
 enum { MG_ALGO_AUTO = 0, MG_ALGO_TILE128 = 1, /* one 128-slot tile per CTA, several CTAs per SM */
        MG_ALGO_TILE256 = 2,                   /* two sub-tiles per CTA share every weight stage */
-       MG_ALGO_RESIDENT = 3 };                /* persistent CTAs, whole weight image resident in shared memory */
+       MG_ALGO_RESIDENT = 3,                  /* persistent CTAs, whole weight image resident in shared memory */
+       MG_ALGO_TILE128_DEEP = 4,              /* TILE128 with two CTAs per SM: two halo buffers, deeper weight ring */
+       MG_ALGO_TILE256_DEEP = 5 };            /* TILE256 with one CTA per SM: two halo buffers, deepest weight ring */
 
 typedef struct {
   mg_grid g;        /* gradient tensor of a consumer */
@@ -103,6 +105,15 @@ int mg_ctx_create(int device, void* cuda_stream, int dtype, mg_ctx** out);
 int mg_ctx_destroy(mg_ctx* ctx);
 int mg_ctx_set_stream(mg_ctx* ctx, void* cuda_stream);
 int mg_ctx_set_impl(mg_ctx* ctx, int impl);          /* mg_impl; AUTO = tcgen05 for bf16 */
+/* Lanes: the per-scale chains of an mg stage (conv -> BN -> ReLU on each grid, models/ilsvrc/rnmg.lua:91-159) are
+ * independent until the next ResampleConcat, so a host may enqueue them on different lanes and let small grids
+ * fill the tail of large ones.  Lane 0 is the stream given to mg_ctx_create / mg_ctx_set_stream, lanes 1..3 are
+ * side streams owned by the context (each with its own scratch).  mg_ctx_lane selects the lane for the calls
+ * that follow; ordering BETWEEN lanes is the host's job: mg_ctx_event_record(ev) marks a point on the current
+ * lane, mg_ctx_event_wait(ev) makes the current lane wait for it (cudaEventRecord / cudaStreamWaitEvent). */
+int mg_ctx_lane(mg_ctx* ctx, int lane);
+int mg_ctx_event_record(mg_ctx* ctx, int ev);
+int mg_ctx_event_wait(mg_ctx* ctx, int ev);
 int mg_ctx_sync(mg_ctx* ctx);                         /* cutorch.synchronize() equivalent */
 /* kernel-selection overrides for tests and tuning (the analogue of cudnn.benchmark / cudnn.fastest,
  * models/ilsvrc/rnmg.lua:230-231); value 0 = automatic choice */

@@ -78,6 +78,7 @@ int mg_ctx_create(int device, void* cuda_stream, int dtype, mg_ctx** out) {
   if (!c) return MG_ERR_INVALID_ARG;
   memset(c, 0, sizeof(*c));
   c->device = device; c->stream = (cudaStream_t)cuda_stream; c->dtype = dtype; c->impl = MG_IMPL_AUTO;
+  c->lane_stream[0] = c->stream;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return MG_ERR_CUDA; }
   if (prop.major != 10) {  // sm_100a only: no fallback architecture
@@ -116,13 +117,66 @@ int mg_ctx_destroy(mg_ctx* ctx) {
   }
   mg_comm_destroy(ctx);
   if (ctx->ws) cudaFree(ctx->ws);
+  for (int l = 1; l < MG_MAX_LANES; ++l) {
+    if (ctx->lane_ws[l]) cudaFree(ctx->lane_ws[l]);
+    if (ctx->lane_stream[l]) cudaStreamDestroy(ctx->lane_stream[l]);
+  }
+  for (int l = 0; l < MG_MAX_LANES; ++l) if (ctx->lane_ev[l]) cudaEventDestroy(ctx->lane_ev[l]);
+  for (int e = 0; e < ctx->n_events; ++e) cudaEventDestroy(ctx->events[e]);
+  free(ctx->events);
   if (ctx->pack_dev) cudaFree(ctx->pack_dev);
   free(ctx->pack_host);
   delete ctx;
   return MG_OK;
 }
 
-int mg_ctx_set_stream(mg_ctx* ctx, void* s) { if (!ctx) return MG_ERR_INVALID_ARG; ctx->stream = (cudaStream_t)s; return MG_OK; }
+int mg_ctx_set_stream(mg_ctx* ctx, void* s) {
+  if (!ctx) return MG_ERR_INVALID_ARG;
+  ctx->lane_stream[0] = (cudaStream_t)s;
+  ctx->stream = ctx->lane_stream[ctx->cur_lane];
+  return MG_OK;
+}
+
+int mg_ctx_lane(mg_ctx* ctx, int lane) {
+  if (!ctx) return MG_ERR_INVALID_ARG;
+  MG_REQUIRE(ctx, lane >= 0 && lane < MG_MAX_LANES, MG_ERR_INVALID_ARG, "lane %d out of range (0..%d)", lane, MG_MAX_LANES - 1);
+  if (lane && !ctx->lane_stream[lane]) {
+    MG_CUDA(ctx, cudaSetDevice(ctx->device));
+    MG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->lane_stream[lane], cudaStreamNonBlocking));
+  }
+  ctx->cur_lane = lane;
+  ctx->stream = ctx->lane_stream[lane];
+  return MG_OK;
+}
+
+static int ensure_events(mg_ctx* ctx, int ev) {
+  MG_REQUIRE(ctx, ev >= 0 && ev < (1 << 16), MG_ERR_INVALID_ARG, "event id %d", ev);
+  if (ev >= ctx->n_events) {
+    const int n = std::max(ev + 1, std::max(64, 2 * ctx->n_events));
+    cudaEvent_t* p = (cudaEvent_t*)realloc(ctx->events, (size_t)n * sizeof(cudaEvent_t));
+    MG_REQUIRE(ctx, p != nullptr, MG_ERR_INVALID_ARG, "events: out of memory");
+    ctx->events = p;
+    for (int e = ctx->n_events; e < n; ++e) MG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->events[e], cudaEventDisableTiming));
+    ctx->n_events = n;
+  }
+  return MG_OK;
+}
+
+int mg_ctx_event_record(mg_ctx* ctx, int ev) {
+  if (!ctx) return MG_ERR_INVALID_ARG;
+  int rc = ensure_events(ctx, ev);
+  if (rc) return rc;
+  MG_CUDA(ctx, cudaEventRecord(ctx->events[ev], ctx->stream));
+  return MG_OK;
+}
+
+int mg_ctx_event_wait(mg_ctx* ctx, int ev) {
+  if (!ctx) return MG_ERR_INVALID_ARG;
+  int rc = ensure_events(ctx, ev);
+  if (rc) return rc;
+  MG_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->events[ev], 0));
+  return MG_OK;
+}
 int mg_ctx_set_impl(mg_ctx* ctx, int impl) {
   if (!ctx || impl < 0 || impl > 2) return MG_ERR_INVALID_ARG;
   ctx->impl = impl; return MG_OK;
@@ -136,7 +190,8 @@ int mg_ctx_set_tuning(mg_ctx* ctx, int knob, int value) {
 int mg_ctx_sync(mg_ctx* ctx) {
   if (!ctx) return MG_ERR_INVALID_ARG;
   MG_CUDA(ctx, cudaSetDevice(ctx->device));
-  MG_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int l = 0; l < MG_MAX_LANES; ++l)
+    if (l == 0 || ctx->lane_stream[l]) MG_CUDA(ctx, cudaStreamSynchronize(ctx->lane_stream[l]));
   if (ctx->comm_stream) MG_CUDA(ctx, cudaStreamSynchronize(ctx->comm_stream));
   return MG_OK;
 }
@@ -261,9 +316,16 @@ int mg_comm_destroy(mg_ctx* ctx) {
 int mg_allreduce_launch(mg_ctx* ctx, void* buf, int64_t count, int is_double) {
   if (!ctx || !buf || count < 0) return MG_ERR_INVALID_ARG;
   MG_REQUIRE(ctx, ctx->nccl_comm != nullptr, MG_ERR_NCCL, "allreduce: communicator not initialised");
-  // comm stream waits for everything enqueued so far on the compute stream (the bucket's wgrads)
+  // comm stream waits for everything enqueued so far on the compute stream (the bucket's wgrads) -- on EVERY lane: the
+  // gradients of one bucket come from chains that ran on different lanes
   MG_CUDA(ctx, cudaEventRecord(ctx->ev_compute, ctx->stream));
   MG_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_compute, 0));
+  for (int l = 0; l < MG_MAX_LANES; ++l) {
+    if (l == ctx->cur_lane || (l && !ctx->lane_stream[l])) continue;
+    if (!ctx->lane_ev[l]) MG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lane_ev[l], cudaEventDisableTiming));
+    MG_CUDA(ctx, cudaEventRecord(ctx->lane_ev[l], ctx->lane_stream[l]));
+    MG_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->lane_ev[l], 0));
+  }
   const int ncclFloat32 = 7, ncclFloat64 = 8, ncclSum = 0;
   MG_NCCL(ctx, g_nccl.AllReduce(buf, buf, (size_t)count, is_double ? ncclFloat64 : ncclFloat32, ncclSum, ctx->nccl_comm, ctx->comm_stream));
   return MG_OK;

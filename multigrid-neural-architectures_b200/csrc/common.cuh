@@ -7,9 +7,10 @@
 #include <string.h>
 #include "../../include/mgconv.h"
 
+#define MG_MAX_LANES 4
 struct mg_ctx {
   int device;
-  cudaStream_t stream;
+  cudaStream_t stream;      // stream every call enqueues on = lane_stream[cur_lane]
   int dtype;        // mg_dtype
   int impl;         // mg_impl
   int num_sms;
@@ -27,6 +28,15 @@ struct mg_ctx {
   // scratch owned by the context (split-K partial sums of the weight gradient), grown on demand
   void* ws;
   size_t ws_bytes;
+  // lanes (mg_ctx_lane): lane 0 is the caller's stream, lanes 1.. are side streams owned by the context; each lane
+  // has its own scratch, so independent chains of a stage (one per scale) may run concurrently
+  cudaStream_t lane_stream[MG_MAX_LANES];
+  int cur_lane;
+  void* lane_ws[MG_MAX_LANES];        // scratch of lanes 1.. (lane 0 uses ws)
+  size_t lane_ws_bytes[MG_MAX_LANES];
+  cudaEvent_t* events;                // mg_ctx_event_record / mg_ctx_event_wait pool
+  int n_events;
+  cudaEvent_t lane_ev[MG_MAX_LANES];  // mg_allreduce_launch: completion of everything enqueued so far on each lane
   // kernel-selection overrides (mg_ctx_set_tuning); 0 = automatic
   int tune_mt;       // 128-slot sub-tiles per CTA of the halo convolution kernel (1 / 2)
   int tune_persist;  // weight-resident persistent kernel: 1 = whenever the weights fit, 2 = never
@@ -38,12 +48,14 @@ struct mg_ctx {
 
 // make the context workspace at least `bytes` large (one blocking cudaMalloc when it grows)
 static inline int mg_ctx_workspace(mg_ctx* ctx, size_t bytes, void** out) {
-  if (ctx->ws_bytes < bytes) {
-    if (ctx->ws) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->ws); ctx->ws = nullptr; ctx->ws_bytes = 0; }
-    if (cudaMalloc(&ctx->ws, bytes) != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "workspace: cudaMalloc(%zu) failed", bytes); return MG_ERR_CUDA; }
-    ctx->ws_bytes = bytes;
+  void** ws = ctx->cur_lane ? &ctx->lane_ws[ctx->cur_lane] : &ctx->ws;
+  size_t* cap = ctx->cur_lane ? &ctx->lane_ws_bytes[ctx->cur_lane] : &ctx->ws_bytes;
+  if (*cap < bytes) {
+    if (*ws) { cudaStreamSynchronize(ctx->stream); cudaFree(*ws); *ws = nullptr; *cap = 0; }
+    if (cudaMalloc(ws, bytes) != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "workspace: cudaMalloc(%zu) failed", bytes); return MG_ERR_CUDA; }
+    *cap = bytes;
   }
-  *out = ctx->ws;
+  *out = *ws;
   return MG_OK;
 }
 

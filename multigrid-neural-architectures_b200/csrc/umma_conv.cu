@@ -995,7 +995,8 @@ static int launch_halo(mg_ctx* ctx, UParams& p, const Geometry& g, int algo) {
   int MT = 1;
   if (CL == 1 && !want_tl) {
     const int64_t ctas2 = mg_cdiv(p.T, 2 * BM) * g.n_tiles;
-    const int want = algo == MG_ALGO_TILE128 ? 1 : (algo == MG_ALGO_TILE256 ? 2 : (ctx->tune_mt ? ctx->tune_mt : mt_env));
+    const int want = (algo == MG_ALGO_TILE128 || algo == MG_ALGO_TILE128_DEEP) ? 1
+                     : ((algo == MG_ALGO_TILE256 || algo == MG_ALGO_TILE256_DEEP) ? 2 : (ctx->tune_mt ? ctx->tune_mt : mt_env));
     // heuristic (scratch/conv_bench.py on R-MG-34): sharing the weight stages pays off for narrow column tiles with a long K
     // loop (224 -> 64 at 14x14: 59 -> 44 us); wide tiles lose more to the shallower weight ring and the lower CTA count
     const bool heur2 = p.n_tile <= 64 && g.n_chunks >= 3 && ctas2 * 10 >= (int64_t)ctx->num_sms * 8;
@@ -1016,6 +1017,9 @@ static int launch_halo(mg_ctx* ctx, UParams& p, const Geometry& g, int algo) {
     const int ctas = std::max(1, std::min(512 / cols, 3));
     budget_kb = ctas == 1 ? 200 : (ctas == 2 ? 108 : 71);
   }
+  // "deep" variants trade resident CTAs for two halo buffers and a longer weight ring (more bytes in flight per CTA)
+  if (algo == MG_ALGO_TILE128_DEEP) budget_kb = 108;
+  if (algo == MG_ALGO_TILE256_DEEP) budget_kb = 200;
   if (budget_env > 0) budget_kb = budget_env;
   // two halo buffers when several chunks follow each other and the budget allows, else one
   const int min_ring = MT == 1 ? 2 : 3;
@@ -1077,7 +1081,7 @@ static bool persist_plan(const mg_ctx* ctx, const mg_conv_desc* d, const Geometr
   static int on = -1, min_tiles_per_sm = -1;
   if (on < 0) { const char* e = getenv("MGCONV_PERSIST"); on = e ? atoi(e) : 1; }
   if (min_tiles_per_sm < 0) { const char* e = getenv("MGCONV_PERSIST_MIN_TILES"); min_tiles_per_sm = e ? atoi(e) : 4; }
-  if (algo == MG_ALGO_TILE128 || algo == MG_ALGO_TILE256) return false;
+  if (algo == MG_ALGO_TILE128 || algo == MG_ALGO_TILE256 || algo == MG_ALGO_TILE128_DEEP || algo == MG_ALGO_TILE256_DEEP) return false;
   const bool forced = algo == MG_ALGO_RESIDENT || ctx->tune_persist == 1;
   if (!forced && (ctx->tune_persist == 2 || !on)) return false;
   if (!g.halo || g.n_tiles != 1) return false;

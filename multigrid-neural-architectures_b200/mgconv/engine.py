@@ -7,7 +7,7 @@ dataparallel.py, torch.distributed rendezvous -- all arithmetic is libmgconv's.
 import os
 import torch
 
-from . import ffi, lower, ops
+from . import ffi, lower, ops, sched
 
 _PRECISION = {"bf16": (ffi.MG_BF16, torch.bfloat16), "fp32": (ffi.MG_F32, torch.float32)}
 _IMPL = {"auto": ffi.MG_IMPL_AUTO, "simt": ffi.MG_IMPL_SIMT, "tcgen05": ffi.MG_IMPL_TCGEN05}
@@ -69,6 +69,9 @@ class Engine:
         # per-layer choice of the 3x3 kernel variant by timing (cudnn.benchmark of the reference); MGCONV_AUTOTUNE=0 keeps the heuristics
         self.autotune = os.environ.get("MGCONV_AUTOTUNE", "1") != "0"
         self._tuned_fwd = self._tuned_bwd = False
+        # per-scale chains of a stage on separate CUDA streams (sched.py); MGCONV_LANES=1 runs the serial plan
+        self.n_lanes = max(1, min(4, int(os.environ.get("MGCONV_LANES", "3"))))
+        self._sched_fwd = self._sched_bwd = None
         for m in model.listModules():
             for _, w, _ in m.own_parameters():
                 if w.device != self.device:
@@ -122,9 +125,17 @@ class Engine:
     def _report_tuning(self, field):
         if os.environ.get("MGCONV_VERBOSE"):
             import collections
-            names = {0: "heuristic", 1: "tile128", 2: "tile256", 3: "resident"}
+            names = {0: "heuristic", 1: "tile128", 2: "tile256", 3: "resident", 4: "tile128deep", 5: "tile256deep"}
             cnt = collections.Counter((o.H, o.CcatP, o.Cout, names[getattr(o.desc, field)]) for o in self.conv_ops if o._tunable())
             print(f"[mgconv] autotune {field}: " + ", ".join(f"{h}x{h} {ci}->{co}: {a} x{n}" for (h, ci, co, a), n in sorted(cnt.items())), flush=True)
+
+    def _use_lanes(self):
+        # cross-replica BatchNorm issues NCCL calls from inside the chains: those must stay on one stream
+        return self.n_lanes > 1 and not self.bn_sync
+
+    def invalidate_schedules(self):
+        """buffer addresses the schedules were derived from changed (parameters re-homed by getParameters())"""
+        self._sched_fwd = self._sched_bwd = None
 
     def _bind_stream(self):
         self.ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
@@ -159,8 +170,13 @@ class Engine:
                 o.tune_fwd(self)
             self._report_tuning("algo_fwd")
         self.zero_sums("fwd")
-        for o in self.plan.ops:
-            o.fwd(self)
+        if self._use_lanes():
+            if self._sched_fwd is None:
+                self._sched_fwd = sched.Schedule(self.plan.ops, lambda o: o.io_fwd(), lambda o: o.fwd, self.n_lanes, 0)
+            self._sched_fwd.run(self)
+        else:
+            for o in self.plan.ops:
+                o.fwd(self)
         return self._results(self.out_struct)
 
     def _results(self, s):
@@ -187,8 +203,15 @@ class Engine:
                 o.tune_bwd(self)
             self._report_tuning("algo_bwd_data")
         self.zero_sums("bwd")
-        for o in reversed(self.plan.ops):
-            o.bwd(self)
+        if self._use_lanes():
+            if self._sched_bwd is None:
+                rops = list(reversed(self.plan.ops))
+                base = len(rops) + 16
+                self._sched_bwd = sched.Schedule(rops, lambda o: o.io_bwd(), lambda o: o.bwd, self.n_lanes, base)
+            self._sched_bwd.run(self)
+        else:
+            for o in reversed(self.plan.ops):
+                o.bwd(self)
         gi = [op.grad_nchw for op in self.input_ops]
         if all(g is None for g in gi):
             return None

@@ -14,7 +14,7 @@ MG_F32, MG_BF16 = 0, 1
 MG_SEG_SAME, MG_SEG_POOL, MG_SEG_UP, MG_SRC_POOL3 = 0, 1, 2, 3
 MG_IMPL_AUTO, MG_IMPL_SIMT, MG_IMPL_TCGEN05 = 0, 1, 2
 MG_TUNE_HALO_SUBTILES, MG_TUNE_PERSISTENT = 0, 1
-MG_ALGO_AUTO, MG_ALGO_TILE128, MG_ALGO_TILE256, MG_ALGO_RESIDENT = 0, 1, 2, 3
+MG_ALGO_AUTO, MG_ALGO_TILE128, MG_ALGO_TILE256, MG_ALGO_RESIDENT, MG_ALGO_TILE128_DEEP, MG_ALGO_TILE256_DEEP = 0, 1, 2, 3, 4, 5
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MGCONV_LIB", os.path.join(_HERE, "libmgconv.so"))
@@ -66,6 +66,9 @@ SIGNATURES = {
     "mg_ctx_set_stream": (_I, [_P, _P]),
     "mg_ctx_set_impl": (_I, [_P, _I]),
     "mg_ctx_sync": (_I, [_P]),
+    "mg_ctx_lane": (_I, [_P, _I]),
+    "mg_ctx_event_record": (_I, [_P, _I]),
+    "mg_ctx_event_wait": (_I, [_P, _I]),
     "mg_ctx_set_tuning": (_I, [_P, _I, _I]),
     "mg_last_error": (C.c_char_p, [_P]),
     "mg_version": (_I, []),

@@ -18,6 +18,21 @@ def cpad(c):
     return (c + 7) // 8 * 8
 
 
+def _k(x):
+    """dependency key of a device buffer: its base address (torch tensor, mg_grid, raw pointer or None)"""
+    if x is None:
+        return None
+    if isinstance(x, torch.Tensor):
+        return x.data_ptr()
+    if isinstance(x, mg_grid):
+        return x.data
+    return int(x)
+
+
+def _keys(*xs):
+    return [k for k in (_k(x) for x in xs) if k]
+
+
 class TSpec:
     """a materialised NHWC activation tensor of the plan"""
 
@@ -81,6 +96,13 @@ class Combine:
     def grid(self):
         return self.t.grid(self.buf)
 
+    def io(self):
+        """(buffers read, buffers written) by run()"""
+        if self.alias or self.noop:
+            return [], []
+        r = _keys(self.t.buf, self.bn_x, *[sr.buf for sr in self.t.srcs], *[sr.aux for sr in self.t.srcs])
+        return r, _keys(self.buf, self.sums)
+
     def run(self):
         if self.alias or self.noop:
             return
@@ -109,6 +131,19 @@ class Op:
     def setup_bwd(self, E): pass
     def fwd(self, E): pass
     def bwd(self, E): pass
+    # device buffers (reads, writes) of fwd() / bwd(): what the lane scheduler (sched.py) orders across streams.
+    # None = unknown: the op then runs on lane 0 behind a full join.
+    def io_fwd(self): return None
+    def io_bwd(self): return None
+    def size(self): return getattr(getattr(self, "out", None), "H", 0)
+
+
+def _merge(*ios):
+    r, w = [], []
+    for io in ios:
+        if io is not None:
+            r += io[0]; w += io[1]
+    return r, w
 
 
 class InputOp(Op):
@@ -122,6 +157,14 @@ class InputOp(Op):
     def setup_fwd(self, E):
         self.out.buf = E.alloc(self.out.shape())
         self.g = self.out.grid()
+
+    def io_fwd(self):
+        return _keys(self.src), _keys(self.out.buf)
+
+    def io_bwd(self):
+        if self.comb is None:
+            return [], []
+        return _merge(self.comb.io(), ([], _keys(self.grad_nchw)))
 
     def fwd(self, E):
         E.ctx.call("mg_import_nchw", ptr(self.src), C.byref(self.g))
@@ -148,6 +191,12 @@ class AvgPoolOp(Op):
     def setup_fwd(self, E):
         self.out.buf = E.alloc(self.out.shape())
         self.gi, self.go = self.inp.grid(), self.out.grid()
+
+    def io_fwd(self):
+        return _keys(self.inp.buf), _keys(self.out.buf)
+
+    def io_bwd(self):
+        return [], []
 
     def fwd(self, E):
         E.ctx.call("mg_avgpool_forward", C.byref(self.gi), self.r, C.byref(self.go))
@@ -211,7 +260,7 @@ class ConvOp(Op):
         """time the kernel variants of one direction on this layer's own buffers and keep the fastest
         (cudnn.benchmark = true of the reference, models/ilsvrc/rnmg.lua:230-231)"""
         best, best_t = 0, None
-        for algo in (ffi.MG_ALGO_TILE128, ffi.MG_ALGO_TILE256, ffi.MG_ALGO_RESIDENT):
+        for algo in (ffi.MG_ALGO_TILE128, ffi.MG_ALGO_TILE256, ffi.MG_ALGO_RESIDENT, ffi.MG_ALGO_TILE128_DEEP, ffi.MG_ALGO_TILE256_DEEP):
             setattr(self.desc, field, algo)
             run()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -235,6 +284,18 @@ class ConvOp(Op):
             g = self.y.G
             self._pick(E, "algo_bwd_data", lambda: E.ctx.call("mg_conv_backward_data", C.byref(self.desc), ptr(self.mod.weight),
                                                               ptr(self.wpack_t), C.byref(g), C.byref(self.dcat_g)))
+
+    def size(self):
+        return self.H
+
+    def io_fwd(self):
+        return _keys(*[t.buf for t, _ in self.segs]), _keys(self.y.buf, self.sums)
+
+    def io_bwd(self):
+        io = self.ycomb.io() if self.ycomb is not None else None
+        r = _keys(self.y.G, *[t.buf for t, _ in self.segs])
+        w = _keys(self.mod.gradWeight, self.mod.gradBias, self.dcat)
+        return _merge(io, (r, w))
 
     def fwd(self, E):
         E.ctx.call("mg_conv_forward", C.byref(self.desc), ptr(self.mod.weight), ptr(self.wpack), ptr(self.mod.bias),
@@ -299,6 +360,16 @@ class UpConvOp(Op):
 
     def pack_jobs(self):
         return []
+
+    def size(self):
+        return self.Ho
+
+    def io_fwd(self):
+        return _keys(self.inp.buf), _keys(self.y.buf, self.sums)
+
+    def io_bwd(self):
+        io = self.ycomb.io() if self.ycomb is not None else None
+        return _merge(io, (_keys(self.y.G, self.inp.buf), _keys(self.mod.gradWeight, self.mod.gradBias, self.dx)))
 
     def fwd(self, E):
         E.ctx.call("mg_upconv2x2_forward", C.byref(self.gi), ptr(self.mod.weight), ptr(self.mod.bias), C.byref(self.yg), ptr(self.sums))
@@ -368,6 +439,21 @@ class ApplyOp(Op):
             self.bnf, self.bnf_key = f, key
         return self.bnf
 
+    def io_fwd(self):
+        r = _keys(self.conv.y.buf, self.conv.sums, None if self.res is None else self.res.buf)
+        w = _keys(self.out.buf, None if self.pooled is None else self.pooled.buf)
+        if self.bn is not None:
+            w += _keys(self.scale, self.shift, self.mean, self.invstd)
+        return r, w
+
+    def io_bwd(self):
+        io = _merge(self.pc.io() if self.pc is not None else None, self.comb.io())
+        if self.bn is not None:
+            bn = self.bn
+            io = _merge(io, (_keys(self.conv.y.buf, self.comb.buf, self.dsums, self.mean, self.invstd),
+                             _keys(self.G, bn.gradWeight, bn.gradBias, self.conv.mod.gradBias)))
+        return io
+
     def fwd(self, E):
         bn = self.bn
         rg = C.byref(self.rg) if self.rg is not None else None
@@ -428,6 +514,12 @@ class PoolOp(Op):
         self.out.buf = E.alloc(self.out.shape())
         self.gi, self.go = self.inp.grid(), self.out.grid()
 
+    def io_fwd(self):
+        return _keys(self.inp.buf), _keys(self.out.buf)
+
+    def io_bwd(self):
+        return self.pc.io() if self.pc is not None else ([], [])
+
     def fwd(self, E):
         E.ctx.call("mg_pool_forward", C.byref(self.gi), C.byref(self.go), 0, None)
 
@@ -451,6 +543,12 @@ class Pool3Op(Op):
         self.gi, self.go = self.inp.grid(), self.out.grid()
         # arg-max codes for the backward routing (1 byte / element), bf16 mode only
         self.code = E.alloc(self.out.shape(), torch.uint8) if (E.dtype == ffi.MG_BF16 and self.inp.needs_grad) else None
+
+    def io_fwd(self):
+        return _keys(self.inp.buf), _keys(self.out.buf, self.code)
+
+    def io_bwd(self):
+        return self.comb.io() if self.comb is not None else ([], [])
 
     def fwd(self, E):
         E.ctx.call("mg_pool3s2_forward", C.byref(self.gi), C.byref(self.go), ptr(self.code))
@@ -479,6 +577,12 @@ class CatOp(Op):
         self.out.buf = E.alloc(self.out.shape())
         self.go = self.out.grid()
         self.gp = [p.grid() for p in self.parts]
+
+    def io_fwd(self):
+        return _keys(*[p.buf for p in self.parts]), _keys(self.out.buf)
+
+    def io_bwd(self):
+        return self.comb.io() if self.comb is not None else ([], [])
 
     def fwd(self, E):
         off = 0
@@ -513,6 +617,12 @@ class GlobalAvgOp(Op):
         self.out.buf = E.alloc(self.out.shape())
         self.gi, self.go = self.inp.grid(), self.out.grid()
 
+    def io_fwd(self):
+        return _keys(self.inp.buf), _keys(self.out.buf)
+
+    def io_bwd(self):
+        return _merge(self.comb.io(), (_keys(self.comb.buf), _keys(self.din)))
+
     def fwd(self, E):
         E.ctx.call("mg_global_avgpool_forward", C.byref(self.gi), C.byref(self.go))
 
@@ -535,6 +645,15 @@ class LogSoftMaxOp(Op):
         self.result = torch.empty((self.inp.N, self.inp.C), dtype=torch.float32, device=E.device)
         self.gi = self.inp.grid()
 
+    def size(self):
+        return self.inp.H
+
+    def io_fwd(self):
+        return _keys(self.inp.buf), _keys(self.result)
+
+    def io_bwd(self):
+        return _keys(self.result, self.grad_out), _keys(self.dl)
+
     def fwd(self, E):
         E.ctx.call("mg_logsoftmax_forward", C.byref(self.gi), ptr(self.result))
 
@@ -556,6 +675,15 @@ class SigmoidOp(Op):
         t = self.inp
         self.result = torch.empty((t.N, t.C, t.H, t.W), dtype=torch.float32, device=E.device)
         self.gi = t.grid()
+
+    def size(self):
+        return self.inp.H
+
+    def io_fwd(self):
+        return _keys(self.inp.buf), _keys(self.result)
+
+    def io_bwd(self):
+        return _keys(self.result, self.grad_out), _keys(self.dx)
 
     def fwd(self, E):
         E.ctx.call("mg_sigmoid_forward", C.byref(self.gi), ptr(self.result))
@@ -582,6 +710,15 @@ class ExportOp(Op):
         t = self.inp
         self.result = torch.empty((t.N, t.C, t.H, t.W), dtype=torch.float32, device=E.device)
         self.gi = t.grid()
+
+    def size(self):
+        return self.inp.H
+
+    def io_fwd(self):
+        return _keys(self.inp.buf), _keys(self.result)
+
+    def io_bwd(self):
+        return _keys(self.grad_out), _keys(self.dx)
 
     def fwd(self, E):
         E.ctx.call("mg_export_nchw", C.byref(self.gi), ptr(self.result))

@@ -204,10 +204,11 @@ EDGE_CASES += [
     (4, [(136, "s")], 14, 14, 136, 3),            # three chunks with a ragged tail, N tile 144
 ]
 # kernel-selection overrides: automatic, two sub-tiles per CTA, persistent weight-resident kernel
-TUNINGS = [(0, 0), (2, 2), (1, 1)]
+# (context sub-tile override, context persistent override, per-layer algo of the descriptor)
+TUNINGS = [(0, 0, 0), (2, 2, 0), (1, 1, 0), (0, 0, ffi.MG_ALGO_TILE128_DEEP), (0, 0, ffi.MG_ALGO_TILE256_DEEP), (0, 2, ffi.MG_ALGO_RESIDENT)]
 
 
-@pytest.mark.parametrize("tuning", TUNINGS, ids=["auto", "subtiles2", "persistent"])
+@pytest.mark.parametrize("tuning", TUNINGS, ids=["auto", "subtiles2", "persistent", "algo_tile128deep", "algo_tile256deep", "algo_resident"])
 @pytest.mark.parametrize("case", EDGE_CASES, ids=[f"case{i}" for i in range(len(EDGE_CASES))])
 def test_conv_edge_shapes_tcgen05(case, tuning):
     """forward / dgrad / wgrad of the bf16 tensor-core path on ragged, tiny, wide and multi-tile shapes,
@@ -227,6 +228,7 @@ def test_conv_edge_shapes_tcgen05(case, tuning):
     wgt = bf16_round(rng.standard_normal((Cout, cat.shape[1], k, k)) * 0.1)
     b = bf16_round(rng.standard_normal(Cout) * 0.1)
     d = conv_desc(grids, modes, k, 1, pad, Cout, H, W)
+    d.algo_fwd = d.algo_bwd_data = tuning[2]
     wd, bd = dev(wgt), dev(b)
     wp = torch.zeros(ffi.lib.mg_conv_packed_bytes(C.byref(d), 0), dtype=torch.uint8, device="cuda")
     wpt = torch.zeros(ffi.lib.mg_conv_packed_bytes(C.byref(d), 1), dtype=torch.uint8, device="cuda")
