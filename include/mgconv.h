@@ -196,6 +196,11 @@ int mg_pool_forward(mg_ctx* ctx, const mg_grid* in, mg_grid* out, int32_t c_offs
 int mg_copy_channels(mg_ctx* ctx, const mg_grid* in, mg_grid* out, int32_t c_offset);
 /* cudnn.SpatialAveragePooling(r,r,r,r) on NHWC (image pyramid, rnmg.lua:175-177) */
 int mg_avgpool_forward(mg_ctx* ctx, const mg_grid* in, int32_t r, mg_grid* out);
+/* im2col of the image-fed stem convolution cudnn.SpatialConvolution(3, C, 7,7, 2,2, 3,3) (rnmg.lua:180):
+ * col[n][oy][ox][ci*k*k + ky*k + kx] = in[n][oy*stride-pad+ky][ox*stride-pad+kx][ci].  The channel order is Torch's
+ * [Cout][Cin][kH][kW] weight layout flattened, so the stem becomes a 1x1 mg_conv over `col` that uses the module's
+ * weight / gradWeight storage unchanged (K = 147 real channels instead of 49 taps x 8 padded ones).  bf16 only. */
+int mg_im2col(mg_ctx* ctx, const mg_grid* in, int32_t ksize, int32_t stride, int32_t pad, mg_grid* col);
 /* SpatialMaxPooling(3,3,2,2,1,1) of the ImageNet stem (rnmg.lua:183) */
 int mg_pool3s2_forward(mg_ctx* ctx, const mg_grid* in, mg_grid* out, uint8_t* argmax_code /* nullable, bf16 mode */);
 /* SelectTable(1) -> AvgPool(HxW) -> View: out[n][c] fp32 (rnmg.lua:281-283) */

@@ -6,6 +6,7 @@
 #include <algorithm>
 
 // bf16 fast paths (elementwise_bf16.cu); each returns false when it does not apply
+bool bf16_im2col(mg_ctx*, const mg_grid* in, int k, int stride, int pad, mg_grid* col);
 bool bf16_apply(mg_ctx*, const mg_grid* z, const mg_grid* s, int relu, mg_grid* out, mg_grid* pooled, const mg_bn_fused* bn);
 bool bf16_bn_stats(mg_ctx*, const mg_grid* y, double* sums);
 bool bf16_combine(mg_ctx*, const mg_grid* x, int relu_mask, const mg_grid* bn_x, int n_src, const mg_grad_src* src, mg_grid* d, double* sums);
@@ -525,6 +526,17 @@ int mg_copy_channels(mg_ctx* ctx, const mg_grid* in, mg_grid* out, int32_t c_off
   MG_REQUIRE(ctx, out->H == in->H && out->W == in->W && out->N == in->N && c_offset + in->C <= out->Cp, MG_ERR_SHAPE, "copy_channels: shape");
   int64_t total = (int64_t)in->N * in->H * in->W * in->C;
   MG_DISPATCH(ctx, copy_channels_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>(make_view<T>(*in), (T*)out->data, out->Cp, c_offset););
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int mg_im2col(mg_ctx* ctx, const mg_grid* in, int32_t ksize, int32_t stride, int32_t pad, mg_grid* col) {
+  if (!ctx || !in || !col || !in->data || !col->data || ksize < 1 || stride < 1 || pad < 0) return MG_ERR_INVALID_ARG;
+  const int Ho = (in->H + 2 * pad - ksize) / stride + 1, Wo = (in->W + 2 * pad - ksize) / stride + 1;
+  MG_REQUIRE(ctx, col->N == in->N && col->H == Ho && col->W == Wo && col->C == in->C * ksize * ksize, MG_ERR_SHAPE,
+             "im2col: col is %dx%dx%d, expected %dx%dx%d", col->H, col->W, col->C, Ho, Wo, in->C * ksize * ksize);
+  MG_REQUIRE(ctx, ctx->dtype == MG_BF16, MG_ERR_UNSUPPORTED, "im2col: bf16 contexts only (the fp32 path convolves the image directly)");
+  MG_REQUIRE(ctx, bf16_im2col(ctx, in, ksize, stride, pad, col), MG_ERR_UNSUPPORTED, "im2col: pending affine or unaligned channel pitch");
   MG_CHECK_LAUNCH(ctx);
   return MG_OK;
 }

@@ -538,6 +538,39 @@ __global__ void __launch_bounds__(256) pool_vec_kernel(const bf16* __restrict__ 
   *reinterpret_cast<uint4*>(out + (((int64_t)n * Ho + oy) * Wo + ox) * o_cp + c_off + c0) = pack8(o);
 }
 
+// im2col of a k x k / stride s / pad p window over a narrow-channel image (the ImageNet stem: 7x7, stride 2, 3 channels):
+// col[n][oy][ox][ci*k*k + ky*k + kx] = in[n][oy*s - p + ky][ox*s - p + kx][ci] (0 outside), channel order = Torch's weight
+// layout [Cout][Cin][k][k] flattened, so the convolution becomes a 1x1 convolution over `col` with the SAME weight
+// and gradWeight storage.  One thread = 8 consecutive col channels (one 16-byte store); the 2-byte gathers hit L1.
+__global__ void __launch_bounds__(256) im2col_bf16_kernel(const bf16* __restrict__ in, int H, int W, int cp_in, int C, int k, int stride, int pad,
+                                                          bf16* __restrict__ col, int Ho, int Wo, int cp_col, int N) {
+  pdl_launch();
+  pdl_wait();
+  const int V = cp_col >> 3;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)N * Ho * Wo * V) return;
+  const int vc = (int)(i % V); int64_t q = i / V;
+  const int ox = (int)(q % Wo); q /= Wo;
+  const int oy = (int)(q % Ho); const int n = (int)(q / Ho);
+  const int kk = k * k, K = C * kk;
+  const bf16* img = in + (int64_t)n * H * W * cp_in;
+  const unsigned short* img16 = reinterpret_cast<const unsigned short*>(img);
+  uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = vc * 8 + e;
+    unsigned short v = 0;
+    if (c < K) {
+      const int ci = c / kk, tap = c - ci * kk;
+      const int ky = tap / k, kx = tap - ky * k;
+      const int y = oy * stride - pad + ky, x = ox * stride - pad + kx;
+      if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) v = __ldg(img16 + ((int64_t)y * W + x) * cp_in + ci);
+    }
+    w[e >> 1] |= (uint32_t)v << (16 * (e & 1));
+  }
+  *reinterpret_cast<uint4*>(col + i * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 static inline unsigned grid_for(int64_t threads) { return (unsigned)mg_cdiv(threads, 256); }
 // persistent-style grid for the reducing kernels: a few CTAs per SM, each thread loops
 static inline unsigned reduce_grid(const mg_ctx* ctx, int64_t items, int per_sm = 4) {
@@ -655,6 +688,14 @@ bool bf16_import_nchw(mg_ctx* ctx, const float* src, mg_grid* dst) {
   if (dst->Cp != 8) return false;
   const int64_t HW = (int64_t)dst->H * dst->W, total = HW * dst->N;
   import_nchw_c8_kernel<<<grid_for(total), 256, 0, ctx->stream>>>(src, (bf16*)dst->data, dst->C, HW, total);
+  return true;
+}
+
+bool bf16_im2col(mg_ctx* ctx, const mg_grid* in, int k, int stride, int pad, mg_grid* col) {
+  if (in->scale || col->Cp % 8) return false;
+  const int64_t total = (int64_t)in->N * col->H * col->W * (col->Cp / 8);
+  mg_launch_pdl(im2col_bf16_kernel, dim3(grid_for(total)), dim3(256), 0, ctx->stream, (const bf16*)in->data, in->H, in->W, in->Cp, in->C, k, stride,
+                pad, (bf16*)col->data, col->H, col->W, col->Cp, in->N);
   return true;
 }
 

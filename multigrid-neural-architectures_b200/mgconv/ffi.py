@@ -90,6 +90,7 @@ SIGNATURES = {
     "mg_pool_forward": (_I, [_P, _G, _G, C.c_int32, _P]),
     "mg_copy_channels": (_I, [_P, _G, _G, C.c_int32]),
     "mg_avgpool_forward": (_I, [_P, _G, C.c_int32, _G]),
+    "mg_im2col": (_I, [_P, _G, C.c_int32, C.c_int32, C.c_int32, _G]),
     "mg_pool3s2_forward": (_I, [_P, _G, _G, _P]),
     "mg_global_avgpool_forward": (_I, [_P, _G, _G]),
     "mg_global_avgpool_backward": (_I, [_P, _G, _G]),

@@ -8,6 +8,7 @@ tensor reads its consumers' gradient grids through the routing that consumer app
 is fixed -- ConcatTable's backward-sum (models/ilsvrc/rnmg.lua:53-82,106,140) without scatter.
 """
 import ctypes as C
+import os
 import torch
 
 from . import ffi
@@ -231,8 +232,28 @@ class ConvOp(Op):
         self.yg = self.y.grid()
         if self.want_stats:
             self.sums = E.alloc_sums(2 * self.Cout, "fwd")
+        # Image-fed strided stem (cudnn.SpatialConvolution(3, C, 7,7, 2,2, 3,3), ilsvrc/rnmg.lua:180) on the tensor-core
+        # path: im2col once, then a 1x1 convolution over the column tensor with the module's own weight storage
+        # ([Cout][3][7][7] flattened IS [Cout][147][1][1]); forward and weight gradient read K = 147 real channels
+        # instead of 49 taps x 8 padded ones.  Only when no gradient w.r.t. the image is wanted.  Opt-in (MGCONV_STEM_IM2COL=1):
+        # measured on R-MG-34 / B = 256 the conv entry points gain 0.45 ms but the 1.3 GB column tensor costs 1.4 ms.
+        t0 = self.segs[0][0]
+        self.col = None
+        if (E.use_packed and len(self.segs) == 1 and self.segs[0][1] == MG_SEG_SAME and self.stride > 1 and self.k > 1
+                and t0.C * self.k * self.k <= 512 and not t0.needs_grad and os.environ.get("MGCONV_STEM_IM2COL", "0") == "1"):
+            K = t0.C * self.k * self.k
+            Kp = cpad(K)
+            self.col = E.alloc((self.y.N, self.Ho, self.Wo, Kp))
+            self.col_g = mg_grid(self.col.data_ptr(), None, None, 0, self.y.N, self.Ho, self.Wo, K, Kp)
+            self.in_g = t0.grid()
+            d1 = mg_conv_desc()
+            d1.n_seg = 1
+            d1.seg[0] = self.col_g
+            d1.seg_mode[0] = MG_SEG_SAME
+            d1.ksize, d1.stride, d1.pad, d1.Cout, d1.H, d1.W = 1, 1, 0, self.Cout, self.Ho, self.Wo
+            self.desc_direct, self.desc = d, d1
         self.wpack = self.wpack_t = None
-        nb = ffi.lib.mg_conv_packed_bytes(C.byref(d), 0) if E.use_packed else 0
+        nb = ffi.lib.mg_conv_packed_bytes(C.byref(self.desc), 0) if E.use_packed else 0
         if nb:
             self.wpack = E.alloc((nb,), torch.uint8)
         self.Ccat = sum(t.C for t, _ in self.segs)
@@ -289,15 +310,17 @@ class ConvOp(Op):
         return self.H
 
     def io_fwd(self):
-        return _keys(*[t.buf for t, _ in self.segs]), _keys(self.y.buf, self.sums)
+        return _keys(*[t.buf for t, _ in self.segs]), _keys(self.y.buf, self.sums, self.col)
 
     def io_bwd(self):
         io = self.ycomb.io() if self.ycomb is not None else None
-        r = _keys(self.y.G, *[t.buf for t, _ in self.segs])
+        r = _keys(self.y.G, self.col, *[t.buf for t, _ in self.segs])
         w = _keys(self.mod.gradWeight, self.mod.gradBias, self.dcat)
         return _merge(io, (r, w))
 
     def fwd(self, E):
+        if self.col is not None:
+            E.ctx.call("mg_im2col", C.byref(self.in_g), self.k, self.stride, self.pad, C.byref(self.col_g))
         E.ctx.call("mg_conv_forward", C.byref(self.desc), ptr(self.mod.weight), ptr(self.wpack), ptr(self.mod.bias),
                    C.byref(self.yg), ptr(self.sums))
 

@@ -307,6 +307,49 @@ def test_stem_conv7x7_stride2(ctx, impl):
     ctx.set_impl(ffi.MG_IMPL_AUTO)
 
 
+@pytest.mark.parametrize("shape", [(2, 3, 20, 20, 16, 7, 2, 3), (3, 3, 15, 23, 40, 7, 2, 3), (2, 1, 9, 9, 8, 3, 2, 1)])
+def test_stem_im2col_then_1x1_conv_equals_strided_conv(shape):
+    """mg_im2col + a 1x1 mg_conv over the column tensor, with the [Cout][Cin][k][k] weight storage reinterpreted as
+    [Cout][Cin*k*k][1][1], is the strided stem convolution (ilsvrc/rnmg.lua:180): columns bit-exact against a numpy
+    gather, forward / gradWeight / gradBias against the oracle"""
+    N, Cin, H, W, Cout, k, stride, pad = shape
+    ctx = ffi.Context(0, torch.cuda.current_stream().cuda_stream, ffi.MG_BF16)
+    x = bf16_round(rnd(N, Cin, H, W))
+    w = bf16_round(rng.standard_normal((Cout, Cin, k, k)) * 0.1)
+    b = bf16_round(rng.standard_normal(Cout) * 0.1)
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    gx = Grid(ffi.MG_BF16, N, Cin, H, W, x)
+    K = Cin * k * k
+    col = Grid(ffi.MG_BF16, N, K, Ho, Wo)
+    col.t.fill_(7.0)                                   # every element, pad channels included, must be overwritten
+    ctx.call("mg_im2col", C.byref(gx.g()), k, stride, pad, C.byref(col.g()))
+    xp = np.pad(x, ((0, 0), (0, 0), (pad, pad), (pad, pad)))
+    ref = np.zeros((N, K, Ho, Wo))
+    for ci in range(Cin):
+        for ky in range(k):
+            for kx in range(k):
+                ref[:, ci * k * k + ky * k + kx] = xp[:, ci, ky:ky + stride * Ho:stride, kx:kx + stride * Wo:stride]
+    assert np.array_equal(col.nchw(), ref) and not col.pad_channels().any()
+    d = conv_desc([col], [MG_SEG_SAME], 1, 1, 0, Cout, Ho, Wo)
+    wd, bd = dev(w), dev(b)                            # same storage, read as [Cout][K][1][1]
+    wp = torch.zeros(ffi.lib.mg_conv_packed_bytes(C.byref(d), 0), dtype=torch.uint8, device="cuda")
+    ctx.call("mg_conv_pack_weights", C.byref(d), ptr(wd), ptr(wp), 0)
+    gy = Grid(ffi.MG_BF16, N, Cout, Ho, Wo)
+    tc0 = ctx.tc_launches()
+    ctx.call("mg_conv_forward", C.byref(d), ptr(wd), ptr(wp), ptr(bd), C.byref(gy.g()), None)
+    tol = TOL[ffi.MG_BF16]
+    assert max_rel(gy.nchw(), O.conv_forward(x, w, b, stride, pad)) <= tol
+    g = rnd(N, Cout, Ho, Wo)
+    _, gw_ref, gb_ref = O.conv_backward(x, w, g, stride, pad)
+    gg = Grid(ffi.MG_BF16, N, Cout, Ho, Wo, g)
+    dw, db = torch.zeros_like(wd), torch.zeros_like(bd)
+    ctx.call("mg_conv_backward_weight", C.byref(d), C.byref(gg.g()), ptr(dw), ptr(db), 1.0)
+    assert ctx.tc_launches() - tc0 == 2
+    torch.cuda.synchronize()
+    assert max_rel(dw.cpu().numpy(), gw_ref) <= tol and max_rel(db.cpu().numpy(), gb_ref) <= tol
+    ctx.close()
+
+
 def test_upconv2x2_forward_backward(ctx):
     """cudnn.SpatialFullConvolution(nIP, nOP, 2,2,2,2) of U-MG (models/mnist-cluttered/unmg.lua:35-41)"""
     N, Cin, Cout, H = 2, 12, 10, 5
