@@ -301,9 +301,15 @@ def main():
     conv_ms_step = serial["conv_ms_per_step"] if serial else inregion_ms
     ref_step_ms = serial["ms_per_step"] if serial else ms_per_step
     achieved = conv_flops_step / (conv_ms_step * 1e-3) / 1e12 if conv_ms_step else None
+    # DRAM bytes of the same launches from the committed ncu pass (profiles/): per step, like `achieved`
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r1g_conv_traffic.json")
+    if os.path.exists(tpath) and args.depth == 34 and Bsz == 256:
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj["dram_bytes_per_step"], "profiles/r1g_conv_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum over the conv launches of one step)"
     roofline = {"bound": "tensor", "kernel": "implicit-GEMM multigrid conv (fwd+dgrad+wgrad launches)",
                 "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": (achieved / tf_peak) if achieved else None,
-                "traffic": None, "peak_source": which, "conv_ms_per_step": conv_ms_step, "conv_launches_per_step": prof["conv_launches"] / args.steps,
+                "traffic": traffic, "traffic_unit": "bytes per step over the same launches", "traffic_source": traffic_src, "peak_source": which, "conv_ms_per_step": conv_ms_step, "conv_launches_per_step": prof["conv_launches"] / args.steps,
                 "share_of_step": (conv_ms_step / ref_step_ms) if conv_ms_step else None,
                 "algorithmic_flops_per_step": conv_flops_step,
                 "timing": ("CUDA events around every conv entry point; %d extra steps of the serial plan (lanes off, %.2f ms/step) right after the "

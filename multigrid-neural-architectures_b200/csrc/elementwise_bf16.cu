@@ -600,7 +600,13 @@ bool bf16_apply(mg_ctx* ctx, const mg_grid* z, const mg_grid* s, int relu, mg_gr
   p.N = z->N; p.H = z->H; p.W = z->W; p.C = z->C; p.Hp = (z->H + 1) / 2; p.Wp = (z->W + 1) / 2;
   if (out->Cp > 2048) return false;
   const int64_t total = (int64_t)p.N * p.Hp * p.Wp * (p.o_cp / 8);
-  mg_launch_pdl(apply_bf16_kernel, dim3(reduce_grid(ctx, total, 8)), dim3(256), bn ? 2 * z->Cp * sizeof(float) : 0, ctx->stream, p);
+  // one 2x2 block per thread up to 64 CTAs per SM, beyond that the threads loop (measured: few fat CTAs lose 10 % here --
+  // the pass has no reduction tail that would favour them)
+  const int lanes = 256 / (out->Cp / 8);
+  const int64_t nblocks = (int64_t)p.N * p.Hp * p.Wp;
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(mg_cdiv(nblocks, lanes), (int64_t)ctx->num_sms * 64));
+  (void)total;
+  mg_launch_pdl(apply_bf16_kernel, dim3(grid), dim3(256), bn ? 2 * z->Cp * sizeof(float) : 0, ctx->stream, p);
   return true;
 }
 

@@ -205,9 +205,17 @@ class Engine:
         self.zero_sums("bwd")
         if self._use_lanes():
             if self._sched_bwd is None:
-                rops = list(reversed(self.plan.ops))
-                base = len(rops) + 16
-                self._sched_bwd = sched.Schedule(rops, lambda o: o.io_bwd(), lambda o: o.bwd, self.n_lanes, base)
+                # a convolution's backward is two units: dgrad (the next stage waits for it) on the lane of its scale,
+                # wgrad (only the optimiser waits for it) on a background lane that fills whatever the chains leave idle
+                units = []
+                bg = self.n_lanes if (self.n_lanes < 4 and os.environ.get("MGCONV_WGRAD_LANE", "1") != "0") else None
+                for o in reversed(self.plan.ops):
+                    if isinstance(o, ops.ConvOp):
+                        units += [sched.Unit(io, run, o.size(), lane) for io, run, lane in o.bwd_units()]
+                    else:
+                        units.append(sched.Unit(o.io_bwd(), o.bwd, o.size()))
+                base = len(self.plan.ops) + 16
+                self._sched_bwd = sched.Schedule(units, lambda u: u.io, lambda u: u.run, self.n_lanes, base, background_lane=bg)
             self._sched_bwd.run(self)
         else:
             for o in reversed(self.plan.ops):

@@ -342,17 +342,31 @@ class ConvOp(Op):
             if nb:
                 self.wpack_t = E.alloc((nb,), torch.uint8)
 
-    def bwd(self, E):
+    def bwd_data(self, E):
+        """gradient of y from its consumers (plain convs), then dgrad: the part the rest of backward waits for"""
         if self.ycomb is not None:
             self.ycomb.run()
-        g = self.y.G
-        fused_bias = self.apply is not None and self.apply.bn is not None and not E.bn_sync   # done by mg_bn_backward
-        E.ctx.call("mg_conv_backward_weight", C.byref(self.desc), C.byref(g), ptr(self.mod.gradWeight),
-                   None if fused_bias else ptr(self.mod.gradBias), E.gscale)
         if self.needs_dgrad:
             E.ctx.call("mg_conv_backward_data", C.byref(self.desc), ptr(self.mod.weight), ptr(self.wpack_t),
-                       C.byref(g), C.byref(self.dcat_g))
+                       C.byref(self.y.G), C.byref(self.dcat_g))
+
+    def bwd_weight(self, E):
+        """accGradParameters: nothing but the optimiser (and the gradient all-reduce) waits for this"""
+        fused_bias = self.apply is not None and self.apply.bn is not None and not E.bn_sync   # done by mg_bn_backward
+        E.ctx.call("mg_conv_backward_weight", C.byref(self.desc), C.byref(self.y.G), ptr(self.mod.gradWeight),
+                   None if fused_bias else ptr(self.mod.gradBias), E.gscale)
         E.param_done(self.mod)
+
+    def bwd(self, E):
+        self.bwd_data(E)
+        self.bwd_weight(E)
+
+    def bwd_units(self):
+        """the two independently schedulable halves of bwd() for the lane scheduler: (io, run, fixed lane or None)"""
+        io_d = _merge(self.ycomb.io() if self.ycomb is not None else None,
+                      (_keys(self.y.G), _keys(self.dcat)) if self.needs_dgrad else ([], []))
+        io_w = (_keys(self.y.G, self.col, *[t.buf for t, _ in self.segs]), _keys(self.mod.gradWeight, self.mod.gradBias))
+        return [(io_d, self.bwd_data, None), (io_w, self.bwd_weight, "background")]
 
 
 class UpConvOp(Op):

@@ -13,9 +13,21 @@ ends with lane 0 waiting for all lanes, so nothing outside the pass ever sees a 
 """
 
 
+class Unit:
+    """a schedulable piece of an op: buffers (reads, writes), callable(E), spatial size, optional fixed lane"""
+
+    def __init__(self, io, run, size, lane=None):
+        self.io, self.run, self._size, self.lane = io, run, size, lane
+
+    def size(self):
+        return self._size
+
+
 class Schedule:
-    def __init__(self, ops, io_of, run_of, n_lanes, ev_base):
-        """ops in execution order; io_of(op) -> (reads, writes) keys or None; run_of(op) -> callable(E)"""
+    def __init__(self, ops, io_of, run_of, n_lanes, ev_base, background_lane=None):
+        """ops in execution order; io_of(op) -> (reads, writes) keys or None; run_of(op) -> callable(E).
+        Ops whose `lane` attribute is "background" (work nothing in the pass waits for, e.g. weight gradients) all
+        go to `background_lane`; everything else is spread over lanes 0..n_lanes-1 by spatial size."""
         sizes = sorted({op.size() for op in ops}, reverse=True)
         lane_of_size = {h: i % n_lanes for i, h in enumerate(sizes)}
         last_w, readers, synced = {}, {}, {}
@@ -33,6 +45,8 @@ class Schedule:
                 record.add(seq)
                 continue
             lane = lane_of_size[op.size()]
+            if getattr(op, "lane", None) == "background" and background_lane is not None:
+                lane = background_lane
             used.add(lane)
             r, w = io
             deps = set()
