@@ -369,11 +369,13 @@ __global__ void __launch_bounds__(H_THREADS, MT == 1 ? 4 : 3) umma_conv_halo_ker
       const int64_t t = t0 - p.Wp - 1 + h;
       uint32_t pix = 0xFFFFFFFFu, pup = 0;
       if (t >= 0 && t < p.T) {
-        const int n = (int)(t / slots_per_img); const int rem = (int)(t - (int64_t)n * slots_per_img);
-        const int yy = rem / p.Wp, xs = rem - yy * p.Wp;
-        if (yy < p.H && xs < p.W) {
-          pix = (uint32_t)(((size_t)n * p.H + yy) * p.W + xs);
-          pup = (uint32_t)(((size_t)n * Hs2 + (yy >> 1)) * Ws2 + (xs >> 1));
+        // T < 2^31 (halo_applies): 32-bit unsigned divisions (the 64-bit ones cost ~1k cycles of every CTA's prologue)
+        const uint32_t tu = (uint32_t)t;
+        const uint32_t n = tu / (uint32_t)slots_per_img, rem = tu - n * (uint32_t)slots_per_img;
+        const uint32_t yy = rem / (uint32_t)p.Wp, xs = rem - yy * (uint32_t)p.Wp;
+        if ((int)yy < p.H && (int)xs < p.W) {
+          pix = (n * p.H + yy) * p.W + xs;
+          pup = (n * Hs2 + (yy >> 1)) * Ws2 + (xs >> 1);
         }
       }
       s_pix[h] = pix; s_pup[h] = pup;

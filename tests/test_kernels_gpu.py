@@ -6,6 +6,7 @@ floating point within rel 1e-4 in fp32 mode and rel 2e-2 in bf16 (fp32 accumulat
 Inputs are rounded to bf16-representable values first, so both sides read identical numbers.
 """
 import ctypes as C
+import os
 import numpy as np
 import pytest
 import torch
@@ -553,6 +554,101 @@ def test_pack_weights_batched_equals_per_conv_packing():
     for j in jobs:
         assert torch.equal(j[2], j[3])
     ctx.close()
+
+
+# ---------------------------------------------------------------- committed golden vectors (tests/golden/)
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name", ["mgconv_3scale_k3.npz", "mgconv_3scale_k1.npz"])
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+def test_golden_mgconv(ctx, name, impl):
+    """multigrid convolution against the committed oracle vectors: forward, the gradient w.r.t. the concatenated input
+    routed back to the three grids (pool arg-max, identity, 2x2 block sum through mg_grad_combine), dW, dbias"""
+    if impl == "auto" and ctx.dtype != ffi.MG_BF16:
+        pytest.skip("tcgen05 path is bf16 only")
+    G = {k: v for k, v in np.load(os.path.join(GOLDEN, name)).items()}
+    f, s, c, w, b, g = (G[k].astype(np.float64) for k in ("finer", "same", "coarser", "weight", "bias", "grad_out"))
+    k = int(G["k"]); pad = 0 if k == 1 else 1
+    N, H, Cout = s.shape[0], s.shape[2], w.shape[0]
+    cs = (f.shape[1], s.shape[1], c.shape[1])
+    # arg-max of the pooling is bit-exact (indices are the only integer data of the path)
+    gf_, gs_, gc_ = Grid(ctx.dtype, N, cs[0], 2 * H, 2 * H, f), Grid(ctx.dtype, N, cs[1], H, H, s), Grid(ctx.dtype, N, cs[2], H // 2, H // 2, c)
+    gp = Grid(ctx.dtype, N, cs[0], H, H)
+    arg = torch.zeros((N, H, H, cs[0]), dtype=torch.int32, device="cuda")
+    ctx.call("mg_pool_forward", C.byref(gf_.g()), C.byref(gp.g()), 0, ptr(arg))
+    torch.cuda.synchronize()
+    assert np.array_equal(arg.permute(0, 3, 1, 2).cpu().numpy(), G["pool_argmax"])
+    ctx.set_impl(ffi.MG_IMPL_SIMT if impl == "simt" else ffi.MG_IMPL_AUTO)
+    d = conv_desc([gp, gs_, gc_], [MG_SEG_SAME, MG_SEG_SAME, MG_SEG_UP], k, 1, pad, Cout, H, H)
+    wd, bd = dev(w), dev(b)
+    wp = wpt = None
+    if impl == "auto":
+        wp = torch.zeros(ffi.lib.mg_conv_packed_bytes(C.byref(d), 0), dtype=torch.uint8, device="cuda")
+        wpt = torch.zeros(ffi.lib.mg_conv_packed_bytes(C.byref(d), 1), dtype=torch.uint8, device="cuda")
+        ctx.call("mg_conv_pack_weights", C.byref(d), ptr(wd), ptr(wp), 0)
+        ctx.call("mg_conv_pack_weights", C.byref(d), ptr(wd), ptr(wpt), 1)
+    gy = Grid(ctx.dtype, N, Cout, H, H)
+    ctx.call("mg_conv_forward", C.byref(d), ptr(wd), ptr(wp), ptr(bd), C.byref(gy.g()), None)
+    tol = TOL[ctx.dtype]
+    assert max_rel(gy.nchw(), G["y"]) <= tol
+    gg = Grid(ctx.dtype, N, Cout, H, H, g)
+    cps = [gp.Cp, gs_.Cp, gc_.Cp]
+    dcat = Grid(ctx.dtype, N, sum(cps), H, H, Cp=sum(cps))
+    ctx.call("mg_conv_backward_data", C.byref(d), ptr(wd), ptr(wpt), C.byref(gg.g()), C.byref(dcat.g()))
+    dw, db = torch.zeros_like(wd), torch.zeros_like(bd)
+    ctx.call("mg_conv_backward_weight", C.byref(d), C.byref(gg.g()), ptr(dw), ptr(db), 1.0)
+    torch.cuda.synchronize()
+    assert max_rel(dw.cpu().numpy(), G["grad_weight"]) <= tol and max_rel(db.cpu().numpy(), G["grad_bias"]) <= tol
+    # route dcat back to the three grids the way a plan does (gather form)
+    offs = [0, cps[0], cps[0] + cps[1]]
+    for grid, off, mode, key in ((gf_, offs[0], MG_SEG_POOL, "grad_finer"), (gs_, offs[1], MG_SEG_SAME, "grad_same"), (gc_, offs[2], MG_SEG_UP, "grad_coarser")):
+        src = (mg_grad_src * 1)()
+        src[0].g, src[0].c_offset, src[0].mode = dcat.g(), off, mode
+        out = Grid(ctx.dtype, grid.N, grid.C, grid.H, grid.W)
+        ctx.call("mg_grad_combine", C.byref(grid.g()), 0, None, 1, src, C.byref(out.g()), None)
+        assert max_rel(out.nchw(), G[key]) <= tol, key
+    ctx.set_impl(ffi.MG_IMPL_AUTO)
+
+
+@pytest.mark.parametrize("name", ["bn_shortcut_relu.npz", "bn_shortcut_relu_odd.npz"])
+def test_golden_bn_shortcut_relu(ctx, name):
+    """SpatialBatchNormalization (train) + zero-padded shortcut + ReLU + pooled companion and their backward against the
+    committed oracle vectors, through the one-pass entry points"""
+    G = {k: v for k, v in np.load(os.path.join(GOLDEN, name)).items()}
+    x, sc, go = (G[k].astype(np.float64) for k in ("x", "shortcut", "grad_out"))
+    N, Cc, H = x.shape[0], x.shape[1], x.shape[2]
+    Cs, eps = sc.shape[1], float(G["eps"])
+    gx = Grid(ctx.dtype, N, Cc, H, H, x)
+    sums = torch.zeros(2 * Cc, dtype=torch.float64, device="cuda")
+    ctx.call("mg_bn_stats", C.byref(gx.g()), ptr(sums))
+    gx.scale, gx.shift = torch.zeros(gx.Cp, device="cuda"), torch.zeros(gx.Cp, device="cuda")
+    smean, sinv = torch.zeros(gx.Cp, device="cuda"), torch.zeros(gx.Cp, device="cuda")
+    gam, bet, rm, rv = dev(G["gamma"]), dev(G["beta"]), dev(np.zeros(Cc)), dev(np.ones(Cc))
+    f = ffi.mg_bn_fused()
+    f.sums, f.count, f.gamma, f.beta = sums.data_ptr(), N * H * H, gam.data_ptr(), bet.data_ptr()
+    f.running_mean, f.running_var, f.eps, f.momentum, f.training = rm.data_ptr(), rv.data_ptr(), eps, 0.1, 1
+    f.save_mean, f.save_invstd = smean.data_ptr(), sinv.data_ptr()
+    gsc, gout, gpool = Grid(ctx.dtype, N, Cs, H, H, sc), Grid(ctx.dtype, N, Cc, H, H), Grid(ctx.dtype, N, Cc, (H + 1) // 2, (H + 1) // 2)
+    ctx.call("mg_bn_residual_forward", C.byref(gx.g()), C.byref(f), C.byref(gsc.g()), 1, C.byref(gout.g()), C.byref(gpool.g()))
+    tol = TOL[ctx.dtype]
+    out = gout.nchw()
+    assert max_rel(out, G["out"]) <= tol and max_rel(gpool.nchw(), G["pooled"]) <= tol
+    assert np.allclose(rm.cpu().numpy(), G["running_mean"], atol=1e-5) and np.allclose(rv.cpu().numpy(), G["running_var"], rtol=1e-4)
+    assert np.allclose(smean.cpu().numpy()[:Cc], G["save_mean"], atol=1e-5) and np.allclose(sinv.cpu().numpy()[:Cc], G["save_invstd"], rtol=1e-4)
+    ggo, gd, gres = Grid(ctx.dtype, N, Cc, H, H, go), Grid(ctx.dtype, N, Cc, H, H), Grid(ctx.dtype, N, Cc, H, H)
+    src = (mg_grad_src * 1)()
+    src[0].g, src[0].c_offset, src[0].mode = ggo.g(), 0, MG_SEG_SAME
+    dsums = torch.zeros(2 * Cc, dtype=torch.float64, device="cuda")
+    ctx.call("mg_grad_combine", C.byref(gout.g()), 1, C.byref(gx.g()), 1, src, C.byref(gd.g()), ptr(dsums))
+    assert max_rel(gd.nchw()[:, :Cs], G["grad_shortcut"]) <= tol
+    dgamma, dbeta, coef = torch.zeros(Cc, device="cuda"), torch.zeros(Cc, device="cuda"), torch.zeros(3 * gx.Cp, device="cuda")
+    xraw = Grid(ctx.dtype, N, Cc, H, H, x)
+    ctx.call("mg_bn_backward", C.byref(xraw.g()), C.byref(gd.g()), C.byref(gres.g()), ptr(dsums), N * H * H, ptr(gam), ptr(smean), ptr(sinv),
+             ptr(dgamma), ptr(dbeta), 1.0, ptr(coef), None)
+    torch.cuda.synchronize()
+    assert max_rel(gres.nchw(), G["grad_x"]) <= tol
+    assert max_rel(dgamma.cpu().numpy(), G["grad_gamma"]) <= tol and max_rel(dbeta.cpu().numpy(), G["grad_beta"]) <= tol
 
 
 # ---------------------------------------------------------------- gradient routing (bit-exact paths)

@@ -201,3 +201,25 @@ def test_mnist_builders_run():
     torch.manual_seed(0)
     assert B.mnist_prnmg(1, 1)(torch.randn(2, 1, 64, 64)).shape == (2, 1, 64, 64)
     assert B.mnist_unmg(10)(torch.randn(2, 1, 64, 64)).shape == (2, 10, 64, 64)
+
+
+def test_oracle_reproduces_golden_vectors():
+    """tests/golden/*.npz are this oracle's outputs on seeded inputs (the reference ships no fixtures):
+    recomputing them pins the oracle against silent drift"""
+    import importlib.util
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "make_golden.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    assert len(mk.CASES) >= 4
+    for name, fn in mk.CASES.items():
+        stored = np.load(os.path.join(here, name))
+        fresh = fn()
+        assert set(stored.files) == set(fresh)
+        for k in stored.files:
+            a, b = stored[k], np.asarray(fresh[k])
+            if a.dtype.kind in "iu":
+                assert np.array_equal(a, b), (name, k)
+            else:
+                assert np.allclose(a, b, rtol=1e-6, atol=1e-6), (name, k)
