@@ -21,11 +21,14 @@ SHAPES = {
     "b3g1": (14, [(256, "s"), (128, "u")], 256, 3),
     "b3g2": (7, [(256, "s"), (128, "s")], 128, 3),
     "b4": (7, [(512, "s")], 512, 3),
+    # ImageNet stem: cudnn.SpatialConvolution(3, 64, 7,7, 2,2, 3,3) on the 224x224 image (ilsvrc/rnmg.lua:180); (H, segs, Cout, k, stride, pad)
+    "stem": (224, [(3, "s")], 64, 7, 2, 3),
 }
 
 
 def run(name, N=256, iters=20, which=("fwd", "dgrad", "wgrad")):
-    H, segs, Cout, k = SHAPES[name]
+    H, segs, Cout, k = SHAPES[name][:4]
+    stride = SHAPES[name][4] if len(SHAPES[name]) > 4 else 1
     ctx = ffi.Context(0, torch.cuda.current_stream().cuda_stream, ffi.MG_BF16)
     gs, modes = [], []
     for c, m in segs:
@@ -33,22 +36,24 @@ def run(name, N=256, iters=20, which=("fwd", "dgrad", "wgrad")):
         g = Grid(ffi.MG_BF16, N, c, h, h)
         g.t.normal_()
         gs.append(g); modes.append(MG_SEG_UP if m == "u" else MG_SEG_SAME)
-    pad = 0 if k == 1 else 1
-    d = conv_desc(gs, modes, k, 1, pad, Cout, H, H)
+    pad = SHAPES[name][5] if len(SHAPES[name]) > 5 else (0 if k == 1 else 1)
+    d = conv_desc(gs, modes, k, stride, pad, Cout, H, H)
+    Ho = (H + 2 * pad - k) // stride + 1
     cin = sum(c for c, _ in segs)
     w = torch.randn(Cout, cin, k, k, device="cuda") * 0.05
     b = torch.zeros(Cout, device="cuda")
     wp = torch.zeros(ffi.lib.mg_conv_packed_bytes(C.byref(d), 0), dtype=torch.uint8, device="cuda")
-    wpt = torch.zeros(ffi.lib.mg_conv_packed_bytes(C.byref(d), 1), dtype=torch.uint8, device="cuda")
+    wpt = torch.zeros(max(16, ffi.lib.mg_conv_packed_bytes(C.byref(d), 1)), dtype=torch.uint8, device="cuda")
     ctx.call("mg_conv_pack_weights", C.byref(d), ptr(w), ptr(wp), 0)
-    ctx.call("mg_conv_pack_weights", C.byref(d), ptr(w), ptr(wpt), 1)
-    y = Grid(ffi.MG_BF16, N, Cout, H, H)
-    g = Grid(ffi.MG_BF16, N, Cout, H, H); g.t.normal_()
+    if stride == 1:
+        ctx.call("mg_conv_pack_weights", C.byref(d), ptr(w), ptr(wpt), 1)
+    y = Grid(ffi.MG_BF16, N, Cout, Ho, Ho)
+    g = Grid(ffi.MG_BF16, N, Cout, Ho, Ho); g.t.normal_()
     cp = sum(x.Cp for x in gs)
     dcat = Grid(ffi.MG_BF16, N, cp, H, H, Cp=cp)
     dw = torch.zeros_like(w); db = torch.zeros_like(b)
     sums = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
-    flops = 2.0 * N * H * H * Cout * cin * k * k
+    flops = 2.0 * N * Ho * Ho * Cout * cin * k * k
     calls = {
         "fwd": lambda: ctx.call("mg_conv_forward", C.byref(d), ptr(w), ptr(wp), ptr(b), C.byref(y.g()), None),
         "fwd_stats": lambda: ctx.call("mg_conv_forward", C.byref(d), ptr(w), ptr(wp), ptr(b), C.byref(y.g()), ptr(sums)),
