@@ -194,6 +194,19 @@ __global__ void __launch_bounds__(N_THREADS, 4) umma_conv_kernel(const __grid_co
         }
       }
     } else {
+      // general geometry (any k / stride / pad: the 7x7 stride-2 stem).  The kernel is issue bound (ncu: 59 % of the issue
+      // slots on the stem), so everything that depends only on the row is decoded once per CTA: image index and the
+      // input coordinates of tap (0,0); a copy then costs two adds, two bound checks and one address computation.
+      int riy[BM / 16], rix[BM / 16], rn[BM / 16];
+#pragma unroll
+      for (int it = 0; it < BM / 16; ++it) {
+        const uint32_t ri = s_row[it * 16 + rg];
+        const bool valid = ri != 0xFFFFFFFFu;
+        rn[it] = valid ? (int)(ri >> 20) : 0;
+        riy[it] = valid ? (int)((ri >> 10) & 1023) * p.stride - p.pad : -(1 << 20);   // far outside: every bound check fails
+        rix[it] = valid ? (int)(ri & 1023) * p.stride - p.pad : -(1 << 20);
+      }
+      const uint32_t dst_thread = (uint32_t)(rg * 128 + ((v ^ (rg & 7)) << 4));          // (it*16+rg)&7 == rg&7
       for (int ks = 0; ks < p.n_stages + L; ++ks) {
         if (ks < p.n_stages) {
           const int s = ks % S;
@@ -207,19 +220,18 @@ __global__ void __launch_bounds__(N_THREADS, 4) umma_conv_kernel(const __grid_co
             while (sg + 1 < p.n_seg && r >= s_seg[sg + 1].kv_begin) ++sg;
           }
           const USeg sgm = s_seg[sg];
-          const int c8 = r - sgm.kv_begin;
-          const int dy = tap / p.k - p.pad, dx = tap % p.k - p.pad;
-          const uint32_t dst0 = smem_u32(a_smem + (size_t)s * A_STAGE_BYTES);
+          const int dy = kv_ok ? tap / p.k : -(1 << 20), dx = tap % p.k;
+          const char* base = reinterpret_cast<const char*>(sgm.ptr) + (r - sgm.kv_begin) * 16;
+          const uint32_t pitch = (uint32_t)sgm.Cp * 2u;
+          const int plane = sgm.Hs * sgm.Ws;
+          const uint32_t dst0 = smem_u32(a_smem + (size_t)s * A_STAGE_BYTES) + dst_thread;
 #pragma unroll
           for (int it = 0; it < BM / 16; ++it) {
-            const int row = it * 16 + rg;
-            const uint32_t ri = s_row[row];
-            const int ox = ri & 1023, oy = (ri >> 10) & 1023, n = ri >> 20;
-            const int iy = oy * p.stride + dy, ix = ox * p.stride + dx;
-            const bool ok = kv_ok && ri != 0xFFFFFFFFu && (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
-            const __nv_bfloat16* src = sgm.ptr;
-            if (ok) src += ((size_t)((size_t)n * sgm.Hs + (iy >> sgm.shift)) * sgm.Ws + (ix >> sgm.shift)) * sgm.Cp + c8 * 8;
-            cp_async16(dst0 + row * 128 + ((v ^ (row & 7)) << 4), src, ok ? 16u : 0u);
+            const int iy = riy[it] + dy, ix = rix[it] + dx;
+            const bool ok = (unsigned)iy < (unsigned)p.H && (unsigned)ix < (unsigned)p.W;
+            const int64_t pixel = (int64_t)rn[it] * plane + (iy >> sgm.shift) * sgm.Ws + (ix >> sgm.shift);
+            const char* src = ok ? base + pixel * pitch : reinterpret_cast<const char*>(sgm.ptr);
+            cp_async16(dst0 + it * 2048, src, ok ? 16u : 0u);
           }
         }
         cp_async_commit();
