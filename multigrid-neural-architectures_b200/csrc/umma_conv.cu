@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(N_THREADS, 4) umma_conv_kernel(const __grid_co
   __shared__ uint32_t tmem_base_s;
   __shared__ uint32_t s_row[BM];
   __shared__ USeg s_seg[MG_MAX_SEG];
+  __shared__ float s_bias[256];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = p.stages;
@@ -94,11 +95,23 @@ __global__ void __launch_bounds__(N_THREADS, 4) umma_conv_kernel(const __grid_co
     int64_t m = m0 + tid;
     uint32_t v = 0xFFFFFFFFu;
     if (m < p.M) {
-      int ox = (int)(m % p.Wo); int64_t q = m / p.Wo;
-      int oy = (int)(q % p.Ho); int n = (int)(q / p.Ho);
-      v = ((uint32_t)n << 20) | ((uint32_t)oy << 10) | (uint32_t)ox;
+      if (p.M < ((int64_t)1 << 32)) {   // 32-bit divisions: the prologue of 25 088 CTAs on the stem
+        const uint32_t mu = (uint32_t)m, q = mu / (uint32_t)p.Wo, ox = mu - q * (uint32_t)p.Wo;
+        const uint32_t n = q / (uint32_t)p.Ho, oy = q - n * (uint32_t)p.Ho;
+        v = (n << 20) | (oy << 10) | ox;
+      } else {
+        int ox = (int)(m % p.Wo); int64_t q = m / p.Wo;
+        int oy = (int)(q % p.Ho); int n = (int)(q / p.Ho);
+        v = ((uint32_t)n << 20) | ((uint32_t)oy << 10) | (uint32_t)ox;
+      }
     }
     s_row[tid] = v;
+  }
+  if (tid >= BM - 64 && tid < BM + 64) {   // bias tile of this column tile (zero beyond Cout): no global loads in the epilogue
+    for (int c = tid - (BM - 64); c < p.n_tile; c += 128) {
+      const int ch = blockIdx.y * p.n_tile + c;
+      s_bias[c] = (p.bias && ch < p.c_bias) ? p.bias[ch] : 0.f;
+    }
   }
   if (tid == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], N_PRODUCERS + 1); mbar_init(&empty_bar[s], 1); }
@@ -261,11 +274,8 @@ __global__ void __launch_bounds__(N_THREADS, 4) umma_conv_kernel(const __grid_co
             uint32_t pk[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              float a = __uint_as_float(acc[h * 8 + 2 * e]), b = __uint_as_float(acc[h * 8 + 2 * e + 1]);
-              if (p.bias) {
-                if (n0 + 2 * e < p.c_bias) a += __ldg(p.bias + n0 + 2 * e);
-                if (n0 + 2 * e + 1 < p.c_bias) b += __ldg(p.bias + n0 + 2 * e + 1);
-              }
+              const float a = __uint_as_float(acc[h * 8 + 2 * e]) + s_bias[c0 + h * 8 + 2 * e];
+              const float b = __uint_as_float(acc[h * 8 + 2 * e + 1]) + s_bias[c0 + h * 8 + 2 * e + 1];
               __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
               pk[e] = *reinterpret_cast<uint32_t*>(&t);
             }
