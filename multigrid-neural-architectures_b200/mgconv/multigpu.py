@@ -205,10 +205,17 @@ def saveDataParallel(filename, model):
     """multigpu.lua:105-135: persist replica 1 with its buffers cleared.  The module graph is
     rebuilt by the builder; what is stored are the per-module tensors in listModules() order."""
     if not dist.is_initialized() or dist.get_rank() == 0:
-        torch.save({"format": "mgconv-b200/1", "modules": _state(model)}, filename)
+        if str(filename).endswith(".t7"):      # the reference's own container: torch.save of the module tree (mgconv/t7.py)
+            from . import t7
+            t7.save_model(filename, model)
+        else:
+            torch.save({"format": "mgconv-b200/1", "modules": _state(model)}, filename)
 
 
 def _load_into(model, filename):
+    if str(filename).endswith(".t7"):          # a Torch7 checkpoint (model_<epoch>.t7, possibly an nn.DataParallelTable)
+        from . import t7
+        return t7.load_into(model, filename)
     blob = torch.load(filename, map_location="cpu")
     mods = (model.model if isinstance(model, DataParallel) else model).listModules()
     if len(mods) != len(blob["modules"]):
