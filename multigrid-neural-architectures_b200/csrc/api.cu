@@ -122,6 +122,7 @@ int mg_ctx_destroy(mg_ctx* ctx) {
     if (ctx->lane_stream[l]) cudaStreamDestroy(ctx->lane_stream[l]);
   }
   for (int l = 0; l < MG_MAX_LANES; ++l) if (ctx->lane_ev[l]) cudaEventDestroy(ctx->lane_ev[l]);
+  for (int l = 0; l < MG_MAX_LANES; ++l) if (ctx->up_ws[l]) cudaFree(ctx->up_ws[l]);
   for (int e = 0; e < ctx->n_events; ++e) cudaEventDestroy(ctx->events[e]);
   free(ctx->events);
   if (ctx->pack_dev) cudaFree(ctx->pack_dev);

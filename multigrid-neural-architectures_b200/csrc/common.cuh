@@ -34,6 +34,8 @@ struct mg_ctx {
   int cur_lane;
   void* lane_ws[MG_MAX_LANES];        // scratch of lanes 1.. (lane 0 uses ws)
   size_t lane_ws_bytes[MG_MAX_LANES];
+  void* up_ws[MG_MAX_LANES];          // scratch of the tensor-core up-convolution (upconv_tc.cu), per lane
+  size_t up_ws_bytes[MG_MAX_LANES];
   cudaEvent_t* events;                // mg_ctx_event_record / mg_ctx_event_wait pool
   int n_events;
   cudaEvent_t lane_ev[MG_MAX_LANES];  // mg_allreduce_launch: completion of everything enqueued so far on each lane

@@ -7,6 +7,8 @@
 
 // bf16 fast paths (elementwise_bf16.cu); each returns false when it does not apply
 bool bf16_im2col(mg_ctx*, const mg_grid* in, int k, int stride, int pad, mg_grid* col);
+int upconv_tc_forward(mg_ctx*, const mg_grid* x, const float* w, const float* bias, mg_grid* y);
+int upconv_tc_backward(mg_ctx*, const mg_grid* x, const float* w, const mg_grid* g, mg_grid* dx, float* dw, float* dbias, float gscale);
 bool bf16_apply(mg_ctx*, const mg_grid* z, const mg_grid* s, int relu, mg_grid* out, mg_grid* pooled, const mg_bn_fused* bn);
 bool bf16_bn_stats(mg_ctx*, const mg_grid* y, double* sums);
 bool bf16_combine(mg_ctx*, const mg_grid* x, int relu_mask, const mg_grid* bn_x, int n_src, const mg_grad_src* src, mg_grid* d, double* sums);
@@ -887,6 +889,11 @@ extern "C" {
 int mg_upconv2x2_forward(mg_ctx* ctx, const mg_grid* x, const float* w, const float* bias, mg_grid* y, double* bn_sums) {
   if (!ctx || !x || !w || !y) return MG_ERR_INVALID_ARG;
   MG_REQUIRE(ctx, y->H == 2 * x->H && y->W == 2 * x->W && y->N == x->N && !x->scale, MG_ERR_SHAPE, "upconv: y must be 2x the size of x");
+  {   // bf16: one 1x1 tensor-core convolution to 4 * Cout channels + depth-to-space (upconv_tc.cu)
+    const int rc = upconv_tc_forward(ctx, x, w, bias, y);
+    if (rc > 0) return rc;
+    if (rc == 0) return bn_sums ? mg_bn_stats(ctx, y, bn_sums) : MG_OK;
+  }
   const int64_t total = (int64_t)y->N * y->H * y->W * y->Cp;
   MG_DISPATCH(ctx, upconv_fwd_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>((const T*)x->data, x->Cp, x->C, w, bias, (T*)y->data, y->Cp, y->C,
                                                                              x->N, x->H, x->W););
@@ -899,6 +906,10 @@ int mg_upconv2x2_backward(mg_ctx* ctx, const mg_grid* x, const float* w, const m
                           float gscale) {
   if (!ctx || !x || !w || !g) return MG_ERR_INVALID_ARG;
   MG_REQUIRE(ctx, g->H == 2 * x->H && g->W == 2 * x->W && g->N == x->N, MG_ERR_SHAPE, "upconv backward: g must be 2x the size of x");
+  {
+    const int rc = upconv_tc_backward(ctx, x, w, g, dx, dw, dbias, gscale);
+    if (rc >= 0) return rc;
+  }
   if (dx) {
     const int64_t total = (int64_t)x->N * x->H * x->W * dx->Cp;
     MG_DISPATCH(ctx, upconv_dgrad_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>((const T*)g->data, g->Cp, g->C, w, (T*)dx->data, dx->Cp, x->C,

@@ -351,9 +351,12 @@ def test_stem_im2col_then_1x1_conv_equals_strided_conv(shape):
     ctx.close()
 
 
-def test_upconv2x2_forward_backward(ctx):
-    """cudnn.SpatialFullConvolution(nIP, nOP, 2,2,2,2) of U-MG (models/mnist-cluttered/unmg.lua:35-41)"""
-    N, Cin, Cout, H = 2, 12, 10, 5
+@pytest.mark.parametrize("shape", [(2, 12, 10, 5), (3, 64, 32, 8), (1, 40, 136, 3)])
+def test_upconv2x2_forward_backward(ctx, shape):
+    """cudnn.SpatialFullConvolution(nIP, nOP, 2,2,2,2) of U-MG (models/mnist-cluttered/unmg.lua:35-41); in bf16 mode it must run
+    as one 1x1 tensor-core convolution to 4 * Cout channels + depth-to-space (upconv_tc.cu), not on the CUDA cores"""
+    N, Cin, Cout, H = shape
+    tc0 = ctx.tc_launches()
     x = rnd(N, Cin, H, H)
     w = bf16_round(rng.standard_normal((Cin, Cout, 2, 2)) * 0.3)
     b = bf16_round(rng.standard_normal(Cout) * 0.1)
@@ -373,6 +376,12 @@ def test_upconv2x2_forward_backward(ctx):
     torch.cuda.synchronize()
     assert max_rel(dx.nchw(), gx_ref) <= tol
     assert max_rel(dw.cpu().numpy(), gw_ref) <= tol and max_rel(db.cpu().numpy(), gb_ref) <= tol
+    assert not gy.pad_channels().any() and not dx.pad_channels().any()
+    assert ctx.tc_launches() - tc0 == (3 if ctx.dtype == ffi.MG_BF16 else 0)     # forward, dgrad, wgrad
+    # accGradParameters accumulates
+    ctx.call("mg_upconv2x2_backward", C.byref(gx.g()), ptr(wd), C.byref(gg.g()), None, ptr(dw), ptr(db), 0.5)
+    torch.cuda.synchronize()
+    assert max_rel(dw.cpu().numpy(), 1.5 * gw_ref) <= tol and max_rel(db.cpu().numpy(), 1.5 * gb_ref) <= tol
 
 
 def test_conv_shape_errors_are_reported_not_fatal(ctx):
