@@ -348,7 +348,7 @@ __device__ __forceinline__ float warp_reduce_scatter16(float (&v)[16], int lane)
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
 
-constexpr int HALO_MAX_SLOTS = 256 + 2 * 64 + 2;   // W <= 63, up to two 128-slot sub-tiles per CTA
+constexpr int HALO_MAX_SLOTS = 256 + 2 * 65 + 2;   // W <= 64, up to two 128-slot sub-tiles per CTA
 constexpr int H_PROD = 256;                        // 8 loader warps (the first 4 also drain TMEM): the gather is issue bound
 constexpr int H_MMA_WARP = H_PROD / 32, H_B_WARP = H_MMA_WARP + 1;
 constexpr int H_THREADS = H_PROD + 64;
@@ -365,8 +365,8 @@ __global__ void __launch_bounds__(H_THREADS, MT == 1 ? 4 : 3) umma_conv_halo_ker
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], a_full[2], a_empty[2], tmem_full_bar;
   __shared__ uint32_t tmem_base_s;
-  __shared__ uint32_t s_pix[BM * MT + 130];    // full-resolution pixel index of a halo slot, 0xFFFFFFFF = padding / outside
-  __shared__ uint32_t s_pup[BM * MT + 130];    // half-resolution pixel index (UP segments)
+  __shared__ uint32_t s_pix[BM * MT + 132];    // full-resolution pixel index of a halo slot, 0xFFFFFFFF = padding / outside
+  __shared__ uint32_t s_pup[BM * MT + 132];    // half-resolution pixel index (UP segments)
   __shared__ USeg s_seg[MG_MAX_SEG];
   __shared__ float s_bias[256];                // bias of this column tile (zero beyond Cout): no global loads in the epilogue
 
@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t b_full, a_full[P_MAX_ABUF], a_empty[P_MAX_ABUF], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ uint32_t s_pix[2][BM + 130], s_pup[2][BM + 130];
+  __shared__ uint32_t s_pix[2][BM + 132], s_pup[2][BM + 132];
   __shared__ USeg s_seg[MG_MAX_SEG];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -925,12 +925,12 @@ struct Geometry {
 };
 
 // the halo kernel serves 3x3 / stride 1 / pad 1 convolutions on grids of at least `MGCONV_HALO_MIN_W`
-// (default 7) and at most 63 columns whose UP segments are exactly half size
+// (default 7) and at most 64 columns whose UP segments are exactly half size
 static bool halo_applies(const mg_conv_desc* d) {
   static int min_w = -1;
   if (min_w < 0) { const char* e = getenv("MGCONV_HALO_MIN_W"); min_w = e ? atoi(e) : 7; }
   if (d->ksize != 3 || d->stride != 1 || d->pad != 1) return false;
-  if (d->W < min_w || d->W > 63 || d->H > 1023) return false;
+  if (d->W < min_w || d->W > 64 || d->H > 1023) return false;
   for (int s = 0; s < d->n_seg; ++s) {
     const mg_grid& g = d->seg[s];
     if (d->seg_mode[s] == MG_SEG_UP) { if (g.H * 2 != d->H || g.W * 2 != d->W) return false; }

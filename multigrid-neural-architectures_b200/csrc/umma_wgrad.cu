@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(W_THREADS, 2) umma_wgrad_kernel(const __grid_c
 // the 128 slots; the nine taps are nine row-shifted views of that halo.  Two taps form one UMMA
 // M = 128 operand (MN-major: its two 64-channel blocks are the same buffer LBO = shift_b - shift_a
 // rows apart), so five accumulators hold dW[tap][64 channels][n_tile] for the whole pixel range.
-constexpr int WH_MAX_SLOTS = 128 + 2 * 64 + 2;
+constexpr int WH_MAX_SLOTS = 128 + 2 * 65 + 2;   // W <= 64
 constexpr int WH_PROD = 512;              // 8 loader warps (the first 4 also drain TMEM)
 constexpr int WH_MMA_WARP = WH_PROD / 32;
 constexpr int WH_THREADS = WH_PROD + 32;
@@ -459,7 +459,7 @@ static bool wgrad_halo_applies(const mg_conv_desc* d) {
   if (on < 0) { const char* e = getenv("MGCONV_WGRAD_HALO"); on = e ? atoi(e) : 1; }
   if (min_w < 0) { const char* e = getenv("MGCONV_HALO_MIN_W"); min_w = e ? atoi(e) : 7; }
   if (!on || d->ksize != 3 || d->stride != 1 || d->pad != 1) return false;
-  if (d->W < min_w || d->W > 63 || d->H > 1023) return false;
+  if (d->W < min_w || d->W > 64 || d->H > 1023) return false;
   for (int s = 0; s < d->n_seg; ++s) {
     const mg_grid& g = d->seg[s];
     if (d->seg_mode[s] == MG_SEG_UP) { if (g.H * 2 != d->H || g.W * 2 != d->W) return false; }

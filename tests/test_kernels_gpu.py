@@ -193,7 +193,7 @@ def test_mgconv_forward_dgrad_wgrad(ctx, case, impl):
 EDGE_CASES = [  # N, [(C, mode 's'|'u')], H, W, Cout, k -- shapes that take the less-travelled paths
     (1, [(8, "s")], 1, 1, 16, 3),                 # 1x1 grid: only the centre tap is ever in bounds (CIFAR coarsest grid)
     (2, [(24, "s"), (8, "u")], 6, 10, 520, 3),    # non-square, Cout > 256 -> several N tiles, rows spanning images
-    (1, [(16, "s")], 5, 70, 8, 3),                # W > 63: per-tap tcgen05 kernels instead of the halo kernels
+    (1, [(16, "s")], 5, 70, 8, 3),                # W > 64: per-tap tcgen05 kernels instead of the halo kernels
     (3, [(3, "s")], 9, 7, 40, 3),                 # Cin = 3 (Cp = 8, five zero channels), odd sizes
     (2, [(72, "s"), (40, "s"), (16, "u")], 4, 4, 24, 1),   # 1x1 kernel over three segments (CIFAR last blocks)
     (5, [(200, "s")], 3, 3, 96, 3),               # K spanning several 64-channel chunks with a ragged last chunk
@@ -203,6 +203,7 @@ EDGE_CASES = [  # N, [(C, mode 's'|'u')], H, W, Cout, k -- shapes that take the 
 EDGE_CASES += [
     (9, [(40, "s"), (24, "u")], 8, 12, 48, 3),    # two chunks, ragged last 256-slot tile (9 * 9 * 13 = 1053 slots)
     (4, [(136, "s")], 14, 14, 136, 3),            # three chunks with a ragged tail, N tile 144
+    (2, [(16, "s"), (8, "u")], 64, 64, 24, 3),    # W = 64: the widest grid the halo kernels take (MNIST-cluttered 64x64 scale)
 ]
 # kernel-selection overrides: automatic, two sub-tiles per CTA, persistent weight-resident kernel
 # (context sub-tile override, context persistent override, per-layer algo of the descriptor)
