@@ -77,49 +77,54 @@ struct ApplyP {
   float* smean; float* sinvstd; float* scale_out; float* shift_out;
 };
 
-__global__ void __launch_bounds__(256, 3) apply_bf16_kernel(ApplyP p) {
+// BatchNorm finalisation of the apply pass, per CTA (expression for expression bn_finalize_kernel).  Not inlined: its fp64
+// arithmetic would otherwise set the register count of the streaming body (64 instead of 40 registers per thread).
+__device__ __forceinline__ void apply_bn_prologue(const ApplyP& p, float* s_aff) {
+  for (int c = threadIdx.x; c < p.z_cp; c += blockDim.x) {
+    float scv = 0.f, shv = 0.f, mv = 0.f, iv = 0.f;
+    if (c < p.C) {
+      double mean, var;
+      if (p.training) {
+        mean = p.sums[c] / (double)p.count;
+        var = p.sums[p.C + c] / (double)p.count - mean * mean;   // biased
+        if (var < 0) var = 0;
+        if (p.rmean && blockIdx.x == 0) {
+          const double unb = p.count > 1 ? var * (double)p.count / (double)(p.count - 1) : var;
+          p.rmean[c] = (float)((1.0 - p.momentum) * p.rmean[c] + p.momentum * mean);
+          p.rvar[c] = (float)((1.0 - p.momentum) * p.rvar[c] + p.momentum * unb);
+        }
+      } else {
+        mean = p.rmean[c]; var = p.rvar[c];
+      }
+      const double invstd = 1.0 / sqrt(var + (double)p.eps);
+      const float g = p.gamma ? p.gamma[c] : 1.f, b = p.beta ? p.beta[c] : 0.f;
+      scv = (float)(g * invstd);
+      shv = (float)(b - g * invstd * mean);
+      mv = (float)mean; iv = (float)invstd;
+    }
+    s_aff[c] = scv; s_aff[p.z_cp + c] = shv;
+    if (blockIdx.x == 0) {
+      p.scale_out[c] = scv; p.shift_out[c] = shv;
+      if (p.smean) { p.smean[c] = mv; p.sinvstd[c] = iv; }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256, 4) apply_bf16_kernel(const __grid_constant__ ApplyP p) {
   pdl_launch();
   pdl_wait();
   extern __shared__ float s_aff[];   // [2][z_cp] when bn
   if (p.bn) {
-    for (int c = threadIdx.x; c < p.z_cp; c += blockDim.x) {
-      float scv = 0.f, shv = 0.f, mv = 0.f, iv = 0.f;
-      if (c < p.C) {
-        double mean, var;
-        if (p.training) {
-          mean = p.sums[c] / (double)p.count;
-          var = p.sums[p.C + c] / (double)p.count - mean * mean;   // biased
-          if (var < 0) var = 0;
-          if (p.rmean && blockIdx.x == 0) {
-            const double unb = p.count > 1 ? var * (double)p.count / (double)(p.count - 1) : var;
-            p.rmean[c] = (float)((1.0 - p.momentum) * p.rmean[c] + p.momentum * mean);
-            p.rvar[c] = (float)((1.0 - p.momentum) * p.rvar[c] + p.momentum * unb);
-          }
-        } else {
-          mean = p.rmean[c]; var = p.rvar[c];
-        }
-        const double invstd = 1.0 / sqrt(var + (double)p.eps);
-        const float g = p.gamma ? p.gamma[c] : 1.f, b = p.beta ? p.beta[c] : 0.f;
-        scv = (float)(g * invstd);
-        shv = (float)(b - g * invstd * mean);
-        mv = (float)mean; iv = (float)invstd;
-      }
-      s_aff[c] = scv; s_aff[p.z_cp + c] = shv;
-      if (blockIdx.x == 0) {
-        p.scale_out[c] = scv; p.shift_out[c] = shv;
-        if (p.smean) { p.smean[c] = mv; p.sinvstd[c] = iv; }
-      }
-    }
+    apply_bn_prologue(p, s_aff);
     __syncthreads();
   }
-  // each CTA streams ONE contiguous range of 2x2 pixel blocks; its threads form `lanes` block lanes x V channel vectors
   const int V = p.o_cp >> 3;
-  const int lanes = blockDim.x / V;
-  const int vc = threadIdx.x % V, lane = threadIdx.x / V;
-  if (lane >= lanes) return;
-  const int64_t nblocks = (int64_t)p.N * p.Hp * p.Wp;
-  const int64_t per_cta = (nblocks + gridDim.x - 1) / gridDim.x;
-  const int64_t b_begin = (int64_t)blockIdx.x * per_cta, b_end = min(nblocks, b_begin + per_cta);
+  const int64_t total = (int64_t)p.N * p.Hp * p.Wp * V;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int vc = (int)(i % V); int64_t q = i / V;
+  const int px = (int)(q % p.Wp); q /= p.Wp;
+  const int py = (int)(q % p.Hp); const int n = (int)(q / p.Hp);
   const int c0 = vc * 8;
   float sc[8], sh[8];
   const bool has_aff = p.bn || p.scale != nullptr;
@@ -128,38 +133,23 @@ __global__ void __launch_bounds__(256, 3) apply_bf16_kernel(ApplyP p) {
     for (int e = 0; e < 8; ++e) { sc[e] = s_aff[c0 + e]; sh[e] = s_aff[p.z_cp + c0 + e]; }
   } else if (has_aff) { ldf8(p.scale + c0, sc); ldf8(p.shift + c0, sh); }
   const bool has_s = p.s != nullptr && c0 < p.s_cp;
-  for (int64_t blk = b_begin + lane; blk < b_end; blk += lanes) {
-    const int px = (int)(blk % p.Wp); int64_t q = blk / p.Wp;
-    const int py = (int)(q % p.Hp); const int n = (int)(q / p.Hp);
-    float best[8];
+  float best[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) best[e] = -INFINITY;
-    // the (up to) eight 16-byte loads of the block are issued before any arithmetic
-    uint4 zr[4], sr[4];
-    bool ok[4];
+  for (int e = 0; e < 8; ++e) best[e] = -INFINITY;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int y = 2 * py + (k >> 1), x = 2 * px + (k & 1);
-      ok[k] = y < p.H && x < p.W;
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const int y = 2 * py + dy, x = 2 * px + dx;
+      if (y >= p.H || x >= p.W) continue;
       const int64_t pix = ((int64_t)n * p.H + y) * p.W + x;
-      zr[k] = make_uint4(0, 0, 0, 0); sr[k] = make_uint4(0, 0, 0, 0);
-      if (ok[k]) {
-        zr[k] = __ldg(reinterpret_cast<const uint4*>(p.z + pix * p.z_cp + c0));
-        if (has_s) sr[k] = __ldg(reinterpret_cast<const uint4*>(p.s + pix * p.s_cp + c0));
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (!ok[k]) continue;
-      const int y = 2 * py + (k >> 1), x = 2 * px + (k & 1);
-      const int64_t pix = ((int64_t)n * p.H + y) * p.W + x;
-      V8 v = unpack8(zr[k]);
+      V8 v = ld8(p.z + pix * p.z_cp + c0);
       if (has_aff) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) v.v[e] = mg_xform(v.v[e], sc[e], sh[e], p.z_relu);
       }
       if (has_s) {
-        const V8 sv = unpack8(sr[k]);
+        const V8 sv = ld8(p.s + pix * p.s_cp + c0);
 #pragma unroll
         for (int e = 0; e < 8; ++e) v.v[e] += sv.v[e];
       }
@@ -175,12 +165,11 @@ __global__ void __launch_bounds__(256, 3) apply_bf16_kernel(ApplyP p) {
       for (int e = 0; e < 8; ++e)
         if (r.v[e] > best[e] || r.v[e] != r.v[e]) best[e] = r.v[e];
     }
-    if (p.pooled && c0 < p.p_cp) {
-      V8 b;
+  if (p.pooled && c0 < p.p_cp) {
+    V8 b;
 #pragma unroll
-      for (int e = 0; e < 8; ++e) b.v[e] = (c0 + e < p.C) ? best[e] : 0.f;
-      *reinterpret_cast<uint4*>(p.pooled + (((int64_t)n * p.Hp + py) * p.Wp + px) * p.p_cp + c0) = pack8(b);
-    }
+    for (int e = 0; e < 8; ++e) b.v[e] = (c0 + e < p.C) ? best[e] : 0.f;
+    *reinterpret_cast<uint4*>(p.pooled + (((int64_t)n * p.Hp + py) * p.Wp + px) * p.p_cp + c0) = pack8(b);
   }
 }
 
@@ -600,12 +589,8 @@ bool bf16_apply(mg_ctx* ctx, const mg_grid* z, const mg_grid* s, int relu, mg_gr
   p.N = z->N; p.H = z->H; p.W = z->W; p.C = z->C; p.Hp = (z->H + 1) / 2; p.Wp = (z->W + 1) / 2;
   if (out->Cp > 2048) return false;
   const int64_t total = (int64_t)p.N * p.Hp * p.Wp * (p.o_cp / 8);
-  // one 2x2 block per thread up to 64 CTAs per SM, beyond that the threads loop (measured: few fat CTAs lose 10 % here --
-  // the pass has no reduction tail that would favour them)
-  const int lanes = 256 / (out->Cp / 8);
-  const int64_t nblocks = (int64_t)p.N * p.Hp * p.Wp;
-  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(mg_cdiv(nblocks, lanes), (int64_t)ctx->num_sms * 64));
-  (void)total;
+  // one 2x2 block x 8 channels per thread (measured: looping CTAs with batched loads need 80 registers and lose 10-40 %)
+  const unsigned grid = grid_for(total);
   mg_launch_pdl(apply_bf16_kernel, dim3(grid), dim3(256), bn ? 2 * z->Cp * sizeof(float) : 0, ctx->stream, p);
   return true;
 }
