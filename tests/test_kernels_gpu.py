@@ -436,6 +436,76 @@ def test_persistent_weight_resident_kernel_block1_shape():
     ctx.close()
 
 
+FULL_SHAPES = [  # R-MG-34 layers at the BASELINE batch (256 per GPU): (H, [(C, mode)], Cout)
+    (56, [(64, "s"), (32, "u")], 64),                # block 1, finest grid (rnmg.lua:250)
+    (28, [(128, "s"), (64, "s"), (32, "u")], 64),    # block 2, middle grid: pooled finer | same | up-sampled coarser
+    (14, [(256, "s"), (128, "u")], 256),             # block 3, finest grid
+    (7, [(512, "s")], 512),                          # block 4
+]
+
+
+@pytest.mark.parametrize("shape", FULL_SHAPES, ids=["b1g1", "b2g2", "b3g1", "b4"])
+def test_full_size_conv_is_linear_and_its_gradients_are_its_adjoints(shape):
+    """BASELINE-size layers (B = 256), where the oracle is too slow: size-independent properties of the three tensor-core
+    passes.  <g, conv(x; w)> = <dgrad(g), cat(x)> = <wgrad(g), w> (the backward passes are the adjoints of the forward one in
+    x and in w), conv(2x) = 2 conv(x) exactly (powers of two commute with bf16 rounding), the fused BatchNorm sums equal the
+    sums of the stored output, and pad channels stay zero."""
+    H, segs, Cout = shape
+    N = 256
+    ctx = ffi.Context(0, torch.cuda.current_stream().cuda_stream, ffi.MG_BF16)
+    torch.manual_seed(11)
+    grids, modes, parts = [], [], []
+    for c, m in segs:
+        h = H // 2 if m == "u" else H
+        g_ = Grid(ffi.MG_BF16, N, c, h, h)
+        g_.t[..., :c].normal_()
+        grids.append(g_); modes.append(MG_SEG_UP if m == "u" else MG_SEG_SAME)
+        x = g_.t[..., :c].float()
+        parts.append(x.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2) if m == "u" else x)
+    cin = sum(c for c, _ in segs)
+    d = conv_desc(grids, modes, 3, 1, 1, Cout, H, H)
+    w = (torch.randn(Cout, cin, 3, 3, device="cuda") * 0.05).to(torch.bfloat16).float()
+    zero_b = torch.zeros(Cout, device="cuda")
+    wp = torch.zeros(ffi.lib.mg_conv_packed_bytes(C.byref(d), 0), dtype=torch.uint8, device="cuda")
+    wpt = torch.zeros(ffi.lib.mg_conv_packed_bytes(C.byref(d), 1), dtype=torch.uint8, device="cuda")
+    ctx.call("mg_conv_pack_weights", C.byref(d), ptr(w), ptr(wp), 0)
+    ctx.call("mg_conv_pack_weights", C.byref(d), ptr(w), ptr(wpt), 1)
+    y = Grid(ffi.MG_BF16, N, Cout, H, H)
+    sums = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
+    ctx.call("mg_conv_forward", C.byref(d), ptr(w), ptr(wp), ptr(zero_b), C.byref(y.g()), ptr(sums))
+    yf = y.t[..., :Cout].double()
+    assert torch.allclose(sums[:Cout], yf.sum((0, 1, 2)), rtol=1e-5, atol=1e-1)
+    assert torch.allclose(sums[Cout:], (yf * yf).sum((0, 1, 2)), rtol=1e-5, atol=1e-1)
+    assert not y.t[..., Cout:].any()
+    # linearity: doubling the input doubles every stored output bit for bit
+    for g_ in grids:
+        g_.t.mul_(2)
+    y2 = Grid(ffi.MG_BF16, N, Cout, H, H)
+    ctx.call("mg_conv_forward", C.byref(d), ptr(w), ptr(wp), ptr(zero_b), C.byref(y2.g()), None)
+    assert torch.equal(y2.t, y.t * 2)
+    for g_ in grids:
+        g_.t.mul_(0.5)
+    # adjoints
+    gg = Grid(ffi.MG_BF16, N, Cout, H, H)
+    gg.t[..., :Cout].normal_()
+    cp = sum(x.Cp for x in grids)
+    dcat = Grid(ffi.MG_BF16, N, cp, H, H, Cp=cp)
+    ctx.call("mg_conv_backward_data", C.byref(d), ptr(w), ptr(wpt), C.byref(gg.g()), C.byref(dcat.g()))
+    dw = torch.zeros_like(w)
+    ctx.call("mg_conv_backward_weight", C.byref(d), C.byref(gg.g()), ptr(dw), None, 1.0)
+    torch.cuda.synchronize()
+    lhs = float((gg.t[..., :Cout].double() * yf).sum())
+    off, mid = 0, 0.0
+    for g_, part in zip(grids, parts):
+        mid += float((dcat.t[..., off:off + g_.C].double() * part.double()).sum())
+        assert not dcat.t[..., off + g_.C:off + g_.Cp].any()
+        off += g_.Cp
+    rhs = float((dw.double() * w.double()).sum())
+    scale = float(gg.t[..., :Cout].double().norm() * yf.norm())     # Cauchy-Schwarz bound of the inner products
+    assert abs(lhs - mid) <= 2e-3 * scale and abs(lhs - rhs) <= 2e-3 * scale, (lhs, mid, rhs, scale)
+    ctx.close()
+
+
 # ---------------------------------------------------------------- BatchNorm + epilogue
 @pytest.mark.parametrize("eps", [1e-5, 1e-3])
 def test_bn_finalize_apply_residual_and_backward(ctx, eps):

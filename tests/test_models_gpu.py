@@ -282,3 +282,35 @@ def test_no_cpu_fallback():
     m = B.cifar_nmg.createModel(B.Opt(nLayer=1))
     with pytest.raises(ffi.MGError):
         m.forward(torch.zeros(1, 3, 32, 32))  # CPU tensor
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_lane_schedule_equals_serial_plan(precision, monkeypatch):
+    """the multi-stream lane schedule (mgconv/sched.py) must compute what the serial plan computes: one training step of
+    R-MG (cifar/rnmg) with 3 lanes + background wgrad lane vs MGCONV_LANES=1, same weights and batch"""
+    outs = {}
+    for lanes in ("1", "3"):
+        monkeypatch.setenv("MGCONV_LANES", lanes)
+        monkeypatch.setenv("MGCONV_AUTOTUNE", "0")
+        torch.manual_seed(5)
+        net = B.load_net("cifar/rnmg")
+        pm = net.createModel(B.Opt(nLayer=1, nGPU=1))
+        pm.precision = precision
+        pm.cuda()
+        params, grads = pm.getParameters()
+        crit = net.createCriterion()
+        g = torch.Generator(device="cpu").manual_seed(9)
+        x = torch.randn(32, 3, 32, 32, generator=g).cuda()
+        t = torch.randint(1, 101, (32,), generator=g).cuda()
+        pm.zeroGradParameters()
+        out, err = net.ftrain(x, t, pm, crit)
+        torch.cuda.synchronize()
+        assert pm._engine.n_lanes == int(lanes)
+        outs[lanes] = (out.clone(), float(err), grads.clone())
+    o1, e1, g1 = outs["1"]
+    o3, e3, g3 = outs["3"]
+    # identical kernels on identical data; only the order of floating-point atomics (BatchNorm sums, split-K) may differ
+    tol = 1e-5 if precision == "fp32" else 2e-2
+    assert abs(e1 - e3) <= tol * max(1.0, abs(e1))
+    assert rel_err(o3.cpu().numpy(), o1.cpu().numpy()) <= tol
+    assert rel_err(g3.cpu().numpy(), g1.cpu().numpy()) <= (1e-4 if precision == "fp32" else 5e-2)
