@@ -1012,7 +1012,7 @@ static int launch_halo(mg_ctx* ctx, UParams& p, const Geometry& g, int algo) {
   // measured: multicast clusters couple the CTAs and lose 5-10 % (weights are not the bottleneck): off by default
   if (cl_env < 0) { const char* e = getenv("MGCONV_CLUSTER"); cl_env = e ? atoi(e) : 1; }
   if (want_tl < 0) { const char* e = getenv("MGCONV_TIMELINE"); want_tl = e ? atoi(e) : 0; }
-  int CL = cl_env;
+  int CL = algo == MG_ALGO_TILE128_MCAST2 ? 2 : ((algo == MG_ALGO_AUTO || algo == MG_ALGO_RESIDENT) ? cl_env : 1);
   if ((p.n_tile * 128 / 16) % CL != 0 || CL < 1) CL = 1;          // each slice must be whole 16-byte units
   if (CL != 1 && CL != 2 && CL != 4) CL = 1;
   // two sub-tiles per CTA (half the weight stream per row) whenever that still leaves about a CTA per SM
@@ -1105,7 +1105,8 @@ static bool persist_plan(const mg_ctx* ctx, const mg_conv_desc* d, const Geometr
   static int on = -1, min_tiles_per_sm = -1;
   if (on < 0) { const char* e = getenv("MGCONV_PERSIST"); on = e ? atoi(e) : 1; }
   if (min_tiles_per_sm < 0) { const char* e = getenv("MGCONV_PERSIST_MIN_TILES"); min_tiles_per_sm = e ? atoi(e) : 4; }
-  if (algo == MG_ALGO_TILE128 || algo == MG_ALGO_TILE256 || algo == MG_ALGO_TILE128_DEEP || algo == MG_ALGO_TILE256_DEEP) return false;
+  if (algo == MG_ALGO_TILE128 || algo == MG_ALGO_TILE256 || algo == MG_ALGO_TILE128_DEEP || algo == MG_ALGO_TILE256_DEEP ||
+      algo == MG_ALGO_TILE128_MCAST2) return false;
   const bool forced = algo == MG_ALGO_RESIDENT || ctx->tune_persist == 1;
   if (!forced && (ctx->tune_persist == 2 || !on)) return false;
   if (!g.halo || g.n_tiles != 1) return false;
