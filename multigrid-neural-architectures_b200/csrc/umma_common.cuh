@@ -87,6 +87,30 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t da, uint64
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One lane of a fully converged warp (elect.sync): the MMA warp runs its issue loop with ALL lanes so that every operand stays
+// warp-uniform (uniform registers, no per-lane serialisation loop around each tcgen05.mma) and only the instruction itself is
+// predicated on the elected lane.  With `if (lane == 0)` around the whole loop the compiler cannot prove uniformity and wraps
+// every MMA in an ELECT / BRA.U.ANY loop plus ~12 uniform-datapath instructions of descriptor arithmetic: ~50 cycles between
+// MMAs, which is longer than an N = 64 MMA itself (32 cycles).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// shared-memory descriptor split in halves: the high word is a constant of the layout, the low word is
+// ((address >> 4) & 0x3FFF) | (LBO field << 16), so stepping K by 32 bytes is `lo += 2`
+constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 bytes, version 1, 128-byte swizzle
+__device__ __forceinline__ uint32_t desc_lo_k_sw128(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ void tc_mma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"

@@ -559,7 +559,9 @@ __global__ void __launch_bounds__(H_THREADS, MT == 1 ? 4 : 3) umma_conv_halo_ker
     }
   } else {
     // ================= MMA issuer: 9 shifted descriptors per chunk ===============================
-    if (lane == 0) {
+    // the whole warp runs the loop (warp-uniform operands), the elected lane issues the MMAs and the commits
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = idesc_bf16_m128(p.n_tile);
       int ks = 0;
       long long wait_a = 0, wait_b = 0, tq = 0;
@@ -568,7 +570,7 @@ __global__ void __launch_bounds__(H_THREADS, MT == 1 ? 4 : 3) umma_conv_halo_ker
         if (tl) tq = clock64();
         mbar_wait(&a_full[buf], (c / p.n_abuf) & 1);
         tc_fence_after();
-        if (tl && c == 0) tl[2] = clock64();
+        if (tl && c == 0 && lane == 0) tl[2] = clock64();
         if (tl && c > 0) wait_a += clock64() - tq;
         const uint32_t a_base = smem_u32(a_smem + (size_t)buf * p.halo_bytes);
         const int kv_here = min(KV_PER_STAGE, p.kv_per_tap - c * KV_PER_STAGE);
@@ -579,19 +581,23 @@ __global__ void __launch_bounds__(H_THREADS, MT == 1 ? 4 : 3) umma_conv_halo_ker
           mbar_wait(&full_bar[s], (ks / S) & 1);
           tc_fence_after();
           if (tl) wait_b += clock64() - tq;
-          const uint32_t a_addr = a_base + (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 128u;
-          const uint32_t b_addr = smem_u32(b_smem + (size_t)s * b_stage_bytes);
+          const uint32_t a_lo = desc_lo_k_sw128(a_base + (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 128u);
+          const uint32_t b_lo = desc_lo_k_sw128(smem_u32(b_smem + (size_t)s * b_stage_bytes));
+          if (leader) {
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt)   // both sub-tiles consume the same weight stage
-            for (int q = 0; q < ksteps; ++q)
-              tc_mma_bf16(tmem_base + (uint32_t)(mt * p.n_tile), smem_desc_k_sw128(a_addr + (uint32_t)(mt * BM * 128) + q * 32),
-                          smem_desc_k_sw128(b_addr + q * 32), idesc, (ks | q) != 0);
-          if (CL == 1) tc_commit(&empty_bar[s]); else tc_commit_mcast(&empty_bar[s], (uint16_t)((1u << CL) - 1));
+            for (int mt = 0; mt < MT; ++mt)   // both sub-tiles consume the same weight stage
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (q < ksteps)
+                  tc_mma_bf16_lohi(tmem_base + (uint32_t)(mt * p.n_tile), a_lo + (uint32_t)(mt * BM * 8 + q * 2), b_lo + (uint32_t)(q * 2), DESC_HI_SW128,
+                                   idesc, (ks | q) != 0);
+            if (CL == 1) tc_commit(&empty_bar[s]); else tc_commit_mcast(&empty_bar[s], (uint16_t)((1u << CL) - 1));
+          }
         }
-        tc_commit(&a_empty[buf]);   // halo buffer free once this chunk's MMAs have read it
+        if (leader) tc_commit(&a_empty[buf]);   // halo buffer free once this chunk's MMAs have read it
       }
-      tc_commit(&tmem_full_bar);
-      if (tl) { tl[5] = wait_a; tl[6] = wait_b; }
+      if (leader) tc_commit(&tmem_full_bar);
+      if (tl && lane == 0) { tl[5] = wait_a; tl[6] = wait_b; }
     }
   }
   __syncthreads();
@@ -801,8 +807,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
         bulk_g2s(smem_u32(b_smem + (size_t)q * b_stage_bytes), p.wpack + (size_t)q * b_stage_bytes, (uint32_t)b_stage_bytes, &b_full);
     }
   } else {
-    // ================= MMA issuer ================================================================
-    if (lane == 0) {
+    // ================= MMA issuer (whole warp, elected lane issues; see elect_one) =================
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = idesc_bf16_m128(p.n_tile);
       const uint32_t b_base = smem_u32(b_smem);
       int ac = 0;
@@ -818,15 +825,18 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
           const uint32_t a_base = smem_u32(a_smem + (size_t)buf * p.halo_bytes);
           const int kv_here = min(KV_PER_STAGE, p.kv_per_tap - c * KV_PER_STAGE);
           const int ksteps = (kv_here + 1) >> 1;
-          for (int tap = 0; tap < KK; ++tap) {
-            const uint32_t a_addr = a_base + (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 128u;
-            const uint32_t b_addr = b_base + (uint32_t)((c * KK + tap) * b_stage_bytes);
-            for (int q = 0; q < ksteps; ++q)
-              tc_mma_bf16(d_tmem, smem_desc_k_sw128(a_addr + q * 32), smem_desc_k_sw128(b_addr + q * 32), idesc, (c | tap | q) != 0);
+          if (leader) {
+            for (int tap = 0; tap < KK; ++tap) {
+              const uint32_t a_lo = desc_lo_k_sw128(a_base + (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 128u);
+              const uint32_t b_lo = desc_lo_k_sw128(b_base + (uint32_t)((c * KK + tap) * b_stage_bytes));
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (q < ksteps) tc_mma_bf16_lohi(d_tmem, a_lo + (uint32_t)(q * 2), b_lo + (uint32_t)(q * 2), DESC_HI_SW128, idesc, (c | tap | q) != 0);
+            }
+            tc_commit(&a_empty[buf]);
           }
-          tc_commit(&a_empty[buf]);
         }
-        tc_commit(&tmem_full[acc]);
+        if (leader) tc_commit(&tmem_full[acc]);
       }
     }
   }
