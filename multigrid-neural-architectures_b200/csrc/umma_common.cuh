@@ -101,6 +101,10 @@ __device__ __forceinline__ bool elect_one() {
 // ((address >> 4) & 0x3FFF) | (LBO field << 16), so stepping K by 32 bytes is `lo += 2`
 constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);   // SBO = 1024 bytes, version 1, 128-byte swizzle
 __device__ __forceinline__ uint32_t desc_lo_k_sw128(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+// MN-major SW128 descriptor, low word: address field | LBO field (bytes between 64-element MN blocks); same high word
+__device__ __forceinline__ uint32_t desc_lo_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
 __device__ __forceinline__ void tc_mma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"

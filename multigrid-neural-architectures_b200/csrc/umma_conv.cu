@@ -297,22 +297,26 @@ __global__ void __launch_bounds__(N_THREADS, 4) umma_conv_kernel(const __grid_co
       }
     }
   } else {
-    // ================= MMA issuer ================================================================
-    if (lane == 0) {
+    // ================= MMA issuer: whole warp, elected lane issues (see elect_one) =================
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = idesc_bf16_m128(p.n_tile);
       for (int ks = 0; ks < p.n_stages; ++ks) {
         const int s = ks % S;
         mbar_wait(&full_bar[s], (ks / S) & 1);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(a_smem + (size_t)s * A_STAGE_BYTES);
-        const uint32_t b_addr = smem_u32(b_smem + (size_t)s * b_stage_bytes);
+        const uint32_t a_lo = desc_lo_k_sw128(smem_u32(a_smem + (size_t)s * A_STAGE_BYTES));
+        const uint32_t b_lo = desc_lo_k_sw128(smem_u32(b_smem + (size_t)s * b_stage_bytes));
         const int kv_here = min(KV_PER_STAGE, p.nkv - ks * KV_PER_STAGE);
         const int ksteps = (kv_here + 1) >> 1;   // 16 bf16 = 2 k-vectors per UMMA K step
-        for (int q = 0; q < ksteps; ++q)
-          tc_mma_bf16(tmem_base, smem_desc_k_sw128(a_addr + q * 32), smem_desc_k_sw128(b_addr + q * 32), idesc, (ks | q) != 0);
-        tc_commit(&empty_bar[s]);   // frees the stage once these MMAs have read it
+        if (leader) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (q < ksteps) tc_mma_bf16_lohi(tmem_base, a_lo + q * 2, b_lo + q * 2, DESC_HI_SW128, idesc, (ks | q) != 0);
+          tc_commit(&empty_bar[s]);   // frees the stage once these MMAs have read it
+        }
       }
-      tc_commit(&tmem_full_bar);    // accumulator complete
+      if (leader) tc_commit(&tmem_full_bar);    // accumulator complete
     }
   }
   __syncthreads();

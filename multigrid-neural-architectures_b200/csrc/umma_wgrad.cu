@@ -187,22 +187,24 @@ __global__ void __launch_bounds__(W_THREADS, 2) umma_wgrad_kernel(const __grid_c
     }
     tc_fence_before();
   } else {
-    // ---- MMA issuer -----------------------------------------------------------------------------
-    if (lane == 0) {
+    // ---- MMA issuer: the whole warp runs the loop, the elected lane issues (see elect_one) -----------
+    {
+      const bool leader = elect_one();
       const uint32_t idesc = idesc_bf16_m128_mn(p.n_tile);
       for (int it = 0; it < n_iters; ++it) {
         const int s = it % S;
         mbar_wait(&full_bar[s], (it / S) & 1);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t b_addr = a_addr + 2 * A_IMG;
+        const uint32_t a_lo = desc_lo_mn_sw128(a_addr, A_IMG), b_lo = desc_lo_mn_sw128(a_addr + 2 * A_IMG, A_IMG);
+        if (leader) {
 #pragma unroll
-        for (int q = 0; q < PIX / 16; ++q)   // 16 pixels (K) per UMMA: 16 rows of 128 bytes
-          tc_mma_bf16(tmem_base, smem_desc_mn_sw128(a_addr + q * 2048, A_IMG), smem_desc_mn_sw128(b_addr + q * 2048, A_IMG), idesc,
-                      (it | q) != 0);
-        tc_commit(&empty_bar[s]);
+          for (int q = 0; q < PIX / 16; ++q)   // 16 pixels (K) per UMMA: 16 rows of 128 bytes = descriptor address + 128
+            tc_mma_bf16_lohi(tmem_base, a_lo + q * 128, b_lo + q * 128, DESC_HI_SW128, idesc, (it | q) != 0);
+          tc_commit(&empty_bar[s]);
+        }
       }
-      tc_commit(&tmem_full_bar);
+      if (leader) tc_commit(&tmem_full_bar);
     }
   }
   __syncthreads();
@@ -395,27 +397,30 @@ __global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __
     tc_fence_before();
     }
   } else {
-    if (lane == 0) {
+    {   // MMA issuer: whole warp, elected lane issues (see elect_one)
+      const bool leader = elect_one();
       const uint32_t idesc = idesc_bf16_m128_mn(p.n_tile);
       for (int it = 0; it < n_iters; ++it) {
         const int s = it % S;
         mbar_wait(&full_bar[s], (it / S) & 1);
         tc_fence_after();
         const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t b_base = a_base + p.halo_bytes;
+        const uint32_t b_lo = desc_lo_mn_sw128(a_base + p.halo_bytes, G_IMG);
+        if (leader) {
 #pragma unroll 1
-        for (int pair = 0; pair < 5; ++pair) {
-          const int ta = pair * 2, tb2 = min(pair * 2 + 1, 8);
-          const int sa = (ta / 3) * p.Wp + ta % 3, sb = (tb2 / 3) * p.Wp + tb2 % 3;   // halo slot of tile row 0
-          const uint32_t lbo = (uint32_t)(sb - sa) * 128u;
+          for (int pair = 0; pair < 5; ++pair) {
+            const int ta = pair * 2, tb2 = min(pair * 2 + 1, 8);
+            const int sa = (ta / 3) * p.Wp + ta % 3, sb = (tb2 / 3) * p.Wp + tb2 % 3;   // halo slot of tile row 0
+            const uint32_t a_lo = desc_lo_mn_sw128(a_base + (uint32_t)sa * 128u, (uint32_t)(sb - sa) * 128u);
+            const uint32_t d_tmem = tmem_base + pair * p.n_tile;
 #pragma unroll
-          for (int q = 0; q < 8; ++q)   // 16 slots (K) per UMMA
-            tc_mma_bf16(tmem_base + pair * p.n_tile, smem_desc_mn_sw128(a_base + (uint32_t)sa * 128u + q * 2048, lbo),
-                        smem_desc_mn_sw128(b_base + q * 2048, G_IMG), idesc, (it | q) != 0);
+            for (int q = 0; q < 8; ++q)   // 16 slots (K) per UMMA = 2048 bytes = descriptor address + 128
+              tc_mma_bf16_lohi(d_tmem, a_lo + q * 128, b_lo + q * 128, DESC_HI_SW128, idesc, (it | q) != 0);
+          }
+          tc_commit(&empty_bar[s]);
         }
-        tc_commit(&empty_bar[s]);
       }
-      tc_commit(&tmem_full_bar);
+      if (leader) tc_commit(&tmem_full_bar);
     }
   }
   __syncthreads();
