@@ -19,17 +19,19 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// bounded wait: a protocol bug traps instead of hanging the GPU
+// bounded wait: a protocol bug traps instead of hanging the GPU.  try_wait carries a suspend-time hint (20 us) so that a parked
+// thread may sleep in hardware instead of spinning through the issue slots (measured: no effect on kernel times either way --
+// the default try_wait already suspends -- kept because it bounds the loop in time rather than in iterations).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t addr = smem_u32(bar);
-  for (uint32_t it = 0; it < (1u << 22); ++it) {
+  for (uint32_t it = 0; it < (1u << 20); ++it) {
     uint32_t done;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(20000u)
         : "memory");
     if (done) return;
   }
