@@ -303,10 +303,10 @@ def main():
     achieved = conv_flops_step / (conv_ms_step * 1e-3) / 1e12 if conv_ms_step else None
     # DRAM bytes of the same launches from the committed ncu pass (profiles/): per step, like `achieved`
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1h_conv_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r1i_conv_traffic.json")
     if os.path.exists(tpath) and args.depth == 34 and Bsz == 256:
         tj = json.load(open(tpath))
-        traffic, traffic_src = tj["dram_bytes_per_step"], "profiles/r1h_conv_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum over the conv launches of one step)"
+        traffic, traffic_src = tj["dram_bytes_per_step"], "profiles/r1i_conv_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum over the conv launches of one step)"
     roofline = {"bound": "tensor", "kernel": "implicit-GEMM multigrid conv (fwd+dgrad+wgrad launches)",
                 "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": (achieved / tf_peak) if achieved else None,
                 "traffic": traffic, "traffic_unit": "bytes per step over the same launches", "traffic_source": traffic_src, "peak_source": which, "conv_ms_per_step": conv_ms_step, "conv_launches_per_step": prof["conv_launches"] / args.steps,
