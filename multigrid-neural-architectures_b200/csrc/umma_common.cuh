@@ -89,6 +89,15 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t da, uint64
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Position in a ring of n slots walked once per loop iteration k: idx = k % n, phase = (k / n) & 1, without the integer
+// divisions (ring sizes are run-time values; in the single-thread issue loops each emulated division is ~20 dependent
+// instructions, several per pipeline stage).
+struct Ring {
+  int idx; uint32_t phase; int n;
+  __device__ __forceinline__ explicit Ring(int n_) : idx(0), phase(0), n(n_) {}
+  __device__ __forceinline__ void next() { if (++idx == n) { idx = 0; phase ^= 1u; } }
+};
+
 // One lane of a fully converged warp (elect.sync): the MMA warp runs its issue loop with ALL lanes so that every operand stays
 // warp-uniform (uniform registers, no per-lane serialisation loop around each tcgen05.mma) and only the instruction itself is
 // predicated on the elected lane.  With `if (lane == 0)` around the whole loop the compiler cannot prove uniformity and wraps

@@ -437,10 +437,11 @@ __global__ void __launch_bounds__(H_THREADS, MT == 1 ? 4 : 3) umma_conv_halo_ker
     const int v = tid & 7;       // k-vector column of the chunk
     const int rg = tid >> 3;     // halo slots rg, rg+16, ...
     const int NB = p.n_abuf, lagA = NB - 1;   // one buffer: publish at once; two: publish the previous chunk
-    for (int c = 0; c < p.n_chunks + lagA; ++c) {
+    Ring ra(NB), rpub(NB);
+    for (int c = 0; c < p.n_chunks + lagA; ++c, ra.next()) {
       if (c < p.n_chunks) {
-        const int buf = c % NB;
-        if (c >= NB) mbar_wait(&a_empty[buf], ((c / NB) - 1) & 1);
+        const int buf = ra.idx;
+        if (c >= NB) mbar_wait(&a_empty[buf], ra.phase ^ 1u);
         const int r = c * KV_PER_STAGE + v;            // k-vector within a tap
         const bool kv_ok = r < p.kv_per_tap;
         int sg = 0;
@@ -475,7 +476,8 @@ __global__ void __launch_bounds__(H_THREADS, MT == 1 ? 4 : 3) umma_conv_halo_ker
       if (c >= lagA) {   // chunk c-lagA has landed for this thread
         cp_async_wait_dyn(lagA);
         fence_proxy_async();
-        mbar_arrive(&a_full[(c - lagA) % NB]);
+        mbar_arrive(&a_full[rpub.idx]);
+        rpub.next();
       }
     }
     // ================= epilogue (warps 0-3): TMEM -> registers -> bf16 NHWC rows ===========
@@ -550,9 +552,10 @@ __global__ void __launch_bounds__(H_THREADS, MT == 1 ? 4 : 3) umma_conv_halo_ker
       const uint8_t* wsrc = p.wpack + (size_t)ntile * n_st * b_stage_bytes;
       const uint32_t rank = CL > 1 ? cluster_ctarank() : 0;
       const uint32_t slice = (uint32_t)b_stage_bytes / CL;   // n_tile * 128 / CL: a multiple of 16 bytes
-      for (int ks = 0; ks < n_st; ++ks) {
-        const int s = ks % S;
-        if (ks >= S) mbar_wait(&empty_bar[s], ((ks / S) - 1) & 1);   // CL arrivals: every CTA of the cluster freed slot s
+      Ring rb(S);
+      for (int ks = 0; ks < n_st; ++ks, rb.next()) {
+        const int s = rb.idx;
+        if (ks >= S) mbar_wait(&empty_bar[s], rb.phase ^ 1u);   // CL arrivals: every CTA of the cluster freed slot s
         mbar_arrive_expect_tx(&full_bar[s], (uint32_t)b_stage_bytes);
         if (CL == 1)
           bulk_g2s(smem_u32(b_smem + (size_t)s * b_stage_bytes), wsrc + (size_t)ks * b_stage_bytes, (uint32_t)b_stage_bytes, &full_bar[s]);
@@ -569,20 +572,21 @@ __global__ void __launch_bounds__(H_THREADS, MT == 1 ? 4 : 3) umma_conv_halo_ker
       const uint32_t idesc = idesc_bf16_m128(p.n_tile);
       int ks = 0;
       long long wait_a = 0, wait_b = 0, tq = 0;
-      for (int c = 0; c < p.n_chunks; ++c) {
-        const int buf = c % p.n_abuf;
+      Ring ra(p.n_abuf), rb(S);
+      for (int c = 0; c < p.n_chunks; ++c, ra.next()) {
+        const int buf = ra.idx;
         if (tl) tq = clock64();
-        mbar_wait(&a_full[buf], (c / p.n_abuf) & 1);
+        mbar_wait(&a_full[buf], ra.phase);
         tc_fence_after();
         if (tl && c == 0 && lane == 0) tl[2] = clock64();
         if (tl && c > 0) wait_a += clock64() - tq;
         const uint32_t a_base = smem_u32(a_smem + (size_t)buf * p.halo_bytes);
         const int kv_here = min(KV_PER_STAGE, p.kv_per_tap - c * KV_PER_STAGE);
         const int ksteps = (kv_here + 1) >> 1;
-        for (int tap = 0; tap < KK; ++tap, ++ks) {
-          const int s = ks % S;
+        for (int tap = 0; tap < KK; ++tap, ++ks, rb.next()) {
+          const int s = rb.idx;
           if (tl) tq = clock64();
-          mbar_wait(&full_bar[s], (ks / S) & 1);
+          mbar_wait(&full_bar[s], rb.phase);
           tc_fence_after();
           if (tl) wait_b += clock64() - tq;
           const uint32_t a_lo = desc_lo_k_sw128(a_base + (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 128u);
@@ -678,7 +682,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
     const int Hs2 = p.H >> 1, Ws2 = p.W >> 1;
     const int total_chunks = n_my * p.n_chunks;
     int cur_it = -1;
-    for (int ac = grp; ac < total_chunks; ac += 2) {
+    Ring ra(NA);                       // this group's chunks are ac = grp, grp + 2, ...: the ring advances two slots per iteration
+    if (grp) ra.next();
+    for (int ac = grp; ac < total_chunks; ac += 2, ra.next(), ra.next()) {
       const int it = ac / p.n_chunks, c = ac - it * p.n_chunks;
       if (it != cur_it) {   // this group's slot tables of tile `it`
         cur_it = it;
@@ -700,8 +706,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
         }
         if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
       }
-      const int buf = ac % NA;
-      if (ac >= NA) mbar_wait(&a_empty[buf], ((ac / NA) - 1) & 1);
+      const int buf = ra.idx;
+      if (ac >= NA) mbar_wait(&a_empty[buf], ra.phase ^ 1u);
       const int r = c * KV_PER_STAGE + v;
       const bool kv_ok = r < p.kv_per_tap;
       int sg = 0;
@@ -817,14 +823,15 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
       const uint32_t idesc = idesc_bf16_m128(p.n_tile);
       const uint32_t b_base = smem_u32(b_smem);
       int ac = 0;
+      Ring ra(NA);
       mbar_wait(&b_full, 0);
       for (int it = 0; it < n_my; ++it) {
         const int acc = it & 1;
         if (it >= 2) { mbar_wait(&tmem_empty[acc], ((it >> 1) - 1) & 1); tc_fence_after(); }
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
-        for (int c = 0; c < p.n_chunks; ++c, ++ac) {
-          const int buf = ac % NA;
-          mbar_wait(&a_full[buf], (ac / NA) & 1);
+        for (int c = 0; c < p.n_chunks; ++c, ++ac, ra.next()) {
+          const int buf = ra.idx;
+          mbar_wait(&a_full[buf], ra.phase);
           tc_fence_after();
           const uint32_t a_base = smem_u32(a_smem + (size_t)buf * p.halo_bytes);
           const int kv_here = min(KV_PER_STAGE, p.kv_per_tap - c * KV_PER_STAGE);

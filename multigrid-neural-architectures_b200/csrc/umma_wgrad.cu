@@ -291,10 +291,11 @@ __global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __
     const int slots_per_img = p.Hp * p.Wp, Hs2 = p.H >> 1, Ws2 = p.W >> 1;
     const int chunks = p.n_blk * 8;               // 16-byte chunks per g row across the blocks
     const int L = p.lag;
-    for (int it = 0; it < n_iters + L; ++it) {
+    Ring rs(S), rpub(S);
+    for (int it = 0; it < n_iters + L; ++it, rs.next()) {
       if (it < n_iters) {
-        const int s = it % S, tb = (it / WH_TB) & 1, toff = (it % WH_TB) * 128;
-        if (it >= S) mbar_wait(&empty_bar[s], ((it / S) - 1) & 1);
+        const int s = rs.idx, tb = (it / WH_TB) & 1, toff = (it % WH_TB) * 128;
+        if (it >= S) mbar_wait(&empty_bar[s], rs.phase ^ 1u);
         // slot -> pixel table of the next WH_TB tiles (consecutive tiles are consecutive slot ranges, so tile j of the group reads
         // the same table 128 * j entries further on): one table computation and one barrier of the 16 loader warps per WH_TB
         // tiles instead of per tile (measured: table + barrier were ~13 % of the kernel).  Double buffered: a thread can only
@@ -365,7 +366,8 @@ __global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __
       if (it >= L) {
         cp_async_wait_dyn(L);
         fence_proxy_async();
-        mbar_arrive(&full_bar[(it - L) % S]);
+        mbar_arrive(&full_bar[rpub.idx]);
+        rpub.next();
       }
     }
     // ---- epilogue (warps 0-3: one TMEM lane quarter each): five accumulators -> partial sums --------
@@ -409,9 +411,10 @@ __global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __
     {   // MMA issuer: whole warp, elected lane issues (see elect_one)
       const bool leader = elect_one();
       const uint32_t idesc = idesc_bf16_m128_mn(p.n_tile);
-      for (int it = 0; it < n_iters; ++it) {
-        const int s = it % S;
-        mbar_wait(&full_bar[s], (it / S) & 1);
+      Ring rs(S);
+      for (int it = 0; it < n_iters; ++it, rs.next()) {
+        const int s = rs.idx;
+        mbar_wait(&full_bar[s], rs.phase);
         tc_fence_after();
         const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
         const uint32_t b_lo = desc_lo_mn_sw128(a_base + p.halo_bytes, G_IMG);
