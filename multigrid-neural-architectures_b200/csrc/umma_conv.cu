@@ -158,10 +158,11 @@ __global__ void __launch_bounds__(N_THREADS, 4) umma_conv_kernel(const __grid_co
         flags[it] = f;
       }
       const uint32_t dst_thread = (uint32_t)(rg * 128 + ((v ^ (rg & 7)) << 4));  // (it*16+rg)&7 == rg&7
-      for (int ks = 0; ks < p.n_stages + L; ++ks) {
+      Ring rs(S), rpub(S);
+      for (int ks = 0; ks < p.n_stages + L; ++ks, rs.next()) {
         if (ks < p.n_stages) {
-          const int s = ks % S;
-          if (ks >= S) mbar_wait(&empty_bar[s], ((ks / S) - 1) & 1);
+          const int s = rs.idx;
+          if (ks >= S) mbar_wait(&empty_bar[s], rs.phase ^ 1u);
           const int j = ks * KV_PER_STAGE + v;
           const bool kv_ok = j < p.nkv;
           int tap = 0, r = 0, sg = 0;
@@ -203,7 +204,8 @@ __global__ void __launch_bounds__(N_THREADS, 4) umma_conv_kernel(const __grid_co
         if (ks >= L) {
           cp_async_wait_dyn(L);
           fence_proxy_async();
-          mbar_arrive(&full_bar[(ks - L) % S]);
+          mbar_arrive(&full_bar[rpub.idx]);
+          rpub.next();
         }
       }
     } else {
@@ -220,10 +222,11 @@ __global__ void __launch_bounds__(N_THREADS, 4) umma_conv_kernel(const __grid_co
         rix[it] = valid ? (int)(ri & 1023) * p.stride - p.pad : -(1 << 20);
       }
       const uint32_t dst_thread = (uint32_t)(rg * 128 + ((v ^ (rg & 7)) << 4));          // (it*16+rg)&7 == rg&7
-      for (int ks = 0; ks < p.n_stages + L; ++ks) {
+      Ring rs(S), rpub(S);
+      for (int ks = 0; ks < p.n_stages + L; ++ks, rs.next()) {
         if (ks < p.n_stages) {
-          const int s = ks % S;
-          if (ks >= S) mbar_wait(&empty_bar[s], ((ks / S) - 1) & 1);
+          const int s = rs.idx;
+          if (ks >= S) mbar_wait(&empty_bar[s], rs.phase ^ 1u);
           // decode this lane's k-vector: (tap, segment, channel offset)
           const int j = ks * KV_PER_STAGE + v;
           const bool kv_ok = j < p.nkv;
@@ -251,7 +254,8 @@ __global__ void __launch_bounds__(N_THREADS, 4) umma_conv_kernel(const __grid_co
         if (ks >= L) {  // stage ks-L has landed for this thread: publish it to the tensor core (async proxy)
           cp_async_wait_dyn(L);
           fence_proxy_async();
-          mbar_arrive(&full_bar[(ks - L) % S]);
+          mbar_arrive(&full_bar[rpub.idx]);
+          rpub.next();
         }
       }
     }
@@ -289,9 +293,10 @@ __global__ void __launch_bounds__(N_THREADS, 4) umma_conv_kernel(const __grid_co
     // ================= B loader: one bulk copy per stage =====================================
     if (lane == 0) {
       const uint8_t* wsrc = p.wpack + (size_t)ntile * p.n_stages * b_stage_bytes;
-      for (int ks = 0; ks < p.n_stages; ++ks) {
-        const int s = ks % S;
-        if (ks >= S) mbar_wait(&empty_bar[s], ((ks / S) - 1) & 1);
+      Ring rs(S);
+      for (int ks = 0; ks < p.n_stages; ++ks, rs.next()) {
+        const int s = rs.idx;
+        if (ks >= S) mbar_wait(&empty_bar[s], rs.phase ^ 1u);
         mbar_arrive_expect_tx(&full_bar[s], (uint32_t)b_stage_bytes);
         bulk_g2s(smem_u32(b_smem + (size_t)s * b_stage_bytes), wsrc + (size_t)ks * b_stage_bytes, (uint32_t)b_stage_bytes, &full_bar[s]);
       }
@@ -301,9 +306,10 @@ __global__ void __launch_bounds__(N_THREADS, 4) umma_conv_kernel(const __grid_co
     {
       const bool leader = elect_one();
       const uint32_t idesc = idesc_bf16_m128(p.n_tile);
-      for (int ks = 0; ks < p.n_stages; ++ks) {
-        const int s = ks % S;
-        mbar_wait(&full_bar[s], (ks / S) & 1);
+      Ring rs(S);
+      for (int ks = 0; ks < p.n_stages; ++ks, rs.next()) {
+        const int s = rs.idx;
+        mbar_wait(&full_bar[s], rs.phase);
         tc_fence_after();
         const uint32_t a_lo = desc_lo_k_sw128(smem_u32(a_smem + (size_t)s * A_STAGE_BYTES));
         const uint32_t b_lo = desc_lo_k_sw128(smem_u32(b_smem + (size_t)s * b_stage_bytes));

@@ -104,10 +104,11 @@ __global__ void __launch_bounds__(W_THREADS, 2) umma_wgrad_kernel(const __grid_c
     const int g_per_thread = (PIX * chunks) / N_PROD;
     const int L = p.lag;
 
-    for (int it = 0; it < n_iters + L; ++it) {
+    Ring rs(S), rpub(S);
+    for (int it = 0; it < n_iters + L; ++it, rs.next()) {
       if (it < n_iters) {
-        const int s = it % S;
-        if (it >= S) mbar_wait(&empty_bar[s], ((it / S) - 1) & 1);
+        const int s = rs.idx;
+        if (it >= S) mbar_wait(&empty_bar[s], rs.phase ^ 1u);
         uint8_t* st = smem + (size_t)s * stage_bytes;
         const uint32_t a_dst = smem_u32(st) + blk * A_IMG;
         const int64_t mbase = pix0 + (int64_t)it * PIX;
@@ -154,7 +155,8 @@ __global__ void __launch_bounds__(W_THREADS, 2) umma_wgrad_kernel(const __grid_c
       if (it >= L) {
         cp_async_wait_dyn(L);
         fence_proxy_async();
-        mbar_arrive(&full_bar[(it - L) % S]);
+        mbar_arrive(&full_bar[rpub.idx]);
+        rpub.next();
       }
     }
     // ---- epilogue: TMEM -> fp32 reductions into dW --------------------------------------------
@@ -191,9 +193,10 @@ __global__ void __launch_bounds__(W_THREADS, 2) umma_wgrad_kernel(const __grid_c
     {
       const bool leader = elect_one();
       const uint32_t idesc = idesc_bf16_m128_mn(p.n_tile);
-      for (int it = 0; it < n_iters; ++it) {
-        const int s = it % S;
-        mbar_wait(&full_bar[s], (it / S) & 1);
+      Ring rs(S);
+      for (int it = 0; it < n_iters; ++it, rs.next()) {
+        const int s = rs.idx;
+        mbar_wait(&full_bar[s], rs.phase);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
         const uint32_t a_lo = desc_lo_mn_sw128(a_addr, A_IMG), b_lo = desc_lo_mn_sw128(a_addr + 2 * A_IMG, A_IMG);
