@@ -159,20 +159,20 @@ __global__ void __launch_bounds__(N_THREADS, 4) umma_conv_kernel(const __grid_co
       }
       const uint32_t dst_thread = (uint32_t)(rg * 128 + ((v ^ (rg & 7)) << 4));  // (it*16+rg)&7 == rg&7
       Ring rs(S), rpub(S);
+      // this thread's k-vector j = ks * 8 + v as (tap = (ty, tx), r): carried along instead of three divisions per stage
+      int tap = v / p.kv_per_tap, r = v - tap * p.kv_per_tap;
+      int ty = tap / p.k, tx = tap - ty * p.k;
       for (int ks = 0; ks < p.n_stages + L; ++ks, rs.next()) {
         if (ks < p.n_stages) {
           const int s = rs.idx;
           if (ks >= S) mbar_wait(&empty_bar[s], rs.phase ^ 1u);
           const int j = ks * KV_PER_STAGE + v;
           const bool kv_ok = j < p.nkv;
-          int tap = 0, r = 0, sg = 0;
-          if (kv_ok) {
-            tap = j / p.kv_per_tap; r = j - tap * p.kv_per_tap;
-            while (sg + 1 < p.n_seg && r >= s_seg[sg + 1].kv_begin) ++sg;
-          }
+          int sg = 0;
+          if (kv_ok) while (sg + 1 < p.n_seg && r >= s_seg[sg + 1].kv_begin) ++sg;
           const USeg sgm = s_seg[sg];
           const int c8 = r - sgm.kv_begin;
-          const int dy = tap / p.k - p.pad, dx = tap % p.k - p.pad;
+          const int dy = ty - p.pad, dx = tx - p.pad;
           const uint32_t dst0 = smem_u32(a_smem + (size_t)s * A_STAGE_BYTES) + dst_thread;
           const uint32_t tapbit = kv_ok ? (1u << tap) : 0u;
           const uint32_t pitch = (uint32_t)sgm.Cp * 2u;
@@ -199,6 +199,8 @@ __global__ void __launch_bounds__(N_THREADS, 4) umma_conv_kernel(const __grid_co
               cp_async16(dst0 + it * 2048, src, ok ? 16u : 0u);
             }
           }
+          r += KV_PER_STAGE;
+          while (r >= p.kv_per_tap) { r -= p.kv_per_tap; ++tap; if (++tx == p.k) { tx = 0; ++ty; } }
         }
         cp_async_commit();
         if (ks >= L) {
@@ -223,20 +225,19 @@ __global__ void __launch_bounds__(N_THREADS, 4) umma_conv_kernel(const __grid_co
       }
       const uint32_t dst_thread = (uint32_t)(rg * 128 + ((v ^ (rg & 7)) << 4));          // (it*16+rg)&7 == rg&7
       Ring rs(S), rpub(S);
+      int tap = v / p.kv_per_tap, r = v - tap * p.kv_per_tap;
+      int ty = tap / p.k, tx = tap - ty * p.k;
       for (int ks = 0; ks < p.n_stages + L; ++ks, rs.next()) {
         if (ks < p.n_stages) {
           const int s = rs.idx;
           if (ks >= S) mbar_wait(&empty_bar[s], rs.phase ^ 1u);
-          // decode this lane's k-vector: (tap, segment, channel offset)
+          // decode this lane's k-vector: (tap = (ty, tx), segment, channel offset), carried along from stage to stage
           const int j = ks * KV_PER_STAGE + v;
           const bool kv_ok = j < p.nkv;
-          int tap = 0, r = 0, sg = 0;
-          if (kv_ok) {
-            tap = j / p.kv_per_tap; r = j - tap * p.kv_per_tap;
-            while (sg + 1 < p.n_seg && r >= s_seg[sg + 1].kv_begin) ++sg;
-          }
+          int sg = 0;
+          if (kv_ok) while (sg + 1 < p.n_seg && r >= s_seg[sg + 1].kv_begin) ++sg;
           const USeg sgm = s_seg[sg];
-          const int dy = kv_ok ? tap / p.k : -(1 << 20), dx = tap % p.k;
+          const int dy = kv_ok ? ty : -(1 << 20), dx = tx;
           const char* base = reinterpret_cast<const char*>(sgm.ptr) + (r - sgm.kv_begin) * 16;
           const uint32_t pitch = (uint32_t)sgm.Cp * 2u;
           const int plane = sgm.Hs * sgm.Ws;
@@ -249,6 +250,8 @@ __global__ void __launch_bounds__(N_THREADS, 4) umma_conv_kernel(const __grid_co
             const char* src = ok ? base + pixel * pitch : reinterpret_cast<const char*>(sgm.ptr);
             cp_async16(dst0 + it * 2048, src, ok ? 16u : 0u);
           }
+          r += KV_PER_STAGE;
+          while (r >= p.kv_per_tap) { r -= p.kv_per_tap; if (++tx == p.k) { tx = 0; ++ty; } }
         }
         cp_async_commit();
         if (ks >= L) {  // stage ks-L has landed for this thread: publish it to the tensor core (async proxy)
@@ -690,8 +693,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
     int cur_it = -1;
     Ring ra(NA);                       // this group's chunks are ac = grp, grp + 2, ...: the ring advances two slots per iteration
     if (grp) ra.next();
-    for (int ac = grp; ac < total_chunks; ac += 2, ra.next(), ra.next()) {
-      const int it = ac / p.n_chunks, c = ac - it * p.n_chunks;
+    int it = grp / p.n_chunks, c = grp - it * p.n_chunks;      // (tile, chunk) of ac, carried along
+    for (int ac = grp; ac < total_chunks; ac += 2, ra.next(), ra.next(), c += 2) {
+      while (c >= p.n_chunks) { c -= p.n_chunks; ++it; }
       if (it != cur_it) {   // this group's slot tables of tile `it`
         cur_it = it;
         const int64_t t0 = (int64_t)(blockIdx.x + it * gridDim.x) * BM;
