@@ -12,6 +12,20 @@ typedef __nv_bfloat16 bf16;
 
 struct V8 { float v[8]; };
 
+// (a, b, c, d) with i = ((a * nb + b) * nc + c) * nd + d.  Work items of these passes are far below 2^32, where the four
+// divisions are 32-bit (a 64-bit division is ~100 instructions -- more than the rest of a thread's work in the apply pass).
+__device__ __forceinline__ void split4(int64_t i, int nb, int nc, int nd, int& a, int& b, int& c, int& d) {
+  if (i < ((int64_t)1 << 32)) {
+    uint32_t q = (uint32_t)i, t;
+    t = q / (uint32_t)nd; d = (int)(q - t * (uint32_t)nd); q = t;
+    t = q / (uint32_t)nc; c = (int)(q - t * (uint32_t)nc); q = t;
+    t = q / (uint32_t)nb; b = (int)(q - t * (uint32_t)nb); a = (int)t;
+  } else {
+    int64_t q = i;
+    d = (int)(q % nd); q /= nd; c = (int)(q % nc); q /= nc; b = (int)(q % nb); a = (int)(q / nb);
+  }
+}
+
 __device__ __forceinline__ V8 ld8(const bf16* p) {
   const uint4 u = *reinterpret_cast<const uint4*>(p);
   V8 r;
@@ -122,9 +136,8 @@ __global__ void __launch_bounds__(256, 4) apply_bf16_kernel(const __grid_constan
   const int64_t total = (int64_t)p.N * p.Hp * p.Wp * V;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int vc = (int)(i % V); int64_t q = i / V;
-  const int px = (int)(q % p.Wp); q /= p.Wp;
-  const int py = (int)(q % p.Hp); const int n = (int)(q / p.Hp);
+  int n, py, px, vc;
+  split4(i, p.Hp, p.Wp, V, n, py, px, vc);
   const int c0 = vc * 8;
   float sc[8], sh[8];
   const bool has_aff = p.bn || p.scale != nullptr;
@@ -256,8 +269,8 @@ __global__ void __launch_bounds__(256, NS < 0 ? 3 : 2) combine_bf16_kernel(const
 
   if (active)
     for (int64_t blk = b_begin + lane; blk < b_end; blk += lanes) {
-      const int bx = (int)(blk % p.Wb); int64_t q = blk / p.Wb;
-      const int by = (int)(q % p.Hb); const int n = (int)(q / p.Hb);
+      int n, by, bx, unused_;
+      split4(blk, p.Hb, p.Wb, 1, n, by, bx, unused_);
       const int y0 = 2 * by, x0 = 2 * bx;
       const bool vy1 = y0 + 1 < p.H, vx1 = x0 + 1 < p.W;
       const bool valid[4] = {true, vx1, vy1, vy1 && vx1};
@@ -455,9 +468,8 @@ __global__ void __launch_bounds__(256) pool3_bf16_kernel(const bf16* __restrict_
   const int V = cp >> 3;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)N * Ho * Wo * V) return;
-  const int vc = (int)(i % V); int64_t q = i / V;
-  const int ox = (int)(q % Wo); q /= Wo;
-  const int oy = (int)(q % Ho); const int n = (int)(q / Ho);
+  int n, oy, ox, vc;
+  split4(i, Ho, Wo, V, n, oy, ox, vc);
   const int c0 = vc * 8;
   float best[8]; int bc[8];
 #pragma unroll
@@ -503,9 +515,8 @@ __global__ void __launch_bounds__(256) pool_vec_kernel(const bf16* __restrict__ 
   const int V = cp >> 3;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)N * Ho * Wo * V) return;
-  const int vc = (int)(i % V); int64_t q = i / V;
-  const int ox = (int)(q % Wo); q /= Wo;
-  const int oy = (int)(q % Ho); const int n = (int)(q / Ho);
+  int n, oy, ox, vc;
+  split4(i, Ho, Wo, V, n, oy, ox, vc);
   const int c0 = vc * 8;
   float acc[8];
 #pragma unroll
@@ -538,9 +549,8 @@ __global__ void __launch_bounds__(256) im2col_bf16_kernel(const bf16* __restrict
   const int V = cp_col >> 3;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)N * Ho * Wo * V) return;
-  const int vc = (int)(i % V); int64_t q = i / V;
-  const int ox = (int)(q % Wo); q /= Wo;
-  const int oy = (int)(q % Ho); const int n = (int)(q / Ho);
+  int n, oy, ox, vc;
+  split4(i, Ho, Wo, V, n, oy, ox, vc);
   const int kk = k * k, K = C * kk;
   const bf16* img = in + (int64_t)n * H * W * cp_in;
   const unsigned short* img16 = reinterpret_cast<const unsigned short*>(img);
