@@ -9,6 +9,10 @@ torch.manual_seed(5)
 net = B.load_net(sys.argv[2] if len(sys.argv) > 2 else "cifar/rnmg")
 mn = "mnist" in (sys.argv[2] if len(sys.argv) > 2 else "")
 pm = net.createModel(B.Opt(nLayer=1, nGPU=1, dataset="mnist-spt") if mn else B.Opt(nLayer=1, nGPU=1)); pm.precision = sys.argv[1]; pm.cuda()
+if os.environ.get("BN_BIAS"):
+    for m in pm.listModules():
+        if m.typename == "nn.SpatialBatchNormalization":
+            m.bias.fill_(float(os.environ["BN_BIAS"]))
 params, grads = pm.getParameters()
 crit = net.createCriterion()
 g = torch.Generator(device="cpu").manual_seed(9)
