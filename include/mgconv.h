@@ -269,6 +269,10 @@ int mg_sgd_step(mg_ctx* ctx, float* w, const float* g, float* v, int64_t n,
 int mg_comm_unique_id(void* out128);                                  /* ncclGetUniqueId */
 int mg_comm_init(mg_ctx* ctx, int rank, int nranks, const void* id128);
 int mg_comm_destroy(mg_ctx* ctx);
+/* lend the communicator of `owner` (same device) to ctx: plans come and go with the input shape (the partial last
+ * batch of pipelines/standard/test.lua:40-44 rebuilds them), the NCCL communicator must not.  ctx gets its own
+ * communication stream; destroying ctx leaves the communicator alone, the owner must outlive every borrower. */
+int mg_comm_share(mg_ctx* ctx, const mg_ctx* owner);
 /* in-place sum all-reduce on the context's communication stream, ordered after everything
  * enqueued so far on the compute stream; mg_allreduce_wait makes the compute stream wait */
 int mg_allreduce_launch(mg_ctx* ctx, void* buf, int64_t count, int is_double);

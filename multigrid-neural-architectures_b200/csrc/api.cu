@@ -305,9 +305,28 @@ int mg_comm_init(mg_ctx* ctx, int rank, int nranks, const void* id128) {
   return MG_OK;
 }
 
+// The communicator outlives the per-shape plans: a host keeps ONE owner context per device (mg_comm_init once) and lends its
+// communicator to every working context (a new one whenever the input shape changes -- the partial last batch of
+// pipelines/standard/test.lua:40-44).  The borrower gets its own communication stream and events.
+int mg_comm_share(mg_ctx* ctx, const mg_ctx* owner) {
+  if (!ctx || !owner) return MG_ERR_INVALID_ARG;
+  MG_REQUIRE(ctx, owner->nccl_comm != nullptr, MG_ERR_NCCL, "comm_share: the owner has no communicator (mg_comm_init it first)");
+  MG_REQUIRE(ctx, owner->device == ctx->device, MG_ERR_INVALID_ARG, "comm_share: owner on device %d, context on %d", owner->device, ctx->device);
+  if (ctx->nccl_comm == owner->nccl_comm) return MG_OK;
+  MG_REQUIRE(ctx, ctx->nccl_comm == nullptr, MG_ERR_INVALID_ARG, "comm_share: the context already has a communicator");
+  MG_CUDA(ctx, cudaSetDevice(ctx->device));
+  MG_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  MG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming));
+  MG_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_comm, cudaEventDisableTiming));
+  ctx->nccl_comm = owner->nccl_comm; ctx->comm_borrowed = 1;
+  ctx->rank = owner->rank; ctx->nranks = owner->nranks;
+  return MG_OK;
+}
+
 int mg_comm_destroy(mg_ctx* ctx) {
   if (!ctx) return MG_ERR_INVALID_ARG;
-  if (ctx->nccl_comm) { g_nccl.CommDestroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
+  if (ctx->nccl_comm && !ctx->comm_borrowed) g_nccl.CommDestroy(ctx->nccl_comm);
+  ctx->nccl_comm = nullptr; ctx->comm_borrowed = 0;
   if (ctx->comm_stream) { cudaStreamDestroy(ctx->comm_stream); ctx->comm_stream = nullptr; }
   if (ctx->ev_compute) { cudaEventDestroy(ctx->ev_compute); ctx->ev_compute = nullptr; }
   if (ctx->ev_comm) { cudaEventDestroy(ctx->ev_comm); ctx->ev_comm = nullptr; }

@@ -22,6 +22,7 @@ struct mg_ctx {
   cudaStream_t comm_stream;
   cudaEvent_t ev_compute, ev_comm;
   int rank, nranks;
+  int comm_borrowed;   // mg_comm_share: nccl_comm belongs to another context (never destroyed here)
   // optional CUDA-event timing of the convolution kernels (bench.py roofline)
   int profile;
   void* prof;  // ProfState*

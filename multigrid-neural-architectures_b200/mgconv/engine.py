@@ -129,6 +129,10 @@ class Engine:
             cnt = collections.Counter((o.H, o.CcatP, o.Cout, names[getattr(o.desc, field)]) for o in self.conv_ops if o._tunable())
             print(f"[mgconv] autotune {field}: " + ", ".join(f"{h}x{h} {ci}->{co}: {a} x{n}" for (h, ci, co, a), n in sorted(cnt.items())), flush=True)
 
+    def set_bn_sync(self, nranks):
+        """0 = per-replica BatchNorm statistics (the reference's DataParallelTable), N = statistics over N equal shards"""
+        self.bn_sync = int(nranks)
+
     def _use_lanes(self):
         # cross-replica BatchNorm issues NCCL calls from inside the chains: those must stay on one stream
         return self.n_lanes > 1 and not self.bn_sync

@@ -112,6 +112,7 @@ SIGNATURES = {
     "mg_comm_unique_id": (_I, [_P]),
     "mg_comm_init": (_I, [_P, _I, _I, _P]),
     "mg_comm_destroy": (_I, [_P]),
+    "mg_comm_share": (_I, [_P, _P]),
     "mg_allreduce_launch": (_I, [_P, _P, _I64, _I]),
     "mg_allreduce_wait": (_I, [_P]),
     "mg_allreduce_inline": (_I, [_P, _P, _I64, _I]),

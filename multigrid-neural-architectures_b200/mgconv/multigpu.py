@@ -62,10 +62,13 @@ class DataParallel:
                               "(one process per GPU: torchrun --nproc-per-node nGPU)")
         self.flat = self.gflat = None
         self.buckets = []
-        self._comm_ready = False
+        self._comm = None          # ffi.Context that OWNS the NCCL communicator; engines borrow it (mg_comm_share)
         self._owner = {}
         self.needsSync = False
         self.train = True
+        self._grads_clean = False  # True right after zeroGradParameters(): backward may all-reduce gflat in place
+        self._gprev = None         # stash of the already reduced micro-batch gradients (-iterSize > 1)
+        self._shards = {}          # local batch size -> (global batch size) agreed on by all ranks
 
     # ---- module protocol passthrough ----------------------------------------------------
     def __getattr__(self, name):
@@ -73,6 +76,25 @@ class DataParallel:
 
     def listModules(self):
         return self.model.listModules()
+
+    # methods of the wrapped model that return `self` must return the WRAPPER (model = model:cuda() keeps the DPT)
+    def cuda(self, device=None):
+        self.model.cuda(device)
+        self.flat = self.gflat = None
+        return self
+
+    def float(self):
+        self.model.float()
+        self.flat = self.gflat = None
+        return self
+
+    def clearState(self):
+        self.model.clearState()
+        return self
+
+    def zeroGradParameters(self):
+        self.model.zeroGradParameters()
+        self._grads_clean = True
 
     def training(self):
         self.train = True
@@ -111,8 +133,16 @@ class DataParallel:
         self.needsSync = False
 
     def _init_comm(self, eng):
-        if self._comm_ready or self.world == 1:
+        """one NCCL communicator per DataParallel, owned by a context of its own: engines are rebuilt whenever the
+        input shape changes (the partial last batch of pipelines/standard/test.lua:40-44), the communicator is not"""
+        if self.world == 1:
             return
+        if self._comm is not None:
+            if not getattr(eng, "_comm_shared", False):
+                eng.ctx.call("mg_comm_share", self._comm.h)
+                eng._comm_shared = True
+            return
+        self._comm = ffi.Context(eng.device.index, 0, ffi.MG_F32)
         uid = torch.zeros(128, dtype=torch.uint8)
         if self.rank == 0:
             ffi_rc = ffi.lib.mg_comm_unique_id(C.c_void_p(uid.data_ptr()))
@@ -124,33 +154,84 @@ class DataParallel:
             uid = u.cpu()
         else:
             dist.broadcast(uid, 0, group=self.group)
-        eng.ctx.call("mg_comm_init", self.rank, self.world, C.c_void_p(uid.data_ptr()))
-        self._comm_ready = True
+        self._comm.call("mg_comm_init", self.rank, self.world, C.c_void_p(uid.data_ptr()))
+        eng.ctx.call("mg_comm_share", self._comm.h)
+        eng._comm_shared = True
+
+    def _agree_on_shards(self, local_B):
+        """DataParallelTable splits dim 1 into ceil(B/nGPU) chunks (multigpu.lua:87): shards may be unequal (B = 10 on 4 GPUs
+        gives 3,3,3,1).  The criterion averages over the LOCAL shard, so a rank's gradient weighs local_B / global_B of the
+        global-mean loss; cross-replica BatchNorm needs the global element count.  An empty shard cannot run."""
+        if local_B not in self._shards:
+            sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(self.world)]
+            mine = torch.tensor([local_B], dtype=torch.int64)
+            if self.world > 1:
+                if dist.get_backend(self.group) == "nccl":
+                    dev = torch.device("cuda", torch.cuda.current_device())
+                    sizes = [t.to(dev) for t in sizes]
+                    dist.all_gather(sizes, mine.to(dev), group=self.group)
+                else:
+                    dist.all_gather(sizes, mine, group=self.group)
+            else:
+                sizes = [mine]
+            sizes = [int(t.item()) for t in sizes]
+            if min(sizes) <= 0:
+                raise ffi.MGError(f"makeDataParallel: shard sizes {sizes}: a rank without images cannot take part in the step "
+                                  "(global batch smaller than ceil(B/nGPU) * (nGPU-1) + 1)")
+            self._shards[local_B] = (sum(sizes), len(set(sizes)) == 1)
+        return self._shards[local_B]
+
+    def _attach(self, eng, input):
+        """bind a (new or cached) engine to this wrapper BEFORE it runs: bucket triggers, communicator, shard weights"""
+        if self.world == 1:
+            return
+        ts = input
+        while isinstance(ts, (list, tuple)):
+            ts = ts[0]
+        local_B = int(ts.shape[0])
+        global_B, equal = self._agree_on_shards(local_B)
+        if self.bnSync and not equal:
+            # the BatchNorm backward mixes the gradients of all ranks; with unequal shards the criteria's 1/local_B
+            # weights differ per rank and the mixed sums would be wrong
+            raise ffi.MGError("-bnSync needs equal shards on every rank (global batch divisible by nGPU)")
+        eng.shard = (local_B, global_B)
+        self._init_comm(eng)
+        if self.gflat is not None:
+            eng.on_param_done = self._param_done
+        eng.set_bn_sync(self.world if self.bnSync else 0)
 
     def forward(self, input):
-        out = self.model.forward(input)
-        eng = self.model._engine
-        if self.world > 1 and eng.on_param_done is None and self.gflat is not None:
-            self._init_comm(eng)
-            eng.on_param_done = self._param_done
-            if self.bnSync:
-                # -bnSync: BatchNorm statistics over the GLOBAL batch (one tiny all-reduce of the per-channel
-                # sums per BN layer, forward and backward) -- equals the single-device result on the whole
-                # batch.  The first forward above still used local statistics: redo it.
-                eng.bn_sync = self.world
-                out = self.model.forward(input)
-        return out
+        # -bnSync: BatchNorm statistics over the GLOBAL batch (one tiny all-reduce of the per-channel sums per BN
+        # layer, forward and backward) -- equals the single-device result on the whole batch.  The engine is bound
+        # before it runs, so the first forward already uses global statistics (no second running-statistics update).
+        eng = self.model._get_engine(input)
+        self._attach(eng, input)
+        return self.model.forward(input)
 
     def backward(self, input, gradOutput, scale=1.0):
-        if self.gflat is not None:
-            self._reset_buckets()
-        gi = self.model.backward(input, gradOutput, scale / self.world)
-        if self.world > 1 and self.gflat is not None:
-            eng = self.model._engine
-            for b, (off, cnt, _) in enumerate(self.buckets):   # parameters the plan never touched
-                if b not in self.launched:
-                    eng.ctx.call("mg_allreduce_launch", ptr(self.gflat[off:off + cnt]), cnt, 0)
-            eng.ctx.call("mg_allreduce_wait")
+        eng = self.model._engine if input is None else self.model._get_engine(input)
+        if self.world == 1 or self.gflat is None:
+            return self.model.backward(input, gradOutput, scale)
+        self._reset_buckets()
+        # Gradient accumulation (-iterSize, model.lua:39-44; pipelines/standard/train.lua:147-169 zeroes the gradients only
+        # before the first micro-batch): backward ACCUMULATES into gflat, so all-reducing gflat in place would sum the
+        # already reduced earlier micro-batches once more per rank.  Unless the gradients were zeroed since the last
+        # backward, set the reduced part aside, reduce only what this backward produces, and add it back.
+        stash = not self._grads_clean
+        self._grads_clean = False
+        if stash:
+            if self._gprev is None:
+                self._gprev = torch.empty_like(self.gflat)
+            self._gprev.copy_(self.gflat)
+            self.gflat.zero_()
+        local_B, global_B = getattr(eng, "shard", (1, self.world))
+        gi = self.model.backward(input, gradOutput, scale * local_B / global_B)
+        for b, (off, cnt, _) in enumerate(self.buckets):   # parameters the plan never touched
+            if b not in self.launched:
+                eng.ctx.call("mg_allreduce_launch", ptr(self.gflat[off:off + cnt]), cnt, 0)
+        eng.ctx.call("mg_allreduce_wait")
+        if stash:
+            self.gflat.add_(self._gprev)
         return gi
 
     def _param_done(self, mod):
@@ -191,12 +272,20 @@ def makeDataParallel(model, nGPU, net=None, bnSync=False):
     return model
 
 
+_BUFFERS = ("running_mean", "running_var")
+
+
 def _state(model):
+    """what a checkpoint holds per module: its parameters and BatchNorm running statistics -- saveDataParallel clears
+    output / gradInput of every module before saving (multigpu.lua:110-131), so no activation is ever stored"""
     m = model.model if isinstance(model, DataParallel) else model
     st = []
     for mod in m.listModules():
-        d = {k: v.detach().cpu().clone() for k, v in vars(mod).items()
-             if isinstance(v, torch.Tensor) and not k.startswith("grad") and not k.startswith("_")}
+        d = {name: w.detach().cpu().clone() for name, w, _ in mod.own_parameters()}
+        for k in _BUFFERS:
+            v = getattr(mod, k, None)
+            if isinstance(v, torch.Tensor):
+                d[k] = v.detach().cpu().clone()
         st.append((mod.typename, d))
     return st
 
@@ -224,7 +313,14 @@ def _load_into(model, filename):
         if tn != mod.typename:
             raise ffi.MGError(f"{filename}: module type {tn} does not match {mod.typename}")
         for k, v in d.items():
-            getattr(mod, k).copy_(v)
+            dst = getattr(mod, k, None)
+            if not isinstance(dst, torch.Tensor):
+                if k in ("output", "gradInput"):     # files written before the state was restricted to parameters
+                    continue
+                raise ffi.MGError(f"{filename}: {tn} has no tensor field '{k}'")
+            if tuple(dst.shape) != tuple(v.shape):
+                raise ffi.MGError(f"{filename}: {tn}.{k} is {tuple(v.shape)} in the file, {tuple(dst.shape)} in the model")
+            dst.copy_(v)
     return model
 
 
@@ -233,7 +329,8 @@ def loadDataParallel(filename, nGPU, net, opt):
     o = type(opt)(opt)
     o["nGPU"] = 1
     model = _load_into(net.createModel(o), filename)
-    return makeDataParallel(model, nGPU, net)
+    bn_sync = bool(opt.get("bnSync", False)) if hasattr(opt, "get") else bool(getattr(opt, "bnSync", False))
+    return makeDataParallel(model, nGPU, net, bnSync=bn_sync)
 
 
 def loadAndRemoveDPT(filename, net, opt):

@@ -20,6 +20,8 @@ import torch
 
 from . import lower as L
 
+MAX_ENGINES = 3   # lowered plans (with their activation buffers) kept per top-level module, one per input shape
+
 
 # ------------------------------------------------------------------------------------
 class Module:
@@ -116,6 +118,7 @@ class Module:
     def clearState(self):
         for m in self.listModules():
             m._engine = None
+            m._engines = None
             m.output = None
             m.gradInput = None
         return self
@@ -126,7 +129,18 @@ class Module:
         from .engine import engine_key
         key = engine_key(input)
         if self._engine is None or self._engine.key != key:
-            self._engine = Engine(self, input)
+            # plans are kept per input shape (most recent MAX_ENGINES): the reference's loop alternates between the training
+            # batch and the partial last batch of the test pass (pipelines/standard/test.lua:40-44) every epoch
+            cache = getattr(self, "_engines", None)
+            if cache is None:
+                cache = self._engines = {}
+            eng = cache.pop(key, None)
+            if eng is None:
+                eng = Engine(self, input)
+                while len(cache) >= MAX_ENGINES:
+                    cache.pop(next(iter(cache)))
+            cache[key] = eng      # most recently used last
+            self._engine = eng
         return self._engine
 
     def forward(self, input):

@@ -376,7 +376,8 @@ def to_t7(module):
             if isinstance(v, (bool, int, float)):
                 f[k] = v
     for k, v in vars(inner).items():
-        if isinstance(v, torch.Tensor) and not k.startswith("_"):
+        # output / gradInput are cleared before saving (multigpu.lua:110-131): activations are never stored
+        if isinstance(v, torch.Tensor) and not k.startswith("_") and k not in ("output", "gradInput"):
             f[k] = v.detach().float().cpu().numpy()
     if inner.typename == "cudnn.SpatialConvolution":
         f["groups"] = 1

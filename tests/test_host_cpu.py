@@ -187,6 +187,66 @@ for order in (list(reversed(mods)), random.Random(rank).sample(mods, len(mods)))
     assert len(launched) == len(m.buckets)
 lo, hi = multigpu.shard_range(7, 2, rank)
 assert (lo, hi) == ((0, 4) if rank == 0 else (4, 7))
+
+# ---- gradient accumulation (-iterSize 2), unequal shards (4 + 3 images) and a plan rebuilt for another batch size ----
+# fake engines: backward ADDS a rank- and call-dependent gradient into gflat (accGradParameters semantics) and the
+# "communicator" all-reduces the pointed-to range over gloo, so the wrapper's bookkeeping is checked end to end
+import ctypes
+calls = []
+class FakeCtx:
+    def __init__(self, eng): self.eng = eng
+    def call(self, name, *a):
+        calls.append((name, id(self.eng)))
+        if name == "mg_allreduce_launch":
+            off = (a[0].value - gflat.data_ptr()) // 4
+            dist.all_reduce(gflat[off:off + a[1]])
+class FakeEng:
+    def __init__(self, key):
+        self.key, self.ctx, self.on_param_done, self.bn_sync = key, FakeCtx(self), None, 0
+        class D: index = 0
+        self.device = D()
+    def set_bn_sync(self, n): self.bn_sync = n
+class FakeComm:
+    h = 1
+    def call(self, *a): calls.append(("comm:" + a[0], 0))
+m._comm = FakeComm()          # stands for the context that owns the NCCL communicator
+engines = {}
+def get_engine(inp):
+    m.model._engine = engines.setdefault(tuple(inp.shape), FakeEng(tuple(inp.shape)))
+    return m.model._engine
+step = [0]
+def model_backward(inp, go, scale=1.0):
+    step[0] += 1
+    gflat.add_(scale * (rank + 1) * step[0])      # local gradient of this micro-batch
+    eng = get_engine(inp)
+    for mod in reversed(mods): eng.on_param_done(mod)
+m.model._get_engine = get_engine
+m.model.backward = model_backward
+m.model.forward = lambda inp: None
+xa = torch.zeros(4 if rank == 0 else 3, 3, 8, 8)
+m.zeroGradParameters()
+for it in range(2):                               # iterSize = 2: gradients zeroed only before the first micro-batch
+    m.forward(xa); m.backward(xa, None)
+w = [4 / 7, 3 / 7]
+want = sum(w[r] * (r + 1) * s for r in range(2) for s in (1, 2))
+assert torch.allclose(gflat, torch.full_like(gflat, want), rtol=1e-6), (float(gflat[0]), want)
+# the user may also zero the flat gradient directly: the wrapper must not rely on zeroGradParameters() having been called
+gflat.zero_(); step[0] = 0
+m.forward(xa); m.backward(xa, None)
+assert torch.allclose(gflat, torch.full_like(gflat, sum(w[r] * (r + 1) for r in range(2))), rtol=1e-6)
+# another batch size (the partial last batch of the test pass): a new engine borrows the SAME communicator
+xb = torch.zeros(2, 3, 8, 8)
+m.zeroGradParameters(); m.forward(xb); m.backward(xb, None)
+shared = [c for c in calls if c[0] == "mg_comm_share"]
+assert len(shared) == 2 and shared[0][1] != shared[1][1], shared
+assert not [c for c in calls if c[0].startswith("comm:")], "the communicator must be initialised once, not per engine"
+# an empty shard is an error on every rank, not a hang
+try:
+    m.forward(torch.zeros(1 if rank == 0 else 0, 3, 8, 8)); raise SystemExit("empty shard accepted")
+except multigpu.ffi.MGError as e:
+    assert "without images" in str(e)
+# wrapper methods that return self keep the wrapper
+assert m.clearState() is m
 dist.barrier()
 print("ok", rank)
 '''

@@ -121,3 +121,38 @@ def test_model_checkpoint_round_trip(tmp_path, net, opt):
     other = B.load_net("cifar/nmg").createModel(B.Opt(nGPU=1, nLayer=2))
     with pytest.raises(t7.T7Error):
         t7.load_into(other, path)
+
+
+@pytest.mark.parametrize("ext", ["pt", "t7"])
+def test_checkpoint_after_a_forward_pass_round_trips(tmp_path, ext):
+    """saveDataParallel after training steps: the top-level module then holds .output / .gradInput tensors, which the
+    reference clears before saving (multigpu.lua:110-131); neither container may store them and both must load into a
+    freshly built model (whose .output is None) -- native format and .t7"""
+    from mgconv import multigpu
+    torch.manual_seed(3)
+    N = B.load_net("cifar/rnmg")
+    opt = B.Opt(nGPU=1, nLayer=1)
+    a = N.createModel(opt)
+    for m in a.listModules():
+        for name in ("weight", "bias", "running_mean", "running_var"):
+            t = getattr(m, name, None)
+            if isinstance(t, torch.Tensor):
+                t.uniform_(0.5, 1.5)
+    a.output, a.gradInput = torch.randn(4, 100), torch.randn(4, 3, 32, 32)      # state left behind by forward / backward
+    path = str(tmp_path / ("model_3." + ext))
+    multigpu.saveDataParallel(path, a)
+    assert a.output is not None                                                  # saving does not disturb the live model
+    b = multigpu.loadAndRemoveDPT(path, N, opt)
+    assert b.output is None
+    n = 0
+    for ma, mb in zip(a.listModules(), b.listModules()):
+        for name in ("weight", "bias", "running_mean", "running_var"):
+            ta, tb = getattr(ma, name, None), getattr(mb, name, None)
+            if isinstance(ta, torch.Tensor):
+                assert torch.equal(ta, tb), (ma.typename, name)
+                n += 1
+    assert n > 20
+    if ext == "pt":   # a file whose shapes do not fit is rejected with a clear error
+        other = B.load_net("cifar/rnmg").createModel(B.Opt(nGPU=1, nLayer=2))
+        with pytest.raises(Exception):
+            multigpu._load_into(other, path)
