@@ -88,7 +88,7 @@ enum { MG_ALGO_AUTO = 0, MG_ALGO_TILE128 = 1, /* one 128-slot tile per CTA, seve
        MG_ALGO_RESIDENT = 3,                  /* persistent CTAs, whole weight image resident in shared memory */
        MG_ALGO_TILE128_DEEP = 4,              /* TILE128 with two CTAs per SM: two halo buffers, deeper weight ring */
        MG_ALGO_TILE256_DEEP = 5,              /* TILE256 with one CTA per SM: two halo buffers, deepest weight ring */
-       MG_ALGO_TILE128_MCAST2 = 6 };          /* TILE128 in clusters of two CTAs: each loads half of a weight stage and multicasts it */
+       MG_ALGO_TILE128_MID = 6 };             /* TILE128 with three CTAs per SM (72 KB each) */
 
 typedef struct {
   mg_grid g;        /* gradient tensor of a consumer */

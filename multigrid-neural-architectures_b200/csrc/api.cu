@@ -1,6 +1,7 @@
 // C-ABI entry points: context management, conv dispatch (tcgen05 vs CUDA-core), data-parallel
 // communicator.  See include/mgconv.h for the contract of every function.
 #include "common.cuh"
+#include "tma.cuh"
 #include <dlfcn.h>
 #include <stdlib.h>
 #include <algorithm>
@@ -127,6 +128,7 @@ int mg_ctx_destroy(mg_ctx* ctx) {
   free(ctx->events);
   if (ctx->pack_dev) cudaFree(ctx->pack_dev);
   free(ctx->pack_host);
+  delete (TmapCache*)ctx->tmaps;
   delete ctx;
   return MG_OK;
 }

@@ -44,6 +44,7 @@ struct mg_ctx {
   int tune_mt;       // 128-slot sub-tiles per CTA of the halo convolution kernel (1 / 2)
   int tune_persist;  // weight-resident persistent kernel: 1 = whenever the weights fit, 2 = never
   // job table of mg_conv_pack_weights_batched (device copy + the host image it was uploaded from)
+  void* tmaps;         // TmapCache* (tma.cuh): CUtensorMap objects of the halo kernels, keyed by (pointer, shape)
   void* pack_dev;
   void* pack_host;
   size_t pack_cap, pack_bytes;

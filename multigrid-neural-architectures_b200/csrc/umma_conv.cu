@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "conv_view.cuh"
 #include "umma_common.cuh"
+#include "tma.cuh"
 #include <algorithm>
 #include <vector>
 
@@ -336,15 +337,19 @@ __global__ void __launch_bounds__(N_THREADS, 4) umma_conv_kernel(const __grid_co
 }
 
 
-// ---------------------------------------------------------------- halo kernel ----------------
+// ---------------------------------------------------------------- halo kernels ----------------
 // 3x3 / stride 1 convolutions.  The CTA's 128 GEMM rows are 128 consecutive SLOTS of the zero-padded
 // linear image space t = (n*(H+1) + y)*(W+1) + x (slot x == W and row y == H are the conv's zero
 // padding, shared between neighbouring rows / images), so that tap (ky,kx) of every row is the slot
-// (ky-1)*(W+1) + (kx-1) further on.  Per 64-channel chunk the producers stage ONE halo of
-// 128 + 2*(W+1) + 2 slots; the nine taps are nine UMMA descriptors into that same buffer, offset by
-// whole 128-byte rows (the 128B swizzle is a function of the absolute shared-memory address, so a
-// descriptor may start at any row -- verified on hardware, scratch/desc_test.cu).  A is fetched from
-// L2 once per chunk instead of once per tap (x4.4 - x7 less gather traffic than umma_conv_kernel).
+// (ky-1)*(W+1) + (kx-1) further on.  K is cut into CHUNKS of up to 64 channels of ONE source grid; per
+// chunk the halo of the tile (128 + 2*(W+1) + 2 slots, widened to whole slot rows) is staged ONCE by
+// the copy engine (TMA, tma.cuh): one cp.async.bulk.tensor per slot row, the zero padding and the
+// nearest-neighbour up-sampling of the coarser grid included -- no thread touches an activation byte.
+// The nine taps are nine UMMA descriptors into that same buffer, offset by whole 128-byte rows (the
+// 128B swizzle is a function of the absolute shared-memory address, so a descriptor may start at any
+// row -- scratch/desc_test.cu, scratch/tma_test.cu).  Weights stream as pre-swizzled stages
+// (cp.async.bulk); a chunk of <= 32 (<= 16) channels packs 2 (4) taps into one 128-byte-row stage.
+
 // butterfly reduce-scatter over the 32 lanes of a warp: every lane contributes v[0..15], afterwards lane l
 // holds the warp-wide sum of element l & 15 (16 shuffles instead of 16 x 5)
 __device__ __forceinline__ float warp_reduce_scatter16(float (&v)[16], int lane) {
@@ -361,72 +366,92 @@ __device__ __forceinline__ float warp_reduce_scatter16(float (&v)[16], int lane)
   return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
 }
 
-constexpr int HALO_MAX_SLOTS = 256 + 2 * 65 + 2;   // W <= 64, up to two 128-slot sub-tiles per CTA
-constexpr int H_PROD = 256;                        // 8 loader warps (the first 4 also drain TMEM): the gather is issue bound
-constexpr int H_MMA_WARP = H_PROD / 32, H_B_WARP = H_MMA_WARP + 1;
-constexpr int H_THREADS = H_PROD + 64;
+constexpr int MAX_CHUNKS = 32;
+struct HChunk { int seg, c0, nch, tps, ksteps, stage0; };   // tps = taps per weight stage (1, 2, 4); stage0 = first weight stage
 
-// CL = thread-block cluster size along the tile index: the CL CTAs of a cluster need the same weight stages, so each
-// loads 1/CL of a stage and multicasts it to all of them (L2 -> SM weight traffic / CL)
+struct HParams {
+  CUtensorMap tmap[MG_MAX_SEG];
+  int seg_up[MG_MAX_SEG];
+  HChunk chunk[MAX_CHUNKS];
+  int n_seg, n_chunks, n_stages, any_up;
+  int H, W, Wp, Hp, Nimg;
+  int64_t T;          // N * Hp * Wp slots
+  int HL;             // halo slots a tile needs = tile slots + 2 * Wp + 2
+  int nr_max;         // slot rows a halo buffer holds
+  int halo_bytes;     // nr_max * Wp * 128 rounded up to 1024
+  int n_abuf;
+  int n_tile;         // UMMA N of this launch (multiple of 16, <= 256)
+  const uint8_t* wpack;
+  const float* bias;
+  int c_bias;
+  __nv_bfloat16* y;
+  int y_pitch, c_valid;
+  int stages, tmem_cols;
+  double* stats;      // forward: per-channel (sum y, sum y^2) of the STORED bf16 output accumulated here ([2][c_stats]), or null
+  int c_stats;
+  int m_tiles;        // persistent kernel: 128-slot tiles in total
+};
+
+// zero the pad column (slot x == W of every row) of `nbuf` halo buffers: the up-sampling box writes only the W valid slots
+__device__ __forceinline__ void zero_pad_column(uint8_t* a_smem, int nbuf, int halo_bytes, int nr_max, int Wp, int tid, int nthreads) {
+  for (int i = tid; i < nbuf * nr_max * 8; i += nthreads) {
+    const int q = i & 7, row = (i >> 3) % nr_max, buf = (i >> 3) / nr_max;
+    *reinterpret_cast<uint4*>(a_smem + (size_t)buf * halo_bytes + (size_t)(row * Wp + Wp - 1) * 128 + q * 16) = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async();
+}
+
+// output pixel of slot t (or false for a padding slot / a slot beyond the batch)
+__device__ __forceinline__ bool slot_pixel(const HParams& p, int64_t t, uint32_t* pix) {
+  if (t >= p.T) return false;
+  const uint32_t tu = (uint32_t)t, spi = (uint32_t)(p.Hp * p.Wp);
+  const uint32_t n = tu / spi, rem = tu - n * spi;
+  const uint32_t yy = rem / (uint32_t)p.Wp, xs = rem - yy * (uint32_t)p.Wp;
+  if ((int)yy >= p.H || (int)xs >= p.W) return false;
+  *pix = (n * p.H + yy) * p.W + xs;
+  return true;
+}
+
 // MT = 128-slot sub-tiles per CTA (1 or 2).  With MT = 2 the CTA owns 256 consecutive slots and two TMEM accumulators:
-// every weight stage feeds both sub-tiles, so the weight stream per output row halves and the halo overhead per row
-// drops -- the kernel is bound by L2 -> SM bandwidth (measured ~42 B/clk/SM chip-wide), of which the weights that every
-// tile re-streams are 70-90 %.  All eight loader warps drain TMEM (warps 0-3 accumulator 0, warps 4-7 accumulator 1).
-template <int CL, int MT>
-__global__ void __launch_bounds__(H_THREADS, MT == 1 ? 4 : 3) umma_conv_halo_kernel(const __grid_constant__ UParams p) {
+// every weight stage feeds both sub-tiles, so the weight stream per output row halves and the halo overhead per row drops
+// (the kernels are bound by L2 -> SM bandwidth, ~42 B/clk/SM chip-wide, of which the re-streamed weights are 70-90 %).
+// Warps: 4*MT epilogue (TMEM lane quarters), one TMA warp for the halos, one thread for the weight stages, one MMA warp.
+template <int MT>
+__global__ void __launch_bounds__(32 * (4 * MT + 3), MT == 1 ? 4 : 2) umma_conv_halo_kernel(const __grid_constant__ HParams p) {
+  constexpr int EPI_WARPS = 4 * MT, A_WARP = EPI_WARPS, B_WARP = EPI_WARPS + 1, M_WARP = EPI_WARPS + 2, NT = 32 * (EPI_WARPS + 3);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], a_full[2], a_empty[2], tmem_full_bar;
   __shared__ uint32_t tmem_base_s;
-  __shared__ uint32_t s_pix[BM * MT + 132];    // full-resolution pixel index of a halo slot, 0xFFFFFFFF = padding / outside
-  __shared__ uint32_t s_pup[BM * MT + 132];    // half-resolution pixel index (UP segments)
-  __shared__ USeg s_seg[MG_MAX_SEG];
   __shared__ float s_bias[256];                // bias of this column tile (zero beyond Cout): no global loads in the epilogue
 
   pdl_launch();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  long long* tl = p.timeline ? p.timeline + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
-  if (tl && tid == 0) { tl[0] = clock64(); unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); tl[7] = sm; }
   const int S = p.stages;
   const int b_stage_bytes = p.n_tile * 128;
-  uint8_t* a_smem = smem;                               // two halo buffers
-  uint8_t* b_smem = smem + (size_t)p.n_abuf * p.halo_bytes;    // B ring
-  const int64_t t0 = (int64_t)blockIdx.x * (BM * MT);
+  uint8_t* a_smem = smem;                                      // halo buffers
+  uint8_t* b_smem = smem + (size_t)p.n_abuf * p.halo_bytes;    // weight ring
+  const int t0 = (int)blockIdx.x * (BM * MT);                  // T < 2^31 (halo_applies)
   const int ntile = blockIdx.y;
-  const int KK = 9;
+  // slot rows [r0, r0 + nr) cover the halo [hs, hs + HL); the tile's first halo slot sits `off` slots into the buffer
+  const int hs = t0 - p.Wp - 1;
+  const int r0 = floordiv(hs, p.Wp);
+  const int nr = (hs + p.HL - 1) / p.Wp - r0 + 1;
+  const int off = hs - r0 * p.Wp;
 
-  if (tid < p.n_seg) s_seg[tid] = p.seg[tid];
-
-  {
-    const int slots_per_img = p.Hp * p.Wp;
-    const int Hs2 = p.H >> 1, Ws2 = p.W >> 1;
-    for (int h = tid; h < p.HL; h += H_THREADS) {
-      const int64_t t = t0 - p.Wp - 1 + h;
-      uint32_t pix = 0xFFFFFFFFu, pup = 0;
-      if (t >= 0 && t < p.T) {
-        // T < 2^31 (halo_applies): 32-bit unsigned divisions (the 64-bit ones cost ~1k cycles of every CTA's prologue)
-        const uint32_t tu = (uint32_t)t;
-        const uint32_t n = tu / (uint32_t)slots_per_img, rem = tu - n * (uint32_t)slots_per_img;
-        const uint32_t yy = rem / (uint32_t)p.Wp, xs = rem - yy * (uint32_t)p.Wp;
-        if ((int)yy < p.H && (int)xs < p.W) {
-          pix = (n * p.H + yy) * p.W + xs;
-          pup = (n * Hs2 + (yy >> 1)) * Ws2 + (xs >> 1);
-        }
-      }
-      s_pix[h] = pix; s_pup[h] = pup;
-    }
-  }
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CL); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], H_PROD); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     mbar_init(&tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == H_MMA_WARP) {
+  if (warp == M_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(p.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (warp == A_WARP && lane < p.n_seg) tma_prefetch_desc(&p.tmap[lane]);
+  if (p.any_up) zero_pad_column(a_smem, p.n_abuf, p.halo_bytes, p.nr_max, p.Wp, tid, NT);
   // everything above touched only kernel parameters, shared memory and TMEM: it overlapped the tail of the
   // previous kernel; from here on the predecessor's output (activations, packed weights, bias) is read
   pdl_wait();
@@ -436,75 +461,24 @@ __global__ void __launch_bounds__(H_THREADS, MT == 1 ? 4 : 3) umma_conv_halo_ker
   }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();   // every CTA's barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  if (tl && tid == 0) tl[1] = clock64();
 
-  if (warp < H_MMA_WARP) {
-    // ================= A producers: one halo per 64-channel chunk ===============================
-    const int v = tid & 7;       // k-vector column of the chunk
-    const int rg = tid >> 3;     // halo slots rg, rg+16, ...
-    const int NB = p.n_abuf, lagA = NB - 1;   // one buffer: publish at once; two: publish the previous chunk
-    Ring ra(NB), rpub(NB);
-    for (int c = 0; c < p.n_chunks + lagA; ++c, ra.next()) {
-      if (c < p.n_chunks) {
-        const int buf = ra.idx;
-        if (c >= NB) mbar_wait(&a_empty[buf], ra.phase ^ 1u);
-        const int r = c * KV_PER_STAGE + v;            // k-vector within a tap
-        const bool kv_ok = r < p.kv_per_tap;
-        int sg = 0;
-        if (kv_ok) while (sg + 1 < p.n_seg && r >= s_seg[sg + 1].kv_begin) ++sg;
-        const USeg sgm = s_seg[sg];
-        const uint32_t pitch = (uint32_t)sgm.Cp * 2u;
-        const char* base = reinterpret_cast<const char*>(sgm.ptr) + (r - sgm.kv_begin) * 16;
-        const uint32_t* tab = sgm.shift ? s_pup : s_pix;
-        const uint32_t dst0 = smem_u32(a_smem + (size_t)buf * p.halo_bytes) + (uint32_t)(v << 4);
-        // table reads are batched ahead of the copies (the asm copies are ordered, the compiler cannot hoist them)
-        for (int h0 = rg; h0 < p.HL; h0 += 4 * (H_PROD / 8)) {
-          uint32_t pv[4], tv[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int h = h0 + u * (H_PROD / 8);
-            pv[u] = h < p.HL ? s_pix[h] : 0xFFFFFFFFu;
-            tv[u] = h < p.HL ? tab[h] : 0u;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int h = h0 + u * (H_PROD / 8);
-            if (h < p.HL) {
-              const bool ok = kv_ok && pv[u] != 0xFFFFFFFFu;
-              const char* src = ok ? base + (uint64_t)tv[u] * pitch : reinterpret_cast<const char*>(sgm.ptr);
-              // 16-byte chunk v of slot h, swizzled by the slot's absolute 128-byte row (buffers are 1024-aligned)
-              cp_async16((dst0 ^ ((uint32_t)(h & 7) << 4)) + (uint32_t)h * 128, src, ok ? 16u : 0u);
-            }
-          }
-        }
-      }
-      cp_async_commit();
-      if (c >= lagA) {   // chunk c-lagA has landed for this thread
-        cp_async_wait_dyn(lagA);
-        fence_proxy_async();
-        mbar_arrive(&a_full[rpub.idx]);
-        rpub.next();
-      }
-    }
-    // ================= epilogue (warps 0-3): TMEM -> registers -> bf16 NHWC rows ===========
+  if (warp < EPI_WARPS) {
+    // ================= epilogue: TMEM -> registers -> bf16 NHWC rows ===========================
     // With p.stats the BatchNorm statistics of this tile (sum, sum of squares of the STORED bf16 values over the
     // valid rows) are reduced here: warp butterfly -> per-warp slots in the (now idle) halo buffer -> one fp64
     // atomic pair per channel and CTA.  The separate statistics pass over y (one HBM read of y) disappears.
-    if (warp < 4 * MT) {
-    mbar_wait(&tmem_full_bar, 0);
-    tc_fence_after();
-    if (tl && tid == 0) tl[3] = clock64();
     const int row = warp * 32 + lane;                      // sub-tile warp >> 2, TMEM lane quarter warp & 3
-    const uint32_t pix = s_pix[row + p.Wp + 1];          // slot t0 + row
-    const bool row_ok = pix != 0xFFFFFFFFu;
+    uint32_t pix = 0;
+    const bool row_ok = slot_pixel(p, (int64_t)t0 + row, &pix);
     const int n_base = ntile * p.n_tile;
     const bool want_stats = p.stats != nullptr;
     float* s_part = reinterpret_cast<float*>(a_smem);     // [4*MT warps][2][256]: every MMA has completed, the halo buffer is free
-    __nv_bfloat16* yrow = p.y + (size_t)(row_ok ? pix : 0) * p.y_pitch;
+    __nv_bfloat16* yrow = p.y + (size_t)pix * p.y_pitch;
     const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * p.n_tile);
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
     for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
       uint32_t acc[16];
       tc_ld16(tacc + (uint32_t)c0, acc);
@@ -552,74 +526,70 @@ __global__ void __launch_bounds__(H_THREADS, MT == 1 ? 4 : 3) umma_conv_halo_ker
         }
       }
     }
-    if (tl && tid == 0) tl[4] = clock64();
+  } else if (warp == A_WARP) {
+    // ================= halo producer: one TMA per slot row and chunk ============================
+    Ring ra(p.n_abuf);
+    for (int c = 0; c < p.n_chunks; ++c, ra.next()) {
+      const int buf = ra.idx;
+      if (c >= p.n_abuf) mbar_wait(&a_empty[buf], ra.phase ^ 1u);
+      const HChunk ch = p.chunk[c];
+      tma_load_rows(&p.tmap[ch.seg], p.seg_up[ch.seg], smem_u32(a_smem + (size_t)buf * p.halo_bytes), &a_full[buf], ch.c0, r0, nr, p.W, p.Hp, lane);
     }
-  } else if (warp == H_B_WARP) {
-    // ================= B loader: one bulk copy per (chunk, tap) stage ============================
+  } else if (warp == B_WARP) {
+    // ================= weight loader: one bulk copy per stage ====================================
     if (lane == 0) {
-      const int n_st = p.n_chunks * KK;
-      const uint8_t* wsrc = p.wpack + (size_t)ntile * n_st * b_stage_bytes;
-      const uint32_t rank = CL > 1 ? cluster_ctarank() : 0;
-      const uint32_t slice = (uint32_t)b_stage_bytes / CL;   // n_tile * 128 / CL: a multiple of 16 bytes
+      const uint8_t* wsrc = p.wpack + (size_t)ntile * p.n_stages * b_stage_bytes;
       Ring rb(S);
-      for (int ks = 0; ks < n_st; ++ks, rb.next()) {
+      for (int ks = 0; ks < p.n_stages; ++ks, rb.next()) {
         const int s = rb.idx;
-        if (ks >= S) mbar_wait(&empty_bar[s], rb.phase ^ 1u);   // CL arrivals: every CTA of the cluster freed slot s
+        if (ks >= S) mbar_wait(&empty_bar[s], rb.phase ^ 1u);
         mbar_arrive_expect_tx(&full_bar[s], (uint32_t)b_stage_bytes);
-        if (CL == 1)
-          bulk_g2s(smem_u32(b_smem + (size_t)s * b_stage_bytes), wsrc + (size_t)ks * b_stage_bytes, (uint32_t)b_stage_bytes, &full_bar[s]);
-        else
-          bulk_g2s_mcast(smem_u32(b_smem + (size_t)s * b_stage_bytes) + rank * slice, wsrc + (size_t)ks * b_stage_bytes + rank * slice, slice,
-                         &full_bar[s], (uint16_t)((1u << CL) - 1));
+        bulk_g2s(smem_u32(b_smem + (size_t)s * b_stage_bytes), wsrc + (size_t)ks * b_stage_bytes, (uint32_t)b_stage_bytes, &full_bar[s]);
       }
     }
   } else {
     // ================= MMA issuer: 9 shifted descriptors per chunk ===============================
     // the whole warp runs the loop (warp-uniform operands), the elected lane issues the MMAs and the commits
-    {
-      const bool leader = elect_one();
-      const uint32_t idesc = idesc_bf16_m128(p.n_tile);
-      int ks = 0;
-      long long wait_a = 0, wait_b = 0, tq = 0;
-      Ring ra(p.n_abuf), rb(S);
-      for (int c = 0; c < p.n_chunks; ++c, ra.next()) {
-        const int buf = ra.idx;
-        if (tl) tq = clock64();
-        mbar_wait(&a_full[buf], ra.phase);
-        tc_fence_after();
-        if (tl && c == 0 && lane == 0) tl[2] = clock64();
-        if (tl && c > 0) wait_a += clock64() - tq;
-        const uint32_t a_base = smem_u32(a_smem + (size_t)buf * p.halo_bytes);
-        const int kv_here = min(KV_PER_STAGE, p.kv_per_tap - c * KV_PER_STAGE);
-        const int ksteps = (kv_here + 1) >> 1;
-        for (int tap = 0; tap < KK; ++tap, ++ks, rb.next()) {
-          const int s = rb.idx;
-          if (tl) tq = clock64();
-          mbar_wait(&full_bar[s], rb.phase);
+    const bool leader = elect_one();
+    const uint32_t idesc = idesc_bf16_m128(p.n_tile);
+    Ring ra(p.n_abuf), rb(S);
+    for (int c = 0; c < p.n_chunks; ++c, ra.next()) {
+      const int buf = ra.idx;
+      const HChunk ch = p.chunk[c];
+      mbar_wait(&a_full[buf], ra.phase);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(a_smem + (size_t)buf * p.halo_bytes) + (uint32_t)off * 128u;
+      const int tps = ch.tps, ksteps = ch.ksteps;
+      const uint32_t sub_lo = 8u / (uint32_t)tps;          // descriptor units (16 bytes) between the taps packed in one stage
+      int sub = 0;
+      uint32_t b_lo = 0;
+      for (int tap = 0; tap < 9; ++tap) {
+        if (sub == 0) {
+          mbar_wait(&full_bar[rb.idx], rb.phase);
           tc_fence_after();
-          if (tl) wait_b += clock64() - tq;
-          const uint32_t a_lo = desc_lo_k_sw128(a_base + (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 128u);
-          const uint32_t b_lo = desc_lo_k_sw128(smem_u32(b_smem + (size_t)s * b_stage_bytes));
-          if (leader) {
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)   // both sub-tiles consume the same weight stage
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (q < ksteps)
-                  tc_mma_bf16_lohi(tmem_base + (uint32_t)(mt * p.n_tile), a_lo + (uint32_t)(mt * BM * 8 + q * 2), b_lo + (uint32_t)(q * 2), DESC_HI_SW128,
-                                   idesc, (ks | q) != 0);
-            if (CL == 1) tc_commit(&empty_bar[s]); else tc_commit_mcast(&empty_bar[s], (uint16_t)((1u << CL) - 1));
-          }
+          b_lo = desc_lo_k_sw128(smem_u32(b_smem + (size_t)rb.idx * b_stage_bytes));
         }
-        if (leader) tc_commit(&a_empty[buf]);   // halo buffer free once this chunk's MMAs have read it
+        const uint32_t a_lo = desc_lo_k_sw128(a_base + (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 128u);
+        const bool last_of_stage = (sub == tps - 1) || tap == 8;
+        if (leader) {
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)   // both sub-tiles consume the same weight stage
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (q < ksteps) {
+                tc_mma_bf16_lohi(tmem_base + (uint32_t)(mt * p.n_tile), a_lo + (uint32_t)(mt * BM * 8 + q * 2), b_lo + (uint32_t)sub * sub_lo + (uint32_t)(q * 2),
+                                 DESC_HI_SW128, idesc, (uint32_t)((c | tap | q) != 0));
+              }
+          if (last_of_stage) tc_commit(&empty_bar[rb.idx]);   // frees the weight stage once these MMAs have read it
+        }
+        if (last_of_stage) { sub = 0; rb.next(); } else ++sub;
       }
-      if (leader) tc_commit(&tmem_full_bar);
-      if (tl && lane == 0) { tl[5] = wait_a; tl[6] = wait_b; }
+      if (leader) tc_commit(&a_empty[buf]);   // halo buffer free once this chunk's MMAs have read it
     }
+    if (leader) tc_commit(&tmem_full_bar);
   }
   __syncthreads();
-  if (CL > 1) cluster_sync_all();   // no CTA leaves while a peer may still multicast into it or arrive on its barriers
-  if (warp == H_MMA_WARP) {
+  if (warp == M_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
@@ -627,44 +597,38 @@ __global__ void __launch_bounds__(H_THREADS, MT == 1 ? 4 : 3) umma_conv_halo_ker
 
 
 // ---------------------------------------------------------------- persistent halo kernel ----------
-// Same operand scheme as umma_conv_halo_kernel for convolutions whose WHOLE packed weight image fits in shared
-// memory next to a ring of halo buffers (R-MG-34 block 1: 96 -> 64 at 56x56 is 147 KB, its dgrad 110 KB).  The
-// non-persistent kernel re-streams the weights for every 128-slot tile -- 2.4x the activation traffic at N = 64 --
-// through a two-deep ring, which makes its main loop a chain of L2 round trips.  Here one CTA per SM loads the
-// weights ONCE, then walks slot tiles blockIdx.x, +gridDim.x, ... with decoupled roles:
-//   8 loader warps   stage halos into a ring that runs ACROSS chunks and tiles (the next tile's halo is in
-//                    flight while the tensor core works on the current one),
-//   1 MMA thread     accumulates tile i into TMEM accumulator i & 1 (every operand already in shared memory),
+// Same operand scheme for convolutions whose WHOLE packed weight image fits in shared memory next to a ring of halo
+// buffers (R-MG-34 block 1: 96 -> 64 at 56x56 is 112 KB, its dgrad 110 KB).  The non-persistent kernel re-streams the
+// weights for every 128-slot tile -- 2.4x the activation traffic at N = 64.  Here one CTA per SM loads the weights ONCE,
+// then walks slot tiles blockIdx.x, +gridDim.x, ... with decoupled roles:
+//   1 TMA warp       stages halos into a ring that runs ACROSS chunks and tiles (the next tile's halo is in flight while
+//                    the tensor core works on the current one),
+//   1 MMA warp       accumulates tile i into TMEM accumulator i & 1 (every operand already in shared memory),
 //   4 epilogue warps drain accumulator (i-1) & 1 meanwhile (TMEM double buffering) and keep the BatchNorm
 //                    statistics of all the CTA's tiles in shared memory: one fp64 atomic pair per channel and CTA.
-constexpr int P_LOAD = 256, P_EPI_WARP0 = 8, P_MMA_WARP = 12, P_B_WARP = 13, P_THREADS = 448;
+constexpr int P_A_WARP = 4, P_B_WARP = 5, P_MMA_WARP = 6, P_THREADS = 224;
 constexpr int P_MAX_ABUF = 6;
 
-__global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel(const __grid_constant__ UParams p) {
+__global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel(const __grid_constant__ HParams p) {
   pdl_launch();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t b_full, a_full[P_MAX_ABUF], a_empty[P_MAX_ABUF], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ uint32_t s_pix[2][BM + 132], s_pup[2][BM + 132];
-  __shared__ USeg s_seg[MG_MAX_SEG];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NA = p.n_abuf;
   const int b_stage_bytes = p.n_tile * 128;
-  const int KK = 9;
-  const int n_st = p.n_chunks * KK;
   uint8_t* a_smem = smem;
-  uint8_t* b_smem = smem + (size_t)NA * p.halo_bytes;                        // all n_st weight stages, resident
-  float* s_bias = reinterpret_cast<float*>(b_smem + (size_t)n_st * b_stage_bytes);   // [n_tile]
-  float* s_part = s_bias + p.n_tile;                                         // [4 epilogue warps][2][n_tile]
+  uint8_t* b_smem = smem + (size_t)NA * p.halo_bytes;                                  // all weight stages, resident
+  float* s_bias = reinterpret_cast<float*>(b_smem + (size_t)p.n_stages * b_stage_bytes);   // [n_tile]
+  float* s_part = s_bias + p.n_tile;                                                   // [4 epilogue warps][2][n_tile]
   const int n_my = (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles blockIdx.x, +gridDim.x, ...
 
-  if (tid < p.n_seg) s_seg[tid] = p.seg[tid];
   for (int c = tid; c < 8 * p.n_tile; c += P_THREADS) s_part[c] = 0.f;
   if (tid == 0) {
     mbar_init(&b_full, 1);
-    for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], P_LOAD / 2); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -673,104 +637,28 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (warp == P_A_WARP && lane < p.n_seg) tma_prefetch_desc(&p.tmap[lane]);
+  if (p.any_up) zero_pad_column(a_smem, NA, p.halo_bytes, p.nr_max, p.Wp, tid, P_THREADS);
   pdl_wait();
   for (int c = tid; c < p.n_tile; c += P_THREADS) s_bias[c] = (p.bias && c < p.c_bias) ? p.bias[c] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const int slots_per_img = p.Hp * p.Wp;
 
-  if (warp < P_EPI_WARP0) {
-    // ================= loaders: two independent groups of four warps ===============================
-    // Group g stages chunks g, g+2, ... of the CTA's chunk sequence (which runs across tiles): wait for the ring
-    // slot, issue, wait for the data, publish.  While one group sits out the L2 latency of its chunk the other
-    // one is issuing, and neither ever waits on a buffer the other group's chunk has to release first.
-    const int grp = warp >> 2, gt = tid & 127;
-    const int v = gt & 7, rg = gt >> 3;            // k-vector column, slot lane 0..15
-    const int Hs2 = p.H >> 1, Ws2 = p.W >> 1;
-    const int total_chunks = n_my * p.n_chunks;
-    int cur_it = -1;
-    Ring ra(NA);                       // this group's chunks are ac = grp, grp + 2, ...: the ring advances two slots per iteration
-    if (grp) ra.next();
-    int it = grp / p.n_chunks, c = grp - it * p.n_chunks;      // (tile, chunk) of ac, carried along
-    for (int ac = grp; ac < total_chunks; ac += 2, ra.next(), ra.next(), c += 2) {
-      while (c >= p.n_chunks) { c -= p.n_chunks; ++it; }
-      if (it != cur_it) {   // this group's slot tables of tile `it`
-        cur_it = it;
-        const int64_t t0 = (int64_t)(blockIdx.x + it * gridDim.x) * BM;
-        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");   // old table no longer read
-        for (int h = gt; h < p.HL; h += 128) {
-          const int64_t t = t0 - p.Wp - 1 + h;
-          uint32_t pix = 0xFFFFFFFFu, pup = 0;
-          if (t >= 0 && t < p.T) {
-            const uint32_t tu = (uint32_t)t;
-            const uint32_t n = tu / (uint32_t)slots_per_img, rem = tu - n * (uint32_t)slots_per_img;
-            const uint32_t yy = rem / (uint32_t)p.Wp, xs = rem - yy * (uint32_t)p.Wp;
-            if ((int)yy < p.H && (int)xs < p.W) {
-              pix = (n * p.H + yy) * p.W + xs;
-              pup = (n * Hs2 + (yy >> 1)) * Ws2 + (xs >> 1);
-            }
-          }
-          s_pix[grp][h] = pix; s_pup[grp][h] = pup;
-        }
-        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
-      }
-      const int buf = ra.idx;
-      if (ac >= NA) mbar_wait(&a_empty[buf], ra.phase ^ 1u);
-      const int r = c * KV_PER_STAGE + v;
-      const bool kv_ok = r < p.kv_per_tap;
-      int sg = 0;
-      if (kv_ok) while (sg + 1 < p.n_seg && r >= s_seg[sg + 1].kv_begin) ++sg;
-      const USeg sgm = s_seg[sg];
-      const uint32_t pitch = (uint32_t)sgm.Cp * 2u;
-      const char* base = reinterpret_cast<const char*>(sgm.ptr) + (r - sgm.kv_begin) * 16;
-      const uint32_t* tab = sgm.shift ? s_pup[grp] : s_pix[grp];
-      const uint32_t dst0 = smem_u32(a_smem + (size_t)buf * p.halo_bytes) + (uint32_t)(v << 4);
-      for (int h0 = rg; h0 < p.HL; h0 += 4 * 16) {
-        uint32_t pv[4], tv[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int h = h0 + u * 16;
-          pv[u] = h < p.HL ? s_pix[grp][h] : 0xFFFFFFFFu;
-          tv[u] = h < p.HL ? tab[h] : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int h = h0 + u * 16;
-          if (h < p.HL) {
-            const bool ok = kv_ok && pv[u] != 0xFFFFFFFFu;
-            const char* src = ok ? base + (uint64_t)tv[u] * pitch : reinterpret_cast<const char*>(sgm.ptr);
-            cp_async16((dst0 ^ ((uint32_t)(h & 7) << 4)) + (uint32_t)h * 128, src, ok ? 16u : 0u);
-          }
-        }
-      }
-      cp_async_commit();
-      cp_async_wait_dyn(0);
-      fence_proxy_async();
-      mbar_arrive(&a_full[buf]);
-    }
-  } else if (warp < P_MMA_WARP) {
+  if (warp < 4) {
     // ================= epilogue warps: drain accumulator it & 1 ====================================
-    const int ew = warp - P_EPI_WARP0, et = tid - P_EPI_WARP0 * 32;   // TMEM lane quarter, thread 0..127
     const bool want_stats = p.stats != nullptr;
     for (int it = 0; it < n_my; ++it) {
       const int mt = blockIdx.x + it * gridDim.x;
       const int acc = it & 1;
-      // this thread's output pixel: slot t0 + row
-      const int row = ew * 32 + lane;
-      const int64_t t = (int64_t)mt * BM + row;
-      bool row_ok = false; uint32_t pix = 0;
-      if (t < p.T) {
-        const uint32_t tu = (uint32_t)t;
-        const uint32_t n = tu / (uint32_t)slots_per_img, rem = tu - n * (uint32_t)slots_per_img;
-        const uint32_t yy = rem / (uint32_t)p.Wp, xs = rem - yy * (uint32_t)p.Wp;
-        if ((int)yy < p.H && (int)xs < p.W) { row_ok = true; pix = (n * p.H + yy) * p.W + xs; }
-      }
+      const int row = warp * 32 + lane;
+      uint32_t pix = 0;
+      const bool row_ok = slot_pixel(p, (int64_t)mt * BM + row, &pix);
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();
       __nv_bfloat16* yrow = p.y + (size_t)pix * p.y_pitch;
-      const uint32_t tcol = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * p.n_tile);
+      const uint32_t tcol = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * p.n_tile);
       for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
         uint32_t a16[16];
         tc_ld16(tcol + (uint32_t)c0, a16);
@@ -801,7 +689,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
             }
             const float tot = warp_reduce_scatter16(sv, lane);
             // slot owned by this lane of this warp for the whole kernel: accumulate over the CTA's tiles without synchronisation
-            if (lane < 16) s_part[(ew * 2 + (lane >> 3)) * p.n_tile + c0 + h * 8 + (lane & 7)] += tot;
+            if (lane < 16) s_part[(warp * 2 + (lane >> 3)) * p.n_tile + c0 + h * 8 + (lane & 7)] += tot;
           }
         }
       }
@@ -810,7 +698,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
     }
     if (want_stats) {
       asm volatile("bar.sync 3, 128;" ::: "memory");
-      for (int c = et; c < p.n_tile; c += 128)
+      for (int c = tid; c < p.n_tile; c += 128)
         if (c < p.c_stats) {
           float a = 0.f, b = 0.f;
 #pragma unroll
@@ -819,46 +707,65 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
           atomicAdd(p.stats + p.c_stats + c, (double)b);
         }
     }
+  } else if (warp == P_A_WARP) {
+    // ================= halo producer: the ring runs across chunks and tiles =======================
+    Ring ra(NA);
+    int ac = 0;
+    for (int it = 0; it < n_my; ++it) {
+      const int t0 = (int)(blockIdx.x + it * gridDim.x) * BM;
+      const int hs = t0 - p.Wp - 1;
+      const int r0 = floordiv(hs, p.Wp);
+      const int nr = (hs + p.HL - 1) / p.Wp - r0 + 1;
+      for (int c = 0; c < p.n_chunks; ++c, ++ac, ra.next()) {
+        const int buf = ra.idx;
+        if (ac >= NA) mbar_wait(&a_empty[buf], ra.phase ^ 1u);
+        const HChunk ch = p.chunk[c];
+        tma_load_rows(&p.tmap[ch.seg], p.seg_up[ch.seg], smem_u32(a_smem + (size_t)buf * p.halo_bytes), &a_full[buf], ch.c0, r0, nr, p.W, p.Hp, lane);
+      }
+    }
   } else if (warp == P_B_WARP) {
     // ================= weight loader: every stage once =============================================
     if (lane == 0) {
-      mbar_arrive_expect_tx(&b_full, (uint32_t)(n_st * b_stage_bytes));
-      for (int q = 0; q < n_st; ++q)
+      mbar_arrive_expect_tx(&b_full, (uint32_t)(p.n_stages * b_stage_bytes));
+      for (int q = 0; q < p.n_stages; ++q)
         bulk_g2s(smem_u32(b_smem + (size_t)q * b_stage_bytes), p.wpack + (size_t)q * b_stage_bytes, (uint32_t)b_stage_bytes, &b_full);
     }
   } else {
     // ================= MMA issuer (whole warp, elected lane issues; see elect_one) =================
-    {
-      const bool leader = elect_one();
-      const uint32_t idesc = idesc_bf16_m128(p.n_tile);
-      const uint32_t b_base = smem_u32(b_smem);
-      int ac = 0;
-      Ring ra(NA);
-      mbar_wait(&b_full, 0);
-      for (int it = 0; it < n_my; ++it) {
-        const int acc = it & 1;
-        if (it >= 2) { mbar_wait(&tmem_empty[acc], ((it >> 1) - 1) & 1); tc_fence_after(); }
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
-        for (int c = 0; c < p.n_chunks; ++c, ++ac, ra.next()) {
-          const int buf = ra.idx;
-          mbar_wait(&a_full[buf], ra.phase);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(a_smem + (size_t)buf * p.halo_bytes);
-          const int kv_here = min(KV_PER_STAGE, p.kv_per_tap - c * KV_PER_STAGE);
-          const int ksteps = (kv_here + 1) >> 1;
-          if (leader) {
-            for (int tap = 0; tap < KK; ++tap) {
-              const uint32_t a_lo = desc_lo_k_sw128(a_base + (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 128u);
-              const uint32_t b_lo = desc_lo_k_sw128(b_base + (uint32_t)((c * KK + tap) * b_stage_bytes));
+    const bool leader = elect_one();
+    const uint32_t idesc = idesc_bf16_m128(p.n_tile);
+    const uint32_t b_base = smem_u32(b_smem);
+    Ring ra(NA);
+    mbar_wait(&b_full, 0);
+    for (int it = 0; it < n_my; ++it) {
+      const int acc = it & 1;
+      if (it >= 2) { mbar_wait(&tmem_empty[acc], ((it >> 1) - 1) & 1); tc_fence_after(); }
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
+      const int t0 = (int)(blockIdx.x + it * gridDim.x) * BM;
+      const int hs = t0 - p.Wp - 1;
+      const int off = hs - floordiv(hs, p.Wp) * p.Wp;
+      for (int c = 0; c < p.n_chunks; ++c, ra.next()) {
+        const int buf = ra.idx;
+        const HChunk ch = p.chunk[c];
+        mbar_wait(&a_full[buf], ra.phase);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(a_smem + (size_t)buf * p.halo_bytes) + (uint32_t)off * 128u;
+        const int tps = ch.tps, ksteps = ch.ksteps;
+        const uint32_t sub_lo = 8u / (uint32_t)tps;
+        if (leader) {
+          int sub = 0, st = ch.stage0;
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t a_lo = desc_lo_k_sw128(a_base + (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 128u);
+            const uint32_t b_lo = desc_lo_k_sw128(b_base + (uint32_t)(st * b_stage_bytes)) + (uint32_t)sub * sub_lo;
 #pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (q < ksteps) tc_mma_bf16_lohi(d_tmem, a_lo + (uint32_t)(q * 2), b_lo + (uint32_t)(q * 2), DESC_HI_SW128, idesc, (c | tap | q) != 0);
-            }
-            tc_commit(&a_empty[buf]);
+            for (int q = 0; q < 4; ++q)
+              if (q < ksteps) tc_mma_bf16_lohi(d_tmem, a_lo + (uint32_t)(q * 2), b_lo + (uint32_t)(q * 2), DESC_HI_SW128, idesc, (uint32_t)((c | tap | q) != 0));
+            if (++sub == tps) { sub = 0; ++st; }
           }
+          tc_commit(&a_empty[buf]);
         }
-        if (leader) tc_commit(&tmem_full[acc]);
       }
+      if (leader) tc_commit(&tmem_full[acc]);
     }
   }
   __syncthreads();
@@ -878,7 +785,9 @@ struct PackParams {
   int seg_C[MG_MAX_SEG], seg_cbegin[MG_MAX_SEG], seg_kvbegin[MG_MAX_SEG], seg_cpbegin[MG_MAX_SEG];
   int kv_per_tap, nkv, n_stages, n_tile, n_tiles;
   int n_rows_valid;  // forward: Cout; transposed: CcatP (rows that may be non-zero)
-  int halo;          // stage order of umma_conv_halo_kernel: stage = chunk * 9 + tap, k-vector = chunk * 8 + v
+  int halo;          // stage order of the halo kernels: per chunk ceil(9 / tps) stages of tps taps each
+  int n_chunks;
+  HChunk chunk[MAX_CHUNKS];
 };
 
 // one thread per (n row, k-vector): writes 16 bytes of the swizzled stage image
@@ -894,30 +803,39 @@ __device__ __forceinline__ void pack_one(const PackParams& p, int64_t i) {
 #pragma unroll
   for (int e = 0; e < 8; ++e) vals[e] = __float2bfloat16_rn(0.f);
   const int KK = p.k * p.k;
-  int tap, r;
+  int tap, r, sg = 0, c0 = 0;   // tap, k-vector within the tap (generic order), K segment and first channel within it
   bool kv_ok;
-  if (p.halo) { tap = stage % KK; r = (stage / KK) * KV_PER_STAGE + v; kv_ok = r < p.kv_per_tap; }
-  else { tap = j / p.kv_per_tap; r = j % p.kv_per_tap; kv_ok = j < p.nkv; }
+  if (p.halo) {
+    int c = 0;
+    while (c + 1 < p.n_chunks && stage >= p.chunk[c + 1].stage0) ++c;
+    const HChunk ch = p.chunk[c];
+    const int per = KV_PER_STAGE / ch.tps;        // k-vectors per tap within a stage
+    tap = (stage - ch.stage0) * ch.tps + v / per;
+    const int cv = v % per;
+    kv_ok = tap < KK && cv * 8 < ch.nch;
+    sg = ch.seg; c0 = ch.c0 + cv * 8;
+    r = 0;
+  } else {
+    tap = j / p.kv_per_tap; r = j % p.kv_per_tap; kv_ok = j < p.nkv;
+    if (!p.transposed) { while (sg + 1 < p.n_seg && r >= p.seg_kvbegin[sg + 1]) ++sg; c0 = (r - p.seg_kvbegin[sg]) * 8; }
+    else c0 = r * 8;
+  }
   if (kv_ok && nrow < p.n_rows_valid) {
     if (!p.transposed) {
-      int sg = 0;
-      while (sg + 1 < p.n_seg && r >= p.seg_kvbegin[sg + 1]) ++sg;
-      const int c0 = (r - p.seg_kvbegin[sg]) * 8;
 #pragma unroll
       for (int e = 0; e < 8; ++e)
         if (c0 + e < p.seg_C[sg]) vals[e] = __float2bfloat16_rn(p.w[((size_t)nrow * p.Ccat + p.seg_cbegin[sg] + c0 + e) * KK + tap]);
     } else {
       // row = padded concat channel, K = (mirrored tap, output channel co)
-      int sg = 0;
-      while (sg + 1 < p.n_seg && nrow >= p.seg_cpbegin[sg + 1]) ++sg;
-      const int cl = nrow - p.seg_cpbegin[sg];
-      if (cl < p.seg_C[sg]) {
-        const int ci = p.seg_cbegin[sg] + cl;
+      int rs = 0;
+      while (rs + 1 < p.n_seg && nrow >= p.seg_cpbegin[rs + 1]) ++rs;
+      const int cl = nrow - p.seg_cpbegin[rs];
+      if (cl < p.seg_C[rs]) {
+        const int ci = p.seg_cbegin[rs] + cl;
         const int ky = p.k - 1 - tap / p.k, kx = p.k - 1 - tap % p.k;
-        const int co0 = r * 8;
 #pragma unroll
         for (int e = 0; e < 8; ++e)
-          if (co0 + e < p.Cout) vals[e] = __float2bfloat16_rn(p.w[((size_t)(co0 + e) * p.Ccat + ci) * KK + ky * p.k + kx]);
+          if (c0 + e < p.Cout) vals[e] = __float2bfloat16_rn(p.w[((size_t)(c0 + e) * p.Ccat + ci) * KK + ky * p.k + kx]);
       }
     }
   }
@@ -953,11 +871,35 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackPar
 struct Geometry {
   int kv_per_tap, nkv, n_stages, n_tile, n_tiles, n_rows;
   int halo, n_chunks;
+  HChunk chunk[MAX_CHUNKS];
 };
 
-// the halo kernel serves 3x3 / stride 1 / pad 1 convolutions on grids of at least `MGCONV_HALO_MIN_W`
+// K of a halo convolution as chunks of <= 64 channels of ONE source grid (a TMA box never spans two grids); a chunk of
+// <= 32 (<= 16) channels packs 2 (4) taps per 128-byte-row weight stage.  Returns the chunk count (> MAX_CHUNKS: no halo path)
+static int build_chunks(const int* kcp, int nk, HChunk* out, int* n_stages) {
+  int n = 0, st = 0;
+  for (int s = 0; s < nk; ++s)
+    for (int c0 = 0; c0 < kcp[s]; c0 += 64) {
+      if (n == MAX_CHUNKS) return MAX_CHUNKS + 1;
+      HChunk& ch = out[n++];
+      ch.seg = s; ch.c0 = c0; ch.nch = std::min(64, kcp[s] - c0);
+      ch.tps = ch.nch > 32 ? 1 : (ch.nch > 16 ? 2 : 4);
+      ch.ksteps = (ch.nch + 15) / 16;
+      ch.stage0 = st;
+      st += (9 + ch.tps - 1) / ch.tps;
+    }
+  *n_stages = st;
+  return n;
+}
+
+static void n_tiling(int n_rows_pad16, int* n_tile, int* n_tiles) {
+  *n_tiles = (n_rows_pad16 + 255) / 256;
+  *n_tile = mg_round_up((n_rows_pad16 + *n_tiles - 1) / *n_tiles, 16);
+}
+
+// the halo kernels serve 3x3 / stride 1 / pad 1 convolutions on grids of at least `MGCONV_HALO_MIN_W`
 // (default 7) and at most 64 columns whose UP segments are exactly half size
-static bool halo_applies(const mg_conv_desc* d) {
+static bool halo_shape_ok(const mg_conv_desc* d) {
   static int min_w = -1;
   if (min_w < 0) { const char* e = getenv("MGCONV_HALO_MIN_W"); min_w = e ? atoi(e) : 7; }
   if (d->ksize != 3 || d->stride != 1 || d->pad != 1) return false;
@@ -970,14 +912,10 @@ static bool halo_applies(const mg_conv_desc* d) {
   return (int64_t)d->seg[0].N * (d->H + 1) * (d->W + 1) < ((int64_t)1 << 31);
 }
 
-static void n_tiling(int n_rows_pad16, int* n_tile, int* n_tiles) {
-  *n_tiles = (n_rows_pad16 + 255) / 256;
-  *n_tile = mg_round_up((n_rows_pad16 + *n_tiles - 1) / *n_tiles, 16);
-}
-
 // geometry of the forward (transposed = 0) or dgrad (transposed = 1) GEMM of a conv descriptor
 static Geometry geometry(const mg_conv_desc* d, int transposed) {
   Geometry g;
+  memset(&g, 0, sizeof(g));
   int CcatP = 0;
   for (int s = 0; s < d->n_seg; ++s) CcatP += d->seg[s].Cp;
   const int CoutP = mg_round_up(d->Cout, 8);
@@ -986,9 +924,14 @@ static Geometry geometry(const mg_conv_desc* d, int transposed) {
   else { g.kv_per_tap = CoutP / 8; g.n_rows = CcatP; n_tiling(mg_round_up(CcatP, 16), &g.n_tile, &g.n_tiles); }
   g.nkv = taps * g.kv_per_tap;
   g.n_stages = (g.nkv + KV_PER_STAGE - 1) / KV_PER_STAGE;
-  g.halo = halo_applies(d) ? 1 : 0;
-  g.n_chunks = (g.kv_per_tap + KV_PER_STAGE - 1) / KV_PER_STAGE;
-  if (g.halo) g.n_stages = g.n_chunks * taps;   // one weight stage per (chunk, tap)
+  g.halo = 0;
+  if (halo_shape_ok(d)) {
+    int kcp[MG_MAX_SEG], nk, n_st = 0;
+    if (!transposed) { nk = d->n_seg; for (int s = 0; s < nk; ++s) kcp[s] = d->seg[s].Cp; }
+    else { nk = 1; kcp[0] = CoutP; }
+    const int nc = build_chunks(kcp, nk, g.chunk, &n_st);
+    if (nc <= MAX_CHUNKS) { g.halo = 1; g.n_chunks = nc; g.n_stages = n_st; }
+  }
   return g;
 }
 
@@ -1032,99 +975,66 @@ static int launch(mg_ctx* ctx, UParams& p, int n_tiles) {
   return MG_OK;
 }
 
-static int launch_halo(mg_ctx* ctx, UParams& p, const Geometry& g, int algo) {
-  p.Wp = p.W + 1; p.Hp = p.H + 1;
-  p.T = (int64_t)p.Nimg * p.Hp * p.Wp;
-  p.n_chunks = g.n_chunks;
+constexpr int SMEM_MAX = 232448 - 4096;   // 227 KB per CTA minus the halo kernels' static shared memory (barriers, bias tile)
+
+// halo geometry of a tile of `slots` GEMM rows on a grid of width W
+static void halo_geometry(HParams& p, int slots) {
+  p.HL = slots + 2 * p.Wp + 2;
+  p.nr_max = (p.HL - 1 + p.Wp - 1) / p.Wp + 1;
+  p.halo_bytes = mg_round_up(p.nr_max * p.Wp * 128, 1024);
+}
+
+static int launch_halo(mg_ctx* ctx, HParams& p, const Geometry& g, int algo) {
   const int b_stage = p.n_tile * 128;
-  static int budget_env = -1, mt_env = -1, cl_env = -1, want_tl = -1;
+  static int budget_env = -1, mt_env = -1;
   if (budget_env < 0) { const char* e = getenv("MGCONV_HALO_SMEM_KB"); budget_env = e ? atoi(e) : 0; }
   if (mt_env < 0) { const char* e = getenv("MGCONV_MT"); mt_env = e ? atoi(e) : 0; }
-  // measured: multicast clusters couple the CTAs and lose 5-10 % (weights are not the bottleneck): off by default
-  if (cl_env < 0) { const char* e = getenv("MGCONV_CLUSTER"); cl_env = e ? atoi(e) : 1; }
-  if (want_tl < 0) { const char* e = getenv("MGCONV_TIMELINE"); want_tl = e ? atoi(e) : 0; }
-  int CL = algo == MG_ALGO_TILE128_MCAST2 ? 2 : ((algo == MG_ALGO_AUTO || algo == MG_ALGO_RESIDENT) ? cl_env : 1);
-  if ((p.n_tile * 128 / 16) % CL != 0 || CL < 1) CL = 1;          // each slice must be whole 16-byte units
-  if (CL != 1 && CL != 2 && CL != 4) CL = 1;
   // two sub-tiles per CTA (half the weight stream per row) whenever that still leaves about a CTA per SM
-  int MT = 1;
-  if (CL == 1 && !want_tl) {
+  int MT;
+  {
     const int64_t ctas2 = mg_cdiv(p.T, 2 * BM) * g.n_tiles;
-    const int want = (algo == MG_ALGO_TILE128 || algo == MG_ALGO_TILE128_DEEP) ? 1
+    const int want = (algo == MG_ALGO_TILE128 || algo == MG_ALGO_TILE128_DEEP || algo == MG_ALGO_TILE128_MID) ? 1
                      : ((algo == MG_ALGO_TILE256 || algo == MG_ALGO_TILE256_DEEP) ? 2 : (ctx->tune_mt ? ctx->tune_mt : mt_env));
-    // heuristic (scratch/conv_bench.py on R-MG-34): sharing the weight stages pays off for narrow column tiles with a long K
-    // loop (224 -> 64 at 14x14: 59 -> 44 us); wide tiles lose more to the shallower weight ring and the lower CTA count
-    const bool heur2 = p.n_tile <= 64 && g.n_chunks >= 3 && ctas2 * 10 >= (int64_t)ctx->num_sms * 8;
+    // heuristic: sharing the weight stages pays off once the K loop is long enough to amortise the bigger halo
+    const bool heur2 = g.n_chunks >= 3 && ctas2 * 10 >= (int64_t)ctx->num_sms * 8;
     MT = (want == 1 || want == 2) ? want : (heur2 ? 2 : 1);
   }
-  p.HL = BM * MT + 2 * p.Wp + 2;
-  p.halo_bytes = mg_round_up(p.HL * 128, 1024);
+  halo_geometry(p, BM * MT);
   int cols = 32;
   while (cols < MT * p.n_tile) cols <<= 1;
   p.tmem_cols = cols;
   int budget_kb;
   if (MT == 1) {
-    // measured on R-MG-34 (scratch/conv_bench.py): narrow tiles are bound by per-CTA latency chains and want
-    // four resident CTAs (54 KB each, one halo buffer); N >= 192 tiles prefer two CTAs with a deeper ring
-    budget_kb = p.n_tile >= 192 ? 108 : 54;
+    // narrow tiles want several resident CTAs (prologue / epilogue of one overlap the main loop of the others);
+    // N >= 192 tiles prefer two CTAs with a deeper weight ring
+    budget_kb = p.n_tile >= 192 ? 108 : 56;
   } else {
-    // TMEM allows 512 / cols CTAs per SM; at most three, so that the weight ring is at least four stages deep
-    const int ctas = std::max(1, std::min(512 / cols, 3));
-    budget_kb = ctas == 1 ? 200 : (ctas == 2 ? 108 : 71);
+    // TMEM allows 512 / cols CTAs per SM; at most two
+    const int ctas = std::max(1, std::min(512 / cols, 2));
+    budget_kb = ctas == 1 ? 200 : 108;
   }
+  if (algo == MG_ALGO_TILE128_MID) budget_kb = 72;
   // "deep" variants trade resident CTAs for two halo buffers and a longer weight ring (more bytes in flight per CTA)
   if (algo == MG_ALGO_TILE128_DEEP) budget_kb = 108;
   if (algo == MG_ALGO_TILE256_DEEP) budget_kb = 200;
   if (budget_env > 0) budget_kb = budget_env;
   // two halo buffers when several chunks follow each other and the budget allows, else one
-  const int min_ring = MT == 1 ? 2 : 3;
+  const int min_ring = 2;
   p.n_abuf = (g.n_chunks > 1 && 2 * p.halo_bytes + min_ring * b_stage <= budget_kb * 1024) ? 2 : 1;
   int S = (budget_kb * 1024 - p.n_abuf * p.halo_bytes) / b_stage;
-  S = std::max(2, std::min(S, MAX_STAGES));
-  p.stages = S; p.lag = 1;
+  S = std::max(2, std::min(S, std::min(MAX_STAGES, p.n_stages)));
+  p.stages = S;
   static bool attr_set = false;
   if (!attr_set) {
-    const int mx = 227 * 1024 - 8 * 1024;
-    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
     attr_set = true;
   }
   const int smem = p.n_abuf * p.halo_bytes + S * b_stage + 1024;
-  MG_REQUIRE(ctx, smem <= 227 * 1024 - 8 * 1024, MG_ERR_UNSUPPORTED, "halo conv: %d bytes of shared memory", smem);
-  dim3 grid((unsigned)mg_round_up((int)mg_cdiv(p.T, BM * MT), CL), (unsigned)g.n_tiles);   // padding CTAs see only invalid slots
-  p.timeline = nullptr;
-  if (want_tl) {   // debug: dump per-CTA phase stamps of this launch to $MGCONV_TIMELINE_FILE after it ran
-    static long long* d_tl = nullptr; static size_t cap = 0;
-    const size_t need = (size_t)grid.x * grid.y * 8;
-    if (cap < need) { if (d_tl) cudaFree(d_tl); cudaMalloc(&d_tl, need * sizeof(long long)); cap = need; }
-    cudaMemsetAsync(d_tl, 0, need * sizeof(long long), ctx->stream);
-    p.timeline = d_tl;
-    umma_conv_halo_kernel<1, 1><<<grid, H_THREADS, smem, ctx->stream>>>(p);
-    cudaStreamSynchronize(ctx->stream);
-    std::vector<long long> h(need);
-    cudaMemcpy(h.data(), d_tl, need * sizeof(long long), cudaMemcpyDeviceToHost);
-    const char* fn = getenv("MGCONV_TIMELINE_FILE");
-    FILE* f = fopen(fn ? fn : "timeline.csv", "w");
-    if (f) { for (size_t i = 0; i < need / 8; ++i) fprintf(f, "%lld,%lld,%lld,%lld,%lld,%lld,%lld,%lld\n", h[i*8], h[i*8+1], h[i*8+2], h[i*8+3], h[i*8+4], h[i*8+7], h[i*8+5], h[i*8+6]); fclose(f); }
-    MG_CHECK_LAUNCH(ctx);
-    ctx->tc_launches++;
-    return MG_OK;
-  }
-  if (CL == 1) {
-    if (MT == 2) MG_CUDA(ctx, mg_launch_pdl(umma_conv_halo_kernel<1, 2>, grid, dim3(H_THREADS), (size_t)smem, ctx->stream, p));
-    else MG_CUDA(ctx, mg_launch_pdl(umma_conv_halo_kernel<1, 1>, grid, dim3(H_THREADS), (size_t)smem, ctx->stream, p));
-  } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = dim3(H_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = ctx->stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    if (CL == 2) MG_CUDA(ctx, cudaLaunchKernelEx(&cfg, umma_conv_halo_kernel<2, 1>, p));
-    else MG_CUDA(ctx, cudaLaunchKernelEx(&cfg, umma_conv_halo_kernel<4, 1>, p));
-  }
+  MG_REQUIRE(ctx, smem <= SMEM_MAX, MG_ERR_UNSUPPORTED, "halo conv: %d bytes of shared memory", smem);
+  dim3 grid((unsigned)mg_cdiv(p.T, BM * MT), (unsigned)g.n_tiles);
+  if (MT == 2) MG_CUDA(ctx, mg_launch_pdl(umma_conv_halo_kernel<2>, grid, dim3(32 * 11), (size_t)smem, ctx->stream, p));
+  else MG_CUDA(ctx, mg_launch_pdl(umma_conv_halo_kernel<1>, grid, dim3(32 * 7), (size_t)smem, ctx->stream, p));
   MG_CHECK_LAUNCH(ctx);
   ctx->tc_launches++;
   return MG_OK;
@@ -1137,49 +1047,40 @@ static bool persist_plan(const mg_ctx* ctx, const mg_conv_desc* d, const Geometr
   if (on < 0) { const char* e = getenv("MGCONV_PERSIST"); on = e ? atoi(e) : 1; }
   if (min_tiles_per_sm < 0) { const char* e = getenv("MGCONV_PERSIST_MIN_TILES"); min_tiles_per_sm = e ? atoi(e) : 4; }
   if (algo == MG_ALGO_TILE128 || algo == MG_ALGO_TILE256 || algo == MG_ALGO_TILE128_DEEP || algo == MG_ALGO_TILE256_DEEP ||
-      algo == MG_ALGO_TILE128_MCAST2) return false;
+      algo == MG_ALGO_TILE128_MID) return false;
   const bool forced = algo == MG_ALGO_RESIDENT || ctx->tune_persist == 1;
   if (!forced && (ctx->tune_persist == 2 || !on)) return false;
   if (!g.halo || g.n_tiles != 1) return false;
-  const int Wp = d->W + 1, Hp = d->H + 1;
-  const int HL = BM + 2 * Wp + 2;
-  const int halo_bytes = mg_round_up(HL * 128, 1024);
-  const int64_t m_tiles = mg_cdiv((int64_t)Nimg * Hp * Wp, BM);
+  HParams hp;
+  hp.Wp = d->W + 1;
+  halo_geometry(hp, BM);
+  const int64_t m_tiles = mg_cdiv((int64_t)Nimg * (d->H + 1) * hp.Wp, BM);
   if (!forced && m_tiles < (int64_t)min_tiles_per_sm * ctx->num_sms) return false;
-  // heuristic (scratch/conv_bench.py on R-MG-34): pays off when a tile is a single chunk (the loaders then run a whole
-  // tile ahead of the tensor core); two-chunk tiles are left to the autotuner
-  if (!forced && g.n_chunks > 1) return false;
-  const int b_bytes = g.n_chunks * 9 * g.n_tile * 128;
+  const int b_bytes = g.n_stages * g.n_tile * 128;
   const int tail = 9 * g.n_tile * 4;                       // bias tile + statistics slots
-  const int budget = 232448 - 9 * 1024 - 1024;             // 227 KB per CTA minus static shared memory and alignment slack
-  const int room = budget - b_bytes - tail;
-  int n_abuf = room / halo_bytes;
+  const int room = SMEM_MAX - 1024 - b_bytes - tail;
+  int n_abuf = room / hp.halo_bytes;
   if (n_abuf < 2) return false;
   n_abuf = std::min(n_abuf, std::min(P_MAX_ABUF, 2 * g.n_chunks + 1));
   int cols = 32;
   while (cols < 2 * g.n_tile) cols <<= 1;                  // two accumulators
   if (cols > 512) return false;
-  pl->n_abuf = n_abuf; pl->smem = n_abuf * halo_bytes + b_bytes + tail + 1024; pl->tmem_cols = cols;
+  pl->n_abuf = n_abuf; pl->smem = n_abuf * hp.halo_bytes + b_bytes + tail + 1024; pl->tmem_cols = cols;
   pl->grid = (int)std::min<int64_t>(m_tiles, ctx->num_sms);
   return true;
 }
 
-static int launch_halo_persistent(mg_ctx* ctx, UParams& p, const Geometry& g, const PersistPlan& pl) {
-  p.Wp = p.W + 1; p.Hp = p.H + 1;
-  p.T = (int64_t)p.Nimg * p.Hp * p.Wp;
-  p.HL = BM + 2 * p.Wp + 2;
-  p.n_chunks = g.n_chunks;
-  p.halo_bytes = mg_round_up(p.HL * 128, 1024);
-  p.m_tiles = (int)mg_cdiv(p.T, BM); p.n_ntiles = 1; p.n_items = p.m_tiles;
+static int launch_halo_persistent(mg_ctx* ctx, HParams& p, const PersistPlan& pl) {
+  halo_geometry(p, BM);
+  p.m_tiles = (int)mg_cdiv(p.T, BM);
   p.tmem_cols = pl.tmem_cols;
   p.n_abuf = pl.n_abuf;
-  p.stages = 0; p.lag = 1;
+  p.stages = 0;
   static bool attr_set = false;
   if (!attr_set) {
-    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448 - 9 * 1024));
+    MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
     attr_set = true;
   }
-  p.timeline = nullptr;
   MG_CUDA(ctx, mg_launch_pdl(umma_conv_halo_persistent_kernel, dim3(pl.grid), dim3(P_THREADS), (size_t)pl.smem, ctx->stream, p));
   MG_CHECK_LAUNCH(ctx);
   ctx->tc_launches++;
@@ -1190,6 +1091,24 @@ static bool fused_stats_on() {
   static int on = -1;
   if (on < 0) { const char* e = getenv("MGCONV_FUSED_STATS"); on = e ? atoi(e) : 1; }
   return on != 0;
+}
+
+// common part of the halo launches: geometry, chunk table and the tensor maps of the K segments (forward: the conv's source
+// grids; dgrad: the gradient grid)
+static int fill_halo_params(mg_ctx* ctx, HParams& p, const Geometry& g, int n_seg, const mg_grid* segs, const int* up, int N, int H, int W) {
+  memset(&p, 0, sizeof(p));
+  p.n_seg = n_seg; p.n_chunks = g.n_chunks; p.n_stages = g.n_stages;
+  for (int c = 0; c < g.n_chunks; ++c) p.chunk[c] = g.chunk[c];
+  p.H = H; p.W = W; p.Wp = W + 1; p.Hp = H + 1; p.Nimg = N;
+  p.T = (int64_t)N * p.Hp * p.Wp;
+  p.n_tile = g.n_tile;
+  for (int s = 0; s < n_seg; ++s) {
+    p.seg_up[s] = up[s];
+    if (up[s]) p.any_up = 1;
+    int rc = mg_tensor_map(ctx, segs[s].data, N, segs[s].H, segs[s].W, segs[s].Cp, up[s] ? 1 : 0, up[s] ? 2 * segs[s].W : p.Wp, &p.tmap[s]);
+    if (rc) return rc;
+  }
+  return MG_OK;
 }
 
 }  // namespace
@@ -1234,6 +1153,8 @@ static PackParams make_pack_params(const mg_conv_desc* d, const float* w, void* 
   p.Ccat = c;
   p.kv_per_tap = g.kv_per_tap; p.nkv = g.nkv; p.n_stages = g.n_stages; p.n_tile = g.n_tile; p.n_tiles = g.n_tiles;
   p.n_rows_valid = g.n_rows; p.halo = g.halo;
+  p.n_chunks = g.n_chunks;
+  for (int i = 0; i < g.n_chunks; ++i) p.chunk[i] = g.chunk[i];
   *total = (int64_t)g.n_tiles * g.n_tile * g.n_stages * KV_PER_STAGE;
   return p;
 }
@@ -1295,18 +1216,38 @@ int umma_pack_weights_batched(mg_ctx* ctx, int n, const mg_conv_desc* const* des
 
 int umma_conv_forward(mg_ctx* ctx, const mg_conv_desc* d, const void* wpack, const float* bias, mg_grid* y, double* bn_sums) {
   Geometry g = geometry(d, 0);
-  UParams p;
-  memset(&p, 0, sizeof(p));
-  p.n_seg = d->n_seg;
-  int cp = 0;
+  int up[MG_MAX_SEG];
   for (int s = 0; s < d->n_seg; ++s) {
     const mg_grid& sg = d->seg[s];
     const int m = d->seg_mode[s];
     if (m == MG_SEG_SAME) MG_REQUIRE(ctx, sg.H == d->H && sg.W == d->W, MG_ERR_SHAPE, "conv: SAME seg %d is %dx%d, expected %dx%d", s, sg.H, sg.W, d->H, d->W);
     else MG_REQUIRE(ctx, sg.H * 2 == d->H && sg.W * 2 == d->W, MG_ERR_SHAPE, "conv: UP seg %d is %dx%d, x2 != %dx%d", s, sg.H, sg.W, d->H, d->W);
     MG_REQUIRE(ctx, sg.N == d->seg[0].N, MG_ERR_SHAPE, "conv: seg %d batch", s);
+    up[s] = m == MG_SEG_UP ? 1 : 0;
+  }
+  if (g.halo) {
+    HParams hp;
+    int rc = fill_halo_params(ctx, hp, g, d->n_seg, d->seg, up, y->N, d->H, d->W);
+    if (rc) return rc;
+    hp.wpack = (const uint8_t*)wpack; hp.bias = bias; hp.c_bias = d->Cout;
+    hp.y = (__nv_bfloat16*)y->data; hp.y_pitch = y->Cp; hp.c_valid = y->Cp;
+    // the halo kernels reduce the BatchNorm statistics in their epilogue; the other kernels are followed by the statistics pass
+    const bool fused_stats = bn_sums && fused_stats_on();
+    if (fused_stats) { hp.stats = bn_sums; hp.c_stats = d->Cout; }
+    PersistPlan pl;
+    rc = persist_plan(ctx, d, g, hp.Nimg, d->algo_fwd, &pl) ? launch_halo_persistent(ctx, hp, pl) : launch_halo(ctx, hp, g, d->algo_fwd);
+    if (rc) return rc;
+    if (bn_sums && !fused_stats) return mg_bn_stats(ctx, y, bn_sums);
+    return MG_OK;
+  }
+  UParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_seg = d->n_seg;
+  int cp = 0;
+  for (int s = 0; s < d->n_seg; ++s) {
+    const mg_grid& sg = d->seg[s];
     p.seg[s].ptr = (const __nv_bfloat16*)sg.data; p.seg[s].Hs = sg.H; p.seg[s].Ws = sg.W; p.seg[s].Cp = sg.Cp;
-    p.seg[s].shift = m == MG_SEG_UP ? 1 : 0; p.seg[s].kv_begin = cp / 8;
+    p.seg[s].shift = up[s]; p.seg[s].kv_begin = cp / 8;
     cp += sg.Cp;
   }
   p.k = d->ksize; p.stride = d->stride; p.pad = d->pad; p.H = d->H; p.W = d->W;
@@ -1315,34 +1256,36 @@ int umma_conv_forward(mg_ctx* ctx, const mg_conv_desc* d, const void* wpack, con
   p.kv_per_tap = g.kv_per_tap; p.nkv = g.nkv; p.n_stages = g.n_stages; p.n_tile = g.n_tile;
   p.wpack = (const uint8_t*)wpack; p.bias = bias; p.c_bias = d->Cout;
   p.y = (__nv_bfloat16*)y->data; p.y_pitch = y->Cp; p.c_valid = y->Cp;
-  // the halo kernel reduces the BatchNorm statistics in its epilogue; the other kernels are followed by the statistics pass
-  const bool fused_stats = bn_sums && g.halo && fused_stats_on();
-  if (fused_stats) { p.stats = bn_sums; p.c_stats = d->Cout; }
-  PersistPlan pl;
-  int rc = g.halo ? (persist_plan(ctx, d, g, p.Nimg, d->algo_fwd, &pl) ? launch_halo_persistent(ctx, p, g, pl) : launch_halo(ctx, p, g, d->algo_fwd))
-                  : launch(ctx, p, g.n_tiles);
+  int rc = launch(ctx, p, g.n_tiles);
   if (rc) return rc;
-  if (bn_sums && !fused_stats) return mg_bn_stats(ctx, y, bn_sums);
+  if (bn_sums) return mg_bn_stats(ctx, y, bn_sums);
   return MG_OK;
 }
 
 int umma_conv_backward_data(mg_ctx* ctx, const mg_conv_desc* d, const void* wpack_t, const mg_grid* gr, mg_grid* dcat) {
   Geometry g = geometry(d, 1);
+  MG_REQUIRE(ctx, gr->Cp == mg_round_up(d->Cout, 8), MG_ERR_SHAPE, "dgrad: g.Cp %d", gr->Cp);
+  MG_REQUIRE(ctx, dcat->Cp == g.n_rows, MG_ERR_SHAPE, "dgrad: dcat.Cp %d != %d", dcat->Cp, g.n_rows);
+  if (g.halo) {
+    HParams hp;
+    const int up0 = 0;
+    int rc = fill_halo_params(ctx, hp, g, 1, gr, &up0, dcat->N, gr->H, gr->W);
+    if (rc) return rc;
+    hp.wpack = (const uint8_t*)wpack_t; hp.bias = nullptr;
+    hp.y = (__nv_bfloat16*)dcat->data; hp.y_pitch = dcat->Cp; hp.c_valid = dcat->Cp;
+    PersistPlan pl;
+    return persist_plan(ctx, d, g, hp.Nimg, d->algo_bwd_data, &pl) ? launch_halo_persistent(ctx, hp, pl) : launch_halo(ctx, hp, g, d->algo_bwd_data);
+  }
   UParams p;
   memset(&p, 0, sizeof(p));
   p.n_seg = 1;
   p.seg[0].ptr = (const __nv_bfloat16*)gr->data; p.seg[0].Hs = gr->H; p.seg[0].Ws = gr->W; p.seg[0].Cp = gr->Cp;
   p.seg[0].shift = 0; p.seg[0].kv_begin = 0;
-  MG_REQUIRE(ctx, gr->Cp == mg_round_up(d->Cout, 8), MG_ERR_SHAPE, "dgrad: g.Cp %d", gr->Cp);
   p.k = d->ksize; p.stride = 1; p.pad = d->ksize - 1 - d->pad; p.H = gr->H; p.W = gr->W;
   p.Ho = dcat->H; p.Wo = dcat->W; p.Nimg = dcat->N;
   p.M = (int64_t)dcat->N * dcat->H * dcat->W;
   p.kv_per_tap = g.kv_per_tap; p.nkv = g.nkv; p.n_stages = g.n_stages; p.n_tile = g.n_tile;
   p.wpack = (const uint8_t*)wpack_t; p.bias = nullptr;
   p.y = (__nv_bfloat16*)dcat->data; p.y_pitch = dcat->Cp; p.c_valid = dcat->Cp;
-  MG_REQUIRE(ctx, dcat->Cp == g.n_rows, MG_ERR_SHAPE, "dgrad: dcat.Cp %d != %d", dcat->Cp, g.n_rows);
-  PersistPlan pl;
-  return g.halo ? (persist_plan(ctx, d, g, p.Nimg, d->algo_bwd_data, &pl) ? launch_halo_persistent(ctx, p, g, pl) : launch_halo(ctx, p, g, d->algo_bwd_data))
-                : launch(ctx, p, g.n_tiles);
+  return launch(ctx, p, g.n_tiles);
 }
-

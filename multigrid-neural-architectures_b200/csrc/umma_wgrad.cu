@@ -13,6 +13,7 @@
 // fp32 reductions (red.global.add), so dW accumulates like Torch's accGradParameters.
 #include "common.cuh"
 #include "umma_common.cuh"
+#include "tma.cuh"
 #include <algorithm>
 
 namespace {
@@ -23,6 +24,7 @@ constexpr int A_IMG = PIX * 128;  // one 64-channel operand image of a stage
 constexpr int N_PROD = 128;
 constexpr int W_THREADS = 160;    // 4 producer/epilogue warps + 1 MMA warp
 constexpr int W_MAX_STAGES = 8;
+constexpr int SMEM_WGRAD = 232448 - 2048;   // 227 KB per CTA minus the kernel's static shared memory
 
 struct WParams {
   USeg seg[MG_MAX_SEG];
@@ -219,34 +221,30 @@ __global__ void __launch_bounds__(W_THREADS, 2) umma_wgrad_kernel(const __grid_c
 
 
 // ---------------------------------------------------------------- halo weight gradient -------------
-// 3x3 / stride 1: the same zero-padded slot space as umma_conv_halo_kernel.  A CTA owns one
-// 64-channel chunk of the gathered input (8 k-vectors), one column tile of Cout (<= 96) and a range of
-// 128-slot tiles.  Per tile it stages ONE halo of the chunk (128 + 2*(W+1) + 2 slots) and the g rows of
-// the 128 slots; the nine taps are nine row-shifted views of that halo.  Two taps form one UMMA
-// M = 128 operand (MN-major: its two 64-channel blocks are the same buffer LBO = shift_b - shift_a
-// rows apart), so five accumulators hold dW[tap][64 channels][n_tile] for the whole pixel range.
-constexpr int WH_MAX_SLOTS = 128 + 2 * 65 + 2;   // W <= 64
-constexpr int WH_TB = 4;                          // consecutive 128-slot tiles served by one slot -> pixel table (one barrier per WH_TB tiles)
-constexpr int WH_TAB = 128 * (WH_TB - 1) + WH_MAX_SLOTS;
-constexpr int WH_PROD = 512;              // 8 loader warps (the first 4 also drain TMEM)
-constexpr int WH_MMA_WARP = WH_PROD / 32;
-constexpr int WH_THREADS = WH_PROD + 32;
-constexpr int G_IMG = 128 * 128;   // g rows of one tile, one 64-channel block
+// 3x3 / stride 1: the same zero-padded slot space as the halo convolution kernels (umma_conv.cu).  A CTA owns one
+// chunk of the gathered input (<= 64 channels of ONE source grid), one column tile of Cout (<= 96) and a range of
+// 128-slot tiles.  Per tile the copy engine stages the halo of the chunk (whole slot rows, tma.cuh) and the g rows of the
+// 128 slots (whole slot rows too: padding slots arrive as zeros, so they add nothing to the sums); the nine taps are nine
+// row-shifted views of that halo.  Two taps form one UMMA M = 128 operand (MN-major: its two 64-channel blocks are the same
+// buffer LBO = shift_b - shift_a rows apart), so five accumulators hold dW[tap][64 channels][n_tile] for the whole range.
+// Warps: 4 epilogue (TMEM lane quarters), one TMA warp, one MMA warp.
+constexpr int WH_THREADS = 192, WH_TMA_WARP = 4, WH_MMA_WARP = 5;
 
 struct WHParams {
-  USeg seg[MG_MAX_SEG];
-  int seg_C[MG_MAX_SEG], seg_cbegin[MG_MAX_SEG];
-  int n_seg;
-  int H, W, Wp, Hp, HL, halo_bytes;
+  CUtensorMap tmap_x[MG_MAX_SEG];   // the source grids (up-sampling map for the coarser grid)
+  CUtensorMap tmap_g;               // the gradient grid
+  int n_seg, any_up;
+  int seg_up[MG_MAX_SEG];           // the grid is the coarser one (zero-stride map, W slots per row)
+  int seg_C[MG_MAX_SEG], seg_Cp[MG_MAX_SEG], seg_cbegin[MG_MAX_SEG];   // logical / padded channels, first concat channel
+  int H, W, Wp, Hp, HL;
+  int nr_max, halo_bytes;    // halo buffer: slot rows, bytes (multiple of 1024)
+  int gnr_max, g_bytes;      // g rows of a tile: slot rows, bytes per 64-channel block (multiple of 1024)
   int64_t T;
-  int kv_per_tap;
-  const __nv_bfloat16* g;
-  int g_cp, Cout, Ccat;
+  int Cout, Ccat;
   int n_tile, n_blk;
-  float* partial;      // [splits][9][Cout][Ccat] fp32 partial sums (context workspace)
+  float* partial;            // [splits][9][Cout][Ccat] fp32 partial sums (context workspace)
   int n_slot_tiles, tiles_per_cta;
-  int stages, lag, tmem_cols;
-  int chunk_shift;     // log2(n_blk * 8)
+  int stages, tmem_cols;
 };
 
 __global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __grid_constant__ WHParams p) {
@@ -255,19 +253,21 @@ __global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t full_bar[W_MAX_STAGES], empty_bar[W_MAX_STAGES], tmem_full_bar;
   __shared__ uint32_t tmem_base_s;
-  __shared__ uint32_t s_pix[2][WH_TAB], s_pup[2][WH_TAB];
-  __shared__ USeg s_seg[MG_MAX_SEG];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int S = p.stages;
-  const int stage_bytes = p.halo_bytes + p.n_blk * G_IMG;
-  const int chunk = blockIdx.x, nt = blockIdx.y;
+  const int stage_bytes = p.halo_bytes + p.n_blk * p.g_bytes;
+  const int nt = blockIdx.y;
   const int tile0 = blockIdx.z * p.tiles_per_cta;
   const int n_iters = min(p.tiles_per_cta, p.n_slot_tiles - tile0);
+  // chunk blockIdx.x = (source grid sg, first channel c0, nch channels)
+  int sg = 0, c0 = (int)blockIdx.x * 64;
+  while (sg + 1 < p.n_seg && c0 >= ((p.seg_Cp[sg] + 63) & ~63)) { c0 -= (p.seg_Cp[sg] + 63) & ~63; ++sg; }
+  const int nch = min(64, p.seg_Cp[sg] - c0);
+  const int up = p.seg_up[sg];
 
-  if (tid < p.n_seg) s_seg[tid] = p.seg[tid];
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], WH_PROD); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1 + p.n_blk); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -276,118 +276,28 @@ __global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (warp == WH_TMA_WARP && lane == 0) { tma_prefetch_desc(&p.tmap_x[sg]); tma_prefetch_desc(&p.tmap_g); }
+  if (up) {   // the up-sampling box leaves the pad slot of every row alone: zero it once (stage buffers are stage_bytes apart)
+    for (int i = tid; i < S * p.nr_max * 8; i += WH_THREADS) {
+      const int q = i & 7, row = (i >> 3) % p.nr_max, st = (i >> 3) / p.nr_max;
+      *reinterpret_cast<uint4*>(smem + (size_t)st * stage_bytes + (size_t)(row * p.Wp + p.W) * 128 + q * 16) = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async();
+  }
   pdl_wait();   // the prologue above overlapped the previous kernel's tail; g and the activations are read below
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp < WH_MMA_WARP) {
-    const int v = tid & 7, rg = tid >> 3;
-    const int r = chunk * 8 + v;                 // this thread's k-vector within a tap
-    const bool kv_ok = r < p.kv_per_tap;
-    int sg = 0;
-    if (kv_ok) while (sg + 1 < p.n_seg && r >= s_seg[sg + 1].kv_begin) ++sg;
-    const USeg sgm = s_seg[sg];
-    const uint32_t pitch = (uint32_t)sgm.Cp * 2u;
-    const char* abase = reinterpret_cast<const char*>(sgm.ptr) + (r - sgm.kv_begin) * 16;
-    const int slots_per_img = p.Hp * p.Wp, Hs2 = p.H >> 1, Ws2 = p.W >> 1;
-    const int chunks = p.n_blk * 8;               // 16-byte chunks per g row across the blocks
-    const int L = p.lag;
-    Ring rs(S), rpub(S);
-    for (int it = 0; it < n_iters + L; ++it, rs.next()) {
-      if (it < n_iters) {
-        const int s = rs.idx, tb = (it / WH_TB) & 1, toff = (it % WH_TB) * 128;
-        if (it >= S) mbar_wait(&empty_bar[s], rs.phase ^ 1u);
-        // slot -> pixel table of the next WH_TB tiles (consecutive tiles are consecutive slot ranges, so tile j of the group reads
-        // the same table 128 * j entries further on): one table computation and one barrier of the 16 loader warps per WH_TB
-        // tiles instead of per tile (measured: table + barrier were ~13 % of the kernel).  Double buffered: a thread can only
-        // be writing group g+1 after every thread passed the barrier of group g, i.e. finished reading group g-1.
-        if (toff == 0) {
-          const int64_t t0 = (int64_t)(tile0 + it) * 128;
-          const int n_ent = min(WH_TB, n_iters - it) * 128 + 2 * p.Wp + 2;
-          for (int h = tid; h < n_ent; h += WH_PROD) {
-            const int64_t t = t0 - p.Wp - 1 + h;
-            uint32_t pix = 0xFFFFFFFFu, pup = 0;
-            if (t >= 0 && t < p.T) {
-              const uint32_t tu = (uint32_t)t;
-              const uint32_t n = tu / (uint32_t)slots_per_img, rem = tu - n * (uint32_t)slots_per_img;
-              const uint32_t yy = rem / (uint32_t)p.Wp, xs = rem - yy * (uint32_t)p.Wp;
-              if ((int)yy < p.H && (int)xs < p.W) {
-                pix = (n * p.H + yy) * p.W + xs;
-                pup = (n * Hs2 + (yy >> 1)) * Ws2 + (xs >> 1);
-              }
-            }
-            s_pix[tb][h] = pix; s_pup[tb][h] = pup;
-          }
-          asm volatile("bar.sync 1, %0;" ::"n"(WH_PROD) : "memory");   // loader warps only
-        }
-        uint8_t* st = smem + (size_t)s * stage_bytes;
-        const uint32_t* tab = (sgm.shift ? s_pup[tb] : s_pix[tb]) + toff;
-        const uint32_t* tpix = s_pix[tb] + toff;
-        const uint32_t dst0 = smem_u32(st) + (uint32_t)(v << 4);
-        for (int h0 = rg; h0 < p.HL; h0 += 4 * (WH_PROD / 8)) {   // table reads batched ahead of the ordered asm copies
-          uint32_t pv[4], tv[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int h = h0 + u * (WH_PROD / 8);
-            pv[u] = h < p.HL ? tpix[h] : 0xFFFFFFFFu;
-            tv[u] = h < p.HL ? tab[h] : 0u;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int h = h0 + u * (WH_PROD / 8);
-            if (h < p.HL) {
-              const bool ok = kv_ok && pv[u] != 0xFFFFFFFFu;
-              const char* src = ok ? abase + (uint64_t)tv[u] * pitch : reinterpret_cast<const char*>(sgm.ptr);
-              cp_async16((dst0 ^ ((uint32_t)(h & 7) << 4)) + (uint32_t)h * 128, src, ok ? 16u : 0u);
-            }
-          }
-        }
-        const uint32_t g_dst = smem_u32(st) + p.halo_bytes;
-        for (int i0 = tid; i0 < 128 * chunks; i0 += 4 * WH_PROD) {
-          uint32_t pv[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * WH_PROD;
-            pv[u] = i < 128 * chunks ? tpix[(i >> p.chunk_shift) + p.Wp + 1] : 0xFFFFFFFFu;
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int i = i0 + u * WH_PROD;
-            if (i < 128 * chunks) {
-              const int row = i >> p.chunk_shift, ch = i & (chunks - 1);
-              const int c0 = nt * p.n_tile + ch * 8;
-              const bool ok = pv[u] != 0xFFFFFFFFu && ch * 8 < p.n_tile && c0 < p.g_cp;
-              const __nv_bfloat16* src = ok ? p.g + (size_t)pv[u] * p.g_cp + c0 : p.g;
-              cp_async16(g_dst + (ch >> 3) * G_IMG + row * 128 + (((ch & 7) ^ (row & 7)) << 4), src, ok ? 16u : 0u);
-            }
-          }
-        }
-      }
-      cp_async_commit();
-      if (it >= L) {
-        cp_async_wait_dyn(L);
-        fence_proxy_async();
-        mbar_arrive(&full_bar[rpub.idx]);
-        rpub.next();
-      }
-    }
-    // ---- epilogue (warps 0-3: one TMEM lane quarter each): five accumulators -> partial sums --------
-    if (warp < 4) {
+  if (warp < 4) {
+    // ---- epilogue: five accumulators -> partial sums ------------------------------------------------
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
     const int row = warp * 32 + lane;            // rows 0..63: first tap of the pair, 64..127: second
-    const int rr0 = chunk * 8 + ((row & 63) >> 3), e = row & 7;
-    int rsg = 0;
-    bool row_ok = rr0 < p.kv_per_tap;
-    int ci = 0;
-    if (row_ok) {
-      while (rsg + 1 < p.n_seg && rr0 >= s_seg[rsg + 1].kv_begin) ++rsg;
-      const int cl = (rr0 - s_seg[rsg].kv_begin) * 8 + e;
-      row_ok = cl < p.seg_C[rsg];
-      ci = p.seg_cbegin[rsg] + cl;
-    }
+    const int cl = c0 + (row & 63);              // channel within the chunk's grid
+    const bool row_ok = (row & 63) < nch && cl < p.seg_C[sg];
+    const int ci = p.seg_cbegin[sg] + cl;
     // plain coalesced stores of this CTA's partial sums (consecutive rows = consecutive ci); the
     // reduction over the pixel splits is a separate pass (wgrad_reduce_kernel): no atomics
     float* part = p.partial + (size_t)blockIdx.z * 9 * p.Cout * p.Ccat;
@@ -409,34 +319,53 @@ __global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __
       }
     }
     tc_fence_before();
+  } else if (warp == WH_TMA_WARP) {
+    // ---- producer: halo rows + g rows of every tile -------------------------------------------------
+    Ring rs(S);
+    for (int it = 0; it < n_iters; ++it, rs.next()) {
+      const int s = rs.idx;
+      if (it >= S) mbar_wait(&empty_bar[s], rs.phase ^ 1u);
+      const int t0 = (tile0 + it) * 128;
+      const int hs = t0 - p.Wp - 1;
+      const int r0 = floordiv(hs, p.Wp);
+      const int nr = (hs + p.HL - 1) / p.Wp - r0 + 1;
+      const int gr0 = t0 / p.Wp;
+      const int gnr = (t0 + 127) / p.Wp - gr0 + 1;
+      const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+      tma_load_rows(&p.tmap_x[sg], up, st, &full_bar[s], c0, r0, nr, p.W, p.Hp, lane);
+      for (int b = 0; b < p.n_blk; ++b)
+        tma_load_rows(&p.tmap_g, 0, st + (uint32_t)(p.halo_bytes + b * p.g_bytes), &full_bar[s], nt * p.n_tile + b * 64, gr0, gnr, p.W, p.Hp, lane);
     }
   } else {
-    {   // MMA issuer: whole warp, elected lane issues (see elect_one)
-      const bool leader = elect_one();
-      const uint32_t idesc = idesc_bf16_m128_mn(p.n_tile);
-      Ring rs(S);
-      for (int it = 0; it < n_iters; ++it, rs.next()) {
-        const int s = rs.idx;
-        mbar_wait(&full_bar[s], rs.phase);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t b_lo = desc_lo_mn_sw128(a_base + p.halo_bytes, G_IMG);
-        if (leader) {
+    // ---- MMA issuer: whole warp, elected lane issues (see elect_one) --------------------------------
+    const bool leader = elect_one();
+    const uint32_t idesc = idesc_bf16_m128_mn(p.n_tile);
+    Ring rs(S);
+    for (int it = 0; it < n_iters; ++it, rs.next()) {
+      const int s = rs.idx;
+      const int t0 = (tile0 + it) * 128;
+      const int hs = t0 - p.Wp - 1;
+      const int off = hs - floordiv(hs, p.Wp) * p.Wp;          // first halo slot within the row-aligned buffer
+      const int goff = t0 - (t0 / p.Wp) * p.Wp;                // first g slot within its row-aligned buffer
+      mbar_wait(&full_bar[s], rs.phase);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)off * 128u;
+      const uint32_t b_lo = desc_lo_mn_sw128(smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)p.halo_bytes + (uint32_t)goff * 128u, (uint32_t)p.g_bytes);
+      if (leader) {
 #pragma unroll 1
-          for (int pair = 0; pair < 5; ++pair) {
-            const int ta = pair * 2, tb2 = min(pair * 2 + 1, 8);
-            const int sa = (ta / 3) * p.Wp + ta % 3, sb = (tb2 / 3) * p.Wp + tb2 % 3;   // halo slot of tile row 0
-            const uint32_t a_lo = desc_lo_mn_sw128(a_base + (uint32_t)sa * 128u, (uint32_t)(sb - sa) * 128u);
-            const uint32_t d_tmem = tmem_base + pair * p.n_tile;
+        for (int pair = 0; pair < 5; ++pair) {
+          const int ta = pair * 2, tb2 = min(pair * 2 + 1, 8);
+          const int sa = (ta / 3) * p.Wp + ta % 3, sb = (tb2 / 3) * p.Wp + tb2 % 3;   // halo slot of tile row 0
+          const uint32_t a_lo = desc_lo_mn_sw128(a_base + (uint32_t)sa * 128u, (uint32_t)(sb - sa) * 128u);
+          const uint32_t d_tmem = tmem_base + pair * p.n_tile;
 #pragma unroll
-            for (int q = 0; q < 8; ++q)   // 16 slots (K) per UMMA = 2048 bytes = descriptor address + 128
-              tc_mma_bf16_lohi(d_tmem, a_lo + q * 128, b_lo + q * 128, DESC_HI_SW128, idesc, (it | q) != 0);
-          }
-          tc_commit(&empty_bar[s]);
+          for (int q = 0; q < 8; ++q)   // 16 slots (K) per UMMA = 2048 bytes = descriptor address + 128
+            tc_mma_bf16_lohi(d_tmem, a_lo + q * 128, b_lo + q * 128, DESC_HI_SW128, idesc, (it | q) != 0);
         }
+        tc_commit(&empty_bar[s]);
       }
-      if (leader) tc_commit(&tmem_full_bar);
     }
+    if (leader) tc_commit(&tmem_full_bar);
   }
   __syncthreads();
   if (warp == WH_MMA_WARP) {
@@ -491,45 +420,39 @@ static bool wgrad_halo_applies(const mg_conv_desc* d) {
 static int wgrad_halo(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g, float* dw, float gscale) {
   WHParams p;
   memset(&p, 0, sizeof(p));
-  p.n_seg = d->n_seg;
-  int c = 0, cp = 0;
-  for (int s = 0; s < d->n_seg; ++s) {
-    const mg_grid& sg = d->seg[s];
-    p.seg[s].ptr = (const __nv_bfloat16*)sg.data; p.seg[s].Hs = sg.H; p.seg[s].Ws = sg.W; p.seg[s].Cp = sg.Cp;
-    p.seg[s].shift = d->seg_mode[s] == MG_SEG_UP ? 1 : 0; p.seg[s].kv_begin = cp / 8;
-    p.seg_C[s] = sg.C; p.seg_cbegin[s] = c;
-    c += sg.C; cp += sg.Cp;
-  }
+  int Ccat = 0;
+  for (int s = 0; s < d->n_seg; ++s) Ccat += d->seg[s].C;
   p.H = d->H; p.W = d->W; p.Wp = d->W + 1; p.Hp = d->H + 1;
   p.T = (int64_t)g->N * p.Hp * p.Wp;
   p.HL = 128 + 2 * p.Wp + 2;
-  p.halo_bytes = mg_round_up(p.HL * 128, 1024);
-  p.kv_per_tap = cp / 8;
-  p.g = (const __nv_bfloat16*)g->data; p.g_cp = g->Cp; p.Cout = d->Cout; p.Ccat = c;
+  p.nr_max = (p.HL - 1 + p.Wp - 1) / p.Wp + 1;
+  p.halo_bytes = mg_round_up(p.nr_max * p.Wp * 128, 1024);
+  p.gnr_max = (127 + p.Wp - 1) / p.Wp + 1;
+  p.g_bytes = mg_round_up(p.gnr_max * p.Wp * 128, 1024);
+  p.Cout = d->Cout; p.Ccat = Ccat;
   // five accumulators of n_tile columns must fit the 512 TMEM columns: n_tile <= 96
   const int np = mg_round_up(d->Cout, 16);
   const int n_tiles = (np + 95) / 96;
   p.n_tile = mg_round_up((np + n_tiles - 1) / n_tiles, 16);
   p.n_blk = (p.n_tile + 63) / 64;
-  p.chunk_shift = p.n_blk > 1 ? 4 : 3;
   p.n_slot_tiles = (int)mg_cdiv(p.T, 128);
-  const int n_chunks = (p.kv_per_tap + 7) / 8;
+  int n_chunks = 0;
+  for (int s = 0; s < d->n_seg; ++s) n_chunks += (d->seg[s].Cp + 63) / 64;
   int64_t splits = std::max<int64_t>(1, (int64_t)ctx->num_sms / ((int64_t)n_chunks * n_tiles));
   splits = std::min<int64_t>(splits, std::max(1, p.n_slot_tiles / 2));
   p.tiles_per_cta = (int)mg_cdiv(p.n_slot_tiles, splits);
   const int z = (int)mg_cdiv(p.n_slot_tiles, p.tiles_per_cta);
-  const int stage_bytes = p.halo_bytes + p.n_blk * G_IMG;
-  int S = std::min(W_MAX_STAGES, (200 * 1024) / stage_bytes);
+  const int stage_bytes = p.halo_bytes + p.n_blk * p.g_bytes;
+  int S = std::min(W_MAX_STAGES, (SMEM_WGRAD - 1024) / stage_bytes);
   S = std::max(2, std::min(S, std::max(2, p.tiles_per_cta)));
-  // a stage is published `lag` iterations after it was issued; lag <= S-2 keeps one slot free so that the
-  // loaders issue the next tile while the tensor core works on the current one (lag = S-1 serialises them)
-  p.stages = S; p.lag = std::max(0, std::min(S - 2, 3));
+  MG_REQUIRE(ctx, S * stage_bytes + 1024 <= SMEM_WGRAD, MG_ERR_UNSUPPORTED, "halo wgrad: %d bytes of shared memory", S * stage_bytes + 1024);
+  p.stages = S;
   int cols = 32;
   while (cols < 5 * p.n_tile) cols <<= 1;
   p.tmem_cols = cols;
   static bool attr_set = false;
   if (!attr_set) {
-    MG_CUDA(ctx, cudaFuncSetAttribute(umma_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 12 * 1024));
+    MG_CUDA(ctx, cudaFuncSetAttribute(umma_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_WGRAD));
     attr_set = true;
   }
   void* ws = nullptr;
@@ -537,6 +460,19 @@ static int wgrad_halo(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g, floa
   int rc = mg_ctx_workspace(ctx, (size_t)z * plane * sizeof(float), &ws);
   if (rc) return rc;
   p.partial = (float*)ws;
+  rc = mg_tensor_map(ctx, g->data, g->N, g->H, g->W, g->Cp, 0, p.Wp, &p.tmap_g);
+  if (rc) return rc;
+  int c = 0;
+  p.n_seg = d->n_seg;
+  for (int s = 0; s < d->n_seg; ++s) {
+    const mg_grid& sg = d->seg[s];
+    p.seg_up[s] = d->seg_mode[s] == MG_SEG_UP ? 1 : 0;
+    if (p.seg_up[s]) p.any_up = 1;
+    rc = mg_tensor_map(ctx, sg.data, sg.N, sg.H, sg.W, sg.Cp, p.seg_up[s], p.seg_up[s] ? 2 * sg.W : p.Wp, &p.tmap_x[s]);
+    if (rc) return rc;
+    p.seg_C[s] = sg.C; p.seg_Cp[s] = sg.Cp; p.seg_cbegin[s] = c;
+    c += sg.C;
+  }
   dim3 grid((unsigned)n_chunks, (unsigned)n_tiles, (unsigned)z);
   MG_CUDA(ctx, mg_launch_pdl(umma_wgrad_halo_kernel, grid, dim3(WH_THREADS), (size_t)(S * stage_bytes + 1024), ctx->stream, p));
   MG_CHECK_LAUNCH(ctx);

@@ -125,7 +125,7 @@ class Engine:
     def _report_tuning(self, field):
         if os.environ.get("MGCONV_VERBOSE"):
             import collections
-            names = {0: "heuristic", 1: "tile128", 2: "tile256", 3: "resident", 4: "tile128deep", 5: "tile256deep", 6: "tile128mcast2"}
+            names = {0: "heuristic", 1: "tile128", 2: "tile256", 3: "resident", 4: "tile128deep", 5: "tile256deep", 6: "tile128mid"}
             cnt = collections.Counter((o.H, o.CcatP, o.Cout, names[getattr(o.desc, field)]) for o in self.conv_ops if o._tunable())
             print(f"[mgconv] autotune {field}: " + ", ".join(f"{h}x{h} {ci}->{co}: {a} x{n}" for (h, ci, co, a), n in sorted(cnt.items())), flush=True)
 

@@ -208,7 +208,7 @@ EDGE_CASES += [
 # kernel-selection overrides: automatic, two sub-tiles per CTA, persistent weight-resident kernel
 # (context sub-tile override, context persistent override, per-layer algo of the descriptor)
 TUNINGS = [(0, 0, 0), (2, 2, 0), (1, 1, 0), (0, 0, ffi.MG_ALGO_TILE128_DEEP), (0, 0, ffi.MG_ALGO_TILE256_DEEP), (0, 2, ffi.MG_ALGO_RESIDENT),
-           (0, 0, ffi.MG_ALGO_TILE128_MCAST2)]
+           (0, 0, ffi.MG_ALGO_TILE128_MID)]
 
 
 @pytest.mark.parametrize("tuning", TUNINGS, ids=["auto", "subtiles2", "persistent", "algo_tile128deep", "algo_tile256deep", "algo_resident", "algo_mcast2"])
