@@ -455,9 +455,9 @@ __global__ void __launch_bounds__(32 * (4 * MT + 3), MT == 1 ? 4 : 2) umma_conv_
   // everything above touched only kernel parameters, shared memory and TMEM: it overlapped the tail of the
   // previous kernel; from here on the predecessor's output (activations, packed weights, bias) is read
   pdl_wait();
-  if (tid < p.n_tile) {
-    const int ch = blockIdx.y * p.n_tile + tid;
-    s_bias[tid] = (p.bias && ch < p.c_bias) ? p.bias[ch] : 0.f;
+  for (int c = tid; c < p.n_tile; c += NT) {
+    const int ch = blockIdx.y * p.n_tile + c;
+    s_bias[c] = (p.bias && ch < p.c_bias) ? p.bias[ch] : 0.f;
   }
   tc_fence_before();
   __syncthreads();

@@ -204,6 +204,7 @@ EDGE_CASES += [
     (9, [(40, "s"), (24, "u")], 8, 12, 48, 3),    # two chunks, ragged last 256-slot tile (9 * 9 * 13 = 1053 slots)
     (4, [(136, "s")], 14, 14, 136, 3),            # three chunks with a ragged tail, N tile 144
     (2, [(16, "s"), (8, "u")], 64, 64, 24, 3),    # W = 64: the widest grid the halo kernels take (MNIST-cluttered 64x64 scale)
+    (3, [(160, "s"), (80, "u")], 8, 8, 160, 3),   # dgrad column tile of 240 > threads of the CTA (bias tile filled by a loop), tap-packed last chunk
 ]
 # kernel-selection overrides: automatic, two sub-tiles per CTA, persistent weight-resident kernel
 # (context sub-tile override, context persistent override, per-layer algo of the descriptor)
