@@ -245,6 +245,7 @@ struct WHParams {
   float* partial;            // [splits][9][Cout][Ccat] fp32 partial sums (context workspace)
   int n_slot_tiles, tiles_per_cta;
   int stages, tmem_cols;
+  int kt;                    // slots per pipeline stage (K of one stage): 128 or 256
 };
 
 __global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __grid_constant__ WHParams p) {
@@ -325,12 +326,12 @@ __global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __
     for (int it = 0; it < n_iters; ++it, rs.next()) {
       const int s = rs.idx;
       if (it >= S) mbar_wait(&empty_bar[s], rs.phase ^ 1u);
-      const int t0 = (tile0 + it) * 128;
+      const int t0 = (tile0 + it) * p.kt;
       const int hs = t0 - p.Wp - 1;
       const int r0 = floordiv(hs, p.Wp);
       const int nr = (hs + p.HL - 1) / p.Wp - r0 + 1;
       const int gr0 = t0 / p.Wp;
-      const int gnr = (t0 + 127) / p.Wp - gr0 + 1;
+      const int gnr = (t0 + p.kt - 1) / p.Wp - gr0 + 1;
       const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
       tma_load_rows(&p.tmap_x[sg], up, st, &full_bar[s], c0, r0, nr, p.W, p.Hp, lane);
       for (int b = 0; b < p.n_blk; ++b)
@@ -340,10 +341,11 @@ __global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __
     // ---- MMA issuer: whole warp, elected lane issues (see elect_one) --------------------------------
     const bool leader = elect_one();
     const uint32_t idesc = idesc_bf16_m128_mn(p.n_tile);
+    const int nq = p.kt >> 4;
     Ring rs(S);
     for (int it = 0; it < n_iters; ++it, rs.next()) {
       const int s = rs.idx;
-      const int t0 = (tile0 + it) * 128;
+      const int t0 = (tile0 + it) * p.kt;
       const int hs = t0 - p.Wp - 1;
       const int off = hs - floordiv(hs, p.Wp) * p.Wp;          // first halo slot within the row-aligned buffer
       const int goff = t0 - (t0 / p.Wp) * p.Wp;                // first g slot within its row-aligned buffer
@@ -358,8 +360,8 @@ __global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __
           const int sa = (ta / 3) * p.Wp + ta % 3, sb = (tb2 / 3) * p.Wp + tb2 % 3;   // halo slot of tile row 0
           const uint32_t a_lo = desc_lo_mn_sw128(a_base + (uint32_t)sa * 128u, (uint32_t)(sb - sa) * 128u);
           const uint32_t d_tmem = tmem_base + pair * p.n_tile;
-#pragma unroll
-          for (int q = 0; q < 8; ++q)   // 16 slots (K) per UMMA = 2048 bytes = descriptor address + 128
+#pragma unroll 8
+          for (int q = 0; q < nq; ++q)   // 16 slots (K) per UMMA = 2048 bytes = descriptor address + 128
             tc_mma_bf16_lohi(d_tmem, a_lo + q * 128, b_lo + q * 128, DESC_HI_SW128, idesc, (it | q) != 0);
         }
         tc_commit(&empty_bar[s]);
@@ -424,18 +426,25 @@ static int wgrad_halo(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g, floa
   for (int s = 0; s < d->n_seg; ++s) Ccat += d->seg[s].C;
   p.H = d->H; p.W = d->W; p.Wp = d->W + 1; p.Hp = d->H + 1;
   p.T = (int64_t)g->N * p.Hp * p.Wp;
-  p.HL = 128 + 2 * p.Wp + 2;
-  p.nr_max = (p.HL - 1 + p.Wp - 1) / p.Wp + 1;
-  p.halo_bytes = mg_round_up(p.nr_max * p.Wp * 128, 1024);
-  p.gnr_max = (127 + p.Wp - 1) / p.Wp + 1;
-  p.g_bytes = mg_round_up(p.gnr_max * p.Wp * 128, 1024);
   p.Cout = d->Cout; p.Ccat = Ccat;
   // five accumulators of n_tile columns must fit the 512 TMEM columns: n_tile <= 96
   const int np = mg_round_up(d->Cout, 16);
   const int n_tiles = (np + 95) / 96;
   p.n_tile = mg_round_up((np + n_tiles - 1) / n_tiles, 16);
   p.n_blk = (p.n_tile + 63) / 64;
-  p.n_slot_tiles = (int)mg_cdiv(p.T, 128);
+  // K tile (slots per pipeline stage): 256 when two such stages fit -- the halo overhead per slot and the number of
+  // stage hand-shakes halve, and the copy engine is fed with fewer, larger batches (scratch/tma_bw.cu)
+  static int kt_env = -1;
+  if (kt_env < 0) { const char* e = getenv("MGCONV_WGRAD_KT"); kt_env = e ? atoi(e) : 0; }
+  for (p.kt = (kt_env == 128 ? 128 : 256); ; p.kt = 128) {
+    p.HL = p.kt + 2 * p.Wp + 2;
+    p.nr_max = (p.HL - 1 + p.Wp - 1) / p.Wp + 1;
+    p.halo_bytes = mg_round_up(p.nr_max * p.Wp * 128, 1024);
+    p.gnr_max = (p.kt - 1 + p.Wp - 1) / p.Wp + 1;
+    p.g_bytes = mg_round_up(p.gnr_max * p.Wp * 128, 1024);
+    if (p.kt == 128 || 2 * (p.halo_bytes + p.n_blk * p.g_bytes) + 1024 <= SMEM_WGRAD) break;
+  }
+  p.n_slot_tiles = (int)mg_cdiv(p.T, p.kt);
   int n_chunks = 0;
   for (int s = 0; s < d->n_seg; ++s) n_chunks += (d->seg[s].Cp + 63) / 64;
   int64_t splits = std::max<int64_t>(1, (int64_t)ctx->num_sms / ((int64_t)n_chunks * n_tiles));
