@@ -58,6 +58,14 @@ typedef enum {
 
 typedef enum { MG_IMPL_AUTO = 0, MG_IMPL_SIMT = 1, MG_IMPL_TCGEN05 = 2 } mg_impl;
 
+/* Per-channel sums behind BatchNorm (forward: sum y, sum y^2; backward: sum d, sum d*y) are accumulated DETERMINISTICALLY:
+ * two's-complement fixed point in two 64-bit limbs, value = hi * 2^-10 + lo * 2^-54 (lo holds the 44 fractional bits of the
+ * 2^-10 quantum of every contribution, with headroom for 2^19 contributions).  Every contribution is converted to this form
+ * and added with integer atomics; integer addition is associative, so the totals are bit-identical from run to run, for any
+ * order in which CTAs (or ranks: an int64 sum all-reduce) arrive.  Contributions must be below 2^40 in magnitude.
+ * A buffer of n sums is n mg_sum (16 bytes each), zeroed by the caller before the first contribution. */
+typedef struct { int64_t hi, lo; } mg_sum;
+
 typedef struct {
   void* data;         /* device, NHWC [N][H][W][Cp] */
   const float* scale; /* device [Cp] or NULL (identity) */
@@ -147,14 +155,14 @@ int mg_conv_pack_weights_batched(mg_ctx* ctx, int32_t n, const mg_conv_desc* con
                                  void* const* wpack, const int32_t* transposed);
 
 /* fused gather + conv + bias; writes raw y and accumulates per-channel (sum, sumsq) of y in
- * bn_sums[2*Cout] (fp64, caller zeroes) for the following SpatialBatchNormalization */
+ * bn_sums[2*Cout] (mg_sum, caller zeroes) for the following SpatialBatchNormalization */
 int mg_conv_forward(mg_ctx* ctx, const mg_conv_desc* d, const float* w, const void* wpack,
-                    const float* bias, mg_grid* y, double* bn_sums);
+                    const float* bias, mg_grid* y, mg_sum* bn_sums);
 
 /* nn.SpatialBatchNormalization statistics -> pending affine of the conv output.
  * training: batch stats from bn_sums over `count` elements per channel, running stats updated
  * (momentum, unbiased var); else running stats.  models/ilsvrc/rnmg.lua:27,37 */
-int mg_bn_finalize(mg_ctx* ctx, const double* bn_sums, int64_t count, int32_t C, int32_t Cp,
+int mg_bn_finalize(mg_ctx* ctx, const mg_sum* bn_sums, int64_t count, int32_t C, int32_t Cp,
                    const float* gamma, const float* beta, float* running_mean, float* running_var,
                    float eps, float momentum, int training,
                    float* scale, float* shift, float* save_mean, float* save_invstd);
@@ -170,7 +178,7 @@ int mg_residual_forward(mg_ctx* ctx, const mg_grid* z, const mg_grid* s, int rel
  * (models/ilsvrc/rnmg.lua:27,37 + 13-20,140-154).  z is the raw conv output; z->scale / z->shift must point at
  * [Cp] workspaces that receive the affine (kept for evaluation-time reuse and the fp32 path). */
 typedef struct {
-  const double* sums;   /* [2*C] (sum y, sum y^2) from mg_conv_forward / mg_bn_stats; unused when !training */
+  const mg_sum* sums;   /* [2*C] (sum y, sum y^2) from mg_conv_forward / mg_bn_stats; unused when !training */
   int64_t count;        /* elements per channel behind the sums */
   const float* gamma;   /* nullable: 1 */
   const float* beta;    /* nullable: 0 */
@@ -184,9 +192,9 @@ typedef struct {
 int mg_bn_residual_forward(mg_ctx* ctx, const mg_grid* z, const mg_bn_fused* bn, const mg_grid* s, int relu,
                            mg_grid* out, mg_grid* pooled);
 
-/* per-channel (sum, sumsq) of a stored grid accumulated into bn_sums[2*C] (fp64, caller zeroes):
+/* per-channel (sum, sumsq) of a stored grid accumulated into bn_sums[2*C] (mg_sum, caller zeroes):
  * the statistics pass of nn.SpatialBatchNormalization when the conv epilogue did not fuse it */
-int mg_bn_stats(mg_ctx* ctx, const mg_grid* y, double* bn_sums);
+int mg_bn_stats(mg_ctx* ctx, const mg_grid* y, mg_sum* bn_sums);
 /* cudaMemsetAsync(ptr, 0, bytes) on the context stream (graph-capturable zeroing of sums/loss) */
 int mg_memset_zero(mg_ctx* ctx, void* ptr, size_t bytes);
 
@@ -212,7 +220,7 @@ int mg_global_avgpool_backward(mg_ctx* ctx, const mg_grid* dout, mg_grid* din);
  * (models/mnist-cluttered/unmg.lua:35-52): y[n,2y+dy,2x+dx,co] = b[co] + sum_ci x[n,y,x,ci] * w[ci][co][dy][dx];
  * weight layout [nIP][nOP][2][2] as Torch stores it.  bn_sums as in mg_conv_forward.  backward: dx (nullable),
  * dw += gscale * ..., dbias += gscale * sum(g) (both nullable). */
-int mg_upconv2x2_forward(mg_ctx* ctx, const mg_grid* x, const float* w, const float* bias, mg_grid* y, double* bn_sums);
+int mg_upconv2x2_forward(mg_ctx* ctx, const mg_grid* x, const float* w, const float* bias, mg_grid* y, mg_sum* bn_sums);
 int mg_upconv2x2_backward(mg_ctx* ctx, const mg_grid* x, const float* w, const mg_grid* g, mg_grid* dx,
                           float* dw, float* dbias, float gscale);
 
@@ -222,12 +230,12 @@ int mg_upconv2x2_backward(mg_ctx* ctx, const mg_grid* x, const float* w, const m
  * when relu_mask.  Writes d (same shape as x).  If bn_sums != NULL also accumulates
  * (sum d, sum d*xraw) per channel with xraw = bn_x ? bn_x : x (raw data). */
 int mg_grad_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid* bn_x,
-                    int32_t n_src, const mg_grad_src* src, mg_grid* d, double* bn_sums);
+                    int32_t n_src, const mg_grad_src* src, mg_grid* d, mg_sum* bn_sums);
 /* BatchNorm backward given the sums: out = gamma*invstd*(d - mean(d) - xhat*mean(d*xhat))
  * (out may alias d); dgamma += gscale*sum(d*xhat); dbeta += gscale*sum(d).
  * conv_dbias (nullable): gradBias of the convolution that produced xraw, += gscale * sum_pixels(out),
  * fused here so that the weight-gradient call can be given dbias = NULL. */
-int mg_bn_backward(mg_ctx* ctx, const mg_grid* xraw, const mg_grid* d, mg_grid* out, const double* bn_sums,
+int mg_bn_backward(mg_ctx* ctx, const mg_grid* xraw, const mg_grid* d, mg_grid* out, const mg_sum* bn_sums,
                    int64_t count, const float* gamma, const float* save_mean, const float* save_invstd,
                    float* dgamma, float* dbeta, float gscale, float* coef_ws /* [3*Cp] scratch */,
                    float* conv_dbias);
@@ -275,6 +283,7 @@ int mg_comm_destroy(mg_ctx* ctx);
 int mg_comm_share(mg_ctx* ctx, const mg_ctx* owner);
 /* in-place sum all-reduce on the context's communication stream, ordered after everything
  * enqueued so far on the compute stream; mg_allreduce_wait makes the compute stream wait */
+/* element type of the all-reduce calls: 0 = fp32, 1 = fp64, 2 = int64 (mg_sum buffers: 2 * n elements) */
 int mg_allreduce_launch(mg_ctx* ctx, void* buf, int64_t count, int is_double);
 int mg_allreduce_wait(mg_ctx* ctx);
 /* in-place sum all-reduce enqueued on the COMPUTE stream itself: the cross-replica BatchNorm statistics

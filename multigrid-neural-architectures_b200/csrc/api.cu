@@ -8,7 +8,7 @@
 #include <new>
 
 // simt_conv.cu
-int simt_conv_forward(mg_ctx*, const mg_conv_desc*, const float*, const float*, mg_grid*, double*);
+int simt_conv_forward(mg_ctx*, const mg_conv_desc*, const float*, const float*, mg_grid*, mg_sum*);
 int simt_conv_backward_data(mg_ctx*, const mg_conv_desc*, const float*, const mg_grid*, mg_grid*);
 int simt_conv_backward_weight(mg_ctx*, const mg_conv_desc*, const mg_grid*, float*, float*, float);
 // umma_conv.cu
@@ -16,7 +16,7 @@ bool umma_conv_supported(const mg_ctx*, const mg_conv_desc*, int kind);
 size_t umma_packed_bytes(const mg_conv_desc*, int transposed);
 int umma_pack_weights(mg_ctx*, const mg_conv_desc*, const float*, void*, int transposed);
 int umma_pack_weights_batched(mg_ctx*, int n, const mg_conv_desc* const*, const float* const*, void* const*, const int32_t*);
-int umma_conv_forward(mg_ctx*, const mg_conv_desc*, const void*, const float*, mg_grid*, double*);
+int umma_conv_forward(mg_ctx*, const mg_conv_desc*, const void*, const float*, mg_grid*, mg_sum*);
 int umma_conv_backward_data(mg_ctx*, const mg_conv_desc*, const void*, const mg_grid*, mg_grid*);
 int umma_conv_backward_weight(mg_ctx*, const mg_conv_desc*, const mg_grid*, float*, float*, float);
 
@@ -124,6 +124,7 @@ int mg_ctx_destroy(mg_ctx* ctx) {
   }
   for (int l = 0; l < MG_MAX_LANES; ++l) if (ctx->lane_ev[l]) cudaEventDestroy(ctx->lane_ev[l]);
   for (int l = 0; l < MG_MAX_LANES; ++l) if (ctx->up_ws[l]) cudaFree(ctx->up_ws[l]);
+  for (int l = 0; l < MG_MAX_LANES; ++l) if (ctx->sum_scratch[l]) cudaFree(ctx->sum_scratch[l]);
   for (int e = 0; e < ctx->n_events; ++e) cudaEventDestroy(ctx->events[e]);
   free(ctx->events);
   if (ctx->pack_dev) cudaFree(ctx->pack_dev);
@@ -218,7 +219,7 @@ int mg_conv_pack_weights_batched(mg_ctx* ctx, int32_t n, const mg_conv_desc* con
 }
 
 int mg_conv_forward(mg_ctx* ctx, const mg_conv_desc* d, const float* w, const void* wpack, const float* bias,
-                    mg_grid* y, double* bn_sums) {
+                    mg_grid* y, mg_sum* bn_sums) {
   if (!ctx || !d || !y || !y->data) return MG_ERR_INVALID_ARG;
   MG_REQUIRE(ctx, y->C == d->Cout && y->Cp >= y->C && y->Cp % 8 == 0, MG_ERR_SHAPE, "conv_forward: y.C %d Cp %d vs Cout %d", y->C, y->Cp, d->Cout);
   int Ho = (d->H + 2 * d->pad - d->ksize) / d->stride + 1, Wo = (d->W + 2 * d->pad - d->ksize) / d->stride + 1;
@@ -348,16 +349,16 @@ int mg_allreduce_launch(mg_ctx* ctx, void* buf, int64_t count, int is_double) {
     MG_CUDA(ctx, cudaEventRecord(ctx->lane_ev[l], ctx->lane_stream[l]));
     MG_CUDA(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->lane_ev[l], 0));
   }
-  const int ncclFloat32 = 7, ncclFloat64 = 8, ncclSum = 0;
-  MG_NCCL(ctx, g_nccl.AllReduce(buf, buf, (size_t)count, is_double ? ncclFloat64 : ncclFloat32, ncclSum, ctx->nccl_comm, ctx->comm_stream));
+  const int ncclInt64 = 4, ncclFloat32 = 7, ncclFloat64 = 8, ncclSum = 0;
+  MG_NCCL(ctx, g_nccl.AllReduce(buf, buf, (size_t)count, is_double == 2 ? ncclInt64 : (is_double ? ncclFloat64 : ncclFloat32), ncclSum, ctx->nccl_comm, ctx->comm_stream));
   return MG_OK;
 }
 
 int mg_allreduce_inline(mg_ctx* ctx, void* buf, int64_t count, int is_double) {
   if (!ctx || !buf || count < 0) return MG_ERR_INVALID_ARG;
   MG_REQUIRE(ctx, ctx->nccl_comm != nullptr, MG_ERR_NCCL, "allreduce: communicator not initialised");
-  const int ncclFloat32 = 7, ncclFloat64 = 8, ncclSum = 0;
-  MG_NCCL(ctx, g_nccl.AllReduce(buf, buf, (size_t)count, is_double ? ncclFloat64 : ncclFloat32, ncclSum, ctx->nccl_comm, ctx->stream));
+  const int ncclInt64 = 4, ncclFloat32 = 7, ncclFloat64 = 8, ncclSum = 0;
+  MG_NCCL(ctx, g_nccl.AllReduce(buf, buf, (size_t)count, is_double == 2 ? ncclInt64 : (is_double ? ncclFloat64 : ncclFloat32), ncclSum, ctx->nccl_comm, ctx->stream));
   return MG_OK;
 }
 

@@ -8,6 +8,7 @@
 #include "../../include/mgconv.h"
 
 #define MG_MAX_LANES 4
+#define MG_SUM_SCRATCH 4096
 struct mg_ctx {
   int device;
   cudaStream_t stream;      // stream every call enqueues on = lane_stream[cur_lane]
@@ -44,6 +45,7 @@ struct mg_ctx {
   int tune_mt;       // 128-slot sub-tiles per CTA of the halo convolution kernel (1 / 2)
   int tune_persist;  // weight-resident persistent kernel: 1 = whenever the weights fit, 2 = never
   // job table of mg_conv_pack_weights_batched (device copy + the host image it was uploaded from)
+  mg_sum* sum_scratch[MG_MAX_LANES];   // zeroed scratch of MG_SUM_SCRATCH deterministic sums per lane (users re-zero what they used)
   void* tmaps;         // TmapCache* (tma.cuh): CUtensorMap objects of the halo kernels, keyed by (pointer, shape)
   void* pack_dev;
   void* pack_host;
@@ -61,6 +63,16 @@ static inline int mg_ctx_workspace(mg_ctx* ctx, size_t bytes, void** out) {
   }
   *out = *ws;
   return MG_OK;
+}
+
+// zeroed per-lane scratch of deterministic sums; a user must leave it zeroed (its finalising kernel re-zeroes what it read)
+static inline mg_sum* mg_ctx_sum_scratch(mg_ctx* ctx) {
+  mg_sum** s = &ctx->sum_scratch[ctx->cur_lane];
+  if (!*s) {
+    if (cudaMalloc((void**)s, MG_SUM_SCRATCH * sizeof(mg_sum)) != cudaSuccess) { *s = nullptr; return nullptr; }
+    cudaMemsetAsync(*s, 0, MG_SUM_SCRATCH * sizeof(mg_sum), ctx->stream);
+  }
+  return *s;
 }
 
 #define MG_FAIL(ctx, code, ...)                                  \
@@ -161,6 +173,31 @@ __device__ __forceinline__ double warp_sum(double v) {
 __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+// ---- deterministic sums (mg_sum, see mgconv.h): value = hi * 2^-10 + lo * 2^-54 ------------------------------
+__device__ __forceinline__ void mg_to_fix(double v, long long& hi, long long& lo) {
+  const double s = v * 1024.0;
+  if (fabs(s) < 1.0e15) {
+    const double f = floor(s);
+    hi = (long long)f;
+    lo = (long long)((s - f) * 17592186044416.0);   // 2^44; truncation: a deterministic function of v
+  } else {   // out of range / inf / nan: poison the sum (read back as NaN)
+    hi = 1ll << 61; lo = 0;
+  }
+}
+__device__ __forceinline__ void mg_sum_add_fix(mg_sum* p, long long hi, long long lo) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(&p->hi), (unsigned long long)hi);
+  atomicAdd(reinterpret_cast<unsigned long long*>(&p->lo), (unsigned long long)lo);
+}
+__device__ __forceinline__ void mg_sum_add(mg_sum* p, double v) {
+  long long hi, lo;
+  mg_to_fix(v, hi, lo);
+  mg_sum_add_fix(p, hi, lo);
+}
+__host__ __device__ __forceinline__ double mg_sum_get(const mg_sum& s) {
+  if (s.hi >= (1ll << 60) || s.hi <= -(1ll << 60)) return nan("");
+  return (double)s.hi * (1.0 / 1024.0) + (double)s.lo * (1.0 / 18014398509481984.0);   // 2^-54
 }
 
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------

@@ -10,9 +10,9 @@ bool bf16_im2col(mg_ctx*, const mg_grid* in, int k, int stride, int pad, mg_grid
 int upconv_tc_forward(mg_ctx*, const mg_grid* x, const float* w, const float* bias, mg_grid* y);
 int upconv_tc_backward(mg_ctx*, const mg_grid* x, const float* w, const mg_grid* g, mg_grid* dx, float* dw, float* dbias, float gscale);
 bool bf16_apply(mg_ctx*, const mg_grid* z, const mg_grid* s, int relu, mg_grid* out, mg_grid* pooled, const mg_bn_fused* bn);
-bool bf16_bn_stats(mg_ctx*, const mg_grid* y, double* sums);
-bool bf16_combine(mg_ctx*, const mg_grid* x, int relu_mask, const mg_grid* bn_x, int n_src, const mg_grad_src* src, mg_grid* d, double* sums);
-bool bf16_bn_bwd_apply(mg_ctx*, const mg_grid* xraw, const mg_grid* d, mg_grid* out, const double* sums, int64_t count, const float* gamma,
+bool bf16_bn_stats(mg_ctx*, const mg_grid* y, mg_sum* sums);
+bool bf16_combine(mg_ctx*, const mg_grid* x, int relu_mask, const mg_grid* bn_x, int n_src, const mg_grad_src* src, mg_grid* d, mg_sum* sums);
+bool bf16_bn_bwd_apply(mg_ctx*, const mg_grid* xraw, const mg_grid* d, mg_grid* out, const mg_sum* sums, int64_t count, const float* gamma,
                        const float* mean, const float* invstd, float* dgamma, float* dbeta, float* conv_dbias, float gscale);
 int simt_dbias(mg_ctx* ctx, const mg_grid* g, int Cout, float* dbias, float gscale);
 bool bf16_pool3(mg_ctx*, const mg_grid* in, mg_grid* out, uint8_t* code);
@@ -47,7 +47,7 @@ __global__ void export_nchw_kernel(GridV<T> g, float* __restrict__ dst) {
 }
 
 // ---------------------------------------------------------------- BN finalise -------
-__global__ void bn_finalize_kernel(const double* sums, int64_t count, int C, int Cp, const float* gamma,
+__global__ void bn_finalize_kernel(const mg_sum* sums, int64_t count, int C, int Cp, const float* gamma,
                                    const float* beta, float* rmean, float* rvar, float eps, float momentum,
                                    int training, float* scale, float* shift, float* smean, float* sinvstd) {
   pdl_launch();
@@ -57,8 +57,8 @@ __global__ void bn_finalize_kernel(const double* sums, int64_t count, int C, int
   if (c >= C) { scale[c] = 0.f; shift[c] = 0.f; if (smean) { smean[c] = 0.f; sinvstd[c] = 0.f; } return; }
   double mean, var;
   if (training) {
-    mean = sums[c] / (double)count;
-    var = sums[C + c] / (double)count - mean * mean;   // biased
+    mean = mg_sum_get(sums[c]) / (double)count;
+    var = mg_sum_get(sums[C + c]) / (double)count - mean * mean;   // biased
     if (var < 0) var = 0;
     if (rmean) {
       double unb = count > 1 ? var * (double)count / (double)(count - 1) : var;
@@ -133,7 +133,7 @@ __global__ void residual_pool_kernel(GridV<T> z, GridV<T> s, int has_s, int relu
 // per-channel sum / sum of squares of a stored grid
 template <typename T>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ y, int cp, int C, int64_t P, int pix_per_block,
-                                                       double* sums) {
+                                                       mg_sum* sums) {
   const int cl = threadIdx.x % 32, lane = threadIdx.x / 32;
   const int c = blockIdx.y * 32 + cl;
   const int64_t p0 = (int64_t)blockIdx.x * pix_per_block, p1 = min(P, p0 + pix_per_block);
@@ -146,8 +146,8 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ y, 
   if (lane == 0 && c < C) {
     float a = 0.f, b = 0.f;
     for (int l = 0; l < 8; ++l) { a += red[0][l][cl]; b += red[1][l][cl]; }
-    atomicAdd(sums + c, (double)a);
-    atomicAdd(sums + C + c, (double)b);
+    mg_sum_add(sums + c, (double)a);
+    mg_sum_add(sums + C + c, (double)b);
   }
 }
 
@@ -254,7 +254,7 @@ struct CombineP {
   const T* bn_x; int bn_cp;
   int n_src; SrcV<T> src[MG_MAX_SRC];
   T* d; int d_cp;
-  double* bn_sums;
+  mg_sum* bn_sums;
   int pix_per_block;
 };
 
@@ -308,31 +308,35 @@ __global__ void __launch_bounds__(256) combine_kernel(CombineP<T> p) {
     if (lane == 0 && c < X.C) {
       float a = 0.f, b = 0.f;
       for (int l = 0; l < 8; ++l) { a += red[0][l][cl]; b += red[1][l][cl]; }
-      atomicAdd(p.bn_sums + c, (double)a);
-      atomicAdd(p.bn_sums + X.C + c, (double)b);
+      mg_sum_add(p.bn_sums + c, (double)a);
+      mg_sum_add(p.bn_sums + X.C + c, (double)b);
     }
   }
 }
 
 // ---------------------------------------------------------------- BN backward -------
 // coef[0*Cp+c]=A, [1*Cp+c]=B, [2*Cp+c]=Cc with d' = A*d + B*xraw + Cc
-__global__ void bn_bwd_coef_kernel(const double* sums, int64_t count, int C, int Cp, const float* gamma,
+__global__ void bn_bwd_coef_kernel(const mg_sum* sums, int64_t count, int C, int Cp, const float* gamma,
                                    const float* mean, const float* invstd, float* dgamma, float* dbeta,
-                                   float gscale, float* coef) {
+                                   float gscale, float* coef, float* conv_dbias) {
   pdl_launch();
   pdl_wait();
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= Cp) return;
   if (c >= C) { coef[c] = 0.f; coef[Cp + c] = 0.f; coef[2 * Cp + c] = 0.f; return; }
-  double sd = sums[c], sdx = sums[C + c];
+  double sd = mg_sum_get(sums[c]), sdx = mg_sum_get(sums[C + c]);
   double mu = mean[c], is = invstd[c], g = gamma ? gamma[c] : 1.0;
   double dg = is * (sdx - mu * sd);
   if (dgamma) dgamma[c] += gscale * (float)dg;
   if (dbeta) dbeta[c] += gscale * (float)sd;
   double n = (double)count;
-  coef[c] = (float)(g * is);
-  coef[Cp + c] = (float)(-g * is * is * dg / n);
-  coef[2 * Cp + c] = (float)(g * is * (mu * is * dg / n - sd / n));
+  const double Ad = g * is, Bd = -g * is * is * dg / n, Cd = g * is * (mu * is * dg / n - sd / n);
+  coef[c] = (float)Ad;
+  coef[Cp + c] = (float)Bd;
+  coef[2 * Cp + c] = (float)Cd;
+  // gradBias of the convolution that produced xraw = sum over pixels of the result = A*sum d + B*sum xraw + C*n
+  // (identically zero in exact arithmetic: pure rounding noise in the reference as well)
+  if (conv_dbias) conv_dbias[c] += gscale * (float)(Ad * sd + Bd * (mu * n) + Cd * n);
 }
 
 template <typename T>
@@ -348,10 +352,17 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ xraw, int x_cp, const 
 }
 
 // ---------------------------------------------------------------- criteria ----------
+// The scalar loss is accumulated as a deterministic integer sum (mg_sum scratch of the context, left zeroed) and added to the
+// caller's float by loss_finalize_kernel: the reported loss is bit-identical from run to run.
+__global__ void loss_finalize_kernel(mg_sum* acc, float* loss) {
+  *loss += (float)mg_sum_get(*acc);
+  acc->hi = 0; acc->lo = 0;
+}
+
 // one block per sample: LogSoftMax + ClassNLLCriterion(mean) forward and gradient
 template <typename T>
 __global__ void nll_kernel(const T* __restrict__ logits, int C, int ld, const int32_t* __restrict__ target,
-                           float* logprob, float* loss, T* dlogits, int dl_ld, float gscale, int N) {
+                           float* logprob, mg_sum* loss, T* dlogits, int dl_ld, float gscale, int N) {
   int n = blockIdx.x;
   const T* row = logits + (size_t)n * ld;
   __shared__ float red[32];
@@ -377,12 +388,12 @@ __global__ void nll_kernel(const T* __restrict__ logits, int C, int ld, const in
     if (logprob) logprob[(size_t)n * C + c] = lp;
     if (dlogits) mg_st(dlogits + (size_t)n * dl_ld + c, gscale * (expf(lp) - (c == t ? 1.f : 0.f)) / (float)N);
   }
-  if (threadIdx.x == 0 && loss) atomicAdd(loss, -(mg_ld(row + t) - lse) / (float)N);
+  if (threadIdx.x == 0 && loss) mg_sum_add(loss, (double)(-(mg_ld(row + t) - lse) / (float)N));
 }
 
 // Sigmoid + BCECriterion (mean over all elements, eps 1e-12)
 template <typename T>
-__global__ void bce_kernel(GridV<T> x, const float* __restrict__ target, float* prob, float* loss, T* dx, int dx_cp, float gscale) {
+__global__ void bce_kernel(GridV<T> x, const float* __restrict__ target, float* prob, mg_sum* loss, T* dx, int dx_cp, float gscale) {
   int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x;
   int64_t total = (int64_t)x.N * x.C * x.H * x.W;
   float l = 0.f;
@@ -401,7 +412,7 @@ __global__ void bce_kernel(GridV<T> x, const float* __restrict__ target, float* 
     }
   }
   l = warp_sum(l);
-  if (loss && threadIdx.x % 32 == 0 && l != 0.f) atomicAdd(loss, l);
+  if (loss && threadIdx.x % 32 == 0 && l != 0.f) mg_sum_add(loss, (double)l);
 }
 
 __global__ void sgd_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ v, int64_t n,
@@ -437,7 +448,7 @@ int mg_export_nchw(mg_ctx* ctx, const mg_grid* src, float* dst) {
   return MG_OK;
 }
 
-int mg_bn_finalize(mg_ctx* ctx, const double* bn_sums, int64_t count, int32_t C, int32_t Cp, const float* gamma,
+int mg_bn_finalize(mg_ctx* ctx, const mg_sum* bn_sums, int64_t count, int32_t C, int32_t Cp, const float* gamma,
                    const float* beta, float* running_mean, float* running_var, float eps, float momentum,
                    int training, float* scale, float* shift, float* save_mean, float* save_invstd) {
   if (!ctx || !scale || !shift) return MG_ERR_INVALID_ARG;
@@ -494,7 +505,7 @@ int mg_bn_residual_forward(mg_ctx* ctx, const mg_grid* z, const mg_bn_fused* bn,
   return mg_residual_forward(ctx, z, s, relu, out, pooled);
 }
 
-int mg_bn_stats(mg_ctx* ctx, const mg_grid* y, double* bn_sums) {
+int mg_bn_stats(mg_ctx* ctx, const mg_grid* y, mg_sum* bn_sums) {
   if (!ctx || !y || !bn_sums) return MG_ERR_INVALID_ARG;
   if (ctx->dtype == MG_BF16 && bf16_bn_stats(ctx, y, bn_sums)) { MG_CHECK_LAUNCH(ctx); return MG_OK; }
   int64_t P = (int64_t)y->N * y->H * y->W;
@@ -584,7 +595,7 @@ int mg_global_avgpool_backward(mg_ctx* ctx, const mg_grid* dout, mg_grid* din) {
 }
 
 int mg_grad_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid* bn_x, int32_t n_src,
-                    const mg_grad_src* src, mg_grid* d, double* bn_sums) {
+                    const mg_grad_src* src, mg_grid* d, mg_sum* bn_sums) {
   if (!ctx || !x || !d || n_src < 0 || n_src > MG_MAX_SRC || (n_src && !src)) return MG_ERR_INVALID_ARG;
   MG_REQUIRE(ctx, d->N == x->N && d->H == x->H && d->W == x->W && d->C == x->C, MG_ERR_SHAPE, "combine: d shape");
   for (int s = 0; s < n_src; ++s) {
@@ -616,7 +627,7 @@ int mg_grad_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid*
   return MG_OK;
 }
 
-int mg_bn_backward(mg_ctx* ctx, const mg_grid* xraw, const mg_grid* d, mg_grid* out, const double* bn_sums, int64_t count,
+int mg_bn_backward(mg_ctx* ctx, const mg_grid* xraw, const mg_grid* d, mg_grid* out, const mg_sum* bn_sums, int64_t count,
                    const float* gamma, const float* save_mean, const float* save_invstd, float* dgamma, float* dbeta,
                    float gscale, float* coef_ws, float* conv_dbias) {
   if (!ctx || !xraw || !d || !out || !bn_sums || !save_mean || !save_invstd || !coef_ws) return MG_ERR_INVALID_ARG;
@@ -628,13 +639,12 @@ int mg_bn_backward(mg_ctx* ctx, const mg_grid* xraw, const mg_grid* d, mg_grid* 
     return MG_OK;
   }
   mg_launch_pdl(bn_bwd_coef_kernel, dim3((unsigned)mg_cdiv(d->Cp, 128)), dim3(128), 0, ctx->stream, bn_sums, count, (int)d->C, (int)d->Cp, gamma,
-                save_mean, save_invstd, dgamma, dbeta, gscale, coef_ws);
+                save_mean, save_invstd, dgamma, dbeta, gscale, coef_ws, conv_dbias);
   MG_CHECK_LAUNCH(ctx);
   int64_t P = (int64_t)d->N * d->H * d->W;
   MG_DISPATCH(ctx, bn_bwd_apply_kernel<T><<<GRID1(P * out->Cp), EB, 0, ctx->stream>>>((const T*)xraw->data, xraw->Cp, (const T*)d->data, d->Cp,
                                                                                       (T*)out->data, out->Cp, d->C, P, coef_ws););
   MG_CHECK_LAUNCH(ctx);
-  if (conv_dbias) return simt_dbias(ctx, out, out->C, conv_dbias, gscale);
   return MG_OK;
 }
 
@@ -642,10 +652,13 @@ int mg_nll_forward_backward(mg_ctx* ctx, const mg_grid* logits, const int32_t* t
                             mg_grid* dlogits, float gscale) {
   if (!ctx || !logits || !target) return MG_ERR_INVALID_ARG;
   MG_REQUIRE(ctx, logits->H == 1 && logits->W == 1, MG_ERR_SHAPE, "nll: logits must be N x 1 x 1 x C");
-  MG_DISPATCH(ctx, nll_kernel<T><<<logits->N, 256, 0, ctx->stream>>>((const T*)logits->data, logits->C, logits->Cp, target, logprob, loss,
+  mg_sum* acc = loss ? mg_ctx_sum_scratch(ctx) : nullptr;
+  MG_REQUIRE(ctx, !loss || acc, MG_ERR_CUDA, "nll: scratch allocation failed");
+  MG_DISPATCH(ctx, nll_kernel<T><<<logits->N, 256, 0, ctx->stream>>>((const T*)logits->data, logits->C, logits->Cp, target, logprob, acc,
                                                                     dlogits ? (T*)dlogits->data : nullptr, dlogits ? dlogits->Cp : 0,
                                                                     gscale, logits->N););
   MG_CHECK_LAUNCH(ctx);
+  if (loss) { loss_finalize_kernel<<<1, 1, 0, ctx->stream>>>(acc, loss); MG_CHECK_LAUNCH(ctx); }
   return MG_OK;
 }
 
@@ -653,9 +666,12 @@ int mg_bce_forward_backward(mg_ctx* ctx, const mg_grid* x, const float* target_n
                             mg_grid* dx, float gscale) {
   if (!ctx || !x || !target_nchw) return MG_ERR_INVALID_ARG;
   int64_t total = (int64_t)x->N * x->C * x->H * x->W;
-  MG_DISPATCH(ctx, bce_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>(make_view<T>(*x), target_nchw, prob_nchw, loss,
+  mg_sum* acc = loss ? mg_ctx_sum_scratch(ctx) : nullptr;
+  MG_REQUIRE(ctx, !loss || acc, MG_ERR_CUDA, "bce: scratch allocation failed");
+  MG_DISPATCH(ctx, bce_kernel<T><<<GRID1(total), EB, 0, ctx->stream>>>(make_view<T>(*x), target_nchw, prob_nchw, acc,
                                                                       dx ? (T*)dx->data : nullptr, dx ? dx->Cp : 0, gscale););
   MG_CHECK_LAUNCH(ctx);
+  if (loss) { loss_finalize_kernel<<<1, 1, 0, ctx->stream>>>(acc, loss); MG_CHECK_LAUNCH(ctx); }
   return MG_OK;
 }
 
@@ -717,17 +733,17 @@ __global__ void logsoftmax_bwd_kernel(const float* __restrict__ logprob, const f
 }
 
 __global__ void nll_criterion_kernel(const float* __restrict__ logprob, const int32_t* __restrict__ target, int N, int C,
-                                     float* loss, float* grad_out, float gscale) {
+                                     mg_sum* loss, float* grad_out, float gscale) {
   int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x;
   if (i >= (int64_t)N * C) return;
   int c = i % C, n = i / C;
   bool hit = target[n] == c;
   if (grad_out) grad_out[i] = hit ? -gscale / (float)N : 0.f;
-  if (hit && loss) atomicAdd(loss, -logprob[i] / (float)N);
+  if (hit && loss) mg_sum_add(loss, (double)(-logprob[i] / (float)N));
 }
 
 __global__ void bce_criterion_kernel(const float* __restrict__ prob, const float* __restrict__ target, int64_t count,
-                                     float* loss, float* grad, float gscale) {
+                                     mg_sum* loss, float* grad, float gscale) {
   int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x;
   float l = 0.f;
   if (i < count) {
@@ -737,7 +753,7 @@ __global__ void bce_criterion_kernel(const float* __restrict__ prob, const float
     if (grad) grad[i] = -gscale * (t - p) / ((1.f - p + eps) * (p + eps)) / (float)count;
   }
   l = warp_sum(l);
-  if (loss && threadIdx.x % 32 == 0 && l != 0.f) atomicAdd(loss, l);
+  if (loss && threadIdx.x % 32 == 0 && l != 0.f) mg_sum_add(loss, (double)l);
 }
 
 template <typename T>
@@ -789,7 +805,10 @@ int mg_logsoftmax_backward(mg_ctx* ctx, const float* logprob, const float* grad_
 int mg_nll_criterion(mg_ctx* ctx, const float* logprob, const int32_t* target, int32_t N, int32_t C, float* loss,
                      float* grad_out, float gscale) {
   if (!ctx || !logprob || !target || N < 1 || C < 1) return MG_ERR_INVALID_ARG;
-  nll_criterion_kernel<<<GRID1((int64_t)N * C), EB, 0, ctx->stream>>>(logprob, target, N, C, loss, grad_out, gscale);
+  mg_sum* acc = loss ? mg_ctx_sum_scratch(ctx) : nullptr;
+  MG_REQUIRE(ctx, !loss || acc, MG_ERR_CUDA, "nll_criterion: scratch allocation failed");
+  nll_criterion_kernel<<<GRID1((int64_t)N * C), EB, 0, ctx->stream>>>(logprob, target, N, C, acc, grad_out, gscale);
+  if (loss) { MG_CHECK_LAUNCH(ctx); loss_finalize_kernel<<<1, 1, 0, ctx->stream>>>(acc, loss); }
   MG_CHECK_LAUNCH(ctx);
   return MG_OK;
 }
@@ -797,7 +816,10 @@ int mg_nll_criterion(mg_ctx* ctx, const float* logprob, const int32_t* target, i
 int mg_bce_criterion(mg_ctx* ctx, const float* prob, const float* target, int64_t count, float* loss, float* grad_prob,
                      float gscale) {
   if (!ctx || !prob || !target || count < 1) return MG_ERR_INVALID_ARG;
-  bce_criterion_kernel<<<GRID1(count), EB, 0, ctx->stream>>>(prob, target, count, loss, grad_prob, gscale);
+  mg_sum* acc = loss ? mg_ctx_sum_scratch(ctx) : nullptr;
+  MG_REQUIRE(ctx, !loss || acc, MG_ERR_CUDA, "bce_criterion: scratch allocation failed");
+  bce_criterion_kernel<<<GRID1(count), EB, 0, ctx->stream>>>(prob, target, count, acc, grad_prob, gscale);
+  if (loss) { MG_CHECK_LAUNCH(ctx); loss_finalize_kernel<<<1, 1, 0, ctx->stream>>>(acc, loss); }
   MG_CHECK_LAUNCH(ctx);
   return MG_OK;
 }
@@ -864,8 +886,8 @@ __global__ void upconv_dgrad_kernel(const T* __restrict__ g, int g_cp, int Cout,
 
 // one block per (ci, co-tile of 64 x 4 positions = 256 threads), pixel range split over blockIdx.z
 template <typename T>
-__global__ void __launch_bounds__(256) upconv_wgrad_kernel(const T* __restrict__ x, int x_cp, const T* __restrict__ g, int g_cp, float* dw,
-                                                           int Cin, int Cout, int N, int H, int W, float gscale, int64_t pix_per_z) {
+__global__ void __launch_bounds__(256) upconv_wgrad_kernel(const T* __restrict__ x, int x_cp, const T* __restrict__ g, int g_cp, float* partial,
+                                                           int Cin, int Cout, int N, int H, int W, int64_t pix_per_z) {
   const int ci = blockIdx.x;
   const int co = blockIdx.y * 64 + (threadIdx.x >> 2), d = threadIdx.x & 3;
   const int64_t P = (int64_t)N * H * W;
@@ -877,7 +899,16 @@ __global__ void __launch_bounds__(256) upconv_wgrad_kernel(const T* __restrict__
     const float xv = mg_ld(x + p * x_cp + ci);
     acc = fmaf(xv, mg_ld(g + (((size_t)n * 2 * H + 2 * yy + (d >> 1)) * 2 * W + 2 * xx + (d & 1)) * g_cp + co), acc);
   }
-  atomicAdd(dw + ((size_t)ci * Cout + co) * 4 + d, gscale * acc);
+  partial[((size_t)blockIdx.z * Cin * Cout + (size_t)ci * Cout + co) * 4 + d] = acc;   // per-split partial sums, added in a fixed order below
+}
+
+// dst[i] += gscale * sum_z partial[z][i], z in increasing order (no floating-point atomics)
+__global__ void partial_reduce_kernel(const float* __restrict__ partial, int splits, int64_t plane, float* __restrict__ dst, float gscale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= plane) return;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += partial[(size_t)z * plane + i];
+  dst[i] += gscale * s;
 }
 
 }  // namespace
@@ -886,7 +917,7 @@ int simt_dbias(mg_ctx* ctx, const mg_grid* g, int Cout, float* dbias, float gsca
 
 extern "C" {
 
-int mg_upconv2x2_forward(mg_ctx* ctx, const mg_grid* x, const float* w, const float* bias, mg_grid* y, double* bn_sums) {
+int mg_upconv2x2_forward(mg_ctx* ctx, const mg_grid* x, const float* w, const float* bias, mg_grid* y, mg_sum* bn_sums) {
   if (!ctx || !x || !w || !y) return MG_ERR_INVALID_ARG;
   MG_REQUIRE(ctx, y->H == 2 * x->H && y->W == 2 * x->W && y->N == x->N && !x->scale, MG_ERR_SHAPE, "upconv: y must be 2x the size of x");
   {   // bf16: one 1x1 tensor-core convolution to 4 * Cout channels + depth-to-space (upconv_tc.cu)
@@ -923,8 +954,14 @@ int mg_upconv2x2_backward(mg_ctx* ctx, const mg_grid* x, const float* w, const m
     const int64_t ppz = mg_cdiv(P, z);
     z = mg_cdiv(P, ppz);
     dim3 grid((unsigned)x->C, (unsigned)gy, (unsigned)z);
-    MG_DISPATCH(ctx, upconv_wgrad_kernel<T><<<grid, 256, 0, ctx->stream>>>((const T*)x->data, x->Cp, (const T*)g->data, g->Cp, dw, x->C, g->C, x->N,
-                                                                          x->H, x->W, gscale, ppz););
+    const int64_t plane = (int64_t)x->C * g->C * 4;
+    void* ws = nullptr;
+    const int rcw = mg_ctx_workspace(ctx, (size_t)z * plane * sizeof(float), &ws);
+    if (rcw) return rcw;
+    MG_DISPATCH(ctx, upconv_wgrad_kernel<T><<<grid, 256, 0, ctx->stream>>>((const T*)x->data, x->Cp, (const T*)g->data, g->Cp, (float*)ws, x->C, g->C, x->N,
+                                                                          x->H, x->W, ppz););
+    MG_CHECK_LAUNCH(ctx);
+    partial_reduce_kernel<<<(unsigned)mg_cdiv(plane, 256), 256, 0, ctx->stream>>>((const float*)ws, (int)z, plane, dw, gscale);
     MG_CHECK_LAUNCH(ctx);
   }
   if (dbias) return simt_dbias(ctx, g, g->C, dbias, gscale);

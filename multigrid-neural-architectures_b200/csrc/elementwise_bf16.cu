@@ -61,17 +61,25 @@ __device__ __forceinline__ void ldf8(const float* p, float (&o)[8]) {
   o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
 }
 
-// per-block reduction of per-thread channel sums into fp64 global sums.
-// Threads of a block own vector column (gtid % V); V*8 <= 4096 channels.
+// per-block reduction of per-thread channel sums into the global sums: fixed order inside the block (no floating-point
+// atomics), deterministic integer accumulation across blocks (mg_sum).  Threads of a block own vector column
+// (tid % V) and pixel lane (tid / V); V*8 <= 4096 channels.  sh: [2][lanes * V * 8] floats, lanes = blockDim.x / V.
 __device__ __forceinline__ void block_channel_sums(const float (&a)[8], const float (&b)[8], int vc, int V, int C, bool active,
-                                                   double* sums, float* sh /* [2 * V * 8] zeroed */) {
+                                                   mg_sum* sums, float* sh) {
+  const int lanes = blockDim.x / V, lane = threadIdx.x / V;
+  const int plane = lanes * V * 8;
   if (active) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { atomicAdd(&sh[vc * 8 + e], a[e]); atomicAdd(&sh[V * 8 + vc * 8 + e], b[e]); }
+    for (int e = 0; e < 8; ++e) { sh[(lane * V + vc) * 8 + e] = a[e]; sh[plane + (lane * V + vc) * 8 + e] = b[e]; }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < V * 8; c += blockDim.x)
-    if (c < C) { atomicAdd(sums + c, (double)sh[c]); atomicAdd(sums + C + c, (double)sh[V * 8 + c]); }
+    if (c < C) {
+      float sa = 0.f, sb = 0.f;
+      for (int l = 0; l < lanes; ++l) { sa += sh[l * V * 8 + c]; sb += sh[plane + l * V * 8 + c]; }
+      mg_sum_add(sums + c, (double)sa);
+      mg_sum_add(sums + C + c, (double)sb);
+    }
 }
 
 // ---------------------------------------------------------------- apply (BN + shortcut + ReLU [+ pool]) ----
@@ -86,7 +94,7 @@ struct ApplyP {
   // running statistics (evaluation) -- expression for expression bn_finalize_kernel -- and block 0 writes the
   // module state (running statistics, saved mean / invstd, scale / shift)
   int bn, training;
-  const double* sums; int64_t count;
+  const mg_sum* sums; int64_t count;
   const float* gamma; const float* beta; float* rmean; float* rvar; float eps, momentum;
   float* smean; float* sinvstd; float* scale_out; float* shift_out;
 };
@@ -99,8 +107,8 @@ __device__ __forceinline__ void apply_bn_prologue(const ApplyP& p, float* s_aff)
     if (c < p.C) {
       double mean, var;
       if (p.training) {
-        mean = p.sums[c] / (double)p.count;
-        var = p.sums[p.C + c] / (double)p.count - mean * mean;   // biased
+        mean = mg_sum_get(p.sums[c]) / (double)p.count;
+        var = mg_sum_get(p.sums[p.C + c]) / (double)p.count - mean * mean;   // biased
         if (var < 0) var = 0;
         if (p.rmean && blockIdx.x == 0) {
           const double unb = p.count > 1 ? var * (double)p.count / (double)(p.count - 1) : var;
@@ -187,13 +195,11 @@ __global__ void __launch_bounds__(256, 4) apply_bf16_kernel(const __grid_constan
 }
 
 // ---------------------------------------------------------------- BN statistics ----------
-__global__ void __launch_bounds__(256) bn_stats_bf16_kernel(const bf16* __restrict__ y, int cp, int C, int64_t P, double* sums) {
+__global__ void __launch_bounds__(256) bn_stats_bf16_kernel(const bf16* __restrict__ y, int cp, int C, int64_t P, mg_sum* sums) {
   pdl_launch();
   pdl_wait();
   extern __shared__ float sh[];
   const int V = cp >> 3;
-  for (int c = threadIdx.x; c < 2 * V * 8; c += blockDim.x) sh[c] = 0.f;
-  __syncthreads();
   // each CTA streams ONE contiguous pixel range (DRAM page locality); inside it the threads of a CTA form
   // `lanes` pixel lanes x V channel vectors and walk the range lane-strided
   const int lanes = blockDim.x / V;            // threads beyond lanes*V idle
@@ -232,7 +238,7 @@ struct CombP {
   int relu_mask;
   int n_src; CSrc src[MG_MAX_SRC];
   bf16* d; int d_cp;
-  double* sums;
+  mg_sum* sums;
   int N, H, W, C, Hb, Wb;        // Hb = ceil(H/2): 2x2 blocks
 };
 
@@ -247,10 +253,6 @@ __global__ void __launch_bounds__(256, NS < 0 ? 3 : 2) combine_bf16_kernel(const
   pdl_wait();
   extern __shared__ float sh[];
   const int V = p.d_cp >> 3;
-  if (p.sums) {
-    for (int c = threadIdx.x; c < 2 * V * 8; c += blockDim.x) sh[c] = 0.f;
-    __syncthreads();
-  }
   const int lanes = blockDim.x / V;
   const int vc = threadIdx.x % V, lane = threadIdx.x / V;
   const int c0 = vc * 8;
@@ -374,10 +376,12 @@ __global__ void __launch_bounds__(256, NS < 0 ? 3 : 2) combine_bf16_kernel(const
 }
 
 // ---------------------------------------------------------------- BN backward apply ----------
-// G = A*D + B*y + C per channel; optionally also the conv's gradBias += gscale * sum_pixels G
-// (accGradParameters of the convolution that produced y), saving a separate pass over G
+// G = A*D + B*y + C per channel.  The gradBias of the convolution that produced y (accGradParameters: sum over pixels of
+// G) needs no pass over G: sum G = A * sum d + B * sum y + C * n, all known from the sums -- and identically zero in exact
+// arithmetic (training-mode BatchNorm removes the mean), i.e. pure rounding noise in the reference too.  Block 0 adds the
+// fp64 evaluation of that expression; nothing is reduced with floating-point atomics.
 struct BnBwdP {   // coefficients derived in-kernel (bn_bwd_coef_kernel, expression for expression); block 0 accumulates dgamma / dbeta
-  const double* sums; int64_t count;
+  const mg_sum* sums; int64_t count;
   const float* gamma; const float* mean; const float* invstd;
   float* dgamma; float* dbeta;
 };
@@ -387,24 +391,23 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_bf16_kernel(const bf16* _
                                                                 float* dbias, float gscale) {
   pdl_launch();
   pdl_wait();
-  extern __shared__ float sh[];   // [V*8] gradBias partials, then [3][V*8] coefficients
+  extern __shared__ float sh[];   // [3][V*8] coefficients
   const int V = o_cp >> 3;
-  float* s_coef = sh + V * 8;
+  float* s_coef = sh;
   for (int c = threadIdx.x; c < V * 8; c += blockDim.x) {
-    sh[c] = 0.f;
     float A = 0.f, B = 0.f, Cc = 0.f;
     if (c < C) {
-      const double sd = bp.sums[c], sdx = bp.sums[C + c];
+      const double sd = mg_sum_get(bp.sums[c]), sdx = mg_sum_get(bp.sums[C + c]);
       const double mu = bp.mean[c], is = bp.invstd[c], g = bp.gamma ? bp.gamma[c] : 1.0;
       const double dg = is * (sdx - mu * sd);
+      const double n = (double)bp.count;
+      const double Ad = g * is, Bd = -g * is * is * dg / n, Cd = g * is * (mu * is * dg / n - sd / n);
       if (blockIdx.x == 0) {
         if (bp.dgamma) bp.dgamma[c] += gscale * (float)dg;
         if (bp.dbeta) bp.dbeta[c] += gscale * (float)sd;
+        if (dbias) dbias[c] += gscale * (float)(Ad * sd + Bd * (mu * n) + Cd * n);
       }
-      const double n = (double)bp.count;
-      A = (float)(g * is);
-      B = (float)(-g * is * is * dg / n);
-      Cc = (float)(g * is * (mu * is * dg / n - sd / n));
+      A = (float)Ad; B = (float)Bd; Cc = (float)Cd;
     }
     s_coef[c] = A; s_coef[V * 8 + c] = B; s_coef[2 * V * 8 + c] = Cc;
   }
@@ -415,9 +418,6 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_bf16_kernel(const bf16* _
   const bool active = lane < lanes;
   const int64_t per_cta = (P + gridDim.x - 1) / gridDim.x;      // contiguous pixel range per CTA
   const int64_t p_begin = (int64_t)blockIdx.x * per_cta, p_end = min(P, p_begin + per_cta);
-  float sb[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) sb[e] = 0.f;
   if (active) {
     float A[8], B[8], Cc[8];
 #pragma unroll
@@ -441,24 +441,10 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_bf16_kernel(const bf16* _
           V8 o;
 #pragma unroll
           for (int e = 0; e < 8; ++e) o.v[e] = (c0 + e < C) ? fmaf(A[e], dv.v[e], fmaf(B[e], xv.v[e], Cc[e])) : 0.f;
-          const uint4 pk = pack8(o);
-          *reinterpret_cast<uint4*>(out + pix * o_cp + c0) = pk;
-          if (dbias) {
-            const V8 r = unpack8(pk);   // sum what the weight-gradient kernel will read
-#pragma unroll
-            for (int e = 0; e < 8; ++e) sb[e] += r.v[e];
-          }
+          *reinterpret_cast<uint4*>(out + pix * o_cp + c0) = pack8(o);
         }
       }
     }
-  }
-  if (dbias) {
-    if (active) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) atomicAdd(&sh[c0 + e], sb[e]);
-    }
-    __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dbias + c, gscale * sh[c]);
   }
 }
 
@@ -605,17 +591,17 @@ bool bf16_apply(mg_ctx* ctx, const mg_grid* z, const mg_grid* s, int relu, mg_gr
   return true;
 }
 
-bool bf16_bn_stats(mg_ctx* ctx, const mg_grid* y, double* sums) {
-  if (y->Cp % 8 || y->Cp > 4096) return false;
+bool bf16_bn_stats(mg_ctx* ctx, const mg_grid* y, mg_sum* sums) {
+  if (y->Cp % 8 || y->Cp > 2048) return false;
   const int64_t P = (int64_t)y->N * y->H * y->W;
   const int V = y->Cp / 8;
-  mg_launch_pdl(bn_stats_bf16_kernel, dim3(reduce_grid(ctx, P * V / 4)), dim3(256), 2 * V * 8 * sizeof(float), ctx->stream, (const bf16*)y->data, y->Cp, y->C, P, sums);
+  mg_launch_pdl(bn_stats_bf16_kernel, dim3(reduce_grid(ctx, P * V / 4)), dim3(256), 2 * 256 * 8 * sizeof(float), ctx->stream, (const bf16*)y->data, y->Cp, y->C, P, sums);
   return true;
 }
 
 bool bf16_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid* bn_x, int n_src, const mg_grad_src* src, mg_grid* d,
-                  double* sums) {
-  if (x->Cp % 8 || d->Cp % 8 || d->Cp > 4096 || x->scale || x->Cp < d->Cp) return false;
+                  mg_sum* sums) {
+  if (x->Cp % 8 || d->Cp % 8 || d->Cp > 2048 || x->scale || x->Cp < d->Cp) return false;
   if (sums && bn_x && bn_x->Cp < d->Cp) return false;
   CombP p;
   memset(&p, 0, sizeof(p));
@@ -638,7 +624,7 @@ bool bf16_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid* b
   if (spec < 0) { const char* e = getenv("MGCONV_COMBINE_SPEC"); spec = e ? atoi(e) : 1; }
   int code = 0;
   for (int s = 0; s < n_src; ++s) code |= (src[s].mode & 3) << (2 * s);
-  const size_t smem = 2 * V * 8 * sizeof(float);
+  const size_t smem = sums ? 2 * 256 * 8 * sizeof(float) : 0;   // block_channel_sums staging
   // the source-mode lists of the multigrid builders (same / pool / up gathers of ResampleConcat + shortcut); anything else
   // takes the generic kernel
 #define MG_COMBINE_CASE(NSRC, M0, M1, M2, M3)                                                                      \
@@ -664,15 +650,15 @@ bool bf16_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid* b
   return true;
 }
 
-bool bf16_bn_bwd_apply(mg_ctx* ctx, const mg_grid* xraw, const mg_grid* d, mg_grid* out, const double* sums, int64_t count, const float* gamma,
+bool bf16_bn_bwd_apply(mg_ctx* ctx, const mg_grid* xraw, const mg_grid* d, mg_grid* out, const mg_sum* sums, int64_t count, const float* gamma,
                        const float* mean, const float* invstd, float* dgamma, float* dbeta, float* conv_dbias, float gscale) {
-  if (xraw->Cp % 8 || d->Cp % 8 || out->Cp % 8 || d->Cp != out->Cp || xraw->Cp < out->Cp || out->Cp > 4096) return false;
+  if (xraw->Cp % 8 || d->Cp % 8 || out->Cp % 8 || d->Cp != out->Cp || xraw->Cp < out->Cp || out->Cp > 2048) return false;
   BnBwdP bp;
   bp.sums = sums; bp.count = count; bp.gamma = gamma; bp.mean = mean; bp.invstd = invstd; bp.dgamma = dgamma; bp.dbeta = dbeta;
   const int64_t P = (int64_t)d->N * d->H * d->W;
   const int V = out->Cp / 8;
   const unsigned grid = reduce_grid(ctx, P * V, 4);
-  mg_launch_pdl(bn_bwd_apply_bf16_kernel, dim3(grid), dim3(256), 4 * V * 8 * sizeof(float), ctx->stream, (const bf16*)xraw->data, xraw->Cp,
+  mg_launch_pdl(bn_bwd_apply_bf16_kernel, dim3(grid), dim3(256), 3 * V * 8 * sizeof(float), ctx->stream, (const bf16*)xraw->data, xraw->Cp,
                 (const bf16*)d->data, d->Cp, (bf16*)out->data, out->Cp, d->C, P, bp, conv_dbias, gscale);
   return true;
 }

@@ -9,6 +9,8 @@
 #include "conv_view.cuh"
 #include <algorithm>
 
+int simt_dbias(mg_ctx* ctx, const mg_grid* g, int Cout, float* dbias, float gscale);
+
 namespace {
 
 constexpr int TM = 64, TN = 64, TK = 16, NT = 256;
@@ -70,7 +72,7 @@ struct FwdProb {
   const float* bias;  // [Cout] or null
   T* y;               // [M][Cp_out]
   int y_cp;
-  double* bn_sums;    // [2*Cout] or null
+  mg_sum* bn_sums;    // [2*Cout] or null
   int64_t M;
   __device__ int64_t L() const { return (int64_t)cv.k * cv.k * cv.Ccat; }
   struct ACtx { int n, oy, ox; bool valid; };
@@ -96,11 +98,9 @@ struct FwdProb {
     return w[((size_t)c.co * cv.Ccat + ci) * cv.k * cv.k + tap];
   }
   __device__ void epilogue(float (&acc)[4][4], int64_t m0, int co0, int tx, int ty) const {
-    __shared__ float red[2][TN];
-    if (bn_sums) {
-      for (int t = threadIdx.x; t < 2 * TN; t += NT) (&red[0][0])[t] = 0.f;
-      __syncthreads();
-    }
+    // per-thread partial sums staged by tile row (ty) and added in a fixed order: no floating-point atomics, the CTA's
+    // contribution is the same from run to run; across CTAs the totals are deterministic integer sums (mg_sum)
+    __shared__ float red[2][TM / 4][TN];
 #pragma unroll
     for (int qb = 0; qb < 4; ++qb) {
       int co = co0 + qb;
@@ -116,8 +116,8 @@ struct FwdProb {
             s += v; s2 += v * v;
           }
         }
-        if (bn_sums) { atomicAdd(&red[0][tx * 4 + qb], s); atomicAdd(&red[1][tx * 4 + qb], s2); }
       }
+      if (bn_sums) { red[0][ty][tx * 4 + qb] = s; red[1][ty][tx * 4 + qb] = s2; }
     }
     if (bn_sums) {
       __syncthreads();
@@ -125,8 +125,10 @@ struct FwdProb {
       if (t < TN) {
         int co = blockIdx.y * TN + t;
         if (co < cv.Cout) {
-          atomicAdd(bn_sums + co, (double)red[0][t]);
-          atomicAdd(bn_sums + cv.Cout + co, (double)red[1][t]);
+          float a = 0.f, b2 = 0.f;
+          for (int r = 0; r < TM / 4; ++r) { a += red[0][r][t]; b2 += red[1][r][t]; }
+          mg_sum_add(bn_sums + co, (double)a);
+          mg_sum_add(bn_sums + cv.Cout + co, (double)b2);
         }
       }
     }
@@ -185,8 +187,7 @@ struct WgradProb {
   ConvV<T> cv;
   const T* g;
   int g_cp;
-  float* dw;
-  float gscale;
+  float* partial;   // [splits][Cout][k*k*Ccat] partial sums (context workspace); simt_wgrad_reduce_kernel adds them in a fixed order
   int64_t M;
   __device__ int64_t L() const { return M; }
   struct ACtx { int co; };
@@ -220,16 +221,28 @@ struct WgradProb {
       for (int qb = 0; qb < 4; ++qb) {
         int j = j0 + qb;
         if (j >= KK * cv.Ccat) continue;
-        int tap = j / cv.Ccat, ci = j % cv.Ccat;
-        atomicAdd(dw + ((size_t)co * cv.Ccat + ci) * KK + tap, gscale * acc[qa][qb]);
+        partial[((size_t)blockIdx.z * cv.Cout + co) * ((size_t)KK * cv.Ccat) + j] = acc[qa][qb];
       }
     }
   }
 };
 
-// dbias[c] += gscale * sum_m g[m][c]
+// dw[co][ci][tap] += gscale * sum_z partial[z][co][tap * Ccat + ci]   (z in increasing order: no floating-point atomics)
+__global__ void simt_wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Cout, int Ccat, int KK, float* __restrict__ dw, float gscale) {
+  const int64_t plane = (int64_t)Cout * KK * Ccat;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= plane) return;
+  float s = 0.f;
+  for (int z = 0; z < splits; ++z) s += partial[(size_t)z * plane + i];
+  const int j = (int)(i % ((int64_t)KK * Ccat)), co = (int)(i / ((int64_t)KK * Ccat));
+  const int tap = j / Ccat, ci = j % Ccat;
+  dw[((size_t)co * Ccat + ci) * KK + tap] += gscale * s;
+}
+
+// scratch[c] += sum_m g[m][c] (deterministic integer accumulation across blocks), then dbias_finalize_kernel:
+// dbias[c] += gscale * scratch[c]; scratch[c] = 0
 template <typename T>
-__global__ void dbias_kernel(const T* g, int cp, int C, int64_t M, float* dbias, float gscale) {
+__global__ void dbias_kernel(const T* g, int cp, int C, int64_t M, mg_sum* scratch) {
   int c = blockIdx.x * 32 + (threadIdx.x % 32);
   int lane_row = threadIdx.x / 32;
   int rows_per_block = blockDim.x / 32;
@@ -243,15 +256,22 @@ __global__ void dbias_kernel(const T* g, int cp, int C, int64_t M, float* dbias,
   if (lane_row == 0 && c < C) {
     float t = 0.f;
     for (int r = 0; r < rows_per_block; ++r) t += red[r][threadIdx.x % 32];
-    atomicAdd(dbias + c, gscale * t);
+    mg_sum_add(scratch + c, (double)t);
   }
+}
+
+__global__ void dbias_finalize_kernel(mg_sum* scratch, int C, float* dbias, float gscale) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  dbias[c] += gscale * (float)mg_sum_get(scratch[c]);
+  scratch[c].hi = 0; scratch[c].lo = 0;
 }
 
 }  // namespace
 
 template <typename T>
 static int simt_forward_t(mg_ctx* ctx, const mg_conv_desc* d, const float* w, const float* bias,
-                          mg_grid* y, double* bn_sums) {
+                          mg_grid* y, mg_sum* bn_sums) {
   FwdProb<T> p;
   int rc = make_conv_view<T>(ctx, *d, &p.cv);
   if (rc) return rc;
@@ -264,7 +284,7 @@ static int simt_forward_t(mg_ctx* ctx, const mg_conv_desc* d, const float* w, co
 }
 
 int simt_conv_forward(mg_ctx* ctx, const mg_conv_desc* d, const float* w, const float* bias,
-                      mg_grid* y, double* bn_sums) {
+                      mg_grid* y, mg_sum* bn_sums) {
   MG_DISPATCH(ctx, return simt_forward_t<T>(ctx, d, w, bias, y, bn_sums););
 }
 
@@ -292,7 +312,7 @@ static int simt_wgrad_t(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g, fl
   WgradProb<T> p;
   int rc = make_conv_view<T>(ctx, *d, &p.cv);
   if (rc) return rc;
-  p.g = (const T*)g->data; p.g_cp = g->Cp; p.dw = dw; p.gscale = gscale;
+  p.g = (const T*)g->data; p.g_cp = g->Cp;
   p.M = (int64_t)p.cv.N * p.cv.Ho * p.cv.Wo;
   int KK = d->ksize * d->ksize * p.cv.Ccat;
   int gx = (int)mg_cdiv(d->Cout, TM), gy = (int)mg_cdiv(KK, TN);
@@ -300,21 +320,29 @@ static int simt_wgrad_t(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g, fl
   int64_t want = (int64_t)ctx->num_sms * 4;
   int gz = (int)std::max<int64_t>(1, std::min<int64_t>(mg_cdiv(want, (int64_t)gx * gy), mg_cdiv(p.M, 256)));
   dim3 grid(gx, gy, gz);
+  const int64_t plane = (int64_t)d->Cout * KK;
+  void* ws = nullptr;
+  rc = mg_ctx_workspace(ctx, (size_t)gz * plane * sizeof(float), &ws);
+  if (rc) return rc;
+  p.partial = (float*)ws;
   simt_gemm_kernel<<<grid, NT, 0, ctx->stream>>>(p);
   MG_CHECK_LAUNCH(ctx);
-  if (dbias) {
-    dim3 g2((unsigned)mg_cdiv(d->Cout, 32), (unsigned)std::min<int64_t>(mg_cdiv(p.M, 64), 256));
-    dbias_kernel<T><<<g2, 256, 0, ctx->stream>>>(p.g, p.g_cp, d->Cout, p.M, dbias, gscale);
-    MG_CHECK_LAUNCH(ctx);
-  }
+  simt_wgrad_reduce_kernel<<<(unsigned)mg_cdiv(plane, 256), 256, 0, ctx->stream>>>(p.partial, gz, d->Cout, p.cv.Ccat, d->ksize * d->ksize, dw, gscale);
+  MG_CHECK_LAUNCH(ctx);
+  if (dbias) return simt_dbias(ctx, g, d->Cout, dbias, gscale);
   return MG_OK;
 }
 
 template <typename T>
 static int simt_dbias_t(mg_ctx* ctx, const mg_grid* g, int Cout, float* dbias, float gscale) {
   const int64_t M = (int64_t)g->N * g->H * g->W;
+  MG_REQUIRE(ctx, Cout <= MG_SUM_SCRATCH, MG_ERR_UNSUPPORTED, "dbias: %d channels", Cout);
+  mg_sum* scratch = mg_ctx_sum_scratch(ctx);
+  MG_REQUIRE(ctx, scratch != nullptr, MG_ERR_CUDA, "dbias: scratch allocation failed");
   dim3 g2((unsigned)mg_cdiv(Cout, 32), (unsigned)std::min<int64_t>(mg_cdiv(M, 64), 256));
-  dbias_kernel<T><<<g2, 256, 0, ctx->stream>>>((const T*)g->data, g->Cp, Cout, M, dbias, gscale);
+  dbias_kernel<T><<<g2, 256, 0, ctx->stream>>>((const T*)g->data, g->Cp, Cout, M, scratch);
+  MG_CHECK_LAUNCH(ctx);
+  dbias_finalize_kernel<<<(unsigned)mg_cdiv(Cout, 256), 256, 0, ctx->stream>>>(scratch, Cout, dbias, gscale);
   MG_CHECK_LAUNCH(ctx);
   return MG_OK;
 }

@@ -60,7 +60,7 @@ struct UParams {
   int halo_bytes;    // HL * 128 rounded up to 1024
   int n_abuf;        // halo buffers (1 or 2)
   long long* timeline;   // debug (MGCONV_TIMELINE=1): per-CTA clock stamps [grid][8], else null
-  double* stats;         // halo forward: per-channel (sum y, sum y^2) of the STORED bf16 output accumulated here ([2][c_stats]), or null
+  mg_sum* stats;         // halo forward: per-channel (sum y, sum y^2) of the STORED bf16 output accumulated here ([2][c_stats]), or null
   int c_stats;
   // persistent halo kernel
   int m_tiles, n_ntiles, n_items;   // slot tiles, column tiles, work items = m_tiles * n_ntiles
@@ -387,7 +387,7 @@ struct HParams {
   __nv_bfloat16* y;
   int y_pitch, c_valid;
   int stages, tmem_cols;
-  double* stats;      // forward: per-channel (sum y, sum y^2) of the STORED bf16 output accumulated here ([2][c_stats]), or null
+  mg_sum* stats;      // forward: per-channel (sum y, sum y^2) of the STORED bf16 output accumulated here ([2][c_stats]), or null
   int c_stats;
   int m_tiles;        // persistent kernel: 128-slot tiles in total
 };
@@ -467,8 +467,8 @@ __global__ void __launch_bounds__(32 * (4 * MT + 3), MT == 1 ? 4 : 2) umma_conv_
   if (warp < EPI_WARPS) {
     // ================= epilogue: TMEM -> registers -> bf16 NHWC rows ===========================
     // With p.stats the BatchNorm statistics of this tile (sum, sum of squares of the STORED bf16 values over the
-    // valid rows) are reduced here: warp butterfly -> per-warp slots in the (now idle) halo buffer -> one fp64
-    // atomic pair per channel and CTA.  The separate statistics pass over y (one HBM read of y) disappears.
+    // valid rows) are reduced here: warp butterfly -> per-warp slots in the (now idle) halo buffer -> one deterministic
+    // (fixed-point integer, mg_sum) atomic pair per channel and CTA.  The separate statistics pass over y (one HBM read of y) disappears.
     const int row = warp * 32 + lane;                      // sub-tile warp >> 2, TMEM lane quarter warp & 3
     uint32_t pix = 0;
     const bool row_ok = slot_pixel(p, (int64_t)t0 + row, &pix);
@@ -518,11 +518,16 @@ __global__ void __launch_bounds__(32 * (4 * MT + 3), MT == 1 ? 4 : 2) umma_conv_
       for (int c = tid; c < p.n_tile; c += 128 * MT) {
         const int ch = n_base + c;
         if (ch < p.c_stats) {
-          float a = 0.f, b = 0.f;
+          // every warp's sums (32 aligned slots, fixed butterfly order) enter as fixed-point integers: the totals do not depend
+          // on how slots are grouped into CTAs, i.e. every kernel variant (TILE128 / TILE256 / RESIDENT) gives the same bits
+          long long ah = 0, al = 0, bh = 0, bl = 0, h, l;
 #pragma unroll
-          for (int w = 0; w < 4 * MT; ++w) { a += s_part[(2 * w) * 256 + c]; b += s_part[(2 * w + 1) * 256 + c]; }
-          atomicAdd(p.stats + ch, (double)a);
-          atomicAdd(p.stats + p.c_stats + ch, (double)b);
+          for (int w = 0; w < 4 * MT; ++w) {
+            mg_to_fix((double)s_part[(2 * w) * 256 + c], h, l); ah += h; al += l;
+            mg_to_fix((double)s_part[(2 * w + 1) * 256 + c], h, l); bh += h; bl += l;
+          }
+          mg_sum_add_fix(p.stats + ch, ah, al);
+          mg_sum_add_fix(p.stats + p.c_stats + ch, bh, bl);
         }
       }
     }
@@ -605,7 +610,7 @@ __global__ void __launch_bounds__(32 * (4 * MT + 3), MT == 1 ? 4 : 2) umma_conv_
 //                    the tensor core works on the current one),
 //   1 MMA warp       accumulates tile i into TMEM accumulator i & 1 (every operand already in shared memory),
 //   4 epilogue warps drain accumulator (i-1) & 1 meanwhile (TMEM double buffering) and keep the BatchNorm
-//                    statistics of all the CTA's tiles in shared memory: one fp64 atomic pair per channel and CTA.
+//                    statistics of all the CTA's tiles in shared memory: one deterministic (integer) atomic pair per channel and CTA.
 constexpr int P_A_WARP = 4, P_B_WARP = 5, P_MMA_WARP = 6, P_THREADS = 224;
 constexpr int P_MAX_ABUF = 6;
 
@@ -621,11 +626,11 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
   const int b_stage_bytes = p.n_tile * 128;
   uint8_t* a_smem = smem;
   uint8_t* b_smem = smem + (size_t)NA * p.halo_bytes;                                  // all weight stages, resident
-  float* s_bias = reinterpret_cast<float*>(b_smem + (size_t)p.n_stages * b_stage_bytes);   // [n_tile]
-  float* s_part = s_bias + p.n_tile;                                                   // [4 epilogue warps][2][n_tile]
+  long long* s_part = reinterpret_cast<long long*>(b_smem + (size_t)p.n_stages * b_stage_bytes);   // [4 epilogue warps][2][n_tile][hi, lo]
+  float* s_bias = reinterpret_cast<float*>(s_part + 16 * p.n_tile);                    // [n_tile]
   const int n_my = (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles blockIdx.x, +gridDim.x, ...
 
-  for (int c = tid; c < 8 * p.n_tile; c += P_THREADS) s_part[c] = 0.f;
+  for (int c = tid; c < 16 * p.n_tile; c += P_THREADS) s_part[c] = 0;
   if (tid == 0) {
     mbar_init(&b_full, 1);
     for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
@@ -688,8 +693,14 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
               sv[8 + 2 * e] = ra * ra; sv[8 + 2 * e + 1] = rb * rb;
             }
             const float tot = warp_reduce_scatter16(sv, lane);
-            // slot owned by this lane of this warp for the whole kernel: accumulate over the CTA's tiles without synchronisation
-            if (lane < 16) s_part[(warp * 2 + (lane >> 3)) * p.n_tile + c0 + h * 8 + (lane & 7)] += tot;
+            // slot owned by this lane of this warp for the whole kernel: accumulate over the CTA's tiles without synchronisation,
+            // as fixed-point integers (exact, so the totals do not depend on which tiles this CTA happened to walk)
+            if (lane < 16) {
+              long long fh, fl;
+              mg_to_fix((double)tot, fh, fl);
+              long long* sp = s_part + (size_t)((warp * 2 + (lane >> 3)) * p.n_tile + c0 + h * 8 + (lane & 7)) * 2;
+              sp[0] += fh; sp[1] += fl;
+            }
           }
         }
       }
@@ -700,11 +711,15 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
       asm volatile("bar.sync 3, 128;" ::: "memory");
       for (int c = tid; c < p.n_tile; c += 128)
         if (c < p.c_stats) {
-          float a = 0.f, b = 0.f;
+          long long ah = 0, al = 0, bh = 0, bl = 0;
 #pragma unroll
-          for (int w = 0; w < 4; ++w) { a += s_part[(w * 2) * p.n_tile + c]; b += s_part[(w * 2 + 1) * p.n_tile + c]; }
-          atomicAdd(p.stats + c, (double)a);
-          atomicAdd(p.stats + p.c_stats + c, (double)b);
+          for (int w = 0; w < 4; ++w) {
+            const long long* sa = s_part + (size_t)((w * 2) * p.n_tile + c) * 2;
+            const long long* sb = s_part + (size_t)((w * 2 + 1) * p.n_tile + c) * 2;
+            ah += sa[0]; al += sa[1]; bh += sb[0]; bl += sb[1];
+          }
+          mg_sum_add_fix(p.stats + c, ah, al);
+          mg_sum_add_fix(p.stats + p.c_stats + c, bh, bl);
         }
     }
   } else if (warp == P_A_WARP) {
@@ -1057,7 +1072,7 @@ static bool persist_plan(const mg_ctx* ctx, const mg_conv_desc* d, const Geometr
   const int64_t m_tiles = mg_cdiv((int64_t)Nimg * (d->H + 1) * hp.Wp, BM);
   if (!forced && m_tiles < (int64_t)min_tiles_per_sm * ctx->num_sms) return false;
   const int b_bytes = g.n_stages * g.n_tile * 128;
-  const int tail = 9 * g.n_tile * 4;                       // bias tile + statistics slots
+  const int tail = g.n_tile * (4 + 128);                   // bias tile + statistics accumulators (4 warps x 2 sums x 2 int64 limbs)
   const int room = SMEM_MAX - 1024 - b_bytes - tail;
   int n_abuf = room / hp.halo_bytes;
   if (n_abuf < 2) return false;
@@ -1214,7 +1229,7 @@ int umma_pack_weights_batched(mg_ctx* ctx, int n, const mg_conv_desc* const* des
   return MG_OK;
 }
 
-int umma_conv_forward(mg_ctx* ctx, const mg_conv_desc* d, const void* wpack, const float* bias, mg_grid* y, double* bn_sums) {
+int umma_conv_forward(mg_ctx* ctx, const mg_conv_desc* d, const void* wpack, const float* bias, mg_grid* y, mg_sum* bn_sums) {
   Geometry g = geometry(d, 0);
   int up[MG_MAX_SEG];
   for (int s = 0; s < d->n_seg; ++s) {

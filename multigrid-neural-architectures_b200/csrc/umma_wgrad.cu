@@ -39,7 +39,7 @@ struct WParams {
   int Cout, Ccat;
   int n_tile;            // UMMA N (multiple of 16)
   int n_blk;             // 64-channel images of g per stage = ceil(n_tile / 64)
-  float* dw;             // [Cout][Ccat][k][k]
+  float* partial;        // [splits][k*k][Cout][Ccat] fp32 partial sums (context workspace), reduced by wgrad_reduce_kernel
   float gscale;
   int64_t pix_per_cta;   // multiple of PIX
   int stages, lag, tmem_cols;
@@ -176,7 +176,9 @@ __global__ void __launch_bounds__(W_THREADS, 2) umma_wgrad_kernel(const __grid_c
       rr = p.seg_cbegin[rsg] + cl;              // logical concat channel ci
     }
     const int KK = p.k * p.k;
-    float* dwrow = p.dw + (size_t)rr * KK + rtap;
+    // plain stores of this CTA's partial sums; the reduction over the pixel splits is a separate pass in a fixed order
+    // (wgrad_reduce_kernel): no floating-point atomics, the gradient is bit-identical from run to run
+    float* prow = p.partial + (((size_t)blockIdx.z * KK + rtap) * p.Cout) * p.Ccat + rr;
     for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
       uint32_t acc[16];
       tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, acc);
@@ -185,7 +187,7 @@ __global__ void __launch_bounds__(W_THREADS, 2) umma_wgrad_kernel(const __grid_c
 #pragma unroll
         for (int x = 0; x < 16; ++x) {
           const int co = nt * p.n_tile + c0 + x;
-          if (co < p.Cout) atomicAdd(dwrow + (size_t)co * p.Ccat * KK, p.gscale * __uint_as_float(acc[x]));
+          if (co < p.Cout) prow[(size_t)co * p.Ccat] = __uint_as_float(acc[x]);
         }
       }
     }
@@ -376,19 +378,19 @@ __global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __
   }
 }
 
-// dw[co][ci][tap] += gscale * sum_z partial[z][tap][co][ci]
+// dw[co][ci][tap] += gscale * sum_z partial[z][tap][co][ci]   (z in increasing order: deterministic)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Cout, int Ccat, float* __restrict__ dw,
-                                                           float gscale) {
+                                                           float gscale, int KK) {
   pdl_launch();
   pdl_wait();
-  const int64_t plane = (int64_t)9 * Cout * Ccat;
+  const int64_t plane = (int64_t)KK * Cout * Ccat;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // index in [tap][co][ci] order (coalesced reads)
   if (i >= plane) return;
   float s = 0.f;
   for (int z = 0; z < splits; ++z) s += partial[(size_t)z * plane + i];
   const int ci = (int)(i % Ccat); const int64_t q = i / Ccat;
   const int co = (int)(q % Cout); const int tap = (int)(q / Cout);
-  dw[((size_t)co * Ccat + ci) * 9 + tap] += gscale * s;
+  dw[((size_t)co * Ccat + ci) * KK + tap] += gscale * s;
 }
 
 }  // namespace
@@ -486,7 +488,7 @@ static int wgrad_halo(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g, floa
   MG_CUDA(ctx, mg_launch_pdl(umma_wgrad_halo_kernel, grid, dim3(WH_THREADS), (size_t)(S * stage_bytes + 1024), ctx->stream, p));
   MG_CHECK_LAUNCH(ctx);
   ctx->tc_launches++;
-  MG_CUDA(ctx, mg_launch_pdl(wgrad_reduce_kernel, dim3((unsigned)mg_cdiv((int64_t)plane, 256)), dim3(256), 0, ctx->stream, (const float*)p.partial, z, p.Cout, p.Ccat, dw, gscale));
+  MG_CUDA(ctx, mg_launch_pdl(wgrad_reduce_kernel, dim3((unsigned)mg_cdiv((int64_t)plane, 256)), dim3(256), 0, ctx->stream, (const float*)p.partial, z, p.Cout, p.Ccat, dw, gscale, 9));
   MG_CHECK_LAUNCH(ctx);
   return MG_OK;
 }
@@ -522,7 +524,7 @@ int umma_conv_backward_weight(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid*
   const int n_tiles = (np + 255) / 256;
   p.n_tile = mg_round_up((np + n_tiles - 1) / n_tiles, 16);
   p.n_blk = (p.n_tile + 63) / 64;
-  p.dw = dw; p.gscale = gscale;
+  p.gscale = gscale;
   const int m_tiles = (p.nkv + 15) / 16;
   // split the pixel range so that four CTAs are resident per SM (the loaders are latency bound)
   static int per_sm = -1;
@@ -548,10 +550,20 @@ int umma_conv_backward_weight(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid*
     MG_CUDA(ctx, cudaFuncSetAttribute(umma_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 8 * 1024));
     attr_set = true;
   }
+  const int KK = p.k * p.k;
+  const size_t plane = (size_t)KK * p.Cout * p.Ccat;
+  void* ws = nullptr;
+  int rc = mg_ctx_workspace(ctx, (size_t)z * plane * sizeof(float), &ws);
+  if (rc) return rc;
+  p.partial = (float*)ws;
+  // rows of the last M tile beyond nkv and pad channels are never written: the reduction must not read garbage there
+  // -- every (tap, co, ci) of the plane IS written by exactly one (M tile, column tile) of every split
   dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)z);
   umma_wgrad_kernel<<<grid, W_THREADS, S * stage_bytes + 1024, ctx->stream>>>(p);
   MG_CHECK_LAUNCH(ctx);
   ctx->tc_launches++;
+  MG_CUDA(ctx, mg_launch_pdl(wgrad_reduce_kernel, dim3((unsigned)mg_cdiv((int64_t)plane, 256)), dim3(256), 0, ctx->stream, (const float*)p.partial, z, p.Cout, p.Ccat, dw, gscale, KK));
+  MG_CHECK_LAUNCH(ctx);
   if (dbias) return simt_dbias(ctx, g, d->Cout, dbias, gscale);
   return MG_OK;
 }

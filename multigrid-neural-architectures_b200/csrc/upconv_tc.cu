@@ -13,7 +13,7 @@
 bool umma_conv_supported(const mg_ctx*, const mg_conv_desc*, int kind);
 size_t umma_packed_bytes(const mg_conv_desc*, int transposed);
 int umma_pack_weights(mg_ctx*, const mg_conv_desc*, const float*, void*, int transposed);
-int umma_conv_forward(mg_ctx*, const mg_conv_desc*, const void*, const float*, mg_grid*, double*);
+int umma_conv_forward(mg_ctx*, const mg_conv_desc*, const void*, const float*, mg_grid*, mg_sum*);
 int umma_conv_backward_data(mg_ctx*, const mg_conv_desc*, const void*, const mg_grid*, mg_grid*);
 int umma_conv_backward_weight(mg_ctx*, const mg_conv_desc*, const mg_grid*, float*, float*, float);
 

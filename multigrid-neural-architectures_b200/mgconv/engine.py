@@ -61,10 +61,10 @@ class Engine:
         self.gscale = 1.0
         self.bytes = 0
         self.on_param_done = None
-        # fp64 BatchNorm sums of the whole plan live in two arenas (forward: sum y, sum y^2; backward: sum d, sum d*y),
-        # each zeroed by ONE memset per pass instead of one per convolution
-        self._sums = {"fwd": [torch.zeros(1 << 17, dtype=torch.float64, device=self.device), 0],
-                      "bwd": [torch.zeros(1 << 17, dtype=torch.float64, device=self.device), 0]}
+        # BatchNorm sums of the whole plan (mg_sum: deterministic fixed-point pairs of int64, see mgconv.h) live in two arenas
+        # (forward: sum y, sum y^2; backward: sum d, sum d*y), each zeroed by ONE memset per pass instead of one per convolution
+        self._sums = {"fwd": [torch.zeros(1 << 18, dtype=torch.int64, device=self.device), 0],
+                      "bwd": [torch.zeros(1 << 18, dtype=torch.int64, device=self.device), 0]}
         self._pack_cache = None
         # per-layer choice of the 3x3 kernel variant by timing (cudnn.benchmark of the reference); MGCONV_AUTOTUNE=0 keeps the heuristics
         self.autotune = os.environ.get("MGCONV_AUTOTUNE", "1") != "0"
@@ -105,11 +105,13 @@ class Engine:
         return t
 
     def alloc_sums(self, n, which):
+        """n deterministic sums (mg_sum = two int64 each)"""
         arena = self._sums[which]
-        n8 = (n + 7) // 8 * 8
+        n2 = 2 * n
+        n8 = (n2 + 7) // 8 * 8
         if arena[1] + n8 > arena[0].numel():
             raise ffi.MGError("BatchNorm statistics arena exhausted")
-        v = arena[0][arena[1]:arena[1] + n]
+        v = arena[0][arena[1]:arena[1] + n2]
         arena[1] += n8
         return v
 

@@ -353,7 +353,7 @@ class ConvOp(Op):
 
     def bwd_weight(self, E):
         """accGradParameters: nothing but the optimiser (and the gradient all-reduce) waits for this"""
-        fused_bias = self.apply is not None and self.apply.bn is not None and not E.bn_sync   # done by mg_bn_backward
+        fused_bias = self.apply is not None and self.apply.bn is not None   # done by mg_bn_backward (from the BatchNorm sums)
         E.ctx.call("mg_conv_backward_weight", C.byref(self.desc), C.byref(self.y.G), ptr(self.mod.gradWeight),
                    None if fused_bias else ptr(self.mod.gradBias), E.gscale)
         E.param_done(self.mod)
@@ -425,7 +425,7 @@ class UpConvOp(Op):
     def bwd(self, E):
         if self.ycomb is not None:
             self.ycomb.run()
-        fused_bias = self.apply is not None and self.apply.bn is not None and not E.bn_sync
+        fused_bias = self.apply is not None and self.apply.bn is not None
         E.ctx.call("mg_upconv2x2_backward", C.byref(self.gi), ptr(self.mod.weight), C.byref(self.y.G),
                    C.byref(self.dxg) if self.dx is not None else None, ptr(self.mod.gradWeight),
                    None if fused_bias else ptr(self.mod.gradBias), E.gscale)
@@ -498,7 +498,7 @@ class ApplyOp(Op):
         pg = C.byref(self.pg) if self.pg is not None else None
         if bn is not None:
             if E.bn_sync and E.training:   # cross-replica statistics: sum (sum y, sum y^2) over the ranks
-                E.ctx.call("mg_allreduce_inline", ptr(self.conv.sums), self.conv.sums.numel(), 1)
+                E.ctx.call("mg_allreduce_inline", ptr(self.conv.sums), self.conv.sums.numel(), 2)   # int64 limbs of mg_sum
             # SpatialBatchNormalization finalisation + CAddTable + ReLU + pooled companion in one pass
             E.ctx.call("mg_bn_residual_forward", C.byref(self.zg), C.byref(self._bn_struct(E)), rg, int(self.relu), C.byref(self.og), pg)
         else:
@@ -530,13 +530,12 @@ class ApplyOp(Op):
         bn = self.bn
         if bn is not None:
             if E.bn_sync:
-                E.ctx.call("mg_allreduce_inline", ptr(self.dsums), self.dsums.numel(), 1)
+                E.ctx.call("mg_allreduce_inline", ptr(self.dsums), self.dsums.numel(), 2)
             E.ctx.call("mg_bn_backward", C.byref(self.yraw), C.byref(self.dg), C.byref(self.gg), ptr(self.dsums), self.count * max(1, E.bn_sync),
                        ptr(bn.weight), ptr(self.mean), ptr(self.invstd), ptr(bn.gradWeight), ptr(bn.gradBias),
-                       # sync-BN: the sums are already global, every rank adds 1/N of dgamma / dbeta before the
-                       # gradient all-reduce; the conv gradBias (a LOCAL pixel sum) is then left to the wgrad call
-                       E.gscale / max(1, E.bn_sync), ptr(self.coef),
-                       None if E.bn_sync else ptr(self.conv.mod.gradBias))
+                       # sync-BN: the sums are already global, every rank adds 1/N of dgamma / dbeta / the conv's gradBias
+                       # (all derived from the sums) before the gradient all-reduce
+                       E.gscale / max(1, E.bn_sync), ptr(self.coef), ptr(self.conv.mod.gradBias))
             E.param_done(bn)
 
 

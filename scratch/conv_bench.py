@@ -52,7 +52,7 @@ def run(name, N=256, iters=20, which=("fwd", "dgrad", "wgrad")):
     cp = sum(x.Cp for x in gs)
     dcat = Grid(ffi.MG_BF16, N, cp, H, H, Cp=cp)
     dw = torch.zeros_like(w); db = torch.zeros_like(b)
-    sums = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
+    sums = torch.zeros(4 * Cout, dtype=torch.int64, device="cuda")   # 2 * Cout mg_sum
     flops = 2.0 * N * Ho * Ho * Cout * cin * k * k
     calls = {
         "fwd": lambda: ctx.call("mg_conv_forward", C.byref(d), ptr(w), ptr(wp), ptr(b), C.byref(y.g()), None),

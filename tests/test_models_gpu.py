@@ -6,8 +6,10 @@ fp32 mode: rel 1e-4 against the fp64 oracle.  bf16 mode: rel 2e-2 (BASELINE.json
 against the fp64 oracle with the product's bf16 *storage points* emulated (util.emulate_bf16_storage):
 a ReLU mask or arg-max decided on a value that bf16 rounding moved across zero flips a whole
 gradient element, which no tolerance on accumulated error can absorb, so both sides must round
-where the product stores.  Whole-network parameter gradients pass through BatchNorm layers that
-normalise over as few as N samples (1x1 grids) and are allowed 10x the unit tolerance in fp32.
+where the product stores.  Every kernel reduction is deterministic (integer mg_sum accumulation, fixed-order
+partial sums), so the measured errors below are properties of the arithmetic, not of a run: whole-network fp32
+gradients are held to 1e-4 (nets whose pyramids end in 1x1 grids: see FP32_GRAD_BAR), bf16 gradients to 1.1x what
+bf16 storage alone costs the fp64 oracle on the same network, two runs / two schedules to bit equality.
 """
 import math
 import numpy as np
@@ -30,6 +32,22 @@ def _param_grads(olist, plist):
     og = np.concatenate([np.concatenate([m.weight.grad.numpy().ravel(), m.bias.grad.numpy().ravel()]) for m in olist])
     pg = np.concatenate([np.concatenate([m.gradWeight.cpu().numpy().ravel(), m.gradBias.cpu().numpy().ravel()]) for m in plist])
     return og, pg
+
+
+def _storage_only_error(om, olist, loss_fn, extra_hooks=None, kinds=(torch.nn.Conv2d, torch.nn.BatchNorm2d, torch.nn.Linear)):
+    """how far bf16 *storage alone* moves the parameter gradients of a network: the same fp64 oracle with the product's
+    storage points rounded to bf16 (util.emulate_bf16_storage) against the unrounded one (weight gradients, module order)"""
+    import copy
+    om16 = emulate_bf16_storage(copy.deepcopy(om))
+    if extra_hooks is not None:
+        extra_hooks(om16)
+    for m in om16.modules():
+        for p_ in m.parameters(recurse=False):
+            p_.grad = None
+    loss_fn(om16).backward()
+    o16 = [m for m in om16.modules() if isinstance(m, kinds)]
+    z = lambda m: (m.weight.grad if m.weight.grad is not None else torch.zeros_like(m.weight)).numpy().ravel()
+    return rel_err(np.concatenate([z(m) for m in o16]), np.concatenate([z(m) for m in olist]))
 
 
 def _is_affine(m):
@@ -97,7 +115,17 @@ NETS = [
      lambda: OB.ilsvrc_rnmg(18, 10, [16, 8, 8], R10_BLOCKS, [1, 1, 1, 1], 2),
      B.ilsvrc_rnmg, dict(nClass=10, inputBlock=[16, 8, 8], cfg=[1, 1, 1, 1], avg=2, blocks=R10_BLOCKS),
      (8, 3, 64, 64), 10, 10),
+    # the BASELINE.json configs themselves
+    ("R-MG-34 ilsvrc/rnmg depth 34 224x224 (config 4)", lambda: OB.ilsvrc_rnmg(34), B.ilsvrc_rnmg, dict(depth=34), (2, 3, 224, 224), 1000, 34),
+    ("PR-NMG-30 cifar/prnmg nLayer=2 wide (config 3)", lambda: OB.cifar_prnmg(2), B.cifar_prnmg, dict(nLayer=2), (8, 3, 32, 32), 100, 30),
 ]
+# fp32 bar on the whole-network parameter gradient (north-star: rel 1e-4).  The three CIFAR nets whose pyramids end in 1x1 grids
+# normalise there over as few as `batch` values; an activation within fp32 rounding of zero then has its ReLU mask decided
+# differently in fp32 and in the fp64 oracle, and BatchNorm's division by a tiny variance spreads that flip over the layer --
+# measured 8e-3 / 1.4e-3 with the deterministic kernels (no run-to-run spread left), every other network agrees to <= 3e-6.
+# R-MG-34 at batch 2 normalises its 7x7 grids over 98 values: 2.5e-3 measured (worst layer, the last 512 -> 512 conv, 8e-3).
+FP32_GRAD_BAR = {"R-NMG-12 cifar/rnmg nLayer=1": 2e-2, "PR-NMG-16 cifar/prnmg nLayer=1 narrow": 5e-3,
+                 "PR-NMG-30 cifar/prnmg nLayer=2 wide (config 3)": 2e-2, "R-MG-34 ilsvrc/rnmg depth 34 224x224 (config 4)": 1e-2}
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -151,13 +179,17 @@ def test_network_forward_backward(precision, case):
     og, pg = np.concatenate(og), np.concatenate(pg)
     worst = max(((rel_err(p.gradWeight.cpu().numpy(), o.weight.grad.numpy()), i, p.typename, tuple(p.weight.shape))
                  for i, (o, p) in enumerate(zip(olist, plist))), key=lambda e: (e[0] != e[0], e[0]))
-    # Whole-network gradients check the WIRING (a routing or shortcut bug is an O(1) error); the 1e-4 /
-    # 2e-2 arithmetic bars are held per kernel (test_kernels_gpu.py) and per residual unit (above).
-    # With ~10^6 activations a handful sit within rounding of zero, their ReLU mask flips between any two
-    # summation orders, and BatchNorm over as few as N samples (1x1 grids) amplifies it: fp32 gets 2e-2.
-    # bf16: as close to the fp64 oracle as bf16 storage allows -- within 1.5x of what rounding the
-    # oracle at the same storage points costs on this very network (measured above), floor 2e-2.
-    gtol = 2e-2 if precision == "fp32" else max(tol, 1.5 * e_storage)
+    # bf16: as close to the fp64 oracle as bf16 storage allows -- the same fp64 oracle rounded at the product's storage points
+    # is `e_storage` away from the unrounded one on this very network; the product must not add more than 10 % to that
+    gtol = FP32_GRAD_BAR.get(name, 1e-4) if precision == "fp32" else max(tol, 1.1 * e_storage)
+    print(f"[measured] {name} {precision}: log-prob {e:.2e}, gradient {rel_err(pg, og):.2e} (storage-only {e_storage:.2e}), worst layer {worst[0]:.2e} {worst[2]}{worst[3]}")
+    if precision == "bf16":
+        g16c = np.concatenate(g16)
+        per = []
+        off = 0
+        for a in g16:
+            per.append(rel_err(pg[off:off + a.size], a)); off += a.size
+        print(f"[measured] {name} bf16 vs the bf16-storage oracle: gradient {rel_err(pg, g16c):.2e}, worst tensor {max(per):.2e}, median {sorted(per)[len(per) // 2]:.2e}")
     assert rel_err(pg, og) <= gtol, ("parameter gradients", rel_err(pg, og), "storage-only", e_storage, worst)
     # running statistics were updated like nn.SpatialBatchNormalization does (momentum 0.1, unbiased var)
     obn = [m for m in olist if _is_affine(m)][0]
@@ -172,15 +204,16 @@ def test_network_forward_backward(precision, case):
     assert e <= tol, ("evaluate()", e)
 
 
-def test_mnist_prnmg_dense_prediction():
-    """models/mnist-cluttered/prnmg.mnist.lua: shrinking pyramid (isDrop), 1x1 conv+BN shortcuts,
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_mnist_prnmg_dense_prediction(precision):
+    """models/mnist-cluttered/prnmg.mnist.lua (BASELINE config 5): shrinking pyramid (isDrop), 1x1 conv+BN shortcuts,
     last unit without ReLU (isOut), Sigmoid + BCECriterion"""
     torch.manual_seed(4)
     rng = np.random.default_rng(6)
     om = OB.mnist_prnmg(1, 1).double()
     pm = B.mnist_prnmg.createModel(B.Opt(nLayer=1, nGPU=1, dataset="mnist-spt"))
-    pm.precision = "fp32"
-    olist, plist = copy_params_from_oracle(om, pm)
+    pm.precision = precision
+    olist, plist = copy_params_from_oracle(om, pm, bf16_weights=precision == "bf16")
     pm.cuda()
     plist = [m for m in pm.listModules() if m.own_parameters()]
     x = bf16_round(rng.standard_normal((2, 1, 64, 64)))
@@ -188,17 +221,21 @@ def test_mnist_prnmg_dense_prediction():
     op = om(_t(x))
     oloss = torch.nn.functional.binary_cross_entropy(op, _t(t))
     oloss.backward()
+    e_storage = _storage_only_error(om, olist, lambda m: torch.nn.functional.binary_cross_entropy(m(_t(x)), _t(t))) if precision == "bf16" else 0.0
     crit = B.mnist_prnmg.createCriterion()
     out, err = B.mnist_prnmg.ftrain(_t(x).float().cuda(), _t(t).float().cuda(), pm, crit)
     torch.cuda.synchronize()
+    tol = TOL[precision]
     e = rel_err(out.cpu().numpy(), op.detach().numpy())
-    assert e <= 1e-4, e
-    assert abs(float(err) - oloss.item()) <= 1e-4
+    assert e <= tol, e
+    assert abs(float(err) - oloss.item()) <= tol
     # grids dropped by the final SelectTable(1) leave some oracle parameters without gradient (None = 0)
     og = np.concatenate([(o.weight.grad if o.weight.grad is not None else torch.zeros_like(o.weight)).numpy().ravel() for o in olist])
     pg = np.concatenate([p.gradWeight.cpu().numpy().ravel() for p in plist])
-    # run-to-run spread of this gradient is ~1e-3 by itself (atomics order -> ReLU / arg-max flips; scratch/nondet.py)
-    assert rel_err(pg, og) <= 5e-3, rel_err(pg, og)
+    print(f"[measured] prnmg.mnist {precision}: probabilities {e:.2e}, gradient {rel_err(pg, og):.2e} (storage-only {e_storage:.2e})")
+    # fp32: 7e-4 measured (deterministic); ReLU masks of the 8x8 .. 64x64 grids decided within fp32 rounding of zero differ from
+    # the fp64 oracle's.  bf16: within 10 % of what bf16 storage alone costs the oracle on this network
+    assert rel_err(pg, og) <= (3e-3 if precision == "fp32" else max(tol, 1.1 * e_storage)), rel_err(pg, og)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -220,11 +257,6 @@ def test_mnist_unmg_concat_unet(precision):
             if precision == "bf16" and not isinstance(o, torch.nn.BatchNorm2d):
                 o.weight.copy_(o.weight.to(torch.bfloat16).to(o.weight.dtype))
             p.weight.copy_(o.weight); p.bias.copy_(o.bias)
-    if precision == "bf16":
-        emulate_bf16_storage(om)
-        for m in om.modules():
-            if isinstance(m, torch.nn.ConvTranspose2d):
-                m.register_forward_hook(lambda _m, _i, o: o.to(torch.bfloat16).to(o.dtype))
     pm.cuda()
     plist = [m for m in pm.listModules() if m.own_parameters()]
     x = bf16_round(rng.standard_normal((4, 1, 64, 64)))
@@ -232,6 +264,14 @@ def test_mnist_unmg_concat_unet(precision):
     op = om(_t(x))
     oloss = torch.nn.functional.binary_cross_entropy(op, _t(t))
     oloss.backward()
+    e_storage = 0.0
+    if precision == "bf16":
+        def extra(m16):
+            for m in m16.modules():
+                if isinstance(m, torch.nn.ConvTranspose2d):
+                    m.register_forward_hook(lambda _m, _i, o: o.to(torch.bfloat16).to(o.dtype))
+        e_storage = _storage_only_error(om, olist, lambda m: torch.nn.functional.binary_cross_entropy(m(_t(x)), _t(t)), extra,
+                                        kinds=(torch.nn.Conv2d, torch.nn.ConvTranspose2d, torch.nn.BatchNorm2d))
     crit = B.mnist_unmg.createCriterion()
     out, err = B.mnist_unmg.ftrain(_t(x).float().cuda(), _t(t).float().cuda(), pm, crit)
     torch.cuda.synchronize()
@@ -242,7 +282,8 @@ def test_mnist_unmg_concat_unet(precision):
     og = np.concatenate([(o.weight.grad if o.weight.grad is not None else torch.zeros_like(o.weight)).numpy().ravel() for o in olist])
     pg = np.concatenate([p.gradWeight.cpu().numpy().ravel() for p in plist])
     e = rel_err(pg, og)
-    assert e <= (2e-2 if precision == "fp32" else 0.3), ("parameter gradients", e)   # wiring check, see module docstring
+    print(f"[measured] unmg {precision}: gradient {e:.2e} (storage-only {e_storage:.2e})")
+    assert e <= (5e-3 if precision == "fp32" else max(tol, 1.1 * e_storage)), ("parameter gradients", e)
     assert pm._engine.ctx.launches() > 0
 
 
@@ -286,6 +327,32 @@ def test_no_cpu_fallback():
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_training_step_is_bit_reproducible(precision):
+    """two runs of the same training step (R-MG-10 at 64x64: halo, persistent, generic and stem kernels, 3 lanes, autotuned
+    kernel variants) give bit-identical log-probabilities, loss and flat gradient: no reduction depends on arrival order"""
+    res = []
+    for run in range(2):
+        torch.manual_seed(7)
+        net = B.load_net("ilsvrc/rnmg")
+        pm = net.createModel(B.Opt(nGPU=1, nClass=10, inputBlock=[16, 8, 8], cfg=[1, 1, 1, 1], avg=2, blocks=R10_BLOCKS))
+        pm.precision = precision
+        pm.cuda()
+        params, grads = pm.getParameters()
+        crit = net.createCriterion()
+        g = torch.Generator(device="cpu").manual_seed(3)
+        x = torch.randn(8, 3, 64, 64, generator=g).cuda()
+        t = torch.randint(1, 11, (8,), generator=g).cuda()
+        for _ in range(2):      # second step: gradient accumulation buffers re-zeroed, autotuned plan in place
+            pm.zeroGradParameters()
+            out, err = net.ftrain(x, t, pm, crit)
+        torch.cuda.synchronize()
+        res.append((out.clone(), float(err), grads.clone()))
+    assert res[0][1] == res[1][1]
+    assert torch.equal(res[0][0], res[1][0])
+    assert torch.equal(res[0][2], res[1][2]), float((res[0][2] - res[1][2]).abs().max())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_lane_schedule_equals_serial_plan(precision, monkeypatch):
     """the multi-stream lane schedule (mgconv/sched.py) must compute what the serial plan computes: one training step of
     R-MG (cifar/rnmg) with 3 lanes + background wgrad lane vs MGCONV_LANES=1, same weights and batch"""
@@ -316,14 +383,8 @@ def test_lane_schedule_equals_serial_plan(precision, monkeypatch):
         outs[lanes] = (out.clone(), float(err), grads.clone())
     o1, e1, g1 = outs["1"]
     o3, e3, g3 = outs["3"]
-    # identical kernels on identical data; only the order of floating-point atomics (BatchNorm sums, split-K) may differ.  That
-    # order already varies between two runs of the SERIAL plan (outputs to ~2e-5, and the gradient jumps between discrete values
-    # ~2e-3 apart in fp32 / ~2e-2 in bf16 when a ReLU mask or arg-max decided within that noise flips: scratch/nondet.py,
-    # also under CUDA_LAUNCH_BLOCKING=1), so the bars are that spread, not bit equality.
-    # measured run-to-run spread of the SERIAL plan on this setup (12 runs, scratch/nondet.py): fp32 outputs 2e-5 (abs),
-    # gradient up to 4e-4; bf16 outputs up to 6e-2 (abs, log-probabilities ~4.6) and gradient up to 5e-2 -- bimodal, when the
-    # float cast of a BatchNorm scale lands on the other side of a rounding boundary and bf16 activations re-round
-    tol = 1e-4 if precision == "fp32" else 5e-2
-    assert abs(e1 - e3) <= tol * max(1.0, abs(e1))
-    assert rel_err(o3.cpu().numpy(), o1.cpu().numpy()) <= tol
-    assert rel_err(g3.cpu().numpy(), g1.cpu().numpy()) <= (1e-2 if precision == "fp32" else 0.15)
+    # identical kernels on identical data, and every cross-CTA reduction (BatchNorm sums, split weight gradients, loss) is
+    # order independent (integer mg_sum accumulation / fixed-order partial sums): the two schedules agree BIT FOR BIT
+    assert e1 == e3, (e1, e3)
+    assert torch.equal(o3, o1), float((o3 - o1).abs().max())
+    assert torch.equal(g3, g1), float((g3 - g1).abs().max())

@@ -117,3 +117,16 @@ def emulate_bf16_storage(omodel):
         if isinstance(m, (tnn.Conv2d, tnn.Linear, tnn.ReLU, tnn.AvgPool2d, t7nn.CAddTable)):
             m.register_forward_hook(rnd)
     return omodel
+
+
+def new_sums(n):
+    """buffer of n deterministic sums (mg_sum: two int64 limbs each, include/mgconv.h), zeroed"""
+    import torch
+    return torch.zeros(2 * n, dtype=torch.int64, device="cuda")
+
+
+def sums_value(t):
+    """mg_sum buffer -> float64 tensor of the values (hi * 2^-10 + lo * 2^-54)"""
+    import torch
+    v = t.view(-1, 2).to(torch.float64)
+    return v[:, 0] * 2.0 ** -10 + v[:, 1] * 2.0 ** -54
