@@ -60,7 +60,24 @@ static inline int mg_tensor_map(mg_ctx* ctx, const void* ptr, int N, int H, int 
   CUtensorMap tm;
   CUresult r;
   const cuuint64_t row = (cuuint64_t)Cp * 2;
-  if (kind == 0) {
+  if (kind == 3) {
+    // output tile of the stem kernel: 16 rows x 8 pixels x 64 channels, 128-byte swizzle (TMA store; clipped at the image edge)
+    cuuint64_t dims[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {row, row * W, row * W * H};
+    cuuint32_t box[4] = {64, 8, 16, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else if (kind == 2) {
+    // stem (7x7 stride 2): the input patch of a 16 x 8 output tile, box_w columns x 37 rows of 8 channels (16 bytes), no swizzle
+    cuuint64_t dims[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {row, row * W, row * W * H};
+    cuuint32_t box[4] = {8, (cuuint32_t)box_w, 37, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    MG_REQUIRE(ctx, Cp == 8, MG_ERR_INVALID_ARG, "tensor map: stem planes need Cp = 8, not %d", Cp);
+    r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else if (kind == 0) {
     cuuint64_t dims[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {row, row * W, row * W * H};
     cuuint32_t box[4] = {64, (cuuint32_t)box_w, 1, 1};
@@ -97,6 +114,14 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm,
                "l"(tm), "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                : "memory");
 }
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // floor(a / b) for b > 0 and any a
 __device__ __forceinline__ int floordiv(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }

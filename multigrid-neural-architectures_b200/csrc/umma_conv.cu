@@ -790,6 +790,266 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
   }
 }
 
+
+// ---------------------------------------------------------------- stem kernel ----------------
+// cudnn.SpatialConvolution(3, C, 7,7, 2,2, 3,3) on the image pyramid (models/ilsvrc/rnmg.lua:180): 2.3 % of the MACs of R-MG-34
+// but, as an im2col gather of 49 taps x 16 bytes per output pixel, 0.8 ms of the step on the generic kernel.  Here nothing is
+// gathered at all.  A tile is 16 x 8 output pixels; the copy engine loads its input patch (37 rows x 21 pixels x 8 channels,
+// out-of-bounds = the conv's zero padding) and four warps split it into two PARITY PLANES (even / odd input columns),
+// 37 rows x 11 pixels each.  (Loading the planes directly with elementStrides = 2 works -- first version of this kernel -- but
+// the copy engine then fetches 16 bytes per request and becomes the bottleneck: 2 600 cycles per tile against 900 of MMAs.)  In a plane the 8 output pixels of a tile row read, for a given tap column, 8 CONSECUTIVE 16-byte pixels
+// -- exactly one UMMA core matrix (8 rows x 16 bytes) of a K-major no-swizzle operand -- and the next tile row is two plane rows
+// further (SBO); taps kx = 2q and 2q+1 sit at the same offset of the even and the odd plane (LBO).  So im2col is 28 shared-
+// memory descriptors per tile (7 kernel rows x 4 column pairs, K = 16 = two taps x 8 channels), and the tensor core reads the
+// patch in place.  Weights (7 stages of [Cout][64 K]) stay resident; the CTA is persistent over tiles with a ring of patches
+// and two TMEM accumulators; the epilogue (bias, bf16 store, BatchNorm sums) is the persistent halo kernel's.
+constexpr int ST_PC = 11, ST_PR = 37;                    // plane columns / rows
+constexpr int ST_ROW = ST_PC * 16;                       // 176 bytes per plane row
+constexpr int ST_PLANE = 6592;                           // plane stride (>= 37 * 176 = 6512; = 64 mod 128: the two K halves of an MMA row group sit in different banks)
+constexpr int ST_SLOT = 13312;                           // two planes, multiple of 256
+constexpr int ST_MAX_RING = 6;
+constexpr int ST_RAW_COLS = 21;                          // input columns of a tile's patch (2 * 8 + 5)
+constexpr int ST_RAW = 12544;                            // raw patch 37 x 21 x 16 bytes = 12432, rounded up to 128
+constexpr int ST_THREADS = 480;                          // 2 x 4 epilogue warps (one group per TMEM accumulator), TMA, weights, MMA, 4 de-interleave warps
+
+struct StemParams {
+  CUtensorMap tmap;          // kind 2 map of the input image grid (Cp = 8): patch boxes
+  CUtensorMap tmap_y;        // kind 3 map of the output grid (TMA store of 16 x 8 x 64-channel tiles), used when tma_out
+  int tma_out;               // n_tile == 64 == y pitch: the epilogue stages the tile in shared memory and the copy engine stores it
+  int H, W, Ho, Wo, Nimg;
+  int tiles_x, tiles_y, n_tiles_total;
+  int n_tile;                // UMMA N (Cout rounded up to 16)
+  int ring;
+  const uint8_t* wpack;      // [7][n_tile][128 B]
+  const float* bias; int c_bias;
+  __nv_bfloat16* y; int y_pitch, c_valid;
+  mg_sum* stats; int c_stats;
+  int tmem_cols;
+};
+
+__device__ __forceinline__ uint64_t smem_desc_k_none(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+__global__ void __launch_bounds__(ST_THREADS, 1) umma_stem_kernel(const __grid_constant__ StemParams p) {
+  pdl_launch();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t b_full, r_full[ST_MAX_RING], r_empty[ST_MAX_RING], a_full[ST_MAX_RING], a_empty[ST_MAX_RING], tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NA = p.ring;
+  const int b_stage_bytes = p.n_tile * 128;
+  uint8_t* b_smem = smem;                                           // 7 weight stages, resident
+  uint8_t* a_smem = smem + 7 * b_stage_bytes;                       // ring of plane pairs (what the tensor core reads)
+  uint8_t* r_smem = a_smem + (size_t)NA * ST_SLOT;                  // ring of raw patches (what the copy engine writes)
+  uint8_t* o_smem = r_smem + (size_t)NA * ST_RAW;                   // two output staging tiles (128 rows x 128 bytes, swizzled), when tma_out
+  long long* s_part = reinterpret_cast<long long*>(o_smem + (p.tma_out ? 2 * 16384 : 0));   // [8 warps][2][n_tile][hi, lo]
+  float* s_bias = reinterpret_cast<float*>(s_part + 32 * p.n_tile);
+  const int n_my = (p.n_tiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  for (int c = tid; c < 32 * p.n_tile; c += ST_THREADS) s_part[c] = 0;
+  if (tid == 0) {
+    mbar_init(&b_full, 1);
+    for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); mbar_init(&r_full[s], 1); mbar_init(&r_empty[s], 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 10) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 8 && lane == 0) tma_prefetch_desc(&p.tmap);
+  // column 10 of every odd plane belongs to the non-existent tap kx = 7 (zero weights): it is never written, so it must hold
+  // finite values -- zero it once
+  for (int i = tid; i < NA * ST_PR; i += ST_THREADS) {
+    const int sl = i / ST_PR, r = i - sl * ST_PR;
+    *reinterpret_cast<uint4*>(a_smem + (size_t)sl * ST_SLOT + ST_PLANE + r * ST_ROW + 10 * 16) = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async();
+  pdl_wait();
+  for (int c = tid; c < p.n_tile; c += ST_THREADS) s_bias[c] = (p.bias && c < p.c_bias) ? p.bias[c] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp < 8) {
+    // ================= epilogue: warps 0-3 drain accumulator 0 (even tiles), warps 4-7 accumulator 1 (odd tiles) =================
+    // (the tile's MMAs take ~900 cycles; one group of four warps needs longer than that for TMEM -> bf16 rows + BatchNorm sums)
+    const bool want_stats = p.stats != nullptr;
+    const int grp = warp >> 2, qw = warp & 3;
+    uint8_t* stage = o_smem + grp * 16384;
+    for (int it = grp; it < n_my; it += 2) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int n = tile / tiles_per_img, tr = tile - n * tiles_per_img;
+      const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
+      const int acc = it & 1;
+      const int row = qw * 32 + lane;                      // TMEM lane = tile row (row >> 3), tile column (row & 7)
+      const int oy = ty * 16 + (row >> 3), ox = tx * 8 + (row & 7);
+      const bool row_ok = oy < p.Ho && ox < p.Wo;
+      mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      if (p.tma_out) {   // the previous tile's store has read the staging buffer
+        if (qw == 0 && lane == 0) tma_store_wait_read();
+        if (grp == 0) asm volatile("bar.sync 4, 128;" ::: "memory"); else asm volatile("bar.sync 5, 128;" ::: "memory");
+      }
+      __nv_bfloat16* yrow = p.y + ((size_t)((size_t)n * p.Ho + (row_ok ? oy : 0)) * p.Wo + (row_ok ? ox : 0)) * p.y_pitch;
+      const uint32_t tcol = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)(acc * p.n_tile);
+      // two TMEM loads in flight per wait (the loop is latency bound: load -> wait -> convert -> store)
+      for (int c00 = 0; c00 < p.n_tile; c00 += 32) {
+        uint32_t a32[2][16];
+        const bool two = c00 + 16 < p.n_tile;
+        tc_ld16(tcol + (uint32_t)c00, a32[0]);
+        if (two) tc_ld16(tcol + (uint32_t)(c00 + 16), a32[1]);
+        tc_wait_ld();
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (u == 1 && !two) break;
+          const int c0 = c00 + u * 16;
+          uint32_t pk[2][4];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int n0 = c0 + h * 8;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a = __uint_as_float(a32[u][h * 8 + 2 * e]) + s_bias[c0 + h * 8 + 2 * e];
+              const float b = __uint_as_float(a32[u][h * 8 + 2 * e + 1]) + s_bias[c0 + h * 8 + 2 * e + 1];
+              __nv_bfloat162 t2 = __floats2bfloat162_rn(a, b);
+              pk[h][e] = *reinterpret_cast<uint32_t*>(&t2);
+            }
+            if (p.tma_out) {   // 16-byte chunk n0 / 8 of row `row`, 128-byte swizzle: conflict-free, un-swizzled by the TMA store
+              *reinterpret_cast<uint4*>(stage + row * 128 + ((((n0 >> 3) ^ (row & 7))) << 4)) = make_uint4(pk[h][0], pk[h][1], pk[h][2], pk[h][3]);
+            } else if (row_ok && n0 + 8 <= p.c_valid) {
+              *reinterpret_cast<uint4*>(yrow + n0) = make_uint4(pk[h][0], pk[h][1], pk[h][2], pk[h][3]);
+            }
+          }
+          if (want_stats) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const bool use = row_ok && c0 + h * 8 + 8 <= p.c_valid;
+              float sv[16];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float ra = use ? __uint_as_float(pk[h][e] << 16) : 0.f, rb = use ? __uint_as_float(pk[h][e] & 0xFFFF0000u) : 0.f;
+                sv[2 * e] = ra; sv[2 * e + 1] = rb;
+                sv[8 + 2 * e] = ra * ra; sv[8 + 2 * e + 1] = rb * rb;
+              }
+              const float tot = warp_reduce_scatter16(sv, lane);
+              if (lane < 16) {
+                long long fh, fl;
+                mg_to_fix((double)tot, fh, fl);
+                long long* sp = s_part + (size_t)((warp * 2 + (lane >> 3)) * p.n_tile + c0 + h * 8 + (lane & 7)) * 2;
+                sp[0] += fh; sp[1] += fl;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (p.tma_out) {   // tile staged: hand it to the copy engine (rows / columns beyond the image are clipped by the tensor map)
+        fence_proxy_async();
+        if (grp == 0) asm volatile("bar.sync 4, 128;" ::: "memory"); else asm volatile("bar.sync 5, 128;" ::: "memory");
+        if (qw == 0 && lane == 0) {
+          tma_store_4d(&p.tmap_y, smem_u32(stage), 0, tx * 8, ty * 16, n);
+          tma_store_commit();
+        }
+      }
+    }
+    if (p.tma_out && qw == 0 && lane == 0) tma_store_wait_all();
+    if (want_stats) {
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      for (int c = tid; c < p.n_tile; c += 256)
+        if (c < p.c_stats) {
+          long long ah = 0, al = 0, bh = 0, bl = 0;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) {
+            const long long* sa = s_part + (size_t)((w * 2) * p.n_tile + c) * 2;
+            const long long* sb = s_part + (size_t)((w * 2 + 1) * p.n_tile + c) * 2;
+            ah += sa[0]; al += sa[1]; bh += sb[0]; bl += sb[1];
+          }
+          mg_sum_add_fix(p.stats + c, ah, al);
+          mg_sum_add_fix(p.stats + p.c_stats + c, bh, bl);
+        }
+    }
+  } else if (warp == 8) {
+    // ================= patch producer: one box of 37 rows x 21 pixels per tile =================
+    if (lane == 0) {
+      Ring rr(NA);
+      for (int it = 0; it < n_my; ++it, rr.next()) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int n = tile / tiles_per_img, tr = tile - n * tiles_per_img;
+        const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
+        const int s = rr.idx;
+        if (it >= NA) mbar_wait(&r_empty[s], rr.phase ^ 1u);
+        mbar_arrive_expect_tx(&r_full[s], (uint32_t)(ST_PR * ST_RAW_COLS * 16));
+        tma_load_4d(smem_u32(r_smem + (size_t)s * ST_RAW), &p.tmap, &r_full[s], 0, 2 * tx * 8 - 3, 2 * ty * 16 - 3, n);
+      }
+    }
+  } else if (warp >= 11) {
+    // ================= de-interleave: raw patch -> even / odd column planes =================
+    const int dt = tid - 11 * 32;
+    Ring rr(NA);
+    for (int it = 0; it < n_my; ++it, rr.next()) {
+      const int s = rr.idx;
+      mbar_wait(&r_full[s], rr.phase);
+      if (it >= NA) mbar_wait(&a_empty[s], rr.phase ^ 1u);      // the MMAs that read this plane slot have completed
+      const uint8_t* raw = r_smem + (size_t)s * ST_RAW;
+      uint8_t* pl = a_smem + (size_t)s * ST_SLOT;
+      for (int i = dt; i < ST_PR * ST_RAW_COLS; i += 128) {
+        const int r = i / ST_RAW_COLS, x = i - r * ST_RAW_COLS;
+        const uint4 v = *reinterpret_cast<const uint4*>(raw + (size_t)i * 16);
+        *reinterpret_cast<uint4*>(pl + (x & 1) * ST_PLANE + r * ST_ROW + (x >> 1) * 16) = v;
+      }
+      fence_proxy_async();              // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(&a_full[s]);
+      mbar_arrive(&r_empty[s]);
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&b_full, (uint32_t)(7 * b_stage_bytes));
+      for (int q = 0; q < 7; ++q) bulk_g2s(smem_u32(b_smem + (size_t)q * b_stage_bytes), p.wpack + (size_t)q * b_stage_bytes, (uint32_t)b_stage_bytes, &b_full);
+    }
+  } else {
+    // ================= MMA issuer: 7 kernel rows x 4 column pairs per tile =================
+    const bool leader = elect_one();
+    const uint32_t idesc = idesc_bf16_m128(p.n_tile);
+    const uint32_t b_base = smem_u32(b_smem);
+    Ring ra(NA);
+    mbar_wait(&b_full, 0);
+    for (int it = 0; it < n_my; ++it, ra.next()) {
+      const int acc = it & 1;
+      if (it >= 2) { mbar_wait(&tmem_empty[acc], ((it >> 1) - 1) & 1); tc_fence_after(); }
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
+      const int s = ra.idx;
+      mbar_wait(&a_full[s], ra.phase);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(a_smem + (size_t)s * ST_SLOT);
+      if (leader) {
+#pragma unroll 1
+        for (int ky = 0; ky < 7; ++ky) {
+          const uint64_t b_desc = smem_desc_k_sw128(b_base + (uint32_t)(ky * b_stage_bytes));
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint64_t a_desc = smem_desc_k_none(a_base + (uint32_t)(ky * ST_ROW + q * 16), ST_PLANE, 2 * ST_ROW);
+            tc_mma_bf16(d_tmem, a_desc, b_desc + (uint64_t)(q * 2), idesc, (uint32_t)((ky | q) != 0));
+          }
+        }
+        tc_commit(&a_empty[s]);
+        tc_commit(&tmem_full[acc]);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 10) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------- weight packing -----------
 struct PackParams {
   const float* w;   // [Cout][Ccat][k][k]
@@ -801,6 +1061,7 @@ struct PackParams {
   int kv_per_tap, nkv, n_stages, n_tile, n_tiles;
   int n_rows_valid;  // forward: Cout; transposed: CcatP (rows that may be non-zero)
   int halo;          // stage order of the halo kernels: per chunk ceil(9 / tps) stages of tps taps each
+  int stem;          // stage order of umma_stem_kernel: stage = kernel row ky, k-vector = (column pair q, parity): tap kx = 2q + parity
   int n_chunks;
   HChunk chunk[MAX_CHUNKS];
 };
@@ -820,7 +1081,11 @@ __device__ __forceinline__ void pack_one(const PackParams& p, int64_t i) {
   const int KK = p.k * p.k;
   int tap, r, sg = 0, c0 = 0;   // tap, k-vector within the tap (generic order), K segment and first channel within it
   bool kv_ok;
-  if (p.halo) {
+  if (p.stem) {
+    tap = stage * p.k + v;          // v = 2q + parity = kx (kx = 7 does not exist: zero column)
+    kv_ok = v < p.k;
+    sg = 0; c0 = 0; r = 0;
+  } else if (p.halo) {
     int c = 0;
     while (c + 1 < p.n_chunks && stage >= p.chunk[c + 1].stage0) ++c;
     const HChunk ch = p.chunk[c];
@@ -885,7 +1150,7 @@ __global__ void __launch_bounds__(256) pack_weights_batched_kernel(const PackPar
 // ---------------------------------------------------------------- host side -----------------
 struct Geometry {
   int kv_per_tap, nkv, n_stages, n_tile, n_tiles, n_rows;
-  int halo, n_chunks;
+  int halo, n_chunks, stem;
   HChunk chunk[MAX_CHUNKS];
 };
 
@@ -905,6 +1170,17 @@ static int build_chunks(const int* kcp, int nk, HChunk* out, int* n_stages) {
     }
   *n_stages = st;
   return n;
+}
+
+// the dedicated stem kernel: 7x7 / stride 2 / pad 3 on one image grid of <= 8 channels (Cp = 8), up to 256 output channels
+static bool stem_shape_ok(const mg_conv_desc* d) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("MGCONV_STEM_KERNEL"); on = e ? atoi(e) : 1; }
+  if (!on || d->ksize != 7 || d->stride != 2 || d->pad != 3 || d->n_seg != 1 || d->seg_mode[0] != MG_SEG_SAME) return false;
+  const mg_grid& g = d->seg[0];
+  if (g.Cp != 8 || g.H != d->H || g.W != d->W || d->Cout > 256) return false;
+  const int n_tile = mg_round_up(d->Cout, 16);
+  return 7 * n_tile * 128 + 2 * (ST_SLOT + ST_RAW) + n_tile * 260 + 2048 <= 232448 - 4096;
 }
 
 static void n_tiling(int n_rows_pad16, int* n_tile, int* n_tiles) {
@@ -940,6 +1216,8 @@ static Geometry geometry(const mg_conv_desc* d, int transposed) {
   g.nkv = taps * g.kv_per_tap;
   g.n_stages = (g.nkv + KV_PER_STAGE - 1) / KV_PER_STAGE;
   g.halo = 0;
+  g.stem = 0;
+  if (!transposed && stem_shape_ok(d)) { g.stem = 1; g.n_stages = 7; return g; }
   if (halo_shape_ok(d)) {
     int kcp[MG_MAX_SEG], nk, n_st = 0;
     if (!transposed) { nk = d->n_seg; for (int s = 0; s < nk; ++s) kcp[s] = d->seg[s].Cp; }
@@ -1167,7 +1445,7 @@ static PackParams make_pack_params(const mg_conv_desc* d, const float* w, void* 
   }
   p.Ccat = c;
   p.kv_per_tap = g.kv_per_tap; p.nkv = g.nkv; p.n_stages = g.n_stages; p.n_tile = g.n_tile; p.n_tiles = g.n_tiles;
-  p.n_rows_valid = g.n_rows; p.halo = g.halo;
+  p.n_rows_valid = g.n_rows; p.halo = g.halo; p.stem = g.stem;
   p.n_chunks = g.n_chunks;
   for (int i = 0; i < g.n_chunks; ++i) p.chunk[i] = g.chunk[i];
   *total = (int64_t)g.n_tiles * g.n_tile * g.n_stages * KV_PER_STAGE;
@@ -1239,6 +1517,39 @@ int umma_conv_forward(mg_ctx* ctx, const mg_conv_desc* d, const void* wpack, con
     else MG_REQUIRE(ctx, sg.H * 2 == d->H && sg.W * 2 == d->W, MG_ERR_SHAPE, "conv: UP seg %d is %dx%d, x2 != %dx%d", s, sg.H, sg.W, d->H, d->W);
     MG_REQUIRE(ctx, sg.N == d->seg[0].N, MG_ERR_SHAPE, "conv: seg %d batch", s);
     up[s] = m == MG_SEG_UP ? 1 : 0;
+  }
+  if (g.stem) {
+    StemParams sp;
+    memset(&sp, 0, sizeof(sp));
+    int rc = mg_tensor_map(ctx, d->seg[0].data, y->N, d->H, d->W, 8, 2, ST_RAW_COLS, &sp.tmap);
+    if (rc) return rc;
+    sp.H = d->H; sp.W = d->W; sp.Ho = y->H; sp.Wo = y->W; sp.Nimg = y->N;
+    sp.tiles_x = (y->W + 7) / 8; sp.tiles_y = (y->H + 15) / 16;
+    sp.n_tiles_total = y->N * sp.tiles_x * sp.tiles_y;
+    sp.n_tile = g.n_tile;
+    sp.wpack = (const uint8_t*)wpack; sp.bias = bias; sp.c_bias = d->Cout;
+    sp.y = (__nv_bfloat16*)y->data; sp.y_pitch = y->Cp; sp.c_valid = y->Cp;
+    // measured (B = 256, 224 x 224 -> 112 x 112 x 64): 210 us without the sums, 435 us with them fused in the epilogue (the four
+    // warps per accumulator cannot keep up with a tile every ~1 200 cycles), 210 + 110 us with the separate statistics pass
+    static int stem_fused = -1;
+    if (stem_fused < 0) { const char* e = getenv("MGCONV_STEM_FUSED_STATS"); stem_fused = e ? atoi(e) : 0; }
+    const bool fused = bn_sums && fused_stats_on() && stem_fused;
+    if (fused) { sp.stats = bn_sums; sp.c_stats = d->Cout; }
+    int cols = 32;
+    while (cols < 2 * g.n_tile) cols <<= 1;
+    sp.tmem_cols = cols;
+    sp.tma_out = (g.n_tile == 64 && y->Cp == 64) ? 1 : 0;
+    if (sp.tma_out) { rc = mg_tensor_map(ctx, y->data, y->N, y->H, y->W, y->Cp, 3, 8, &sp.tmap_y); if (rc) return rc; }
+    const int fixed = 7 * g.n_tile * 128 + g.n_tile * 260 + 1024 + (sp.tma_out ? 32768 : 0);
+    sp.ring = std::max(2, std::min(ST_MAX_RING, (SMEM_MAX - fixed) / (ST_SLOT + ST_RAW)));
+    static bool attr_set = false;
+    if (!attr_set) { MG_CUDA(ctx, cudaFuncSetAttribute(umma_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX)); attr_set = true; }
+    const int grid = std::min(sp.n_tiles_total, ctx->num_sms);
+    MG_CUDA(ctx, mg_launch_pdl(umma_stem_kernel, dim3(grid), dim3(ST_THREADS), (size_t)(fixed + sp.ring * (ST_SLOT + ST_RAW)), ctx->stream, sp));
+    MG_CHECK_LAUNCH(ctx);
+    ctx->tc_launches++;
+    if (bn_sums && !fused) return mg_bn_stats(ctx, y, bn_sums);
+    return MG_OK;
   }
   if (g.halo) {
     HParams hp;

@@ -311,6 +311,43 @@ def test_stem_conv7x7_stride2(ctx, impl):
     ctx.set_impl(ffi.MG_IMPL_AUTO)
 
 
+@pytest.mark.parametrize("case", [(3, 3, 36, 44, 64), (2, 3, 70, 30, 32), (5, 1, 17, 9, 24), (2, 3, 224, 224, 64)],
+                         ids=["cout64-tma-store", "cout32", "odd-cin1", "imagenet-size"])
+@pytest.mark.parametrize("fused", ["0", "1"], ids=["stats-pass", "stats-fused"])
+def test_stem_kernel_shapes(case, fused, monkeypatch):
+    """the dedicated 7x7 / stride-2 kernel (zero-copy im2col through UMMA descriptors over parity planes of the input patch):
+    ragged tiles in both directions, the TMA-store epilogue (Cout = 64) and the direct-store one, fused BatchNorm sums"""
+    N, Cin, H, W, Cout = case
+    monkeypatch.setenv("MGCONV_STEM_FUSED_STATS", fused)   # read once per process: the first parametrisation decides; both paths are
+    ctx = ffi.Context(0, torch.cuda.current_stream().cuda_stream, ffi.MG_BF16)   # also exercised through MGCONV_STEM_FUSED_STATS=1 runs
+    x = rnd(N, Cin, H, W)
+    w = bf16_round(rng.standard_normal((Cout, Cin, 7, 7)) * 0.1)
+    b = bf16_round(rng.standard_normal(Cout) * 0.1)
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    gx = Grid(ffi.MG_BF16, N, Cin, H, W, x)
+    d = conv_desc([gx], [MG_SEG_SAME], 7, 2, 3, Cout, H, W)
+    wd, bd = dev(w), dev(b)
+    wp = torch.zeros(ffi.lib.mg_conv_packed_bytes(C.byref(d), 0), dtype=torch.uint8, device="cuda")
+    ctx.call("mg_conv_pack_weights", C.byref(d), ptr(wd), ptr(wp), 0)
+    gy = Grid(ffi.MG_BF16, N, Cout, Ho, Wo)
+    sums = new_sums(2 * Cout)
+    tc0 = ctx.tc_launches()
+    ctx.call("mg_conv_forward", C.byref(d), ptr(wd), ptr(wp), ptr(bd), C.byref(gy.g()), ptr(sums))
+    assert ctx.tc_launches() - tc0 == 1
+    torch.cuda.synchronize()
+    xin = torch.from_numpy(bf16_round(x)).cuda().float()
+    y_ref = torch.nn.functional.conv2d(xin.double(), torch.from_numpy(w).cuda().double(), torch.from_numpy(b).cuda().double(), 2, 3)
+    yn = gy.t[..., :Cout].double().permute(0, 3, 1, 2)
+    assert float((yn - y_ref).abs().max() / y_ref.abs().max()) <= TOL[ffi.MG_BF16]
+    assert not gy.pad_channels().any()
+    sv = sums_value(sums)
+    assert torch.allclose(sv[:Cout], yn.sum((0, 2, 3)), rtol=1e-5, atol=1e-2)
+    assert torch.allclose(sv[Cout:], (yn * yn).sum((0, 2, 3)), rtol=1e-5, atol=1e-2)
+    if N * H * W < 20000:   # small cases also against the numpy oracle
+        assert max_rel(gy.nchw(), O.conv_forward(bf16_round(x), w, b, 2, 3)) <= TOL[ffi.MG_BF16]
+    ctx.close()
+
+
 @pytest.mark.parametrize("shape", [(2, 3, 20, 20, 16, 7, 2, 3), (3, 3, 15, 23, 40, 7, 2, 3), (2, 1, 9, 9, 8, 3, 2, 1)])
 def test_stem_im2col_then_1x1_conv_equals_strided_conv(shape):
     """mg_im2col + a 1x1 mg_conv over the column tensor, with the [Cout][Cin][k][k] weight storage reinterpreted as
@@ -505,6 +542,37 @@ def test_full_size_conv_is_linear_and_its_gradients_are_its_adjoints(shape):
     rhs = float((dw.double() * w.double()).sum())
     scale = float(gg.t[..., :Cout].double().norm() * yf.norm())     # Cauchy-Schwarz bound of the inner products
     assert abs(lhs - mid) <= 2e-3 * scale and abs(lhs - rhs) <= 2e-3 * scale, (lhs, mid, rhs, scale)
+    # VALUES at the full batch against an independent fp32 computation of the same layer (PyTorch / cuDNN, TF32 off) on the
+    # same bf16-representable operands: forward, dgrad and wgrad of all 256 images ...
+    tf32 = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        xin = torch.cat(parts, dim=3).permute(0, 3, 1, 2).contiguous()          # gathered input, NCHW fp32
+        gn = gg.t[..., :Cout].float().permute(0, 3, 1, 2).contiguous()
+        y_ref = torch.nn.functional.conv2d(xin, w, None, 1, 1)
+        dx_ref = torch.nn.grad.conv2d_input(xin.shape, w, gn, stride=1, padding=1)
+        dw_ref = torch.nn.grad.conv2d_weight(xin, w.shape, gn, stride=1, padding=1)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    tol = TOL[ffi.MG_BF16]
+    yn = y.t[..., :Cout].float().permute(0, 3, 1, 2)
+    assert float((yn - y_ref).abs().max() / y_ref.abs().max()) <= tol
+    assert float((yn - y_ref).norm() / y_ref.norm()) <= 4e-3          # bf16 rounding of the stored output: 2^-9 per element
+    off = lo = 0
+    for g_ in grids:
+        dseg = dcat.t[..., off:off + g_.C].float().permute(0, 3, 1, 2)
+        ref = dx_ref[:, lo:lo + g_.C]
+        assert float((dseg - ref).abs().max() / dx_ref.abs().max()) <= tol
+        assert float((dseg - ref).norm() / ref.norm()) <= 4e-3
+        off += g_.Cp; lo += g_.C
+    assert float((dw - dw_ref).abs().max() / dw_ref.abs().max()) <= tol
+    assert float((dw - dw_ref).norm() / dw_ref.norm()) <= 1e-3        # fp32 accumulation over 256 images, fp32 result
+    # ... and the first and last image of the batch against the numpy fp64 oracle (the check that anchors the comparison above)
+    sel = [0, N - 1]
+    xs_np = xin[sel].double().cpu().numpy()
+    yo = O.conv_forward(xs_np, w.double().cpu().numpy(), np.zeros(Cout), 1, 1)
+    assert max_rel(yn[sel].double().cpu().numpy(), yo) <= tol
+    assert max_rel(y_ref[sel].double().cpu().numpy(), yo) <= 1e-5
     ctx.close()
 
 
