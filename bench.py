@@ -284,31 +284,17 @@ def main():
     # current one trains: the copy runs on a side stream into the other of two device buffers.
     e2e = None
     if not args.no_e2e:
-        copy_stream = torch.cuda.Stream(dev)
-        bufs = [(torch.empty_like(dev_x), torch.empty_like(dev_t)) for _ in range(2)]
-        ready = [torch.cuda.Event(), torch.cuda.Event()]
-        consumed = [torch.cuda.Event(), torch.cuda.Event()]
-
-        def stage(i):
-            b = i & 1
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(consumed[b])          # the step that last read this buffer is done
-                bufs[b][0].copy_(host_x, non_blocking=True)
-                bufs[b][1].copy_(host_t, non_blocking=True)
-                ready[b].record(copy_stream)
-
+        from mgconv.utilfuncs import Put2GPU
+        stg = Put2GPU(local)                         # the package's double-buffered put2GPU (mgconv/utilfuncs.py)
         sync_all()
-        for b in range(2):
-            consumed[b].record()
         e0.record()
-        stage(0)
+        stg.stage(0, host_x, host_t)
         for i in range(args.steps):
             if i + 1 < args.steps:
-                stage(i + 1)
-            b = i & 1
-            torch.cuda.current_stream().wait_event(ready[b])
-            step(bufs[b][0], bufs[b][1])
-            consumed[b].record()
+                stg.stage(i + 1, host_x, host_t)
+            bx, bt = stg.get(i)
+            step(bx, bt)
+            stg.done(i)
             _ = float(state["loss"])                # D2H read of the step's loss
         e1.record()
         sync_all()

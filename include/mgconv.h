@@ -127,7 +127,8 @@ int mg_ctx_sync(mg_ctx* ctx);                         /* cutorch.synchronize() e
 /* kernel-selection overrides for tests and tuning (the analogue of cudnn.benchmark / cudnn.fastest,
  * models/ilsvrc/rnmg.lua:230-231); value 0 = automatic choice */
 enum { MG_TUNE_HALO_SUBTILES = 0, /* 1 / 2: 128-slot sub-tiles per CTA of the 3x3 tensor-core kernel */
-       MG_TUNE_PERSISTENT = 1     /* 1: weight-resident persistent kernel whenever the weights fit, 2: never */ };
+       MG_TUNE_PERSISTENT = 1,    /* 1: weight-resident persistent kernel whenever the weights fit, 2: never */
+       MG_TUNE_STEM_FUSED_STATS = 2 /* 1: the 7x7 stem kernel reduces the BatchNorm sums in its epilogue, 0: separate pass (default) */ };
 int mg_ctx_set_tuning(mg_ctx* ctx, int knob, int value);
 const char* mg_last_error(mg_ctx* ctx);
 int mg_version(void);
@@ -142,6 +143,15 @@ int mg_ctx_profile_read(mg_ctx* ctx, double* conv_ms, int64_t* conv_calls);
 /* ---- layout conversion at the Torch boundary (NCHW fp32 <-> grid) --------------------- */
 int mg_import_nchw(mg_ctx* ctx, const float* src, mg_grid* dst);            /* put2GPU output -> grid */
 int mg_export_nchw(mg_ctx* ctx, const mg_grid* src, float* dst);            /* applies pending affine */
+
+/* GPU side of the data hooks (dataset/cifar100-whitened/donkey.lua:57-71 random crop, 131-139 horizontal flip with
+ * probability 0.5, 19-23 of dataset/mnist-spt/donkey.lua mean / std normalisation; test hook: centre crop padded with zeros,
+ * 166-175), applied to a batch that put2GPU (utils/utilfuncs.lua:3-30) already moved to the device:
+ *   dst[n][c][y][x] = (src[n][c][y0[n]+y][x0[n] + (flip[n] ? oW-1-x : x)] - mean[c]) / std[c],   0 outside the source image.
+ * src NCHW fp32 [N][C][H][W], dst NCHW fp32 [N][C][oH][oW]; y0 / x0 / flip (int32 [N]) and mean / std (fp32 [C]) are device
+ * pointers and may be NULL (no offset / no flip / no normalisation). */
+int mg_crop_flip_normalize(mg_ctx* ctx, const float* src, int32_t N, int32_t C, int32_t H, int32_t W, float* dst, int32_t oH, int32_t oW,
+                           const int32_t* y0, const int32_t* x0, const int32_t* flip, const float* mean, const float* stdv);
 
 /* ---- forward -------------------------------------------------------------------------- */
 /* packed weight bytes for the tcgen05 path (0 when the SIMT path is used) */

@@ -189,6 +189,7 @@ int mg_ctx_set_tuning(mg_ctx* ctx, int knob, int value) {
   if (!ctx) return MG_ERR_INVALID_ARG;
   if (knob == MG_TUNE_HALO_SUBTILES) { MG_REQUIRE(ctx, value >= 0 && value <= 2, MG_ERR_INVALID_ARG, "set_tuning: sub-tiles %d", value); ctx->tune_mt = value; return MG_OK; }
   if (knob == MG_TUNE_PERSISTENT) { MG_REQUIRE(ctx, value >= 0 && value <= 2, MG_ERR_INVALID_ARG, "set_tuning: persistent %d", value); ctx->tune_persist = value; return MG_OK; }
+  if (knob == MG_TUNE_STEM_FUSED_STATS) { MG_REQUIRE(ctx, value >= 0 && value <= 1, MG_ERR_INVALID_ARG, "set_tuning: stem fused stats %d", value); ctx->tune_stem_fused = value; return MG_OK; }
   MG_FAIL(ctx, MG_ERR_INVALID_ARG, "set_tuning: unknown knob %d", knob);
 }
 int mg_ctx_sync(mg_ctx* ctx) {

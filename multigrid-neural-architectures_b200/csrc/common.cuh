@@ -44,6 +44,7 @@ struct mg_ctx {
   // kernel-selection overrides (mg_ctx_set_tuning); 0 = automatic
   int tune_mt;       // 128-slot sub-tiles per CTA of the halo convolution kernel (1 / 2)
   int tune_persist;  // weight-resident persistent kernel: 1 = whenever the weights fit, 2 = never
+  int tune_stem_fused;  // stem kernel: 1 = BatchNorm sums in its epilogue, 0 = separate statistics pass (faster, default)
   // job table of mg_conv_pack_weights_batched (device copy + the host image it was uploaded from)
   mg_sum* sum_scratch[MG_MAX_LANES];   // zeroed scratch of MG_SUM_SCRATCH deterministic sums per lane (users re-zero what they used)
   void* tmaps;         // TmapCache* (tma.cuh): CUtensorMap objects of the halo kernels, keyed by (pointer, shape)

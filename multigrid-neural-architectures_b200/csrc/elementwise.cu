@@ -351,6 +351,27 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ xraw, int x_cp, const 
   mg_st(out + i, v);
 }
 
+// ---------------------------------------------------------------- input path: crop / flip / normalise ----------
+// dst[n][c][y][x] = (src[n][c][y0[n] + y][x0[n] + (flip[n] ? oW-1-x : x)] - mean[c]) / std[c], zero where the window leaves
+// the source image (the reference's test hook pads its centre crop with zeros, dataset/cifar100-whitened/donkey.lua:172-174)
+__global__ void crop_flip_normalize_kernel(const float* __restrict__ src, int C, int H, int W, float* __restrict__ dst, int oH, int oW,
+                                           const int32_t* __restrict__ y0, const int32_t* __restrict__ x0, const int32_t* __restrict__ flip,
+                                           const float* __restrict__ mean, const float* __restrict__ stdv, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * EB + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % oW); int64_t q = i / oW;
+  const int y = (int)(q % oH); q /= oH;
+  const int c = (int)(q % C); const int n = (int)(q / C);
+  const int sx = (x0 ? x0[n] : 0) + ((flip && flip[n]) ? oW - 1 - x : x), sy = (y0 ? y0[n] : 0) + y;
+  float v = 0.f;
+  if (sx >= 0 && sx < W && sy >= 0 && sy < H) {
+    v = src[(((int64_t)n * C + c) * H + sy) * W + sx];
+    if (mean) v -= mean[c];
+    if (stdv) v /= stdv[c];
+  }
+  dst[i] = v;
+}
+
 // ---------------------------------------------------------------- criteria ----------
 // The scalar loss is accumulated as a deterministic integer sum (mg_sum scratch of the context, left zeroed) and added to the
 // caller's float by loss_finalize_kernel: the reported loss is bit-identical from run to run.
@@ -644,6 +665,15 @@ int mg_bn_backward(mg_ctx* ctx, const mg_grid* xraw, const mg_grid* d, mg_grid* 
   int64_t P = (int64_t)d->N * d->H * d->W;
   MG_DISPATCH(ctx, bn_bwd_apply_kernel<T><<<GRID1(P * out->Cp), EB, 0, ctx->stream>>>((const T*)xraw->data, xraw->Cp, (const T*)d->data, d->Cp,
                                                                                       (T*)out->data, out->Cp, d->C, P, coef_ws););
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
+int mg_crop_flip_normalize(mg_ctx* ctx, const float* src, int32_t N, int32_t C, int32_t H, int32_t W, float* dst, int32_t oH, int32_t oW,
+                           const int32_t* y0, const int32_t* x0, const int32_t* flip, const float* mean, const float* stdv) {
+  if (!ctx || !src || !dst || N < 1 || C < 1 || H < 1 || W < 1 || oH < 1 || oW < 1) return MG_ERR_INVALID_ARG;
+  const int64_t total = (int64_t)N * C * oH * oW;
+  crop_flip_normalize_kernel<<<GRID1(total), EB, 0, ctx->stream>>>(src, C, H, W, dst, oH, oW, y0, x0, flip, mean, stdv, total);
   MG_CHECK_LAUNCH(ctx);
   return MG_OK;
 }

@@ -1531,9 +1531,7 @@ int umma_conv_forward(mg_ctx* ctx, const mg_conv_desc* d, const void* wpack, con
     sp.y = (__nv_bfloat16*)y->data; sp.y_pitch = y->Cp; sp.c_valid = y->Cp;
     // measured (B = 256, 224 x 224 -> 112 x 112 x 64): 210 us without the sums, 435 us with them fused in the epilogue (the four
     // warps per accumulator cannot keep up with a tile every ~1 200 cycles), 210 + 110 us with the separate statistics pass
-    static int stem_fused = -1;
-    if (stem_fused < 0) { const char* e = getenv("MGCONV_STEM_FUSED_STATS"); stem_fused = e ? atoi(e) : 0; }
-    const bool fused = bn_sums && fused_stats_on() && stem_fused;
+    const bool fused = bn_sums && fused_stats_on() && ctx->tune_stem_fused;
     if (fused) { sp.stats = bn_sums; sp.c_stats = d->Cout; }
     int cols = 32;
     while (cols < 2 * g.n_tile) cols <<= 1;

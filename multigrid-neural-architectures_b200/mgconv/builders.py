@@ -254,8 +254,9 @@ def _classifier(nIn, nLinear, avg=None):
 
 # ------------------------------------------------------------------------------------ init (a11)
 def MSRinit(model):
-    """N(0, sqrt(2/(kW*kH*nOutputPlane))), bias 0 -- ConvInit of models/ilsvrc/rnmg.lua:288-294,
-    MSRinit of models/cifar/nmg.lua:197-210 and utils/modelfuncs.lua:3-15"""
+    """N(0, sqrt(2/(kW*kH*nOutputPlane))), bias 0 -- the builders' own fan-OUT initialiser: ConvInit of
+    models/ilsvrc/rnmg.lua:288-294, MSRinit of models/cifar/nmg.lua:197-210.  (utils/modelfuncs.lua:3-11 is a different,
+    fan-IN initialiser with an exponent argument: mgconv/modelfuncs.py:MSRinit.)"""
     for name in ("nn.SpatialConvolution", "cudnn.SpatialConvolution"):
         for v in model.findModules(name):
             n = v.kW * v.kH * v.nOutputPlane
@@ -599,6 +600,77 @@ class mnist_prnmg(BASICNET):
         return {"LR": 0.1 * 0.1 ** math.floor((currentEpoch - 1) / 30), "WD": 1e-4}
 
 
+def mgConv_pnmg_mnist(nInputPlanes, nOutputPlanes, isDrop=False, isOut=False):
+    """models/mnist-cluttered/pnmg.mnist.lua:83-121: Sequential{ ResampleConcat(nIPs, isDrop), ParallelTable{ 3x3 Conv, BN(1e-3)
+    [, ReLU] } } -- mgConv (83-102) with the ReLU, mgConvOutput (104-121) without"""
+    mg_conv = nn.Sequential()
+    resample_concat, _nIPs = ResampleConcat(nInputPlanes, isDrop)
+    mg_conv.add(resample_concat)
+    convs = nn.ParallelTable()
+    for i in range(len(_nIPs)):
+        convs.add((ConvBN if isOut else ConvBNReLU)(nn.Sequential(), _nIPs[i], nOutputPlanes[i], 3, 1e-3))
+    mg_conv.add(convs)
+    return mg_conv
+
+
+class mnist_pnmg(BASICNET):
+    """models/mnist-cluttered/pnmg.mnist.lua: the plain progressive multigrid network for dense prediction on cluttered MNIST
+    (shrinking pyramid through isDrop, last stage without ReLU, Sigmoid + BCE)"""
+    name = "mnist-cluttered/pnmg.mnist"
+
+    @classmethod
+    def createModel(cls, opt):
+        nClass = opt.nClass or (10 if opt.dataset == "mnist-seg" else 1)          # pnmg.mnist.lua:225
+        nLayer = opt.nLayer or 1
+        w = opt.widths or [64, 32, 16, 8]
+        blocks = [(list(w), False)] * 4 + [(w[:3], True), (w[:2], True), ([nClass], True)]   # 226-234
+        model = nn.Sequential()
+        nIPs = [1] * len(w)
+        for indBlock, (nOPs, isDrop) in enumerate(blocks, 1):
+            if indBlock == 1:       # MultiGridsInput, 150-196
+                model.add(mgConvInput_pyramid(nOPs, 1, 1e-3))
+                n = len(nOPs)
+                for nGrid in range(1, n + 1):
+                    for _ in range(nLayer):
+                        if nGrid > 1:
+                            mg_convs = nn.ConcatTable()
+                            for j in range(1, n - nGrid + 1):
+                                mg_convs.add(nn.SelectTable(j))
+                            _select = nn.ConcatTable()
+                            _nOPs = []
+                            for j in range(n - nGrid + 1, n + 1):
+                                _select.add(nn.SelectTable(j))
+                                _nOPs.append(nOPs[j - 1])
+                            mg_convs.add(nn.Sequential().add(_select).add(mgConv_pnmg_mnist(_nOPs, _nOPs)))
+                            model.add(mg_convs)
+                            model.add(nn.FlattenTable())
+                        else:
+                            convs = nn.ParallelTable()
+                            for _j in range(n - 1):
+                                convs.add(nn.Identity())
+                            convs.add(ConvBNReLU(nn.Sequential(), nOPs[-1], nOPs[-1], 3, 1e-3))
+                            model.add(convs)
+            else:                   # MultiGrids 198-205 / MultiGridsOutput 207-215
+                last = indBlock == len(blocks)
+                for i in range(1, nLayer + 1):
+                    model.add(mgConv_pnmg_mnist(nIPs, nOPs, isDrop if i == 1 else False, last and i == nLayer))
+                    nIPs = list(nOPs)
+            nIPs = list(nOPs)
+        model.add(nn.SelectTable(1))
+        model.add(nn.Sigmoid())
+        MSRinit(model)              # convolutions only (253-266): BN gamma keeps the Torch7 default U(0,1)
+        return _finish(model, opt, cls)
+
+    @classmethod
+    def createCriterion(cls):       # pnmg.mnist.lua:275-279
+        return nn.MultiCriterion().add(nn.BCECriterion())
+
+    @classmethod
+    def trainRule(cls, currentEpoch, opt):   # 312-319: LR decays log-linearly from 1e-1 to 1e-4 over nEpochs
+        total = max(2, int(opt.nEpochs or 30))
+        return {"LR": 10 ** -((currentEpoch - 1) * 3 / (total - 1) + 1), "WD": 5e-4}
+
+
 class mnist_unmg(BASICNET):
     """models/mnist-cluttered/unmg.lua: U-Net whose every stage is a multigrid convolution; skip connections
     are zipped by nn.ConcatUnet (layers/ConcatUnet.lua) and joined per grid by MapTable(JoinTable(2))"""
@@ -682,7 +754,7 @@ class mnist_unmg(BASICNET):
         return {"LR": 0.1 * 0.1 ** math.floor((currentEpoch - 1) / 30), "WD": 1e-4}
 
 
-NETS = {c.name: c for c in (cifar_nmg, cifar_rnmg, cifar_pnmg, cifar_prnmg, ilsvrc_rnmg, mnist_prnmg, mnist_unmg)}
+NETS = {c.name: c for c in (cifar_nmg, cifar_rnmg, cifar_pnmg, cifar_prnmg, ilsvrc_rnmg, mnist_prnmg, mnist_pnmg, mnist_unmg)}
 
 
 def load_net(netType):

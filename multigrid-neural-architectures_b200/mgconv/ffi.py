@@ -13,7 +13,7 @@ MG_MAX_SRC = 8
 MG_F32, MG_BF16 = 0, 1
 MG_SEG_SAME, MG_SEG_POOL, MG_SEG_UP, MG_SRC_POOL3 = 0, 1, 2, 3
 MG_IMPL_AUTO, MG_IMPL_SIMT, MG_IMPL_TCGEN05 = 0, 1, 2
-MG_TUNE_HALO_SUBTILES, MG_TUNE_PERSISTENT = 0, 1
+MG_TUNE_HALO_SUBTILES, MG_TUNE_PERSISTENT, MG_TUNE_STEM_FUSED_STATS = 0, 1, 2
 MG_ALGO_AUTO, MG_ALGO_TILE128, MG_ALGO_TILE256, MG_ALGO_RESIDENT, MG_ALGO_TILE128_DEEP, MG_ALGO_TILE256_DEEP, MG_ALGO_TILE128_MID = 0, 1, 2, 3, 4, 5, 6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -78,6 +78,7 @@ SIGNATURES = {
     "mg_ctx_profile_read": (_I, [_P, C.POINTER(C.c_double), C.POINTER(_I64)]),
     "mg_import_nchw": (_I, [_P, _P, _G]),
     "mg_export_nchw": (_I, [_P, _G, _P]),
+    "mg_crop_flip_normalize": (_I, [_P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P]),
     "mg_conv_packed_bytes": (_SZ, [_D, _I]),
     "mg_conv_pack_weights": (_I, [_P, _D, _P, _P, _I]),
     "mg_conv_forward": (_I, [_P, _D, _P, _P, _P, _G, _P]),

@@ -379,14 +379,17 @@ class Linear(Module):
         self.bias = torch.empty(outputSize)
         self.gradWeight = torch.zeros_like(self.weight)
         self.gradBias = torch.zeros_like(self.bias)
-        stdv = 1.0 / math.sqrt(inputSize)
-        self.weight.uniform_(-stdv, stdv)
-        self.bias.uniform_(-stdv, stdv)
+        self.reset()
         # a Linear on N x C x 1 x 1 is a 1x1 convolution
         self.nInputPlane, self.nOutputPlane = inputSize, outputSize
         self.kW = self.kH = 1
         self.dW = self.dH = 1
         self.padW = self.padH = 0
+
+    def reset(self, stdv=None):  # torch7 Linear:reset()
+        stdv = stdv or 1.0 / math.sqrt(self.weight.shape[1])
+        self.weight.uniform_(-stdv, stdv)
+        self.bias.uniform_(-stdv, stdv)
 
     def own_parameters(self):
         return [("weight", self.weight, self.gradWeight), ("bias", self.bias, self.gradBias)]
@@ -408,6 +411,12 @@ class SpatialBatchNormalization(Module):
         self.gradBias = torch.zeros(nOutput)
         self.running_mean = torch.zeros(nOutput)
         self.running_var = torch.ones(nOutput)
+
+    def reset(self):  # torch7 BatchNormalization:reset()
+        self.weight.uniform_(0, 1)
+        self.bias.zero_()
+        self.running_mean.zero_()
+        self.running_var.fill_(1)
 
     def own_parameters(self):
         return [("weight", self.weight, self.gradWeight), ("bias", self.bias, self.gradBias)]

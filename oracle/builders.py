@@ -434,6 +434,59 @@ def mnist_prnmg(nLayer=1, nClass=1):
     return model
 
 
+def pnmg_mnist_mgConv(nInputPlanes, nOutputPlanes, isDrop=False, isOut=False):
+    """models/mnist-cluttered/pnmg.mnist.lua:83-102 (mgConv) / 104-121 (mgConvOutput: ConvBN, no ReLU)"""
+    mg_conv = nn.Sequential()
+    rc, nIPs = ResampleConcat(nInputPlanes, isDrop)
+    mg_conv.add(rc)
+    convs = nn.ParallelTable()
+    for i in range(len(nIPs)):
+        convs.add((ConvBN if isOut else ConvBNReLU)(nn.Sequential(), nIPs[i], nOutputPlanes[i], 3, 1e-3))
+    mg_conv.add(convs)
+    return mg_conv
+
+
+def mnist_pnmg(nLayer=1, nClass=1):
+    """models/mnist-cluttered/pnmg.mnist.lua:219-272 (+ MultiGridsInput 150-196, MultiGrids 198-205, MultiGridsOutput 207-215)"""
+    blocks = [([64, 32, 16, 8], False)] * 4 + [([64, 32, 16], True), ([64, 32], True), ([nClass], True)]
+    model = nn.Sequential()
+    nIPs = [1, 1, 1, 1]
+    for indBlock, (nOPs, isDrop) in enumerate(blocks, 1):
+        if indBlock == 1:
+            model.add(image_pyramid_convs(nOPs, 1, 1e-3))
+            n = len(nOPs)
+            for nGrid in range(1, n + 1):
+                for _ in range(nLayer):
+                    if nGrid > 1:
+                        mg_convs = nn.ConcatTable()
+                        for j in range(1, n - nGrid + 1):
+                            mg_convs.add(nn.SelectTable(j))
+                        _select = nn.ConcatTable()
+                        _nOPs = []
+                        for j in range(n - nGrid + 1, n + 1):
+                            _select.add(nn.SelectTable(j))
+                            _nOPs.append(nOPs[j - 1])
+                        mg_convs.add(nn.Sequential().add(_select).add(pnmg_mnist_mgConv(_nOPs, _nOPs)))
+                        model.add(mg_convs)
+                        model.add(nn.FlattenTable())
+                    else:
+                        convs = nn.ParallelTable()
+                        for _j in range(n - 1):
+                            convs.add(nn.Identity())
+                        convs.add(ConvBNReLU(nn.Sequential(), nOPs[-1], nOPs[-1], 3, 1e-3))
+                        model.add(convs)
+        else:
+            last = indBlock == len(blocks)
+            for i in range(1, nLayer + 1):
+                model.add(pnmg_mnist_mgConv(nIPs, nOPs, isDrop if i == 1 else False, last and i == nLayer))
+                nIPs = list(nOPs)
+        nIPs = list(nOPs)
+    model.add(nn.SelectTable(1))
+    model.add(nn.Sigmoid())
+    nn.conv_init_msr_fanout(model)
+    return model
+
+
 def mnist_unmg(nClass=10):
     """models/mnist-cluttered/unmg.lua:174-258 (U-MG; the nn.ConcatUnet user)"""
     blocks = [([64, 32, 16], False), ([128, 64, 32], True), ([256, 128], True), ([512], None)]

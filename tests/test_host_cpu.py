@@ -330,3 +330,51 @@ def test_lane_schedule_orders_every_conflicting_pair():
                 if conflict:
                     assert i in before[j], (trial, i, j)
         assert done[0] >= set(range(len(ops)))                              # final join
+
+
+def test_modelfuncs_initialisers_statistics():
+    """utils/modelfuncs.lua:3-54: MSRinit(model, backend, pow) is the FAN-IN normal with an exponent, XAVinit the uniform
+    const * sqrt(sqrt / (nIn + nOut)), GAUSSinit N(mean, stddev); every one zeroes the conv biases; BNinit / FCinit /
+    DisableBias as the Lua does.  Statistics are checked on the layers with enough weights for a 5 % bar."""
+    import math
+    import torch
+    from mgconv import modelfuncs as MF, builders as B
+    torch.manual_seed(0)
+    model = B.load_net("cifar/rnmg").createModel(B.Opt(nGPU=1, nLayer=1))
+    convs = model.findModules("cudnn.SpatialConvolution")
+    assert len(convs) > 10
+    big = [v for v in convs if v.weight.numel() >= 50000]
+    for pw in (0.5, 0.3):
+        MF.MSRinit(model, "cudnn", pw)
+        for v in big:
+            want = math.pow(2.0 / (v.kW * v.kH * v.nInputPlane), pw)
+            assert abs(float(v.weight.std()) / want - 1) < 0.05 and abs(float(v.weight.mean())) < 0.05 * want
+        assert all(float(v.bias.abs().max()) == 0 for v in convs)
+    MF.MSRinit(model, "nn", 0.5)      # either backend spelling reaches the same modules (cudnn.convert leaves both in the wild)
+    MF.XAVinit(model, "cudnn", 1.0, 6.0)
+    for v in big:
+        val = math.sqrt(6.0 / (v.nInputPlane + v.nOutputPlane))
+        assert float(v.weight.abs().max()) <= val and abs(float(v.weight.std()) / (val / math.sqrt(3)) - 1) < 0.05
+    MF.GAUSSinit(model, "cudnn", 0.25, 0.02)
+    for v in big:
+        assert abs(float(v.weight.mean()) - 0.25) < 2e-3 and abs(float(v.weight.std()) / 0.02 - 1) < 0.05
+    MF.BNinit(model, "nn", 0.5, 0.125)
+    bns = model.findModules("nn.SpatialBatchNormalization")
+    assert bns and all(float(m.weight.min()) == 0.5 == float(m.weight.max()) and float(m.bias.min()) == 0.125 for m in bns)
+    for m in model.findModules("nn.Linear"):
+        m.bias.fill_(3.0)
+    MF.FCinit(model)
+    assert all(float(m.bias.abs().max()) == 0 for m in model.findModules("nn.Linear"))
+    convs[0].bias.fill_(1.0)
+    MF.DisableBias(model, "cudnn")
+    assert float(convs[0].bias.abs().max()) == 0 and convs[0].noBias
+    with pytest.raises(AssertionError):
+        MF.MSRinit(model, "cunn", 0.5)    # modelfuncs.lua:4 asserts the backend name
+
+
+def test_put2gpu_mirrors_utilfuncs_structure():
+    """utils/utilfuncs.lua:19-30: a tensor destination takes exactly one CPU tensor, anything else is the Lua's error"""
+    import torch
+    from mgconv import utilfuncs as U
+    with pytest.raises(Exception):
+        U.put2GPU([torch.zeros(2), torch.zeros(2)], torch.zeros(2))

@@ -313,13 +313,13 @@ def test_stem_conv7x7_stride2(ctx, impl):
 
 @pytest.mark.parametrize("case", [(3, 3, 36, 44, 64), (2, 3, 70, 30, 32), (5, 1, 17, 9, 24), (2, 3, 224, 224, 64)],
                          ids=["cout64-tma-store", "cout32", "odd-cin1", "imagenet-size"])
-@pytest.mark.parametrize("fused", ["0", "1"], ids=["stats-pass", "stats-fused"])
-def test_stem_kernel_shapes(case, fused, monkeypatch):
+@pytest.mark.parametrize("fused", [0, 1], ids=["stats-pass", "stats-fused"])
+def test_stem_kernel_shapes(case, fused):
     """the dedicated 7x7 / stride-2 kernel (zero-copy im2col through UMMA descriptors over parity planes of the input patch):
     ragged tiles in both directions, the TMA-store epilogue (Cout = 64) and the direct-store one, fused BatchNorm sums"""
     N, Cin, H, W, Cout = case
-    monkeypatch.setenv("MGCONV_STEM_FUSED_STATS", fused)   # read once per process: the first parametrisation decides; both paths are
-    ctx = ffi.Context(0, torch.cuda.current_stream().cuda_stream, ffi.MG_BF16)   # also exercised through MGCONV_STEM_FUSED_STATS=1 runs
+    ctx = ffi.Context(0, torch.cuda.current_stream().cuda_stream, ffi.MG_BF16)
+    ctx.set_tuning(ffi.MG_TUNE_STEM_FUSED_STATS, fused)
     x = rnd(N, Cin, H, W)
     w = bf16_round(rng.standard_normal((Cout, Cin, 7, 7)) * 0.1)
     b = bf16_round(rng.standard_normal(Cout) * 0.1)
@@ -333,7 +333,7 @@ def test_stem_kernel_shapes(case, fused, monkeypatch):
     sums = new_sums(2 * Cout)
     tc0 = ctx.tc_launches()
     ctx.call("mg_conv_forward", C.byref(d), ptr(wd), ptr(wp), ptr(bd), C.byref(gy.g()), ptr(sums))
-    assert ctx.tc_launches() - tc0 == 1
+    assert ctx.tc_launches() - tc0 == 1, "the stem must run on its tensor-core kernel"
     torch.cuda.synchronize()
     xin = torch.from_numpy(bf16_round(x)).cuda().float()
     y_ref = torch.nn.functional.conv2d(xin.double(), torch.from_numpy(w).cuda().double(), torch.from_numpy(b).cuda().double(), 2, 3)
@@ -572,7 +572,7 @@ def test_full_size_conv_is_linear_and_its_gradients_are_its_adjoints(shape):
     xs_np = xin[sel].double().cpu().numpy()
     yo = O.conv_forward(xs_np, w.double().cpu().numpy(), np.zeros(Cout), 1, 1)
     assert max_rel(yn[sel].double().cpu().numpy(), yo) <= tol
-    assert max_rel(y_ref[sel].double().cpu().numpy(), yo) <= 1e-5
+    assert max_rel(y_ref[sel].double().cpu().numpy(), yo) <= 1e-4          # fp32 accumulation over K up to 4 608
     ctx.close()
 
 
