@@ -9,9 +9,13 @@
  * Plain C, handle based, no C++ types or exceptions cross the boundary.  The header is
  * consumed verbatim by LuaJIT `ffi.cdef` (lua/mgconv_ffi.lua) and by Python ctypes/cffi
  * (mgconv/ffi.py).  Every function returns mg_status (0 = ok); the message of the last
- * failure on a context is available from mg_last_error().  Nothing here allocates device
- * memory: the host (Torch) owns all tensors and passes raw device pointers on every call
- * (getParameters() re-homes weights after construction -- pipelines/standard/train.lua:115).
+ * failure on a context is available from mg_last_error().  The host (Torch) owns every tensor it
+ * can see -- activations at the boundary, parameters, gradients, running statistics, stage workspaces --
+ * and passes raw device pointers on every call (getParameters() re-homes weights after construction,
+ * pipelines/standard/train.lua:115).  A context owns only small internal scratch, allocated lazily and
+ * grown on demand (split weight-gradient partial sums per lane, the job table of the batched weight
+ * packing, a few KB of deterministic-sum scratch, tensor-map cache) plus the NCCL communicator and its
+ * streams / events; none of it is ever visible to or serialised by the host.
  * All work is enqueued on the stream given to the context; no call synchronises.
  *
  * Tensor convention ("grid"): NHWC, element type = the context dtype (fp32 or bf16),
@@ -256,6 +260,41 @@ int mg_conv_backward_data(mg_ctx* ctx, const mg_conv_desc* d, const float* w, co
 /* dw += gscale * g^T * gather(x) ; dbias += gscale * sum(g)   (accGradParameters) */
 int mg_conv_backward_weight(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g,
                             float* dw, float* dbias, float gscale);
+
+/* ---- one multigrid stage per call (plan level) ------------------------------------------
+ * What a Torch7 host needs to stand in for the module graph mgConv() assembles (models/ilsvrc/rnmg.lua:91-159, residual;
+ * models/cifar/nmg.lua:31-86, plain): tensors cross the boundary exactly as the reference's modules see them -- one NCHW fp32
+ * device tensor per grid, finest first -- and parameters keep Torch's layout (conv weight [C_out][C_cat][k][k] with the input
+ * planes ordered finer | same | coarser, bias [C_out]; BN weight / bias / running_mean / running_var [C_out]).  The plan holds
+ * no device memory: mg_plan_workspace_bytes() tells the host how large a buffer (256-byte aligned, e.g. one CudaTensor) to
+ * pass to every call; the same buffer must be passed to the backward call that follows a forward call.  The host need not
+ * know anything about segments, pooled companions, epilogue fusion or gradient routing.
+ * Index of the parameters of (layer l, grid i): l * n_scales + i; a residual unit has two layers, a plain stage one. */
+enum { MG_STAGE_MAX_GRIDS = 4 };
+typedef struct {
+  int32_t n_scales;                       /* grids, finest first; H[i] == 2 * H[i+1] */
+  int32_t C_in[MG_STAGE_MAX_GRIDS], C_out[MG_STAGE_MAX_GRIDS];
+  int32_t H[MG_STAGE_MAX_GRIDS], W[MG_STAGE_MAX_GRIDS];
+  int32_t ksize[MG_STAGE_MAX_GRIDS];      /* 3 (pad 1) or 1 (pad 0) per grid */
+  int32_t residual;                       /* 1: ReLU(BN(mg(ReLU(BN(mg(x))))) + Shortcut(x)), Shortcut = Identity / nn.Padding (C_in <= C_out) */
+  int32_t no_final_relu;                  /* isOut of models/mnist-cluttered/prnmg.mnist.lua:108-175 */
+  float eps, momentum;                    /* of every SpatialBatchNormalization of the stage */
+} mg_stage_desc;
+typedef struct {
+  const float* conv_w[2 * MG_STAGE_MAX_GRIDS]; const float* conv_b[2 * MG_STAGE_MAX_GRIDS];
+  const float* bn_g[2 * MG_STAGE_MAX_GRIDS];   const float* bn_b[2 * MG_STAGE_MAX_GRIDS];
+  float* bn_rm[2 * MG_STAGE_MAX_GRIDS];        float* bn_rv[2 * MG_STAGE_MAX_GRIDS];     /* running statistics, updated when training */
+  float* conv_gw[2 * MG_STAGE_MAX_GRIDS];      float* conv_gb[2 * MG_STAGE_MAX_GRIDS];   /* gradWeight / gradBias: accumulated (+=) */
+  float* bn_gg[2 * MG_STAGE_MAX_GRIDS];        float* bn_gb[2 * MG_STAGE_MAX_GRIDS];
+} mg_stage_params;
+typedef struct mg_stage_plan mg_stage_plan;
+int mg_plan_create(mg_ctx* ctx, const mg_stage_desc* d, int32_t batch, mg_stage_plan** out);
+size_t mg_plan_workspace_bytes(const mg_stage_plan* plan);
+int mg_plan_destroy(mg_stage_plan* plan);
+/* updateOutput: x[i] -> y[i] (NCHW fp32, [batch][C][H[i]][W[i]]); training != 0: batch statistics + running-statistics update */
+int mg_stage_forward(mg_stage_plan* plan, void* workspace, const float* const* x, const mg_stage_params* params, float* const* y, int training);
+/* updateGradInput + accGradParameters(scale): dy[i] -> dx[i] (dx or single entries may be NULL: no input gradient wanted) */
+int mg_stage_backward(mg_stage_plan* plan, void* workspace, const float* const* dy, const mg_stage_params* params, float* const* dx, float scale);
 
 /* ---- head / criterion / optimiser ("next" rows of the scope table) ------------------- */
 /* LogSoftMax + ClassNLLCriterion (mean): logits grid N x 1 x 1 x C; target int32 0-based;

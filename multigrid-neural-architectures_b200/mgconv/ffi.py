@@ -39,6 +39,20 @@ class mg_grad_src(C.Structure):
     _fields_ = [("g", mg_grid), ("c_offset", C.c_int32), ("mode", C.c_int32), ("aux", C.c_void_p)]
 
 
+MG_STAGE_MAX_GRIDS = 4
+
+
+class mg_stage_desc(C.Structure):
+    _fields_ = [("n_scales", C.c_int32), ("C_in", C.c_int32 * MG_STAGE_MAX_GRIDS), ("C_out", C.c_int32 * MG_STAGE_MAX_GRIDS),
+                ("H", C.c_int32 * MG_STAGE_MAX_GRIDS), ("W", C.c_int32 * MG_STAGE_MAX_GRIDS), ("ksize", C.c_int32 * MG_STAGE_MAX_GRIDS),
+                ("residual", C.c_int32), ("no_final_relu", C.c_int32), ("eps", C.c_float), ("momentum", C.c_float)]
+
+
+class mg_stage_params(C.Structure):
+    _fields_ = [(name, C.c_void_p * (2 * MG_STAGE_MAX_GRIDS)) for name in
+                ("conv_w", "conv_b", "bn_g", "bn_b", "bn_rm", "bn_rv", "conv_gw", "conv_gb", "bn_gg", "bn_gb")]
+
+
 class mg_bn_fused(C.Structure):
     _fields_ = [("sums", C.c_void_p), ("count", C.c_int64), ("gamma", C.c_void_p), ("beta", C.c_void_p),
                 ("running_mean", C.c_void_p), ("running_var", C.c_void_p), ("eps", C.c_float), ("momentum", C.c_float),
@@ -110,6 +124,11 @@ SIGNATURES = {
     "mg_nll_criterion": (_I, [_P, _P, _P, C.c_int32, C.c_int32, _P, _P, _F]),
     "mg_bce_criterion": (_I, [_P, _P, _P, _I64, _P, _P, _F]),
     "mg_sgd_step": (_I, [_P, _P, _P, _P, _I64, _F, _F, _F, _I]),
+    "mg_plan_create": (_I, [_P, C.POINTER(mg_stage_desc), C.c_int32, C.POINTER(_P)]),
+    "mg_plan_workspace_bytes": (_SZ, [_P]),
+    "mg_plan_destroy": (_I, [_P]),
+    "mg_stage_forward": (_I, [_P, _P, C.POINTER(_P), C.POINTER(mg_stage_params), C.POINTER(_P), _I]),
+    "mg_stage_backward": (_I, [_P, _P, C.POINTER(_P), C.POINTER(mg_stage_params), C.POINTER(_P), _F]),
     "mg_comm_unique_id": (_I, [_P]),
     "mg_comm_init": (_I, [_P, _I, _I, _P]),
     "mg_comm_destroy": (_I, [_P]),
