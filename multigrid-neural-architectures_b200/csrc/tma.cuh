@@ -60,7 +60,16 @@ static inline int mg_tensor_map(mg_ctx* ctx, const void* ptr, int N, int H, int 
   CUtensorMap tm;
   CUresult r;
   const cuuint64_t row = (cuuint64_t)Cp * 2;
-  if (kind == 3) {
+  if (kind == 4) {
+    // whole-image boxes: (H+1)*(W+1) slots per image divide the tile (7 x 7 grids: 64 slots), so ONE box of box_w images is the
+    // tile -- pad column, pad row and images beyond the batch are out-of-bounds zeros
+    cuuint64_t dims[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {row, row * W, row * W * H};
+    cuuint32_t box[4] = {64, (cuuint32_t)(W + 1), (cuuint32_t)(H + 1), (cuuint32_t)box_w};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else if (kind == 3) {
     // output tile of the stem kernel: 16 rows x 8 pixels x 64 channels, 128-byte swizzle (TMA store; clipped at the image edge)
     cuuint64_t dims[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {row, row * W, row * W * H};
@@ -125,6 +134,14 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 
 // floor(a / b) for b > 0 and any a
 __device__ __forceinline__ int floordiv(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+
+// whole-image mode (kind 4 map): the tile is `imgs` complete images starting at image n0
+__device__ __forceinline__ void tma_load_images(const CUtensorMap* tm, uint32_t dst, uint64_t* bar, int c0, int n0, uint32_t bytes, int lane) {
+  if (lane == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+    tma_load_4d(dst, tm, bar, c0, 0, 0, n0);
+  }
+}
 
 // One warp stages slot rows [r0, r0 + nr) (64 channels from c0 of one source grid) at `dst` (row i at dst + i * Wp * 128) and
 // arms `bar` with the byte count; every lane issues its own rows.  up: coarser grid through the zero-stride map (W slots per

@@ -374,6 +374,7 @@ struct HParams {
   int seg_up[MG_MAX_SEG];
   HChunk chunk[MAX_CHUNKS];
   int n_seg, n_chunks, n_stages, any_up;
+  int img_box;        // whole-image TMA boxes (tma.cuh kind 4): the buffer is exactly the halo, (W+2) zero slots | tile | (W+2) zero slots
   int H, W, Wp, Hp, Nimg;
   int64_t T;          // N * Hp * Wp slots
   int HL;             // halo slots a tile needs = tile slots + 2 * Wp + 2
@@ -397,6 +398,18 @@ __device__ __forceinline__ void zero_pad_column(uint8_t* a_smem, int nbuf, int h
   for (int i = tid; i < nbuf * nr_max * 8; i += nthreads) {
     const int q = i & 7, row = (i >> 3) % nr_max, buf = (i >> 3) / nr_max;
     *reinterpret_cast<uint4*>(a_smem + (size_t)buf * halo_bytes + (size_t)(row * Wp + Wp - 1) * 128 + q * 16) = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async();
+}
+
+// whole-image mode: the Wp + 1 slots before and after the tile are never written by the copy engine; they are the zero pad row
+// of the neighbouring image (before) and slots only padding outputs read (after) -- zero them once
+__device__ __forceinline__ void zero_halo_margins(uint8_t* a_smem, int nbuf, int halo_bytes, int HL, int Wp, int tid, int nthreads) {
+  const int m = Wp + 1;
+  for (int i = tid; i < nbuf * 2 * m * 8; i += nthreads) {
+    const int q = i & 7, sl = (i >> 3) % (2 * m), buf = (i >> 3) / (2 * m);
+    const int slot = sl < m ? sl : HL - 2 * m + sl;
+    *reinterpret_cast<uint4*>(a_smem + (size_t)buf * halo_bytes + (size_t)slot * 128 + q * 16) = make_uint4(0, 0, 0, 0);
   }
   fence_proxy_async();
 }
@@ -437,7 +450,7 @@ __global__ void __launch_bounds__(32 * (4 * MT + 3), MT == 1 ? 4 : 2) umma_conv_
   const int hs = t0 - p.Wp - 1;
   const int r0 = floordiv(hs, p.Wp);
   const int nr = (hs + p.HL - 1) / p.Wp - r0 + 1;
-  const int off = hs - r0 * p.Wp;
+  const int off = p.img_box ? 0 : hs - r0 * p.Wp;
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
@@ -451,7 +464,8 @@ __global__ void __launch_bounds__(32 * (4 * MT + 3), MT == 1 ? 4 : 2) umma_conv_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (warp == A_WARP && lane < p.n_seg) tma_prefetch_desc(&p.tmap[lane]);
-  if (p.any_up) zero_pad_column(a_smem, p.n_abuf, p.halo_bytes, p.nr_max, p.Wp, tid, NT);
+  if (p.img_box) zero_halo_margins(a_smem, p.n_abuf, p.halo_bytes, p.HL, p.Wp, tid, NT);
+  else if (p.any_up) zero_pad_column(a_smem, p.n_abuf, p.halo_bytes, p.nr_max, p.Wp, tid, NT);
   // everything above touched only kernel parameters, shared memory and TMEM: it overlapped the tail of the
   // previous kernel; from here on the predecessor's output (activations, packed weights, bias) is read
   pdl_wait();
@@ -538,7 +552,9 @@ __global__ void __launch_bounds__(32 * (4 * MT + 3), MT == 1 ? 4 : 2) umma_conv_
       const int buf = ra.idx;
       if (c >= p.n_abuf) mbar_wait(&a_empty[buf], ra.phase ^ 1u);
       const HChunk ch = p.chunk[c];
-      tma_load_rows(&p.tmap[ch.seg], p.seg_up[ch.seg], smem_u32(a_smem + (size_t)buf * p.halo_bytes), &a_full[buf], ch.c0, r0, nr, p.W, p.Hp, lane);
+      const uint32_t dst = smem_u32(a_smem + (size_t)buf * p.halo_bytes);
+      if (p.img_box) tma_load_images(&p.tmap[ch.seg], dst + (uint32_t)(p.Wp + 1) * 128u, &a_full[buf], ch.c0, t0 / (p.Hp * p.Wp), (uint32_t)(BM * MT) * 128u, lane);
+      else tma_load_rows(&p.tmap[ch.seg], p.seg_up[ch.seg], dst, &a_full[buf], ch.c0, r0, nr, p.W, p.Hp, lane);
     }
   } else if (warp == B_WARP) {
     // ================= weight loader: one bulk copy per stage ====================================
@@ -643,7 +659,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (warp == P_A_WARP && lane < p.n_seg) tma_prefetch_desc(&p.tmap[lane]);
-  if (p.any_up) zero_pad_column(a_smem, NA, p.halo_bytes, p.nr_max, p.Wp, tid, P_THREADS);
+  if (p.img_box) zero_halo_margins(a_smem, NA, p.halo_bytes, p.HL, p.Wp, tid, P_THREADS);
+  else if (p.any_up) zero_pad_column(a_smem, NA, p.halo_bytes, p.nr_max, p.Wp, tid, P_THREADS);
   pdl_wait();
   for (int c = tid; c < p.n_tile; c += P_THREADS) s_bias[c] = (p.bias && c < p.c_bias) ? p.bias[c] : 0.f;
   tc_fence_before();
@@ -735,7 +752,9 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
         const int buf = ra.idx;
         if (ac >= NA) mbar_wait(&a_empty[buf], ra.phase ^ 1u);
         const HChunk ch = p.chunk[c];
-        tma_load_rows(&p.tmap[ch.seg], p.seg_up[ch.seg], smem_u32(a_smem + (size_t)buf * p.halo_bytes), &a_full[buf], ch.c0, r0, nr, p.W, p.Hp, lane);
+        const uint32_t dst = smem_u32(a_smem + (size_t)buf * p.halo_bytes);
+        if (p.img_box) tma_load_images(&p.tmap[ch.seg], dst + (uint32_t)(p.Wp + 1) * 128u, &a_full[buf], ch.c0, t0 / (p.Hp * p.Wp), (uint32_t)BM * 128u, lane);
+        else tma_load_rows(&p.tmap[ch.seg], p.seg_up[ch.seg], dst, &a_full[buf], ch.c0, r0, nr, p.W, p.Hp, lane);
       }
     }
   } else if (warp == P_B_WARP) {
@@ -758,7 +777,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
       const int t0 = (int)(blockIdx.x + it * gridDim.x) * BM;
       const int hs = t0 - p.Wp - 1;
-      const int off = hs - floordiv(hs, p.Wp) * p.Wp;
+      const int off = p.img_box ? 0 : hs - floordiv(hs, p.Wp) * p.Wp;
       for (int c = 0; c < p.n_chunks; ++c, ra.next()) {
         const int buf = ra.idx;
         const HChunk ch = p.chunk[c];
@@ -1274,10 +1293,30 @@ constexpr int SMEM_MAX = 232448 - 4096;   // 227 KB per CTA minus the halo kerne
 static void halo_geometry(HParams& p, int slots) {
   p.HL = slots + 2 * p.Wp + 2;
   p.nr_max = (p.HL - 1 + p.Wp - 1) / p.Wp + 1;
-  p.halo_bytes = mg_round_up(p.nr_max * p.Wp * 128, 1024);
+  p.halo_bytes = mg_round_up((p.img_box ? p.HL : p.nr_max * p.Wp) * 128, 1024);
 }
 
-static int launch_halo(mg_ctx* ctx, HParams& p, const Geometry& g, int algo) {
+// whole-image TMA boxes: images of (H+1)*(W+1) slots that divide the tile (7 x 7 grids), no up-sampled segment
+static bool img_box_ok(const HParams& p, int slots) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("MGCONV_IMG_BOX"); on = e ? atoi(e) : 1; }
+  const int spi = p.Hp * p.Wp;
+  return on && !p.any_up && slots % spi == 0 && slots / spi <= 256;
+}
+
+// (re)build the tensor maps of the K segments for the tile size at hand
+static int halo_tensor_maps(mg_ctx* ctx, HParams& p, const mg_grid* segs, int slots) {
+  p.img_box = img_box_ok(p, slots) ? 1 : 0;
+  for (int s = 0; s < p.n_seg; ++s) {
+    const mg_grid& g = segs[s];
+    int rc = p.img_box ? mg_tensor_map(ctx, g.data, p.Nimg, g.H, g.W, g.Cp, 4, slots / (p.Hp * p.Wp), &p.tmap[s])
+                       : mg_tensor_map(ctx, g.data, p.Nimg, g.H, g.W, g.Cp, p.seg_up[s] ? 1 : 0, p.seg_up[s] ? 2 * g.W : p.Wp, &p.tmap[s]);
+    if (rc) return rc;
+  }
+  return MG_OK;
+}
+
+static int launch_halo(mg_ctx* ctx, HParams& p, const Geometry& g, int algo, const mg_grid* segs) {
   const int b_stage = p.n_tile * 128;
   static int budget_env = -1, mt_env = -1;
   if (budget_env < 0) { const char* e = getenv("MGCONV_HALO_SMEM_KB"); budget_env = e ? atoi(e) : 0; }
@@ -1292,6 +1331,7 @@ static int launch_halo(mg_ctx* ctx, HParams& p, const Geometry& g, int algo) {
     const bool heur2 = g.n_chunks >= 3 && ctas2 * 10 >= (int64_t)ctx->num_sms * 8;
     MT = (want == 1 || want == 2) ? want : (heur2 ? 2 : 1);
   }
+  { int rc = halo_tensor_maps(ctx, p, segs, BM * MT); if (rc) return rc; }
   halo_geometry(p, BM * MT);
   int cols = 32;
   while (cols < MT * p.n_tile) cols <<= 1;
@@ -1345,7 +1385,7 @@ static bool persist_plan(const mg_ctx* ctx, const mg_conv_desc* d, const Geometr
   if (!forced && (ctx->tune_persist == 2 || !on)) return false;
   if (!g.halo || g.n_tiles != 1) return false;
   HParams hp;
-  hp.Wp = d->W + 1;
+  hp.Wp = d->W + 1; hp.img_box = 0;     // sized for the row mode (the whole-image mode needs no more)
   halo_geometry(hp, BM);
   const int64_t m_tiles = mg_cdiv((int64_t)Nimg * (d->H + 1) * hp.Wp, BM);
   if (!forced && m_tiles < (int64_t)min_tiles_per_sm * ctx->num_sms) return false;
@@ -1363,7 +1403,8 @@ static bool persist_plan(const mg_ctx* ctx, const mg_conv_desc* d, const Geometr
   return true;
 }
 
-static int launch_halo_persistent(mg_ctx* ctx, HParams& p, const PersistPlan& pl) {
+static int launch_halo_persistent(mg_ctx* ctx, HParams& p, const PersistPlan& pl, const mg_grid* segs) {
+  { int rc = halo_tensor_maps(ctx, p, segs, BM); if (rc) return rc; }
   halo_geometry(p, BM);
   p.m_tiles = (int)mg_cdiv(p.T, BM);
   p.tmem_cols = pl.tmem_cols;
@@ -1398,8 +1439,6 @@ static int fill_halo_params(mg_ctx* ctx, HParams& p, const Geometry& g, int n_se
   for (int s = 0; s < n_seg; ++s) {
     p.seg_up[s] = up[s];
     if (up[s]) p.any_up = 1;
-    int rc = mg_tensor_map(ctx, segs[s].data, N, segs[s].H, segs[s].W, segs[s].Cp, up[s] ? 1 : 0, up[s] ? 2 * segs[s].W : p.Wp, &p.tmap[s]);
-    if (rc) return rc;
   }
   return MG_OK;
 }
@@ -1559,7 +1598,7 @@ int umma_conv_forward(mg_ctx* ctx, const mg_conv_desc* d, const void* wpack, con
     const bool fused_stats = bn_sums && fused_stats_on();
     if (fused_stats) { hp.stats = bn_sums; hp.c_stats = d->Cout; }
     PersistPlan pl;
-    rc = persist_plan(ctx, d, g, hp.Nimg, d->algo_fwd, &pl) ? launch_halo_persistent(ctx, hp, pl) : launch_halo(ctx, hp, g, d->algo_fwd);
+    rc = persist_plan(ctx, d, g, hp.Nimg, d->algo_fwd, &pl) ? launch_halo_persistent(ctx, hp, pl, d->seg) : launch_halo(ctx, hp, g, d->algo_fwd, d->seg);
     if (rc) return rc;
     if (bn_sums && !fused_stats) return mg_bn_stats(ctx, y, bn_sums);
     return MG_OK;
@@ -1598,7 +1637,7 @@ int umma_conv_backward_data(mg_ctx* ctx, const mg_conv_desc* d, const void* wpac
     hp.wpack = (const uint8_t*)wpack_t; hp.bias = nullptr;
     hp.y = (__nv_bfloat16*)dcat->data; hp.y_pitch = dcat->Cp; hp.c_valid = dcat->Cp;
     PersistPlan pl;
-    return persist_plan(ctx, d, g, hp.Nimg, d->algo_bwd_data, &pl) ? launch_halo_persistent(ctx, hp, pl) : launch_halo(ctx, hp, g, d->algo_bwd_data);
+    return persist_plan(ctx, d, g, hp.Nimg, d->algo_bwd_data, &pl) ? launch_halo_persistent(ctx, hp, pl, gr) : launch_halo(ctx, hp, g, d->algo_bwd_data, gr);
   }
   UParams p;
   memset(&p, 0, sizeof(p));

@@ -248,6 +248,7 @@ struct WHParams {
   int n_slot_tiles, tiles_per_cta;
   int stages, tmem_cols;
   int kt;                    // slots per pipeline stage (K of one stage): 128 or 256
+  int img_box;               // whole-image TMA boxes (7 x 7 grids): buffers hold exactly the halo / the tile's g rows
 };
 
 __global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __grid_constant__ WHParams p) {
@@ -280,7 +281,15 @@ __global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (warp == WH_TMA_WARP && lane == 0) { tma_prefetch_desc(&p.tmap_x[sg]); tma_prefetch_desc(&p.tmap_g); }
-  if (up) {   // the up-sampling box leaves the pad slot of every row alone: zero it once (stage buffers are stage_bytes apart)
+  if (p.img_box) {   // margins of the halo (Wp + 1 slots before / after the tile) are never written by the copy engine: zero them once
+    const int m = p.Wp + 1;
+    for (int i = tid; i < S * 2 * m * 8; i += WH_THREADS) {
+      const int q = i & 7, sl = (i >> 3) % (2 * m), st = (i >> 3) / (2 * m);
+      const int slot = sl < m ? sl : p.HL - 2 * m + sl;
+      *reinterpret_cast<uint4*>(smem + (size_t)st * stage_bytes + (size_t)slot * 128 + q * 16) = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async();
+  } else if (up) {   // the up-sampling box leaves the pad slot of every row alone: zero it once (stage buffers are stage_bytes apart)
     for (int i = tid; i < S * p.nr_max * 8; i += WH_THREADS) {
       const int q = i & 7, row = (i >> 3) % p.nr_max, st = (i >> 3) / p.nr_max;
       *reinterpret_cast<uint4*>(smem + (size_t)st * stage_bytes + (size_t)(row * p.Wp + p.W) * 128 + q * 16) = make_uint4(0, 0, 0, 0);
@@ -335,9 +344,16 @@ __global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __
       const int gr0 = t0 / p.Wp;
       const int gnr = (t0 + p.kt - 1) / p.Wp - gr0 + 1;
       const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
-      tma_load_rows(&p.tmap_x[sg], up, st, &full_bar[s], c0, r0, nr, p.W, p.Hp, lane);
-      for (int b = 0; b < p.n_blk; ++b)
-        tma_load_rows(&p.tmap_g, 0, st + (uint32_t)(p.halo_bytes + b * p.g_bytes), &full_bar[s], nt * p.n_tile + b * 64, gr0, gnr, p.W, p.Hp, lane);
+      if (p.img_box) {
+        const int n0 = t0 / (p.Hp * p.Wp);
+        tma_load_images(&p.tmap_x[sg], st + (uint32_t)(p.Wp + 1) * 128u, &full_bar[s], c0, n0, (uint32_t)p.kt * 128u, lane);
+        for (int b = 0; b < p.n_blk; ++b)
+          tma_load_images(&p.tmap_g, st + (uint32_t)(p.halo_bytes + b * p.g_bytes), &full_bar[s], nt * p.n_tile + b * 64, n0, (uint32_t)p.kt * 128u, lane);
+      } else {
+        tma_load_rows(&p.tmap_x[sg], up, st, &full_bar[s], c0, r0, nr, p.W, p.Hp, lane);
+        for (int b = 0; b < p.n_blk; ++b)
+          tma_load_rows(&p.tmap_g, 0, st + (uint32_t)(p.halo_bytes + b * p.g_bytes), &full_bar[s], nt * p.n_tile + b * 64, gr0, gnr, p.W, p.Hp, lane);
+      }
     }
   } else {
     // ---- MMA issuer: whole warp, elected lane issues (see elect_one) --------------------------------
@@ -349,8 +365,8 @@ __global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __
       const int s = rs.idx;
       const int t0 = (tile0 + it) * p.kt;
       const int hs = t0 - p.Wp - 1;
-      const int off = hs - floordiv(hs, p.Wp) * p.Wp;          // first halo slot within the row-aligned buffer
-      const int goff = t0 - (t0 / p.Wp) * p.Wp;                // first g slot within its row-aligned buffer
+      const int off = p.img_box ? 0 : hs - floordiv(hs, p.Wp) * p.Wp;          // first halo slot within the row-aligned buffer
+      const int goff = p.img_box ? 0 : t0 - (t0 / p.Wp) * p.Wp;                // first g slot within its row-aligned buffer
       mbar_wait(&full_bar[s], rs.phase);
       tc_fence_after();
       const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)off * 128u;
@@ -438,12 +454,18 @@ static int wgrad_halo(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g, floa
   // stage hand-shakes halve, and the copy engine is fed with fewer, larger batches (scratch/tma_bw.cu)
   static int kt_env = -1;
   if (kt_env < 0) { const char* e = getenv("MGCONV_WGRAD_KT"); kt_env = e ? atoi(e) : 0; }
+  static int img_env = -1;
+  if (img_env < 0) { const char* e = getenv("MGCONV_IMG_BOX"); img_env = e ? atoi(e) : 1; }
+  bool any_up = false;
+  for (int s = 0; s < d->n_seg; ++s) any_up = any_up || d->seg_mode[s] == MG_SEG_UP;
   for (p.kt = (kt_env == 128 ? 128 : 256); ; p.kt = 128) {
+    // whole-image TMA boxes when the images ((H+1)*(W+1) slots: 64 on the 7 x 7 grids) divide the K tile: one copy per operand
+    p.img_box = (img_env && !any_up && p.kt % (p.Hp * p.Wp) == 0) ? 1 : 0;
     p.HL = p.kt + 2 * p.Wp + 2;
     p.nr_max = (p.HL - 1 + p.Wp - 1) / p.Wp + 1;
-    p.halo_bytes = mg_round_up(p.nr_max * p.Wp * 128, 1024);
+    p.halo_bytes = mg_round_up((p.img_box ? p.HL : p.nr_max * p.Wp) * 128, 1024);
     p.gnr_max = (p.kt - 1 + p.Wp - 1) / p.Wp + 1;
-    p.g_bytes = mg_round_up(p.gnr_max * p.Wp * 128, 1024);
+    p.g_bytes = mg_round_up((p.img_box ? p.kt : p.gnr_max * p.Wp) * 128, 1024);
     if (p.kt == 128 || 2 * (p.halo_bytes + p.n_blk * p.g_bytes) + 1024 <= SMEM_WGRAD) break;
   }
   p.n_slot_tiles = (int)mg_cdiv(p.T, p.kt);
@@ -471,7 +493,8 @@ static int wgrad_halo(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g, floa
   int rc = mg_ctx_workspace(ctx, (size_t)z * plane * sizeof(float), &ws);
   if (rc) return rc;
   p.partial = (float*)ws;
-  rc = mg_tensor_map(ctx, g->data, g->N, g->H, g->W, g->Cp, 0, p.Wp, &p.tmap_g);
+  const int imgs = p.kt / (p.Hp * p.Wp);
+  rc = p.img_box ? mg_tensor_map(ctx, g->data, g->N, g->H, g->W, g->Cp, 4, imgs, &p.tmap_g) : mg_tensor_map(ctx, g->data, g->N, g->H, g->W, g->Cp, 0, p.Wp, &p.tmap_g);
   if (rc) return rc;
   int c = 0;
   p.n_seg = d->n_seg;
@@ -479,7 +502,8 @@ static int wgrad_halo(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g, floa
     const mg_grid& sg = d->seg[s];
     p.seg_up[s] = d->seg_mode[s] == MG_SEG_UP ? 1 : 0;
     if (p.seg_up[s]) p.any_up = 1;
-    rc = mg_tensor_map(ctx, sg.data, sg.N, sg.H, sg.W, sg.Cp, p.seg_up[s], p.seg_up[s] ? 2 * sg.W : p.Wp, &p.tmap_x[s]);
+    rc = p.img_box ? mg_tensor_map(ctx, sg.data, sg.N, sg.H, sg.W, sg.Cp, 4, imgs, &p.tmap_x[s])
+                   : mg_tensor_map(ctx, sg.data, sg.N, sg.H, sg.W, sg.Cp, p.seg_up[s], p.seg_up[s] ? 2 * sg.W : p.Wp, &p.tmap_x[s]);
     if (rc) return rc;
     p.seg_C[s] = sg.C; p.seg_Cp[s] = sg.Cp; p.seg_cbegin[s] = c;
     c += sg.C;
