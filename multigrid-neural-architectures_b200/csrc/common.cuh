@@ -187,6 +187,19 @@ __device__ __forceinline__ void mg_to_fix(double v, long long& hi, long long& lo
     hi = 1ll << 61; lo = 0;
   }
 }
+// the same conversion for an fp32 value without fp64 instructions: v * 2^10, its floor, the remainder and its scaling by 2^44 are
+// all exact in fp32 (power-of-two scalings; the remainder of a 24-bit number has at most 24 bits), so the result is bit-identical
+// to mg_to_fix((double)v)
+__device__ __forceinline__ void mg_to_fix_f32(float v, long long& hi, long long& lo) {
+  const float s = v * 1024.0f;
+  if (fabsf(s) < 1.0e15f) {
+    const float f = floorf(s);
+    hi = __float2ll_rz(f);
+    lo = __float2ll_rz((s - f) * 17592186044416.0f);
+  } else {
+    hi = 1ll << 61; lo = 0;
+  }
+}
 __device__ __forceinline__ void mg_sum_add_fix(mg_sum* p, long long hi, long long lo) {
   atomicAdd(reinterpret_cast<unsigned long long*>(&p->hi), (unsigned long long)hi);
   atomicAdd(reinterpret_cast<unsigned long long*>(&p->lo), (unsigned long long)lo);

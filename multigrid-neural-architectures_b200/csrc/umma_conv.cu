@@ -537,8 +537,8 @@ __global__ void __launch_bounds__(32 * (4 * MT + 3), MT == 1 ? 4 : 2) umma_conv_
           long long ah = 0, al = 0, bh = 0, bl = 0, h, l;
 #pragma unroll
           for (int w = 0; w < 4 * MT; ++w) {
-            mg_to_fix((double)s_part[(2 * w) * 256 + c], h, l); ah += h; al += l;
-            mg_to_fix((double)s_part[(2 * w + 1) * 256 + c], h, l); bh += h; bl += l;
+            mg_to_fix_f32(s_part[(2 * w) * 256 + c], h, l); ah += h; al += l;
+            mg_to_fix_f32(s_part[(2 * w + 1) * 256 + c], h, l); bh += h; bl += l;
           }
           mg_sum_add_fix(p.stats + ch, ah, al);
           mg_sum_add_fix(p.stats + p.c_stats + ch, bh, bl);
@@ -714,7 +714,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
             // as fixed-point integers (exact, so the totals do not depend on which tiles this CTA happened to walk)
             if (lane < 16) {
               long long fh, fl;
-              mg_to_fix((double)tot, fh, fl);
+              mg_to_fix_f32(tot, fh, fl);
               long long* sp = s_part + (size_t)((warp * 2 + (lane >> 3)) * p.n_tile + c0 + h * 8 + (lane & 7)) * 2;
               sp[0] += fh; sp[1] += fl;
             }
@@ -959,7 +959,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) umma_stem_kernel(const __grid_c
               const float tot = warp_reduce_scatter16(sv, lane);
               if (lane < 16) {
                 long long fh, fl;
-                mg_to_fix((double)tot, fh, fl);
+                mg_to_fix_f32(tot, fh, fl);
                 long long* sp = s_part + (size_t)((warp * 2 + (lane >> 3)) * p.n_tile + c0 + h * 8 + (lane & 7)) * 2;
                 sp[0] += fh; sp[1] += fl;
               }
@@ -1347,6 +1347,9 @@ static int launch_halo(mg_ctx* ctx, HParams& p, const Geometry& g, int algo, con
     budget_kb = ctas == 1 ? 200 : 108;
   }
   if (algo == MG_ALGO_TILE128_MID) budget_kb = 72;
+  // grids with at most one CTA per SM (7 x 7 layers: 128 tiles) gain nothing from co-resident CTAs: every CTA streams the whole
+  // weight image through its own ring, so give that ring all the shared memory there is (up to MAX_STAGES stages in flight)
+  if ((algo == MG_ALGO_AUTO || algo == MG_ALGO_RESIDENT) && mg_cdiv(p.T, BM * MT) * g.n_tiles <= ctx->num_sms) budget_kb = 200;
   // "deep" variants trade resident CTAs for two halo buffers and a longer weight ring (more bytes in flight per CTA)
   if (algo == MG_ALGO_TILE128_DEEP) budget_kb = 108;
   if (algo == MG_ALGO_TILE256_DEEP) budget_kb = 200;

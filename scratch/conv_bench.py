@@ -30,6 +30,7 @@ def run(name, N=256, iters=20, which=("fwd", "dgrad", "wgrad")):
     H, segs, Cout, k = SHAPES[name][:4]
     stride = SHAPES[name][4] if len(SHAPES[name]) > 4 else 1
     ctx = ffi.Context(0, torch.cuda.current_stream().cuda_stream, ffi.MG_BF16)
+    ctx.set_tuning(ffi.MG_TUNE_STEM_FUSED_STATS, int(os.environ.get("MGCONV_STEM_FUSED", "0")))
     gs, modes = [], []
     for c, m in segs:
         h = H // 2 if m == "u" else H
@@ -38,6 +39,7 @@ def run(name, N=256, iters=20, which=("fwd", "dgrad", "wgrad")):
         gs.append(g); modes.append(MG_SEG_UP if m == "u" else MG_SEG_SAME)
     pad = SHAPES[name][5] if len(SHAPES[name]) > 5 else (0 if k == 1 else 1)
     d = conv_desc(gs, modes, k, stride, pad, Cout, H, H)
+    d.algo_fwd = d.algo_bwd_data = int(os.environ.get("MGCONV_ALGO", "0"))
     Ho = (H + 2 * pad - k) // stride + 1
     cin = sum(c for c, _ in segs)
     w = torch.randn(Cout, cin, k, k, device="cuda") * 0.05
