@@ -132,7 +132,7 @@ __device__ __forceinline__ void apply_bn_prologue(const ApplyP& p, float* s_aff)
   }
 }
 
-__global__ void __launch_bounds__(256, 4) apply_bf16_kernel(const __grid_constant__ ApplyP p) {
+__global__ void __launch_bounds__(256, 3) apply_bf16_kernel(const __grid_constant__ ApplyP p) {
   pdl_launch();
   pdl_wait();
   extern __shared__ float s_aff[];   // [2][z_cp] when bn
@@ -154,38 +154,49 @@ __global__ void __launch_bounds__(256, 4) apply_bf16_kernel(const __grid_constan
     for (int e = 0; e < 8; ++e) { sc[e] = s_aff[c0 + e]; sh[e] = s_aff[p.z_cp + c0 + e]; }
   } else if (has_aff) { ldf8(p.scale + c0, sc); ldf8(p.shift + c0, sh); }
   const bool has_s = p.s != nullptr && c0 < p.s_cp;
+  // every load of the 2x2 block is issued before the first use (the stores below may alias z as far as the compiler knows, so
+  // it would otherwise order load - store - load: eight dependent round trips per thread instead of one).  Pixels outside the
+  // grid re-read pixel 0 of the block (always valid) and are dropped at the store.
+  const int y0 = 2 * py, x0 = 2 * px;
+  const bool ok[4] = {true, x0 + 1 < p.W, y0 + 1 < p.H, x0 + 1 < p.W && y0 + 1 < p.H};
+  int64_t pix[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) pix[k] = ((int64_t)n * p.H + y0 + (ok[k] ? (k >> 1) : 0)) * p.W + x0 + (ok[k] ? (k & 1) : 0);
+  uint4 zr[4], sr[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) zr[k] = *reinterpret_cast<const uint4*>(p.z + pix[k] * p.z_cp + c0);
+  if (has_s) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) sr[k] = *reinterpret_cast<const uint4*>(p.s + pix[k] * p.s_cp + c0);
+  }
   float best[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) best[e] = -INFINITY;
 #pragma unroll
-  for (int dy = 0; dy < 2; ++dy)
+  for (int k = 0; k < 4; ++k) {
+    if (!ok[k]) continue;
+    V8 v = unpack8(zr[k]);
+    if (has_aff) {
 #pragma unroll
-    for (int dx = 0; dx < 2; ++dx) {
-      const int y = 2 * py + dy, x = 2 * px + dx;
-      if (y >= p.H || x >= p.W) continue;
-      const int64_t pix = ((int64_t)n * p.H + y) * p.W + x;
-      V8 v = ld8(p.z + pix * p.z_cp + c0);
-      if (has_aff) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v.v[e] = mg_xform(v.v[e], sc[e], sh[e], p.z_relu);
-      }
-      if (has_s) {
-        const V8 sv = ld8(p.s + pix * p.s_cp + c0);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v.v[e] += sv.v[e];
-      }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        if (p.relu) v.v[e] = fmaxf(v.v[e], 0.f);
-        if (c0 + e >= p.C) v.v[e] = 0.f;
-      }
-      const uint4 u = pack8(v);
-      *reinterpret_cast<uint4*>(p.out + pix * p.o_cp + c0) = u;
-      const V8 r = unpack8(u);   // pool what was stored
-#pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (r.v[e] > best[e] || r.v[e] != r.v[e]) best[e] = r.v[e];
+      for (int e = 0; e < 8; ++e) v.v[e] = mg_xform(v.v[e], sc[e], sh[e], p.z_relu);
     }
+    if (has_s) {
+      const V8 sv = unpack8(sr[k]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v.v[e] += sv.v[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (p.relu) v.v[e] = fmaxf(v.v[e], 0.f);
+      if (c0 + e >= p.C) v.v[e] = 0.f;
+    }
+    const uint4 u = pack8(v);
+    *reinterpret_cast<uint4*>(p.out + pix[k] * p.o_cp + c0) = u;
+    const V8 r = unpack8(u);   // pool what was stored
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (r.v[e] > best[e] || r.v[e] != r.v[e]) best[e] = r.v[e];
+  }
   if (p.pooled && c0 < p.p_cp) {
     V8 b;
 #pragma unroll
@@ -366,6 +377,143 @@ __global__ void __launch_bounds__(256, NS < 0 ? 3 : 2) combine_bf16_kernel(const
           }
           if (p.sums) {
             const V8 yr = ldg8(p.bnx + pix[k] * p.bn_cp + c0);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { sd[e] += acc[k].v[e]; sdx[e] = fmaf(acc[k].v[e], yr.v[e], sdx[e]); }
+          }
+          *reinterpret_cast<uint4*>(p.d + pix[k] * p.d_cp + c0) = pack8(acc[k]);
+        }
+    }
+  if (p.sums) block_channel_sums(sd, sdx, vc, V, p.C, active, p.sums, sh);
+}
+
+// The specialised lists whose modes are same / pool / up only: all loads of a 2x2 block are issued as raw 16-byte registers
+// before the first use (first the 16 of an up-sampled source, which are summed at once; then the activation, the raw
+// BatchNorm input and every same / pool source together), so a thread has up to 17 independent loads in flight instead of a
+// chain of dependent ones (the older form above reuses one destination register for consecutive loads and interleaves the
+// BatchNorm-input loads with the stores: ~13 round trips per block).  Pixels outside the grid (odd H / W) re-read pixel 0 of
+// the block and are dropped at the store.  Same arithmetic and summation order as combine_bf16_kernel.
+template <int NS, int MODES>
+__global__ void __launch_bounds__(256, 2) combine_fast_kernel(const __grid_constant__ CombP p) {
+  pdl_launch();
+  pdl_wait();
+  extern __shared__ float sh[];
+  const int V = p.d_cp >> 3;
+  const int lanes = blockDim.x / V;
+  const int vc = threadIdx.x % V, lane = threadIdx.x / V;
+  const int c0 = vc * 8;
+  const int64_t nblocks = (int64_t)p.N * p.Hb * p.Wb;
+  const int64_t per_cta = (nblocks + gridDim.x - 1) / gridDim.x;
+  const int64_t b_begin = (int64_t)blockIdx.x * per_cta, b_end = min(nblocks, b_begin + per_cta);
+  const bool active = lane < lanes;
+  float sd[8], sdx[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { sd[e] = 0.f; sdx[e] = 0.f; }
+  constexpr bool any_pool = ((MODES & 3) == 1 && NS > 0) || (((MODES >> 2) & 3) == 1 && NS > 1) || (((MODES >> 4) & 3) == 1 && NS > 2) ||
+                            (((MODES >> 6) & 3) == 1 && NS > 3);
+  const bool need_x = p.relu_mask != 0 || any_pool;
+  const bool has_sums = p.sums != nullptr;
+
+  if (active)
+    for (int64_t blk = b_begin + lane; blk < b_end; blk += lanes) {
+      int n, by, bx, unused_;
+      split4(blk, p.Hb, p.Wb, 1, n, by, bx, unused_);
+      const int y0 = 2 * by, x0 = 2 * bx;
+      const bool vy1 = y0 + 1 < p.H, vx1 = x0 + 1 < p.W;
+      const bool valid[4] = {true, vx1, vy1, vy1 && vx1};
+      int64_t pix[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) pix[k] = ((int64_t)n * p.H + y0 + (valid[k] ? (k >> 1) : 0)) * p.W + x0 + (valid[k] ? (k & 1) : 0);
+      V8 acc[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[k].v[e] = 0.f;
+      // ---- up-sampled sources: this tensor was up-sampled into the consumer, so each pixel collects a 2x2 block of g ----
+#pragma unroll
+      for (int s = 0; s < NS; ++s)
+        if (((MODES >> (2 * s)) & 3) == MG_SEG_UP) {
+          const CSrc& S = p.src[s];
+          uint4 r[16];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int y = y0 + (valid[k] ? (k >> 1) : 0), x = x0 + (valid[k] ? (k & 1) : 0);
+            const bf16* gp = S.g + (((int64_t)n * S.H + 2 * y) * S.W + 2 * x) * S.cp + S.c_off + c0;
+            r[4 * k] = __ldg(reinterpret_cast<const uint4*>(gp));
+            r[4 * k + 1] = __ldg(reinterpret_cast<const uint4*>(gp + S.cp));
+            r[4 * k + 2] = __ldg(reinterpret_cast<const uint4*>(gp + (int64_t)S.W * S.cp));
+            r[4 * k + 3] = __ldg(reinterpret_cast<const uint4*>(gp + (int64_t)S.W * S.cp + S.cp));
+          }
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const V8 g0 = unpack8(r[4 * k]), g1 = unpack8(r[4 * k + 1]), g2 = unpack8(r[4 * k + 2]), g3 = unpack8(r[4 * k + 3]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[k].v[e] += g0.v[e] + g1.v[e] + g2.v[e] + g3.v[e];
+          }
+        }
+      // ---- everything else, raw ----
+      uint4 Xr[4], Yr[4], Gr[NS > 0 ? NS : 1][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { Xr[k] = make_uint4(0, 0, 0, 0); Yr[k] = make_uint4(0, 0, 0, 0); }
+      if (need_x) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) Xr[k] = __ldg(reinterpret_cast<const uint4*>(p.x + pix[k] * p.x_cp + c0));
+      }
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const CSrc& S = p.src[s];
+        const int mode = (MODES >> (2 * s)) & 3;
+        if (mode == MG_SEG_SAME) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) Gr[s][k] = __ldg(reinterpret_cast<const uint4*>(S.g + pix[k] * S.cp + S.c_off + c0));
+        } else if (mode == MG_SEG_POOL) {
+          Gr[s][0] = __ldg(reinterpret_cast<const uint4*>(S.g + (((int64_t)n * S.H + by) * S.W + bx) * S.cp + S.c_off + c0));
+        }
+      }
+      if (has_sums) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) Yr[k] = __ldg(reinterpret_cast<const uint4*>(p.bnx + pix[k] * p.bn_cp + c0));
+      }
+      // ---- accumulate: up-sampled sources first (above), then the others in list order.  The order is a property of the
+      // source-mode list alone (never of the launch, the lane or the run), so results stay reproducible; against the generic
+      // kernel the fp32 sum of the <= 4 sources may differ in its last bit for lists with an up-sampled source ----
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        const int mode = (MODES >> (2 * s)) & 3;
+        if (mode == MG_SEG_SAME) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const V8 g = unpack8(Gr[s][k]);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[k].v[e] += g.v[e];
+          }
+        } else if (mode == MG_SEG_POOL) {
+          const V8 g = unpack8(Gr[s][0]);
+          V8 X[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) X[k] = unpack8(Xr[k]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float best = -INFINITY; int bi = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (valid[k]) { const float v = X[k].v[e]; if (v > best || v != v) { best = v; bi = k; } }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (bi == k) acc[k].v[e] += g.v[e];
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (valid[k]) {
+          const V8 xk = unpack8(Xr[k]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            if (p.relu_mask && !(xk.v[e] > 0.f)) acc[k].v[e] = 0.f;
+            if (c0 + e >= p.C) acc[k].v[e] = 0.f;
+          }
+          if (has_sums) {
+            const V8 yr = unpack8(Yr[k]);
 #pragma unroll
             for (int e = 0; e < 8; ++e) { sd[e] += acc[k].v[e]; sdx[e] = fmaf(acc[k].v[e], yr.v[e], sdx[e]); }
           }
@@ -622,6 +770,8 @@ bool bf16_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid* b
   const int64_t items = (int64_t)p.N * p.Hb * p.Wb * V;
   static int spec = -1;
   if (spec < 0) { const char* e = getenv("MGCONV_COMBINE_SPEC"); spec = e ? atoi(e) : 1; }
+  static int fast = -1;   // batched-load form of the specialised kernels (MGCONV_COMBINE_FAST=0: the older form, for A/B timing)
+  if (fast < 0) { const char* e = getenv("MGCONV_COMBINE_FAST"); fast = e ? atoi(e) : 1; }
   int code = 0;
   for (int s = 0; s < n_src; ++s) code |= (src[s].mode & 3) << (2 * s);
   const size_t smem = sums ? 2 * 256 * 8 * sizeof(float) : 0;   // block_channel_sums staging
@@ -629,8 +779,12 @@ bool bf16_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid* b
   // takes the generic kernel
 #define MG_COMBINE_CASE(NSRC, M0, M1, M2, M3)                                                                      \
   if (spec && n_src == NSRC && code == ((M0) | (M1) << 2 | (M2) << 4 | (M3) << 6)) {                                  \
-    mg_launch_pdl(combine_bf16_kernel<NSRC, ((M0) | (M1) << 2 | (M2) << 4 | (M3) << 6)>, dim3(reduce_grid(ctx, items, 2)), \
-                  dim3(256), smem, ctx->stream, p);                                                                  \
+    if (fast && (M0) != 3)                                                                                           \
+      mg_launch_pdl(combine_fast_kernel<NSRC, ((M0) | (M1) << 2 | (M2) << 4 | (M3) << 6)>, dim3(reduce_grid(ctx, items, 2)), \
+                    dim3(256), smem, ctx->stream, p);                                                                \
+    else                                                                                                             \
+      mg_launch_pdl(combine_bf16_kernel<NSRC, ((M0) | (M1) << 2 | (M2) << 4 | (M3) << 6)>, dim3(reduce_grid(ctx, items, 2)), \
+                    dim3(256), smem, ctx->stream, p);                                                                \
     return true;                                                                                                     \
   }
   MG_COMBINE_CASE(1, 0, 0, 0, 0)

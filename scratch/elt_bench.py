@@ -18,8 +18,8 @@ dcat1, dcat2, dfin = G(Cc + Cc // 2, H, cp=Cc + Cc // 2), G(Cc + Cc // 2 + Cc //
 D, Gg = G(Cc, H), G(Cc, H)
 src = (mg_grad_src * 3)()
 src[0].g, src[0].c_offset, src[0].mode = dcat1.g(), 0, MG_SEG_SAME
-src[1].g, src[1].c_offset, src[1].mode = dcat2.g(), 0, MG_SEG_POOL
-src[2].g, src[2].c_offset, src[2].mode = dfin.g(), 0, MG_SEG_SAME
+src[1].g, src[1].c_offset, src[1].mode = dfin.g(), 0, MG_SEG_SAME
+src[2].g, src[2].c_offset, src[2].mode = dcat2.g(), 0, MG_SEG_POOL
 coef = torch.rand(3 * y.Cp, device="cuda"); mean = torch.rand(y.Cp, device="cuda"); inv = torch.rand(y.Cp, device="cuda")
 gam = torch.rand(Cc, device="cuda"); dg = torch.zeros(Cc, device="cuda"); db = torch.zeros(Cc, device="cuda"); cdb = torch.zeros(Cc, device="cuda")
 yraw = G(Cc, H)
