@@ -452,6 +452,7 @@ __global__ void __launch_bounds__(256, 2) combine_fast_kernel(const __grid_const
         }
       // ---- everything else, raw ----
       uint4 Xr[4], Yr[4], Gr[NS > 0 ? NS : 1][4];
+      uint2 Cd[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) { Xr[k] = make_uint4(0, 0, 0, 0); Yr[k] = make_uint4(0, 0, 0, 0); }
       if (need_x) {
@@ -467,6 +468,16 @@ __global__ void __launch_bounds__(256, 2) combine_fast_kernel(const __grid_const
           for (int k = 0; k < 4; ++k) Gr[s][k] = __ldg(reinterpret_cast<const uint4*>(S.g + pix[k] * S.cp + S.c_off + c0));
         } else if (mode == MG_SEG_POOL) {
           Gr[s][0] = __ldg(reinterpret_cast<const uint4*>(S.g + (((int64_t)n * S.H + by) * S.W + bx) * S.cp + S.c_off + c0));
+        } else if (mode == 3) {
+          // SpatialMaxPooling(3,3,2,2,1,1) of the stem: the 2x2 block lies in the four windows (by + wy, bx + wx); window w of the
+          // block is loaded once (gradient + arg-max codes) instead of once per pixel it covers
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int oy = min(by + (w >> 1), S.H - 1), ox = min(bx + (w & 1), S.W - 1);
+            const int64_t o = ((int64_t)n * S.H + oy) * S.W + ox;
+            Gr[s][w] = __ldg(reinterpret_cast<const uint4*>(S.g + o * S.cp + S.c_off + c0));
+            Cd[w] = __ldg(reinterpret_cast<const uint2*>(S.aux + o * S.cp + S.c_off + c0));
+          }
         }
       }
       if (has_sums) {
@@ -500,6 +511,27 @@ __global__ void __launch_bounds__(256, 2) combine_fast_kernel(const __grid_const
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               if (bi == k) acc[k].v[e] += g.v[e];
+          }
+        } else if (mode == 3) {
+          const CSrc& S = p.src[s];
+          // pixel (dy, dx) of the block lies in window (wy, wx) iff (wy == 0 || dy == 1) && (wx == 0 || dx == 1), at tap
+          // (dy + 1 - 2 wy, dx + 1 - 2 wx); windows in (oy, ox) order as the generic kernel visits them
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int wy = w >> 1, wx = w & 1;
+            if (by + wy >= S.H || bx + wx >= S.W) continue;
+            const V8 g = unpack8(Gr[s][w]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int dy = k >> 1, dx = k & 1;
+              if ((wy == 1 && dy == 0) || (wx == 1 && dx == 0)) continue;
+              const int want = (dy + 1 - 2 * wy) * 3 + (dx + 1 - 2 * wx);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int cd = ((e < 4 ? Cd[w].x : Cd[w].y) >> (8 * (e & 3))) & 0xFF;
+                if (cd == want) acc[k].v[e] += g.v[e];
+              }
+            }
           }
         }
       }
@@ -608,15 +640,22 @@ __global__ void __launch_bounds__(256) pool3_bf16_kernel(const bf16* __restrict_
   float best[8]; int bc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; bc[e] = -1; }
-  for (int ky = 0; ky < 3; ++ky)
-    for (int kx = 0; kx < 3; ++kx) {
-      const int y = 2 * oy - 1 + ky, x = 2 * ox - 1 + kx;
-      if (y < 0 || y >= H || x < 0 || x >= W) continue;
-      const V8 v = ld8(in + (((int64_t)n * H + y) * W + x) * cp + c0);
+  // the nine taps are loaded before the first comparison (taps outside the image re-read a clamped pixel and are skipped)
+  uint4 r[9];
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (v.v[e] > best[e] || v.v[e] != v.v[e] || bc[e] < 0) { best[e] = v.v[e]; bc[e] = ky * 3 + kx; }
-    }
+  for (int t = 0; t < 9; ++t) {
+    const int y = min(max(2 * oy - 1 + t / 3, 0), H - 1), x = min(max(2 * ox - 1 + t % 3, 0), W - 1);
+    r[t] = __ldg(reinterpret_cast<const uint4*>(in + (((int64_t)n * H + y) * W + x) * cp + c0));
+  }
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int y = 2 * oy - 1 + t / 3, x = 2 * ox - 1 + t % 3;
+    if (y < 0 || y >= H || x < 0 || x >= W) continue;
+    const V8 v = unpack8(r[t]);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (v.v[e] > best[e] || v.v[e] != v.v[e] || bc[e] < 0) { best[e] = v.v[e]; bc[e] = t; }
+  }
   V8 b;
 #pragma unroll
   for (int e = 0; e < 8; ++e) b.v[e] = (c0 + e < C) ? best[e] : 0.f;
@@ -779,7 +818,7 @@ bool bf16_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid* b
   // takes the generic kernel
 #define MG_COMBINE_CASE(NSRC, M0, M1, M2, M3)                                                                      \
   if (spec && n_src == NSRC && code == ((M0) | (M1) << 2 | (M2) << 4 | (M3) << 6)) {                                  \
-    if (fast && (M0) != 3)                                                                                           \
+    if (fast)                                                                                                        \
       mg_launch_pdl(combine_fast_kernel<NSRC, ((M0) | (M1) << 2 | (M2) << 4 | (M3) << 6)>, dim3(reduce_grid(ctx, items, 2)), \
                     dim3(256), smem, ctx->stream, p);                                                                \
     else                                                                                                             \

@@ -395,18 +395,42 @@ __global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __
 }
 
 // dw[co][ci][tap] += gscale * sum_z partial[z][tap][co][ci]   (z in increasing order: deterministic)
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Cout, int Ccat, float* __restrict__ dw,
+// A CTA owns blockDim.x consecutive (co, ci) pairs x blockDim.y tap lanes: the partial planes are read coalesced along ci, the
+// sums are transposed through shared memory and dw is updated as ONE contiguous range of blockDim.x * KK floats (Torch's
+// [Cout][Ccat][k][k] layout puts the taps innermost: a thread-per-element store would be a 4-byte write every KK * 4 bytes).
+__global__ void __launch_bounds__(288) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int Cout, int Ccat, float* __restrict__ dw,
                                                            float gscale, int KK) {
   pdl_launch();
   pdl_wait();
-  const int64_t plane = (int64_t)KK * Cout * Ccat;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // index in [tap][co][ci] order (coalesced reads)
-  if (i >= plane) return;
-  float s = 0.f;
-  for (int z = 0; z < splits; ++z) s += partial[(size_t)z * plane + i];
-  const int ci = (int)(i % Ccat); const int64_t q = i / Ccat;
-  const int co = (int)(q % Cout); const int tap = (int)(q / Cout);
-  dw[((size_t)co * Ccat + ci) * KK + tap] += gscale * s;
+  extern __shared__ float s_t[];   // [blockDim.x][KK]
+  const int64_t pairs = (int64_t)Cout * Ccat;
+  const int64_t q0 = (int64_t)blockIdx.x * blockDim.x, q = q0 + threadIdx.x;
+  if (q < pairs) {
+    const size_t zstride = (size_t)KK * pairs;
+    for (int tap = threadIdx.y; tap < KK; tap += blockDim.y) {
+      const float* src = partial + (size_t)tap * pairs + q;
+      float s = 0.f;
+      int z = 0;
+      for (; z + 4 <= splits; z += 4) {   // four loads in flight, added in split order
+        const float a = src[(size_t)z * zstride], b = src[(size_t)(z + 1) * zstride], c = src[(size_t)(z + 2) * zstride], d = src[(size_t)(z + 3) * zstride];
+        s += a; s += b; s += c; s += d;
+      }
+      for (; z < splits; ++z) s += src[(size_t)z * zstride];
+      s_t[threadIdx.x * KK + tap] = s;
+    }
+  }
+  __syncthreads();
+  const int64_t n_out = min((int64_t)blockDim.x, pairs - q0) * KK;
+  float* dst = dw + q0 * KK;
+  const int nthr = blockDim.x * blockDim.y;
+  for (int64_t j = threadIdx.y * blockDim.x + threadIdx.x; j < n_out; j += nthr) dst[j] += gscale * s_t[j];
+}
+
+static inline cudaError_t launch_wgrad_reduce(mg_ctx* ctx, const float* partial, int z, int Cout, int Ccat, float* dw, float gscale, int KK) {
+  const int tl = KK <= 9 ? KK : 8;          // tap lanes
+  const int pb = KK == 1 ? 256 : 32;        // pairs per CTA
+  const int64_t pairs = (int64_t)Cout * Ccat;
+  return mg_launch_pdl(wgrad_reduce_kernel, dim3((unsigned)mg_cdiv(pairs, pb)), dim3(pb, tl), (size_t)pb * KK * sizeof(float), ctx->stream, partial, z, Cout, Ccat, dw, gscale, KK);
 }
 
 }  // namespace
@@ -512,7 +536,7 @@ static int wgrad_halo(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g, floa
   MG_CUDA(ctx, mg_launch_pdl(umma_wgrad_halo_kernel, grid, dim3(WH_THREADS), (size_t)(S * stage_bytes + 1024), ctx->stream, p));
   MG_CHECK_LAUNCH(ctx);
   ctx->tc_launches++;
-  MG_CUDA(ctx, mg_launch_pdl(wgrad_reduce_kernel, dim3((unsigned)mg_cdiv((int64_t)plane, 256)), dim3(256), 0, ctx->stream, (const float*)p.partial, z, p.Cout, p.Ccat, dw, gscale, 9));
+  MG_CUDA(ctx, launch_wgrad_reduce(ctx, p.partial, z, p.Cout, p.Ccat, dw, gscale, 9));
   MG_CHECK_LAUNCH(ctx);
   return MG_OK;
 }
@@ -586,7 +610,7 @@ int umma_conv_backward_weight(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid*
   umma_wgrad_kernel<<<grid, W_THREADS, S * stage_bytes + 1024, ctx->stream>>>(p);
   MG_CHECK_LAUNCH(ctx);
   ctx->tc_launches++;
-  MG_CUDA(ctx, mg_launch_pdl(wgrad_reduce_kernel, dim3((unsigned)mg_cdiv((int64_t)plane, 256)), dim3(256), 0, ctx->stream, (const float*)p.partial, z, p.Cout, p.Ccat, dw, gscale, KK));
+  MG_CUDA(ctx, launch_wgrad_reduce(ctx, p.partial, z, p.Cout, p.Ccat, dw, gscale, KK));
   MG_CHECK_LAUNCH(ctx);
   if (dbias) return simt_dbias(ctx, g, d->Cout, dbias, gscale);
   return MG_OK;
