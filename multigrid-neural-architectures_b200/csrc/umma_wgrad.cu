@@ -433,6 +433,190 @@ static inline cudaError_t launch_wgrad_reduce(mg_ctx* ctx, const float* partial,
   return mg_launch_pdl(wgrad_reduce_kernel, dim3((unsigned)mg_cdiv(pairs, pb)), dim3(pb, tl), (size_t)pb * KK * sizeof(float), ctx->stream, partial, z, Cout, Ccat, dw, gscale, KK);
 }
 
+
+// ---------------------------------------------------------------- stem weight gradient -------------
+// accGradParameters of cudnn.SpatialConvolution(3, C, 7,7, 2,2, 3,3) (models/ilsvrc/rnmg.lua:180), C <= 64.  Same staging as the
+// forward stem kernel (umma_conv.cu): a tile is 16 x 8 output pixels, the copy engine loads its 37 x 21-pixel input patch and
+// four warps split it into the even / odd column planes.  GEMM per tile: D[co][(tap, ch)] += sum over the 128 pixels of
+// g[pixel][co] * x[pixel + tap][ch].  A = the g tile (128 rows of 128 bytes, MN-major SW128, loaded by the copy engine; channels
+// beyond Cp arrive as zeros).  B = the patch IN PLACE: in a plane the taps kx, kx+2, kx+4, kx+6 of an output pixel are four
+// CONSECUTIVE 16-byte pixels, and the next output pixel is the same window shifted by one pixel -- so an MN-major no-swizzle
+// descriptor with SBO = 16 bytes (next tap: core matrices that overlap) and LBO = two plane rows (the next eight pixels = the next
+// tile row) reads the Toeplitz operand [16 pixels][4 taps x 8 channels] without any gather.  14 accumulators (7 kernel rows x 2
+// parities) of 32 columns live in TMEM over ALL tiles of the (persistent) CTA; the partial sums are reduced in a fixed order.
+// The MMAs are M = 64 (Cout <= 64): D row m sits in TMEM lane (m % 16) + 32 * (m / 16).
+constexpr int SG_PC = 11, SG_PR = 37, SG_ROW = SG_PC * 16, SG_PLANE = 6592, SG_SLOT = 13312, SG_RAW_COLS = 21, SG_RAW = 12544, SG_G = 16384;
+constexpr int SG_STAGE = SG_G + SG_SLOT + SG_RAW, SG_MAX_RING = 5, SG_THREADS = 320;   // 4 epilogue warps, TMA, MMA, 4 de-interleave warps
+
+struct StemWParams {
+  CUtensorMap tmap_x;   // kind 2: input patches
+  CUtensorMap tmap_g;   // kind 3: 16 x 8 x 64-channel tiles of the gradient
+  int tiles_x, tiles_y, n_tiles_total, ring;
+  int Cout, Cin;
+  float* partial;       // [gridDim.x][Cout][Cin][49]
+};
+
+__global__ void __launch_bounds__(SG_THREADS, 1) umma_stem_wgrad_kernel(const __grid_constant__ StemWParams p) {
+  pdl_launch();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t r_full[SG_MAX_RING], r_empty[SG_MAX_RING], a_full[SG_MAX_RING], a_empty[SG_MAX_RING], g_full[SG_MAX_RING], tmem_full;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NA = p.ring;
+  uint8_t* g_smem = smem;                                  // ring of g tiles (1024-aligned: SW128)
+  uint8_t* a_smem = g_smem + (size_t)NA * SG_G;            // ring of plane pairs
+  uint8_t* r_smem = a_smem + (size_t)NA * SG_SLOT;         // ring of raw patches
+  const int n_my = (p.n_tiles_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (tid == 0) {
+    for (int s = 0; s < NA; ++s) {
+      mbar_init(&r_full[s], 1); mbar_init(&r_empty[s], 128); mbar_init(&a_full[s], 128); mbar_init(&a_empty[s], 1); mbar_init(&g_full[s], 1);
+    }
+    mbar_init(&tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 5) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 4 && lane == 0) { tma_prefetch_desc(&p.tmap_x); tma_prefetch_desc(&p.tmap_g); }
+  // column 10 of the odd planes belongs to the non-existent tap kx = 7 (its accumulator columns are never read): finite values
+  for (int i = tid; i < NA * SG_PR; i += SG_THREADS) {
+    const int sl = i / SG_PR, r = i - sl * SG_PR;
+    *reinterpret_cast<uint4*>(a_smem + (size_t)sl * SG_SLOT + SG_PLANE + r * SG_ROW + 10 * 16) = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async();
+  pdl_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp < 4) {
+    // ================= epilogue: 14 accumulators -> this CTA's partial dW, Torch layout [co][ci][ky][kx] =================
+    mbar_wait(&tmem_full, 0);
+    tc_fence_after();
+    // M = 64: row m of D lives in TMEM lane (m % 16) + 32 * (m / 16) -- the lower half of every warp's 32-lane quarter
+    const int co = warp * 16 + lane;
+    const bool co_ok = lane < 16 && co < p.Cout;
+    float* out = p.partial + ((size_t)blockIdx.x * p.Cout + (co_ok ? co : 0)) * p.Cin * 49;
+    {
+      for (int a = 0; a < 14; ++a) {
+        const int ky = a >> 1, par = a & 1;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t acc[16];
+          tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * 32 + h * 16), acc);
+          tc_wait_ld();
+          if (co_ok) {
+#pragma unroll
+            for (int x = 0; x < 16; ++x) {
+              const int j = h * 2 + (x >> 3), ci = x & 7, kx = 2 * j + par;
+              if (kx < 7 && ci < p.Cin) out[ci * 49 + ky * 7 + kx] = n_my > 0 ? __uint_as_float(acc[x]) : 0.f;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // ================= producer: patch + g tile per tile =================
+    if (lane == 0) {
+      Ring rr(NA);
+      for (int it = 0; it < n_my; ++it, rr.next()) {
+        const int tile = blockIdx.x + it * gridDim.x;
+        const int n = tile / tiles_per_img, tr = tile - n * tiles_per_img;
+        const int ty = tr / p.tiles_x, tx = tr - ty * p.tiles_x;
+        const int s = rr.idx;
+        if (it >= NA) mbar_wait(&r_empty[s], rr.phase ^ 1u);
+        mbar_arrive_expect_tx(&r_full[s], (uint32_t)(SG_PR * SG_RAW_COLS * 16));
+        tma_load_4d(smem_u32(r_smem + (size_t)s * SG_RAW), &p.tmap_x, &r_full[s], 0, 2 * tx * 8 - 3, 2 * ty * 16 - 3, n);
+        if (it >= NA) mbar_wait(&a_empty[s], rr.phase ^ 1u);     // the MMAs that read this g tile have completed
+        mbar_arrive_expect_tx(&g_full[s], (uint32_t)SG_G);
+        tma_load_4d(smem_u32(g_smem + (size_t)s * SG_G), &p.tmap_g, &g_full[s], 0, tx * 8, ty * 16, n);
+      }
+    }
+  } else if (warp == 5) {
+    // ================= MMA issuer: per tile 8 K steps (two tile rows each) x 14 accumulators =================
+    const bool leader = elect_one();
+    // M = 64 (the output channels), N = 32, both operands MN-major: half the shared-memory read of an M = 128 instruction per MMA
+    // (the A tile is re-read by every one of the 14 MMAs of a K step: the kernel is bound by that read, not by the MMA rate)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(64 >> 4) << 24);
+    // B: MN-major, no swizzle: SBO (MN direction, next tap of the same parity) = 16 bytes, LBO (K direction, next 8 pixels) = 2 plane rows
+    const uint32_t b_hi = (16u >> 4) | (1u << 14);
+    const uint32_t b_lbo = ((uint32_t)(2 * SG_ROW) >> 4) << 16;
+    Ring ra(NA);
+    for (int it = 0; it < n_my; ++it, ra.next()) {
+      const int s = ra.idx;
+      mbar_wait(&a_full[s], ra.phase);
+      mbar_wait(&g_full[s], ra.phase);
+      tc_fence_after();
+      const uint32_t a_lo0 = desc_lo_mn_sw128(smem_u32(g_smem + (size_t)s * SG_G), 0);
+      const uint32_t pl = smem_u32(a_smem + (size_t)s * SG_SLOT);
+      if (leader) {
+#pragma unroll 1
+        for (int r = 0; r < 8; ++r) {
+          const uint32_t a_lo = a_lo0 + (uint32_t)r * 128u;                     // 16 pixels = 2048 bytes
+          const uint32_t row0 = pl + (uint32_t)(4 * r) * SG_ROW;                // plane row of output row 2r, tap row 0
+#pragma unroll
+          for (int a = 0; a < 14; ++a) {
+            const uint32_t baddr = row0 + (uint32_t)((a >> 1) * SG_ROW + (a & 1) * SG_PLANE);
+            tc_mma_bf16_lohi2(tmem_base + (uint32_t)(a * 32), a_lo, DESC_HI_SW128, ((baddr >> 4) & 0x3FFFu) | b_lbo, b_hi, idesc, (uint32_t)((it | r) != 0));
+          }
+        }
+        tc_commit(&a_empty[s]);
+      }
+    }
+    if (leader) tc_commit(&tmem_full);
+  } else {
+    // ================= de-interleave: raw patch -> even / odd column planes =================
+    const int dt = tid - 6 * 32;
+    Ring rr(NA);
+    for (int it = 0; it < n_my; ++it, rr.next()) {
+      const int s = rr.idx;
+      mbar_wait(&r_full[s], rr.phase);
+      if (it >= NA) mbar_wait(&a_empty[s], rr.phase ^ 1u);
+      const uint8_t* raw = r_smem + (size_t)s * SG_RAW;
+      uint8_t* plp = a_smem + (size_t)s * SG_SLOT;
+      for (int i = dt; i < SG_PR * SG_RAW_COLS; i += 128) {
+        const int r = i / SG_RAW_COLS, x = i - r * SG_RAW_COLS;
+        const uint4 v = *reinterpret_cast<const uint4*>(raw + (size_t)i * 16);
+        *reinterpret_cast<uint4*>(plp + (x & 1) * SG_PLANE + r * SG_ROW + (x >> 1) * 16) = v;
+      }
+      fence_proxy_async();
+      mbar_arrive(&a_full[s]);
+      mbar_arrive(&r_empty[s]);
+    }
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// dw[i] += gscale * sum_z partial[z][i]: blockDim.y lanes each sum every blockDim.y-th split in increasing order, the lanes are
+// added in lane order (a fixed tree: deterministic)
+__global__ void __launch_bounds__(256) stem_wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int n, float* __restrict__ dw, float gscale) {
+  pdl_launch();
+  pdl_wait();
+  __shared__ float s_red[8][32];
+  const int i = blockIdx.x * 32 + threadIdx.x;
+  float s = 0.f;
+  if (i < n)
+    for (int z = threadIdx.y; z < splits; z += 8) s += partial[(size_t)z * n + i];
+  s_red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && i < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) t += s_red[l][threadIdx.x];
+    dw[i] += gscale * t;
+  }
+}
+
 }  // namespace
 
 int simt_dbias(mg_ctx* ctx, const mg_grid* g, int Cout, float* dbias, float gscale);
@@ -541,7 +725,52 @@ static int wgrad_halo(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g, floa
   return MG_OK;
 }
 
+static bool wgrad_stem_applies(const mg_conv_desc* d, const mg_grid* g) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("MGCONV_STEM_WGRAD"); on = e ? atoi(e) : 1; }
+  if (!on || d->ksize != 7 || d->stride != 2 || d->pad != 3 || d->n_seg != 1 || d->seg_mode[0] != MG_SEG_SAME) return false;
+  const mg_grid& x = d->seg[0];
+  return x.Cp == 8 && x.H == d->H && x.W == d->W && d->Cout <= 64 && g->Cp % 8 == 0 && !x.scale;
+}
+
+static int wgrad_stem(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g, float* dw, float gscale) {
+  StemWParams p;
+  memset(&p, 0, sizeof(p));
+  const mg_grid& x = d->seg[0];
+  int rc = mg_tensor_map(ctx, x.data, x.N, x.H, x.W, 8, 2, SG_RAW_COLS, &p.tmap_x);
+  if (rc) return rc;
+  rc = mg_tensor_map(ctx, g->data, g->N, g->H, g->W, g->Cp, 3, 8, &p.tmap_g);
+  if (rc) return rc;
+  p.tiles_x = (g->W + 7) / 8; p.tiles_y = (g->H + 15) / 16;
+  p.n_tiles_total = g->N * p.tiles_x * p.tiles_y;
+  p.Cout = d->Cout; p.Cin = x.C;
+  const int grid = std::max(1, std::min(ctx->num_sms, p.n_tiles_total));
+  p.ring = std::max(2, std::min(SG_MAX_RING, (p.n_tiles_total + grid - 1) / grid));
+  const int n = d->Cout * x.C * 49;
+  void* ws = nullptr;
+  rc = mg_ctx_workspace(ctx, (size_t)grid * n * sizeof(float), &ws);
+  if (rc) return rc;
+  p.partial = (float*)ws;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MG_CUDA(ctx, cudaFuncSetAttribute(umma_stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SG_MAX_RING * SG_STAGE + 1024));
+    attr_set = true;
+  }
+  MG_CUDA(ctx, mg_launch_pdl(umma_stem_wgrad_kernel, dim3(grid), dim3(SG_THREADS), (size_t)(p.ring * SG_STAGE + 1024), ctx->stream, p));
+  MG_CHECK_LAUNCH(ctx);
+  ctx->tc_launches++;
+  MG_CUDA(ctx, mg_launch_pdl(stem_wgrad_reduce_kernel, dim3((unsigned)mg_cdiv(n, 32)), dim3(32, 8), 0, ctx->stream, (const float*)p.partial, grid, n, dw, gscale));
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
 int umma_conv_backward_weight(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g, float* dw, float* dbias, float gscale) {
+  if (wgrad_stem_applies(d, g)) {
+    int rc = wgrad_stem(ctx, d, g, dw, gscale);
+    if (rc) return rc;
+    if (dbias) return simt_dbias(ctx, g, d->Cout, dbias, gscale);
+    return MG_OK;
+  }
   if (wgrad_halo_applies(d)) {
     int rc = wgrad_halo(ctx, d, g, dw, gscale);
     if (rc) return rc;

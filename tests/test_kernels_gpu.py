@@ -345,6 +345,21 @@ def test_stem_kernel_shapes(case, fused):
     assert torch.allclose(sv[Cout:], (yn * yn).sum((0, 2, 3)), rtol=1e-5, atol=1e-2)
     if N * H * W < 20000:   # small cases also against the numpy oracle
         assert max_rel(gy.nchw(), O.conv_forward(bf16_round(x), w, b, 2, 3)) <= TOL[ffi.MG_BF16]
+    # weight gradient on the dedicated kernel (the patch read in place as a Toeplitz operand): against an independent fp64
+    # computation on the same bf16 inputs, accumulating twice (accGradParameters adds into gradWeight)
+    g = rnd(N, Cout, Ho, Wo)
+    gg = Grid(ffi.MG_BF16, N, Cout, Ho, Wo, g)
+    dw, db = torch.zeros_like(wd), torch.zeros_like(bd)
+    tc0 = ctx.tc_launches()
+    ctx.call("mg_conv_backward_weight", C.byref(d), C.byref(gg.g()), ptr(dw), ptr(db), 1.0)
+    if Cout <= 64:
+        assert ctx.tc_launches() - tc0 == 1, "the stem weight gradient must run on its tensor-core kernel"
+    ctx.call("mg_conv_backward_weight", C.byref(d), C.byref(gg.g()), ptr(dw), ptr(db), 0.5)
+    torch.cuda.synchronize()
+    gd = torch.from_numpy(bf16_round(g)).cuda().double()
+    dw_ref = torch.nn.grad.conv2d_weight(xin.double(), w.shape, gd, stride=2, padding=3) * 1.5
+    assert float((dw.double() - dw_ref).abs().max() / dw_ref.abs().max()) <= 1e-4, "fp32 accumulation of exact bf16 products"
+    assert torch.allclose(db.double(), gd.sum((0, 2, 3)) * 1.5, rtol=1e-4, atol=1e-3)
     ctx.close()
 
 
