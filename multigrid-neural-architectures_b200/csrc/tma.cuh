@@ -55,12 +55,20 @@ static inline int mg_tensor_map(mg_ctx* ctx, const void* ptr, int N, int H, int 
   if (it != tc->map.end()) { *out = it->second; return MG_OK; }
   mg_encode_tiled_fn enc = mg_encode_tiled();
   MG_REQUIRE(ctx, enc != nullptr, MG_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-  MG_REQUIRE(ctx, ((uintptr_t)ptr & 15) == 0 && Cp % 8 == 0, MG_ERR_INVALID_ARG, "tensor map: base %p / Cp %d not 16-byte aligned", ptr, Cp);
+  MG_REQUIRE(ctx, ((uintptr_t)ptr & 15) == 0 && (Cp % 8 == 0 || kind == 5), MG_ERR_INVALID_ARG, "tensor map: base %p / Cp %d not 16-byte aligned", ptr, Cp);
   MG_REQUIRE(ctx, box_w >= 1 && box_w <= 256, MG_ERR_UNSUPPORTED, "tensor map: box of %d slots", box_w);
   CUtensorMap tm;
   CUresult r;
   const cuuint64_t row = (cuuint64_t)Cp * 2;
-  if (kind == 4) {
+  if (kind == 5) {
+    // packed weight image as rows of 128 bytes (N = total rows, box_w = rows per copy): the pair kernels load half a stage per CTA
+    cuuint64_t dims[2] = {64, (cuuint64_t)N};
+    cuuint64_t strides[1] = {128};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_w};
+    cuuint32_t es[2] = {1, 1};
+    r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else if (kind == 4) {
     // whole-image boxes: (H+1)*(W+1) slots per image divide the tile (7 x 7 grids: 64 slots), so ONE box of box_w images is the
     // tile -- pad column, pad row and images beyond the batch are out-of-bounds zeros
     cuuint64_t dims[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -131,6 +139,38 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, uint32_t src
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// CTA-pair (cta_group::2) variants: the copy lands in the executing CTA's shared memory, the completion bytes are counted on the
+// barrier at the same offset of the pair's EVEN CTA (the one that issues the MMAs): bit 24 of a shared::cluster address is the
+// CTA's parity within the pair (cute: Sm100MmaPeerBitMask)
+constexpr uint32_t MG_PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+               "l"(tm), "r"((uint32_t)__cvta_generic_to_shared(bar) & MG_PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+               "l"(tm), "r"((uint32_t)__cvta_generic_to_shared(bar) & MG_PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(tm), "r"((uint32_t)__cvta_generic_to_shared(bar) & MG_PEER_BIT_MASK), "r"(c0), "r"(c1)
+               : "memory");
+}
+// slot rows [r0, r0 + nr) like tma_load_rows, without arming the barrier (the pair's even CTA arms it with the bytes of both CTAs)
+__device__ __forceinline__ void tma_load_rows_pair(const CUtensorMap* tm, int up, uint32_t dst, uint64_t* bar, int c0, int r0, int nr, int W, int Hp, int lane) {
+  const int Wp = W + 1;
+  for (int i = lane; i < nr; i += 32) {
+    const int R = r0 + i;
+    int n = -1, y = 0;
+    if (R >= 0) { n = R / Hp; y = R - n * Hp; }
+    const uint32_t d = dst + (uint32_t)(i * Wp) * 128u;
+    if (up) tma_load_5d_pair(d, tm, bar, c0, 0, 0, y >> 1, n);
+    else tma_load_4d_pair(d, tm, bar, c0, 0, y, n);
+  }
+}
 
 // floor(a / b) for b > 0 and any a
 __device__ __forceinline__ int floordiv(int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }

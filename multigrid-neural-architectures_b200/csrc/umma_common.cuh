@@ -89,6 +89,41 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t da, uint64
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- CTA pairs (cta_group::2): one MMA instruction spans the two SMs of a TPC -- each CTA supplies its own 128 rows of A and half
+// of B (N / 2 rows), D is 128 lanes x N columns in each CTA's TMEM; issued by the pair's even CTA only
+__device__ __forceinline__ void tc_mma_bf16_lohi_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair once all MMAs issued so far have completed
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// wait with cluster-scope acquire: the completion bytes / arrivals come from the peer CTA's copy engine and tensor core
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  for (uint32_t it = 0; it < (1u << 20); ++it) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(20000u)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
 // Position in a ring of n slots walked once per loop iteration k: idx = k % n, phase = (k / n) & 1, without the integer
 // divisions (ring sizes are run-time values; in the single-thread issue loops each emulated division is ~20 dependent
 // instructions, several per pipeline stage).

@@ -391,13 +391,14 @@ struct HParams {
   mg_sum* stats;      // forward: per-channel (sum y, sum y^2) of the STORED bf16 output accumulated here ([2][c_stats]), or null
   int c_stats;
   int m_tiles;        // persistent kernel: 128-slot tiles in total
+  CUtensorMap tmap_w; // pair kernels: the packed weight image as rows of 128 bytes (tma.cuh kind 5)
 };
 
 // zero the pad column (slot x == W of every row) of `nbuf` halo buffers: the up-sampling box writes only the W valid slots
-__device__ __forceinline__ void zero_pad_column(uint8_t* a_smem, int nbuf, int halo_bytes, int nr_max, int Wp, int tid, int nthreads) {
+__device__ __forceinline__ void zero_pad_column(uint8_t* a_smem, int nbuf, int halo_bytes, int nr_max, int Wp, int tid, int nthreads, int org = 0) {
   for (int i = tid; i < nbuf * nr_max * 8; i += nthreads) {
     const int q = i & 7, row = (i >> 3) % nr_max, buf = (i >> 3) / nr_max;
-    *reinterpret_cast<uint4*>(a_smem + (size_t)buf * halo_bytes + (size_t)(row * Wp + Wp - 1) * 128 + q * 16) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(a_smem + (size_t)buf * halo_bytes + (size_t)(org + row * Wp + Wp - 1) * 128 + q * 16) = make_uint4(0, 0, 0, 0);
   }
   fence_proxy_async();
 }
@@ -613,6 +614,211 @@ __global__ void __launch_bounds__(32 * (4 * MT + 3), MT == 1 ? 4 : 2) umma_conv_
   if (warp == M_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+
+// ---------------------------------------------------------------- CTA-pair halo kernel ----------
+// The same operand scheme on tcgen05 CTA pairs (cta_group::2): the two CTAs of a cluster own two consecutive tiles; ONE MMA
+// instruction (M = 256) issued by the even CTA drives the tensor cores of both SMs, each reading its own halo (A) and HALF of the
+// weight stage (N / 2 rows of B) from its own shared memory.  Per SM the weight stream -- what bounds the N >= 128 layers at the
+// chip's L2 -> SM rate -- halves, and the ring holds twice the stages in the same memory.  Every copy of either CTA counts its
+// bytes on the EVEN CTA's barriers (cp.async.bulk.tensor.cta_group::2); tcgen05.commit multicasts the "stage free" / "accumulator
+// complete" arrivals to both CTAs.  The tile's first halo slot sits Wp slots into the buffer in BOTH CTAs (the MMA's A descriptor
+// is one address for the pair), so each CTA lands its rows Wp - off slots in.
+template <int MT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * MT + 3), MT == 1 ? 4 : 2) umma_conv_halo_pair_kernel(const __grid_constant__ HParams p) {
+  constexpr int EPI_WARPS = 4 * MT, A_WARP = EPI_WARPS, B_WARP = EPI_WARPS + 1, M_WARP = EPI_WARPS + 2, NT = 32 * (EPI_WARPS + 3);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[MAX_STAGES], empty_bar[MAX_STAGES], a_full[2], a_empty[2], tmem_full_bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float s_bias[256];
+
+  pdl_launch();
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int S = p.stages;
+  const int b_half_bytes = (p.n_tile >> 1) * 128;              // this CTA's half of a weight stage
+  uint8_t* a_smem = smem;
+  uint8_t* b_smem = smem + (size_t)p.n_abuf * p.halo_bytes;
+  const int t0 = (int)blockIdx.x * (BM * MT);
+  const int ntile = blockIdx.y;
+  const int hs = t0 - p.Wp - 1;
+  const int r0 = floordiv(hs, p.Wp);
+  const int nr = (hs + p.HL - 1) / p.Wp - r0 + 1;
+  const int off = hs - r0 * p.Wp;
+  const int org = p.img_box ? 0 : p.Wp - off;                  // slots: where this CTA's first slot row lands in the buffer
+  const int a_first = p.img_box ? 0 : p.Wp;                    // slots: the tile's first halo slot, the same in both CTAs
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == M_WARP) {   // the same warp of both CTAs allocates the pair's columns
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (warp == A_WARP && lane < p.n_seg) tma_prefetch_desc(&p.tmap[lane]);
+  if (warp == B_WARP && lane == 0) tma_prefetch_desc(&p.tmap_w);
+  if (p.img_box) zero_halo_margins(a_smem, p.n_abuf, p.halo_bytes, p.HL, p.Wp, tid, NT);
+  else if (p.any_up) zero_pad_column(a_smem, p.n_abuf, p.halo_bytes, p.nr_max, p.Wp, tid, NT, org);
+  pdl_wait();
+  for (int c = tid; c < p.n_tile; c += NT) {
+    const int ch = blockIdx.y * p.n_tile + c;
+    s_bias[c] = (p.bias && ch < p.c_bias) ? p.bias[ch] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();     // both CTAs' barriers are initialised before any remote completion can arrive
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < EPI_WARPS) {
+    // ================= epilogue (per CTA: its own 128 * MT rows x all N columns) =================
+    const int row = warp * 32 + lane;
+    uint32_t pix = 0;
+    const bool row_ok = slot_pixel(p, (int64_t)t0 + row, &pix);
+    const int n_base = ntile * p.n_tile;
+    const bool want_stats = p.stats != nullptr;
+    float* s_part = reinterpret_cast<float*>(a_smem);
+    __nv_bfloat16* yrow = p.y + (size_t)pix * p.y_pitch;
+    const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * p.n_tile);
+    mbar_wait_cluster(&tmem_full_bar, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+      uint32_t acc[16];
+      tc_ld16(tacc + (uint32_t)c0, acc);
+      tc_wait_ld();
+      uint32_t pk[2][4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int n0 = n_base + c0 + h * 8;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float a = __uint_as_float(acc[h * 8 + 2 * e]) + s_bias[c0 + h * 8 + 2 * e];
+          const float b = __uint_as_float(acc[h * 8 + 2 * e + 1]) + s_bias[c0 + h * 8 + 2 * e + 1];
+          __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+          pk[h][e] = *reinterpret_cast<uint32_t*>(&t);
+        }
+        if (row_ok && n0 + 8 <= p.c_valid) *reinterpret_cast<uint4*>(yrow + n0) = make_uint4(pk[h][0], pk[h][1], pk[h][2], pk[h][3]);
+      }
+      if (want_stats) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const bool use = row_ok && n_base + c0 + h * 8 + 8 <= p.c_valid;
+          float sv[16];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float ra = use ? __uint_as_float(pk[h][e] << 16) : 0.f, rb = use ? __uint_as_float(pk[h][e] & 0xFFFF0000u) : 0.f;
+            sv[2 * e] = ra; sv[2 * e + 1] = rb;
+            sv[8 + 2 * e] = ra * ra; sv[8 + 2 * e + 1] = rb * rb;
+          }
+          const float tot = warp_reduce_scatter16(sv, lane);
+          if (lane < 16) s_part[(warp * 2 + (lane >> 3)) * 256 + c0 + h * 8 + (lane & 7)] = tot;
+        }
+      }
+    }
+    tc_fence_before();
+    if (want_stats) {
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * MT) : "memory");
+      for (int c = tid; c < p.n_tile; c += 128 * MT) {
+        const int ch = n_base + c;
+        if (ch < p.c_stats) {
+          long long ah = 0, al = 0, bh = 0, bl = 0, h, l;
+#pragma unroll
+          for (int w = 0; w < 4 * MT; ++w) {
+            mg_to_fix_f32(s_part[(2 * w) * 256 + c], h, l); ah += h; al += l;
+            mg_to_fix_f32(s_part[(2 * w + 1) * 256 + c], h, l); bh += h; bl += l;
+          }
+          mg_sum_add_fix(p.stats + ch, ah, al);
+          mg_sum_add_fix(p.stats + p.c_stats + ch, bh, bl);
+        }
+      }
+    }
+  } else if (warp == A_WARP) {
+    // ================= halo producer: this CTA's rows, bytes counted on the even CTA's barrier =================
+    // bytes the pair lands per chunk: rows of both tiles (the even CTA knows its peer's geometry)
+    const int hs_p = t0 + BM * MT - p.Wp - 1;
+    const int r0_p = floordiv(hs_p, p.Wp);
+    const int nr_p = (hs_p + p.HL - 1) / p.Wp - r0_p + 1;
+    Ring ra(p.n_abuf);
+    for (int c = 0; c < p.n_chunks; ++c, ra.next()) {
+      const int buf = ra.idx;
+      if (c >= p.n_abuf) mbar_wait_cluster(&a_empty[buf], ra.phase ^ 1u);
+      const HChunk ch = p.chunk[c];
+      const uint32_t dst = smem_u32(a_smem + (size_t)buf * p.halo_bytes);
+      if (p.img_box) {
+        if (lane == 0) {
+          if (rank == 0) mbar_arrive_expect_tx(&a_full[buf], 2u * (uint32_t)(BM * MT) * 128u);
+          tma_load_4d_pair(dst + (uint32_t)(p.Wp + 1) * 128u, &p.tmap[ch.seg], &a_full[buf], ch.c0, 0, 0, t0 / (p.Hp * p.Wp));
+        }
+      } else {
+        const int up = p.seg_up[ch.seg];
+        if (rank == 0 && lane == 0) mbar_arrive_expect_tx(&a_full[buf], (uint32_t)(nr + nr_p) * (uint32_t)(up ? p.W : p.Wp) * 128u);
+        __syncwarp();
+        tma_load_rows_pair(&p.tmap[ch.seg], up, dst + (uint32_t)org * 128u, &a_full[buf], ch.c0, r0, nr, p.W, p.Hp, lane);
+      }
+    }
+  } else if (warp == B_WARP) {
+    // ================= weight loader: this CTA's half of every stage =================
+    if (lane == 0) {
+      const int row0 = ntile * p.n_stages * p.n_tile + (int)rank * (p.n_tile >> 1);
+      Ring rb(S);
+      for (int ks = 0; ks < p.n_stages; ++ks, rb.next()) {
+        const int s = rb.idx;
+        if (ks >= S) mbar_wait_cluster(&empty_bar[s], rb.phase ^ 1u);
+        if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2u * (uint32_t)b_half_bytes);
+        tma_load_2d_pair(smem_u32(b_smem + (size_t)s * b_half_bytes), &p.tmap_w, &full_bar[s], 0, row0 + ks * p.n_tile);
+      }
+    }
+  } else if (rank == 0) {
+    // ================= MMA issuer (even CTA only): M = 256 across the pair =================
+    const bool leader = elect_one();
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    Ring ra(p.n_abuf), rb(S);
+    for (int c = 0; c < p.n_chunks; ++c, ra.next()) {
+      const int buf = ra.idx;
+      const HChunk ch = p.chunk[c];
+      mbar_wait_cluster(&a_full[buf], ra.phase);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(a_smem + (size_t)buf * p.halo_bytes) + (uint32_t)a_first * 128u;
+      const int tps = ch.tps, ksteps = ch.ksteps;
+      const uint32_t sub_lo = 8u / (uint32_t)tps;
+      int sub = 0;
+      uint32_t b_lo = 0;
+      for (int tap = 0; tap < 9; ++tap) {
+        if (sub == 0) {
+          mbar_wait_cluster(&full_bar[rb.idx], rb.phase);
+          tc_fence_after();
+          b_lo = desc_lo_k_sw128(smem_u32(b_smem + (size_t)rb.idx * b_half_bytes));
+        }
+        const uint32_t a_lo = desc_lo_k_sw128(a_base + (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 128u);
+        const bool last_of_stage = (sub == tps - 1) || tap == 8;
+        if (leader) {
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (q < ksteps) {
+                tc_mma_bf16_lohi_pair(tmem_base + (uint32_t)(mt * p.n_tile), a_lo + (uint32_t)(mt * BM * 8 + q * 2), b_lo + (uint32_t)sub * sub_lo + (uint32_t)(q * 2),
+                                      DESC_HI_SW128, idesc, (uint32_t)((c | tap | q) != 0));
+              }
+          if (last_of_stage) tc_commit_pair(&empty_bar[rb.idx]);
+        }
+        if (last_of_stage) { sub = 0; rb.next(); } else ++sub;
+      }
+      if (leader) tc_commit_pair(&a_empty[buf]);
+    }
+    if (leader) tc_commit_pair(&tmem_full_bar);
+  }
+  __syncthreads();
+  cluster_sync_all();     // neither CTA leaves (or frees TMEM) while its peer may still read its shared memory or signal its barriers
+  if (warp == M_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
 }
 
@@ -1331,11 +1537,40 @@ static int launch_halo(mg_ctx* ctx, HParams& p, const Geometry& g, int algo, con
     const bool heur2 = g.n_chunks >= 3 && ctas2 * 10 >= (int64_t)ctx->num_sms * 8;
     MT = (want == 1 || want == 2) ? want : (heur2 ? 2 : 1);
   }
+  const bool pair = algo == MG_ALGO_PAIR128 || algo == MG_ALGO_PAIR256;
+  if (pair) MT = algo == MG_ALGO_PAIR256 ? 2 : 1;
   { int rc = halo_tensor_maps(ctx, p, segs, BM * MT); if (rc) return rc; }
   halo_geometry(p, BM * MT);
   int cols = 32;
   while (cols < MT * p.n_tile) cols <<= 1;
   p.tmem_cols = cols;
+  if (pair) {
+    // CTA pairs (cta_group::2): half a weight stage per CTA; rows land up to Wp slots into the halo buffer (see the kernel)
+    if (!p.img_box) p.halo_bytes = mg_round_up((p.nr_max * p.Wp + p.Wp) * 128, 1024);
+    const int half = b_stage / 2;
+    const int ctas = std::max(1, std::min(512 / cols, 2));
+    int budget = (budget_env > 0 ? budget_env : (ctas == 1 ? 200 : 108)) * 1024;
+    p.n_abuf = (g.n_chunks > 1 && 2 * p.halo_bytes + 2 * half <= budget) ? 2 : 1;
+    int S = (budget - p.n_abuf * p.halo_bytes) / half;
+    S = std::max(2, std::min(S, std::min(MAX_STAGES, p.n_stages)));
+    p.stages = S;
+    const int smem = p.n_abuf * p.halo_bytes + S * half + 1024;
+    MG_REQUIRE(ctx, smem <= SMEM_MAX, MG_ERR_UNSUPPORTED, "pair halo conv: %d bytes of shared memory", smem);
+    int rc = mg_tensor_map(ctx, p.wpack, g.n_tiles * p.n_stages * p.n_tile, 0, 0, 0, 5, p.n_tile / 2, &p.tmap_w);
+    if (rc) return rc;
+    static bool pair_attr_set = false;
+    if (!pair_attr_set) {
+      MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_pair_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+      MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_pair_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+      pair_attr_set = true;
+    }
+    dim3 grid((unsigned)mg_round_up((int)mg_cdiv(p.T, BM * MT), 2), (unsigned)g.n_tiles);   // an odd tile count gets an all-padding tile
+    if (MT == 2) MG_CUDA(ctx, mg_launch_pdl(umma_conv_halo_pair_kernel<2>, grid, dim3(32 * 11), (size_t)smem, ctx->stream, p));
+    else MG_CUDA(ctx, mg_launch_pdl(umma_conv_halo_pair_kernel<1>, grid, dim3(32 * 7), (size_t)smem, ctx->stream, p));
+    MG_CHECK_LAUNCH(ctx);
+    ctx->tc_launches++;
+    return MG_OK;
+  }
   int budget_kb;
   if (MT == 1) {
     // narrow tiles want several resident CTAs (prologue / epilogue of one overlap the main loop of the others);
@@ -1383,7 +1618,7 @@ static bool persist_plan(const mg_ctx* ctx, const mg_conv_desc* d, const Geometr
   if (on < 0) { const char* e = getenv("MGCONV_PERSIST"); on = e ? atoi(e) : 1; }
   if (min_tiles_per_sm < 0) { const char* e = getenv("MGCONV_PERSIST_MIN_TILES"); min_tiles_per_sm = e ? atoi(e) : 4; }
   if (algo == MG_ALGO_TILE128 || algo == MG_ALGO_TILE256 || algo == MG_ALGO_TILE128_DEEP || algo == MG_ALGO_TILE256_DEEP ||
-      algo == MG_ALGO_TILE128_MID) return false;
+      algo == MG_ALGO_TILE128_MID || algo == MG_ALGO_PAIR128 || algo == MG_ALGO_PAIR256) return false;
   const bool forced = algo == MG_ALGO_RESIDENT || ctx->tune_persist == 1;
   if (!forced && (ctx->tune_persist == 2 || !on)) return false;
   if (!g.halo || g.n_tiles != 1) return false;
