@@ -26,6 +26,22 @@ __device__ __forceinline__ void split4(int64_t i, int nb, int nc, int nd, int& a
   }
 }
 
+// division by a run-time constant as multiply-high + shift (valid for dividends < 2^31): the index decode of the streaming
+// passes was ~400 of their ~1000 instructions per thread with emulated divisions (ncu: issue slots 63-66 % busy)
+struct FastDiv { uint32_t mul, shift, d; };
+static inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f; f.d = d; f.mul = 0; f.shift = 0;
+  if (d > 1) {
+    uint32_t lg = 0;
+    while ((1ull << lg) < d) ++lg;
+    const uint32_t p = 31 + lg;
+    f.mul = (uint32_t)(((1ull << p) + d - 1) / d);
+    f.shift = p - 32;
+  }
+  return f;
+}
+__device__ __forceinline__ uint32_t fd_div(uint32_t n, const FastDiv& f) { return f.d == 1 ? n : (__umulhi(n, f.mul) >> f.shift); }
+
 __device__ __forceinline__ V8 ld8(const bf16* p) {
   const uint4 u = *reinterpret_cast<const uint4*>(p);
   V8 r;
@@ -97,6 +113,7 @@ struct ApplyP {
   const mg_sum* sums; int64_t count;
   const float* gamma; const float* beta; float* rmean; float* rvar; float eps, momentum;
   float* smean; float* sinvstd; float* scale_out; float* shift_out;
+  FastDiv fd_v, fd_wp, fd_hp;   // index decode (items and pixels < 2^31: checked by the launcher)
 };
 
 // BatchNorm finalisation of the apply pass, per CTA (expression for expression bn_finalize_kernel).  Not inlined: its fp64
@@ -140,13 +157,18 @@ __global__ void __launch_bounds__(256, 3) apply_bf16_kernel(const __grid_constan
     apply_bn_prologue(p, s_aff);
     __syncthreads();
   }
-  const int V = p.o_cp >> 3;
-  const int64_t total = (int64_t)p.N * p.Hp * p.Wp * V;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  int n, py, px, vc;
-  split4(i, p.Hp, p.Wp, V, n, py, px, vc);
-  const int c0 = vc * 8;
+  const uint32_t V = (uint32_t)p.o_cp >> 3;
+  const uint32_t total = (uint32_t)p.N * p.Hp * p.Wp * V;
+  // grid-stride loop: large tensors run on ~6 CTAs per SM, so the BatchNorm prologue above (fp64 division / square root: ~400
+  // instructions per thread) is paid once per several blocks instead of once per block
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+  uint32_t q = fd_div(i, p.fd_v);
+  const uint32_t vc = i - q * V;
+  uint32_t t = fd_div(q, p.fd_wp);
+  const uint32_t px = q - t * (uint32_t)p.Wp;
+  const uint32_t n = fd_div(t, p.fd_hp);
+  const uint32_t py = t - n * (uint32_t)p.Hp;
+  const int c0 = (int)vc * 8;
   float sc[8], sh[8];
   const bool has_aff = p.bn || p.scale != nullptr;
   if (p.bn) {
@@ -157,51 +179,64 @@ __global__ void __launch_bounds__(256, 3) apply_bf16_kernel(const __grid_constan
   // every load of the 2x2 block is issued before the first use (the stores below may alias z as far as the compiler knows, so
   // it would otherwise order load - store - load: eight dependent round trips per thread instead of one).  Pixels outside the
   // grid re-read pixel 0 of the block (always valid) and are dropped at the store.
-  const int y0 = 2 * py, x0 = 2 * px;
-  const bool ok[4] = {true, x0 + 1 < p.W, y0 + 1 < p.H, x0 + 1 < p.W && y0 + 1 < p.H};
-  int64_t pix[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) pix[k] = ((int64_t)n * p.H + y0 + (ok[k] ? (k >> 1) : 0)) * p.W + x0 + (ok[k] ? (k & 1) : 0);
+  const uint32_t y0 = 2 * py, x0 = 2 * px;
+  const bool okx = x0 + 1 < (uint32_t)p.W, oky = y0 + 1 < (uint32_t)p.H;
+  const bool ok[4] = {true, okx, oky, okx && oky};
+  const uint32_t pix0 = (n * (uint32_t)p.H + y0) * (uint32_t)p.W + x0;
+  const uint32_t pix[4] = {pix0, pix0 + (okx ? 1u : 0u), pix0 + (oky ? (uint32_t)p.W : 0u), pix0 + (okx && oky ? (uint32_t)p.W + 1u : 0u)};
   uint4 zr[4], sr[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) zr[k] = *reinterpret_cast<const uint4*>(p.z + pix[k] * p.z_cp + c0);
+  for (int k = 0; k < 4; ++k) zr[k] = *reinterpret_cast<const uint4*>(p.z + (size_t)pix[k] * p.z_cp + c0);
   if (has_s) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) sr[k] = *reinterpret_cast<const uint4*>(p.s + pix[k] * p.s_cp + c0);
+    for (int k = 0; k < 4; ++k) sr[k] = *reinterpret_cast<const uint4*>(p.s + (size_t)pix[k] * p.s_cp + c0);
   }
-  float best[8];
+  const bool ragged = c0 + 8 > p.C;          // the vector holds pad channels (stored as zeros)
+  const bool zrelu = p.z_relu != 0, relu = p.relu != 0;
+  // the pooled companion is the maximum of the STORED bf16 values: packed bf16x2 maxima (NaN-propagating like the scalar form)
+  __nv_bfloat162 best[4];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) best[e] = -INFINITY;
+  for (int j = 0; j < 4; ++j) best[j] = __halves2bfloat162(__ushort_as_bfloat16((unsigned short)0xFF80), __ushort_as_bfloat16((unsigned short)0xFF80));
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     if (!ok[k]) continue;
     V8 v = unpack8(zr[k]);
     if (has_aff) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v.v[e] = mg_xform(v.v[e], sc[e], sh[e], p.z_relu);
+      for (int e = 0; e < 8; ++e) { v.v[e] = fmaf(v.v[e], sc[e], sh[e]); if (zrelu) v.v[e] = fmaxf(v.v[e], 0.f); }   // = mg_xform
     }
     if (has_s) {
       const V8 sv = unpack8(sr[k]);
 #pragma unroll
       for (int e = 0; e < 8; ++e) v.v[e] += sv.v[e];
     }
+    if (relu) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      if (p.relu) v.v[e] = fmaxf(v.v[e], 0.f);
-      if (c0 + e >= p.C) v.v[e] = 0.f;
+      for (int e = 0; e < 8; ++e) v.v[e] = fmaxf(v.v[e], 0.f);
+    }
+    if (ragged) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) if (c0 + e >= p.C) v.v[e] = 0.f;
     }
     const uint4 u = pack8(v);
-    *reinterpret_cast<uint4*>(p.out + pix[k] * p.o_cp + c0) = u;
-    const V8 r = unpack8(u);   // pool what was stored
+    *reinterpret_cast<uint4*>(p.out + (size_t)pix[k] * p.o_cp + c0) = u;
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-    for (int e = 0; e < 8; ++e)
-      if (r.v[e] > best[e] || r.v[e] != r.v[e]) best[e] = r.v[e];
+    for (int j = 0; j < 4; ++j) best[j] = __hmax2_nan(best[j], *reinterpret_cast<const __nv_bfloat162*>(&w[j]));
   }
   if (p.pooled && c0 < p.p_cp) {
-    V8 b;
+    uint32_t w[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) b.v[e] = (c0 + e < p.C) ? best[e] : 0.f;
-    *reinterpret_cast<uint4*>(p.pooled + (((int64_t)n * p.Hp + py) * p.Wp + px) * p.p_cp + c0) = pack8(b);
+    for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<uint32_t*>(&best[j]);
+    if (ragged) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (c0 + 2 * j >= p.C) w[j] &= 0xFFFF0000u;
+        if (c0 + 2 * j + 1 >= p.C) w[j] &= 0x0000FFFFu;
+      }
+    }
+    *reinterpret_cast<uint4*>(p.pooled + (size_t)((n * (uint32_t)p.Hp + py) * (uint32_t)p.Wp + px) * p.p_cp + c0) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
   }
 }
 
@@ -772,8 +807,12 @@ bool bf16_apply(mg_ctx* ctx, const mg_grid* z, const mg_grid* s, int relu, mg_gr
   p.N = z->N; p.H = z->H; p.W = z->W; p.C = z->C; p.Hp = (z->H + 1) / 2; p.Wp = (z->W + 1) / 2;
   if (out->Cp > 2048) return false;
   const int64_t total = (int64_t)p.N * p.Hp * p.Wp * (p.o_cp / 8);
+  if (total >= ((int64_t)1 << 31) || (int64_t)p.N * p.H * p.W >= ((int64_t)1 << 31)) return false;   // 32-bit index decode
+  p.fd_v = make_fastdiv((uint32_t)(p.o_cp / 8)); p.fd_wp = make_fastdiv((uint32_t)p.Wp); p.fd_hp = make_fastdiv((uint32_t)p.Hp);
   // one 2x2 block x 8 channels per thread (measured: looping CTAs with batched loads need 80 registers and lose 10-40 %)
-  const unsigned grid = grid_for(total);
+  static int per_sm = -1;
+  if (per_sm < 0) { const char* e = getenv("MGCONV_APPLY_CTAS"); per_sm = e ? atoi(e) : 6; }
+  const unsigned grid = (unsigned)std::min<int64_t>(grid_for(total), (int64_t)per_sm * ctx->num_sms);
   mg_launch_pdl(apply_bf16_kernel, dim3(grid), dim3(256), bn ? 2 * z->Cp * sizeof(float) : 0, ctx->stream, p);
   return true;
 }
