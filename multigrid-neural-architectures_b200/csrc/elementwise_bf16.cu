@@ -286,6 +286,7 @@ struct CombP {
   bf16* d; int d_cp;
   mg_sum* sums;
   int N, H, W, C, Hb, Wb;        // Hb = ceil(H/2): 2x2 blocks
+  FastDiv fd_wb, fd_hb;          // combine_fast_kernel: index decode
 };
 
 // NS >= 0: the number of sources and their modes (2 bits each in MODES) are compile-time constants, so the source loop
@@ -436,9 +437,9 @@ __global__ void __launch_bounds__(256, 2) combine_fast_kernel(const __grid_const
   const int lanes = blockDim.x / V;
   const int vc = threadIdx.x % V, lane = threadIdx.x / V;
   const int c0 = vc * 8;
-  const int64_t nblocks = (int64_t)p.N * p.Hb * p.Wb;
-  const int64_t per_cta = (nblocks + gridDim.x - 1) / gridDim.x;
-  const int64_t b_begin = (int64_t)blockIdx.x * per_cta, b_end = min(nblocks, b_begin + per_cta);
+  const uint32_t nblocks = (uint32_t)p.N * p.Hb * p.Wb;       // blocks and pixels < 2^31: checked by the launcher
+  const uint32_t per_cta = (nblocks + gridDim.x - 1) / gridDim.x;
+  const uint32_t b_begin = blockIdx.x * per_cta, b_end = min(nblocks, b_begin + per_cta);
   const bool active = lane < lanes;
   float sd[8], sdx[8];
 #pragma unroll
@@ -449,15 +450,16 @@ __global__ void __launch_bounds__(256, 2) combine_fast_kernel(const __grid_const
   const bool has_sums = p.sums != nullptr;
 
   if (active)
-    for (int64_t blk = b_begin + lane; blk < b_end; blk += lanes) {
-      int n, by, bx, unused_;
-      split4(blk, p.Hb, p.Wb, 1, n, by, bx, unused_);
+    for (uint32_t blk = b_begin + lane; blk < b_end; blk += lanes) {
+      const uint32_t tq = fd_div(blk, p.fd_wb);
+      const int bx = (int)(blk - tq * (uint32_t)p.Wb);
+      const int n = (int)fd_div(tq, p.fd_hb);
+      const int by = (int)(tq - (uint32_t)n * (uint32_t)p.Hb);
       const int y0 = 2 * by, x0 = 2 * bx;
       const bool vy1 = y0 + 1 < p.H, vx1 = x0 + 1 < p.W;
       const bool valid[4] = {true, vx1, vy1, vy1 && vx1};
-      int64_t pix[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) pix[k] = ((int64_t)n * p.H + y0 + (valid[k] ? (k >> 1) : 0)) * p.W + x0 + (valid[k] ? (k & 1) : 0);
+      const uint32_t pix0 = ((uint32_t)n * (uint32_t)p.H + (uint32_t)y0) * (uint32_t)p.W + (uint32_t)x0;
+      const uint32_t pix[4] = {pix0, pix0 + (vx1 ? 1u : 0u), pix0 + (vy1 ? (uint32_t)p.W : 0u), pix0 + (vy1 && vx1 ? (uint32_t)p.W + 1u : 0u)};
       V8 acc[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k)
@@ -472,7 +474,7 @@ __global__ void __launch_bounds__(256, 2) combine_fast_kernel(const __grid_const
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int y = y0 + (valid[k] ? (k >> 1) : 0), x = x0 + (valid[k] ? (k & 1) : 0);
-            const bf16* gp = S.g + (((int64_t)n * S.H + 2 * y) * S.W + 2 * x) * S.cp + S.c_off + c0;
+            const bf16* gp = S.g + (size_t)(((uint32_t)n * (uint32_t)S.H + 2u * (uint32_t)y) * (uint32_t)S.W + 2u * (uint32_t)x) * S.cp + S.c_off + c0;
             r[4 * k] = __ldg(reinterpret_cast<const uint4*>(gp));
             r[4 * k + 1] = __ldg(reinterpret_cast<const uint4*>(gp + S.cp));
             r[4 * k + 2] = __ldg(reinterpret_cast<const uint4*>(gp + (int64_t)S.W * S.cp));
@@ -492,7 +494,7 @@ __global__ void __launch_bounds__(256, 2) combine_fast_kernel(const __grid_const
       for (int k = 0; k < 4; ++k) { Xr[k] = make_uint4(0, 0, 0, 0); Yr[k] = make_uint4(0, 0, 0, 0); }
       if (need_x) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) Xr[k] = __ldg(reinterpret_cast<const uint4*>(p.x + pix[k] * p.x_cp + c0));
+        for (int k = 0; k < 4; ++k) Xr[k] = __ldg(reinterpret_cast<const uint4*>(p.x + (size_t)pix[k] * p.x_cp + c0));
       }
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
@@ -500,16 +502,16 @@ __global__ void __launch_bounds__(256, 2) combine_fast_kernel(const __grid_const
         const int mode = (MODES >> (2 * s)) & 3;
         if (mode == MG_SEG_SAME) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) Gr[s][k] = __ldg(reinterpret_cast<const uint4*>(S.g + pix[k] * S.cp + S.c_off + c0));
+          for (int k = 0; k < 4; ++k) Gr[s][k] = __ldg(reinterpret_cast<const uint4*>(S.g + (size_t)pix[k] * S.cp + S.c_off + c0));
         } else if (mode == MG_SEG_POOL) {
-          Gr[s][0] = __ldg(reinterpret_cast<const uint4*>(S.g + (((int64_t)n * S.H + by) * S.W + bx) * S.cp + S.c_off + c0));
+          Gr[s][0] = __ldg(reinterpret_cast<const uint4*>(S.g + (size_t)(((uint32_t)n * (uint32_t)S.H + (uint32_t)by) * (uint32_t)S.W + (uint32_t)bx) * S.cp + S.c_off + c0));
         } else if (mode == 3) {
           // SpatialMaxPooling(3,3,2,2,1,1) of the stem: the 2x2 block lies in the four windows (by + wy, bx + wx); window w of the
           // block is loaded once (gradient + arg-max codes) instead of once per pixel it covers
 #pragma unroll
           for (int w = 0; w < 4; ++w) {
             const int oy = min(by + (w >> 1), S.H - 1), ox = min(bx + (w & 1), S.W - 1);
-            const int64_t o = ((int64_t)n * S.H + oy) * S.W + ox;
+            const size_t o = (size_t)(((uint32_t)n * (uint32_t)S.H + (uint32_t)oy) * (uint32_t)S.W + (uint32_t)ox);
             Gr[s][w] = __ldg(reinterpret_cast<const uint4*>(S.g + o * S.cp + S.c_off + c0));
             Cd[w] = __ldg(reinterpret_cast<const uint2*>(S.aux + o * S.cp + S.c_off + c0));
           }
@@ -517,7 +519,7 @@ __global__ void __launch_bounds__(256, 2) combine_fast_kernel(const __grid_const
       }
       if (has_sums) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) Yr[k] = __ldg(reinterpret_cast<const uint4*>(p.bnx + pix[k] * p.bn_cp + c0));
+        for (int k = 0; k < 4; ++k) Yr[k] = __ldg(reinterpret_cast<const uint4*>(p.bnx + (size_t)pix[k] * p.bn_cp + c0));
       }
       // ---- accumulate: up-sampled sources first (above), then the others in list order.  The order is a property of the
       // source-mode list alone (never of the launch, the lane or the run), so results stay reproducible; against the generic
@@ -584,7 +586,7 @@ __global__ void __launch_bounds__(256, 2) combine_fast_kernel(const __grid_const
 #pragma unroll
             for (int e = 0; e < 8; ++e) { sd[e] += acc[k].v[e]; sdx[e] = fmaf(acc[k].v[e], yr.v[e], sdx[e]); }
           }
-          *reinterpret_cast<uint4*>(p.d + pix[k] * p.d_cp + c0) = pack8(acc[k]);
+          *reinterpret_cast<uint4*>(p.d + (size_t)pix[k] * p.d_cp + c0) = pack8(acc[k]);
         }
     }
   if (p.sums) block_channel_sums(sd, sdx, vc, V, p.C, active, p.sums, sh);
@@ -848,8 +850,11 @@ bool bf16_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid* b
   const int64_t items = (int64_t)p.N * p.Hb * p.Wb * V;
   static int spec = -1;
   if (spec < 0) { const char* e = getenv("MGCONV_COMBINE_SPEC"); spec = e ? atoi(e) : 1; }
-  static int fast = -1;   // batched-load form of the specialised kernels (MGCONV_COMBINE_FAST=0: the older form, for A/B timing)
-  if (fast < 0) { const char* e = getenv("MGCONV_COMBINE_FAST"); fast = e ? atoi(e) : 1; }
+  static int fast_env = -1;   // batched-load form of the specialised kernels (MGCONV_COMBINE_FAST=0: the older form, for A/B timing)
+  if (fast_env < 0) { const char* e = getenv("MGCONV_COMBINE_FAST"); fast_env = e ? atoi(e) : 1; }
+  bool fast = fast_env != 0 && (int64_t)p.N * p.H * p.W < ((int64_t)1 << 31);   // 32-bit pixel indices (of the finer source grids too)
+  for (int s = 0; s < n_src; ++s) fast = fast && (int64_t)src[s].g.N * src[s].g.H * src[s].g.W < ((int64_t)1 << 31);
+  p.fd_wb = make_fastdiv((uint32_t)p.Wb); p.fd_hb = make_fastdiv((uint32_t)p.Hb);
   int code = 0;
   for (int s = 0; s < n_src; ++s) code |= (src[s].mode & 3) << (2 * s);
   const size_t smem = sums ? 2 * 256 * 8 * sizeof(float) : 0;   // block_channel_sums staging
