@@ -114,6 +114,7 @@ struct ApplyP {
   const float* gamma; const float* beta; float* rmean; float* rvar; float eps, momentum;
   float* smean; float* sinvstd; float* scale_out; float* shift_out;
   FastDiv fd_v, fd_wp, fd_hp;   // index decode (items and pixels < 2^31: checked by the launcher)
+  double inv_count, unbias;     // 1 / count, count / (count - 1)
 };
 
 // BatchNorm finalisation of the apply pass, per CTA (expression for expression bn_finalize_kernel).  Not inlined: its fp64
@@ -124,18 +125,20 @@ __device__ __forceinline__ void apply_bn_prologue(const ApplyP& p, float* s_aff)
     if (c < p.C) {
       double mean, var;
       if (p.training) {
-        mean = mg_sum_get(p.sums[c]) / (double)p.count;
-        var = mg_sum_get(p.sums[p.C + c]) / (double)p.count - mean * mean;   // biased
+        // reciprocal of the count and the unbiasing factor come from the host as doubles, the inverse standard deviation from
+        // rsqrt: no fp64 division / square root routine (each ~100 instructions, executed by every CTA of the pass)
+        mean = mg_sum_get(p.sums[c]) * p.inv_count;
+        var = mg_sum_get(p.sums[p.C + c]) * p.inv_count - mean * mean;   // biased
         if (var < 0) var = 0;
         if (p.rmean && blockIdx.x == 0) {
-          const double unb = p.count > 1 ? var * (double)p.count / (double)(p.count - 1) : var;
+          const double unb = var * p.unbias;
           p.rmean[c] = (float)((1.0 - p.momentum) * p.rmean[c] + p.momentum * mean);
           p.rvar[c] = (float)((1.0 - p.momentum) * p.rvar[c] + p.momentum * unb);
         }
       } else {
         mean = p.rmean[c]; var = p.rvar[c];
       }
-      const double invstd = 1.0 / sqrt(var + (double)p.eps);
+      const double invstd = rsqrt(var + (double)p.eps);
       const float g = p.gamma ? p.gamma[c] : 1.f, b = p.beta ? p.beta[c] : 0.f;
       scv = (float)(g * invstd);
       shv = (float)(b - g * invstd * mean);
@@ -601,6 +604,7 @@ struct BnBwdP {   // coefficients derived in-kernel (bn_bwd_coef_kernel, express
   const mg_sum* sums; int64_t count;
   const float* gamma; const float* mean; const float* invstd;
   float* dgamma; float* dbeta;
+  double inv_count;
 };
 
 __global__ void __launch_bounds__(256, 3) bn_bwd_apply_bf16_kernel(const bf16* __restrict__ xraw, int x_cp, const bf16* d, int d_cp, bf16* out,
@@ -617,8 +621,8 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_bf16_kernel(const bf16* _
       const double sd = mg_sum_get(bp.sums[c]), sdx = mg_sum_get(bp.sums[C + c]);
       const double mu = bp.mean[c], is = bp.invstd[c], g = bp.gamma ? bp.gamma[c] : 1.0;
       const double dg = is * (sdx - mu * sd);
-      const double n = (double)bp.count;
-      const double Ad = g * is, Bd = -g * is * is * dg / n, Cd = g * is * (mu * is * dg / n - sd / n);
+      const double n = (double)bp.count, rn = bp.inv_count;   // reciprocal from the host: no fp64 division routine per CTA
+      const double Ad = g * is, Bd = -g * is * is * dg * rn, Cd = g * is * (mu * is * dg * rn - sd * rn);
       if (blockIdx.x == 0) {
         if (bp.dgamma) bp.dgamma[c] += gscale * (float)dg;
         if (bp.dbeta) bp.dbeta[c] += gscale * (float)sd;
@@ -801,6 +805,7 @@ bool bf16_apply(mg_ctx* ctx, const mg_grid* z, const mg_grid* s, int relu, mg_gr
     p.bn = 1; p.training = bn->training; p.sums = bn->sums; p.count = bn->count; p.gamma = bn->gamma; p.beta = bn->beta;
     p.rmean = bn->running_mean; p.rvar = bn->running_var; p.eps = bn->eps; p.momentum = bn->momentum;
     p.smean = bn->save_mean; p.sinvstd = bn->save_invstd; p.scale_out = const_cast<float*>(z->scale); p.shift_out = const_cast<float*>(z->shift);
+    p.inv_count = 1.0 / (double)bn->count; p.unbias = bn->count > 1 ? (double)bn->count / (double)(bn->count - 1) : 1.0;
   }
   p.z = (const bf16*)z->data; p.z_cp = z->Cp; p.scale = z->scale; p.shift = z->shift; p.z_relu = z->relu;
   p.s = s ? (const bf16*)s->data : nullptr; p.s_cp = s ? s->Cp : 0;
@@ -891,7 +896,7 @@ bool bf16_bn_bwd_apply(mg_ctx* ctx, const mg_grid* xraw, const mg_grid* d, mg_gr
                        const float* mean, const float* invstd, float* dgamma, float* dbeta, float* conv_dbias, float gscale) {
   if (xraw->Cp % 8 || d->Cp % 8 || out->Cp % 8 || d->Cp != out->Cp || xraw->Cp < out->Cp || out->Cp > 2048) return false;
   BnBwdP bp;
-  bp.sums = sums; bp.count = count; bp.gamma = gamma; bp.mean = mean; bp.invstd = invstd; bp.dgamma = dgamma; bp.dbeta = dbeta;
+  bp.sums = sums; bp.count = count; bp.inv_count = 1.0 / (double)count; bp.gamma = gamma; bp.mean = mean; bp.invstd = invstd; bp.dgamma = dgamma; bp.dbeta = dbeta;
   const int64_t P = (int64_t)d->N * d->H * d->W;
   const int V = out->Cp / 8;
   const unsigned grid = reduce_grid(ctx, P * V, 4);
