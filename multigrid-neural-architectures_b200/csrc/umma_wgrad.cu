@@ -394,6 +394,176 @@ __global__ void __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_kernel(const __
   }
 }
 
+// ---------------------------------------------------------------- CTA-pair halo weight gradient -------------
+// The same kernel on tcgen05 CTA pairs (cta_group::2): the two CTAs of a cluster own two consecutive CHUNKS (64 input channels
+// each) of the same pixel tiles and column tile.  One MMA (M = 256) issued by the even CTA drives both tensor cores: rows 0-127 are
+// the even CTA's tap pair of its chunk, rows 128-255 the odd CTA's; the gradient operand g (N columns) is split, each CTA stages
+// only its half of the channels.  Per SM: half the g bytes, half the MMA instructions (the per-instruction issue cost is what
+// holds N <= 96 MMAs at ~77 % of the tensor peak: scratch/mma_rate.cu), and a stage small enough for a third ring slot.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WH_THREADS, 1) umma_wgrad_halo_pair_kernel(const __grid_constant__ WHParams p) {
+  pdl_launch();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full_bar[W_MAX_STAGES], empty_bar[W_MAX_STAGES], tmem_full_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int S = p.stages;
+  const int stage_bytes = p.halo_bytes + p.g_bytes;      // one 64-channel block of g per CTA: its half of the column tile
+  const int nt = blockIdx.y;
+  const int tile0 = blockIdx.z * p.tiles_per_cta;
+  const int n_iters = min(p.tiles_per_cta, p.n_slot_tiles - tile0);
+  int sg = 0, c0 = (int)blockIdx.x * 64;
+  bool dummy = false;                                    // odd chunk count: the last pair's odd CTA has no chunk (loads zeros)
+  {
+    int total = 0;
+    for (int s2 = 0; s2 < p.n_seg; ++s2) total += (p.seg_Cp[s2] + 63) & ~63;
+    dummy = c0 >= total;
+  }
+  if (!dummy) while (sg + 1 < p.n_seg && c0 >= ((p.seg_Cp[sg] + 63) & ~63)) { c0 -= (p.seg_Cp[sg] + 63) & ~63; ++sg; }
+  const int nch = dummy ? 0 : min(64, p.seg_Cp[sg] - c0);
+  const int up = p.seg_up[sg];                           // (a CTA without a chunk reads grid 0 beyond its channels: zeros)
+  const int half = p.n_tile >> 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == WH_MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (warp == WH_TMA_WARP && lane == 0) { tma_prefetch_desc(&p.tmap_x[sg]); tma_prefetch_desc(&p.tmap_g); }
+  if (p.img_box) {
+    const int m = p.Wp + 1;
+    for (int i = tid; i < S * 2 * m * 8; i += WH_THREADS) {
+      const int q = i & 7, sl = (i >> 3) % (2 * m), st = (i >> 3) / (2 * m);
+      const int slot = sl < m ? sl : p.HL - 2 * m + sl;
+      *reinterpret_cast<uint4*>(smem + (size_t)st * stage_bytes + (size_t)slot * 128 + q * 16) = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async();
+  } else if (up) {
+    for (int i = tid; i < S * p.nr_max * 8; i += WH_THREADS) {
+      const int q = i & 7, row = (i >> 3) % p.nr_max, st = (i >> 3) / p.nr_max;
+      *reinterpret_cast<uint4*>(smem + (size_t)st * stage_bytes + (size_t)(row * p.Wp + p.W) * 128 + q * 16) = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async();
+  }
+  pdl_wait();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < 4) {
+    // ---- epilogue: this CTA's chunk, all n_tile columns ------------------------------------------------
+    mbar_wait_cluster(&tmem_full_bar, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    const int cl = c0 + (row & 63);
+    const bool row_ok = !dummy && (row & 63) < nch && cl < p.seg_C[sg];
+    const int ci = dummy ? 0 : p.seg_cbegin[sg] + cl;
+    float* part = p.partial + (size_t)blockIdx.z * 9 * p.Cout * p.Ccat;
+    for (int pair = 0; pair < 5; ++pair) {
+      const int tap = pair * 2 + (row >> 6);
+      const bool ok = row_ok && tap < 9;
+      float* prow = part + (size_t)tap * p.Cout * p.Ccat + ci;
+      for (int cc = 0; cc < p.n_tile; cc += 16) {
+        uint32_t acc[16];
+        tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(pair * p.n_tile + cc), acc);
+        tc_wait_ld();
+        if (ok) {
+#pragma unroll
+          for (int x = 0; x < 16; ++x) {
+            const int co = nt * p.n_tile + cc + x;
+            if (co < p.Cout) prow[(size_t)co * p.Ccat] = __uint_as_float(acc[x]);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == WH_TMA_WARP) {
+    // ---- producer: this CTA's halo chunk + its half of the g columns; bytes counted on the even CTA's barrier ----
+    Ring rs(S);
+    for (int it = 0; it < n_iters; ++it, rs.next()) {
+      const int s = rs.idx;
+      if (it >= S) mbar_wait_cluster(&empty_bar[s], rs.phase ^ 1u);
+      const int t0 = (tile0 + it) * p.kt;
+      const int hs = t0 - p.Wp - 1;
+      const int r0 = floordiv(hs, p.Wp);
+      const int nr = (hs + p.HL - 1) / p.Wp - r0 + 1;
+      const int gr0 = t0 / p.Wp;
+      const int gnr = (t0 + p.kt - 1) / p.Wp - gr0 + 1;
+      const uint32_t st = smem_u32(smem + (size_t)s * stage_bytes);
+      const int gc0 = nt * p.n_tile + (int)rank * half;
+      // a CTA without a chunk (odd count) loads channels beyond the grid: zeros
+      const int xc0 = dummy ? (1 << 20) : c0;
+      if (p.img_box) {
+        const int n0 = t0 / (p.Hp * p.Wp);
+        if (lane == 0) {
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 4u * (uint32_t)p.kt * 128u);
+          tma_load_4d_pair(st + (uint32_t)(p.Wp + 1) * 128u, &p.tmap_x[sg], &full_bar[s], xc0, 0, 0, n0);
+          tma_load_4d_pair(st + (uint32_t)p.halo_bytes, &p.tmap_g, &full_bar[s], gc0, 0, 0, n0);
+        }
+      } else {
+        // the two CTAs of a pair may stage segments of different kinds (same-size / up-sampled): the even CTA needs its peer's row bytes
+        if (rank == 0 && lane == 0) {
+          int sg1 = 0, c1 = ((int)blockIdx.x + 1) * 64;
+          int total = 0;
+          for (int s2 = 0; s2 < p.n_seg; ++s2) total += (p.seg_Cp[s2] + 63) & ~63;
+          int up1 = p.seg_up[0];
+          if (c1 < total) { while (sg1 + 1 < p.n_seg && c1 >= ((p.seg_Cp[sg1] + 63) & ~63)) { c1 -= (p.seg_Cp[sg1] + 63) & ~63; ++sg1; } up1 = p.seg_up[sg1]; }
+          const uint32_t bytes = (uint32_t)nr * (uint32_t)((up ? p.W : p.Wp) + (up1 ? p.W : p.Wp)) * 128u + 2u * (uint32_t)gnr * (uint32_t)p.Wp * 128u;
+          mbar_arrive_expect_tx(&full_bar[s], bytes);
+        }
+        __syncwarp();
+        tma_load_rows_pair(&p.tmap_x[sg], up, st, &full_bar[s], xc0, r0, nr, p.W, p.Hp, lane);
+        tma_load_rows_pair(&p.tmap_g, 0, st + (uint32_t)p.halo_bytes, &full_bar[s], gc0, gr0, gnr, p.W, p.Hp, lane);
+      }
+    }
+  } else if (rank == 0) {
+    // ---- MMA issuer (even CTA): M = 256 across the pair ------------------------------------------
+    const bool leader = elect_one();
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    const int nq = p.kt >> 4;
+    Ring rs(S);
+    for (int it = 0; it < n_iters; ++it, rs.next()) {
+      const int s = rs.idx;
+      const int t0 = (tile0 + it) * p.kt;
+      const int hs = t0 - p.Wp - 1;
+      const int off = p.img_box ? 0 : hs - floordiv(hs, p.Wp) * p.Wp;
+      const int goff = p.img_box ? 0 : t0 - (t0 / p.Wp) * p.Wp;
+      mbar_wait_cluster(&full_bar[s], rs.phase);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)off * 128u;
+      const uint32_t b_lo = desc_lo_mn_sw128(smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)p.halo_bytes + (uint32_t)goff * 128u, (uint32_t)p.g_bytes);
+      if (leader) {
+#pragma unroll 1
+        for (int pair = 0; pair < 5; ++pair) {
+          const int ta = pair * 2, tb2 = min(pair * 2 + 1, 8);
+          const int sa = (ta / 3) * p.Wp + ta % 3, sb = (tb2 / 3) * p.Wp + tb2 % 3;
+          const uint32_t a_lo = desc_lo_mn_sw128(a_base + (uint32_t)sa * 128u, (uint32_t)(sb - sa) * 128u);
+          const uint32_t d_tmem = tmem_base + pair * p.n_tile;
+#pragma unroll 8
+          for (int q = 0; q < nq; ++q)
+            tc_mma_bf16_lohi_pair(d_tmem, a_lo + q * 128, b_lo + q * 128, DESC_HI_SW128, idesc, (it | q) != 0);
+        }
+        tc_commit_pair(&empty_bar[s]);
+      }
+    }
+    if (leader) tc_commit_pair(&tmem_full_bar);
+  }
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == WH_MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
 // dw[co][ci][tap] += gscale * sum_z partial[z][tap][co][ci]   (z in increasing order: deterministic)
 // A CTA owns blockDim.x consecutive (co, ci) pairs x blockDim.y tap lanes: the partial planes are read coalesced along ci, the
 // sums are transposed through shared memory and dw is updated as ONE contiguous range of blockDim.x * KK floats (Torch's
@@ -715,6 +885,37 @@ static int wgrad_halo(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g, floa
     if (rc) return rc;
     p.seg_C[s] = sg.C; p.seg_Cp[s] = sg.Cp; p.seg_cbegin[s] = c;
     c += sg.C;
+  }
+  // CTA pairs (cta_group::2): two chunks per cluster share the pixel tiles, each CTA stages half of the g columns.  Taken when the
+  // chunk count is even (an odd count leaves one CTA of the last pair without work); MGCONV_WGRAD_PAIR = 0 never, 2 always
+  static int pair_env = -1;
+  if (pair_env < 0) { const char* e = getenv("MGCONV_WGRAD_PAIR"); pair_env = e ? atoi(e) : 1; }
+  const bool pair = pair_env == 2 || (pair_env == 1 && n_chunks % 2 == 0);
+  if (pair) {
+    const int n_chunks2 = mg_round_up(n_chunks, 2);
+    int64_t sp = std::max<int64_t>(1, (int64_t)ctx->num_sms / ((int64_t)n_chunks2 * n_tiles));
+    sp = std::min<int64_t>(sp, std::max(1, p.n_slot_tiles / 2));
+    p.tiles_per_cta = (int)mg_cdiv(p.n_slot_tiles, sp);
+    const int zp = (int)mg_cdiv(p.n_slot_tiles, p.tiles_per_cta);
+    const int stage_p = p.halo_bytes + p.g_bytes;
+    int Sp = std::min(W_MAX_STAGES, (SMEM_WGRAD - 1024) / stage_p);
+    Sp = std::max(2, std::min(Sp, std::max(2, p.tiles_per_cta)));
+    p.stages = Sp;
+    rc = mg_ctx_workspace(ctx, (size_t)zp * plane * sizeof(float), &ws);
+    if (rc) return rc;
+    p.partial = (float*)ws;
+    static bool pair_attr = false;
+    if (!pair_attr) {
+      MG_CUDA(ctx, cudaFuncSetAttribute(umma_wgrad_halo_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_WGRAD));
+      pair_attr = true;
+    }
+    dim3 gridp((unsigned)n_chunks2, (unsigned)n_tiles, (unsigned)zp);
+    MG_CUDA(ctx, mg_launch_pdl(umma_wgrad_halo_pair_kernel, gridp, dim3(WH_THREADS), (size_t)(Sp * stage_p + 1024), ctx->stream, p));
+    MG_CHECK_LAUNCH(ctx);
+    ctx->tc_launches++;
+    MG_CUDA(ctx, launch_wgrad_reduce(ctx, p.partial, zp, p.Cout, p.Ccat, dw, gscale, 9));
+    MG_CHECK_LAUNCH(ctx);
+    return MG_OK;
   }
   dim3 grid((unsigned)n_chunks, (unsigned)n_tiles, (unsigned)z);
   MG_CUDA(ctx, mg_launch_pdl(umma_wgrad_halo_kernel, grid, dim3(WH_THREADS), (size_t)(S * stage_bytes + 1024), ctx->stream, p));
