@@ -38,7 +38,8 @@ assert e_out <= tol, ("log-probabilities", e_out)
 assert e_g <= 10 * tol, ("gradients", e_g)
 # local-BN mode (the reference's DataParallelTable): statistics per shard -> differs from the whole-batch run
 out3, _, _ = run(world, x[lo:hi], t[lo:hi], False)
-assert rel(out3, out1[lo:hi]) > 10 * tol, "per-replica BN must differ from whole-batch BN"
+e_local = rel(out3, out1[lo:hi])
+assert e_local > max(1e-3, 5 * e_out), ("per-replica BN must differ from whole-batch BN", e_local, e_out)
 dist.barrier()
-print(f"dp-equivalence ok rank {rank}: out {e_out:.2e} grad {e_g:.2e}")
+print(f"dp-equivalence ok rank {rank} [{precision}]: sync-BN vs single GPU: out {e_out:.2e} grad {e_g:.2e}; per-replica BN differs by {e_local:.2e}", flush=True)
 dist.destroy_process_group()

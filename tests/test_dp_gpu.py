@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("precision", ["fp32"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_two_gpu_syncbn_equals_single_gpu(precision):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
