@@ -102,7 +102,8 @@ enum { MG_ALGO_AUTO = 0, MG_ALGO_TILE128 = 1, /* one 128-slot tile per CTA, seve
        MG_ALGO_TILE256_DEEP = 5,              /* TILE256 with one CTA per SM: two halo buffers, deepest weight ring */
        MG_ALGO_TILE128_MID = 6,               /* TILE128 with three CTAs per SM (72 KB each) */
        MG_ALGO_PAIR128 = 7,                   /* tcgen05 CTA pairs (cta_group::2, M = 256 per MMA): each SM streams half of every weight stage */
-       MG_ALGO_PAIR256 = 8 };                 /* CTA pairs with two sub-tiles per CTA (512 slots per pair) */
+       MG_ALGO_PAIR256 = 8,                   /* CTA pairs with two sub-tiles per CTA (512 slots per pair) */
+       MG_ALGO_RESIDENT_PAIR = 9 };           /* persistent CTA pairs: half of the weight image resident per CTA, deeper halo ring */
 
 typedef struct {
   mg_grid g;        /* gradient tensor of a consumer */

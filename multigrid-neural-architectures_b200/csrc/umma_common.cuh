@@ -107,6 +107,12 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
                "h"((uint16_t)3)
                : "memory");
 }
+// arrive on the barrier at this offset in CTA `rank` of the cluster (release at cluster scope)
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
 // wait with cluster-scope acquire: the completion bytes / arrivals come from the peer CTA's copy engine and tensor core
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t addr = smem_u32(bar);

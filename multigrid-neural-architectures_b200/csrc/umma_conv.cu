@@ -392,6 +392,7 @@ struct HParams {
   int c_stats;
   int m_tiles;        // persistent kernel: 128-slot tiles in total
   CUtensorMap tmap_w; // pair kernels: the packed weight image as rows of 128 bytes (tma.cuh kind 5)
+  int tile_rows;      // persistent kernel, row-aligned tiles: a tile is tile_rows whole slot rows (tile_rows * Wp <= 128 slots), 0 = 128-slot tiles
 };
 
 // zero the pad column (slot x == W of every row) of `nbuf` halo buffers: the up-sampling box writes only the W valid slots
@@ -833,7 +834,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * MT + 3), M
 //   1 MMA warp       accumulates tile i into TMEM accumulator i & 1 (every operand already in shared memory),
 //   4 epilogue warps drain accumulator (i-1) & 1 meanwhile (TMEM double buffering) and keep the BatchNorm
 //                    statistics of all the CTA's tiles in shared memory: one deterministic (integer) atomic pair per channel and CTA.
-constexpr int P_A_WARP = 4, P_B_WARP = 5, P_MMA_WARP = 6, P_THREADS = 224;
+constexpr int P_A_WARP = 8, P_B_WARP = 9, P_MMA_WARP = 10, P_THREADS = 352;   // 2 x 4 epilogue warps (one group per TMEM accumulator), TMA, weights, MMA
 constexpr int P_MAX_ABUF = 6;
 
 __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel(const __grid_constant__ HParams p) {
@@ -849,10 +850,16 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
   uint8_t* a_smem = smem;
   uint8_t* b_smem = smem + (size_t)NA * p.halo_bytes;                                  // all weight stages, resident
   long long* s_part = reinterpret_cast<long long*>(b_smem + (size_t)p.n_stages * b_stage_bytes);   // [4 epilogue warps][2][n_tile][hi, lo]
-  float* s_bias = reinterpret_cast<float*>(s_part + 16 * p.n_tile);                    // [n_tile]
+  float* s_bias = reinterpret_cast<float*>(s_part + 32 * p.n_tile);                    // [n_tile]
   const int n_my = (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // tiles blockIdx.x, +gridDim.x, ...
+  // Row-aligned tiles (tile_rows > 0): a tile is R whole slot rows, its halo exactly the R + 2 rows around it plus one slot on either
+  // side.  The slot before (the pad slot of row r - 2: always zero) is buffer slot 0, zeroed once; rows land from buffer slot 1.
+  // Against 128-slot tiles at arbitrary offsets (halo = up to 6 rows of a 56-wide grid for 2.25 rows of outputs) the halo buffer
+  // shrinks by a third, which is what lets the ring run a tile ahead of the tensor core next to the resident weights.
+  const int R = p.tile_rows;
+  const int tile_slots = R ? R * p.Wp : BM;
 
-  for (int c = tid; c < 16 * p.n_tile; c += P_THREADS) s_part[c] = 0;
+  for (int c = tid; c < 32 * p.n_tile; c += P_THREADS) s_part[c] = 0;
   if (tid == 0) {
     mbar_init(&b_full, 1);
     for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
@@ -866,7 +873,15 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
   }
   if (warp == P_A_WARP && lane < p.n_seg) tma_prefetch_desc(&p.tmap[lane]);
   if (p.img_box) zero_halo_margins(a_smem, NA, p.halo_bytes, p.HL, p.Wp, tid, P_THREADS);
-  else if (p.any_up) zero_pad_column(a_smem, NA, p.halo_bytes, p.nr_max, p.Wp, tid, P_THREADS);
+  else if (p.any_up) zero_pad_column(a_smem, NA, p.halo_bytes, p.nr_max, p.Wp, tid, P_THREADS, R ? 1 : 0);
+  if (R) {   // buffer slot 0 and the slot after the last row: never written by the copy engine
+    for (int i = tid; i < NA * 2 * 8; i += P_THREADS) {
+      const int q = i & 7, which = (i >> 3) & 1, buf = i >> 4;
+      const int slot = which ? 1 + (R + 2) * p.Wp : 0;
+      *reinterpret_cast<uint4*>(a_smem + (size_t)buf * p.halo_bytes + (size_t)slot * 128 + q * 16) = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async();
+  }
   pdl_wait();
   for (int c = tid; c < p.n_tile; c += P_THREADS) s_bias[c] = (p.bias && c < p.c_bias) ? p.bias[c] : 0.f;
   tc_fence_before();
@@ -874,19 +889,31 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp < 4) {
-    // ================= epilogue warps: drain accumulator it & 1 ====================================
+  if (warp < 8) {
+    // ================= epilogue: warps 0-3 drain accumulator 0 (even tiles), warps 4-7 accumulator 1 (odd tiles) ==========
+    // (with the BatchNorm sums one group of four warps needs ~4 600 cycles per 64-column tile, the MMAs ~3 300: measured with
+    // MG_PHASE_PROF; two groups keep the drain off the critical path)
+    const int grp = warp >> 2, qw = warp & 3;
     const bool want_stats = p.stats != nullptr;
-    for (int it = 0; it < n_my; ++it) {
+#ifdef MG_PHASE_PROF
+    long long e_wait = 0, e_work = 0;
+#endif
+    for (int it = grp; it < n_my; it += 2) {
       const int mt = blockIdx.x + it * gridDim.x;
       const int acc = it & 1;
-      const int row = warp * 32 + lane;
+      const int row = qw * 32 + lane;
       uint32_t pix = 0;
-      const bool row_ok = slot_pixel(p, (int64_t)mt * BM + row, &pix);
+      const bool row_ok = row < tile_slots && slot_pixel(p, (int64_t)mt * tile_slots + row, &pix);
+#ifdef MG_PHASE_PROF
+      const long long e0 = clock64();
+#endif
       mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       tc_fence_after();
+#ifdef MG_PHASE_PROF
+      const long long e1 = clock64();
+#endif
       __nv_bfloat16* yrow = p.y + (size_t)pix * p.y_pitch;
-      const uint32_t tcol = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * p.n_tile);
+      const uint32_t tcol = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)(acc * p.n_tile);
       for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
         uint32_t a16[16];
         tc_ld16(tcol + (uint32_t)c0, a16);
@@ -929,14 +956,20 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);   // 128 arrivals: the accumulator may be overwritten
+#ifdef MG_PHASE_PROF
+      e_wait += e1 - e0; e_work += clock64() - e1;
+#endif
     }
+#ifdef MG_PHASE_PROF
+    if (blockIdx.x == 3 && tid == 0) printf("epilogue warp0: tiles %d wait_tmem_full %lld work %lld cycles/tile\n", n_my, e_wait / n_my, e_work / n_my);
+#endif
     if (want_stats) {
-      asm volatile("bar.sync 3, 128;" ::: "memory");
-      for (int c = tid; c < p.n_tile; c += 128)
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      for (int c = tid; c < p.n_tile; c += 256)
         if (c < p.c_stats) {
           long long ah = 0, al = 0, bh = 0, bl = 0;
 #pragma unroll
-          for (int w = 0; w < 4; ++w) {
+          for (int w = 0; w < 8; ++w) {
             const long long* sa = s_part + (size_t)((w * 2) * p.n_tile + c) * 2;
             const long long* sb = s_part + (size_t)((w * 2 + 1) * p.n_tile + c) * 2;
             ah += sa[0]; al += sa[1]; bh += sb[0]; bl += sb[1];
@@ -950,15 +983,15 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
     Ring ra(NA);
     int ac = 0;
     for (int it = 0; it < n_my; ++it) {
-      const int t0 = (int)(blockIdx.x + it * gridDim.x) * BM;
+      const int t0 = (int)(blockIdx.x + it * gridDim.x) * tile_slots;
       const int hs = t0 - p.Wp - 1;
-      const int r0 = floordiv(hs, p.Wp);
-      const int nr = (hs + p.HL - 1) / p.Wp - r0 + 1;
+      const int r0 = R ? t0 / p.Wp - 1 : floordiv(hs, p.Wp);
+      const int nr = R ? R + 2 : (hs + p.HL - 1) / p.Wp - r0 + 1;
       for (int c = 0; c < p.n_chunks; ++c, ++ac, ra.next()) {
         const int buf = ra.idx;
         if (ac >= NA) mbar_wait(&a_empty[buf], ra.phase ^ 1u);
         const HChunk ch = p.chunk[c];
-        const uint32_t dst = smem_u32(a_smem + (size_t)buf * p.halo_bytes);
+        const uint32_t dst = smem_u32(a_smem + (size_t)buf * p.halo_bytes) + (R ? 128u : 0u);
         if (p.img_box) tma_load_images(&p.tmap[ch.seg], dst + (uint32_t)(p.Wp + 1) * 128u, &a_full[buf], ch.c0, t0 / (p.Hp * p.Wp), (uint32_t)BM * 128u, lane);
         else tma_load_rows(&p.tmap[ch.seg], p.seg_up[ch.seg], dst, &a_full[buf], ch.c0, r0, nr, p.W, p.Hp, lane);
       }
@@ -977,18 +1010,34 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
     const uint32_t b_base = smem_u32(b_smem);
     Ring ra(NA);
     mbar_wait(&b_full, 0);
+#ifdef MG_PHASE_PROF
+    long long m_wait_e = 0, m_wait_a = 0, m_issue = 0, m_t0 = clock64();
+#endif
     for (int it = 0; it < n_my; ++it) {
       const int acc = it & 1;
+#ifdef MG_PHASE_PROF
+      const long long q0 = clock64();
+#endif
       if (it >= 2) { mbar_wait(&tmem_empty[acc], ((it >> 1) - 1) & 1); tc_fence_after(); }
+#ifdef MG_PHASE_PROF
+      m_wait_e += clock64() - q0;
+#endif
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
-      const int t0 = (int)(blockIdx.x + it * gridDim.x) * BM;
+      const int t0 = (int)(blockIdx.x + it * gridDim.x) * tile_slots;
       const int hs = t0 - p.Wp - 1;
-      const int off = p.img_box ? 0 : hs - floordiv(hs, p.Wp) * p.Wp;
+      const int off = (p.img_box || R) ? 0 : hs - floordiv(hs, p.Wp) * p.Wp;
       for (int c = 0; c < p.n_chunks; ++c, ra.next()) {
         const int buf = ra.idx;
         const HChunk ch = p.chunk[c];
+#ifdef MG_PHASE_PROF
+        const long long q1 = clock64();
+#endif
         mbar_wait(&a_full[buf], ra.phase);
         tc_fence_after();
+#ifdef MG_PHASE_PROF
+        const long long q2 = clock64();
+        m_wait_a += q2 - q1;
+#endif
         const uint32_t a_base = smem_u32(a_smem + (size_t)buf * p.halo_bytes) + (uint32_t)off * 128u;
         const int tps = ch.tps, ksteps = ch.ksteps;
         const uint32_t sub_lo = 8u / (uint32_t)tps;
@@ -1004,14 +1053,224 @@ __global__ void __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_kernel
           }
           tc_commit(&a_empty[buf]);
         }
+#ifdef MG_PHASE_PROF
+        m_issue += clock64() - q2;
+#endif
       }
       if (leader) tc_commit(&tmem_full[acc]);
     }
+#ifdef MG_PHASE_PROF
+    if (blockIdx.x == 3 && lane == 0) printf("MMA warp: tiles %d total %lld wait_tmem_empty %lld wait_a_full %lld issue %lld cycles/tile\n", n_my, (clock64() - m_t0) / n_my, m_wait_e / n_my, m_wait_a / n_my, m_issue / n_my);
+#endif
   }
   __syncthreads();
   if (warp == P_MMA_WARP) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+
+// ---------------------------------------------------------------- persistent CTA-pair halo kernel ----------
+// The weight-resident kernel on tcgen05 CTA pairs: each CTA keeps HALF of every weight stage (so the ring of halos next to it is
+// deep enough to run two tiles ahead: on the 56 x 56 layers the single-CTA kernel holds 115 KB of weights and two halo buffers, and
+// every tile exposes the copy engine's latency), the pair walks tile pairs (2 * (pair + it * P) + rank), one M = 256 MMA per K step
+// serves both tiles.  Needs a tile offset that is the same in both CTAs: row-aligned tiles or whole-image boxes.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1) umma_conv_halo_persistent_pair_kernel(const __grid_constant__ HParams p) {
+  pdl_launch();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t b_full, a_full[P_MAX_ABUF], a_empty[P_MAX_ABUF], tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int NA = p.n_abuf;
+  const int b_half_bytes = (p.n_tile >> 1) * 128;
+  uint8_t* a_smem = smem;
+  uint8_t* b_smem = smem + (size_t)NA * p.halo_bytes;                                  // this CTA's half of all weight stages
+  long long* s_part = reinterpret_cast<long long*>(b_smem + (size_t)p.n_stages * b_half_bytes);
+  float* s_bias = reinterpret_cast<float*>(s_part + 32 * p.n_tile);
+  const int R = p.tile_rows;
+  const int tile_slots = R ? R * p.Wp : BM;
+  const int pair = (int)blockIdx.x >> 1, P = (int)gridDim.x >> 1;
+  const int pair_tiles = (p.m_tiles + 1) >> 1;                                         // tile pairs in total
+  const int n_my = (pair_tiles - pair + P - 1) / P;                                    // the same in both CTAs of a pair
+
+  for (int c = tid; c < 32 * p.n_tile; c += P_THREADS) s_part[c] = 0;
+  if (tid == 0) {
+    mbar_init(&b_full, 1);
+    for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 256); }   // epilogue threads of both CTAs
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == P_MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  if (warp == P_A_WARP && lane < p.n_seg) tma_prefetch_desc(&p.tmap[lane]);
+  if (warp == P_B_WARP && lane == 0) tma_prefetch_desc(&p.tmap_w);
+  if (p.img_box) zero_halo_margins(a_smem, NA, p.halo_bytes, p.HL, p.Wp, tid, P_THREADS);
+  else if (p.any_up) zero_pad_column(a_smem, NA, p.halo_bytes, p.nr_max, p.Wp, tid, P_THREADS, R ? 1 : 0);
+  if (R) {
+    for (int i = tid; i < NA * 2 * 8; i += P_THREADS) {
+      const int q = i & 7, which = (i >> 3) & 1, buf = i >> 4;
+      const int slot = which ? 1 + (R + 2) * p.Wp : 0;
+      *reinterpret_cast<uint4*>(a_smem + (size_t)buf * p.halo_bytes + (size_t)slot * 128 + q * 16) = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async();
+  }
+  pdl_wait();
+  for (int c = tid; c < p.n_tile; c += P_THREADS) s_bias[c] = (p.bias && c < p.c_bias) ? p.bias[c] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp < 8) {
+    // ================= epilogue: this CTA's tile of the pair; warps 0-3 even iterations, warps 4-7 odd ones ===========
+    const int grp = warp >> 2, qw = warp & 3;
+    const bool want_stats = p.stats != nullptr;
+    for (int it = grp; it < n_my; it += 2) {
+      const int mt = 2 * (pair + it * P) + (int)rank;
+      const int acc = it & 1;
+      const int row = qw * 32 + lane;
+      uint32_t pix = 0;
+      const bool row_ok = mt < p.m_tiles && row < tile_slots && slot_pixel(p, (int64_t)mt * tile_slots + row, &pix);
+      mbar_wait_cluster(&tmem_full[acc], (it >> 1) & 1);
+      tc_fence_after();
+      __nv_bfloat16* yrow = p.y + (size_t)pix * p.y_pitch;
+      const uint32_t tcol = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)(acc * p.n_tile);
+      for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+        uint32_t a16[16];
+        tc_ld16(tcol + (uint32_t)c0, a16);
+        tc_wait_ld();
+        uint32_t pk[2][4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int n0 = c0 + h * 8;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = __uint_as_float(a16[h * 8 + 2 * e]) + s_bias[c0 + h * 8 + 2 * e];
+            const float b = __uint_as_float(a16[h * 8 + 2 * e + 1]) + s_bias[c0 + h * 8 + 2 * e + 1];
+            __nv_bfloat162 t2 = __floats2bfloat162_rn(a, b);
+            pk[h][e] = *reinterpret_cast<uint32_t*>(&t2);
+          }
+          if (row_ok && n0 + 8 <= p.c_valid) *reinterpret_cast<uint4*>(yrow + n0) = make_uint4(pk[h][0], pk[h][1], pk[h][2], pk[h][3]);
+        }
+        if (want_stats) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const bool use = row_ok && c0 + h * 8 + 8 <= p.c_valid;
+            float sv[16];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float ra = use ? __uint_as_float(pk[h][e] << 16) : 0.f, rb = use ? __uint_as_float(pk[h][e] & 0xFFFF0000u) : 0.f;
+              sv[2 * e] = ra; sv[2 * e + 1] = rb;
+              sv[8 + 2 * e] = ra * ra; sv[8 + 2 * e + 1] = rb * rb;
+            }
+            const float tot = warp_reduce_scatter16(sv, lane);
+            if (lane < 16) {
+              long long fh, fl;
+              mg_to_fix_f32(tot, fh, fl);
+              long long* sp = s_part + (size_t)((warp * 2 + (lane >> 3)) * p.n_tile + c0 + h * 8 + (lane & 7)) * 2;
+              sp[0] += fh; sp[1] += fl;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(&tmem_empty[acc], 0);   // 256 arrivals on the even CTA's barrier: both tiles drained
+    }
+    if (want_stats) {
+      asm volatile("bar.sync 3, 256;" ::: "memory");
+      for (int c = tid; c < p.n_tile; c += 256)
+        if (c < p.c_stats) {
+          long long ah = 0, al = 0, bh = 0, bl = 0;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) {
+            const long long* sa = s_part + (size_t)((w * 2) * p.n_tile + c) * 2;
+            const long long* sb = s_part + (size_t)((w * 2 + 1) * p.n_tile + c) * 2;
+            ah += sa[0]; al += sa[1]; bh += sb[0]; bl += sb[1];
+          }
+          mg_sum_add_fix(p.stats + c, ah, al);
+          mg_sum_add_fix(p.stats + p.c_stats + c, bh, bl);
+        }
+    }
+  } else if (warp == P_A_WARP) {
+    // ================= halo producer: this CTA's tile; bytes of both CTAs counted on the even CTA's barrier ==========
+    Ring ra(NA);
+    int ac = 0;
+    for (int it = 0; it < n_my; ++it) {
+      const int t0 = (2 * (pair + it * P) + (int)rank) * tile_slots;
+      const int r0 = t0 / p.Wp - 1;
+      const int nr = R + 2;
+      for (int c = 0; c < p.n_chunks; ++c, ++ac, ra.next()) {
+        const int buf = ra.idx;
+        if (ac >= NA) mbar_wait_cluster(&a_empty[buf], ra.phase ^ 1u);
+        const HChunk ch = p.chunk[c];
+        const uint32_t dst = smem_u32(a_smem + (size_t)buf * p.halo_bytes) + (R ? 128u : 0u);
+        if (p.img_box) {
+          if (lane == 0) {
+            if (rank == 0) mbar_arrive_expect_tx(&a_full[buf], 2u * (uint32_t)BM * 128u);
+            tma_load_4d_pair(dst + (uint32_t)(p.Wp + 1) * 128u, &p.tmap[ch.seg], &a_full[buf], ch.c0, 0, 0, t0 / (p.Hp * p.Wp));
+          }
+        } else {
+          const int up = p.seg_up[ch.seg];
+          if (rank == 0 && lane == 0) mbar_arrive_expect_tx(&a_full[buf], 2u * (uint32_t)nr * (uint32_t)(up ? p.W : p.Wp) * 128u);
+          __syncwarp();
+          tma_load_rows_pair(&p.tmap[ch.seg], up, dst, &a_full[buf], ch.c0, r0, nr, p.W, p.Hp, lane);
+        }
+      }
+    }
+  } else if (warp == P_B_WARP) {
+    // ================= weight loader: this CTA's half of every stage, once =============================
+    if (lane == 0) {
+      if (rank == 0) mbar_arrive_expect_tx(&b_full, (uint32_t)(2 * p.n_stages * b_half_bytes));
+      for (int q = 0; q < p.n_stages; ++q)
+        tma_load_2d_pair(smem_u32(b_smem + (size_t)q * b_half_bytes), &p.tmap_w, &b_full, 0, q * p.n_tile + (int)rank * (p.n_tile >> 1));
+    }
+  } else if (rank == 0) {
+    // ================= MMA issuer (even CTA): M = 256 across the pair =================
+    const bool leader = elect_one();
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    const uint32_t b_base = smem_u32(b_smem);
+    Ring ra(NA);
+    mbar_wait_cluster(&b_full, 0);
+    for (int it = 0; it < n_my; ++it) {
+      const int acc = it & 1;
+      if (it >= 2) { mbar_wait_cluster(&tmem_empty[acc], ((it >> 1) - 1) & 1); tc_fence_after(); }
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.n_tile);
+      for (int c = 0; c < p.n_chunks; ++c, ra.next()) {
+        const int buf = ra.idx;
+        const HChunk ch = p.chunk[c];
+        mbar_wait_cluster(&a_full[buf], ra.phase);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(a_smem + (size_t)buf * p.halo_bytes);
+        const int tps = ch.tps, ksteps = ch.ksteps;
+        const uint32_t sub_lo = 8u / (uint32_t)tps;
+        if (leader) {
+          int sub = 0, st = ch.stage0;
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t a_lo = desc_lo_k_sw128(a_base + (uint32_t)((tap / 3) * p.Wp + (tap % 3)) * 128u);
+            const uint32_t b_lo = desc_lo_k_sw128(b_base + (uint32_t)(st * b_half_bytes)) + (uint32_t)sub * sub_lo;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (q < ksteps) tc_mma_bf16_lohi_pair(d_tmem, a_lo + (uint32_t)(q * 2), b_lo + (uint32_t)(q * 2), DESC_HI_SW128, idesc, (uint32_t)((c | tap | q) != 0));
+            if (++sub == tps) { sub = 0; ++st; }
+          }
+          tc_commit_pair(&a_empty[buf]);
+        }
+      }
+      if (leader) tc_commit_pair(&tmem_full[acc]);
+    }
+  }
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == P_MMA_WARP) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
 }
 
@@ -1612,23 +1871,43 @@ static int launch_halo(mg_ctx* ctx, HParams& p, const Geometry& g, int algo, con
 }
 
 // shared-memory plan of the persistent kernel, or false when the weights do not fit / the launch is too small to pay off
-struct PersistPlan { int n_abuf, smem, tmem_cols, grid; };
+struct PersistPlan { int n_abuf, smem, tmem_cols, grid, tile_rows, halo_bytes, pair; };
+// row-aligned tiles of the persistent kernel: R whole slot rows per tile when they fill at least 85 % of the 128 MMA rows
+static int persist_tile_rows(const mg_conv_desc* d, int Nimg, bool any_up) {
+  const int Wp = d->W + 1, Hp = d->H + 1;
+  if (Wp > BM) return 0;
+  if (!any_up && BM % (Hp * Wp) == 0) return 0;          // whole-image boxes (7 x 7 grids) are better still
+  const int R = BM / Wp;
+  if (R < 1 || R * Wp * 100 < BM * 85) return 0;
+  (void)Nimg;
+  return R;
+}
 static bool persist_plan(const mg_ctx* ctx, const mg_conv_desc* d, const Geometry& g, int Nimg, int algo, PersistPlan* pl) {
   static int on = -1, min_tiles_per_sm = -1;
   if (on < 0) { const char* e = getenv("MGCONV_PERSIST"); on = e ? atoi(e) : 1; }
   if (min_tiles_per_sm < 0) { const char* e = getenv("MGCONV_PERSIST_MIN_TILES"); min_tiles_per_sm = e ? atoi(e) : 4; }
   if (algo == MG_ALGO_TILE128 || algo == MG_ALGO_TILE256 || algo == MG_ALGO_TILE128_DEEP || algo == MG_ALGO_TILE256_DEEP ||
       algo == MG_ALGO_TILE128_MID || algo == MG_ALGO_PAIR128 || algo == MG_ALGO_PAIR256) return false;
-  const bool forced = algo == MG_ALGO_RESIDENT || ctx->tune_persist == 1;
+  const bool pair = algo == MG_ALGO_RESIDENT_PAIR;
+  const bool forced = algo == MG_ALGO_RESIDENT || pair || ctx->tune_persist == 1;
   if (!forced && (ctx->tune_persist == 2 || !on)) return false;
   if (!g.halo || g.n_tiles != 1) return false;
   HParams hp;
   hp.Wp = d->W + 1; hp.img_box = 0;     // sized for the row mode (the whole-image mode needs no more)
   halo_geometry(hp, BM);
-  const int64_t m_tiles = mg_cdiv((int64_t)Nimg * (d->H + 1) * hp.Wp, BM);
+  bool any_up = false;
+  for (int s = 0; s < d->n_seg; ++s) any_up = any_up || d->seg_mode[s] == MG_SEG_UP;
+  // row-aligned tiles: always for CTA pairs (same tile offset in both CTAs); for the single-CTA kernel only on request -- its
+  // ring stays two tiles short either way and 12 % more tiles cost more than the smaller halo saves (measured: 125 -> 133 us)
+  static int aligned_single = -1;
+  if (aligned_single < 0) { const char* e = getenv("MGCONV_PERSIST_ALIGNED"); aligned_single = e ? atoi(e) : 0; }
+  const int R = (pair || aligned_single) ? persist_tile_rows(d, Nimg, any_up && g.n_chunks > 0) : 0;
+  if (R) hp.halo_bytes = mg_round_up(((R + 2) * hp.Wp + 2) * 128, 1024);
+  const int64_t m_tiles = R ? mg_cdiv((int64_t)Nimg * (d->H + 1), R) : mg_cdiv((int64_t)Nimg * (d->H + 1) * hp.Wp, BM);
   if (!forced && m_tiles < (int64_t)min_tiles_per_sm * ctx->num_sms) return false;
-  const int b_bytes = g.n_stages * g.n_tile * 128;
-  const int tail = g.n_tile * (4 + 128);                   // bias tile + statistics accumulators (4 warps x 2 sums x 2 int64 limbs)
+  if (pair && !R && !(!any_up && BM % ((d->H + 1) * hp.Wp) == 0)) return false;   // CTA pairs need the same tile offset in both CTAs
+  const int b_bytes = g.n_stages * g.n_tile * (pair ? 64 : 128);                  // a pair keeps half of every stage per CTA
+  const int tail = g.n_tile * (4 + 256);                   // bias tile + statistics accumulators (8 warps x 2 sums x 2 int64 limbs)
   const int room = SMEM_MAX - 1024 - b_bytes - tail;
   int n_abuf = room / hp.halo_bytes;
   if (n_abuf < 2) return false;
@@ -1638,6 +1917,8 @@ static bool persist_plan(const mg_ctx* ctx, const mg_conv_desc* d, const Geometr
   if (cols > 512) return false;
   pl->n_abuf = n_abuf; pl->smem = n_abuf * hp.halo_bytes + b_bytes + tail + 1024; pl->tmem_cols = cols;
   pl->grid = (int)std::min<int64_t>(m_tiles, ctx->num_sms);
+  if (pair) pl->grid = 2 * (int)std::min<int64_t>((m_tiles + 1) / 2, ctx->num_sms / 2);
+  pl->tile_rows = R; pl->halo_bytes = hp.halo_bytes; pl->pair = pair ? 1 : 0;
   return true;
 }
 
@@ -1645,6 +1926,12 @@ static int launch_halo_persistent(mg_ctx* ctx, HParams& p, const PersistPlan& pl
   { int rc = halo_tensor_maps(ctx, p, segs, BM); if (rc) return rc; }
   halo_geometry(p, BM);
   p.m_tiles = (int)mg_cdiv(p.T, BM);
+  p.tile_rows = p.img_box ? 0 : pl.tile_rows;
+  if (p.tile_rows) {
+    p.halo_bytes = pl.halo_bytes;
+    p.nr_max = p.tile_rows + 2;
+    p.m_tiles = (int)mg_cdiv((int64_t)p.Nimg * p.Hp, p.tile_rows);
+  }
   p.tmem_cols = pl.tmem_cols;
   p.n_abuf = pl.n_abuf;
   p.stages = 0;
@@ -1652,6 +1939,19 @@ static int launch_halo_persistent(mg_ctx* ctx, HParams& p, const PersistPlan& pl
   if (!attr_set) {
     MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
     attr_set = true;
+  }
+  if (pl.pair) {
+    int rc = mg_tensor_map(ctx, p.wpack, p.n_stages * p.n_tile, 0, 0, 0, 5, p.n_tile / 2, &p.tmap_w);
+    if (rc) return rc;
+    static bool pair_attr = false;
+    if (!pair_attr) {
+      MG_CUDA(ctx, cudaFuncSetAttribute(umma_conv_halo_persistent_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
+      pair_attr = true;
+    }
+    MG_CUDA(ctx, mg_launch_pdl(umma_conv_halo_persistent_pair_kernel, dim3(pl.grid), dim3(P_THREADS), (size_t)pl.smem, ctx->stream, p));
+    MG_CHECK_LAUNCH(ctx);
+    ctx->tc_launches++;
+    return MG_OK;
   }
   MG_CUDA(ctx, mg_launch_pdl(umma_conv_halo_persistent_kernel, dim3(pl.grid), dim3(P_THREADS), (size_t)pl.smem, ctx->stream, p));
   MG_CHECK_LAUNCH(ctx);

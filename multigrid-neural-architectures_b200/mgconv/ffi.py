@@ -15,7 +15,7 @@ MG_SEG_SAME, MG_SEG_POOL, MG_SEG_UP, MG_SRC_POOL3 = 0, 1, 2, 3
 MG_IMPL_AUTO, MG_IMPL_SIMT, MG_IMPL_TCGEN05 = 0, 1, 2
 MG_TUNE_HALO_SUBTILES, MG_TUNE_PERSISTENT, MG_TUNE_STEM_FUSED_STATS = 0, 1, 2
 MG_ALGO_AUTO, MG_ALGO_TILE128, MG_ALGO_TILE256, MG_ALGO_RESIDENT, MG_ALGO_TILE128_DEEP, MG_ALGO_TILE256_DEEP, MG_ALGO_TILE128_MID = 0, 1, 2, 3, 4, 5, 6
-MG_ALGO_PAIR128, MG_ALGO_PAIR256 = 7, 8
+MG_ALGO_PAIR128, MG_ALGO_PAIR256, MG_ALGO_RESIDENT_PAIR = 7, 8, 9
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MGCONV_LIB", os.path.join(_HERE, "libmgconv.so"))

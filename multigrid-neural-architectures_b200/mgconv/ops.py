@@ -282,7 +282,7 @@ class ConvOp(Op):
         (cudnn.benchmark = true of the reference, models/ilsvrc/rnmg.lua:230-231)"""
         best, best_t = 0, None
         for algo in (ffi.MG_ALGO_TILE128, ffi.MG_ALGO_TILE256, ffi.MG_ALGO_RESIDENT, ffi.MG_ALGO_TILE128_DEEP, ffi.MG_ALGO_TILE256_DEEP,
-                     ffi.MG_ALGO_TILE128_MID, ffi.MG_ALGO_PAIR128, ffi.MG_ALGO_PAIR256):
+                     ffi.MG_ALGO_TILE128_MID, ffi.MG_ALGO_PAIR128, ffi.MG_ALGO_PAIR256, ffi.MG_ALGO_RESIDENT_PAIR):
             setattr(self.desc, field, algo)
             run()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -209,10 +209,10 @@ EDGE_CASES += [
 # kernel-selection overrides: automatic, two sub-tiles per CTA, persistent weight-resident kernel
 # (context sub-tile override, context persistent override, per-layer algo of the descriptor)
 TUNINGS = [(0, 0, 0), (2, 2, 0), (1, 1, 0), (0, 0, ffi.MG_ALGO_TILE128_DEEP), (0, 0, ffi.MG_ALGO_TILE256_DEEP), (0, 2, ffi.MG_ALGO_RESIDENT),
-           (0, 0, ffi.MG_ALGO_TILE128_MID), (0, 0, ffi.MG_ALGO_PAIR128), (0, 0, ffi.MG_ALGO_PAIR256)]
+           (0, 0, ffi.MG_ALGO_TILE128_MID), (0, 0, ffi.MG_ALGO_PAIR128), (0, 0, ffi.MG_ALGO_PAIR256), (0, 2, ffi.MG_ALGO_RESIDENT_PAIR)]
 
 
-@pytest.mark.parametrize("tuning", TUNINGS, ids=["auto", "subtiles2", "persistent", "algo_tile128deep", "algo_tile256deep", "algo_resident", "algo_tile128mid", "algo_pair128", "algo_pair256"])
+@pytest.mark.parametrize("tuning", TUNINGS, ids=["auto", "subtiles2", "persistent", "algo_tile128deep", "algo_tile256deep", "algo_resident", "algo_tile128mid", "algo_pair128", "algo_pair256", "algo_resident_pair"])
 @pytest.mark.parametrize("case", EDGE_CASES, ids=[f"case{i}" for i in range(len(EDGE_CASES))])
 def test_conv_edge_shapes_tcgen05(case, tuning):
     """forward / dgrad / wgrad of the bf16 tensor-core path on ragged, tiny, wide and multi-tile shapes,
