@@ -199,7 +199,7 @@ def main():
     model.cuda()
     criterion = net.createCriterion()
     params, grads = model.getParameters()
-    rule = net.trainRule(1, B.Opt())
+    rule = net.trainRule(1, B.Opt(nEpochs=20))   # opts.lua:32: -nEpochs defaults to 20
     optimState = dict(learningRate=rule["LR"], momentum=0.9, weightDecay=rule["WD"], dampening=0.0, learningRateDecay=0.0)
 
     Bsz = args.batch or shape[0]
