@@ -492,12 +492,13 @@ class ApplyOp(Op):
                              _keys(self.G, bn.gradWeight, bn.gradBias, self.conv.mod.gradBias)))
         return io
 
-    def fwd(self, E):
+    def fwd(self, E, synced=False):
+        """synced: the engine has already all-reduced this layer's statistics together with those of the other scales of the stage"""
         bn = self.bn
         rg = C.byref(self.rg) if self.rg is not None else None
         pg = C.byref(self.pg) if self.pg is not None else None
         if bn is not None:
-            if E.bn_sync and E.training:   # cross-replica statistics: sum (sum y, sum y^2) over the ranks
+            if E.bn_sync and E.training and not synced:   # cross-replica statistics: sum (sum y, sum y^2) over the ranks
                 E.ctx.call("mg_allreduce_inline", ptr(self.conv.sums), self.conv.sums.numel(), 2)   # int64 limbs of mg_sum
             # SpatialBatchNormalization finalisation + CAddTable + ReLU + pooled companion in one pass
             E.ctx.call("mg_bn_residual_forward", C.byref(self.zg), C.byref(self._bn_struct(E)), rg, int(self.relu), C.byref(self.og), pg)
@@ -524,12 +525,18 @@ class ApplyOp(Op):
             y.G = t.grid(D)
 
     def bwd(self, E):
+        self.bwd_combine(E)
+        self.bwd_bn(E)
+
+    def bwd_combine(self, E):
         if self.pc is not None:
             self.pc.run()
         self.comb.run()
+
+    def bwd_bn(self, E, synced=False):
         bn = self.bn
         if bn is not None:
-            if E.bn_sync:
+            if E.bn_sync and not synced:
                 E.ctx.call("mg_allreduce_inline", ptr(self.dsums), self.dsums.numel(), 2)
             E.ctx.call("mg_bn_backward", C.byref(self.yraw), C.byref(self.dg), C.byref(self.gg), ptr(self.dsums), self.count * max(1, E.bn_sync),
                        ptr(bn.weight), ptr(self.mean), ptr(self.invstd), ptr(bn.gradWeight), ptr(bn.gradBias),
