@@ -130,6 +130,13 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   __trap();
 }
 
+// shared -> global bulk copy (async proxy; the issuing thread waits with bulk_store_wait before its shared memory is reused or released)
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_wait() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // Position in a ring of n slots walked once per loop iteration k: idx = k % n, phase = (k / n) & 1, without the integer
 // divisions (ring sizes are run-time values; in the single-thread issue loops each emulated division is ~20 dependent
 // instructions, several per pipeline stage).

@@ -393,6 +393,8 @@ struct HParams {
   int m_tiles;        // persistent kernel: 128-slot tiles in total
   CUtensorMap tmap_w; // pair kernels: the packed weight image as rows of 128 bytes (tma.cuh kind 5)
   int tile_rows;      // persistent kernel, row-aligned tiles: a tile is tile_rows whole slot rows (tile_rows * Wp <= 128 slots), 0 = 128-slot tiles
+  int epi_stage;      // halo / pair kernels: the epilogue stages every output row in shared memory (byte offset of the staging area + 1, 0 = direct
+                      // stores) and hands it to the copy engine as ONE bulk store per row
 };
 
 // zero the pad column (slot x == W of every row) of `nbuf` halo buffers: the up-sampling box writes only the W valid slots
@@ -495,6 +497,13 @@ __global__ void __launch_bounds__(32 * (4 * MT + 3), MT == 1 ? 4 : 2) umma_conv_
     const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * p.n_tile);
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
+    // Output rows leave through the copy engine: the lane writes its row (n_tile bf16 values) into a shared-memory staging row --
+    // pitch n_tile * 2 + 16 bytes, so the 16-byte stores of a quarter warp hit distinct banks -- and issues ONE bulk store for it.
+    // Direct stores are 2 * n_tile / 16 instructions per thread, each scattering 32 lanes over 32 different 128-byte lines: measured
+    // (MG_PHASE_PROF) 9 300 cycles per 128 x 192 tile, a third of the CTA's lifetime.  Every MMA has completed: the halo buffers and
+    // the weight ring are free.
+    const int stage_pitch = p.n_tile * 2 + 16;
+    uint8_t* stage_row = p.epi_stage ? smem + (p.epi_stage - 1) + (size_t)row * stage_pitch : nullptr;
     for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
       uint32_t acc[16];
       tc_ld16(tacc + (uint32_t)c0, acc);
@@ -510,7 +519,8 @@ __global__ void __launch_bounds__(32 * (4 * MT + 3), MT == 1 ? 4 : 2) umma_conv_
           __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
           pk[h][e] = *reinterpret_cast<uint32_t*>(&t);
         }
-        if (row_ok && n0 + 8 <= p.c_valid) *reinterpret_cast<uint4*>(yrow + n0) = make_uint4(pk[h][0], pk[h][1], pk[h][2], pk[h][3]);
+        if (stage_row) *reinterpret_cast<uint4*>(stage_row + (c0 + h * 8) * 2) = make_uint4(pk[h][0], pk[h][1], pk[h][2], pk[h][3]);
+        else if (row_ok && n0 + 8 <= p.c_valid) *reinterpret_cast<uint4*>(yrow + n0) = make_uint4(pk[h][0], pk[h][1], pk[h][2], pk[h][3]);
       }
       if (want_stats) {
 #pragma unroll
@@ -526,6 +536,14 @@ __global__ void __launch_bounds__(32 * (4 * MT + 3), MT == 1 ? 4 : 2) umma_conv_
           const float tot = warp_reduce_scatter16(sv, lane);   // lane l: (l & 15) < 8 -> sum of column, else sum of squares
           if (lane < 16) s_part[(warp * 2 + (lane >> 3)) * 256 + c0 + h * 8 + (lane & 7)] = tot;
         }
+      }
+    }
+    if (stage_row) {
+      const int ncols = min(p.n_tile, p.c_valid - n_base);          // columns of this tile inside the row pitch (multiple of 8)
+      if (row_ok && ncols > 0) {
+        fence_proxy_async();                                        // this thread's staging writes -> visible to the copy engine
+        bulk_s2g(yrow + n_base, smem_u32(stage_row), (uint32_t)ncols * 2u);
+        bulk_store_commit();
       }
     }
     tc_fence_before();
@@ -547,6 +565,7 @@ __global__ void __launch_bounds__(32 * (4 * MT + 3), MT == 1 ? 4 : 2) umma_conv_
         }
       }
     }
+    if (stage_row) bulk_store_wait();   // the copy engine has read (and written) this thread's row before the CTA's shared memory goes away
   } else if (warp == A_WARP) {
     // ================= halo producer: one TMA per slot row and chunk ============================
     Ring ra(p.n_abuf);
@@ -689,6 +708,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * MT + 3), M
     const uint32_t tacc = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * p.n_tile);
     mbar_wait_cluster(&tmem_full_bar, 0);
     tc_fence_after();
+    // Output rows leave through the copy engine: the lane writes its row (n_tile bf16 values) into a shared-memory staging row --
+    // pitch n_tile * 2 + 16 bytes, so the 16-byte stores of a quarter warp hit distinct banks -- and issues ONE bulk store for it.
+    // Direct stores are 2 * n_tile / 16 instructions per thread, each scattering 32 lanes over 32 different 128-byte lines: measured
+    // (MG_PHASE_PROF) 9 300 cycles per 128 x 192 tile, a third of the CTA's lifetime.  Every MMA has completed: the halo buffers and
+    // the weight ring are free.
+    const int stage_pitch = p.n_tile * 2 + 16;
+    uint8_t* stage_row = p.epi_stage ? smem + (p.epi_stage - 1) + (size_t)row * stage_pitch : nullptr;
     for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
       uint32_t acc[16];
       tc_ld16(tacc + (uint32_t)c0, acc);
@@ -704,7 +730,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * MT + 3), M
           __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
           pk[h][e] = *reinterpret_cast<uint32_t*>(&t);
         }
-        if (row_ok && n0 + 8 <= p.c_valid) *reinterpret_cast<uint4*>(yrow + n0) = make_uint4(pk[h][0], pk[h][1], pk[h][2], pk[h][3]);
+        if (stage_row) *reinterpret_cast<uint4*>(stage_row + (c0 + h * 8) * 2) = make_uint4(pk[h][0], pk[h][1], pk[h][2], pk[h][3]);
+        else if (row_ok && n0 + 8 <= p.c_valid) *reinterpret_cast<uint4*>(yrow + n0) = make_uint4(pk[h][0], pk[h][1], pk[h][2], pk[h][3]);
       }
       if (want_stats) {
 #pragma unroll
@@ -720,6 +747,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * MT + 3), M
           const float tot = warp_reduce_scatter16(sv, lane);
           if (lane < 16) s_part[(warp * 2 + (lane >> 3)) * 256 + c0 + h * 8 + (lane & 7)] = tot;
         }
+      }
+    }
+    if (stage_row) {
+      const int ncols = min(p.n_tile, p.c_valid - n_base);          // columns of this tile inside the row pitch (multiple of 8)
+      if (row_ok && ncols > 0) {
+        fence_proxy_async();                                        // this thread's staging writes -> visible to the copy engine
+        bulk_s2g(yrow + n_base, smem_u32(stage_row), (uint32_t)ncols * 2u);
+        bulk_store_commit();
       }
     }
     tc_fence_before();
@@ -739,6 +774,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (4 * MT + 3), M
         }
       }
     }
+    if (stage_row) bulk_store_wait();   // the copy engine has read (and written) this thread's row before the CTA's shared memory goes away
   } else if (warp == A_WARP) {
     // ================= halo producer: this CTA's rows, bytes counted on the even CTA's barrier =================
     // bytes the pair lands per chunk: rows of both tiles (the even CTA knows its peer's geometry)
@@ -1781,6 +1817,17 @@ static int halo_tensor_maps(mg_ctx* ctx, HParams& p, const mg_grid* segs, int sl
   return MG_OK;
 }
 
+// staging area of the bulk-store epilogue: behind the statistics scratch, if the CTA's shared memory (free once the MMAs are done)
+// holds 128 * MT rows of n_tile * 2 + 16 bytes; returns byte offset + 1, or 0 for direct stores (MGCONV_EPI_STAGE=0)
+static int epilogue_staging(const HParams& p, int MT, int smem_usable) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("MGCONV_EPI_STAGE"); on = e ? atoi(e) : 1; }
+  if (!on) return 0;
+  const int off = p.stats ? MT * 4 * 2 * 256 * 4 : 0;
+  const int need = off + MT * BM * (p.n_tile * 2 + 16);
+  return need <= smem_usable ? off + 1 : 0;
+}
+
 static int launch_halo(mg_ctx* ctx, HParams& p, const Geometry& g, int algo, const mg_grid* segs) {
   const int b_stage = p.n_tile * 128;
   static int budget_env = -1, mt_env = -1;
@@ -1815,6 +1862,7 @@ static int launch_halo(mg_ctx* ctx, HParams& p, const Geometry& g, int algo, con
     p.stages = S;
     const int smem = p.n_abuf * p.halo_bytes + S * half + 1024;
     MG_REQUIRE(ctx, smem <= SMEM_MAX, MG_ERR_UNSUPPORTED, "pair halo conv: %d bytes of shared memory", smem);
+    p.epi_stage = epilogue_staging(p, MT, smem - 1024);
     int rc = mg_tensor_map(ctx, p.wpack, g.n_tiles * p.n_stages * p.n_tile, 0, 0, 0, 5, p.n_tile / 2, &p.tmap_w);
     if (rc) return rc;
     static bool pair_attr_set = false;
@@ -1862,6 +1910,7 @@ static int launch_halo(mg_ctx* ctx, HParams& p, const Geometry& g, int algo, con
   }
   const int smem = p.n_abuf * p.halo_bytes + S * b_stage + 1024;
   MG_REQUIRE(ctx, smem <= SMEM_MAX, MG_ERR_UNSUPPORTED, "halo conv: %d bytes of shared memory", smem);
+  p.epi_stage = epilogue_staging(p, MT, smem - 1024);
   dim3 grid((unsigned)mg_cdiv(p.T, BM * MT), (unsigned)g.n_tiles);
   if (MT == 2) MG_CUDA(ctx, mg_launch_pdl(umma_conv_halo_kernel<2>, grid, dim3(32 * 11), (size_t)smem, ctx->stream, p));
   else MG_CUDA(ctx, mg_launch_pdl(umma_conv_halo_kernel<1>, grid, dim3(32 * 7), (size_t)smem, ctx->stream, p));
