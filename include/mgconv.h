@@ -229,6 +229,10 @@ int mg_avgpool_forward(mg_ctx* ctx, const mg_grid* in, int32_t r, mg_grid* out);
 int mg_im2col(mg_ctx* ctx, const mg_grid* in, int32_t ksize, int32_t stride, int32_t pad, mg_grid* col);
 /* SpatialMaxPooling(3,3,2,2,1,1) of the ImageNet stem (rnmg.lua:183) */
 int mg_pool3s2_forward(mg_ctx* ctx, const mg_grid* in, mg_grid* out, uint8_t* argmax_code /* nullable, bf16 mode */);
+/* SpatialBatchNormalization -> ReLU -> SpatialMaxPooling(3,3,2,2,1,1) of the ImageNet stem (models/ilsvrc/rnmg.lua:181-183) as ONE pass
+ * over the raw conv output z (bf16 contexts): BatchNorm finalisation as in mg_bn_residual_forward, pooled output + arg-max codes; the
+ * full-resolution activation is never written.  Backward: mg_grad_combine with relu_mask = 2 (see there). */
+int mg_bn_relu_pool3_forward(mg_ctx* ctx, const mg_grid* z, const mg_bn_fused* bn, mg_grid* out, uint8_t* argmax_code);
 /* SelectTable(1) -> AvgPool(HxW) -> View: out[n][c] fp32 (rnmg.lua:281-283) */
 int mg_global_avgpool_forward(mg_ctx* ctx, const mg_grid* in, mg_grid* out);
 int mg_global_avgpool_backward(mg_ctx* ctx, const mg_grid* dout, mg_grid* din);
@@ -245,7 +249,9 @@ int mg_upconv2x2_backward(mg_ctx* ctx, const mg_grid* x, const float* w, const m
 /* Sum of all consumers' gradient contributions into tensor x (ConcatTable backward sums
  * its branches), routed through pool argmax / upsample block-sum, times the ReLU mask of x
  * when relu_mask.  Writes d (same shape as x).  If bn_sums != NULL also accumulates
- * (sum d, sum d*xraw) per channel with xraw = bn_x ? bn_x : x (raw data). */
+ * (sum d, sum d*xraw) per channel with xraw = bn_x ? bn_x : x (raw data).
+ * relu_mask = 2 (bf16): the tensor was never stored (mg_bn_relu_pool3_forward); x is its pooled form, the single source routes
+ * through that call's arg-max codes and the mask of an element is the sign of the pooled value it was the arg-max of. */
 int mg_grad_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid* bn_x,
                     int32_t n_src, const mg_grad_src* src, mg_grid* d, mg_sum* bn_sums);
 /* BatchNorm backward given the sums: out = gamma*invstd*(d - mean(d) - xhat*mean(d*xhat))

@@ -16,6 +16,7 @@ bool bf16_bn_bwd_apply(mg_ctx*, const mg_grid* xraw, const mg_grid* d, mg_grid* 
                        const float* mean, const float* invstd, float* dgamma, float* dbeta, float* conv_dbias, float gscale);
 int simt_dbias(mg_ctx* ctx, const mg_grid* g, int Cout, float* dbias, float gscale);
 bool bf16_pool3(mg_ctx*, const mg_grid* in, mg_grid* out, uint8_t* code);
+bool bf16_bn_relu_pool3(mg_ctx*, const mg_grid* z, const mg_bn_fused* bn, mg_grid* out, uint8_t* code);
 bool bf16_import_nchw(mg_ctx*, const float* src, mg_grid* dst);
 bool bf16_avgpool(mg_ctx*, const mg_grid* in, int r, mg_grid* out);
 bool bf16_pool2(mg_ctx*, const mg_grid* in, mg_grid* out, int c_off);
@@ -526,6 +527,18 @@ int mg_bn_residual_forward(mg_ctx* ctx, const mg_grid* z, const mg_bn_fused* bn,
   return mg_residual_forward(ctx, z, s, relu, out, pooled);
 }
 
+int mg_bn_relu_pool3_forward(mg_ctx* ctx, const mg_grid* z, const mg_bn_fused* bn, mg_grid* out, uint8_t* argmax_code) {
+  if (!ctx || !z || !bn || !out || !argmax_code) return MG_ERR_INVALID_ARG;
+  MG_REQUIRE(ctx, z->scale && z->shift, MG_ERR_INVALID_ARG, "bn_relu_pool3: z needs scale / shift workspaces");
+  MG_REQUIRE(ctx, bn->training ? bn->sums != nullptr : (bn->running_mean && bn->running_var), MG_ERR_INVALID_ARG, "bn_relu_pool3: missing statistics");
+  MG_REQUIRE(ctx, out->N == z->N && out->H == (z->H - 1) / 2 + 1 && out->W == (z->W - 1) / 2 + 1 && out->C == z->C, MG_ERR_SHAPE,
+             "bn_relu_pool3: out %dx%dx%d for %dx%dx%d", out->H, out->W, out->C, z->H, z->W, z->C);
+  MG_REQUIRE(ctx, ctx->dtype == MG_BF16, MG_ERR_UNSUPPORTED, "bn_relu_pool3: bf16 contexts only (fp32 runs mg_bn_residual_forward + mg_pool3s2_forward)");
+  MG_REQUIRE(ctx, bf16_bn_relu_pool3(ctx, z, bn, out, argmax_code), MG_ERR_UNSUPPORTED, "bn_relu_pool3: unsupported layout");
+  MG_CHECK_LAUNCH(ctx);
+  return MG_OK;
+}
+
 int mg_bn_stats(mg_ctx* ctx, const mg_grid* y, mg_sum* bn_sums) {
   if (!ctx || !y || !bn_sums) return MG_ERR_INVALID_ARG;
   if (ctx->dtype == MG_BF16 && bf16_bn_stats(ctx, y, bn_sums)) { MG_CHECK_LAUNCH(ctx); return MG_OK; }
@@ -618,6 +631,16 @@ int mg_global_avgpool_backward(mg_ctx* ctx, const mg_grid* dout, mg_grid* din) {
 int mg_grad_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid* bn_x, int32_t n_src,
                     const mg_grad_src* src, mg_grid* d, mg_sum* bn_sums) {
   if (!ctx || !x || !d || n_src < 0 || n_src > MG_MAX_SRC || (n_src && !src)) return MG_ERR_INVALID_ARG;
+  if (relu_mask == 2) {
+    // the tensor itself was never stored (mg_bn_relu_pool3_forward): x is its 3x3 / stride-2 max-pooled form, the one source routes
+    // through the arg-max codes, and the ReLU mask of an element is the sign of the pooled value it was the arg-max of
+    MG_REQUIRE(ctx, n_src == 1 && src[0].mode == 3 && src[0].aux && bn_x, MG_ERR_INVALID_ARG, "combine: relu_mask 2 needs one arg-max-coded source and bn_x");
+    MG_REQUIRE(ctx, x->N == d->N && x->C == d->C && x->H == (d->H - 1) / 2 + 1 && x->W == (d->W - 1) / 2 + 1 && src[0].g.H == x->H && src[0].g.W == x->W
+               && bn_x->H == d->H && bn_x->W == d->W, MG_ERR_SHAPE, "combine: relu_mask 2 shapes");
+    MG_REQUIRE(ctx, ctx->dtype == MG_BF16 && bf16_combine(ctx, x, relu_mask, bn_x, n_src, src, d, bn_sums), MG_ERR_UNSUPPORTED, "combine: relu_mask 2 is a bf16 fast path");
+    MG_CHECK_LAUNCH(ctx);
+    return MG_OK;
+  }
   MG_REQUIRE(ctx, d->N == x->N && d->H == x->H && d->W == x->W && d->C == x->C, MG_ERR_SHAPE, "combine: d shape");
   for (int s = 0; s < n_src; ++s) {
     const mg_grid& g = src[s].g;

@@ -449,7 +449,7 @@ __global__ void __launch_bounds__(256, 2) combine_fast_kernel(const __grid_const
   for (int e = 0; e < 8; ++e) { sd[e] = 0.f; sdx[e] = 0.f; }
   constexpr bool any_pool = ((MODES & 3) == 1 && NS > 0) || (((MODES >> 2) & 3) == 1 && NS > 1) || (((MODES >> 4) & 3) == 1 && NS > 2) ||
                             (((MODES >> 6) & 3) == 1 && NS > 3);
-  const bool need_x = p.relu_mask != 0 || any_pool;
+  const bool need_x = p.relu_mask == 1 || any_pool;   // relu_mask == 2: x is the POOLED tensor of the single mode-3 source (stem)
   const bool has_sums = p.sums != nullptr;
 
   if (active)
@@ -517,6 +517,8 @@ __global__ void __launch_bounds__(256, 2) combine_fast_kernel(const __grid_const
             const size_t o = (size_t)(((uint32_t)n * (uint32_t)S.H + (uint32_t)oy) * (uint32_t)S.W + (uint32_t)ox);
             Gr[s][w] = __ldg(reinterpret_cast<const uint4*>(S.g + o * S.cp + S.c_off + c0));
             Cd[w] = __ldg(reinterpret_cast<const uint2*>(S.aux + o * S.cp + S.c_off + c0));
+            // the activation was never stored (mg_bn_relu_pool3_forward): its ReLU mask at an arg-max is the sign of the pooled value
+            if (p.relu_mask == 2) Xr[w] = __ldg(reinterpret_cast<const uint4*>(p.x + o * p.x_cp + c0));
           }
         }
       }
@@ -560,7 +562,12 @@ __global__ void __launch_bounds__(256, 2) combine_fast_kernel(const __grid_const
           for (int w = 0; w < 4; ++w) {
             const int wy = w >> 1, wx = w & 1;
             if (by + wy >= S.H || bx + wx >= S.W) continue;
-            const V8 g = unpack8(Gr[s][w]);
+            V8 g = unpack8(Gr[s][w]);
+            if (p.relu_mask == 2) {
+              const V8 pw = unpack8(Xr[w]);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) if (!(pw.v[e] > 0.f)) g.v[e] = 0.f;
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int dy = k >> 1, dx = k & 1;
@@ -581,7 +588,7 @@ __global__ void __launch_bounds__(256, 2) combine_fast_kernel(const __grid_const
           const V8 xk = unpack8(Xr[k]);
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
-            if (p.relu_mask && !(xk.v[e] > 0.f)) acc[k].v[e] = 0.f;
+            if (p.relu_mask == 1 && !(xk.v[e] > 0.f)) acc[k].v[e] = 0.f;
             if (c0 + e >= p.C) acc[k].v[e] = 0.f;
           }
           if (has_sums) {
@@ -710,6 +717,79 @@ __global__ void __launch_bounds__(256) pool3_bf16_kernel(const bf16* __restrict_
   }
 }
 
+// ---------------------------------------------------------------- stem: BN + ReLU + 3x3 / stride-2 max-pool in one pass ----------
+// SpatialBatchNormalization -> ReLU -> SpatialMaxPooling(3,3,2,2,1,1) of the ImageNet stem (models/ilsvrc/rnmg.lua:181-183) without
+// the full-resolution activation: one thread = one pooled pixel x 8 channels reads its 3x3 window of the raw conv output, applies
+// the (fused, apply_bn_prologue) BatchNorm affine and the ReLU, rounds to bf16 exactly where the two-pass form stores, and keeps
+// the first maximum + its tap code.  The activation is only ever consumed by the pool, and backward needs it only for the ReLU
+// mask AT the arg-max, where it equals the pooled value (combine: relu_mask = 2) -- so it never exists in HBM: per step 0.54 GB not
+// written and 1.1 GB not read back.
+__global__ void __launch_bounds__(256, 3) bn_relu_pool3_bf16_kernel(const __grid_constant__ ApplyP p, uint8_t* __restrict__ code, int Ho, int Wo) {
+  pdl_launch();
+  pdl_wait();
+  extern __shared__ float s_aff[];   // [2][z_cp]
+  apply_bn_prologue(p, s_aff);
+  __syncthreads();
+  const uint32_t V = (uint32_t)p.o_cp >> 3;
+  const uint32_t total = (uint32_t)p.N * Ho * Wo * V;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t q = fd_div(i, p.fd_v);
+    const uint32_t vc = i - q * V;
+    uint32_t t = fd_div(q, p.fd_wp);                 // fd_wp / fd_hp hold Wo / Ho here
+    const int ox = (int)(q - t * (uint32_t)Wo);
+    const uint32_t n = fd_div(t, p.fd_hp);
+    const int oy = (int)(t - n * (uint32_t)Ho);
+    const int c0 = (int)vc * 8;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sc[e] = s_aff[c0 + e]; sh[e] = s_aff[p.z_cp + c0 + e]; }
+    uint4 r[9];
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) {
+      const int y = min(max(2 * oy - 1 + tp / 3, 0), p.H - 1), x = min(max(2 * ox - 1 + tp % 3, 0), p.W - 1);
+      r[tp] = __ldg(reinterpret_cast<const uint4*>(p.z + (size_t)((n * (uint32_t)p.H + (uint32_t)y) * (uint32_t)p.W + (uint32_t)x) * p.z_cp + c0));
+    }
+    // arg-max on packed bf16 pairs (the kernel is issue bound: 9 taps x 8 channels per thread): strictly-greater keeps the FIRST
+    // maximum like the scalar pool (values are >= 0 after the ReLU, so the first valid tap always beats the -inf start)
+    __nv_bfloat162 best[4];
+    uint32_t bc[4];                 // two 16-bit tap codes per register
+    const __nv_bfloat162 ninf = __halves2bfloat162(__ushort_as_bfloat16((unsigned short)0xFF80), __ushort_as_bfloat16((unsigned short)0xFF80));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { best[j] = ninf; bc[j] = 0; }
+    const bool ragged = c0 + 8 > p.C;
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) {
+      const int y = 2 * oy - 1 + tp / 3, x = 2 * ox - 1 + tp % 3;
+      if (y < 0 || y >= p.H || x < 0 || x >= p.W) continue;
+      const V8 v = unpack8(r[tp]);
+      V8 a;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a.v[e] = fmaxf(fmaf(v.v[e], sc[e], sh[e]), 0.f);   // = mg_xform + ReLU
+      if (ragged) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) if (c0 + e >= p.C) a.v[e] = 0.f;                  // pad channels zero
+      }
+      const uint4 u = pack8(a);                                                        // what the apply pass would have stored
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      const uint32_t tp2 = (uint32_t)tp * 0x00010001u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat162 ab = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+        const uint32_t m = __hgt2_mask(ab, best[j]);                                   // 0xFFFF per half where ab > best
+        best[j] = __hmax2(best[j], ab);
+        bc[j] = (tp2 & m) | (bc[j] & ~m);
+      }
+    }
+    const size_t o = (size_t)((n * (uint32_t)Ho + (uint32_t)oy) * (uint32_t)Wo + (uint32_t)ox);
+    *reinterpret_cast<uint4*>(p.out + o * p.o_cp + c0) = make_uint4(*reinterpret_cast<uint32_t*>(&best[0]), *reinterpret_cast<uint32_t*>(&best[1]),
+                                                                     *reinterpret_cast<uint32_t*>(&best[2]), *reinterpret_cast<uint32_t*>(&best[3]));
+    uint2 cd;   // byte e = code of channel c0 + e: register j holds channels 2j (low half) and 2j + 1 (high half)
+    cd.x = (bc[0] & 0xFF) | ((bc[0] >> 16 & 0xFF) << 8) | ((bc[1] & 0xFF) << 16) | ((bc[1] >> 16 & 0xFF) << 24);
+    cd.y = (bc[2] & 0xFF) | ((bc[2] >> 16 & 0xFF) << 8) | ((bc[3] & 0xFF) << 16) | ((bc[3] >> 16 & 0xFF) << 24);
+    *reinterpret_cast<uint2*>(code + o * p.o_cp + c0) = cd;
+  }
+}
+
 // ---------------------------------------------------------------- image import / pyramid / plain pool ----------
 // NCHW fp32 (Torch boundary) -> NHWC bf16 with C <= 8: one thread per pixel, coalesced plane reads, one 16-byte store
 __global__ void __launch_bounds__(256) import_nchw_c8_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int C, int64_t HW, int64_t total) {
@@ -835,6 +915,7 @@ bool bf16_bn_stats(mg_ctx* ctx, const mg_grid* y, mg_sum* sums) {
 bool bf16_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid* bn_x, int n_src, const mg_grad_src* src, mg_grid* d,
                   mg_sum* sums) {
   if (x->Cp % 8 || d->Cp % 8 || d->Cp > 2048 || x->scale || x->Cp < d->Cp) return false;
+  if (relu_mask == 2 && !(n_src == 1 && src[0].mode == 3 && src[0].aux && bn_x)) return false;   // x = pooled tensor of the stem's mode-3 source
   if (sums && bn_x && bn_x->Cp < d->Cp) return false;
   CombP p;
   memset(&p, 0, sizeof(p));
@@ -850,14 +931,14 @@ bool bf16_combine(mg_ctx* ctx, const mg_grid* x, int relu_mask, const mg_grid* b
   const mg_grid* bx = bn_x ? bn_x : x;
   p.bnx = (const bf16*)bx->data; p.bn_cp = bx->Cp;
   p.relu_mask = relu_mask; p.d = (bf16*)d->data; p.d_cp = d->Cp; p.sums = sums;
-  p.N = x->N; p.H = x->H; p.W = x->W; p.C = x->C; p.Hb = (x->H + 1) / 2; p.Wb = (x->W + 1) / 2;
+  p.N = d->N; p.H = d->H; p.W = d->W; p.C = d->C; p.Hb = (d->H + 1) / 2; p.Wb = (d->W + 1) / 2;
   const int V = d->Cp / 8;
   const int64_t items = (int64_t)p.N * p.Hb * p.Wb * V;
   static int spec = -1;
   if (spec < 0) { const char* e = getenv("MGCONV_COMBINE_SPEC"); spec = e ? atoi(e) : 1; }
   static int fast_env = -1;   // batched-load form of the specialised kernels (MGCONV_COMBINE_FAST=0: the older form, for A/B timing)
   if (fast_env < 0) { const char* e = getenv("MGCONV_COMBINE_FAST"); fast_env = e ? atoi(e) : 1; }
-  bool fast = fast_env != 0 && (int64_t)p.N * p.H * p.W < ((int64_t)1 << 31);   // 32-bit pixel indices (of the finer source grids too)
+  bool fast = (fast_env != 0 || relu_mask == 2) && (int64_t)p.N * p.H * p.W < ((int64_t)1 << 31);   // 32-bit pixel indices (of the finer source grids too)
   for (int s = 0; s < n_src; ++s) fast = fast && (int64_t)src[s].g.N * src[s].g.H * src[s].g.W < ((int64_t)1 << 31);
   p.fd_wb = make_fastdiv((uint32_t)p.Wb); p.fd_hb = make_fastdiv((uint32_t)p.Hb);
   int code = 0;
@@ -910,6 +991,24 @@ bool bf16_pool3(mg_ctx* ctx, const mg_grid* in, mg_grid* out, uint8_t* code) {
   const int64_t total = (int64_t)in->N * out->H * out->W * (in->Cp / 8);
   pool3_bf16_kernel<<<grid_for(total), 256, 0, ctx->stream>>>((const bf16*)in->data, in->H, in->W, in->Cp, in->C, (bf16*)out->data, code,
                                                              out->H, out->W, in->N);
+  return true;
+}
+
+bool bf16_bn_relu_pool3(mg_ctx* ctx, const mg_grid* z, const mg_bn_fused* bn, mg_grid* out, uint8_t* code) {
+  if (z->Cp % 8 || out->Cp != z->Cp || z->Cp > 4096 || !z->scale || !z->shift || !code) return false;
+  const int64_t total = (int64_t)z->N * out->H * out->W * (z->Cp / 8);
+  if (total >= ((int64_t)1 << 31) || (int64_t)z->N * z->H * z->W >= ((int64_t)1 << 31)) return false;
+  ApplyP p;
+  memset(&p, 0, sizeof(p));
+  p.bn = 1; p.training = bn->training; p.sums = bn->sums; p.count = bn->count; p.gamma = bn->gamma; p.beta = bn->beta;
+  p.rmean = bn->running_mean; p.rvar = bn->running_var; p.eps = bn->eps; p.momentum = bn->momentum;
+  p.smean = bn->save_mean; p.sinvstd = bn->save_invstd; p.scale_out = const_cast<float*>(z->scale); p.shift_out = const_cast<float*>(z->shift);
+  p.inv_count = 1.0 / (double)bn->count; p.unbias = bn->count > 1 ? (double)bn->count / (double)(bn->count - 1) : 1.0;
+  p.z = (const bf16*)z->data; p.z_cp = z->Cp; p.out = (bf16*)out->data; p.o_cp = out->Cp;
+  p.N = z->N; p.H = z->H; p.W = z->W; p.C = z->C;
+  p.fd_v = make_fastdiv((uint32_t)(p.o_cp / 8)); p.fd_wp = make_fastdiv((uint32_t)out->W); p.fd_hp = make_fastdiv((uint32_t)out->H);
+  const unsigned grid = (unsigned)std::min<int64_t>(grid_for(total), (int64_t)6 * ctx->num_sms);
+  mg_launch_pdl(bn_relu_pool3_bf16_kernel, dim3(grid), dim3(256), 2 * z->Cp * sizeof(float), ctx->stream, p, code, out->H, out->W);
   return true;
 }
 

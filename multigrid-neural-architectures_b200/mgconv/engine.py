@@ -85,6 +85,7 @@ class Engine:
         self.plan = b
         self.input_ops = [o for o in b.ops if isinstance(o, ops.InputOp)]
         self.conv_ops = [o for o in b.ops if isinstance(o, ops.ConvOp)]
+        ops.fuse_stem_pool3(b.ops, self)
         for o in b.ops:
             o.setup_fwd(self)
         self._bwd_ready = False

@@ -108,6 +108,7 @@ SIGNATURES = {
     "mg_avgpool_forward": (_I, [_P, _G, C.c_int32, _G]),
     "mg_im2col": (_I, [_P, _G, C.c_int32, C.c_int32, C.c_int32, _G]),
     "mg_pool3s2_forward": (_I, [_P, _G, _G, _P]),
+    "mg_bn_relu_pool3_forward": (_I, [_P, _G, C.POINTER(mg_bn_fused), _G, _P]),
     "mg_global_avgpool_forward": (_I, [_P, _G, _G]),
     "mg_global_avgpool_backward": (_I, [_P, _G, _G]),
     "mg_upconv2x2_forward": (_I, [_P, _G, _P, _P, _G, _P]),

@@ -67,8 +67,11 @@ class Src:
 class Combine:
     """gradient of tensor t = sum of its registered sources (optionally x ReLU mask, + BN sums)"""
 
-    def __init__(self, E, t, relu_mask=False, bn_x=None, sums=None, private=False):
+    def __init__(self, E, t, relu_mask=False, bn_x=None, sums=None, private=False, pooled_mask=None):
+        """pooled_mask: t itself was never stored (stem: BN + ReLU + pool fused); its ReLU mask at an arg-max is the sign of
+        the pooled tensor given here (mg_grad_combine relu_mask = 2)"""
         self.E, self.t = E, t
+        self.pooled_mask = pooled_mask
         srcs = t.srcs
         if len(srcs) > MG_MAX_SRC:
             raise NotImplementedError(f"{t.name}: {len(srcs)} gradient sources > MG_MAX_SRC")
@@ -81,7 +84,7 @@ class Combine:
             return
         self.buf = E.alloc(t.shape())
         self.noop = len(srcs) == 0  # unused output (e.g. grids dropped by SelectTable(1)): gradient stays zero
-        self.x = t.grid()
+        self.x = t.grid() if pooled_mask is None else pooled_mask.grid()
         self.bn_x = bn_x.grid() if bn_x is not None else None
         self.arr = (mg_grad_src * max(1, len(srcs)))()
         for i, s in enumerate(srcs):
@@ -90,7 +93,7 @@ class Combine:
             self.arr[i].mode = s.mode
             self.arr[i].aux = None if s.aux is None else s.aux.data_ptr()
         self.n = len(srcs)
-        self.relu_mask = int(relu_mask)
+        self.relu_mask = int(relu_mask) if pooled_mask is None else 2
         self.sums = sums
         self.d = t.grid(self.buf)
 
@@ -101,7 +104,7 @@ class Combine:
         """(buffers read, buffers written) by run()"""
         if self.alias or self.noop:
             return [], []
-        r = _keys(self.t.buf, self.bn_x, *[sr.buf for sr in self.t.srcs], *[sr.aux for sr in self.t.srcs])
+        r = _keys(self.t.buf if self.pooled_mask is None else self.pooled_mask.buf, self.bn_x, *[sr.buf for sr in self.t.srcs], *[sr.aux for sr in self.t.srcs])
         return r, _keys(self.buf, self.sums)
 
     def run(self):
@@ -443,10 +446,12 @@ class ApplyOp(Op):
         conv.want_stats = bn is not None
         out.producer = self
         self.pooled = None
+        self.pool3 = None    # Pool3Op fused into this pass (fuse_stem_pool3): BN + ReLU + 3x3 / stride-2 max-pool, `out` never stored
 
     def setup_fwd(self, E):
         t, y = self.out, self.conv.y
-        t.buf = E.alloc(t.shape())
+        # fused with the stem's pool: the activation is never written -- a one-element stand-in keeps the mg_grid structs valid
+        t.buf = E.alloc(t.shape()) if self.pool3 is None else E.alloc((8,))
         self.og = t.grid()
         self.pg = None
         if self.pooled is not None:
@@ -480,6 +485,8 @@ class ApplyOp(Op):
     def io_fwd(self):
         r = _keys(self.conv.y.buf, self.conv.sums, None if self.res is None else self.res.buf)
         w = _keys(self.out.buf, None if self.pooled is None else self.pooled.buf)
+        if self.pool3 is not None:
+            w += _keys(self.pool3.out.buf, self.pool3.code)
         if self.bn is not None:
             w += _keys(self.scale, self.shift, self.mean, self.invstd)
         return r, w
@@ -500,6 +507,9 @@ class ApplyOp(Op):
         if bn is not None:
             if E.bn_sync and E.training and not synced:   # cross-replica statistics: sum (sum y, sum y^2) over the ranks
                 E.ctx.call("mg_allreduce_inline", ptr(self.conv.sums), self.conv.sums.numel(), 2)   # int64 limbs of mg_sum
+            if self.pool3 is not None:   # stem: + SpatialMaxPooling(3,3,2,2,1,1), arg-max codes for the backward routing
+                E.ctx.call("mg_bn_relu_pool3_forward", C.byref(self.zg), C.byref(self._bn_struct(E)), C.byref(self.pool3.go), ptr(self.pool3.code))
+                return
             # SpatialBatchNormalization finalisation + CAddTable + ReLU + pooled companion in one pass
             E.ctx.call("mg_bn_residual_forward", C.byref(self.zg), C.byref(self._bn_struct(E)), rg, int(self.relu), C.byref(self.og), pg)
         else:
@@ -510,7 +520,7 @@ class ApplyOp(Op):
         self.pc = plan_companion_grad(E, t, self.pooled)
         self.dsums = E.alloc_sums(2 * t.C, "bwd") if self.bn is not None else None
         self.comb = Combine(E, t, relu_mask=self.relu, bn_x=y if self.bn is not None else None, sums=self.dsums,
-                            private=self.bn is not None)
+                            private=self.bn is not None, pooled_mask=None if self.pool3 is None else self.pool3.out)
         D = self.comb.buf
         if self.res is not None and self.res.needs_grad:
             self.res.srcs.append(Src(D, t.H, t.W, t.C, t.Cp, 0, MG_SEG_SAME))
@@ -581,21 +591,25 @@ class Pool3Op(Op):
     def __init__(self, inp, out):
         self.inp, self.out = inp, out
         out.producer = self
+        self.fused = False   # run by the producing ApplyOp (fuse_stem_pool3)
 
     def setup_fwd(self, E):
         self.out.buf = E.alloc(self.out.shape())
         self.gi, self.go = self.inp.grid(), self.out.grid()
         # arg-max codes for the backward routing (1 byte / element), bf16 mode only
-        self.code = E.alloc(self.out.shape(), torch.uint8) if (E.dtype == ffi.MG_BF16 and self.inp.needs_grad) else None
+        self.code = E.alloc(self.out.shape(), torch.uint8) if (E.dtype == ffi.MG_BF16 and (self.inp.needs_grad or self.fused)) else None
 
     def io_fwd(self):
+        if self.fused:
+            return [], []
         return _keys(self.inp.buf), _keys(self.out.buf, self.code)
 
     def io_bwd(self):
         return self.comb.io() if self.comb is not None else ([], [])
 
     def fwd(self, E):
-        E.ctx.call("mg_pool3s2_forward", C.byref(self.gi), C.byref(self.go), ptr(self.code))
+        if not self.fused:
+            E.ctx.call("mg_pool3s2_forward", C.byref(self.gi), C.byref(self.go), ptr(self.code))
 
     def setup_bwd(self, E):
         t = self.out
@@ -607,6 +621,37 @@ class Pool3Op(Op):
     def bwd(self, E):
         if self.comb is not None:
             self.comb.run()
+
+
+def _tensor_refs(op):
+    """TSpec objects an op holds (attributes, lists, (tensor, mode) pairs)"""
+    out = []
+    def visit(v):
+        if isinstance(v, TSpec):
+            out.append(v)
+        elif isinstance(v, (list, tuple)):
+            for e in v:
+                visit(e)
+    for v in vars(op).values():
+        visit(v)
+    return out
+
+
+def fuse_stem_pool3(plan_ops, E):
+    """BN -> ReLU -> SpatialMaxPooling(3,3,2,2,1,1) (ilsvrc/rnmg.lua:181-183) as one pass when the activation has no other reader:
+    it is then never written (forward) nor read (backward).  bf16 contexts, training graphs (arg-max codes needed)."""
+    if E.dtype != ffi.MG_BF16 or os.environ.get("MGCONV_FUSE_POOL3", "1") == "0":
+        return
+    for P in [o for o in plan_ops if isinstance(o, Pool3Op)]:
+        A = P.inp.producer
+        if not (isinstance(A, ApplyOp) and A.bn is not None and A.relu and A.res is None and A.pooled is None and A.out is P.inp):
+            continue
+        if not P.inp.needs_grad or P.inp.pooled is not None:
+            continue
+        others = [o for o in plan_ops if o is not A and o is not P and any(t is P.inp for t in _tensor_refs(o))]
+        if others:
+            continue
+        A.pool3, P.fused = P, True
 
 
 class CatOp(Op):

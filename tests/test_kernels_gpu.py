@@ -868,6 +868,55 @@ def test_grad_combine_stem_pool3(ctx):
         assert max_rel(gd2.nchw(), O.maxpool_backward(g, idx, x.shape)) <= TOL[ctx.dtype]  # overlapping windows: sums round
 
 
+def test_stem_bn_relu_pool3_fused_equals_two_passes():
+    """mg_bn_relu_pool3_forward (BN + ReLU + SpatialMaxPooling(3,3,2,2,1,1) in one pass, ilsvrc/rnmg.lua:181-183; the activation is
+    never stored) == mg_bn_residual_forward + mg_pool3s2_forward bit for bit (pooled values, arg-max codes, BatchNorm state), and
+    mg_grad_combine with relu_mask = 2 (mask = sign of the pooled value at the arg-max) == the masked routing through the stored
+    activation, bit for bit, including the BatchNorm backward sums"""
+    ctx = ffi.Context(0, torch.cuda.current_stream().cuda_stream, ffi.MG_BF16)
+    for (N, Cc, H, W) in [(2, 20, 13, 12), (3, 64, 16, 16), (1, 5, 7, 9)]:
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = bf16_round(rnd(N, Cc, H, W) * 1.5 - 0.2)
+        gamma, beta = dev(rng.random(Cc) + 0.5), dev(rng.standard_normal(Cc) * 0.3)
+        g = rnd(N, Cc, Ho, Wo)
+        res = {}
+        for mode in ("two", "fused"):
+            rm, rv = dev(np.full(Cc, 0.25)), dev(np.full(Cc, 1.5))
+            gy = Grid(ffi.MG_BF16, N, Cc, H, W, y)
+            sums = new_sums(2 * Cc)
+            ctx.call("mg_bn_stats", C.byref(gy.g()), ptr(sums))
+            gy.scale, gy.shift = torch.zeros(gy.Cp, device="cuda"), torch.zeros(gy.Cp, device="cuda")
+            smean, sinv = torch.zeros(gy.Cp, device="cuda"), torch.zeros(gy.Cp, device="cuda")
+            f = ffi.mg_bn_fused()
+            f.sums, f.count, f.gamma, f.beta = sums.data_ptr(), N * H * W, gamma.data_ptr(), beta.data_ptr()
+            f.running_mean, f.running_var, f.eps, f.momentum, f.training = rm.data_ptr(), rv.data_ptr(), 1e-5, 0.1, 1
+            f.save_mean, f.save_invstd = smean.data_ptr(), sinv.data_ptr()
+            ga, gp = Grid(ffi.MG_BF16, N, Cc, H, W), Grid(ffi.MG_BF16, N, Cc, Ho, Wo)
+            code = torch.zeros((N, Ho, Wo, gp.Cp), dtype=torch.uint8, device="cuda")
+            if mode == "two":
+                ctx.call("mg_bn_residual_forward", C.byref(gy.g()), C.byref(f), None, 1, C.byref(ga.g()), None)
+                ctx.call("mg_pool3s2_forward", C.byref(ga.g()), C.byref(gp.g()), ptr(code))
+            else:
+                ctx.call("mg_bn_relu_pool3_forward", C.byref(gy.g()), C.byref(f), C.byref(gp.g()), ptr(code))
+            # backward: gradient of the pooled tensor routed back through the codes, ReLU mask, BatchNorm sums
+            gg, gd = Grid(ffi.MG_BF16, N, Cc, Ho, Wo, g), Grid(ffi.MG_BF16, N, Cc, H, W)
+            src = (mg_grad_src * 1)()
+            src[0].g, src[0].c_offset, src[0].mode, src[0].aux = gg.g(), 0, MG_SRC_POOL3, code.data_ptr()
+            dsums = new_sums(2 * Cc)
+            if mode == "two":
+                ctx.call("mg_grad_combine", C.byref(ga.g()), 1, C.byref(gy.g()), 1, src, C.byref(gd.g()), ptr(dsums))
+            else:
+                ctx.call("mg_grad_combine", C.byref(gp.g()), 2, C.byref(gy.g()), 1, src, C.byref(gd.g()), ptr(dsums))
+            torch.cuda.synchronize()
+            res[mode] = [gp.t.clone(), code[..., :Cc].clone(), gd.t.clone(), dsums.clone(), rm.clone(), rv.clone(), smean.clone(), sinv.clone(),
+                         gy.scale.clone(), gy.shift.clone()]
+        names = ["pooled", "codes", "D", "bn backward sums", "running_mean", "running_var", "save_mean", "save_invstd", "scale", "shift"]
+        for nm, a, b in zip(names, res["two"], res["fused"]):
+            assert torch.equal(a, b), (nm, (N, Cc, H, W), int((a != b).sum()), a.numel())
+        assert res["fused"][0].abs().sum() > 0 and res["fused"][2].abs().sum() > 0
+    ctx.close()
+
+
 # ---------------------------------------------------------------- head, criteria, optimiser
 def test_logsoftmax_nll_and_fused(ctx):
     N, Cc = 6, 37
