@@ -898,7 +898,9 @@ static int wgrad_halo(mg_ctx* ctx, const mg_conv_desc* d, const mg_grid* g, floa
     p.tiles_per_cta = (int)mg_cdiv(p.n_slot_tiles, sp);
     const int zp = (int)mg_cdiv(p.n_slot_tiles, p.tiles_per_cta);
     const int stage_p = p.halo_bytes + p.g_bytes;
-    int Sp = std::min(W_MAX_STAGES, (SMEM_WGRAD - 1024) / stage_p);
+    static int smem_cap = -1;   // (experiment) MGCONV_WGRAD_SMEM_KB: leave shared memory for co-resident CTAs of other lanes
+    if (smem_cap < 0) { const char* e = getenv("MGCONV_WGRAD_SMEM_KB"); smem_cap = e ? atoi(e) * 1024 : SMEM_WGRAD; }
+    int Sp = std::min(W_MAX_STAGES, (std::min(SMEM_WGRAD, smem_cap) - 1024) / stage_p);
     Sp = std::max(2, std::min(Sp, std::max(2, p.tiles_per_cta)));
     p.stages = Sp;
     rc = mg_ctx_workspace(ctx, (size_t)zp * plane * sizeof(float), &ws);

@@ -370,6 +370,10 @@ class ConvOp(Op):
         io_d = _merge(self.ycomb.io() if self.ycomb is not None else None,
                       (_keys(self.y.G), _keys(self.dcat)) if self.needs_dgrad else ([], []))
         io_w = (_keys(self.y.G, self.col, *[t.buf for t, _ in self.segs]), _keys(self.mod.gradWeight, self.mod.gradBias))
+        if self.needs_dgrad and os.environ.get("MGCONV_WGRAD_AFTER_DGRAD", "0") != "0":
+            # (experiment) start the weight gradient only when the layer's dgrad has finished: two tensor-bound kernels then do not
+            # share the SMs, and the weight gradient overlaps the HBM-bound passes of the next layer instead
+            io_w = (io_w[0] + _keys(self.dcat), io_w[1])
         return [(io_d, self.bwd_data, None), (io_w, self.bwd_weight, "background")]
 
 
