@@ -14,7 +14,7 @@ import torch
 from oracle import nn_ops as O
 from mgconv import ffi
 from mgconv.ffi import ptr, mg_grad_src, MG_SEG_SAME, MG_SEG_POOL, MG_SEG_UP, MG_SRC_POOL3
-from util import Grid, conv_desc, dev, rel_err, max_rel, bf16_round, TOL, TDT, new_sums, sums_value
+from util import Grid, conv_desc, dev, rel_err, max_rel, elem_rel, bf16_round, TOL, TDT, new_sums, sums_value
 
 pytestmark = pytest.mark.gpu
 DTYPES = [ffi.MG_F32, ffi.MG_BF16]
@@ -159,6 +159,7 @@ def test_mgconv_forward_dgrad_wgrad(ctx, case, impl):
     tol = TOL[ctx.dtype]
     y = gy.nchw()
     assert max_rel(y, y_ref) <= tol, max_rel(y, y_ref)
+    assert elem_rel(y, y_ref) <= tol, ("per-element", elem_rel(y, y_ref))
     assert not gy.pad_channels().any()
     # BatchNorm statistics accumulated by the conv
     cnt = N * H * H
@@ -178,6 +179,7 @@ def test_mgconv_forward_dgrad_wgrad(ctx, case, impl):
     dc = dcat.nchw()
     got = np.concatenate([dc[:, 0:cs[0]], dc[:, cps[0]:cps[0] + cs[1]], dc[:, cps[0] + cps[1]:cps[0] + cps[1] + cs[2]]], axis=1)
     assert max_rel(got, gcat_ref) <= tol, max_rel(got, gcat_ref)
+    assert elem_rel(got, gcat_ref) <= tol, ("per-element", elem_rel(got, gcat_ref))
     dw = torch.zeros_like(wd)
     db = torch.zeros_like(bd)
     tc0 = ctx.tc_launches()
@@ -186,6 +188,7 @@ def test_mgconv_forward_dgrad_wgrad(ctx, case, impl):
     assert ctx.tc_launches() - tc0 == (2 if impl == "auto" else 0), "wgrad must run on the tcgen05 kernel in auto/bf16 mode"
     torch.cuda.synchronize()
     assert max_rel(dw.cpu().numpy(), 1.5 * gw_ref) <= tol, max_rel(dw.cpu().numpy(), 1.5 * gw_ref)
+    assert elem_rel(dw.cpu().numpy(), 1.5 * gw_ref) <= tol, ("per-element", elem_rel(dw.cpu().numpy(), 1.5 * gw_ref))
     assert max_rel(db.cpu().numpy(), 1.5 * gb_ref) <= tol
     ctx.set_impl(ffi.MG_IMPL_AUTO)
 

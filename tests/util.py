@@ -79,6 +79,14 @@ def max_rel(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
+def elem_rel(a, b, floor_frac=0.02):
+    """per-ELEMENT relative error max |a - b| / max(|b|, floor), floor = floor_frac x the largest magnitude of the reference
+    (elements smaller than the floor are held to an absolute error of tol x floor): the north-star's `rel` read element-wise"""
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    floor = max(floor_frac * np.abs(b).max(), 1e-30)
+    return float((np.abs(a - b) / np.maximum(np.abs(b), floor)).max())
+
+
 def copy_params_from_oracle(omodel, model, bf16_weights=False):
     """oracle (torch.nn) parameters/buffers -> product modules, matched in construction order.
     bf16_weights: first round the oracle's conv / linear weights to bf16-representable values, so
